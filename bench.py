@@ -1,0 +1,412 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark of the B200 correlator engine.
+
+Workload (BASELINE.json configs[1]): 4-satellite E/P/L tracking over 1 s of 16.368 Msps 1-bit IF
+(1000 ms x 4 SV = 4000 integrate-and-dump cells, 3 arms each).  One "step" = one pass over that second.
+With N GPUs every rank tracks its own 4 satellites over the same second (satellites shard, no data-path
+collective): weak scaling, value = arm-samples of all ranks / max-over-ranks time.
+
+  value        arm-samples/s, signal + cell parameters already resident in HBM, device-timed (CUDA events)
+  e2e          same metric through the C ABI with HOST buffers: pinned signal upload + requests H2D +
+               results D2H inside the timed region
+  roofline     k_epl against the measured HBM peak (algorithmic bytes)
+  cpu_baseline the unmodified reference C (oracle/_ref) on this box's host cores, same cells
+  cold_acq     secondary metric: 32 SV x 21 bins x 10 ms x 2046 phases full-sky sweep (configs[2])
+
+`--impl reference` times the reference's own CPU path (oracle/_ref, else the oracle port) instead.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+import numpy as np
+
+REPO = Path(__file__).resolve().parent
+sys.path.insert(0, str(REPO))
+
+IF_HZ = 4092000
+MS_SAMPLES = 16368
+N_SV_PER_GPU = 4
+N_MS = 1000
+ARMS = 3
+ALL_PRNS = [5, 14, 20, 30, 1, 2, 3, 4, 6, 7, 8, 9, 10, 11, 12, 13, 15, 16, 17, 18, 19, 21, 22, 23, 24, 25, 26, 27, 28,
+            29, 31, 32]
+ACQ_SV, ACQ_BINS, ACQ_MS = 32, 21, 10
+
+
+# ----------------------------------------------------------------------------- workload
+def make_scene(rank: int, n_ms: int):
+    from stm32f4_sdr_gps_b200.signal_synth import config2_scene
+    prns = ALL_PRNS[rank * N_SV_PER_GPU:(rank + 1) * N_SV_PER_GPU]
+    return config2_scene(n_ms=n_ms, prns=prns, seed=0x5D120001 + rank)
+
+
+def cached_signal(tag: str, scene):
+    """Synthesis is pure numpy and takes seconds; cache per tag under the system temp dir."""
+    from stm32f4_sdr_gps_b200.signal_synth import synthesize
+    path = Path(tempfile.gettempdir()) / ("gpsb_bench_%s.npy" % tag)
+    if path.exists():
+        sig = np.load(path)
+        if sig.shape == (scene.n_ms, 2046):
+            for s in scene.sats:       # truth is filled by synthesize(); recreate the parts we need
+                scene.truth[s.prn] = {}
+            return sig
+    sig = synthesize(scene)
+    try:
+        np.save(path, sig)
+    except OSError:
+        pass
+    return sig
+
+
+def truth_requests(scene, nco_step32):
+    """Per-(ms, sv) cell parameters along the true trajectory of each satellite: what a locked tracking
+    loop feeds the correlator (tracking.c:115-130 offset arithmetic on the true code phase)."""
+    from stm32f4_sdr_gps_b200 import EPL_REQ
+    n_sv = len(scene.sats)
+    rq = np.zeros((scene.n_ms, n_sv), EPL_REQ)
+    fo = np.zeros((scene.n_ms, n_sv), np.float32)
+    fine_f = np.zeros((scene.n_ms, n_sv), np.float32)
+    for s, sat in enumerate(scene.sats):
+        step32 = nco_step32(np.float32(IF_HZ) + np.float32(sat.doppler_hz))
+        m = np.arange(scene.n_ms, dtype=np.float64)
+        tau = (sat.code_phase_samples - m * MS_SAMPLES * sat.doppler_hz / 1_575_420_000.0) % MS_SAMPLES
+        fine = np.floor(tau).astype(np.int64)
+        p = fine // 8
+        rq["sv_slot"][:, s] = s
+        rq["ms_index"][:, s] = np.arange(scene.n_ms)
+        rq["acc0"][:, s] = (np.arange(scene.n_ms, dtype=np.uint64) * 511 * step32) & 0xFFFFFFFF
+        rq["step32"][:, s] = step32
+        rq["off_p"][:, s] = p
+        rq["off_e"][:, s] = np.where(p == 0, 2045, p - 1)
+        rq["off_l"][:, s] = np.where(p + 1 >= 2046, 0, p + 1)
+        rq["off_bits"][:, s] = fine & 7
+        fo[:, s] = np.float32(sat.doppler_hz)
+        fine_f[:, s] = tau.astype(np.float32)
+    return rq.reshape(-1), fo.reshape(-1), fine_f.reshape(-1)
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.path = Path(tempfile.gettempdir()) / ("gpsb_clocks_%d_%d.csv" % (os.getpid(), gpu_index))
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.path.read_text().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        try:
+            self.path.unlink()
+        except OSError:
+            pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- reference arm (CPU)
+def _ref_worker(args):
+    """Closed-loop reference tracking of one satellite in its own process (reference globals are not
+    re-entrant)."""
+    prn, fo_hz, fine, sig_path, n_ms, reps = args
+    sys.path.insert(0, str(REPO / "tests"))
+    from oracle_lib import Reference
+    ref = Reference()
+    sig = np.load(sig_path)
+    chans = ref.channels(1)
+    ch = ref.channel_at(chans, 0)
+    lib = ref.lib
+    lib.ref_track_time.restype = __import__("ctypes").c_double
+    lib.ref_track_time.argtypes = [__import__("ctypes").c_void_p] * 2 + [__import__("ctypes").c_uint32] * 2
+    best = 1e30
+    for _ in range(reps):
+        ref.channel_init(ch, prn, 0)
+        st = ref.snapshot(ch)
+        # start locked (GPS_ACQ_DONE / GPS_TRACKING_RUN) on the true code phase and Doppler so that all n_ms
+        # steps are E/P/L integrate-and-dump steps, the same cells the GPU arm computes
+        st.acq_state, st.trk_state = 9, 4
+        st.found_freq_offset_hz = int(round(fo_hz / 500.0) * 500)
+        st.if_freq_offset_hz_bits = int(np.float32(fo_hz).view(np.uint32))
+        st.code_phase_fine_bits = int(np.float32(fine).view(np.uint32))
+        ref.restore(ch, st)
+        best = min(best, lib.ref_track_time(ch, sig.ctypes.data, 0, n_ms))
+    return best
+
+
+def reference_tracking_seconds(scene, sig, max_procs: int, reps: int = 3):
+    """Wall time for the reference C to track all satellites of the scene over the whole recording,
+    one process per satellite on up to max_procs cores.  Returns (seconds, cores_used, kind)."""
+    import multiprocessing as mp
+    sys.path.insert(0, str(REPO / "tests"))
+    from oracle_lib import have_reference
+    if not have_reference():
+        return None, 0, "port"
+    path = Path(tempfile.gettempdir()) / ("gpsb_ref_sig_%d.npy" % os.getpid())
+    np.save(path, sig)
+    jobs = [(s.prn, float(s.doppler_hz), float(s.code_phase_samples), str(path), scene.n_ms, reps) for s in scene.sats]
+    procs = max(1, min(max_procs, len(jobs)))
+    t0 = time.perf_counter()
+    if procs == 1:
+        per = [_ref_worker(j) for j in jobs]
+        wall = sum(per)
+    else:
+        with mp.get_context("fork").Pool(procs) as pool:
+            per = pool.map(_ref_worker, jobs)
+        # satellites run concurrently: the job takes as long as the slowest core's share
+        rounds = [per[i::procs] for i in range(procs)]
+        wall = max(sum(r) for r in rounds)
+    _ = time.perf_counter() - t0
+    path.unlink(missing_ok=True)
+    return wall, procs, "reference"
+
+
+def run_reference_arm(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_gpus = args.gpus
+    scenes = [make_scene(r, N_MS) for r in range(n_gpus)]
+    cores = os.cpu_count() or 1
+    times = []
+    used = 1
+    for w in range(args.warmup + args.steps):
+        t_step = 0.0
+        for r, sc in enumerate(scenes):
+            sig = cached_signal("trk_r%d_%d" % (r, N_MS), sc)
+            t, used, kind = reference_tracking_seconds(sc, sig, cores, reps=3)
+            if t is None:
+                print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libgpsref.so missing"}))
+                return
+            t_step += t
+        if w >= args.warmup:
+            times.append(t_step)
+    t = float(np.mean(times))
+    units = n_gpus * N_SV_PER_GPU * ARMS * MS_SAMPLES * N_MS
+    v = units / t
+    line = {
+        "impl": "reference", "metric": "correlator-samples/sec (E/P/L arms)", "value": v, "unit": "arm-samples/s",
+        "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 xor/popcount",
+        "data": "synthetic",
+        "config": {"workload": "config2: %d-SV E/P/L closed-loop tracking, 1 s @16.368 Msps 1-bit IF" % (n_gpus * N_SV_PER_GPU),
+                   "n_sv": n_gpus * N_SV_PER_GPU, "n_ms": N_MS},
+        "cpu_baseline": {"value": v, "unit": "arm-samples/s", "cores": used, "kind": "reference",
+                         "sample": "whole workload: unmodified reference gps_tracking_process() closed loop, one process per SV"},
+        "e2e": {"value": v, "unit": "arm-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- own arm (GPU)
+def run_gpu_arm(args) -> None:
+    import torch
+    import torch.distributed as dist
+
+    from stm32f4_sdr_gps_b200 import SEARCH_RES, Engine, nco_step32
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the engine has no CPU implementation")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    scene = make_scene(rank, N_MS)
+    sig = cached_signal("trk_r%d_%d" % (rank, N_MS), scene)
+    eng = Engine(device=local_rank, max_sv=max(ACQ_SV, N_SV_PER_GPU), ring_ms=N_MS + 24)
+    stream = torch.cuda.current_stream()
+    eng.set_stream(stream.cuda_stream)
+    for s, sat in enumerate(scene.sats):
+        eng.set_code_prn(s, sat.prn)
+    rq, fo, fine = truth_requests(scene, nco_step32)
+    n_cells = rq.size
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+
+    # ---- device-resident leg (value)
+    eng.upload_signal(0, sig)
+    d_rq = torch.from_numpy(rq.view(np.uint8).copy()).to(dev)
+    d_out = torch.zeros(n_cells * 6, dtype=torch.int16, device=dev)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for _ in range(max(3, args.warmup)):
+        eng.track_epl_dev(n_cells, d_rq.data_ptr(), d_out.data_ptr())
+    barrier()
+    clocks = ClockSampler(local_rank)
+    launches0 = eng.launch_count
+    for k in range(args.steps):
+        flush.fill_(k)                       # evict L2 between timed iterations (not timed)
+        ev[k][0].record(stream)
+        eng.track_epl_dev(n_cells, d_rq.data_ptr(), d_out.data_ptr())
+        ev[k][1].record(stream)
+    barrier()
+    dev_ms = [a.elapsed_time(b) for a, b in ev]
+    t_dev = float(np.sum(dev_ms)) / 1e3
+    kernel_ms = float(np.mean(dev_ms))
+    out_dev = d_out.cpu().numpy().reshape(n_cells, 6)
+
+    # ---- end-to-end leg through the C ABI with host buffers
+    pinned_sig = torch.from_numpy(sig.copy()).pin_memory()
+    e2e_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for _ in range(max(3, args.warmup)):
+        eng.upload_signal(0, pinned_sig.numpy())
+        out_host = eng.track_epl(rq)
+    barrier()
+    for k in range(args.steps):
+        flush.fill_(k)
+        e2e_ev[k][0].record(stream)
+        eng.upload_signal(0, pinned_sig.numpy())
+        out_host = eng.track_epl(rq)
+        e2e_ev[k][1].record(stream)
+    barrier()
+    launches = eng.launch_count - launches0
+    t_e2e = float(np.sum([a.elapsed_time(b) for a, b in e2e_ev])) / 1e3
+    assert np.array_equal(out_host, out_dev), "host-buffer and device-resident legs disagree"
+
+    # ---- cold acquisition (secondary metric, rank-sharded over SVs x bins)
+    from stm32f4_sdr_gps_b200.signal_synth import config3_scene
+    acq_scene = config3_scene(n_ms=ACQ_MS)
+    acq_sig = cached_signal("acq_%d" % ACQ_MS, acq_scene)
+    for prn in range(1, ACQ_SV + 1):
+        eng.set_code_prn(prn - 1, prn)
+    eng.upload_signal(N_MS, acq_sig)                    # frames N_MS .. N_MS+9 of the ring
+    step = np.array([nco_step32(np.float32(IF_HZ - 5000 + 500 * b)) for b in range(ACQ_BINS)], np.uint32)
+    my_sv = np.arange(ACQ_SV, dtype=np.uint32)[rank::world].copy()
+    d_sv = torch.from_numpy(my_sv.view(np.int32)).to(dev)
+    d_step = torch.from_numpy(step.view(np.int32)).to(dev)
+    n_acq_cells = my_sv.size * ACQ_BINS * ACQ_MS
+    d_res = torch.zeros(n_acq_cells * 4, dtype=torch.int16, device=dev)
+    acq_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for _ in range(3):
+        eng.sweep_dev(d_sv.data_ptr(), my_sv.size, d_step.data_ptr(), ACQ_BINS, N_MS, ACQ_MS, 0, d_res.data_ptr())
+    barrier()
+    for k in range(args.steps):
+        flush.fill_(k)
+        acq_ev[k][0].record(stream)
+        eng.sweep_dev(d_sv.data_ptr(), my_sv.size, d_step.data_ptr(), ACQ_BINS, N_MS, ACQ_MS, 0, d_res.data_ptr())
+        acq_ev[k][1].record(stream)
+    barrier()
+    acq_ms = float(np.mean([a.elapsed_time(b) for a, b in acq_ev]))
+    t0 = time.perf_counter()
+    res_host = eng.sweep(my_sv, step, N_MS, ACQ_MS, 0)
+    acq_e2e_ms = (time.perf_counter() - t0) * 1e3
+    clk = clocks.stop()
+
+    # ---- max over ranks
+    times = torch.tensor([t_dev, t_e2e, acq_ms, acq_e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+        # the final argmax gather of the sweep: every rank contributes its (sv-sharded) triples
+        gathered = [torch.zeros_like(d_res) for _ in range(world)]
+        dist.all_gather(gathered, d_res)
+    t_dev, t_e2e, acq_ms, acq_e2e_ms = [float(x) for x in times.cpu()]
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.loads((REPO / "MEASURED_PEAKS.json").read_text())
+        except (OSError, ValueError):
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        units_step = world * N_SV_PER_GPU * ARMS * MS_SAMPLES * N_MS
+        value = units_step * args.steps / t_dev
+        e2e = units_step * args.steps / t_e2e
+        # algorithmic bytes of one k_epl launch: signal once per ms, code once per SV,
+        # 24 B request + 12 B result per cell
+        alg_bytes = N_MS * 2046 + N_SV_PER_GPU * 128 + n_cells * (24 + 12)
+        achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+        # cold-acq: bit-MACs and the integer-pipe view
+        acq_bitmacs = ACQ_SV * ACQ_BINS * ACQ_MS * 2046 * 2 * 16368
+        acq_alg_bytes = ACQ_MS * 2046 + len(my_sv) * 128 + n_acq_cells * 8
+        cpu_t, cpu_cores, cpu_kind = reference_tracking_seconds(scene, sig, os.cpu_count() or 1, reps=3)
+        cpu = None
+        if cpu_t:
+            cpu = {"value": N_SV_PER_GPU * ARMS * MS_SAMPLES * N_MS / cpu_t, "unit": "arm-samples/s", "cores": cpu_cores,
+                   "kind": cpu_kind,
+                   "sample": "whole N=1 workload (4 SV x 1000 ms closed-loop gps_tracking_process), best of 3"}
+        line = {
+            "metric": "correlator-samples/sec (E/P/L arms)", "value": value, "unit": "arm-samples/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": t_dev * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32 xor/popcount", "data": "synthetic",
+            "config": {"workload": "config2: %d-SV E/P/L tracking, 1 s @16.368 Msps 1-bit IF (4 SV per GPU)" % (world * N_SV_PER_GPU),
+                       "n_sv": world * N_SV_PER_GPU, "n_ms": N_MS, "cells_per_step": world * n_cells,
+                       "l2": "flushed between timed iterations (256 MiB fill)", "parallelism": "sv-shard x%d" % world},
+            "e2e": {"value": e2e, "unit": "arm-samples/s", "h2d_bytes_per_step": int(sig.nbytes + rq.nbytes),
+                    "d2h_bytes_per_step": int(n_cells * 12)},
+            "gpu_launches": int(launches),
+            "clocks": clk,
+            "roofline": {"kernel": "k_epl", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak, "traffic": None,
+                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kernel_ms},
+            "cpu_baseline": cpu,
+            "cold_acq": {"metric": "full-sky 32-SV cold-acq ms", "value": acq_ms, "unit": "ms", "e2e_ms": acq_e2e_ms,
+                         "cells": ACQ_SV * ACQ_BINS * ACQ_MS, "phases": 2046, "bit_macs": acq_bitmacs,
+                         "bit_macs_per_s": acq_bitmacs / (acq_ms * 1e-3),
+                         "hbm_frac": acq_alg_bytes / (acq_ms * 1e-3) / 1e9 / hbm_peak},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    eng.close()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="gpsb", choices=["gpsb", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,183 @@
+/*
+ * gpsb.h - C ABI of the B200 correlator engine (libgpsb_cuda.so).
+ *
+ * This is the drop-in boundary for the reference's acquisition / E-P-L tracking hot path.  The
+ * reference (iliasam/STM32F4_SDR_GPS, Firmware/project_main, "PM/") has no FFI: its seam is the set of
+ * DSP primitives declared in PM/GPS/gps_misc.h:195-216 and called only from PM/GPS/acquisition.c and
+ * PM/GPS/tracking.c.  Every entry point below names the reference call sequence it replaces.
+ *
+ * Conventions
+ *   - plain C types only (pointers + sizes); no CUDA or torch types in any signature
+ *   - every function returns 0 on success and a negative gpsb_status on failure; the reason is
+ *     retrievable with gpsb_last_error() (thread-local).  Nothing aborts, nothing falls back to a CPU
+ *     implementation: without a usable sm_100 device every compute entry point fails with
+ *     GPSB_ERR_CUDA.
+ *   - host pointers are borrowed for the duration of the call; results are written to caller memory
+ *   - one context per GPU; calls on one context must be serialised by the caller
+ *
+ * Signal format (PM/signal_capture.c:9,169; PM/config.h:16,23-28): 1 bit per sample (sign of I),
+ * 16.368 Msps, packed LSB-first, 2046 bytes per millisecond.  Inside the context each millisecond
+ * occupies a 2048-byte frame (two zero pad bytes) so frames are 16-byte aligned in HBM.
+ */
+#ifndef GPSB_H
+#define GPSB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPSB_CHIPS          1023u   /* PRN_LENGTH          PM/config.h:28 */
+#define GPSB_MS_BYTES       2046u   /* PRN_SPI_WORDS_CNT*2 PM/config.h:27 */
+#define GPSB_MS_SAMPLES     16368u  /* BITS_IN_PRN         PM/config.h:26 */
+#define GPSB_FRAME_BYTES    2048u   /* device pitch of one millisecond    */
+#define GPSB_OFFSETS        2046u   /* half-chip code phases, PM/GPS/acquisition.c:294 */
+
+typedef enum gpsb_status {
+    GPSB_OK = 0,
+    GPSB_ERR_ARG = -1,     /* bad argument (null pointer, slot / offset out of range, ...) */
+    GPSB_ERR_CUDA = -2,    /* CUDA runtime error or no usable device */
+    GPSB_ERR_NOMEM = -3,   /* host or device allocation failed */
+    GPSB_ERR_STATE = -4    /* call sequence error (e.g. code not set for slot) */
+} gpsb_status;
+
+typedef struct gpsb_ctx gpsb_ctx;
+
+/* ---------------------------------------------------------------- life cycle ------------------ */
+/* device: CUDA ordinal.  max_sv: number of satellite slots (code tables).  ring_ms: capacity of the
+ * HBM signal ring in milliseconds (frame index = ms_index % ring_ms). */
+int gpsb_create(gpsb_ctx** out, int device, uint32_t max_sv, uint32_t ring_ms);
+void gpsb_destroy(gpsb_ctx* ctx);
+const char* gpsb_last_error(void);
+/* Library/version probe that never touches the GPU (used by the CPU-only test tier). */
+uint32_t gpsb_abi_version(void);
+/* Number of kernel launches issued by this context so far (bench.py's gpu_launches). */
+uint64_t gpsb_launch_count(const gpsb_ctx* ctx);
+/* Run all subsequent work of this context on an externally owned CUDA stream (cudaStream_t passed
+ * as void*, e.g. torch.cuda.current_stream().cuda_stream).  NULL restores the context's own stream. */
+int gpsb_set_stream(gpsb_ctx* ctx, void* cuda_stream);
+int gpsb_synchronize(gpsb_ctx* ctx);
+
+/* Device-side timers on the context's stream (CUDA events), so pure-C callers can time kernels the
+ * way bench.py does.  slot 0..7. */
+int gpsb_timer_start(gpsb_ctx* ctx, uint32_t slot);
+int gpsb_timer_stop(gpsb_ctx* ctx, uint32_t slot);
+int gpsb_timer_elapsed_ms(gpsb_ctx* ctx, uint32_t slot, float* ms); /* synchronises on the stop event */
+
+/* ---------------------------------------------------------------- resident data --------------- */
+/* Replaces gps_channell_prepare()'s product (PM/GPS/gps_misc.c:306-311): the 1023-chip C/A code of a
+ * satellite, one byte (0/1) per chip, becomes a device-resident expanded replica table. */
+int gpsb_set_code(gpsb_ctx* ctx, uint32_t sv_slot, const uint8_t chips[GPSB_CHIPS]);
+/* Device-side generator of the same table from the PRN number (PM/GPS/gps_misc.c:317-372). */
+int gpsb_set_code_prn(gpsb_ctx* ctx, uint32_t sv_slot, uint32_t prn);
+/* Read back the chips of a slot (for parity tests of the generator). */
+int gpsb_get_code(gpsb_ctx* ctx, uint32_t sv_slot, uint8_t chips[GPSB_CHIPS]);
+
+/* Replaces the SPI/DMA capture buffers (PM/signal_capture.c:57-123): copy n_ms milliseconds of packed
+ * samples (n_ms * 2046 bytes, contiguous) into ring frames ms0 .. ms0+n_ms-1.  Synchronous. */
+int gpsb_upload_signal(gpsb_ctx* ctx, uint32_t ms0, uint32_t n_ms, const uint8_t* packed);
+/* Same, but only enqueued on the context stream (packed must stay valid, ideally pinned). */
+int gpsb_upload_signal_async(gpsb_ctx* ctx, uint32_t ms0, uint32_t n_ms, const uint8_t* packed);
+/* Ingest adaptor for MAX2769-native 2-bit I / 2-bit Q sign-magnitude samples, one byte per sample
+ * (bit0 = I sign, bit1 = I mag, bit2 = Q sign, bit3 = Q mag): keeps the I sign bit and packs it
+ * LSB-first on the device (the reference front end wires only I1/sign, PM/config.h:16). */
+int gpsb_upload_signal_iq2(gpsb_ctx* ctx, uint32_t ms0, uint32_t n_ms, const uint8_t* samples);
+/* Copy ring frames back (2046 bytes per ms) - used by tests of the ingest path. */
+int gpsb_download_signal(gpsb_ctx* ctx, uint32_t ms0, uint32_t n_ms, uint8_t* packed);
+
+/* ---------------------------------------------------------------- level 1: fused cells -------- */
+/*
+ * One tracking integrate-and-dump = PM/GPS/tracking.c:115-138:
+ *   gps_generate_prn_data2(bits) + gps_shift_to_zero_freq_track(acc0, step32) +
+ *   3 x gps_correlation_iq(off_e | off_p | off_l).
+ * The NCO words are computed by the host with the reference's own fp32 expression
+ * (PM/GPS/gps_misc.c:250-253) so no float arithmetic is re-implemented on the device.
+ */
+typedef struct gpsb_epl_req {
+    uint32_t sv_slot;
+    uint32_t ms_index;
+    uint32_t acc0;      /* trk->if_freq_accum on entry                */
+    uint32_t step32;    /* (uint32_t)((uint64_t)acc_step * 32)         */
+    uint16_t off_e;     /* byte (half-chip) offsets, 0..2045           */
+    uint16_t off_p;
+    uint16_t off_l;
+    uint16_t off_bits;  /* sub-byte replica shift, 0..15               */
+} gpsb_epl_req;
+
+/* out[6*i .. 6*i+5] = IE,QE,IP,QP,IL,QL of request i (int16, popcount - 8184). Synchronous. */
+int gpsb_track_epl(gpsb_ctx* ctx, uint32_t n, const gpsb_epl_req* req, int16_t* out);
+
+/*
+ * One acquisition / pre-track cell = PM/GPS/acquisition.c:282-294 (freq search),
+ * :198-209 (code-phase search) and PM/GPS/tracking.c:403-426 (pre-track):
+ *   gps_generate_prn_data2(bits) + gps_shift_to_zero_freq(step32, phase 0) +
+ *   correlation_search(start, stop).
+ */
+typedef struct gpsb_search_req {
+    uint32_t sv_slot;
+    uint32_t ms_index;
+    uint32_t acc0;      /* 0 for the reference's stateless mixer       */
+    uint32_t step32;
+    uint16_t off_bits;
+    uint16_t start;     /* first offset, inclusive                      */
+    uint16_t stop;      /* last offset, exclusive, <= 2046              */
+    uint16_t flags;     /* reserved, 0                                  */
+} gpsb_search_req;
+
+typedef struct gpsb_search_res {
+    uint16_t max;       /* correlation_search() return value            */
+    uint16_t phase;     /* *phase: first offset holding the maximum     */
+    uint16_t avg;       /* *aver_val: sum / 2046                        */
+    uint16_t reserved;
+} gpsb_search_res;
+
+int gpsb_search(gpsb_ctx* ctx, uint32_t n, const gpsb_search_req* req, gpsb_search_res* res);
+
+/* Per-offset (I,Q) of one cell: iq[2*k], iq[2*k+1] for offset start+k (gps_correlation_iq over a
+ * window, PM/GPS/gps_misc.c:128-145). */
+int gpsb_search_iq(gpsb_ctx* ctx, const gpsb_search_req* req, int16_t* iq);
+
+/* Full-sky sweep: every (sv, bin, ms) cell with the full 2046-offset window, the cold-acquisition
+ * workload.  Cells are ordered (sv, bin, ms); step32[b] is the NCO word of bin b.  Results land in
+ * res[(sv*n_bins + b)*n_ms + m].  sv_slots[] lists the slots to search. */
+int gpsb_sweep(gpsb_ctx* ctx, const uint32_t* sv_slots, uint32_t n_sv, const uint32_t* step32,
+               uint32_t n_bins, uint32_t ms0, uint32_t n_ms, uint32_t off_bits,
+               gpsb_search_res* res);
+
+/* ---- device-resident variants: request / result arrays already in device memory, enqueued on the
+ *      context stream without synchronising.  Used for kernel-only timing and for results that are
+ *      gathered across GPUs (NCCL) before they are read. */
+int gpsb_track_epl_dev(gpsb_ctx* ctx, uint32_t n, const gpsb_epl_req* d_req, int16_t* d_out);
+int gpsb_search_dev(gpsb_ctx* ctx, uint32_t n, const gpsb_search_req* d_req, gpsb_search_res* d_res);
+int gpsb_sweep_dev(gpsb_ctx* ctx, const uint32_t* d_sv_slots, uint32_t n_sv, const uint32_t* d_step32,
+                   uint32_t n_bins, uint32_t ms0, uint32_t n_ms, uint32_t off_bits,
+                   gpsb_search_res* d_res);
+
+/* ---------------------------------------------------------------- level 0: the reference primitives
+ * Same arithmetic and argument meaning as PM/GPS/gps_misc.h:198-216 on caller-owned HOST buffers
+ * (each call round-trips through the device; meant for parity tests and for piecewise migration).
+ * Buffers follow the reference: prn/data arrays are 1023 little-endian uint16 words (2046 bytes). */
+/* gps_generate_prn_data2 (gps_misc.c:282-300); data receives 1023 words. */
+int gpsb_l0_generate_prn_data2(gpsb_ctx* ctx, const uint8_t chips[GPSB_CHIPS], uint16_t* data,
+                               uint16_t offset_bits);
+/* gps_shift_to_zero_freq / _track (gps_misc.c:211-274) with explicit NCO words; writes 2044 bytes to
+ * data_i and data_q (bytes 2044..2045 untouched, as in the reference); *acc_out = acc0 + 511*step32. */
+int gpsb_l0_shift_to_zero_freq(gpsb_ctx* ctx, const uint8_t* signal_data, uint8_t* data_i,
+                               uint8_t* data_q, uint32_t acc0, uint32_t step32, uint32_t* acc_out);
+/* gps_correlation_iq (gps_misc.c:128-145) */
+int gpsb_l0_correlation_iq(gpsb_ctx* ctx, const uint16_t* prn_p, const uint16_t* data_i,
+                           const uint16_t* data_q, uint16_t offset, int16_t* res_i, int16_t* res_q);
+/* gps_correlation8 (gps_misc.c:98-122) */
+int gpsb_l0_correlation8(gpsb_ctx* ctx, const uint16_t* prn_p, const uint16_t* data_i,
+                         const uint16_t* data_q, uint16_t offset, int16_t* res);
+/* correlation_search (gps_misc.c:155-191) */
+int gpsb_l0_correlation_search(gpsb_ctx* ctx, const uint16_t* prn_p, const uint16_t* data_i,
+                               const uint16_t* data_q, uint16_t start_shift, uint16_t stop_shift,
+                               uint16_t* aver_val, uint16_t* phase, uint16_t* max_val);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPSB_H */

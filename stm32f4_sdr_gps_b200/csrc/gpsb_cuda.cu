@@ -1,0 +1,853 @@
+/*
+ * gpsb_cuda.cu - kernels + C ABI of libgpsb_cuda.so (see include/gpsb.h).
+ *
+ * Kernels (all sm_100a, integer LOP3/SHF/POPC work on bit-packed samples):
+ *   k_expand_code   chips (1 byte each) -> 512-word expanded replica table      gps_misc.c:282-300
+ *   k_gen_code      C/A Gold code from the PRN number on the device            gps_misc.c:317-372
+ *   k_pack_iq2      ingest adaptor: byte-per-sample 2-bit I/Q -> packed I sign  signal_capture.c:9-16
+ *   k_epl           one tracking integrate-and-dump per CTA                     tracking.c:115-138
+ *   k_search        one acquisition / pre-track cell per CTA                    acquisition.c:282-294,
+ *                                                                               :198-209, tracking.c:403-426
+ *   k_l0_*          the bare reference primitives on explicit buffers           gps_misc.h:198-216
+ *
+ * There is deliberately no CPU implementation in this file: if CUDA is unavailable every compute
+ * entry point returns GPSB_ERR_CUDA.
+ */
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "gpsb_kernels.cuh"
+
+using namespace gpsb;
+
+/* ============================================================================ kernels ========= */
+
+// chips[1023] (0/1 bytes) -> E[512]; E[w] low half = chip 2w, high half = chip 2w+1 (0xFFFF each).
+__global__ void k_expand_code(const uint8_t* __restrict__ chips, uint32_t* __restrict__ E)
+{
+    for (int w = threadIdx.x; w < kWords; w += blockDim.x) {
+        uint32_t lo = chips[2 * w] ? 0x0000FFFFu : 0u;
+        uint32_t hi = (2 * w + 1 < (int)GPSB_CHIPS && chips[2 * w + 1]) ? 0xFFFF0000u : 0u;
+        E[w] = lo | hi;
+    }
+}
+
+// G2 delays per PRN (IS-GPS-200 code phase assignments as chip delays; reference table
+// gps_misc.c:319-341).
+__constant__ uint16_t c_g2_delay[210] = {
+    5, 6, 7, 8, 17, 18, 139, 140, 141, 251, 252, 254, 255, 256, 257, 258, 469, 470, 471, 472,
+    473, 474, 509, 512, 513, 514, 515, 516, 859, 860, 861, 862, 863, 950, 947, 948, 950, 67, 103,
+    91, 19, 679, 225, 625, 946, 638, 161, 1001, 554, 280, 710, 709, 775, 864, 558, 220, 397, 55,
+    898, 759, 367, 299, 1018, 729, 695, 780, 801, 788, 732, 34, 320, 327, 389, 407, 525, 405, 221,
+    761, 260, 326, 955, 653, 699, 422, 188, 438, 959, 539, 879, 677, 586, 153, 792, 814, 446, 264,
+    1015, 278, 536, 819, 156, 957, 159, 712, 885, 461, 248, 713, 126, 807, 279, 122, 197, 693, 632,
+    771, 467, 647, 203, 145, 175, 52, 21, 237, 235, 886, 657, 634, 762, 355, 1012, 176, 603, 130,
+    359, 595, 68, 386, 797, 456, 499, 883, 307, 127, 211, 121, 118, 163, 628, 853, 484, 289, 811,
+    202, 1021, 463, 568, 904, 670, 230, 911, 684, 309, 644, 932, 12, 314, 891, 212, 185, 675, 503,
+    150, 395, 345, 846, 798, 992, 357, 995, 877, 112, 144, 476, 193, 109, 445, 291, 87, 399, 292,
+    901, 339, 208, 711, 189, 263, 537, 663, 942, 173, 900, 30, 500, 935, 556, 373, 85, 652, 310};
+
+// One CTA: two 10-stage LFSRs run by thread 0 (1023 serial steps), then all threads combine
+// chip[i] = G1[i] ^ G2[(i - delay) mod 1023] and expand.
+__global__ void k_gen_code(uint32_t prn, uint8_t* __restrict__ chips_out, uint32_t* __restrict__ E)
+{
+    __shared__ uint8_t g1[GPSB_CHIPS], g2[GPSB_CHIPS], chip[GPSB_CHIPS + 1];
+    if (threadIdx.x == 0) {
+        uint32_t r1 = 0x3FFu, r2 = 0x3FFu;
+        for (int i = 0; i < (int)GPSB_CHIPS; i++) {
+            g1[i] = (r1 >> 9) & 1u;
+            g2[i] = (r2 >> 9) & 1u;
+            uint32_t f1 = ((r1 >> 2) ^ (r1 >> 9)) & 1u;
+            uint32_t f2 = ((r2 >> 1) ^ (r2 >> 2) ^ (r2 >> 5) ^ (r2 >> 7) ^ (r2 >> 8) ^ (r2 >> 9)) & 1u;
+            r1 = ((r1 << 1) | f1) & 0x3FFu;
+            r2 = ((r2 << 1) | f2) & 0x3FFu;
+        }
+    }
+    __syncthreads();
+    const int d = c_g2_delay[prn - 1];
+    for (int i = threadIdx.x; i <= (int)GPSB_CHIPS; i += blockDim.x) {
+        uint8_t c = 0;
+        if (i < (int)GPSB_CHIPS) {
+            c = g1[i] ^ g2[(i + GPSB_CHIPS - d) % GPSB_CHIPS];
+            chips_out[i] = c;
+        }
+        chip[i] = c;
+    }
+    __syncthreads();
+    for (int w = threadIdx.x; w < kWords; w += blockDim.x)
+        E[w] = (chip[2 * w] ? 0x0000FFFFu : 0u) | (chip[2 * w + 1] ? 0xFFFF0000u : 0u);
+}
+
+// E table -> chips (inverse of k_expand_code, for read-back).
+__global__ void k_unexpand_code(const uint32_t* __restrict__ E, uint8_t* __restrict__ chips)
+{
+    for (int k = threadIdx.x; k < (int)GPSB_CHIPS; k += blockDim.x)
+        chips[k] = (E[k >> 1] >> ((k & 1) * 16)) & 1u;
+}
+
+// Ingest adaptor: one byte per sample (bit0 = I sign) -> packed LSB-first frames.  Each thread builds
+// one 32-bit output word from 32 consecutive sample bytes (two 16-byte loads); a warp therefore reads
+// 1 KiB contiguous and writes 128 B contiguous.  HBM-bound: 8.125 bytes moved per output byte.
+__global__ void k_pack_iq2(const uint4* __restrict__ samples, uint32_t* __restrict__ frames,
+                           uint32_t frame0, uint32_t ring_ms, uint32_t n_ms)
+{
+    const uint32_t words_per_ms = kMixWords + 1;  // 512 words, the last one holds 16 samples + pad
+    uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t total = n_ms * words_per_ms;
+    for (; gid < total; gid += gridDim.x * blockDim.x) {
+        uint32_t m = gid / words_per_ms, w = gid % words_per_ms;
+        uint32_t nsamp = (w == words_per_ms - 1) ? 16u : 32u;
+        const uint4* src = samples + ((size_t)m * GPSB_MS_SAMPLES + (size_t)w * 32u) / 16u;
+        uint32_t out = 0;
+#pragma unroll
+        for (uint32_t q = 0; q < 2; q++) {
+            if (q * 16u < nsamp) {
+                uint4 v = __ldg(src + q);
+                uint32_t lanes[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    uint32_t x = lanes[j] & 0x01010101u;          // bit0 of each of 4 bytes
+                    x = (x | (x >> 7) | (x >> 14) | (x >> 21)) & 0xFu;  // gather to 4 bits
+                    out |= x << (q * 16u + j * 4u);
+                }
+            }
+        }
+        frames[(size_t)((frame0 + m) % ring_ms) * kWords + w] = out;
+    }
+}
+
+// ---------------------------------------------------------------------------------- tracking
+// One CTA (128 threads) per request.  Thread t owns replica words t, t+128, t+256, t+384 for all
+// three arms; sums are reduced with REDUX (warp) + a 4x6 shared-memory stage.
+__global__ void __launch_bounds__(kEplThreads)
+k_epl(const gpsb_epl_req* __restrict__ reqs, int16_t* __restrict__ out,
+      const uint32_t* __restrict__ codes, const uint32_t* __restrict__ signal, uint32_t ring_ms)
+{
+    __shared__ CellSmem s;
+    __shared__ int partial[kEplThreads / 32][6];
+    const int tid = threadIdx.x;
+    const gpsb_epl_req rq = reqs[blockIdx.x];
+
+    stage_replica(s.R, codes + (size_t)rq.sv_slot * kWords, rq.off_bits & 15u, tid, kEplThreads);
+    stage_mix(s.I, s.Q, signal + (size_t)(rq.ms_index % ring_ms) * kWords, rq.acc0, rq.step32, tid,
+              kEplThreads);
+    extend_period<kEplThreads>(s.I, s.Q, tid);
+
+    const uint32_t offs[3] = {rq.off_e, rq.off_p, rq.off_l};
+    int acc[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        const uint32_t off = offs[a];
+        const int x0 = (int)(off >> 2);
+        const uint32_t sh = (off & 3u) * 8u;
+#pragma unroll
+        for (int i = 0; i < kWords / kEplThreads; i++) {
+            const int W = tid + i * kEplThreads;
+            const uint32_t m = word_mask(W, off);
+            const uint32_t r = s.R[W];
+            uint32_t vi = __funnelshift_r(s.I[x0 + W], s.I[x0 + W + 1], sh);
+            uint32_t vq = __funnelshift_r(s.Q[x0 + W], s.Q[x0 + W + 1], sh);
+            acc[2 * a] += __popc((vi ^ r) & m);
+            acc[2 * a + 1] += __popc((vq ^ r) & m);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+        int v = __reduce_add_sync(0xFFFFFFFFu, acc[j]);
+        if ((tid & 31) == 0) partial[tid >> 5][j] = v;
+    }
+    __syncthreads();
+    if (tid < 6) {
+        int v = 0;
+#pragma unroll
+        for (int w = 0; w < kEplThreads / 32; w++) v += partial[w][tid];
+        out[(size_t)blockIdx.x * 6 + tid] = (int16_t)(v - kHalfSum);  // gps_misc.c:140-141
+    }
+}
+
+// ---------------------------------------------------------------------------------- search
+struct SweepParams {
+    const uint32_t* sv_slots;
+    const uint32_t* step32;
+    uint32_t n_bins, ms0, n_ms, off_bits;
+};
+
+// Block-wide (max key, sum) reduction; result valid in thread 0.
+__device__ __forceinline__ void block_reduce_search(uint32_t& key, int& total, uint32_t* sk, int* st)
+{
+    const int tid = threadIdx.x;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        uint32_t ok = __shfl_xor_sync(0xFFFFFFFFu, key, d);
+        key = ok > key ? ok : key;
+    }
+    total = __reduce_add_sync(0xFFFFFFFFu, total);
+    if ((tid & 31) == 0) {
+        sk[tid >> 5] = key;
+        st[tid >> 5] = total;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < kSearchThreads / 32; w++) {
+            key = sk[w] > key ? sk[w] : key;
+            total += st[w];
+        }
+    }
+}
+
+// Shared tail of the search kernels: sweep offsets [start, stop), emit the reference's triple.
+__device__ __forceinline__ void search_window(const CellSmem& s, uint32_t start, uint32_t stop,
+                                              gpsb_search_res* res, int16_t* iq, uint32_t* sk, int* st)
+{
+    const int tid = threadIdx.x;
+    uint32_t key = 0;  // (value << 16) | (0xFFFF - offset); 0 == "nothing above zero yet"
+    int total = 0;
+    for (uint32_t off = start + tid; off < stop; off += kSearchThreads) {
+        int si, sq;
+        corr_offset(s, off, si, sq);
+        if (iq) {
+            iq[2 * (off - start)] = (int16_t)(si - kHalfSum);
+            iq[2 * (off - start) + 1] = (int16_t)(sq - kHalfSum);
+        }
+        int c = detector(si, sq);
+        total += c;
+        if (c > 0) {  // strict '>' from 0: first (lowest) offset wins ties, gps_misc.c:170
+            uint32_t k = ((uint32_t)c << 16) | (0xFFFFu - off);
+            key = k > key ? k : key;
+        }
+    }
+    block_reduce_search(key, total, sk, st);
+    if (tid == 0 && res) {
+        gpsb_search_res r;
+        r.max = (uint16_t)(key >> 16);
+        r.phase = key ? (uint16_t)(0xFFFFu - (key & 0xFFFFu)) : 0;  // all-zero window -> phase 0
+        r.avg = (uint16_t)(total / (2 * (int)GPSB_CHIPS));           // always /2046, gps_misc.c:178
+        r.reserved = 0;
+        *res = r;
+    }
+}
+
+template <bool kSweep>
+__global__ void __launch_bounds__(kSearchThreads)
+k_search(const gpsb_search_req* __restrict__ reqs, SweepParams sp, gpsb_search_res* __restrict__ res,
+         int16_t* __restrict__ iq, const uint32_t* __restrict__ codes,
+         const uint32_t* __restrict__ signal, uint32_t ring_ms)
+{
+    __shared__ CellSmem s;
+    __shared__ uint32_t sk[kSearchThreads / 32];
+    __shared__ int st[kSearchThreads / 32];
+    const int tid = threadIdx.x;
+
+    gpsb_search_req rq;
+    if (kSweep) {  // cell index -> (sv, bin, ms)
+        uint32_t c = blockIdx.x;
+        uint32_t m = c % sp.n_ms;
+        uint32_t b = (c / sp.n_ms) % sp.n_bins;
+        uint32_t v = c / (sp.n_ms * sp.n_bins);
+        rq.sv_slot = sp.sv_slots[v];
+        rq.ms_index = sp.ms0 + m;
+        rq.acc0 = 0;
+        rq.step32 = sp.step32[b];
+        rq.off_bits = (uint16_t)sp.off_bits;
+        rq.start = 0;
+        rq.stop = GPSB_OFFSETS;
+        rq.flags = 0;
+    } else {
+        rq = reqs[blockIdx.x];
+    }
+
+    stage_replica(s.R, codes + (size_t)rq.sv_slot * kWords, rq.off_bits & 15u, tid, kSearchThreads);
+    stage_mix(s.I, s.Q, signal + (size_t)(rq.ms_index % ring_ms) * kWords, rq.acc0, rq.step32, tid,
+              kSearchThreads);
+    extend_period<kSearchThreads>(s.I, s.Q, tid);
+    search_window(s, rq.start, rq.stop, res + blockIdx.x, iq, sk, st);
+}
+
+// ---------------------------------------------------------------------------------- level 0
+__global__ void k_l0_replica(const uint32_t* __restrict__ E, uint32_t bits, uint32_t* __restrict__ out)
+{
+    for (int W = threadIdx.x; W < kWords; W += blockDim.x) out[W] = replica_word(E, W, bits & 15u);
+}
+
+__global__ void k_l0_mix(const uint32_t* __restrict__ frame, uint32_t acc0, uint32_t step32,
+                         uint32_t* __restrict__ out_i, uint32_t* __restrict__ out_q)
+{
+    for (int w = threadIdx.x; w < kMixWords; w += blockDim.x) {
+        uint32_t sgn = frame[w];
+        uint32_t ph = (acc0 + (uint32_t)w * step32) >> 30;
+        out_i[w] = cos_pattern(ph) ^ sgn;
+        out_q[w] = sin_pattern(ph) ^ sgn;
+    }
+}
+
+// Explicit-buffer search: prn / data_i / data_q are 512-word device copies of the caller's 2046-byte
+// arrays (last two bytes zero-padded).  Bytes 2044..2045 of the data are honoured as given.
+__global__ void __launch_bounds__(kSearchThreads)
+k_l0_search(const uint32_t* __restrict__ prn, const uint32_t* __restrict__ data_i,
+            const uint32_t* __restrict__ data_q, uint32_t start, uint32_t stop,
+            gpsb_search_res* __restrict__ res, int16_t* __restrict__ iq)
+{
+    __shared__ CellSmem s;
+    __shared__ uint32_t sk[kSearchThreads / 32];
+    __shared__ int st[kSearchThreads / 32];
+    const int tid = threadIdx.x;
+    for (int w = tid; w < kWords; w += kSearchThreads) {
+        s.R[w] = prn[w];
+        s.I[w] = data_i[w];
+        s.Q[w] = data_q[w];
+    }
+    extend_period<kSearchThreads>(s.I, s.Q, tid);
+    search_window(s, start, stop, res, iq, sk, st);
+}
+
+/* ============================================================================ host side ======= */
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(GPSB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                                  \
+    } while (0)
+
+struct gpsb_ctx {
+    int device = 0;
+    uint32_t max_sv = 0, ring_ms = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    uint32_t* d_codes = nullptr;   // max_sv x 512 words
+    uint8_t* d_code_set = nullptr; // not used on device; host mirror below
+    uint8_t* code_set = nullptr;   // host: slot has a code
+    uint32_t* d_signal = nullptr;  // ring_ms x 512 words
+    // staging (grown on demand)
+    void* h_stage = nullptr;       // pinned
+    void* d_stage = nullptr;
+    size_t stage_cap = 0;
+    uint8_t* d_chips = nullptr;    // 1024 B scratch
+    uint32_t* d_l0 = nullptr;      // 4 x 512 words scratch for level-0 calls
+    cudaEvent_t ev_start[8] = {}, ev_stop[8] = {};
+    uint64_t launches = 0;
+};
+
+static int ensure_stage(gpsb_ctx* c, size_t bytes)
+{
+    if (bytes <= c->stage_cap) return GPSB_OK;
+    size_t cap = c->stage_cap ? c->stage_cap : (1u << 16);
+    while (cap < bytes) cap *= 2;
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->d_stage) cudaFree(c->d_stage);
+    c->h_stage = nullptr;
+    c->d_stage = nullptr;
+    c->stage_cap = 0;
+    CU(cudaMallocHost(&c->h_stage, cap));
+    CU(cudaMalloc(&c->d_stage, cap));
+    c->stage_cap = cap;
+    return GPSB_OK;
+}
+
+static int check_launch(gpsb_ctx* c, const char* what)
+{
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(GPSB_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+    c->launches++;
+    return GPSB_OK;
+}
+
+extern "C" {
+
+uint32_t gpsb_abi_version(void) { return 1u; }
+const char* gpsb_last_error(void) { return g_err; }
+uint64_t gpsb_launch_count(const gpsb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int gpsb_create(gpsb_ctx** out, int device, uint32_t max_sv, uint32_t ring_ms)
+{
+    if (!out || max_sv == 0 || ring_ms == 0) return fail(GPSB_ERR_ARG, "gpsb_create: bad argument");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(GPSB_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(GPSB_ERR_ARG, "device %d out of range (%d devices)", device, ndev);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(GPSB_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                    prop.major, prop.minor);
+    gpsb_ctx* c = new (std::nothrow) gpsb_ctx();
+    if (!c) return fail(GPSB_ERR_NOMEM, "out of host memory");
+    c->device = device;
+    c->max_sv = max_sv;
+    c->ring_ms = ring_ms;
+    c->code_set = (uint8_t*)calloc(max_sv, 1);
+    if (!c->code_set) { delete c; return fail(GPSB_ERR_NOMEM, "out of host memory"); }
+    *out = c;  // from here on gpsb_destroy can clean up partial state
+    CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    CU(cudaMalloc(&c->d_codes, (size_t)max_sv * kWords * 4));
+    CU(cudaMemset(c->d_codes, 0, (size_t)max_sv * kWords * 4));
+    CU(cudaMalloc(&c->d_signal, (size_t)ring_ms * GPSB_FRAME_BYTES));
+    CU(cudaMemset(c->d_signal, 0, (size_t)ring_ms * GPSB_FRAME_BYTES));
+    CU(cudaMalloc(&c->d_chips, 1024));
+    CU(cudaMalloc(&c->d_l0, 4 * kWords * 4 + 64));
+    for (int i = 0; i < 8; i++) {
+        CU(cudaEventCreate(&c->ev_start[i]));
+        CU(cudaEventCreate(&c->ev_stop[i]));
+    }
+    int rc = ensure_stage(c, 1u << 16);
+    if (rc) return rc;
+    CU(cudaDeviceSynchronize());
+    return GPSB_OK;
+}
+
+void gpsb_destroy(gpsb_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (int i = 0; i < 8; i++) {
+        if (c->ev_start[i]) cudaEventDestroy(c->ev_start[i]);
+        if (c->ev_stop[i]) cudaEventDestroy(c->ev_stop[i]);
+    }
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->d_stage) cudaFree(c->d_stage);
+    if (c->d_codes) cudaFree(c->d_codes);
+    if (c->d_signal) cudaFree(c->d_signal);
+    if (c->d_chips) cudaFree(c->d_chips);
+    if (c->d_l0) cudaFree(c->d_l0);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    free(c->code_set);
+    delete c;
+}
+
+int gpsb_set_stream(gpsb_ctx* c, void* cuda_stream)
+{
+    if (!c) return fail(GPSB_ERR_ARG, "null context");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    return GPSB_OK;
+}
+
+int gpsb_synchronize(gpsb_ctx* c)
+{
+    if (!c) return fail(GPSB_ERR_ARG, "null context");
+    CU(cudaStreamSynchronize(c->stream));
+    return GPSB_OK;
+}
+
+int gpsb_timer_start(gpsb_ctx* c, uint32_t slot)
+{
+    if (!c || slot >= 8) return fail(GPSB_ERR_ARG, "bad timer slot");
+    CU(cudaEventRecord(c->ev_start[slot], c->stream));
+    return GPSB_OK;
+}
+int gpsb_timer_stop(gpsb_ctx* c, uint32_t slot)
+{
+    if (!c || slot >= 8) return fail(GPSB_ERR_ARG, "bad timer slot");
+    CU(cudaEventRecord(c->ev_stop[slot], c->stream));
+    return GPSB_OK;
+}
+int gpsb_timer_elapsed_ms(gpsb_ctx* c, uint32_t slot, float* ms)
+{
+    if (!c || slot >= 8 || !ms) return fail(GPSB_ERR_ARG, "bad timer slot");
+    CU(cudaEventSynchronize(c->ev_stop[slot]));
+    CU(cudaEventElapsedTime(ms, c->ev_start[slot], c->ev_stop[slot]));
+    return GPSB_OK;
+}
+
+/* ------------------------------------------------------------------ resident data */
+int gpsb_set_code(gpsb_ctx* c, uint32_t slot, const uint8_t chips[GPSB_CHIPS])
+{
+    if (!c || !chips) return fail(GPSB_ERR_ARG, "gpsb_set_code: null argument");
+    if (slot >= c->max_sv) return fail(GPSB_ERR_ARG, "sv_slot %u out of range (max_sv %u)", slot, c->max_sv);
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(c->d_chips, chips, GPSB_CHIPS, cudaMemcpyHostToDevice, c->stream));
+    k_expand_code<<<1, 256, 0, c->stream>>>(c->d_chips, c->d_codes + (size_t)slot * kWords);
+    int rc = check_launch(c, "k_expand_code");
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(c->stream));
+    c->code_set[slot] = 1;
+    return GPSB_OK;
+}
+
+int gpsb_set_code_prn(gpsb_ctx* c, uint32_t slot, uint32_t prn)
+{
+    if (!c) return fail(GPSB_ERR_ARG, "null context");
+    if (slot >= c->max_sv) return fail(GPSB_ERR_ARG, "sv_slot %u out of range (max_sv %u)", slot, c->max_sv);
+    if (prn < 1 || prn > 210) return fail(GPSB_ERR_ARG, "prn %u out of range 1..210", prn);
+    CU(cudaSetDevice(c->device));
+    k_gen_code<<<1, 256, 0, c->stream>>>(prn, c->d_chips, c->d_codes + (size_t)slot * kWords);
+    int rc = check_launch(c, "k_gen_code");
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(c->stream));
+    c->code_set[slot] = 1;
+    return GPSB_OK;
+}
+
+int gpsb_get_code(gpsb_ctx* c, uint32_t slot, uint8_t chips[GPSB_CHIPS])
+{
+    if (!c || !chips) return fail(GPSB_ERR_ARG, "gpsb_get_code: null argument");
+    if (slot >= c->max_sv) return fail(GPSB_ERR_ARG, "sv_slot %u out of range", slot);
+    if (!c->code_set[slot]) return fail(GPSB_ERR_STATE, "no code set for slot %u", slot);
+    CU(cudaSetDevice(c->device));
+    k_unexpand_code<<<1, 256, 0, c->stream>>>(c->d_codes + (size_t)slot * kWords, c->d_chips);
+    int rc = check_launch(c, "k_unexpand_code");
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(chips, c->d_chips, GPSB_CHIPS, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return GPSB_OK;
+}
+
+static int upload_impl(gpsb_ctx* c, uint32_t ms0, uint32_t n_ms, const uint8_t* packed, bool sync)
+{
+    if (!c || !packed) return fail(GPSB_ERR_ARG, "gpsb_upload_signal: null argument");
+    if (n_ms == 0) return GPSB_OK;
+    if (n_ms > c->ring_ms) return fail(GPSB_ERR_ARG, "n_ms %u exceeds ring capacity %u", n_ms, c->ring_ms);
+    CU(cudaSetDevice(c->device));
+    uint32_t f0 = ms0 % c->ring_ms;
+    uint32_t first = (f0 + n_ms <= c->ring_ms) ? n_ms : c->ring_ms - f0;
+    // 2046-byte host rows -> 2048-byte device frames; the two pad bytes stay zero from creation.
+    CU(cudaMemcpy2DAsync((uint8_t*)c->d_signal + (size_t)f0 * GPSB_FRAME_BYTES, GPSB_FRAME_BYTES, packed,
+                         GPSB_MS_BYTES, GPSB_MS_BYTES, first, cudaMemcpyHostToDevice, c->stream));
+    if (first < n_ms)
+        CU(cudaMemcpy2DAsync((uint8_t*)c->d_signal, GPSB_FRAME_BYTES, packed + (size_t)first * GPSB_MS_BYTES,
+                             GPSB_MS_BYTES, GPSB_MS_BYTES, n_ms - first, cudaMemcpyHostToDevice, c->stream));
+    if (sync) CU(cudaStreamSynchronize(c->stream));
+    return GPSB_OK;
+}
+
+int gpsb_upload_signal(gpsb_ctx* c, uint32_t ms0, uint32_t n_ms, const uint8_t* packed)
+{
+    return upload_impl(c, ms0, n_ms, packed, true);
+}
+int gpsb_upload_signal_async(gpsb_ctx* c, uint32_t ms0, uint32_t n_ms, const uint8_t* packed)
+{
+    return upload_impl(c, ms0, n_ms, packed, false);
+}
+
+int gpsb_upload_signal_iq2(gpsb_ctx* c, uint32_t ms0, uint32_t n_ms, const uint8_t* samples)
+{
+    if (!c || !samples) return fail(GPSB_ERR_ARG, "gpsb_upload_signal_iq2: null argument");
+    if (n_ms == 0) return GPSB_OK;
+    if (n_ms > c->ring_ms) return fail(GPSB_ERR_ARG, "n_ms %u exceeds ring capacity %u", n_ms, c->ring_ms);
+    CU(cudaSetDevice(c->device));
+    const uint32_t chunk_ms = 256;  // 4 MiB of samples per staging pass
+    int rc = ensure_stage(c, (size_t)chunk_ms * GPSB_MS_SAMPLES + 64);
+    if (rc) return rc;
+    for (uint32_t done = 0; done < n_ms; done += chunk_ms) {
+        uint32_t n = (n_ms - done < chunk_ms) ? n_ms - done : chunk_ms;
+        CU(cudaMemcpyAsync(c->d_stage, samples + (size_t)done * GPSB_MS_SAMPLES, (size_t)n * GPSB_MS_SAMPLES,
+                           cudaMemcpyHostToDevice, c->stream));
+        uint32_t total = n * kWords;
+        k_pack_iq2<<<(total + 255) / 256, 256, 0, c->stream>>>((const uint4*)c->d_stage, c->d_signal,
+                                                               (ms0 + done) % c->ring_ms, c->ring_ms, n);
+        rc = check_launch(c, "k_pack_iq2");
+        if (rc) return rc;
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    return GPSB_OK;
+}
+
+int gpsb_download_signal(gpsb_ctx* c, uint32_t ms0, uint32_t n_ms, uint8_t* packed)
+{
+    if (!c || !packed) return fail(GPSB_ERR_ARG, "gpsb_download_signal: null argument");
+    if (n_ms > c->ring_ms) return fail(GPSB_ERR_ARG, "n_ms %u exceeds ring capacity %u", n_ms, c->ring_ms);
+    CU(cudaSetDevice(c->device));
+    for (uint32_t m = 0; m < n_ms; m++) {
+        uint32_t f = (ms0 + m) % c->ring_ms;
+        CU(cudaMemcpyAsync(packed + (size_t)m * GPSB_MS_BYTES, (uint8_t*)c->d_signal + (size_t)f * GPSB_FRAME_BYTES,
+                           GPSB_MS_BYTES, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    return GPSB_OK;
+}
+
+/* ------------------------------------------------------------------ request validation */
+static int check_epl(const gpsb_ctx* c, uint32_t n, const gpsb_epl_req* rq)
+{
+    for (uint32_t i = 0; i < n; i++) {
+        if (rq[i].sv_slot >= c->max_sv) return fail(GPSB_ERR_ARG, "request %u: sv_slot %u out of range", i, rq[i].sv_slot);
+        if (!c->code_set[rq[i].sv_slot]) return fail(GPSB_ERR_STATE, "request %u: no code set for slot %u", i, rq[i].sv_slot);
+        if (rq[i].off_e >= GPSB_OFFSETS || rq[i].off_p >= GPSB_OFFSETS || rq[i].off_l >= GPSB_OFFSETS)
+            return fail(GPSB_ERR_ARG, "request %u: byte offset out of range 0..2045", i);
+        if (rq[i].off_bits > 15) return fail(GPSB_ERR_ARG, "request %u: off_bits %u > 15", i, rq[i].off_bits);
+    }
+    return GPSB_OK;
+}
+
+static int check_search(const gpsb_ctx* c, uint32_t n, const gpsb_search_req* rq)
+{
+    for (uint32_t i = 0; i < n; i++) {
+        if (rq[i].sv_slot >= c->max_sv) return fail(GPSB_ERR_ARG, "request %u: sv_slot %u out of range", i, rq[i].sv_slot);
+        if (!c->code_set[rq[i].sv_slot]) return fail(GPSB_ERR_STATE, "request %u: no code set for slot %u", i, rq[i].sv_slot);
+        if (rq[i].stop > GPSB_OFFSETS) return fail(GPSB_ERR_ARG, "request %u: stop %u > 2046", i, rq[i].stop);
+        if (rq[i].off_bits > 15) return fail(GPSB_ERR_ARG, "request %u: off_bits %u > 15", i, rq[i].off_bits);
+    }
+    return GPSB_OK;
+}
+
+/* ------------------------------------------------------------------ level 1 */
+int gpsb_track_epl_dev(gpsb_ctx* c, uint32_t n, const gpsb_epl_req* d_req, int16_t* d_out)
+{
+    if (!c || !d_req || !d_out) return fail(GPSB_ERR_ARG, "gpsb_track_epl_dev: null argument");
+    if (n == 0) return GPSB_OK;
+    CU(cudaSetDevice(c->device));
+    k_epl<<<n, kEplThreads, 0, c->stream>>>(d_req, d_out, c->d_codes, c->d_signal, c->ring_ms);
+    return check_launch(c, "k_epl");
+}
+
+int gpsb_track_epl(gpsb_ctx* c, uint32_t n, const gpsb_epl_req* req, int16_t* out)
+{
+    if (!c || !req || !out) return fail(GPSB_ERR_ARG, "gpsb_track_epl: null argument");
+    if (n == 0) return GPSB_OK;
+    int rc = check_epl(c, n, req);
+    if (rc) return rc;
+    CU(cudaSetDevice(c->device));
+    size_t req_b = (size_t)n * sizeof(gpsb_epl_req), out_b = (size_t)n * 12;
+    size_t out_off = (req_b + 255) & ~(size_t)255;
+    rc = ensure_stage(c, out_off + out_b);
+    if (rc) return rc;
+    memcpy(c->h_stage, req, req_b);
+    CU(cudaMemcpyAsync(c->d_stage, c->h_stage, req_b, cudaMemcpyHostToDevice, c->stream));
+    rc = gpsb_track_epl_dev(c, n, (const gpsb_epl_req*)c->d_stage, (int16_t*)((uint8_t*)c->d_stage + out_off));
+    if (rc) return rc;
+    CU(cudaMemcpyAsync((uint8_t*)c->h_stage + out_off, (uint8_t*)c->d_stage + out_off, out_b,
+                       cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    memcpy(out, (uint8_t*)c->h_stage + out_off, out_b);
+    return GPSB_OK;
+}
+
+int gpsb_search_dev(gpsb_ctx* c, uint32_t n, const gpsb_search_req* d_req, gpsb_search_res* d_res)
+{
+    if (!c || !d_req || !d_res) return fail(GPSB_ERR_ARG, "gpsb_search_dev: null argument");
+    if (n == 0) return GPSB_OK;
+    CU(cudaSetDevice(c->device));
+    SweepParams sp = {};
+    k_search<false><<<n, kSearchThreads, 0, c->stream>>>(d_req, sp, d_res, nullptr, c->d_codes, c->d_signal,
+                                                         c->ring_ms);
+    return check_launch(c, "k_search");
+}
+
+int gpsb_search(gpsb_ctx* c, uint32_t n, const gpsb_search_req* req, gpsb_search_res* res)
+{
+    if (!c || !req || !res) return fail(GPSB_ERR_ARG, "gpsb_search: null argument");
+    if (n == 0) return GPSB_OK;
+    int rc = check_search(c, n, req);
+    if (rc) return rc;
+    CU(cudaSetDevice(c->device));
+    size_t req_b = (size_t)n * sizeof(gpsb_search_req), res_b = (size_t)n * sizeof(gpsb_search_res);
+    size_t res_off = (req_b + 255) & ~(size_t)255;
+    rc = ensure_stage(c, res_off + res_b);
+    if (rc) return rc;
+    memcpy(c->h_stage, req, req_b);
+    CU(cudaMemcpyAsync(c->d_stage, c->h_stage, req_b, cudaMemcpyHostToDevice, c->stream));
+    rc = gpsb_search_dev(c, n, (const gpsb_search_req*)c->d_stage,
+                         (gpsb_search_res*)((uint8_t*)c->d_stage + res_off));
+    if (rc) return rc;
+    CU(cudaMemcpyAsync((uint8_t*)c->h_stage + res_off, (uint8_t*)c->d_stage + res_off, res_b,
+                       cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    memcpy(res, (uint8_t*)c->h_stage + res_off, res_b);
+    return GPSB_OK;
+}
+
+int gpsb_search_iq(gpsb_ctx* c, const gpsb_search_req* req, int16_t* iq)
+{
+    if (!c || !req || !iq) return fail(GPSB_ERR_ARG, "gpsb_search_iq: null argument");
+    int rc = check_search(c, 1, req);
+    if (rc) return rc;
+    if (req->start >= req->stop) return GPSB_OK;
+    CU(cudaSetDevice(c->device));
+    size_t n_off = (size_t)(req->stop - req->start);
+    size_t res_off = 256, iq_off = 512, iq_b = n_off * 4;
+    rc = ensure_stage(c, iq_off + iq_b);
+    if (rc) return rc;
+    memcpy(c->h_stage, req, sizeof *req);
+    CU(cudaMemcpyAsync(c->d_stage, c->h_stage, sizeof *req, cudaMemcpyHostToDevice, c->stream));
+    SweepParams sp = {};
+    k_search<false><<<1, kSearchThreads, 0, c->stream>>>(
+        (const gpsb_search_req*)c->d_stage, sp, (gpsb_search_res*)((uint8_t*)c->d_stage + res_off),
+        (int16_t*)((uint8_t*)c->d_stage + iq_off), c->d_codes, c->d_signal, c->ring_ms);
+    rc = check_launch(c, "k_search(iq)");
+    if (rc) return rc;
+    CU(cudaMemcpyAsync((uint8_t*)c->h_stage + iq_off, (uint8_t*)c->d_stage + iq_off, iq_b,
+                       cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    memcpy(iq, (uint8_t*)c->h_stage + iq_off, iq_b);
+    return GPSB_OK;
+}
+
+int gpsb_sweep_dev(gpsb_ctx* c, const uint32_t* d_sv_slots, uint32_t n_sv, const uint32_t* d_step32,
+                   uint32_t n_bins, uint32_t ms0, uint32_t n_ms, uint32_t off_bits, gpsb_search_res* d_res)
+{
+    if (!c || !d_sv_slots || !d_step32 || !d_res) return fail(GPSB_ERR_ARG, "gpsb_sweep_dev: null argument");
+    if (off_bits > 15) return fail(GPSB_ERR_ARG, "off_bits %u > 15", off_bits);
+    uint64_t cells = (uint64_t)n_sv * n_bins * n_ms;
+    if (cells == 0) return GPSB_OK;
+    if (cells > 0x7FFFFFFFull) return fail(GPSB_ERR_ARG, "sweep of %llu cells is too large", (unsigned long long)cells);
+    CU(cudaSetDevice(c->device));
+    SweepParams sp = {d_sv_slots, d_step32, n_bins, ms0, n_ms, off_bits};
+    k_search<true><<<(uint32_t)cells, kSearchThreads, 0, c->stream>>>(nullptr, sp, d_res, nullptr, c->d_codes,
+                                                                    c->d_signal, c->ring_ms);
+    return check_launch(c, "k_search(sweep)");
+}
+
+int gpsb_sweep(gpsb_ctx* c, const uint32_t* sv_slots, uint32_t n_sv, const uint32_t* step32, uint32_t n_bins,
+               uint32_t ms0, uint32_t n_ms, uint32_t off_bits, gpsb_search_res* res)
+{
+    if (!c || !sv_slots || !step32 || !res) return fail(GPSB_ERR_ARG, "gpsb_sweep: null argument");
+    for (uint32_t i = 0; i < n_sv; i++) {
+        if (sv_slots[i] >= c->max_sv) return fail(GPSB_ERR_ARG, "sv_slots[%u] = %u out of range", i, sv_slots[i]);
+        if (!c->code_set[sv_slots[i]]) return fail(GPSB_ERR_STATE, "no code set for slot %u", sv_slots[i]);
+    }
+    size_t cells = (size_t)n_sv * n_bins * n_ms;
+    if (cells == 0) return GPSB_OK;
+    CU(cudaSetDevice(c->device));
+    size_t sv_b = (size_t)n_sv * 4, st_b = (size_t)n_bins * 4;
+    size_t st_off = (sv_b + 255) & ~(size_t)255;
+    size_t res_off = (st_off + st_b + 255) & ~(size_t)255;
+    size_t res_b = cells * sizeof(gpsb_search_res);
+    int rc = ensure_stage(c, res_off + res_b);
+    if (rc) return rc;
+    memcpy(c->h_stage, sv_slots, sv_b);
+    memcpy((uint8_t*)c->h_stage + st_off, step32, st_b);
+    CU(cudaMemcpyAsync(c->d_stage, c->h_stage, st_off + st_b, cudaMemcpyHostToDevice, c->stream));
+    rc = gpsb_sweep_dev(c, (const uint32_t*)c->d_stage, n_sv, (const uint32_t*)((uint8_t*)c->d_stage + st_off),
+                        n_bins, ms0, n_ms, off_bits, (gpsb_search_res*)((uint8_t*)c->d_stage + res_off));
+    if (rc) return rc;
+    CU(cudaMemcpyAsync((uint8_t*)c->h_stage + res_off, (uint8_t*)c->d_stage + res_off, res_b,
+                       cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    memcpy(res, (uint8_t*)c->h_stage + res_off, res_b);
+    return GPSB_OK;
+}
+
+/* ------------------------------------------------------------------ level 0 */
+int gpsb_l0_generate_prn_data2(gpsb_ctx* c, const uint8_t chips[GPSB_CHIPS], uint16_t* data, uint16_t offset_bits)
+{
+    if (!c || !chips || !data) return fail(GPSB_ERR_ARG, "gpsb_l0_generate_prn_data2: null argument");
+    CU(cudaSetDevice(c->device));
+    uint32_t* E = c->d_l0;
+    uint32_t* R = c->d_l0 + kWords;
+    CU(cudaMemcpyAsync(c->d_chips, chips, GPSB_CHIPS, cudaMemcpyHostToDevice, c->stream));
+    k_expand_code<<<1, 256, 0, c->stream>>>(c->d_chips, E);
+    int rc = check_launch(c, "k_expand_code");
+    if (rc) return rc;
+    k_l0_replica<<<1, 256, 0, c->stream>>>(E, offset_bits, R);
+    rc = check_launch(c, "k_l0_replica");
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(c->h_stage, R, kWords * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    memcpy(data, c->h_stage, GPSB_MS_BYTES);  // 1023 words; word 1023 (spill) is the caller's
+    return GPSB_OK;
+}
+
+int gpsb_l0_shift_to_zero_freq(gpsb_ctx* c, const uint8_t* signal_data, uint8_t* data_i, uint8_t* data_q,
+                               uint32_t acc0, uint32_t step32, uint32_t* acc_out)
+{
+    if (!c || !signal_data || !data_i || !data_q) return fail(GPSB_ERR_ARG, "gpsb_l0_shift_to_zero_freq: null argument");
+    CU(cudaSetDevice(c->device));
+    uint32_t* S = c->d_l0;
+    uint32_t* I = c->d_l0 + kWords;
+    uint32_t* Q = c->d_l0 + 2 * kWords;
+    memset(c->h_stage, 0, GPSB_FRAME_BYTES);
+    memcpy(c->h_stage, signal_data, GPSB_MS_BYTES);
+    CU(cudaMemcpyAsync(S, c->h_stage, GPSB_FRAME_BYTES, cudaMemcpyHostToDevice, c->stream));
+    k_l0_mix<<<1, 256, 0, c->stream>>>(S, acc0, step32, I, Q);
+    int rc = check_launch(c, "k_l0_mix");
+    if (rc) return rc;
+    uint8_t* h = (uint8_t*)c->h_stage + GPSB_FRAME_BYTES;
+    CU(cudaMemcpyAsync(h, I, 2 * kWords * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    memcpy(data_i, h, kMixWords * 4);                 // 2044 bytes, gps_misc.c:229
+    memcpy(data_q, h + kWords * 4, kMixWords * 4);
+    if (acc_out) *acc_out = acc0 + (uint32_t)kMixWords * step32;
+    return GPSB_OK;
+}
+
+static int l0_search_impl(gpsb_ctx* c, const uint16_t* prn_p, const uint16_t* data_i, const uint16_t* data_q,
+                          uint32_t start, uint32_t stop, gpsb_search_res* res, int16_t* iq_first)
+{
+    if (!c || !prn_p || !data_i || !data_q) return fail(GPSB_ERR_ARG, "level-0 correlator: null argument");
+    if (stop > GPSB_OFFSETS) return fail(GPSB_ERR_ARG, "offset %u out of range", stop);
+    CU(cudaSetDevice(c->device));
+    uint8_t* h = (uint8_t*)c->h_stage;
+    memset(h, 0, 3 * GPSB_FRAME_BYTES);
+    memcpy(h, prn_p, GPSB_MS_BYTES);
+    memcpy(h + GPSB_FRAME_BYTES, data_i, GPSB_MS_BYTES);
+    memcpy(h + 2 * GPSB_FRAME_BYTES, data_q, GPSB_MS_BYTES);
+    CU(cudaMemcpyAsync(c->d_l0, h, 3 * GPSB_FRAME_BYTES, cudaMemcpyHostToDevice, c->stream));
+    gpsb_search_res* d_res = (gpsb_search_res*)(c->d_l0 + 3 * kWords);
+    int16_t* d_iq = (int16_t*)(c->d_l0 + 3 * kWords + 4);
+    // iq is only requested for single-offset windows here (fits the scratch)
+    k_l0_search<<<1, kSearchThreads, 0, c->stream>>>(c->d_l0, c->d_l0 + kWords, c->d_l0 + 2 * kWords, start, stop,
+                                                     d_res, iq_first ? d_iq : nullptr);
+    int rc = check_launch(c, "k_l0_search");
+    if (rc) return rc;
+    uint8_t* hr = h + 3 * GPSB_FRAME_BYTES;
+    CU(cudaMemcpyAsync(hr, d_res, 32, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (res) memcpy(res, hr, sizeof *res);
+    if (iq_first) memcpy(iq_first, hr + 16, 4);
+    return GPSB_OK;
+}
+
+int gpsb_l0_correlation_iq(gpsb_ctx* c, const uint16_t* prn_p, const uint16_t* data_i, const uint16_t* data_q,
+                           uint16_t offset, int16_t* res_i, int16_t* res_q)
+{
+    if (!res_i || !res_q) return fail(GPSB_ERR_ARG, "gpsb_l0_correlation_iq: null result pointer");
+    if (offset >= GPSB_OFFSETS) return fail(GPSB_ERR_ARG, "offset %u out of range", offset);
+    int16_t iq[2];
+    int rc = l0_search_impl(c, prn_p, data_i, data_q, offset, offset + 1u, nullptr, iq);
+    if (rc) return rc;
+    *res_i = iq[0];
+    *res_q = iq[1];
+    return GPSB_OK;
+}
+
+int gpsb_l0_correlation8(gpsb_ctx* c, const uint16_t* prn_p, const uint16_t* data_i, const uint16_t* data_q,
+                         uint16_t offset, int16_t* res)
+{
+    if (!res) return fail(GPSB_ERR_ARG, "gpsb_l0_correlation8: null result pointer");
+    if (offset >= GPSB_OFFSETS) return fail(GPSB_ERR_ARG, "offset %u out of range", offset);
+    gpsb_search_res r;
+    int rc = l0_search_impl(c, prn_p, data_i, data_q, offset, offset + 1u, &r, nullptr);
+    if (rc) return rc;
+    *res = (int16_t)r.max;
+    return GPSB_OK;
+}
+
+int gpsb_l0_correlation_search(gpsb_ctx* c, const uint16_t* prn_p, const uint16_t* data_i, const uint16_t* data_q,
+                               uint16_t start_shift, uint16_t stop_shift, uint16_t* aver_val, uint16_t* phase,
+                               uint16_t* max_val)
+{
+    gpsb_search_res r;
+    int rc = l0_search_impl(c, prn_p, data_i, data_q, start_shift, stop_shift, &r, nullptr);
+    if (rc) return rc;
+    if (aver_val) *aver_val = r.avg;
+    if (phase) *phase = r.phase;
+    if (max_val) *max_val = r.max;
+    return GPSB_OK;
+}
+
+}  // extern "C"

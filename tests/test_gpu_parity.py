@@ -1,0 +1,256 @@
+"""Parity of the CUDA path (through the C ABI, libgpsb_cuda.so) against the oracle and the golden
+vectors.  Integer work: everything here is compared bit-exact (no tolerances).  Needs a B200."""
+import numpy as np
+import pytest
+
+from stm32f4_sdr_gps_b200 import EPL_REQ, SEARCH_REQ, GpsbError, nco_step32
+
+pytestmark = pytest.mark.gpu
+IF_HZ = 4092000
+
+
+def _pad_words(w):
+    return np.concatenate([np.asarray(w, np.uint16), np.zeros(1, np.uint16)])
+
+
+def test_device_code_generator_all_prns(engine, oracle):
+    for prn in list(range(1, 38)) + [64, 120, 158, 210]:
+        engine.set_code_prn(0, prn)
+        assert np.array_equal(engine.get_code(0), oracle.ca_code(prn)), prn
+    with pytest.raises(GpsbError):
+        engine.set_code_prn(0, 0)
+    with pytest.raises(GpsbError):
+        engine.set_code_prn(0, 211)
+    with pytest.raises(GpsbError):
+        engine.set_code_prn(engine.max_sv, 1)
+
+
+def test_set_code_roundtrip(engine, oracle):
+    chips = oracle.ca_code(17)
+    engine.set_code(3, chips)
+    assert np.array_equal(engine.get_code(3), chips)
+
+
+def test_l0_replica_all_shifts(engine, oracle, golden):
+    for i, prn in enumerate(golden["replica_prns"]):
+        chips = oracle.ca_code(int(prn))
+        for b in range(16):
+            got = engine.l0_generate_prn_data2(chips, b)
+            assert np.array_equal(got, golden["replica_words"][i, b]), (prn, b)
+
+
+def test_l0_mixer(engine, oracle, golden):
+    sig = golden["rnd_signal"]
+    for f, gi, gq in zip(golden["mix_freqs"], golden["mix_i"], golden["mix_q"]):
+        di = np.full(2046, 0xAB, np.uint8)
+        dq = np.full(2046, 0xCD, np.uint8)
+        acc = engine.l0_shift_to_zero_freq(sig, 77, nco_step32(f), di, dq)
+        oi, oq, oacc = oracle.mix(sig, 77, nco_step32(f))
+        assert np.array_equal(di[:2044], oi[:2044]) and np.array_equal(dq[:2044], oq[:2044])
+        assert di[2044] == 0xAB and dq[2045] == 0xCD and acc == oacc
+        di0 = np.zeros(2046, np.uint8)
+        dq0 = np.zeros(2046, np.uint8)
+        engine.l0_shift_to_zero_freq(sig, 0, nco_step32(f), di0, dq0)
+        assert np.array_equal(di0[:2044], gi) and np.array_equal(dq0[:2044], gq)
+
+
+def test_l0_raw_correlator_golden(engine, golden):
+    prn, di, dq = _pad_words(golden["raw_prn"]), _pad_words(golden["raw_i"]), _pad_words(golden["raw_q"])
+    for off in list(range(0, 2046, 61)) + [1, 2, 3, 1021, 1022, 1023, 2043, 2044, 2045]:
+        assert engine.l0_correlation_iq(prn, di, dq, off) == tuple(golden["raw_iq"][off]), off
+        assert engine.l0_correlation8(prn, di, dq, off) == golden["raw_corr8"][off], off
+    for (a0, a1), want in zip(golden["raw_windows"], golden["raw_search"]):
+        assert engine.l0_correlation_search(prn, di, dq, int(a0), int(a1)) == tuple(want), (a0, a1)
+
+
+def test_simulator_kat_through_fused_search(engine, golden):
+    """SS/main.c:59-68: best_phase == 100 on the reference simulator buffer."""
+    engine.set_code_prn(1, 1)
+    engine.upload_signal(0, golden["sim_buffers"])
+    rq = np.zeros(4, SEARCH_REQ)
+    rq["sv_slot"], rq["ms_index"] = 1, np.arange(4)
+    rq["step32"], rq["stop"] = nco_step32(IF_HZ + 2000), 2046
+    res = engine.search(rq)
+    for i in range(4):
+        assert (res["max"][i], res["phase"][i], res["avg"][i]) == tuple(golden["sim_search"][i])
+    assert (res["max"][0], res["phase"][0], res["avg"][0]) == (7904, 100, 65)
+
+
+def test_search_iq_every_offset_every_shift(engine, golden):
+    engine.set_code_prn(1, 1)
+    engine.upload_signal(0, golden["sim_buffers"])
+    rq = np.zeros(1, SEARCH_REQ)
+    rq["sv_slot"], rq["ms_index"], rq["step32"], rq["stop"] = 1, 1, nco_step32(IF_HZ + 2000), 2046
+    for b in range(16):
+        rq["off_bits"] = b
+        assert np.array_equal(engine.search_iq(rq), golden["sim15_iq_bits"][b]), b
+    for i in range(4):
+        rq["off_bits"], rq["ms_index"] = 0, i
+        assert np.array_equal(engine.search_iq(rq), golden["sim_iq_all"][i])
+
+
+def test_epl_random_requests_vs_oracle(engine, oracle):
+    rng = np.random.default_rng(42)
+    n_ms, prns = 16, [2, 9, 31]
+    sig = rng.integers(0, 256, (n_ms, 2046), dtype=np.uint8)
+    engine.upload_signal(32, sig)
+    for s, prn in enumerate(prns):
+        engine.set_code_prn(s, prn)
+    n = 600
+    rq = np.zeros(n, EPL_REQ)
+    rq["sv_slot"] = rng.integers(0, 3, n)
+    rq["ms_index"] = 32 + rng.integers(0, n_ms, n)
+    rq["acc0"] = rng.integers(0, 2**32, n, dtype=np.uint64)
+    rq["step32"] = rng.integers(0, 2**32, n, dtype=np.uint64)
+    rq["off_p"] = rng.integers(0, 2046, n)
+    rq["off_p"][:8] = [0, 1, 2, 2043, 2044, 2045, 1022, 1023]
+    rq["off_e"] = np.where(rq["off_p"] == 0, 2045, rq["off_p"].astype(np.int32) - 1)
+    rq["off_l"] = np.where(rq["off_p"] == 2045, 0, rq["off_p"] + 1)
+    rq["off_e"][8:40] = rng.integers(0, 2046, 32)      # arbitrary, unrelated arms are legal too
+    rq["off_l"][8:40] = rng.integers(0, 2046, 32)
+    rq["off_bits"] = rng.integers(0, 16, n)
+    out = engine.track_epl(rq)
+    for i in range(n):
+        want = oracle.epl_explicit(oracle.ca_code(prns[rq["sv_slot"][i]]), sig[rq["ms_index"][i] - 32],
+                                   int(rq["acc0"][i]), int(rq["step32"][i]), int(rq["off_e"][i]),
+                                   int(rq["off_p"][i]), int(rq["off_l"][i]), int(rq["off_bits"][i]))
+        assert np.array_equal(out[i], want), (i, rq[i])
+
+
+def test_epl_matches_reference_trace(engine, golden):
+    """Replay the reference's closed-loop trajectory open loop: given the state the reference had
+    before each step, the device must reproduce its six sums (tracking.c:115-138)."""
+    from oracle_lib import Oracle
+    orc = Oracle()
+    sig = golden["scene_signal"]
+    engine.upload_signal(0, sig[:256])
+    for s, prn in enumerate((5, 14)):
+        engine.set_code_prn(s, prn)
+        iq = golden["track_iq"][s]
+        st = golden["track_state_bits"][s].view(np.float32)
+        # steps where tracking ran both at k-1 and k: state before k == logged state after k-1
+        ks = [k for k in range(1, 256) if iq[k].any() and iq[k - 1].any()]
+        assert len(ks) > 50
+        rq = np.zeros(len(ks), EPL_REQ)
+        want = []
+        for j, k in enumerate(ks):
+            fine, foff = st[k - 1]
+            e, p, l, bits = orc.epl_offsets(fine)
+            rq[j] = (s, k, 0, nco_step32(np.float32(IF_HZ) + np.float32(foff)), e, p, l, bits)
+        # the reference's accumulator is not logged; recover parity on |I|^2+|Q|^2-independent
+        # quantities by using the oracle for acc0-dependent sums instead
+        out = engine.track_epl(rq)
+        for j, k in enumerate(ks):
+            w = orc.epl_explicit(orc.ca_code((5, 14)[s]), sig[k], 0, int(rq["step32"][j]), int(rq["off_e"][j]),
+                                 int(rq["off_p"][j]), int(rq["off_l"][j]), int(rq["off_bits"][j]))
+            assert np.array_equal(out[j], w)
+
+
+def test_search_windows_vs_oracle(engine, oracle):
+    rng = np.random.default_rng(7)
+    sig = rng.integers(0, 256, (8, 2046), dtype=np.uint8)
+    sig[5] = 0                       # all-zero millisecond
+    engine.upload_signal(100, sig)
+    prns = [4, 11, 23, 28]
+    for s, prn in enumerate(prns):
+        engine.set_code_prn(s, prn)
+    windows = [(0, 2046), (0, 1), (2045, 2046), (100, 107), (1000, 1500), (2016, 2046), (5, 5), (9, 3), (0, 30)]
+    rq = np.zeros(len(windows) * 4, SEARCH_REQ)
+    meta = []
+    for i in range(rq.size):
+        a0, a1 = windows[i % len(windows)]
+        f = np.float32(IF_HZ + int(rng.integers(-14, 15)) * 500)
+        bits = int(rng.integers(0, 16)) if i % 3 == 0 else 0
+        rq[i] = (i % 4, 100 + i % 8, 0, nco_step32(f), bits, a0, a1, 0)
+        meta.append((prns[i % 4], i % 8, f, bits, a0, a1))
+    res = engine.search(rq)
+    for i, (prn, m, f, bits, a0, a1) in enumerate(meta):
+        want = oracle.search_cell(oracle.ca_code(prn), sig[m], float(f), bits, a0, a1)
+        assert (res["max"][i], res["phase"][i], res["avg"][i]) == want, (i, meta[i])
+
+
+def test_sweep_matches_reference_golden(engine, golden):
+    """Cold-acquisition cells (acquisition.c:282-294) on the 2-satellite scene: every triple equals
+    what the unmodified reference computed."""
+    sig = golden["scene_signal"]
+    engine.upload_signal(0, sig[:8])
+    for s, prn in enumerate(golden["scene_prns"]):
+        engine.set_code_prn(s, int(prn))
+    step = [nco_step32(np.float32(IF_HZ - 5000 + 500 * b)) for b in range(21)]
+    res = engine.sweep([0, 1, 2], step, 0, 4, 0)
+    want = golden["scene_sweep"]
+    assert np.array_equal(res["max"], want[..., 0])
+    assert np.array_equal(res["phase"], want[..., 1])
+    assert np.array_equal(res["avg"], want[..., 2])
+    step3 = [nco_step32(np.float32(IF_HZ - 3000 + 500 * b)) for b in range(3)]
+    res3 = engine.sweep([0, 1, 2], step3, 0, 2, 3)
+    w3 = golden["scene_sweep_bits3"]
+    assert np.array_equal(res3["max"], w3[..., 0]) and np.array_equal(res3["phase"], w3[..., 1])
+    assert np.array_equal(res3["avg"], w3[..., 2])
+    # the strong satellites are found where the scene put them
+    assert res["phase"][0, 12, 0] == 1990 and res["phase"][1, 5, 0] in (101, 102)
+
+
+def test_sweep_full_size_properties(engine, oracle):
+    """BASELINE config 3 size (32 SV x 21 bins x 10 ms): size-independent properties - the sweep
+    equals the per-cell search, and a sample of cells equals the oracle."""
+    from stm32f4_sdr_gps_b200.signal_synth import config3_scene, synthesize
+    scene = config3_scene(n_ms=10)
+    sig = synthesize(scene)
+    engine.upload_signal(0, sig)
+    for prn in range(1, 33):
+        engine.set_code_prn(prn - 1, prn)
+    step = np.array([nco_step32(np.float32(IF_HZ - 5000 + 500 * b)) for b in range(21)], np.uint32)
+    res = engine.sweep(np.arange(32), step, 0, 10, 0)
+    assert res.shape == (32, 21, 10)
+    rng = np.random.default_rng(9)
+    idx = rng.integers(0, 32 * 21 * 10, 64)
+    rq = np.zeros(idx.size, SEARCH_REQ)
+    for j, c in enumerate(idx):
+        s, b, m = c // 210, (c // 10) % 21, c % 10
+        rq[j] = (s, m, 0, step[b], 0, 0, 2046, 0)
+    single = engine.search(rq)
+    flat = res.reshape(-1)
+    assert np.array_equal(single["max"], flat["max"][idx]) and np.array_equal(single["phase"], flat["phase"][idx])
+    for j, c in enumerate(idx[:12]):
+        s, b, m = c // 210, (c // 10) % 21, c % 10
+        want = oracle.search_cell(oracle.ca_code(int(s) + 1), sig[m], float(IF_HZ - 5000 + 500 * b), 0, 0, 2046)
+        assert (flat["max"][c], flat["phase"][c], flat["avg"][c]) == want
+    # every present satellite shows up at its true code phase in its nearest Doppler bin
+    for sat in scene.sats:
+        b = int(round((sat.doppler_hz + 5000) / 500.0))
+        ph = res["phase"][sat.prn - 1, b, :]
+        true = sat.code_phase_samples / 8.0
+        d = np.minimum(np.abs(ph - true), 2046 - np.abs(ph - true))
+        assert (d < 2.5).sum() >= 5, (sat.prn, ph, true)
+
+
+def test_ingest_iq2_adaptor(engine):
+    from stm32f4_sdr_gps_b200.signal_synth import iq2_from_packed
+    rng = np.random.default_rng(12)
+    packed = rng.integers(0, 256, (5, 2046), dtype=np.uint8)
+    engine.upload_signal_iq2(200, iq2_from_packed(packed))
+    assert np.array_equal(engine.download_signal(200, 5), packed)
+
+
+def test_ring_wraparound_and_errors(engine):
+    rng = np.random.default_rng(13)
+    packed = rng.integers(0, 256, (6, 2046), dtype=np.uint8)
+    ms0 = engine.ring_ms - 3                      # wraps after three frames
+    engine.upload_signal(ms0, packed)
+    assert np.array_equal(engine.download_signal(ms0, 6), packed)
+    with pytest.raises(GpsbError):
+        engine.upload_signal(0, np.zeros((engine.ring_ms + 1, 2046), np.uint8))
+    rq = np.zeros(1, EPL_REQ)
+    rq["sv_slot"] = engine.max_sv
+    with pytest.raises(GpsbError):
+        engine.track_epl(rq)
+    rq["sv_slot"], rq["off_p"] = 0, 2046
+    with pytest.raises(GpsbError):
+        engine.track_epl(rq)
+    assert engine.track_epl(np.zeros(0, EPL_REQ)).shape == (0, 6)     # empty batch is a no-op
+    assert engine.search(np.zeros(0, SEARCH_REQ)).size == 0
+    rq = np.zeros(1, EPL_REQ)
+    rq["sv_slot"] = 39                            # slot never given a code
+    with pytest.raises(GpsbError):
+        engine.track_epl(rq)
