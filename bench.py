@@ -252,7 +252,8 @@ def run_gpu_arm(args) -> None:
     scene = make_scene(rank, N_MS)
     sig = cached_signal("trk_r%d_%d" % (rank, N_MS), scene)
     eng = Engine(device=local_rank, max_sv=max(ACQ_SV, N_SV_PER_GPU), ring_ms=N_MS + 24)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)       # a real (non-default) stream shared by torch events and the engine
+    torch.cuda.set_stream(stream)
     eng.set_stream(stream.cuda_stream)
     for s, sat in enumerate(scene.sats):
         eng.set_code_prn(s, sat.prn)

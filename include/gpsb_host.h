@@ -1,0 +1,329 @@
+/*
+ * gpsb_host.h - host-side C mirror of the reference receiver API for the acquisition / tracking hot
+ * path (libgpsb_host.so), running its correlations on the B200 through include/gpsb.h.
+ *
+ * Reference = iliasam/STM32F4_SDR_GPS, Firmware/project_main ("PM/").  The reference has no plugin
+ * interface; its seam is a set of plain C headers.  This library exports
+ *
+ *   (1) the SAME function names and signatures as PM/GPS/acquisition.h:7-12, PM/GPS/tracking.h:6,
+ *       PM/GPS/gps_master.h:7-15 and PM/GPS/gps_misc.h:195-216, operating on the SAME channel record
+ *       (gps_ch_t, PM/GPS/gps_misc.h:184-193), so that a build of the reference firmware logic can link
+ *       against it instead of acquisition.c / tracking.c / gps_misc.c / nav_data.c / gps_master.c;
+ *   (2) batched forms (gpsb_rx_*) that evaluate ALL channels of a millisecond - or a whole cold-start
+ *       sweep - in one GPU launch; these are what a B200 deployment calls.
+ *
+ * What runs where: every XOR/popcount correlation runs on the GPU (no CPU correlator exists in this
+ * library; without a CUDA device the calls fail and report through gpsb_host_last_status()).  The
+ * loop filters, votes and nav-bit logic are scalar float/integer code that feeds the next step's NCO
+ * words; they run on the host with the host libm, exactly as the reference does, so their state is
+ * bit-identical to the reference's (SURVEY.md section 7 "hard parts").
+ *
+ * The reference keeps several pieces of cross-call state in file-scope globals that only work under
+ * its one-channel-at-a-time schedule (PM/GPS/acquisition.c:28-33, tracking.c:33-34, nav_data.c:29,
+ * 48-51).  The reference-named entry points below keep ONE such shared set, like the reference; the
+ * gpsb_rx_* batched entry points keep one set PER CHANNEL, which equals the reference run with a single
+ * active channel.
+ */
+#ifndef GPSB_HOST_H
+#define GPSB_HOST_H
+
+#include <stdint.h>
+#include <time.h>
+
+#include "gpsb.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------------
+ * Receiver constants (PM/config.h).  Names are kept so reference code compiles against this header.
+ * ---------------------------------------------------------------------------------------------- */
+#ifndef _CONFIG_H
+#define IF_FREQ_HZ                 ((int)4092000)              /* config.h:23 */
+#define SPI_BAUDRATE_HZ            ((int)16368000)             /* config.h:24 */
+#define PRN_SPEED_HZ               1000                        /* config.h:25 */
+#define BITS_IN_PRN                (SPI_BAUDRATE_HZ / PRN_SPEED_HZ)
+#define PRN_SPI_WORDS_CNT          (BITS_IN_PRN / 16)
+#define PRN_LENGTH                 1023
+#define ENABLE_CODE_FILTER         1                           /* config.h:36 */
+#define CODE_FILTER_LENGTH         100
+#define ACQ_SEARCH_FREQ_HZ         (7000)                      /* config.h:41 */
+#define ACQ_SEARCH_STEP_HZ         (500)
+#define ACQ_COUNT                  (ACQ_SEARCH_FREQ_HZ * 2 / ACQ_SEARCH_STEP_HZ + 1)
+#define ACQ_PHASE1_HIST_STEP       (64)
+#define ACQ_PHASE1_HIST_SIZE       ((PRN_LENGTH + 1) * 2 / ACQ_PHASE1_HIST_STEP)
+#define PRE_TRACK_POINTS_MAX_CNT   30
+#define IF_NCO_STEP_HZ             (0.003810972f)              /* config.h:53 */
+#define TRACKING_CH_LENGTH         4
+#define GPS_SAT_CNT                4                           /* default; see gpsb_host_set_sat_cnt */
+#define TRACKING_DLL1_C1           (1.0f)
+#define TRACKING_DLL1_C2           (300.0f)
+#define TRACKING_PLL1_C1           (4.0f)
+#define TRACKING_PLL1_C2           (3000.0f)
+#define TRACKING_PLL2_C1           (8.0f)
+#define TRACKING_PLL2_C2           (5000.0f)
+#define TRACKING_FLL1_C1           (200.0f)
+#define TRACKING_FLL1_C2           (2000.0f)
+#endif
+
+/* ------------------------------------------------------------------------------------------------
+ * Channel record.  Field order, names and types reproduce PM/GPS/gps_misc.h:20-193 because the
+ * record IS the interface: callers own it, fill prn / given_freq_offset_hz, and read results out of it.
+ * If the reference header was included first its definitions are used as they are.
+ * ---------------------------------------------------------------------------------------------- */
+#ifndef _GPS_MISC_H
+#define GPS_NAV_WORD_LENGTH            30
+#define GPS_NAV_SUBFRAME_LENGTH_BYTES  38
+
+typedef enum {
+    GPS_ACQ_NEED_FREQ_SEARCH = 0, GPS_ACQ_FREQ_SEARCH_RUN, GPS_ACQ_FREQ_SEARCH_DONE,
+    GPS_ACQ_CODE_PHASE_SEARCH1, GPS_ACQ_CODE_PHASE_SEARCH1_DONE,
+    GPS_ACQ_CODE_PHASE_SEARCH2, GPS_ACQ_CODE_PHASE_SEARCH2_DONE,
+    GPS_ACQ_CODE_PHASE_SEARCH3, GPS_ACQ_CODE_PHASE_SEARCH3_DONE,
+    GPS_ACQ_DONE,
+} gps_acq_state_t;
+
+typedef enum {
+    GPS_TRACKNG_IDLE, GPS_NEED_PRE_TRACK, GPS_PRE_TRACK_RUN, GPS_PRE_TRACK_DONE, GPS_TRACKING_RUN,
+} gps_tracking_state_t;
+
+typedef struct {
+    uint8_t  freq_index;              /* Doppler bin under test, 0 == -ACQ_SEARCH_FREQ_HZ         */
+    int16_t  found_freq_offset_hz;
+    int16_t  given_freq_offset_hz;    /* non-zero: skip the Doppler search                        */
+    uint16_t found_code_phase;        /* half chips, 0..2046                                      */
+    uint16_t code_search_start;
+    uint16_t code_search_stop;
+    uint16_t code_hist_step;
+    gps_acq_state_t state;
+    uint8_t  code_phase_histogram[ACQ_PHASE1_HIST_SIZE];
+    uint32_t start_timestamp;
+    float    hist_ratio;
+} gps_acq_t;
+
+typedef struct {
+    uint16_t code_search_start;
+    uint16_t code_search_stop;
+    float    if_freq_offset_hz;
+    uint32_t if_freq_accum;
+    uint16_t pre_track_phases[PRE_TRACK_POINTS_MAX_CNT];
+    uint8_t  pre_track_count;
+    uint32_t prev_track_timestamp;
+    float    code_phase_fine;         /* samples (1/16 chip), 0..16368                            */
+    float    old_code_phase_fine;
+    uint8_t  code_phase_swap_flag;
+    float    dll_code_err;
+    float    pll_code_err;
+    int16_t  fll_old_i;
+    int16_t  fll_old_q;
+    float    fll_err;
+    int16_t  pll_check_buf[TRACKING_CH_LENGTH];
+    uint8_t  pll_bad_state_cnt;
+    uint16_t pll_bad_state_master_cnt;
+    uint32_t i_part_summ;
+    uint32_t q_part_summ;
+    uint16_t snr_summ_cnt;
+    float    snr_value;
+#if (ENABLE_CODE_FILTER)
+    uint32_t filt_start_time_ms;
+    uint16_t code_filt_cnt;
+    float    code_phase_fine_filt;
+#endif
+    gps_tracking_state_t state;
+} gps_tracking_t;
+
+typedef struct {
+    uint8_t  period_sync_ok_flag;
+    uint8_t  right_period_cnt;
+    uint32_t old_swap_time;
+    uint8_t  old_reminder;
+    uint8_t  accurate_swap_time;
+    uint8_t  accurate_swap_ok;
+    uint8_t  last_bit_pos_cnt;
+    uint8_t  last_bit_neg_cnt;
+    uint8_t  inv_polarity_flag;
+    uint8_t  polarity_found;
+    uint8_t  inv_preabmle_cnt;
+    uint8_t  word_buf[GPS_NAV_WORD_LENGTH];
+    uint8_t  word_cnt;
+    uint8_t  word_bit_cnt;
+    uint8_t  old_D29;
+    uint8_t  old_D30;
+    uint32_t word_detection_timestamp;
+    uint32_t word_cnt_test;
+    uint32_t last_subframe_time;
+    uint32_t first_subframe_time;
+    uint16_t subframe_cnt;
+    uint8_t  new_subframe_flag;
+    uint8_t  subframe_data[GPS_NAV_SUBFRAME_LENGTH_BYTES];
+} gps_nav_data_t;
+
+typedef struct { double pseudorange_m; double tow_s; } gps_obs_data_t;
+
+/* RTKLIB-derived ephemeris containers; carried for layout only, the hot path never touches them. */
+typedef struct { time_t time; double sec; } gtime_t;
+typedef struct {
+    int sat, iode, iodc, sva, svh, week, code, flag;
+    gtime_t toe, toc, ttr;
+    double A, e, i0, OMG0, omg, M0, deln, OMGd, idot;
+    double crc, crs, cuc, cus, cic, cis;
+    double toes, fit, f0, f1, f2;
+    double tgd[4];
+} eph_t;
+typedef struct {
+    eph_t eph;
+    int ctype;
+    double tow_gpst;
+    int week_gpst, cnt, cntth, update, prn, week_gst;
+    uint16_t sub_cnt;
+    uint8_t received_mask, received_mask_proc;
+} sdreph_t;
+
+typedef struct {
+    gps_acq_t      acq_data;
+    gps_tracking_t tracking_data;
+    gps_nav_data_t nav_data;
+    gps_obs_data_t obs_data;
+    sdreph_t       eph_data;
+    uint8_t        prn;
+    uint8_t        prn_code[PRN_LENGTH];
+} gps_ch_t;
+#endif /* _GPS_MISC_H */
+
+/* ------------------------------------------------------------------------------------------------
+ * Binding to a GPU context and to the millisecond clock.
+ * ---------------------------------------------------------------------------------------------- */
+/* All reference-named calls below run on this context (one per process for the drop-in API).
+ * The context must have been created with max_sv >= 211: satellite slot == PRN number. */
+int  gpsb_host_attach(gpsb_ctx* ctx);
+gpsb_ctx* gpsb_host_context(void);
+/* Status of the most recent GPU call made on behalf of a void reference-named function
+ * (the reference API has no error channel, PM/GPS/acquisition.c:136, tracking.c:96). */
+int  gpsb_host_last_status(void);
+/* Number of receiver channels the array forms iterate over (GPS_SAT_CNT, PM/config.h:59). */
+void gpsb_host_set_sat_cnt(uint32_t n);
+uint32_t gpsb_host_sat_cnt(void);
+/* Replaces the SPI/DMA millisecond counter, PM/signal_capture.c:57-82.  The library provides
+ * signal_capture_get_packet_cnt() (signal_capture.h:15) as a WEAK symbol backed by this value, so an
+ * application that has its own capture layer overrides it by simply defining the function. */
+void gpsb_host_set_packet_cnt(uint32_t ms);
+uint32_t signal_capture_get_packet_cnt(void);
+/* Deterministic replacement of rand() in the false-lock reseed (PM/GPS/tracking.c:316): NULL = libc. */
+void gpsb_host_set_rand(int (*fn)(void));
+
+/* ------------------------------------------------------------------------------------------------
+ * (1) Reference-named API.
+ * ---------------------------------------------------------------------------------------------- */
+/* PM/GPS/gps_misc.h:195-196 */
+void gps_fill_summ_table(void);                 /* no table is needed on the GPU; kept for link parity */
+void gps_channell_prepare(gps_ch_t* channel);   /* fills prn_code[] and loads device slot `prn`      */
+
+/* PM/GPS/acquisition.h:7-12 */
+void acquisition_process(gps_ch_t* channel, uint8_t* data);
+uint32_t* acquisition_get_hist(void);
+void acquisition_start_channel(gps_ch_t* channel);
+void acquisition_start_code_search_channel(gps_ch_t* channel);
+void acquisition_start_code_search3_channel(gps_ch_t* channel);
+void acquisition_process_channel(gps_ch_t* channel, uint8_t* data);   /* acquisition.c:134 */
+
+/* PM/GPS/tracking.h:6 */
+void gps_tracking_process(gps_ch_t* channel, uint8_t* data, uint8_t index);
+
+/* PM/GPS/nav_data.h:7 and the non-static word assembler, nav_data.c:257 */
+void gps_nav_data_analyse_new_code(gps_ch_t* channel, uint8_t index, int16_t new_i);
+void gps_nav_data_words_detection(gps_ch_t* channel, uint8_t new_bit);
+
+/* PM/GPS/gps_master.h:7-15 (sequencing only: no UART, keys, RTCM or position solver here) */
+void    gps_master_handling(gps_ch_t* channels, uint8_t index);
+uint8_t gps_master_need_acq(void);
+uint8_t gps_master_need_freq_search(gps_ch_t* channels);
+uint8_t gps_master_is_code_search3(gps_ch_t* channels);
+void    gps_master_reset_to_aqc_start(gps_ch_t* channels);
+
+/* PM/GPS/gps_misc.h:198-216 - the DSP primitives with their exact reference signatures, each one a
+ * round trip through the GPU (level 0 of include/gpsb.h). */
+int16_t  gps_correlation8(uint16_t* prn_p, uint16_t* data_i, uint16_t* data_q, uint16_t offset);
+void     gps_correlation_iq(uint16_t* prn_p, uint16_t* data_i, uint16_t* data_q, uint16_t offset,
+                            int16_t* res_i, int16_t* res_q);
+uint16_t correlation_search(uint16_t* prn_p, uint16_t* data_i, uint16_t* data_q, uint16_t start_shift,
+                            uint16_t stop_shift, uint16_t* aver_val, uint16_t* phase);
+void     gps_shift_to_zero_freq(uint8_t* signal_data, uint8_t* data_i, uint8_t* data_q, float freq_hz);
+void     gps_shift_to_zero_freq_track(gps_tracking_t* trk_channel, uint8_t* signal_data, uint8_t* data_i,
+                                      uint8_t* data_q);
+void     gps_generate_prn_data2(gps_ch_t* channel, uint16_t* data, uint16_t offset_bits);
+void     gps_rewind_if_phase(gps_tracking_t* trk_channel, uint8_t steps);
+void     gps_generate_prn(uint8_t* dest, int prn);                       /* gps_misc.c:317 */
+
+/* ------------------------------------------------------------------------------------------------
+ * (2) Batched receiver: many channels per launch, signal resident in the context's HBM ring.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct gpsb_rx gpsb_rx;
+
+/* channels: caller-owned array of n_ch records (prn set, gps_channell_prepare not required).
+ * The receiver borrows the array until gpsb_rx_destroy. */
+int  gpsb_rx_create(gpsb_rx** out, gpsb_ctx* ctx, gps_ch_t* channels, uint32_t n_ch);
+void gpsb_rx_destroy(gpsb_rx* rx);
+
+/* One millisecond of tracking for every channel (gps_tracking_process for each, PM/main.c:155, in the
+ * "every satellite every millisecond" schedule: slot index = ms % 4).  Frame `ms` must already be in
+ * the ring (gpsb_upload_signal).  Exactly one k_epl launch (+ one search launch while any channel is
+ * still in pre-track). */
+int gpsb_rx_track_ms(gpsb_rx* rx, uint32_t ms);
+/* n_ms consecutive milliseconds starting at ms0; optional logs, each may be NULL:
+ *   iq_log  [n_ms][n_ch][6]  IE,QE,IP,QP,IL,QL (zeros for channels not in GPS_TRACKING_RUN that ms)
+ *   nav_log [n_ms][n_ch]     -1, or the 20-ms data bit handed to the word assembler that ms        */
+int gpsb_rx_track_run(gpsb_rx* rx, uint32_t ms0, uint32_t n_ms, int16_t* iq_log, int8_t* nav_log);
+
+/* One acquisition snapshot for every channel (acquisition_process, PM/main.c:166) in one launch. */
+int gpsb_rx_acquire_ms(gpsb_rx* rx, uint32_t ms);
+
+/* Cold start, all channels at once: every (channel, Doppler bin, ms) cell of a sweep
+ * (n_bins bins from first_bin_hz in steps of bin_step_hz, ms0 .. ms0+n_ms-1, n_ms <= 24) in one launch,
+ * followed per channel by the reference's 10-cell chain vote and histogram decision
+ * (PM/GPS/acquisition.c:322-416) applied bin by bin.  On return each channel that passed the vote is in
+ * GPS_ACQ_FREQ_SEARCH_DONE with found_freq_offset_hz set; votes[ch*n_bins+b] (may be NULL) receives
+ * the chain length of every bin and phases[ch*n_bins+b] the code phase of the longest chain. */
+int gpsb_rx_cold_sweep(gpsb_rx* rx, int32_t first_bin_hz, int32_t bin_step_hz, uint32_t n_bins,
+                       uint32_t ms0, uint32_t n_ms, uint8_t* votes, uint16_t* phases);
+
+/* ------------------------------------------------------------------------------------------------
+ * (3) Split-phase form of the two per-channel steps.  PLAN performs the state transitions of
+ * acquisition_process_channel() / gps_tracking_process() up to the point where a correlation is needed
+ * and describes that correlation; FINISH consumes its result (votes, loop filters, nav bits).  Running
+ * PLAN, the described cell on the GPU, then FINISH equals one reference call; callers that schedule
+ * channels themselves use this to batch cells (gpsb_rx_* is built on it).  Uses the shared scratch.
+ * ---------------------------------------------------------------------------------------------- */
+typedef enum { GPSB_WANT_NOTHING = 0, GPSB_WANT_SEARCH, GPSB_WANT_EPL } gpsb_want;
+typedef struct gpsb_plan {
+    gpsb_want want;
+    gpsb_search_req search;     /* valid when want == GPSB_WANT_SEARCH (start >= stop: empty window) */
+    gpsb_epl_req epl;           /* valid when want == GPSB_WANT_EPL                                  */
+    int stage;                  /* 1 Doppler cell, 2 code-search window, 3 pre-track window, 4 E/P/L */
+} gpsb_plan;
+int gpsb_host_plan_acq(gps_ch_t* ch, uint32_t frame_ms, gpsb_plan* plan);
+int gpsb_host_finish_acq(gps_ch_t* ch, const gpsb_plan* plan, const gpsb_search_res* res);
+int gpsb_host_plan_track(gps_ch_t* ch, uint32_t frame_ms, uint8_t index, gpsb_plan* plan);
+int gpsb_host_finish_track(gps_ch_t* ch, uint8_t index, const gpsb_plan* plan, const gpsb_search_res* res,
+                           const int16_t* iq6);
+/* The 20-ms data bit handed to the word assembler by the most recent finish (shared scratch), or -1. */
+int gpsb_host_last_nav_bit(void);
+void gpsb_host_master_reset(void);
+
+/* Channel-array helpers for bindings that cannot lay out gps_ch_t themselves (ctypes, cgo, ...). */
+gps_ch_t* gpsb_host_channels_alloc(uint32_t n);
+void gpsb_host_channels_free(gps_ch_t* p);
+gps_ch_t* gpsb_host_channel_at(gps_ch_t* base, uint32_t i);
+void gpsb_host_channel_init(gps_ch_t* ch, uint32_t prn, int32_t given_freq_offset_hz);
+const uint8_t* gpsb_host_channel_code(const gps_ch_t* ch);
+
+/* Flat, layout-independent snapshot of one channel (include/gpsb_flat_state.h) for parity tests. */
+struct gpsb_flat_state;
+void gpsb_host_snapshot(const gps_ch_t* ch, struct gpsb_flat_state* out);
+void gpsb_host_restore(gps_ch_t* ch, const struct gpsb_flat_state* in);
+uint32_t gpsb_host_sizeof_channel(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPSB_HOST_H */

@@ -38,6 +38,19 @@ void sim_add_noise(uint16_t* buff_p, uint8_t noise_level);
 
 double ref_now_s(void);
 
+/* ------------------------------------------------------------------ gps_master.c link stubs
+ * gps_master.c (compiled unmodified for its acquisition/tracking sequencing, gps_master.c:68-156)
+ * also references the terminal UI, the key handler and the position solver; none of them is on the
+ * hot path, so they are inert here. */
+#include "gps_master.h"
+#include "rtk_common.h"
+uint8_t key_up_presed = 0;
+void print_state_handling(uint32_t time_ms) { (void)time_ms; }
+void print_state_update_acquisition(gps_ch_t* channels, uint32_t time_ms) { (void)channels; (void)time_ms; }
+void print_state_update_tracking(gps_ch_t* channels, uint32_t time_ms) { (void)channels; (void)time_ms; }
+uint8_t solving_is_busy(void) { return 0; }
+void gps_pos_solve(obsd_t* obs_p) { (void)obs_p; }
+
 /* ------------------------------------------------------------------ ms counter seam */
 static uint32_t g_packet_cnt = 0;
 uint32_t signal_capture_get_packet_cnt(void) { return g_packet_cnt; }

@@ -1,0 +1,392 @@
+/*
+ * rx.c - batched receiver: every channel's correlation for one millisecond (or one whole cold-start
+ * sweep) goes to the GPU in a single launch; the per-channel votes and loop filters then run on the
+ * host exactly as in acq.c / track.c / nav.c.
+ *
+ * Each channel owns its own gpsb_aux, so the result for a channel equals what the reference computes
+ * when that channel is the only active one (the reference's shared scratch, acquisition.c:28-33,
+ * tracking.c:33-34, nav_data.c:29,48-51, only works one channel at a time).
+ */
+#include <stdlib.h>
+
+#include "../../include/gpsb_flat_state.h"
+#include "host_internal.h"
+
+struct gpsb_rx {
+    gpsb_ctx* ctx;
+    gps_ch_t* ch;
+    uint32_t n_ch;
+    gpsb_aux* aux;
+    gpsb_plan* plan;
+    gpsb_epl_req* epl_rq;
+    int16_t* epl_out;
+    uint32_t* epl_owner;
+    gpsb_search_req* s_rq;
+    gpsb_search_res* s_res;
+    uint32_t* s_owner;
+};
+
+int gpsb_rx_create(gpsb_rx** out, gpsb_ctx* ctx, gps_ch_t* channels, uint32_t n_ch)
+{
+    if (!out || !ctx || !channels || n_ch == 0) return GPSB_ERR_ARG;
+    gpsb_rx* rx = (gpsb_rx*)calloc(1, sizeof *rx);
+    if (!rx) return GPSB_ERR_NOMEM;
+    rx->ctx = ctx;
+    rx->ch = channels;
+    rx->n_ch = n_ch;
+    rx->aux = (gpsb_aux*)calloc(n_ch, sizeof(gpsb_aux));
+    rx->plan = (gpsb_plan*)calloc(n_ch, sizeof(gpsb_plan));
+    rx->epl_rq = (gpsb_epl_req*)calloc(n_ch, sizeof(gpsb_epl_req));
+    rx->epl_out = (int16_t*)calloc((size_t)n_ch * 6, sizeof(int16_t));
+    rx->epl_owner = (uint32_t*)calloc(n_ch, sizeof(uint32_t));
+    rx->s_rq = (gpsb_search_req*)calloc(n_ch, sizeof(gpsb_search_req));
+    rx->s_res = (gpsb_search_res*)calloc(n_ch, sizeof(gpsb_search_res));
+    rx->s_owner = (uint32_t*)calloc(n_ch, sizeof(uint32_t));
+    if (!rx->aux || !rx->plan || !rx->epl_rq || !rx->epl_out || !rx->epl_owner || !rx->s_rq || !rx->s_res ||
+        !rx->s_owner) {
+        gpsb_rx_destroy(rx);
+        return GPSB_ERR_NOMEM;
+    }
+    for (uint32_t i = 0; i < n_ch; i++) {
+        rx->aux[i].last_nav_bit = -1;
+        if (channels[i].prn >= 1) {
+            gps_generate_prn(channels[i].prn_code, channels[i].prn);
+            int rc = gpsb_set_code(ctx, channels[i].prn, channels[i].prn_code);
+            if (rc != GPSB_OK) {
+                gpsb_rx_destroy(rx);
+                return rc;
+            }
+        }
+    }
+    *out = rx;
+    return GPSB_OK;
+}
+
+void gpsb_rx_destroy(gpsb_rx* rx)
+{
+    if (!rx) return;
+    free(rx->aux);
+    free(rx->plan);
+    free(rx->epl_rq);
+    free(rx->epl_out);
+    free(rx->epl_owner);
+    free(rx->s_rq);
+    free(rx->s_res);
+    free(rx->s_owner);
+    free(rx);
+}
+
+/* Gather the planned cells, run them (one launch per kind), return the counts. */
+static int run_plans(gpsb_rx* rx, uint32_t* n_epl_out, uint32_t* n_s_out)
+{
+    uint32_t n_epl = 0, n_s = 0;
+    for (uint32_t i = 0; i < rx->n_ch; i++) {
+        gpsb_plan* p = &rx->plan[i];
+        if (p->want == GPSB_WANT_EPL) {
+            rx->epl_rq[n_epl] = p->epl;
+            rx->epl_owner[n_epl++] = i;
+        } else if (p->want == GPSB_WANT_SEARCH) {
+            if (p->search.start < p->search.stop) {
+                rx->s_rq[n_s] = p->search;
+                rx->s_owner[n_s++] = i;
+            }
+        }
+    }
+    int rc = GPSB_OK;
+    if (n_epl) rc = gpsb_track_epl(rx->ctx, n_epl, rx->epl_rq, rx->epl_out);
+    if (rc == GPSB_OK && n_s) rc = gpsb_search(rx->ctx, n_s, rx->s_rq, rx->s_res);
+    *n_epl_out = n_epl;
+    *n_s_out = n_s;
+    return hx_note(rc);
+}
+
+static const gpsb_search_res k_empty_window = {0, 0, 0, 0};
+
+int gpsb_rx_track_ms(gpsb_rx* rx, uint32_t ms)
+{
+    if (!rx) return GPSB_ERR_ARG;
+    gpsb_host_set_packet_cnt(ms);
+    const uint8_t index = (uint8_t)(ms % GPSB_SLOT_LEN);
+    for (uint32_t i = 0; i < rx->n_ch; i++) hx_trk_plan(&rx->ch[i], &rx->aux[i], ms, index, &rx->plan[i]);
+    uint32_t n_epl, n_s;
+    int rc = run_plans(rx, &n_epl, &n_s);
+    if (rc != GPSB_OK) return rc;
+    for (uint32_t k = 0; k < n_epl; k++) {
+        uint32_t i = rx->epl_owner[k];
+        hx_trk_finish_epl(&rx->ch[i], &rx->aux[i], index, rx->epl_out + 6u * k);
+    }
+    uint32_t k = 0;
+    for (uint32_t i = 0; i < rx->n_ch; i++) {
+        if (rx->plan[i].want != GPSB_WANT_SEARCH) continue;
+        const gpsb_search_res* r = &k_empty_window;
+        if (k < n_s && rx->s_owner[k] == i) r = &rx->s_res[k++];
+        hx_trk_finish_search(&rx->ch[i], &rx->aux[i], index, r);
+    }
+    return GPSB_OK;
+}
+
+int gpsb_rx_track_run(gpsb_rx* rx, uint32_t ms0, uint32_t n_ms, int16_t* iq_log, int8_t* nav_log)
+{
+    if (!rx) return GPSB_ERR_ARG;
+    for (uint32_t m = 0; m < n_ms; m++) {
+        for (uint32_t i = 0; i < rx->n_ch; i++) rx->aux[i].last_nav_bit = -1;
+        int rc = gpsb_rx_track_ms(rx, ms0 + m);
+        if (rc != GPSB_OK) return rc;
+        if (iq_log) {
+            int16_t* row = iq_log + (size_t)m * rx->n_ch * 6;
+            memset(row, 0, (size_t)rx->n_ch * 12);
+            uint32_t k = 0;
+            for (uint32_t i = 0; i < rx->n_ch; i++)
+                if (rx->plan[i].want == GPSB_WANT_EPL) memcpy(row + 6u * i, rx->epl_out + 6u * k++, 12);
+        }
+        if (nav_log)
+            for (uint32_t i = 0; i < rx->n_ch; i++)
+                nav_log[(size_t)m * rx->n_ch + i] = rx->plan[i].want == GPSB_WANT_EPL ? rx->aux[i].last_nav_bit : -1;
+    }
+    return GPSB_OK;
+}
+
+int gpsb_rx_acquire_ms(gpsb_rx* rx, uint32_t ms)
+{
+    if (!rx) return GPSB_ERR_ARG;
+    gpsb_host_set_packet_cnt(ms);
+    for (uint32_t i = 0; i < rx->n_ch; i++) hx_acq_plan(&rx->ch[i], &rx->aux[i], ms, &rx->plan[i]);
+    uint32_t n_epl, n_s;
+    int rc = run_plans(rx, &n_epl, &n_s);
+    if (rc != GPSB_OK) return rc;
+    uint32_t k = 0;
+    for (uint32_t i = 0; i < rx->n_ch; i++) {
+        if (rx->plan[i].want != GPSB_WANT_SEARCH) continue;
+        const gpsb_search_res* r = &k_empty_window;
+        if (k < n_s && rx->s_owner[k] == i) r = &rx->s_res[k++];
+        hx_acq_finish(&rx->ch[i], &rx->aux[i], &rx->plan[i], r);
+    }
+    return GPSB_OK;
+}
+
+/* Start the Doppler search of one channel on its private vote buffers (acquisition.c:68-87). */
+static void start_doppler_search(gps_ch_t* ch, gpsb_aux* aux)
+{
+    gps_acq_t* a = &ch->acq_data;
+    if (a->state != GPS_ACQ_NEED_FREQ_SEARCH) return;
+    if (a->given_freq_offset_hz != 0) {
+        a->found_freq_offset_hz = a->given_freq_offset_hz;
+        a->state = GPS_ACQ_FREQ_SEARCH_DONE;
+        return;
+    }
+    memset(aux->freq_hist, 0, sizeof aux->freq_hist);
+    memset(aux->bin_phases, 0, sizeof aux->bin_phases);
+    aux->bin_count = 0;
+    a->freq_index = 0;
+    a->state = GPS_ACQ_FREQ_SEARCH_RUN;
+}
+
+int gpsb_rx_cold_sweep(gpsb_rx* rx, int32_t first_bin_hz, int32_t bin_step_hz, uint32_t n_bins, uint32_t ms0,
+                       uint32_t n_ms, uint8_t* votes, uint16_t* phases)
+{
+    if (!rx || n_bins == 0 || n_bins > GPSB_MAX_BINS || n_ms == 0 || n_ms > GPSB_FREQ_POINTS_MAX - 1)
+        return hx_note(GPSB_ERR_ARG);
+    uint32_t* slots = (uint32_t*)malloc(sizeof(uint32_t) * rx->n_ch);
+    uint32_t* who = (uint32_t*)malloc(sizeof(uint32_t) * rx->n_ch);
+    uint32_t* step32 = (uint32_t*)malloc(sizeof(uint32_t) * n_bins);
+    if (!slots || !who || !step32) {
+        free(slots); free(who); free(step32);
+        return hx_note(GPSB_ERR_NOMEM);
+    }
+    uint32_t n_sv = 0;
+    for (uint32_t i = 0; i < rx->n_ch; i++) {
+        if (rx->ch[i].prn < 1) continue;
+        start_doppler_search(&rx->ch[i], &rx->aux[i]);
+        if (rx->ch[i].acq_data.state != GPS_ACQ_FREQ_SEARCH_RUN) continue;
+        slots[n_sv] = rx->ch[i].prn;
+        who[n_sv++] = i;
+    }
+    for (uint32_t b = 0; b < n_bins; b++)        /* int -> float at the call site, acquisition.c:288 */
+        step32[b] = hx_nco_step32((float)(IF_FREQ_HZ + (int16_t)(first_bin_hz + (int32_t)b * bin_step_hz)));
+    int rc = GPSB_OK;
+    gpsb_search_res* cells = NULL;
+    if (n_sv) {
+        cells = (gpsb_search_res*)malloc(sizeof(gpsb_search_res) * (size_t)n_sv * n_bins * n_ms);
+        rc = cells ? gpsb_sweep(rx->ctx, slots, n_sv, step32, n_bins, ms0, n_ms, 0, cells) : GPSB_ERR_NOMEM;
+    }
+    if (rc == GPSB_OK) {
+        gpsb_host_set_packet_cnt(ms0 + n_ms - 1);
+        for (uint32_t s = 0; s < n_sv; s++) {
+            gps_ch_t* ch = &rx->ch[who[s]];
+            gpsb_aux* aux = &rx->aux[who[s]];
+            for (uint32_t b = 0; b < n_bins; b++) {
+                uint16_t grp[GPSB_FREQ_POINTS_MAX];
+                for (uint32_t m = 0; m < n_ms; m++) grp[m] = cells[((size_t)s * n_bins + b) * n_ms + m].phase;
+                uint16_t at = 0;
+                uint8_t chain = hx_chain_vote(grp, (uint8_t)n_ms, &at);
+                if (votes) votes[(size_t)who[s] * n_bins + b] = chain;
+                if (phases) phases[(size_t)who[s] * n_bins + b] = at;
+                if (ch->acq_data.state != GPS_ACQ_FREQ_SEARCH_RUN) continue;   /* decided at an earlier bin */
+                if (chain >= 2) aux->freq_hist[b] += chain;
+                ch->acq_data.freq_index = (uint8_t)b;
+                hx_freq_hist_decide(ch, aux->freq_hist, n_bins, first_bin_hz, bin_step_hz);
+            }
+        }
+    }
+    free(cells); free(slots); free(who); free(step32);
+    return hx_note(rc);
+}
+
+/* ---------------------------------------------------------------------------- split-phase API */
+int gpsb_host_plan_acq(gps_ch_t* ch, uint32_t frame_ms, gpsb_plan* plan)
+{
+    if (!ch || !plan) return GPSB_ERR_ARG;
+    hx_acq_plan(ch, &g_shared_aux, frame_ms, plan);
+    return GPSB_OK;
+}
+
+int gpsb_host_finish_acq(gps_ch_t* ch, const gpsb_plan* plan, const gpsb_search_res* res)
+{
+    if (!ch || !plan) return GPSB_ERR_ARG;
+    hx_acq_finish(ch, &g_shared_aux, plan, res ? res : &k_empty_window);
+    return GPSB_OK;
+}
+
+int gpsb_host_plan_track(gps_ch_t* ch, uint32_t frame_ms, uint8_t index, gpsb_plan* plan)
+{
+    if (!ch || !plan) return GPSB_ERR_ARG;
+    hx_trk_plan(ch, &g_shared_aux, frame_ms, index, plan);
+    return GPSB_OK;
+}
+
+int gpsb_host_finish_track(gps_ch_t* ch, uint8_t index, const gpsb_plan* plan, const gpsb_search_res* res,
+                           const int16_t* iq6)
+{
+    if (!ch || !plan) return GPSB_ERR_ARG;
+    if (plan->want == GPSB_WANT_SEARCH) hx_trk_finish_search(ch, &g_shared_aux, index, res ? res : &k_empty_window);
+    else if (plan->want == GPSB_WANT_EPL && iq6) hx_trk_finish_epl(ch, &g_shared_aux, index, iq6);
+    return GPSB_OK;
+}
+
+int gpsb_host_last_nav_bit(void) { return g_shared_aux.last_nav_bit; }
+
+/* ---------------------------------------------------------------------------- flat snapshots */
+static uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+static float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+
+uint32_t gpsb_host_sizeof_channel(void) { return (uint32_t)sizeof(gps_ch_t); }
+
+#define COPY_OUT(dst, src) o->dst = (uint32_t)(src)
+void gpsb_host_snapshot(const gps_ch_t* ch, struct gpsb_flat_state* o)
+{
+    const gps_acq_t* a = &ch->acq_data;
+    const gps_tracking_t* t = &ch->tracking_data;
+    const gps_nav_data_t* n = &ch->nav_data;
+    memset(o, 0, sizeof *o);
+    o->prn = ch->prn;
+    COPY_OUT(acq_state, a->state);                   COPY_OUT(freq_index, a->freq_index);
+    o->found_freq_offset_hz = a->found_freq_offset_hz; o->given_freq_offset_hz = a->given_freq_offset_hz;
+    COPY_OUT(found_code_phase, a->found_code_phase);
+    COPY_OUT(acq_code_search_start, a->code_search_start);
+    COPY_OUT(acq_code_search_stop, a->code_search_stop);
+    COPY_OUT(code_hist_step, a->code_hist_step);     COPY_OUT(acq_start_timestamp, a->start_timestamp);
+    o->hist_ratio_bits = f2u(a->hist_ratio);
+    memcpy(o->code_phase_histogram, a->code_phase_histogram, GPSB_FLAT_HIST_SIZE);
+
+    COPY_OUT(trk_state, t->state);
+    COPY_OUT(trk_code_search_start, t->code_search_start);
+    COPY_OUT(trk_code_search_stop, t->code_search_stop);
+    o->if_freq_offset_hz_bits = f2u(t->if_freq_offset_hz);
+    COPY_OUT(if_freq_accum, t->if_freq_accum);       COPY_OUT(pre_track_count, t->pre_track_count);
+    COPY_OUT(prev_track_timestamp, t->prev_track_timestamp);
+    o->code_phase_fine_bits = f2u(t->code_phase_fine);
+    o->old_code_phase_fine_bits = f2u(t->old_code_phase_fine);
+    COPY_OUT(code_phase_swap_flag, t->code_phase_swap_flag);
+    o->dll_code_err_bits = f2u(t->dll_code_err);     o->pll_code_err_bits = f2u(t->pll_code_err);
+    o->fll_old_i = t->fll_old_i;                     o->fll_old_q = t->fll_old_q;
+    o->fll_err_bits = f2u(t->fll_err);
+    COPY_OUT(pll_bad_state_cnt, t->pll_bad_state_cnt);
+    COPY_OUT(pll_bad_state_master_cnt, t->pll_bad_state_master_cnt);
+    COPY_OUT(i_part_summ, t->i_part_summ);           COPY_OUT(q_part_summ, t->q_part_summ);
+    COPY_OUT(snr_summ_cnt, t->snr_summ_cnt);         o->snr_value_bits = f2u(t->snr_value);
+    COPY_OUT(filt_start_time_ms, t->filt_start_time_ms);
+    COPY_OUT(code_filt_cnt, t->code_filt_cnt);
+    o->code_phase_fine_filt_bits = f2u(t->code_phase_fine_filt);
+    memcpy(o->pre_track_phases, t->pre_track_phases, sizeof o->pre_track_phases);
+    memcpy(o->pll_check_buf, t->pll_check_buf, sizeof o->pll_check_buf);
+
+    COPY_OUT(period_sync_ok_flag, n->period_sync_ok_flag); COPY_OUT(right_period_cnt, n->right_period_cnt);
+    COPY_OUT(old_swap_time, n->old_swap_time);       COPY_OUT(old_reminder, n->old_reminder);
+    COPY_OUT(accurate_swap_time, n->accurate_swap_time); COPY_OUT(accurate_swap_ok, n->accurate_swap_ok);
+    COPY_OUT(last_bit_pos_cnt, n->last_bit_pos_cnt); COPY_OUT(last_bit_neg_cnt, n->last_bit_neg_cnt);
+    COPY_OUT(inv_polarity_flag, n->inv_polarity_flag); COPY_OUT(polarity_found, n->polarity_found);
+    COPY_OUT(inv_preabmle_cnt, n->inv_preabmle_cnt); COPY_OUT(word_cnt, n->word_cnt);
+    COPY_OUT(word_bit_cnt, n->word_bit_cnt);         COPY_OUT(old_D29, n->old_D29);
+    COPY_OUT(old_D30, n->old_D30);
+    COPY_OUT(word_detection_timestamp, n->word_detection_timestamp);
+    COPY_OUT(word_cnt_test, n->word_cnt_test);       COPY_OUT(last_subframe_time, n->last_subframe_time);
+    COPY_OUT(first_subframe_time, n->first_subframe_time); COPY_OUT(subframe_cnt, n->subframe_cnt);
+    COPY_OUT(new_subframe_flag, n->new_subframe_flag);
+    memcpy(o->word_buf, n->word_buf, GPSB_FLAT_WORD_BITS);
+    memcpy(o->subframe_data, n->subframe_data, GPSB_FLAT_SUBFRAME_BYTES);
+}
+
+void gpsb_host_restore(gps_ch_t* ch, const struct gpsb_flat_state* s)
+{
+    gps_acq_t* a = &ch->acq_data;
+    gps_tracking_t* t = &ch->tracking_data;
+    gps_nav_data_t* n = &ch->nav_data;
+    a->state = (gps_acq_state_t)s->acq_state;        a->freq_index = (uint8_t)s->freq_index;
+    a->found_freq_offset_hz = (int16_t)s->found_freq_offset_hz;
+    a->given_freq_offset_hz = (int16_t)s->given_freq_offset_hz;
+    a->found_code_phase = (uint16_t)s->found_code_phase;
+    a->code_search_start = (uint16_t)s->acq_code_search_start;
+    a->code_search_stop = (uint16_t)s->acq_code_search_stop;
+    a->code_hist_step = (uint16_t)s->code_hist_step; a->start_timestamp = s->acq_start_timestamp;
+    a->hist_ratio = u2f(s->hist_ratio_bits);
+    memcpy(a->code_phase_histogram, s->code_phase_histogram, GPSB_FLAT_HIST_SIZE);
+
+    t->state = (gps_tracking_state_t)s->trk_state;
+    t->code_search_start = (uint16_t)s->trk_code_search_start;
+    t->code_search_stop = (uint16_t)s->trk_code_search_stop;
+    t->if_freq_offset_hz = u2f(s->if_freq_offset_hz_bits);
+    t->if_freq_accum = s->if_freq_accum;             t->pre_track_count = (uint8_t)s->pre_track_count;
+    t->prev_track_timestamp = s->prev_track_timestamp;
+    t->code_phase_fine = u2f(s->code_phase_fine_bits);
+    t->old_code_phase_fine = u2f(s->old_code_phase_fine_bits);
+    t->code_phase_swap_flag = (uint8_t)s->code_phase_swap_flag;
+    t->dll_code_err = u2f(s->dll_code_err_bits);     t->pll_code_err = u2f(s->pll_code_err_bits);
+    t->fll_old_i = (int16_t)s->fll_old_i;            t->fll_old_q = (int16_t)s->fll_old_q;
+    t->fll_err = u2f(s->fll_err_bits);
+    t->pll_bad_state_cnt = (uint8_t)s->pll_bad_state_cnt;
+    t->pll_bad_state_master_cnt = (uint16_t)s->pll_bad_state_master_cnt;
+    t->i_part_summ = s->i_part_summ;                 t->q_part_summ = s->q_part_summ;
+    t->snr_summ_cnt = (uint16_t)s->snr_summ_cnt;     t->snr_value = u2f(s->snr_value_bits);
+    t->filt_start_time_ms = s->filt_start_time_ms;   t->code_filt_cnt = (uint16_t)s->code_filt_cnt;
+    t->code_phase_fine_filt = u2f(s->code_phase_fine_filt_bits);
+    memcpy(t->pre_track_phases, s->pre_track_phases, sizeof t->pre_track_phases);
+    memcpy(t->pll_check_buf, s->pll_check_buf, sizeof t->pll_check_buf);
+
+    n->period_sync_ok_flag = (uint8_t)s->period_sync_ok_flag; n->right_period_cnt = (uint8_t)s->right_period_cnt;
+    n->old_swap_time = s->old_swap_time;             n->old_reminder = (uint8_t)s->old_reminder;
+    n->accurate_swap_time = (uint8_t)s->accurate_swap_time; n->accurate_swap_ok = (uint8_t)s->accurate_swap_ok;
+    n->last_bit_pos_cnt = (uint8_t)s->last_bit_pos_cnt; n->last_bit_neg_cnt = (uint8_t)s->last_bit_neg_cnt;
+    n->inv_polarity_flag = (uint8_t)s->inv_polarity_flag; n->polarity_found = (uint8_t)s->polarity_found;
+    n->inv_preabmle_cnt = (uint8_t)s->inv_preabmle_cnt; n->word_cnt = (uint8_t)s->word_cnt;
+    n->word_bit_cnt = (uint8_t)s->word_bit_cnt;      n->old_D29 = (uint8_t)s->old_D29;
+    n->old_D30 = (uint8_t)s->old_D30;
+    n->word_detection_timestamp = s->word_detection_timestamp;
+    n->word_cnt_test = s->word_cnt_test;             n->last_subframe_time = s->last_subframe_time;
+    n->first_subframe_time = s->first_subframe_time; n->subframe_cnt = (uint16_t)s->subframe_cnt;
+    n->new_subframe_flag = (uint8_t)s->new_subframe_flag;
+    memcpy(n->word_buf, s->word_buf, GPSB_FLAT_WORD_BITS);
+    memcpy(n->subframe_data, s->subframe_data, GPSB_FLAT_SUBFRAME_BYTES);
+}
+
+/* Channel array helpers for language bindings that cannot lay out gps_ch_t themselves. */
+gps_ch_t* gpsb_host_channels_alloc(uint32_t n) { return (gps_ch_t*)calloc(n, sizeof(gps_ch_t)); }
+void gpsb_host_channels_free(gps_ch_t* p) { free(p); }
+gps_ch_t* gpsb_host_channel_at(gps_ch_t* base, uint32_t i) { return base + i; }
+void gpsb_host_channel_init(gps_ch_t* ch, uint32_t prn, int32_t given_freq_offset_hz)
+{
+    memset(ch, 0, sizeof *ch);
+    ch->prn = (uint8_t)prn;
+    ch->acq_data.given_freq_offset_hz = (int16_t)given_freq_offset_hz;
+    if (prn >= 1) gps_generate_prn(ch->prn_code, (int)prn);
+}
+const uint8_t* gpsb_host_channel_code(const gps_ch_t* ch) { return ch->prn_code; }
