@@ -146,6 +146,16 @@ int gpsb_sweep(gpsb_ctx* ctx, const uint32_t* sv_slots, uint32_t n_sv, const uin
                uint32_t n_bins, uint32_t ms0, uint32_t n_ms, uint32_t off_bits,
                gpsb_search_res* res);
 
+/* Two interchangeable, bit-identical implementations of the wide-window search (north_star: "batched
+ * direct correlator or ... chosen by measurement"):
+ *   GPSB_SWEEP_DIRECT  XOR + POPC per 32 samples for every offset (POPC-pipe bound)
+ *   GPSB_SWEEP_DP4A    per-byte popcounts once per millisecond, then a +-1-chip x small-integer circular
+ *                      correlation on the integer dot-product pipe (default; about 8x fewer issue slots)
+ * Applies to gpsb_sweep / gpsb_sweep_dev and to gpsb_search requests whose window is >= 384 offsets. */
+#define GPSB_SWEEP_DIRECT 0
+#define GPSB_SWEEP_DP4A   1
+int gpsb_set_sweep_method(gpsb_ctx* ctx, int method);
+
 /* ---- device-resident variants: request / result arrays already in device memory, enqueued on the
  *      context stream without synchronising.  Used for kernel-only timing and for results that are
  *      gathered across GPUs (NCCL) before they are read. */

@@ -23,18 +23,42 @@
 
 #include "gpsb_kernels.cuh"
 
+namespace gpsb {
+struct SweepParams {
+    const uint32_t* sv_slots;
+    const uint32_t* step32;
+    uint32_t n_bins, ms0, n_ms, off_bits;
+};
+}  // namespace gpsb
+
+#include "gpsb_acq_dp4a.cuh"
+
 using namespace gpsb;
 
 /* ============================================================================ kernels ========= */
 
 // chips[1023] (0/1 bytes) -> E[512]; E[w] low half = chip 2w, high half = chip 2w+1 (0xFFFF each).
-__global__ void k_expand_code(const uint8_t* __restrict__ chips, uint32_t* __restrict__ E)
+// S[k] (optional) = chips 4k..4k+3 as int8 +1 (chip 0) / -1 (chip 1), zero from chip 1022 on: the multiplier
+// table of the dp4a search, whose whole-chip sum covers chips 0..1021 (gpsb_acq_dp4a.cuh).
+__device__ __forceinline__ uint32_t signed_chip_word(const uint8_t* chips, int k)
+{
+    uint32_t v = 0;
+    for (int i = 0; i < 4; i++) {
+        const int c = 4 * k + i;
+        if (c < (int)GPSB_CHIPS - 1) v |= (chips[c] ? 0xFFu : 0x01u) << (8 * i);
+    }
+    return v;
+}
+
+__global__ void k_expand_code(const uint8_t* __restrict__ chips, uint32_t* __restrict__ E, uint32_t* __restrict__ S)
 {
     for (int w = threadIdx.x; w < kWords; w += blockDim.x) {
         uint32_t lo = chips[2 * w] ? 0x0000FFFFu : 0u;
         uint32_t hi = (2 * w + 1 < (int)GPSB_CHIPS && chips[2 * w + 1]) ? 0xFFFF0000u : 0u;
         E[w] = lo | hi;
     }
+    if (S)
+        for (int k = threadIdx.x; k < kChipSteps; k += blockDim.x) S[k] = signed_chip_word(chips, k);
 }
 
 // G2 delays per PRN (IS-GPS-200 code phase assignments as chip delays; reference table
@@ -54,7 +78,8 @@ __constant__ uint16_t c_g2_delay[210] = {
 
 // One CTA: two 10-stage LFSRs run by thread 0 (1023 serial steps), then all threads combine
 // chip[i] = G1[i] ^ G2[(i - delay) mod 1023] and expand.
-__global__ void k_gen_code(uint32_t prn, uint8_t* __restrict__ chips_out, uint32_t* __restrict__ E)
+__global__ void k_gen_code(uint32_t prn, uint8_t* __restrict__ chips_out, uint32_t* __restrict__ E,
+                           uint32_t* __restrict__ S)
 {
     __shared__ uint8_t g1[GPSB_CHIPS], g2[GPSB_CHIPS], chip[GPSB_CHIPS + 1];
     if (threadIdx.x == 0) {
@@ -81,6 +106,7 @@ __global__ void k_gen_code(uint32_t prn, uint8_t* __restrict__ chips_out, uint32
     __syncthreads();
     for (int w = threadIdx.x; w < kWords; w += blockDim.x)
         E[w] = (chip[2 * w] ? 0x0000FFFFu : 0u) | (chip[2 * w + 1] ? 0xFFFF0000u : 0u);
+    for (int k = threadIdx.x; k < kChipSteps; k += blockDim.x) S[k] = signed_chip_word(chip, k);
 }
 
 // E table -> chips (inverse of k_expand_code, for read-back).
@@ -171,12 +197,6 @@ k_epl(const gpsb_epl_req* __restrict__ reqs, int16_t* __restrict__ out,
 }
 
 // ---------------------------------------------------------------------------------- search
-struct SweepParams {
-    const uint32_t* sv_slots;
-    const uint32_t* step32;
-    uint32_t n_bins, ms0, n_ms, off_bits;
-};
-
 // Block-wide (max key, sum) reduction; result valid in thread 0.
 __device__ __forceinline__ void block_reduce_search(uint32_t& key, int& total, uint32_t* sk, int* st)
 {
@@ -235,7 +255,7 @@ __device__ __forceinline__ void search_window(const CellSmem& s, uint32_t start,
 template <bool kSweep>
 __global__ void __launch_bounds__(kSearchThreads)
 k_search(const gpsb_search_req* __restrict__ reqs, SweepParams sp, gpsb_search_res* __restrict__ res,
-         int16_t* __restrict__ iq, const uint32_t* __restrict__ codes,
+         const uint32_t* __restrict__ res_map, int16_t* __restrict__ iq, const uint32_t* __restrict__ codes,
          const uint32_t* __restrict__ signal, uint32_t ring_ms)
 {
     __shared__ CellSmem s;
@@ -265,7 +285,7 @@ k_search(const gpsb_search_req* __restrict__ reqs, SweepParams sp, gpsb_search_r
     stage_mix(s.I, s.Q, signal + (size_t)(rq.ms_index % ring_ms) * kWords, rq.acc0, rq.step32, tid,
               kSearchThreads);
     extend_period<kSearchThreads>(s.I, s.Q, tid);
-    search_window(s, rq.start, rq.stop, res + blockIdx.x, iq, sk, st);
+    search_window(s, rq.start, rq.stop, res + (res_map ? res_map[blockIdx.x] : blockIdx.x), iq, sk, st);
 }
 
 // ---------------------------------------------------------------------------------- level 0
@@ -332,6 +352,8 @@ struct gpsb_ctx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     uint32_t* d_codes = nullptr;   // max_sv x 512 words
+    uint32_t* d_schips = nullptr;  // max_sv x 256 words: +-1 chip bytes for the dp4a search
+    int sweep_method = GPSB_SWEEP_DP4A;
     uint8_t* d_code_set = nullptr; // not used on device; host mirror below
     uint8_t* code_set = nullptr;   // host: slot has a code
     uint32_t* d_signal = nullptr;  // ring_ms x 512 words
@@ -404,6 +426,14 @@ int gpsb_create(gpsb_ctx** out, int device, uint32_t max_sv, uint32_t ring_ms)
     c->stream = c->own_stream;
     CU(cudaMalloc(&c->d_codes, (size_t)max_sv * kWords * 4));
     CU(cudaMemset(c->d_codes, 0, (size_t)max_sv * kWords * 4));
+    CU(cudaMalloc(&c->d_schips, (size_t)max_sv * kChipSteps * 4));
+    CU(cudaMemset(c->d_schips, 0, (size_t)max_sv * kChipSteps * 4));
+    CU(cudaFuncSetAttribute(k_acq_dp4a<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AcqSmem<8>)));
+    CU(cudaFuncSetAttribute(k_acq_dp4a<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AcqSmem<8>)));
+    CU(cudaFuncSetAttribute(k_acq_dp4a<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AcqSmem<4>)));
+    CU(cudaFuncSetAttribute(k_acq_dp4a<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AcqSmem<4>)));
+    CU(cudaFuncSetAttribute(k_acq_dp4a<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AcqSmem<1>)));
+    CU(cudaFuncSetAttribute(k_acq_dp4a<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AcqSmem<1>)));
     CU(cudaMalloc(&c->d_signal, (size_t)ring_ms * GPSB_FRAME_BYTES));
     CU(cudaMemset(c->d_signal, 0, (size_t)ring_ms * GPSB_FRAME_BYTES));
     CU(cudaMalloc(&c->d_chips, 1024));
@@ -430,6 +460,7 @@ void gpsb_destroy(gpsb_ctx* c)
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->d_stage) cudaFree(c->d_stage);
     if (c->d_codes) cudaFree(c->d_codes);
+    if (c->d_schips) cudaFree(c->d_schips);
     if (c->d_signal) cudaFree(c->d_signal);
     if (c->d_chips) cudaFree(c->d_chips);
     if (c->d_l0) cudaFree(c->d_l0);
@@ -481,7 +512,8 @@ int gpsb_set_code(gpsb_ctx* c, uint32_t slot, const uint8_t chips[GPSB_CHIPS])
     if (slot >= c->max_sv) return fail(GPSB_ERR_ARG, "sv_slot %u out of range (max_sv %u)", slot, c->max_sv);
     CU(cudaSetDevice(c->device));
     CU(cudaMemcpyAsync(c->d_chips, chips, GPSB_CHIPS, cudaMemcpyHostToDevice, c->stream));
-    k_expand_code<<<1, 256, 0, c->stream>>>(c->d_chips, c->d_codes + (size_t)slot * kWords);
+    k_expand_code<<<1, 256, 0, c->stream>>>(c->d_chips, c->d_codes + (size_t)slot * kWords,
+                                            c->d_schips + (size_t)slot * kChipSteps);
     int rc = check_launch(c, "k_expand_code");
     if (rc) return rc;
     CU(cudaStreamSynchronize(c->stream));
@@ -495,7 +527,8 @@ int gpsb_set_code_prn(gpsb_ctx* c, uint32_t slot, uint32_t prn)
     if (slot >= c->max_sv) return fail(GPSB_ERR_ARG, "sv_slot %u out of range (max_sv %u)", slot, c->max_sv);
     if (prn < 1 || prn > 210) return fail(GPSB_ERR_ARG, "prn %u out of range 1..210", prn);
     CU(cudaSetDevice(c->device));
-    k_gen_code<<<1, 256, 0, c->stream>>>(prn, c->d_chips, c->d_codes + (size_t)slot * kWords);
+    k_gen_code<<<1, 256, 0, c->stream>>>(prn, c->d_chips, c->d_codes + (size_t)slot * kWords,
+                                         c->d_schips + (size_t)slot * kChipSteps);
     int rc = check_launch(c, "k_gen_code");
     if (rc) return rc;
     CU(cudaStreamSynchronize(c->stream));
@@ -643,10 +676,14 @@ int gpsb_search_dev(gpsb_ctx* c, uint32_t n, const gpsb_search_req* d_req, gpsb_
     if (n == 0) return GPSB_OK;
     CU(cudaSetDevice(c->device));
     SweepParams sp = {};
-    k_search<false><<<n, kSearchThreads, 0, c->stream>>>(d_req, sp, d_res, nullptr, c->d_codes, c->d_signal,
+    k_search<false><<<n, kSearchThreads, 0, c->stream>>>(d_req, sp, d_res, nullptr, nullptr, c->d_codes, c->d_signal,
                                                          c->ring_ms);
     return check_launch(c, "k_search");
 }
+
+// Requests whose window is at least this wide go through the dp4a kernel (which always evaluates all
+// 2046 offsets at a cost of about 2046/8 direct offsets per satellite); narrower ones stay direct.
+static const uint32_t kWideWindow = 384;
 
 int gpsb_search(gpsb_ctx* c, uint32_t n, const gpsb_search_req* req, gpsb_search_res* res)
 {
@@ -655,19 +692,83 @@ int gpsb_search(gpsb_ctx* c, uint32_t n, const gpsb_search_req* req, gpsb_search
     int rc = check_search(c, n, req);
     if (rc) return rc;
     CU(cudaSetDevice(c->device));
-    size_t req_b = (size_t)n * sizeof(gpsb_search_req), res_b = (size_t)n * sizeof(gpsb_search_res);
-    size_t res_off = (req_b + 255) & ~(size_t)255;
+    // staging layout: [direct requests][direct index map][groups][results by original index]
+    const size_t req_b = (size_t)n * sizeof(gpsb_search_req), map_b = (size_t)n * 4;
+    const size_t grp_b = (size_t)n * sizeof(AcqGroup), res_b = (size_t)n * sizeof(gpsb_search_res);
+    const size_t map_off = (req_b + 255) & ~(size_t)255;
+    const size_t grp_off = (map_off + map_b + 255) & ~(size_t)255;
+    const size_t res_off = (grp_off + grp_b + 255) & ~(size_t)255;
     rc = ensure_stage(c, res_off + res_b);
     if (rc) return rc;
-    memcpy(c->h_stage, req, req_b);
-    CU(cudaMemcpyAsync(c->d_stage, c->h_stage, req_b, cudaMemcpyHostToDevice, c->stream));
-    rc = gpsb_search_dev(c, n, (const gpsb_search_req*)c->d_stage,
-                         (gpsb_search_res*)((uint8_t*)c->d_stage + res_off));
-    if (rc) return rc;
-    CU(cudaMemcpyAsync((uint8_t*)c->h_stage + res_off, (uint8_t*)c->d_stage + res_off, res_b,
-                       cudaMemcpyDeviceToHost, c->stream));
+    uint8_t* h = (uint8_t*)c->h_stage;
+    gpsb_search_req* h_req = (gpsb_search_req*)h;
+    uint32_t* h_map = (uint32_t*)(h + map_off);
+    AcqGroup* h_grp = (AcqGroup*)(h + grp_off);
+    uint32_t n_direct = 0, n_grp = 0, max_in_group = 0;
+    memset(h + res_off, 0, res_b);              // empty windows (start >= stop) report max 0, phase 0, avg 0
+    for (uint32_t i = 0; i < n; i++) {
+        const gpsb_search_req& r = req[i];
+        if (r.start >= r.stop) continue;
+        const bool wide = c->sweep_method == GPSB_SWEEP_DP4A && (uint32_t)(r.stop - r.start) >= kWideWindow;
+        if (!wide) {
+            h_req[n_direct] = r;
+            h_map[n_direct++] = i;
+            continue;
+        }
+        AcqGroup* g = n_grp ? &h_grp[n_grp - 1] : nullptr;
+        if (!g || g->n_sv >= 8 || g->ms_index != r.ms_index || g->acc0 != r.acc0 || g->step32 != r.step32 ||
+            g->off_bits != r.off_bits) {
+            g = &h_grp[n_grp++];
+            memset(g, 0, sizeof *g);
+            g->ms_index = r.ms_index;
+            g->acc0 = r.acc0;
+            g->step32 = r.step32;
+            g->off_bits = r.off_bits;
+        }
+        g->sv_slot[g->n_sv] = r.sv_slot;
+        g->start[g->n_sv] = r.start;
+        g->stop[g->n_sv] = r.stop;
+        g->res_index[g->n_sv] = i;
+        g->n_sv++;
+        if (g->n_sv > max_in_group) max_in_group = g->n_sv;
+    }
+    CU(cudaMemcpyAsync(c->d_stage, c->h_stage, res_off + res_b, cudaMemcpyHostToDevice, c->stream));
+    uint8_t* d = (uint8_t*)c->d_stage;
+    gpsb_search_res* d_res = (gpsb_search_res*)(d + res_off);
+    if (n_direct) {
+        SweepParams sp = {};
+        k_search<false><<<n_direct, kSearchThreads, 0, c->stream>>>((const gpsb_search_req*)d, sp, d_res,
+                                                                   (const uint32_t*)(d + map_off), nullptr,
+                                                                   c->d_codes, c->d_signal, c->ring_ms);
+        rc = check_launch(c, "k_search");
+        if (rc) return rc;
+    }
+    if (n_grp) {
+        SweepParams sp = {};
+        const AcqGroup* dg = (const AcqGroup*)(d + grp_off);
+        if (max_in_group > 4)
+            k_acq_dp4a<8, false><<<n_grp, kAcqThreads, sizeof(AcqSmem<8>), c->stream>>>(
+                dg, sp, 0, d_res, c->d_codes, c->d_schips, c->d_signal, c->ring_ms);
+        else if (max_in_group > 1)
+            k_acq_dp4a<4, false><<<n_grp, kAcqThreads, sizeof(AcqSmem<4>), c->stream>>>(
+                dg, sp, 0, d_res, c->d_codes, c->d_schips, c->d_signal, c->ring_ms);
+        else
+            k_acq_dp4a<1, false><<<n_grp, kAcqThreads, sizeof(AcqSmem<1>), c->stream>>>(
+                dg, sp, 0, d_res, c->d_codes, c->d_schips, c->d_signal, c->ring_ms);
+        rc = check_launch(c, "k_acq_dp4a");
+        if (rc) return rc;
+    }
+    CU(cudaMemcpyAsync(h + res_off, d + res_off, res_b, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    memcpy(res, (uint8_t*)c->h_stage + res_off, res_b);
+    memcpy(res, h + res_off, res_b);
+    return GPSB_OK;
+}
+
+int gpsb_set_sweep_method(gpsb_ctx* c, int method)
+{
+    if (!c) return fail(GPSB_ERR_ARG, "null context");
+    if (method != GPSB_SWEEP_DIRECT && method != GPSB_SWEEP_DP4A) return fail(GPSB_ERR_ARG, "unknown sweep method %d", method);
+    c->sweep_method = method;
     return GPSB_OK;
 }
 
@@ -686,7 +787,7 @@ int gpsb_search_iq(gpsb_ctx* c, const gpsb_search_req* req, int16_t* iq)
     CU(cudaMemcpyAsync(c->d_stage, c->h_stage, sizeof *req, cudaMemcpyHostToDevice, c->stream));
     SweepParams sp = {};
     k_search<false><<<1, kSearchThreads, 0, c->stream>>>(
-        (const gpsb_search_req*)c->d_stage, sp, (gpsb_search_res*)((uint8_t*)c->d_stage + res_off),
+        (const gpsb_search_req*)c->d_stage, sp, (gpsb_search_res*)((uint8_t*)c->d_stage + res_off), nullptr,
         (int16_t*)((uint8_t*)c->d_stage + iq_off), c->d_codes, c->d_signal, c->ring_ms);
     rc = check_launch(c, "k_search(iq)");
     if (rc) return rc;
@@ -707,9 +808,27 @@ int gpsb_sweep_dev(gpsb_ctx* c, const uint32_t* d_sv_slots, uint32_t n_sv, const
     if (cells > 0x7FFFFFFFull) return fail(GPSB_ERR_ARG, "sweep of %llu cells is too large", (unsigned long long)cells);
     CU(cudaSetDevice(c->device));
     SweepParams sp = {d_sv_slots, d_step32, n_bins, ms0, n_ms, off_bits};
-    k_search<true><<<(uint32_t)cells, kSearchThreads, 0, c->stream>>>(nullptr, sp, d_res, nullptr, c->d_codes,
-                                                                    c->d_signal, c->ring_ms);
-    return check_launch(c, "k_search(sweep)");
+    if (c->sweep_method == GPSB_SWEEP_DIRECT) {
+        k_search<true><<<(uint32_t)cells, kSearchThreads, 0, c->stream>>>(nullptr, sp, d_res, nullptr, nullptr,
+                                                                        c->d_codes, c->d_signal, c->ring_ms);
+        return check_launch(c, "k_search(sweep)");
+    }
+    // byte-popcount / dp4a search: one CTA per (bin, ms) x tile of up to 8 satellites
+    const uint32_t groups = n_bins * n_ms;
+    if (n_sv > 4) {
+        dim3 grid(groups, (n_sv + 7) / 8);
+        k_acq_dp4a<8, true><<<grid, kAcqThreads, sizeof(AcqSmem<8>), c->stream>>>(
+            nullptr, sp, n_sv, d_res, c->d_codes, c->d_schips, c->d_signal, c->ring_ms);
+    } else if (n_sv > 1) {
+        dim3 grid(groups, 1);
+        k_acq_dp4a<4, true><<<grid, kAcqThreads, sizeof(AcqSmem<4>), c->stream>>>(
+            nullptr, sp, n_sv, d_res, c->d_codes, c->d_schips, c->d_signal, c->ring_ms);
+    } else {
+        dim3 grid(groups, 1);
+        k_acq_dp4a<1, true><<<grid, kAcqThreads, sizeof(AcqSmem<1>), c->stream>>>(
+            nullptr, sp, n_sv, d_res, c->d_codes, c->d_schips, c->d_signal, c->ring_ms);
+    }
+    return check_launch(c, "k_acq_dp4a(sweep)");
 }
 
 int gpsb_sweep(gpsb_ctx* c, const uint32_t* sv_slots, uint32_t n_sv, const uint32_t* step32, uint32_t n_bins,
@@ -750,7 +869,7 @@ int gpsb_l0_generate_prn_data2(gpsb_ctx* c, const uint8_t chips[GPSB_CHIPS], uin
     uint32_t* E = c->d_l0;
     uint32_t* R = c->d_l0 + kWords;
     CU(cudaMemcpyAsync(c->d_chips, chips, GPSB_CHIPS, cudaMemcpyHostToDevice, c->stream));
-    k_expand_code<<<1, 256, 0, c->stream>>>(c->d_chips, E);
+    k_expand_code<<<1, 256, 0, c->stream>>>(c->d_chips, E, nullptr);
     int rc = check_launch(c, "k_expand_code");
     if (rc) return rc;
     k_l0_replica<<<1, 256, 0, c->stream>>>(E, offset_bits, R);

@@ -80,6 +80,7 @@ def load_library(path: Path | None = None) -> C.CDLL:
         "gpsb_search": (i32, [vp, u32, vp, vp]),
         "gpsb_search_iq": (i32, [vp, vp, vp]),
         "gpsb_sweep": (i32, [vp, vp, u32, vp, u32, u32, u32, u32, vp]),
+        "gpsb_set_sweep_method": (i32, [vp, i32]),
         "gpsb_track_epl_dev": (i32, [vp, u32, vp, vp]),
         "gpsb_search_dev": (i32, [vp, u32, vp, vp]),
         "gpsb_sweep_dev": (i32, [vp, vp, u32, vp, u32, u32, u32, u32, vp]),
@@ -225,6 +226,10 @@ class Engine:
         res = np.zeros((sv.size, st.size, n_ms), SEARCH_RES)
         self._check(self.lib.gpsb_sweep(self._ctx, _p(sv), sv.size, _p(st), st.size, ms0, n_ms, off_bits, _p(res)))
         return res
+
+    def set_sweep_method(self, method: int) -> None:
+        """0 = direct XOR/popcount, 1 = byte-popcount dp4a correlation (default)."""
+        self._check(self.lib.gpsb_set_sweep_method(self._ctx, method))
 
     # device-resident variants: raw device pointers (ints), asynchronous on the context stream
     def track_epl_dev(self, n: int, d_req: int, d_out: int) -> None:

@@ -48,3 +48,15 @@ def engine():
     eng = Engine(device=0, max_sv=40, ring_ms=256)
     yield eng
     eng.close()
+
+
+@pytest.fixture(scope="session")
+def host_engine():
+    """Engine sized for the host-side mirror: satellite slot == PRN (1..210), 1 s signal ring."""
+    from stm32f4_sdr_gps_b200 import Engine, load_host_library
+    eng = Engine(device=0, max_sv=211, ring_ms=1024)
+    lib = load_host_library()
+    assert lib.gpsb_host_attach(eng.handle) == 0
+    yield eng
+    lib.gpsb_host_attach(None)
+    eng.close()

@@ -258,3 +258,43 @@ def test_ring_wraparound_and_errors(engine):
     rq["sv_slot"] = 39                            # slot never given a code
     with pytest.raises(GpsbError):
         engine.track_epl(rq)
+
+
+def test_dp4a_and_direct_search_agree_all_bit_shifts(engine, oracle):
+    """The two wide-window implementations (include/gpsb.h GPSB_SWEEP_*) are bit-identical, for every
+    sub-byte replica shift, on random data, an all-ones and an all-zero millisecond; a sample of cells is
+    also checked against the oracle."""
+    rng = np.random.default_rng(21)
+    sig = rng.integers(0, 256, (6, 2046), dtype=np.uint8)
+    sig[4] = 0xFF
+    sig[5] = 0
+    engine.upload_signal(40, sig)
+    prns = [1, 6, 13, 17, 22, 26, 29, 30, 32]           # 9 satellites: one full tile of 8 + a tile of 1
+    for s, prn in enumerate(prns):
+        engine.set_code_prn(s, prn)
+    step = np.array([nco_step32(np.float32(IF_HZ + d)) for d in (-4500, 0, 2250)], np.uint32)
+    for bits in range(16):
+        engine.set_sweep_method(1)
+        a = engine.sweep(np.arange(9), step, 40, 6, bits)
+        engine.set_sweep_method(0)
+        b = engine.sweep(np.arange(9), step, 40, 6, bits)
+        engine.set_sweep_method(1)
+        assert np.array_equal(a, b), bits
+        if bits in (0, 5, 15):
+            for (s, k, m) in ((0, 0, 0), (8, 2, 3), (4, 1, 4), (7, 2, 5)):
+                f = float(np.float32(IF_HZ + (-4500, 0, 2250)[k]))
+                want = oracle.search_cell(oracle.ca_code(prns[s]), sig[m], f, bits, 0, 2046)
+                assert (a["max"][s, k, m], a["phase"][s, k, m], a["avg"][s, k, m]) == want, (bits, s, k, m)
+    # grouped host requests: same millisecond / NCO, different satellites and windows, mixed with narrow ones
+    rq = np.zeros(12, SEARCH_REQ)
+    for i in range(12):
+        rq[i] = (i % 9, 40 + (i // 6), 0, step[1], 2, 0 if i % 3 else 100, 2046 if i % 4 else 1500, 0)
+    rq[5]["start"], rq[5]["stop"] = 700, 730              # narrow: direct kernel
+    rq[7]["start"], rq[7]["stop"] = 30, 30                # empty
+    res = engine.search(rq)
+    for i in range(12):
+        want = oracle.search_cell(oracle.ca_code(prns[i % 9]), sig[i // 6], float(np.float32(IF_HZ)), 2,
+                                  int(rq[i]["start"]), int(rq[i]["stop"]))
+        if rq[i]["start"] >= rq[i]["stop"]:
+            want = (0, 0, 0)
+        assert (res["max"][i], res["phase"][i], res["avg"][i]) == want, i
