@@ -80,7 +80,7 @@ def truth_requests(scene, nco_step32):
         tau = (sat.code_phase_samples - m * MS_SAMPLES * sat.doppler_hz / 1_575_420_000.0) % MS_SAMPLES
         fine = np.floor(tau).astype(np.int64)
         p = fine // 8
-        rq["sv_slot"][:, s] = s
+        rq["sv_slot"][:, s] = sat.prn             # satellite slot == PRN, as the host-side mirror uses them
         rq["ms_index"][:, s] = np.arange(scene.n_ms)
         rq["acc0"][:, s] = (np.arange(scene.n_ms, dtype=np.uint64) * 511 * step32) & 0xFFFFFFFF
         rq["step32"][:, s] = step32
@@ -233,11 +233,28 @@ def run_reference_arm(args) -> None:
 
 
 # ----------------------------------------------------------------------------- own arm (GPU)
+def arm_locked(channels, scene):
+    """Channels start locked on the true Doppler / code phase (GPS_ACQ_DONE, GPS_TRACKING_RUN) so that every
+    millisecond is an E/P/L integrate-and-dump step - the same start the reference arm gets."""
+    for i, sat in enumerate(scene.sats):
+        st = channels.snapshot(i)
+        for name, _ in st._fields_:
+            if name not in ("prn",):
+                v = getattr(st, name)
+                if not hasattr(v, "__len__"):
+                    setattr(st, name, 0)
+        st.acq_state, st.trk_state = 9, 4
+        st.found_freq_offset_hz = int(round(sat.doppler_hz / 500.0) * 500)
+        st.if_freq_offset_hz_bits = int(np.float32(sat.doppler_hz).view(np.uint32))
+        st.code_phase_fine_bits = int(np.float32(sat.code_phase_samples).view(np.uint32))
+        channels.restore(i, st)
+
+
 def run_gpu_arm(args) -> None:
     import torch
     import torch.distributed as dist
 
-    from stm32f4_sdr_gps_b200 import SEARCH_RES, Engine, nco_step32
+    from stm32f4_sdr_gps_b200 import Channels, Engine, Receiver, nco_step32
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -248,17 +265,14 @@ def run_gpu_arm(args) -> None:
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
+    steps, warm = args.steps, max(3, args.warmup)
 
     scene = make_scene(rank, N_MS)
     sig = cached_signal("trk_r%d_%d" % (rank, N_MS), scene)
-    eng = Engine(device=local_rank, max_sv=max(ACQ_SV, N_SV_PER_GPU), ring_ms=N_MS + 24)
+    eng = Engine(device=local_rank, max_sv=211, ring_ms=N_MS + 24)
     stream = torch.cuda.Stream(device=dev)       # a real (non-default) stream shared by torch events and the engine
     torch.cuda.set_stream(stream)
     eng.set_stream(stream.cuda_stream)
-    for s, sat in enumerate(scene.sats):
-        eng.set_code_prn(s, sat.prn)
-    rq, fo, fine = truth_requests(scene, nco_step32)
-    n_cells = rq.size
 
     def barrier():
         torch.cuda.synchronize()
@@ -266,84 +280,136 @@ def run_gpu_arm(args) -> None:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def events(n):
+        return [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
 
-    # ---- device-resident leg (value)
-    eng.upload_signal(0, sig)
-    d_rq = torch.from_numpy(rq.view(np.uint8).copy()).to(dev)
-    d_out = torch.zeros(n_cells * 6, dtype=torch.int16, device=dev)
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    for _ in range(max(3, args.warmup)):
-        eng.track_epl_dev(n_cells, d_rq.data_ptr(), d_out.data_ptr())
+    # ---- closed-loop tracking through the host-side mirror (the drop-in path): value and e2e
+    channels = Channels([s.prn for s in scene.sats])
+    rx = Receiver(eng, channels)
+    pinned_sig = torch.from_numpy(sig.copy()).pin_memory()
+    eng.upload_signal(0, pinned_sig.numpy())
+    for _ in range(warm):
+        arm_locked(channels, scene)
+        rx.track_run(0, N_MS, log=False)
     barrier()
     clocks = ClockSampler(local_rank)
     launches0 = eng.launch_count
-    for k in range(args.steps):
+    ev = events(steps)
+    wall0 = time.perf_counter()
+    for k in range(steps):
+        arm_locked(channels, scene)
         flush.fill_(k)                       # evict L2 between timed iterations (not timed)
+        ev[k][0].record(stream)
+        rx.track_run(0, N_MS, log=False)
+        ev[k][1].record(stream)
+    barrier()
+    wall_loop = time.perf_counter() - wall0
+    t_dev = float(np.sum([a.elapsed_time(b) for a, b in ev])) / 1e3
+    launches_value = eng.launch_count - launches0
+    final_fine = [np.uint32(channels.snapshot(i).code_phase_fine_bits).view(np.float32) for i in range(channels.n)]
+
+    ev = events(steps)
+    for k in range(steps):
+        arm_locked(channels, scene)
+        flush.fill_(k)
+        ev[k][0].record(stream)
+        eng.upload_signal(0, pinned_sig.numpy())          # host buffer -> HBM ring, inside the timed region
+        iq_log, nav_log = rx.track_run(0, N_MS, log=True)   # per-ms sums and nav bits land in host arrays
+        ev[k][1].record(stream)
+    barrier()
+    t_e2e = float(np.sum([a.elapsed_time(b) for a, b in ev])) / 1e3
+    launches = eng.launch_count - launches0
+
+    # ---- the dominant kernel of that loop (k_epl_rt, N_SV cells per launch): average launch duration
+    from stm32f4_sdr_gps_b200 import EPL_REQ
+    rq_all, _, _ = truth_requests(scene, nco_step32)
+    rq_ms = rq_all.reshape(N_MS, -1)
+    n_probe = 200
+    pe = events(1)
+    for m in range(20):
+        eng.track_epl(rq_ms[m])
+    barrier()
+    t0 = time.perf_counter()
+    pe[0][0].record(stream)
+    for m in range(n_probe):
+        eng.track_epl(rq_ms[m])
+    pe[0][1].record(stream)
+    barrier()
+    rtt_us = (time.perf_counter() - t0) / n_probe * 1e6
+    rt_kernel_ms = pe[0][0].elapsed_time(pe[0][1]) / n_probe      # upper bound: includes launch gaps
+
+    # ---- open-loop batch replay of the same 4000 cells in ONE launch (kernel-level throughput)
+    n_cells = rq_all.size
+    d_rq = torch.from_numpy(rq_all.view(np.uint8).copy()).to(dev)
+    d_out = torch.zeros(n_cells * 6, dtype=torch.int16, device=dev)
+    for _ in range(warm):
+        eng.track_epl_dev(n_cells, d_rq.data_ptr(), d_out.data_ptr())
+    barrier()
+    ev = events(steps)
+    for k in range(steps):
+        flush.fill_(k)
         ev[k][0].record(stream)
         eng.track_epl_dev(n_cells, d_rq.data_ptr(), d_out.data_ptr())
         ev[k][1].record(stream)
     barrier()
-    dev_ms = [a.elapsed_time(b) for a, b in ev]
-    t_dev = float(np.sum(dev_ms)) / 1e3
-    kernel_ms = float(np.mean(dev_ms))
-    out_dev = d_out.cpu().numpy().reshape(n_cells, 6)
+    batch_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
 
-    # ---- end-to-end leg through the C ABI with host buffers
-    pinned_sig = torch.from_numpy(sig.copy()).pin_memory()
-    e2e_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    for _ in range(max(3, args.warmup)):
-        eng.upload_signal(0, pinned_sig.numpy())
-        out_host = eng.track_epl(rq)
-    barrier()
-    for k in range(args.steps):
-        flush.fill_(k)
-        e2e_ev[k][0].record(stream)
-        eng.upload_signal(0, pinned_sig.numpy())
-        out_host = eng.track_epl(rq)
-        e2e_ev[k][1].record(stream)
-    barrier()
-    launches = eng.launch_count - launches0
-    t_e2e = float(np.sum([a.elapsed_time(b) for a, b in e2e_ev])) / 1e3
-    assert np.array_equal(out_host, out_dev), "host-buffer and device-resident legs disagree"
-
-    # ---- cold acquisition (secondary metric, rank-sharded over SVs x bins)
+    # ---- cold acquisition (secondary metric, satellites sharded over ranks)
     from stm32f4_sdr_gps_b200.signal_synth import config3_scene
     acq_scene = config3_scene(n_ms=ACQ_MS)
     acq_sig = cached_signal("acq_%d" % ACQ_MS, acq_scene)
     for prn in range(1, ACQ_SV + 1):
-        eng.set_code_prn(prn - 1, prn)
+        eng.set_code_prn(prn, prn)
     eng.upload_signal(N_MS, acq_sig)                    # frames N_MS .. N_MS+9 of the ring
     step = np.array([nco_step32(np.float32(IF_HZ - 5000 + 500 * b)) for b in range(ACQ_BINS)], np.uint32)
-    my_sv = np.arange(ACQ_SV, dtype=np.uint32)[rank::world].copy()
+    my_sv = np.arange(1, ACQ_SV + 1, dtype=np.uint32)[rank::world].copy()
     d_sv = torch.from_numpy(my_sv.view(np.int32)).to(dev)
     d_step = torch.from_numpy(step.view(np.int32)).to(dev)
     n_acq_cells = my_sv.size * ACQ_BINS * ACQ_MS
     d_res = torch.zeros(n_acq_cells * 4, dtype=torch.int16, device=dev)
-    acq_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    for _ in range(3):
-        eng.sweep_dev(d_sv.data_ptr(), my_sv.size, d_step.data_ptr(), ACQ_BINS, N_MS, ACQ_MS, 0, d_res.data_ptr())
-    barrier()
-    for k in range(args.steps):
-        flush.fill_(k)
-        acq_ev[k][0].record(stream)
-        eng.sweep_dev(d_sv.data_ptr(), my_sv.size, d_step.data_ptr(), ACQ_BINS, N_MS, ACQ_MS, 0, d_res.data_ptr())
-        acq_ev[k][1].record(stream)
-    barrier()
-    acq_ms = float(np.mean([a.elapsed_time(b) for a, b in acq_ev]))
-    t0 = time.perf_counter()
-    res_host = eng.sweep(my_sv, step, N_MS, ACQ_MS, 0)
-    acq_e2e_ms = (time.perf_counter() - t0) * 1e3
+    acq_ms = {}
+    for method, name in ((0, "direct"), (1, "dp4a")):
+        eng.set_sweep_method(method)
+        for _ in range(3):
+            eng.sweep_dev(d_sv.data_ptr(), my_sv.size, d_step.data_ptr(), ACQ_BINS, N_MS, ACQ_MS, 0, d_res.data_ptr())
+        barrier()
+        ev = events(steps)
+        for k in range(steps):
+            flush.fill_(k)
+            ev[k][0].record(stream)
+            eng.sweep_dev(d_sv.data_ptr(), my_sv.size, d_step.data_ptr(), ACQ_BINS, N_MS, ACQ_MS, 0, d_res.data_ptr())
+            ev[k][1].record(stream)
+        barrier()
+        acq_ms[name] = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    # end to end: host signal in, all-channel Doppler votes out (upload + sweep + D2H + host chain votes)
+    acq_ch = Channels([int(p) for p in my_sv])
+    acq_rx = Receiver(eng, acq_ch)
+    pinned_acq = torch.from_numpy(acq_sig.copy()).pin_memory()
+    t_acq_e2e = []
+    for k in range(5):
+        for i in range(acq_ch.n):
+            st = acq_ch.snapshot(i)
+            st.acq_state = 0
+            acq_ch.restore(i, st)
+        t0 = time.perf_counter()
+        eng.upload_signal(N_MS, pinned_acq.numpy())
+        votes, phases = acq_rx.cold_sweep(-5000, 500, ACQ_BINS, N_MS, ACQ_MS)
+        t_acq_e2e.append((time.perf_counter() - t0) * 1e3)
+    acq_e2e_ms = float(np.min(t_acq_e2e))
+    found = int(sum(1 for i in range(acq_ch.n) if acq_ch.snapshot(i).acq_state == 2))
     clk = clocks.stop()
 
     # ---- max over ranks
-    times = torch.tensor([t_dev, t_e2e, acq_ms, acq_e2e_ms], dtype=torch.float64, device=dev)
+    times = torch.tensor([t_dev, t_e2e, acq_ms["dp4a"], acq_ms["direct"], acq_e2e_ms, batch_ms], dtype=torch.float64,
+                         device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-        # the final argmax gather of the sweep: every rank contributes its (sv-sharded) triples
+        # the final argmax gather of the sweep: every rank contributes its (satellite-sharded) triples
         gathered = [torch.zeros_like(d_res) for _ in range(world)]
         dist.all_gather(gathered, d_res)
-    t_dev, t_e2e, acq_ms, acq_e2e_ms = [float(x) for x in times.cpu()]
+    t_dev, t_e2e, acq_dp4a_ms, acq_direct_ms, acq_e2e_ms, batch_ms = [float(x) for x in times.cpu()]
 
     if rank == 0:
         peaks = {}
@@ -353,15 +419,19 @@ def run_gpu_arm(args) -> None:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         units_step = world * N_SV_PER_GPU * ARMS * MS_SAMPLES * N_MS
-        value = units_step * args.steps / t_dev
-        e2e = units_step * args.steps / t_e2e
-        # algorithmic bytes of one k_epl launch: signal once per ms, code once per SV,
-        # 24 B request + 12 B result per cell
-        alg_bytes = N_MS * 2046 + N_SV_PER_GPU * 128 + n_cells * (24 + 12)
-        achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
-        # cold-acq: bit-MACs and the integer-pipe view
+        value = units_step * steps / t_dev
+        e2e = units_step * steps / t_e2e
+        # algorithmic bytes: signal once per ms, 128 B of code per SV, 24 B request +
+        # 12 B result per cell
+        rt_bytes = 2046 + N_SV_PER_GPU * 128 + N_SV_PER_GPU * (24 + 12)
+        rt_achieved = rt_bytes / (rt_kernel_ms * 1e-3) / 1e9
+        batch_bytes = N_MS * 2046 + N_SV_PER_GPU * 128 + n_cells * (24 + 12)
         acq_bitmacs = ACQ_SV * ACQ_BINS * ACQ_MS * 2046 * 2 * 16368
         acq_alg_bytes = ACQ_MS * 2046 + len(my_sv) * 128 + n_acq_cells * 8
+        # dp4a issue slots of the sweep: 4 correlations (I/Q x parity) x 1023 lags x 256 steps per cell
+        acq_dp4a = ACQ_SV * ACQ_BINS * ACQ_MS * 4 * 1023 * 256 / world
+        sm_clk = (clk.get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0) * 1e6
+        idp_peak = 148 * 64 * sm_clk                       # IDP.4A: 64 lanes/clk/SM measured (tools/ubench_int.cu)
         cpu_t, cpu_cores, cpu_kind = reference_tracking_seconds(scene, sig, os.cpu_count() or 1, reps=3)
         cpu = None
         if cpu_t:
@@ -370,29 +440,47 @@ def run_gpu_arm(args) -> None:
                    "sample": "whole N=1 workload (4 SV x 1000 ms closed-loop gps_tracking_process), best of 3"}
         line = {
             "metric": "correlator-samples/sec (E/P/L arms)", "value": value, "unit": "arm-samples/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-            "ms_per_step": t_dev * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak",
+            "n_gpus": world, "steps": steps, "warmup": warm,
+            "ms_per_step": t_dev * 1e3 / steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32 xor/popcount", "data": "synthetic",
-            "config": {"workload": "config2: %d-SV E/P/L tracking, 1 s @16.368 Msps 1-bit IF (4 SV per GPU)" % (world * N_SV_PER_GPU),
+            "config": {"workload": "config2: %d-SV E/P/L closed-loop tracking, 1 s @16.368 Msps 1-bit IF (4 SV per GPU, "
+                                   "every SV every ms, loop filters on the host)" % (world * N_SV_PER_GPU),
                        "n_sv": world * N_SV_PER_GPU, "n_ms": N_MS, "cells_per_step": world * n_cells,
                        "l2": "flushed between timed iterations (256 MiB fill)", "parallelism": "sv-shard x%d" % world},
-            "e2e": {"value": e2e, "unit": "arm-samples/s", "h2d_bytes_per_step": int(sig.nbytes + rq.nbytes),
+            "e2e": {"value": e2e, "unit": "arm-samples/s", "h2d_bytes_per_step": int(sig.nbytes + n_cells * 24),
                     "d2h_bytes_per_step": int(n_cells * 12)},
             "gpu_launches": int(launches),
             "clocks": clk,
-            "roofline": {"kernel": "k_epl", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": None,
-                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
-                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kernel_ms},
+            "roofline": {"kernel": "k_epl_rt (4 cells per launch, 1000 serial launches per step)", "bound": "hbm",
+                         "achieved": rt_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": rt_achieved / hbm_peak,
+                         "traffic": None, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+                         "algorithmic_bytes_per_launch": rt_bytes, "kernel_ms": rt_kernel_ms,
+                         "note": "latency-bound by construction: each launch depends on the previous launch's sums through "
+                                 "the host loop filters; round trip %.2f us per ms" % rtt_us},
             "cpu_baseline": cpu,
-            "cold_acq": {"metric": "full-sky 32-SV cold-acq ms", "value": acq_ms, "unit": "ms", "e2e_ms": acq_e2e_ms,
+            "closed_loop": {"round_trip_us": rtt_us, "wall_ms_per_step": wall_loop * 1e3 / steps,
+                            "launches_per_step": launches_value / steps,
+                            "final_code_phase": [float(x) for x in final_fine]},
+            "batch_replay": {"what": "the same %d cells replayed open loop in ONE k_epl launch (signal + requests resident)" % n_cells,
+                             "value": N_SV_PER_GPU * ARMS * MS_SAMPLES * N_MS / (batch_ms * 1e-3), "unit": "arm-samples/s",
+                             "kernel_ms": batch_ms,
+                             "roofline": {"bound": "hbm", "achieved": batch_bytes / (batch_ms * 1e-3) / 1e9, "peak": hbm_peak,
+                                          "unit": "GB/s", "frac": batch_bytes / (batch_ms * 1e-3) / 1e9 / hbm_peak,
+                                          "algorithmic_bytes_per_launch": batch_bytes}},
+            "cold_acq": {"metric": "full-sky 32-SV cold-acq ms", "value": acq_dp4a_ms, "unit": "ms",
+                         "direct_xor_popc_ms": acq_direct_ms, "e2e_ms": acq_e2e_ms,
                          "cells": ACQ_SV * ACQ_BINS * ACQ_MS, "phases": 2046, "bit_macs": acq_bitmacs,
-                         "bit_macs_per_s": acq_bitmacs / (acq_ms * 1e-3),
-                         "hbm_frac": acq_alg_bytes / (acq_ms * 1e-3) / 1e9 / hbm_peak},
+                         "bit_macs_per_s": acq_bitmacs / (acq_dp4a_ms * 1e-3), "doppler_votes_passed_rank0": found,
+                         "roofline": {"kernel": "k_acq_dp4a", "bound": "int-dot-product pipe (IDP.4A 64 lanes/clk/SM)",
+                                      "achieved": acq_dp4a / (acq_dp4a_ms * 1e-3) / 1e12, "peak": idp_peak / 1e12,
+                                      "unit": "T dp4a/s", "frac": acq_dp4a / (acq_dp4a_ms * 1e-3) / idp_peak,
+                                      "hbm_frac": acq_alg_bytes / (acq_dp4a_ms * 1e-3) / 1e9 / hbm_peak}},
         }
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    rx.close()
+    acq_rx.close()
     eng.close()
 
 

@@ -106,8 +106,22 @@ typedef struct gpsb_epl_req {
     uint16_t off_bits;  /* sub-byte replica shift, 0..15               */
 } gpsb_epl_req;
 
-/* out[6*i .. 6*i+5] = IE,QE,IP,QP,IL,QL of request i (int16, popcount - 8184). Synchronous. */
+/* out[6*i .. 6*i+5] = IE,QE,IP,QP,IL,QL of request i (int16, popcount - 8184). Synchronous.
+ * Batches of up to 128 cells take the closed-loop fast path (requests in the kernel parameter space,
+ * results + completion flag in mapped pinned memory: one launch, no copies, no stream synchronise);
+ * gpsb_set_realtime(ctx, 0) forces the staged-copy path used for larger batches. */
 int gpsb_track_epl(gpsb_ctx* ctx, uint32_t n, const gpsb_epl_req* req, int16_t* out);
+int gpsb_set_realtime(gpsb_ctx* ctx, int enabled);
+
+/* Tracking session: keeps one resident CTA per channel slot polling a command slot in mapped pinned
+ * host memory, so that a gpsb_track_epl call of n <= n_slots cells costs one PCIe round trip instead
+ * of a kernel launch (the 1-kHz loop of PM/main.c:134-156 is serial per channel: latency is the whole
+ * budget).  The resident kernel leaves by itself after 250 ms without a command or 20 s of life and is
+ * re-launched transparently, so a stalled host can never wedge the GPU.  While a session is open the
+ * other entry points keep working (they use the context stream; the session has its own). */
+int gpsb_session_begin(gpsb_ctx* ctx, uint32_t n_slots);
+int gpsb_session_end(gpsb_ctx* ctx);
+uint32_t gpsb_session_slots(const gpsb_ctx* ctx);
 
 /*
  * One acquisition / pre-track cell = PM/GPS/acquisition.c:282-294 (freq search),

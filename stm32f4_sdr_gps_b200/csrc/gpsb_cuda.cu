@@ -150,14 +150,13 @@ __global__ void k_pack_iq2(const uint4* __restrict__ samples, uint32_t* __restri
 // ---------------------------------------------------------------------------------- tracking
 // One CTA (128 threads) per request.  Thread t owns replica words t, t+128, t+256, t+384 for all
 // three arms; sums are reduced with REDUX (warp) + a 4x6 shared-memory stage.
-__global__ void __launch_bounds__(kEplThreads)
-k_epl(const gpsb_epl_req* __restrict__ reqs, int16_t* __restrict__ out,
-      const uint32_t* __restrict__ codes, const uint32_t* __restrict__ signal, uint32_t ring_ms)
+__device__ __forceinline__ void epl_cell(const gpsb_epl_req& rq, int16_t* __restrict__ out6,
+                                         const uint32_t* __restrict__ codes, const uint32_t* __restrict__ signal,
+                                         uint32_t ring_ms)
 {
     __shared__ CellSmem s;
     __shared__ int partial[kEplThreads / 32][6];
     const int tid = threadIdx.x;
-    const gpsb_epl_req rq = reqs[blockIdx.x];
 
     stage_replica(s.R, codes + (size_t)rq.sv_slot * kWords, rq.off_bits & 15u, tid, kEplThreads);
     stage_mix(s.I, s.Q, signal + (size_t)(rq.ms_index % ring_ms) * kWords, rq.acc0, rq.step32, tid,
@@ -192,7 +191,127 @@ k_epl(const gpsb_epl_req* __restrict__ reqs, int16_t* __restrict__ out,
         int v = 0;
 #pragma unroll
         for (int w = 0; w < kEplThreads / 32; w++) v += partial[w][tid];
-        out[(size_t)blockIdx.x * 6 + tid] = (int16_t)(v - kHalfSum);  // gps_misc.c:140-141
+        out6[tid] = (int16_t)(v - kHalfSum);  // gps_misc.c:140-141
+    }
+}
+
+__global__ void __launch_bounds__(kEplThreads)
+k_epl(const gpsb_epl_req* __restrict__ reqs, int16_t* __restrict__ out,
+      const uint32_t* __restrict__ codes, const uint32_t* __restrict__ signal, uint32_t ring_ms)
+{
+    const gpsb_epl_req rq = reqs[blockIdx.x];
+    epl_cell(rq, out + (size_t)blockIdx.x * 6, codes, signal, ring_ms);
+}
+
+// ---------------------------------------------------------------------------------- closed-loop (1 kHz) paths
+// The tracking loop is serial per channel: the NCO words of millisecond t+1 come out of the host loop
+// filters fed with the sums of millisecond t (tracking.c:140-143).  What matters is therefore the round
+// trip, not bandwidth.  Two forms, both exchanging with the host through MAPPED PINNED memory only:
+//
+//  k_epl_rt          one launch per millisecond; the requests ride in the kernel parameter space, every CTA
+//                    writes its six sums plus the batch sequence number as ONE 16-byte store to host memory;
+//                    the host spins on the sequence numbers (no memcpy nodes, no stream synchronise).
+//  k_epl_session     persistent: one CTA per channel slot stays resident for a whole tracking run, polls its
+//                    32-byte command slot in host memory, answers with the same 16-byte record.  No launch on
+//                    the critical path at all.  Bounded by an idle time-out and a maximum lifetime (global
+//                    timer), so it can never outlive a stalled or dead host.
+constexpr int kRtMaxCells = 128;
+constexpr uint32_t kRtStop = 0xFFFFFFFFu;
+struct EplRtBatch {
+    gpsb_epl_req rq[kRtMaxCells];
+};
+struct RtCmd {   // host -> device, 32 bytes; both 16-byte halves carry the sequence number
+    uint32_t w[8];   // sv_slot, ms_index, acc0, seq | step32, off_e|off_p<<16, off_l|off_bits<<16, seq
+};
+struct RtRsp {   // device -> host, 16 bytes, written with a single store
+    int16_t sums[6];
+    uint32_t seq;
+};
+
+__device__ __forceinline__ void publish_sums(RtRsp* __restrict__ slot, const int16_t* sums6, uint32_t seq)
+{
+    uint4 v;
+    v.x = (uint16_t)sums6[0] | ((uint32_t)(uint16_t)sums6[1] << 16);
+    v.y = (uint16_t)sums6[2] | ((uint32_t)(uint16_t)sums6[3] << 16);
+    v.z = (uint16_t)sums6[4] | ((uint32_t)(uint16_t)sums6[5] << 16);
+    v.w = seq;
+    // one 16-byte transaction: sums and tag arrive together
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(slot), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(kEplThreads)
+k_epl_rt(const __grid_constant__ EplRtBatch batch, RtRsp* __restrict__ host_rsp,
+         const uint32_t* __restrict__ codes, const uint32_t* __restrict__ signal, uint32_t ring_ms, uint32_t seq)
+{
+    __shared__ int16_t sums[8];
+    epl_cell(batch.rq[blockIdx.x], sums, codes, signal, ring_ms);
+    __syncthreads();
+    if (threadIdx.x == 0) publish_sums(host_rsp + blockIdx.x, sums, seq);
+}
+
+__device__ __forceinline__ uint64_t global_ns()
+{
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__device__ __forceinline__ uint4 ld_host16(const volatile void* p)
+{
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
+__global__ void __launch_bounds__(kEplThreads)
+k_epl_session(const volatile RtCmd* __restrict__ host_cmd, RtRsp* __restrict__ host_rsp,
+              const uint32_t* __restrict__ codes, const uint32_t* __restrict__ signal, uint32_t ring_ms,
+              uint32_t last_seq, uint64_t idle_ns, uint64_t life_ns)
+{
+    __shared__ int16_t sums[8];
+    __shared__ uint32_t cw[8];
+    __shared__ int go;
+    const volatile RtCmd* my_cmd = host_cmd + blockIdx.x;
+    const uint64_t t_begin = global_ns();
+    uint64_t t_last = t_begin;
+    for (;;) {
+        if (threadIdx.x == 0) {
+            go = 0;
+            for (;;) {
+                const uint4 a = ld_host16(&my_cmd->w[0]);
+                const uint4 b = ld_host16(&my_cmd->w[4]);
+                if (a.w == b.w && a.w != last_seq) {
+                    if (a.w != kRtStop) {
+                        cw[0] = a.x; cw[1] = a.y; cw[2] = a.z; cw[3] = a.w;
+                        cw[4] = b.x; cw[5] = b.y; cw[6] = b.z;
+                        go = 1;
+                    }
+                    break;
+                }
+                const uint64_t now = global_ns();
+                if (now - t_last > idle_ns || now - t_begin > life_ns) break;   // host gone quiet / lease over
+            }
+        }
+        __syncthreads();
+        if (!go) return;
+        gpsb_epl_req rq;
+        rq.sv_slot = cw[0];
+        rq.ms_index = cw[1];
+        rq.acc0 = cw[2];
+        rq.step32 = cw[4];
+        rq.off_e = (uint16_t)(cw[5] & 0xFFFFu);
+        rq.off_p = (uint16_t)(cw[5] >> 16);
+        rq.off_l = (uint16_t)(cw[6] & 0xFFFFu);
+        rq.off_bits = (uint16_t)(cw[6] >> 16);
+        last_seq = cw[3];
+        if (rq.sv_slot != 0xFFFFFFFFu) {            // 0xFFFFFFFF = keep-alive for a slot without work this ms
+            epl_cell(rq, sums, codes, signal, ring_ms);
+            __syncthreads();
+            if (threadIdx.x == 0) publish_sums(host_rsp + blockIdx.x, sums, last_seq);
+        }
+        if (threadIdx.x == 0) t_last = global_ns();
+        __syncthreads();
     }
 }
 
@@ -354,6 +473,16 @@ struct gpsb_ctx {
     uint32_t* d_codes = nullptr;   // max_sv x 512 words
     uint32_t* d_schips = nullptr;  // max_sv x 256 words: +-1 chip bytes for the dp4a search
     int sweep_method = GPSB_SWEEP_DP4A;
+    // closed-loop mailbox (mapped pinned host memory, see k_epl_rt / k_epl_session)
+    RtCmd* h_cmd = nullptr;        // kRtMaxCells command slots, host view
+    RtCmd* d_cmd = nullptr;        // device alias
+    RtRsp* h_rsp = nullptr;        // kRtMaxCells response slots, host view
+    RtRsp* d_rsp = nullptr;
+    uint32_t rt_seq = 0;
+    int realtime = 1;
+    cudaStream_t rt_stream = nullptr;   // the session kernel lives on its own stream
+    uint32_t session_slots = 0;         // > 0 while a session kernel is (supposed to be) resident
+    uint64_t session_relaunches = 0;
     uint8_t* d_code_set = nullptr; // not used on device; host mirror below
     uint8_t* code_set = nullptr;   // host: slot has a code
     uint32_t* d_signal = nullptr;  // ring_ms x 512 words
@@ -390,6 +519,69 @@ static int check_launch(gpsb_ctx* c, const char* what)
     if (e != cudaSuccess) return fail(GPSB_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
     c->launches++;
     return GPSB_OK;
+}
+
+/* ------------------------------------------------------------------ closed-loop mailbox helpers */
+static uint32_t next_seq(gpsb_ctx* c)
+{
+    uint32_t s = ++c->rt_seq;
+    if (s == 0 || s == kRtStop) s = c->rt_seq = 1;
+    return s;
+}
+
+static int session_launch(gpsb_ctx* c, uint32_t last_seq)
+{
+    // 250 ms without a command, or 20 s of life, and the kernel leaves on its own (it is re-launched on demand)
+    k_epl_session<<<c->session_slots, kEplThreads, 0, c->rt_stream>>>(c->d_cmd, c->d_rsp, c->d_codes, c->d_signal,
+                                                                     c->ring_ms, last_seq, 250000000ull,
+                                                                     20000000000ull);
+    return check_launch(c, "k_epl_session");
+}
+
+// Wait until response slots 0..n-1 carry `seq`, then copy the sums out.  `watch` is the stream whose work
+// produces them; in session mode a finished stream means the resident kernel timed out and is re-launched.
+static int collect_responses(gpsb_ctx* c, uint32_t n, uint32_t seq, int16_t* out, cudaStream_t watch, bool session)
+{
+    for (uint32_t i = 0; i < n; i++) {
+        volatile RtRsp* r = c->h_rsp + i;
+        uint64_t spins = 0;
+        while (r->seq != seq) {
+            if ((++spins & 0x3FFFF) != 0) continue;
+            cudaError_t q = cudaStreamQuery(watch);
+            if (q == cudaErrorNotReady) continue;
+            if (q != cudaSuccess) return fail(GPSB_ERR_CUDA, "closed-loop kernel failed: %s", cudaGetErrorString(q));
+            if (r->seq == seq) break;
+            if (!session) return fail(GPSB_ERR_CUDA, "k_epl_rt finished without publishing cell %u", i);
+            c->session_relaunches++;                 // the resident kernel left (idle / lease): start a new one
+            int rc = session_launch(c, seq - 1);
+            if (rc) return rc;
+        }
+        __atomic_thread_fence(__ATOMIC_ACQUIRE);
+        memcpy(out + 6u * i, (const void*)r->sums, 12);
+    }
+    return GPSB_OK;
+}
+
+static int session_exchange(gpsb_ctx* c, uint32_t n, const gpsb_epl_req* req, int16_t* out)
+{
+    const uint32_t seq = next_seq(c);
+    for (uint32_t i = 0; i < n; i++) {
+        volatile uint32_t* w = c->h_cmd[i].w;
+        w[0] = req[i].sv_slot;
+        w[1] = req[i].ms_index;
+        w[2] = req[i].acc0;
+        w[4] = req[i].step32;
+        w[5] = (uint32_t)req[i].off_e | ((uint32_t)req[i].off_p << 16);
+        w[6] = (uint32_t)req[i].off_l | ((uint32_t)req[i].off_bits << 16);
+    }
+    for (uint32_t i = n; i < c->session_slots; i++) c->h_cmd[i].w[0] = 0xFFFFFFFFu;   // keep idle slots alive
+    __atomic_thread_fence(__ATOMIC_RELEASE);         // payload before tags (x86: store order is kept anyway)
+    for (uint32_t i = 0; i < c->session_slots; i++) {
+        volatile uint32_t* w = c->h_cmd[i].w;
+        w[3] = seq;
+        w[7] = seq;
+    }
+    return collect_responses(c, n, seq, out, c->rt_stream, true);
 }
 
 extern "C" {
@@ -437,6 +629,19 @@ int gpsb_create(gpsb_ctx** out, int device, uint32_t max_sv, uint32_t ring_ms)
     CU(cudaMalloc(&c->d_signal, (size_t)ring_ms * GPSB_FRAME_BYTES));
     CU(cudaMemset(c->d_signal, 0, (size_t)ring_ms * GPSB_FRAME_BYTES));
     CU(cudaMalloc(&c->d_chips, 1024));
+    {
+        void* hp = nullptr;
+        const size_t bytes = kRtMaxCells * (sizeof(RtCmd) + sizeof(RtRsp));
+        CU(cudaHostAlloc(&hp, bytes, cudaHostAllocMapped));
+        memset(hp, 0, bytes);
+        void* dp = nullptr;
+        CU(cudaHostGetDevicePointer(&dp, hp, 0));
+        c->h_cmd = (RtCmd*)hp;
+        c->d_cmd = (RtCmd*)dp;
+        c->h_rsp = (RtRsp*)((uint8_t*)hp + kRtMaxCells * sizeof(RtCmd));
+        c->d_rsp = (RtRsp*)((uint8_t*)dp + kRtMaxCells * sizeof(RtCmd));
+        CU(cudaStreamCreateWithFlags(&c->rt_stream, cudaStreamNonBlocking));
+    }
     CU(cudaMalloc(&c->d_l0, 4 * kWords * 4 + 64));
     for (int i = 0; i < 8; i++) {
         CU(cudaEventCreate(&c->ev_start[i]));
@@ -463,6 +668,9 @@ void gpsb_destroy(gpsb_ctx* c)
     if (c->d_schips) cudaFree(c->d_schips);
     if (c->d_signal) cudaFree(c->d_signal);
     if (c->d_chips) cudaFree(c->d_chips);
+    if (c->session_slots) gpsb_session_end(c);
+    if (c->rt_stream) cudaStreamDestroy(c->rt_stream);
+    if (c->h_cmd) cudaFreeHost((void*)c->h_cmd);
     if (c->d_l0) cudaFree(c->d_l0);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     free(c->code_set);
@@ -655,6 +863,18 @@ int gpsb_track_epl(gpsb_ctx* c, uint32_t n, const gpsb_epl_req* req, int16_t* ou
     int rc = check_epl(c, n, req);
     if (rc) return rc;
     CU(cudaSetDevice(c->device));
+    if (c->session_slots && n <= c->session_slots) return session_exchange(c, n, req, out);
+    if (c->realtime && n <= (uint32_t)kRtMaxCells) {
+        // closed-loop fast path: one launch, no copies, completion by sequence numbers in mapped host memory
+        static_assert(sizeof(EplRtBatch) <= 4096, "request batch must fit the kernel parameter space");
+        EplRtBatch batch;
+        memcpy(batch.rq, req, (size_t)n * sizeof(gpsb_epl_req));
+        const uint32_t seq = next_seq(c);
+        k_epl_rt<<<n, kEplThreads, 0, c->stream>>>(batch, c->d_rsp, c->d_codes, c->d_signal, c->ring_ms, seq);
+        rc = check_launch(c, "k_epl_rt");
+        if (rc) return rc;
+        return collect_responses(c, n, seq, out, c->stream, false);
+    }
     size_t req_b = (size_t)n * sizeof(gpsb_epl_req), out_b = (size_t)n * 12;
     size_t out_off = (req_b + 255) & ~(size_t)255;
     rc = ensure_stage(c, out_off + out_b);
@@ -761,6 +981,43 @@ int gpsb_search(gpsb_ctx* c, uint32_t n, const gpsb_search_req* req, gpsb_search
     CU(cudaMemcpyAsync(h + res_off, d + res_off, res_b, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     memcpy(res, h + res_off, res_b);
+    return GPSB_OK;
+}
+
+int gpsb_session_begin(gpsb_ctx* c, uint32_t n_slots)
+{
+    if (!c) return fail(GPSB_ERR_ARG, "null context");
+    if (n_slots == 0 || n_slots > (uint32_t)kRtMaxCells) return fail(GPSB_ERR_ARG, "session of %u slots (1..%d)", n_slots, kRtMaxCells);
+    if (c->session_slots) return fail(GPSB_ERR_STATE, "a tracking session is already open");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));            // codes / frames uploaded so far are visible to the session
+    for (uint32_t i = 0; i < n_slots; i++) c->h_cmd[i].w[3] = c->h_cmd[i].w[7] = c->rt_seq;
+    c->session_slots = n_slots;
+    int rc = session_launch(c, c->rt_seq);
+    if (rc) c->session_slots = 0;
+    return rc;
+}
+
+int gpsb_session_end(gpsb_ctx* c)
+{
+    if (!c) return fail(GPSB_ERR_ARG, "null context");
+    if (!c->session_slots) return GPSB_OK;
+    for (uint32_t i = 0; i < c->session_slots; i++) {
+        volatile uint32_t* w = c->h_cmd[i].w;
+        w[3] = kRtStop;
+        w[7] = kRtStop;
+    }
+    c->session_slots = 0;
+    CU(cudaStreamSynchronize(c->rt_stream));
+    return GPSB_OK;
+}
+
+uint32_t gpsb_session_slots(const gpsb_ctx* c) { return c ? c->session_slots : 0; }
+
+int gpsb_set_realtime(gpsb_ctx* c, int enabled)
+{
+    if (!c) return fail(GPSB_ERR_ARG, "null context");
+    c->realtime = enabled ? 1 : 0;
     return GPSB_OK;
 }
 

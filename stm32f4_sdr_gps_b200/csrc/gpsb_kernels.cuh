@@ -72,7 +72,7 @@ __device__ __forceinline__ void stage_mix(uint32_t* I, uint32_t* Q, const uint32
     for (int w = tid; w < kWords; w += nthreads) {
         uint32_t vi = 0u, vq = 0u;
         if (w < kMixWords) {
-            uint32_t s = __ldg(frame + w);
+            uint32_t s = __ldcg(frame + w);   // L2 only: ring frames are rewritten by DMA under resident kernels
             uint32_t ph = (acc0 + (uint32_t)w * step32) >> 30;
             vi = cos_pattern(ph) ^ s;
             vq = sin_pattern(ph) ^ s;

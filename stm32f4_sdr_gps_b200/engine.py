@@ -81,6 +81,10 @@ def load_library(path: Path | None = None) -> C.CDLL:
         "gpsb_search_iq": (i32, [vp, vp, vp]),
         "gpsb_sweep": (i32, [vp, vp, u32, vp, u32, u32, u32, u32, vp]),
         "gpsb_set_sweep_method": (i32, [vp, i32]),
+        "gpsb_set_realtime": (i32, [vp, i32]),
+        "gpsb_session_begin": (i32, [vp, u32]),
+        "gpsb_session_end": (i32, [vp]),
+        "gpsb_session_slots": (u32, [vp]),
         "gpsb_track_epl_dev": (i32, [vp, u32, vp, vp]),
         "gpsb_search_dev": (i32, [vp, u32, vp, vp]),
         "gpsb_sweep_dev": (i32, [vp, vp, u32, vp, u32, u32, u32, u32, vp]),
@@ -230,6 +234,15 @@ class Engine:
     def set_sweep_method(self, method: int) -> None:
         """0 = direct XOR/popcount, 1 = byte-popcount dp4a correlation (default)."""
         self._check(self.lib.gpsb_set_sweep_method(self._ctx, method))
+
+    def set_realtime(self, enabled: bool) -> None:
+        self._check(self.lib.gpsb_set_realtime(self._ctx, int(bool(enabled))))
+
+    def session_begin(self, n_slots: int) -> None:
+        self._check(self.lib.gpsb_session_begin(self._ctx, n_slots))
+
+    def session_end(self) -> None:
+        self._check(self.lib.gpsb_session_end(self._ctx))
 
     # device-resident variants: raw device pointers (ints), asynchronous on the context stream
     def track_epl_dev(self, n: int, d_req: int, d_out: int) -> None:

@@ -128,10 +128,16 @@ int gpsb_rx_track_ms(gpsb_rx* rx, uint32_t ms)
 int gpsb_rx_track_run(gpsb_rx* rx, uint32_t ms0, uint32_t n_ms, int16_t* iq_log, int8_t* nav_log)
 {
     if (!rx) return GPSB_ERR_ARG;
+    /* a run of many milliseconds is served by resident CTAs (one per channel): no launch per ms */
+    const int own_session = n_ms > 8 && rx->n_ch <= 128 && gpsb_session_slots(rx->ctx) == 0 &&
+                            gpsb_session_begin(rx->ctx, rx->n_ch) == GPSB_OK;
     for (uint32_t m = 0; m < n_ms; m++) {
         for (uint32_t i = 0; i < rx->n_ch; i++) rx->aux[i].last_nav_bit = -1;
         int rc = gpsb_rx_track_ms(rx, ms0 + m);
-        if (rc != GPSB_OK) return rc;
+        if (rc != GPSB_OK) {
+            if (own_session) gpsb_session_end(rx->ctx);
+            return rc;
+        }
         if (iq_log) {
             int16_t* row = iq_log + (size_t)m * rx->n_ch * 6;
             memset(row, 0, (size_t)rx->n_ch * 12);
@@ -143,6 +149,7 @@ int gpsb_rx_track_run(gpsb_rx* rx, uint32_t ms0, uint32_t n_ms, int16_t* iq_log,
             for (uint32_t i = 0; i < rx->n_ch; i++)
                 nav_log[(size_t)m * rx->n_ch + i] = rx->plan[i].want == GPSB_WANT_EPL ? rx->aux[i].last_nav_bit : -1;
     }
+    if (own_session) return hx_note(gpsb_session_end(rx->ctx));
     return GPSB_OK;
 }
 

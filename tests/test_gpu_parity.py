@@ -298,3 +298,41 @@ def test_dp4a_and_direct_search_agree_all_bit_shifts(engine, oracle):
         if rq[i]["start"] >= rq[i]["stop"]:
             want = (0, 0, 0)
         assert (res["max"][i], res["phase"][i], res["avg"][i]) == want, i
+
+
+def test_closed_loop_paths_agree(engine, oracle):
+    """The three ways a small E/P/L batch can reach the GPU - staged copies, parameter-space launch with
+    mapped-memory completion (k_epl_rt), resident session kernel (k_epl_session) - return identical sums,
+    also when the ring frame is rewritten while the session kernel is resident."""
+    rng = np.random.default_rng(31)
+    sig = rng.integers(0, 256, (4, 2046), dtype=np.uint8)
+    engine.upload_signal(60, sig)
+    for s, prn in enumerate((8, 15, 21)):
+        engine.set_code_prn(s, prn)
+    rq = np.zeros(3, EPL_REQ)
+    for i in range(3):
+        rq[i] = (i, 60 + i, 1000 * i, 0x40000000 + 12345 * i, 500 + i, 501 + i, 502 + i, i)
+    want = np.stack([oracle.epl_explicit(oracle.ca_code((8, 15, 21)[i]), sig[i], int(rq["acc0"][i]), int(rq["step32"][i]),
+                                         500 + i, 501 + i, 502 + i, i) for i in range(3)])
+    engine.set_realtime(False)
+    assert np.array_equal(engine.track_epl(rq), want)
+    engine.set_realtime(True)
+    assert np.array_equal(engine.track_epl(rq), want)
+    engine.session_begin(4)
+    try:
+        for _ in range(50):
+            assert np.array_equal(engine.track_epl(rq), want)
+        assert np.array_equal(engine.track_epl(rq[:1]), want[:1])      # fewer cells than slots
+        sig2 = rng.integers(0, 256, (4, 2046), dtype=np.uint8)
+        engine.upload_signal(60, sig2)                                  # DMA under the resident kernel
+        want2 = np.stack([oracle.epl_explicit(oracle.ca_code((8, 15, 21)[i]), sig2[i], int(rq["acc0"][i]),
+                                              int(rq["step32"][i]), 500 + i, 501 + i, 502 + i, i) for i in range(3)])
+        assert np.array_equal(engine.track_epl(rq), want2)
+        import time
+        time.sleep(0.6)                                                 # idle time-out: the kernel leaves ...
+        assert np.array_equal(engine.track_epl(rq), want2)              # ... and is re-launched on demand
+        with pytest.raises(GpsbError):
+            engine.session_begin(2)                                     # already open
+    finally:
+        engine.session_end()
+    assert np.array_equal(engine.track_epl(rq), want2)
