@@ -34,7 +34,7 @@ sys.path.insert(0, str(REPO))
 IF_HZ = 4092000
 MS_SAMPLES = 16368
 N_SV_PER_GPU = 4
-N_MS = 1000
+N_MS = int(os.environ.get("GPSB_BENCH_NMS", "1000"))   # shrink only for profiler runs (never for a reported number)
 ARMS = 3
 ALL_PRNS = [5, 14, 20, 30, 1, 2, 3, 4, 6, 7, 8, 9, 10, 11, 12, 13, 15, 16, 17, 18, 19, 21, 22, 23, 24, 25, 26, 27, 28,
             29, 31, 32]
@@ -102,12 +102,22 @@ class ClockSampler:
     def __init__(self, gpu_index: int):
         self.path = Path(tempfile.gettempdir()) / ("gpsb_clocks_%d_%d.csv" % (os.getpid(), gpu_index))
         self.proc = None
+        def die_with_parent():          # never leave a sampler behind if the bench dies (PR_SET_PDEATHSIG, SIGTERM)
+            import ctypes
+            ctypes.CDLL("libc.so.6").prctl(1, 15)
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+                ["timeout", "900", "nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.FIELDS,
+                 "--format=csv,noheader,nounits", "-lms", "100"], stdout=open(self.path, "w"),
+                stderr=subprocess.DEVNULL, preexec_fn=die_with_parent)
+            import atexit
+            atexit.register(self._kill)
         except OSError:
             self.proc = None
+
+    def _kill(self) -> None:
+        if self.proc is not None and self.proc.poll() is None:
+            self.proc.kill()
 
     def stop(self) -> dict:
         if self.proc is None:
@@ -329,12 +339,12 @@ def run_gpu_arm(args) -> None:
     n_probe = 200
     pe = events(1)
     for m in range(20):
-        eng.track_epl(rq_ms[m])
+        eng.track_epl(rq_ms[m % N_MS])
     barrier()
     t0 = time.perf_counter()
     pe[0][0].record(stream)
     for m in range(n_probe):
-        eng.track_epl(rq_ms[m])
+        eng.track_epl(rq_ms[m % N_MS])
     pe[0][1].record(stream)
     barrier()
     rtt_us = (time.perf_counter() - t0) / n_probe * 1e6

@@ -989,6 +989,8 @@ int gpsb_session_begin(gpsb_ctx* c, uint32_t n_slots)
     if (!c) return fail(GPSB_ERR_ARG, "null context");
     if (n_slots == 0 || n_slots > (uint32_t)kRtMaxCells) return fail(GPSB_ERR_ARG, "session of %u slots (1..%d)", n_slots, kRtMaxCells);
     if (c->session_slots) return fail(GPSB_ERR_STATE, "a tracking session is already open");
+    if (getenv("GPSB_DISABLE_SESSION"))   // profilers replay kernels and cannot feed a resident one
+        return fail(GPSB_ERR_STATE, "tracking sessions disabled by GPSB_DISABLE_SESSION");
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));            // codes / frames uploaded so far are visible to the session
     for (uint32_t i = 0; i < n_slots; i++) c->h_cmd[i].w[3] = c->h_cmd[i].w[7] = c->rt_seq;

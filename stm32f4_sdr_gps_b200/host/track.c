@@ -52,6 +52,10 @@ static void arm_offsets(float code_phase_fine, gpsb_epl_req* rq)
     uint16_t late = (uint16_t)(prompt + 1);
     if (early >= GPSB_HALF_CHIPS) early = GPSB_HALF_CHIPS - 1;
     if (late >= GPSB_HALF_CHIPS) late = 0;
+    /* A code phase just above 16368 (the DLL's "16368 - x" wrap of a negative x, tracking.c:353-358) gives
+     * a prompt offset of exactly 2046; the reference's pointer arithmetic then runs its second loop over
+     * the whole buffer from byte 0 (gps_misc.c:57,73-81), i.e. it computes offset 0. */
+    if (prompt >= GPSB_HALF_CHIPS) prompt = (uint16_t)(prompt - GPSB_HALF_CHIPS);
     rq->off_bits = (uint16_t)(fine & (GPSB_FINE_PER_HALFCHIP - 1));
     rq->off_e = early;
     rq->off_p = prompt;

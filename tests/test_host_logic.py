@@ -311,3 +311,35 @@ def test_chain_vote_and_empty_windows():
     assert plan.want == WANT_NOTHING
     mine.free()
     idle.free()
+
+
+def test_prompt_offset_2046_edge(oracle, reference, golden):
+    """code_phase_fine in (16368, 16376): prompt byte offset 2046, early 2045, late 0 (tracking.c:115-130).
+    The reference evaluates offset 2046 as offset 0; so must we - state compared after the step."""
+    lib = load_host_library()
+    sig = golden["scene_signal"]
+    prn = 5
+    chips = oracle.ca_code(prn)
+    for fine in (16369.25, 16375.9, 16368.0, 0.4, 7.99):
+        rchans = reference.channels(1)
+        rch = reference.channel_at(rchans, 0)
+        reference.channel_init(rch, prn, 0)
+        mine = Channels([prn])
+        lib.gpsb_host_attach(None)
+        st = reference.snapshot(rch)
+        st.acq_state, st.trk_state = 9, 4
+        st.if_freq_offset_hz_bits = int(np.float32(1020.0).view(np.uint32))
+        st.code_phase_fine_bits = int(np.float32(fine).view(np.uint32))
+        st.prev_track_timestamp = 99
+        reference.restore(rch, st)
+        mst = mine.snapshot(0)
+        for name, _ in st._fields_:
+            setattr(mst, name, getattr(st, name))
+        mine.restore(0, mst)
+        for ms in (100, 101):
+            reference.set_ms(ms)
+            reference.lib.gps_tracking_process(rch, sig[ms].ctypes.data, ms % 4)
+            host_track_ms(lib, oracle, mine.at(0), chips, sig[ms], ms, ms % 4)
+            a, b = mine.snapshot(0), reference.snapshot(rch)
+            assert states_equal(a, b), (fine, ms, diff_fields(a, b))
+        mine.free()
