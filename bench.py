@@ -205,6 +205,29 @@ def reference_tracking_seconds(scene, sig, max_procs: int, reps: int = 3):
     return wall, procs, "reference"
 
 
+def reference_sweep_rate(acq_sig, n_sv: int = 2, n_ms: int = 2):
+    """Reference C (oracle/_ref) on a bounded sample of the cold-acquisition cells: n_sv x 21 bins x n_ms full
+    2046-phase searches on one core.  Returns (cells_per_second, n_cells) or (None, 0)."""
+    import ctypes as C
+    sys.path.insert(0, str(REPO / "tests"))
+    from oracle_lib import Reference, have_reference
+    if not have_reference():
+        return None, 0
+    ref = Reference()
+    lib = ref.lib
+    lib.ref_sweep_time.restype = C.c_double
+    lib.ref_sweep_time.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_int32, C.c_int32, C.c_uint32,
+                                   C.c_uint32, C.c_void_p]
+    chans = ref.channels(n_sv)
+    for i in range(n_sv):
+        ref.channel_init(ref.channel_at(chans, i), i + 1, 0)
+    out = np.zeros((n_sv, ACQ_BINS, n_ms, 3), np.uint16)
+    sig = np.ascontiguousarray(acq_sig[:n_ms])
+    best = min(lib.ref_sweep_time(chans, n_sv, sig.ctypes.data, n_ms, -5000, 500, ACQ_BINS, 0, out.ctypes.data)
+               for _ in range(2))
+    return n_sv * ACQ_BINS * n_ms / best, n_sv * ACQ_BINS * n_ms
+
+
 def run_reference_arm(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -374,7 +397,8 @@ def run_gpu_arm(args) -> None:
         eng.set_code_prn(prn, prn)
     eng.upload_signal(N_MS, acq_sig)                    # frames N_MS .. N_MS+9 of the ring
     step = np.array([nco_step32(np.float32(IF_HZ - 5000 + 500 * b)) for b in range(ACQ_BINS)], np.uint32)
-    my_sv = np.arange(1, ACQ_SV + 1, dtype=np.uint32)[rank::world].copy()
+    from stm32f4_sdr_gps_b200 import sharding
+    my_sv = (sharding.shard_satellites(ACQ_SV, rank, world) + 1).astype(np.uint32)      # PRN = index + 1
     d_sv = torch.from_numpy(my_sv.view(np.int32)).to(dev)
     d_step = torch.from_numpy(step.view(np.int32)).to(dev)
     n_acq_cells = my_sv.size * ACQ_BINS * ACQ_MS
@@ -416,9 +440,12 @@ def run_gpu_arm(args) -> None:
                          device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-        # the final argmax gather of the sweep: every rank contributes its (satellite-sharded) triples
-        gathered = [torch.zeros_like(d_res) for _ in range(world)]
-        dist.all_gather(gathered, d_res)
+    # the one exchange of the path: all-gather of the sweep triples so every rank holds the full grid
+    local = d_res.cpu().numpy().view(np.uint16).reshape(my_sv.size, ACQ_BINS, ACQ_MS, 4)
+    t0 = time.perf_counter()
+    grid = sharding.gather_sweep(sharding.pack_local(local, ACQ_SV, rank, world), ACQ_SV, world, device=dev)
+    gather_ms = (time.perf_counter() - t0) * 1e3
+    assert grid.shape == (ACQ_SV, ACQ_BINS, ACQ_MS, 4) and np.array_equal(grid[my_sv - 1], local)
     t_dev, t_e2e, acq_dp4a_ms, acq_direct_ms, acq_e2e_ms, batch_ms = [float(x) for x in times.cpu()]
 
     if rank == 0:
@@ -443,6 +470,7 @@ def run_gpu_arm(args) -> None:
         sm_clk = (clk.get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0) * 1e6
         idp_peak = 148 * 64 * sm_clk                       # IDP.4A: 64 lanes/clk/SM measured (tools/ubench_int.cu)
         cpu_t, cpu_cores, cpu_kind = reference_tracking_seconds(scene, sig, os.cpu_count() or 1, reps=3)
+        acq_cpu_rate, acq_cpu_cells = reference_sweep_rate(acq_sig)
         cpu = None
         if cpu_t:
             cpu = {"value": N_SV_PER_GPU * ARMS * MS_SAMPLES * N_MS / cpu_t, "unit": "arm-samples/s", "cores": cpu_cores,
@@ -481,6 +509,11 @@ def run_gpu_arm(args) -> None:
                          "direct_xor_popc_ms": acq_direct_ms, "e2e_ms": acq_e2e_ms,
                          "cells": ACQ_SV * ACQ_BINS * ACQ_MS, "phases": 2046, "bit_macs": acq_bitmacs,
                          "bit_macs_per_s": acq_bitmacs / (acq_dp4a_ms * 1e-3), "doppler_votes_passed_rank0": found,
+                         "cpu_baseline": None if not acq_cpu_rate else {
+                             "value": ACQ_SV * ACQ_BINS * ACQ_MS / acq_cpu_rate * 1e3, "unit": "ms (extrapolated, 1 core)",
+                             "cores": 1, "kind": "reference",
+                             "sample": "%d of the 6720 cells (2 SV x 21 bins x 2 ms), correlation_search 0..2046" % acq_cpu_cells},
+                         "gather_ms": gather_ms, "sharding": "satellites round-robin over %d rank(s)" % world,
                          "roofline": {"kernel": "k_acq_dp4a", "bound": "int-dot-product pipe (IDP.4A 64 lanes/clk/SM)",
                                       "achieved": acq_dp4a / (acq_dp4a_ms * 1e-3) / 1e12, "peak": idp_peak / 1e12,
                                       "unit": "T dp4a/s", "frac": acq_dp4a / (acq_dp4a_ms * 1e-3) / idp_peak,

@@ -122,6 +122,13 @@ int gpsb_set_realtime(gpsb_ctx* ctx, int enabled);
 int gpsb_session_begin(gpsb_ctx* ctx, uint32_t n_slots);
 int gpsb_session_end(gpsb_ctx* ctx);
 uint32_t gpsb_session_slots(const gpsb_ctx* ctx);
+/* The two halves of one session exchange for a single slot.  A slot must be driven by one thread at a
+ * time; different slots may be driven concurrently from different threads (every channel of the 1-kHz
+ * loop is independent, PM/GPS/gps_misc.h:184: all state is per gps_ch_t).  req == NULL posts a keep-alive.
+ * While a session is open gpsb_search and the staged gpsb_track_epl path remain usable from any thread
+ * (they serialise on an internal lock). */
+int gpsb_session_post(gpsb_ctx* ctx, uint32_t slot, const gpsb_epl_req* req, uint32_t* seq);
+int gpsb_session_wait(gpsb_ctx* ctx, uint32_t slot, uint32_t seq, int16_t out6[6]);
 
 /*
  * One acquisition / pre-track cell = PM/GPS/acquisition.c:282-294 (freq search),

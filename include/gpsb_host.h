@@ -274,6 +274,9 @@ int gpsb_rx_track_ms(gpsb_rx* rx, uint32_t ms);
  *   iq_log  [n_ms][n_ch][6]  IE,QE,IP,QP,IL,QL (zeros for channels not in GPS_TRACKING_RUN that ms)
  *   nav_log [n_ms][n_ch]     -1, or the 20-ms data bit handed to the word assembler that ms        */
 int gpsb_rx_track_run(gpsb_rx* rx, uint32_t ms0, uint32_t n_ms, int16_t* iq_log, int8_t* nav_log);
+/* Host threads used by gpsb_rx_track_run for the per-channel loop filters (each drives its own channels'
+ * session slots): 0 = automatic (online CPUs - 1, at most 16, at most one per channel), 1 = single thread. */
+void gpsb_rx_set_threads(gpsb_rx* rx, uint32_t n);
 
 /* One acquisition snapshot for every channel (acquisition_process, PM/main.c:166) in one launch. */
 int gpsb_rx_acquire_ms(gpsb_rx* rx, uint32_t ms);

@@ -34,7 +34,7 @@ NVCC_FLAGS = [
 ]
 # host C: IEEE semantics exactly like the reference build recipe (no fast-math, no FMA contraction)
 GCC_FLAGS = ["-std=gnu11", "-O2", "-fPIC", "-shared", "-fno-strict-aliasing", "-ffp-contract=off",
-             "-fno-fast-math", "-Wall", "-Wextra", "-Wno-unused-parameter"]
+             "-fno-fast-math", "-pthread", "-D_GNU_SOURCE", "-Wall", "-Wextra", "-Wno-unused-parameter"]
 
 
 def _nvcc() -> str:

@@ -19,6 +19,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <pthread.h>
 #include <new>
 
 #include "gpsb_kernels.cuh"
@@ -267,30 +268,52 @@ __device__ __forceinline__ uint4 ld_host16(const volatile void* p)
 __global__ void __launch_bounds__(kEplThreads)
 k_epl_session(const volatile RtCmd* __restrict__ host_cmd, RtRsp* __restrict__ host_rsp,
               const uint32_t* __restrict__ codes, const uint32_t* __restrict__ signal, uint32_t ring_ms,
-              uint32_t last_seq, uint64_t idle_ns, uint64_t life_ns)
+              uint64_t idle_ns, uint64_t life_ns, uint32_t stagger_ns)
 {
     __shared__ int16_t sums[8];
     __shared__ uint32_t cw[8];
+    __shared__ uint32_t seen_seq;      // newest command tag any poller has seen
     __shared__ int go;
     const volatile RtCmd* my_cmd = host_cmd + blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // Every slot carries its own sequence; what this slot answered last is in its response record, so a
+    // re-launched kernel picks up exactly the commands that are still unanswered.
+    uint32_t last_seq = 0;
+    if (threadIdx.x == 0) {
+        const uint4 r = ld_host16(host_rsp + blockIdx.x);
+        seen_seq = r.w;
+        go = 1;
+    }
+    __syncthreads();
+    last_seq = seen_seq;
     const uint64_t t_begin = global_ns();
     uint64_t t_last = t_begin;
     for (;;) {
-        if (threadIdx.x == 0) {
-            go = 0;
+        // one poller per warp, staggered by a fraction of the PCIe read latency, so a new command is noticed
+        // about a quarter of a read period after it lands instead of half a period
+        if (lane == 0) {
+            if (warp) {      // phase offset of this poller; gives up at once when another poller has the command
+                const uint64_t t0 = global_ns();
+                while (global_ns() - t0 < (uint64_t)stagger_ns * warp)
+                    if (*(volatile uint32_t*)&seen_seq != last_seq) break;
+            }
             for (;;) {
+                if (*(volatile uint32_t*)&seen_seq != last_seq) break;       // another poller has it
                 const uint4 a = ld_host16(&my_cmd->w[0]);
                 const uint4 b = ld_host16(&my_cmd->w[4]);
                 if (a.w == b.w && a.w != last_seq) {
-                    if (a.w != kRtStop) {
+                    if (atomicCAS(&seen_seq, last_seq, a.w) == last_seq) {
                         cw[0] = a.x; cw[1] = a.y; cw[2] = a.z; cw[3] = a.w;
                         cw[4] = b.x; cw[5] = b.y; cw[6] = b.z;
-                        go = 1;
+                        go = a.w != kRtStop;
                     }
                     break;
                 }
                 const uint64_t now = global_ns();
-                if (now - t_last > idle_ns || now - t_begin > life_ns) break;   // host gone quiet / lease over
+                if (now - t_last > idle_ns || now - t_begin > life_ns) {      // host gone quiet / lease over
+                    if (atomicCAS(&seen_seq, last_seq, last_seq + 1u) == last_seq) go = 0;
+                    break;
+                }
             }
         }
         __syncthreads();
@@ -310,7 +333,7 @@ k_epl_session(const volatile RtCmd* __restrict__ host_cmd, RtRsp* __restrict__ h
             __syncthreads();
             if (threadIdx.x == 0) publish_sums(host_rsp + blockIdx.x, sums, last_seq);
         }
-        if (threadIdx.x == 0) t_last = global_ns();
+        t_last = global_ns();
         __syncthreads();
     }
 }
@@ -478,7 +501,10 @@ struct gpsb_ctx {
     RtCmd* d_cmd = nullptr;        // device alias
     RtRsp* h_rsp = nullptr;        // kRtMaxCells response slots, host view
     RtRsp* d_rsp = nullptr;
-    uint32_t rt_seq = 0;
+    uint32_t rt_seq = 0;                 // tag of the launch-per-ms path (k_epl_rt)
+    uint32_t slot_seq[128] = {};         // per-slot tags of the session path; each slot is driven by ONE thread
+    pthread_mutex_t relaunch_lock = PTHREAD_MUTEX_INITIALIZER;
+    pthread_mutex_t call_lock = PTHREAD_MUTEX_INITIALIZER;   // serialises the staged (non-session) entry points
     int realtime = 1;
     cudaStream_t rt_stream = nullptr;   // the session kernel lives on its own stream
     uint32_t session_slots = 0;         // > 0 while a session kernel is (supposed to be) resident
@@ -521,67 +547,86 @@ static int check_launch(gpsb_ctx* c, const char* what)
     return GPSB_OK;
 }
 
-/* ------------------------------------------------------------------ closed-loop mailbox helpers */
-static uint32_t next_seq(gpsb_ctx* c)
-{
-    uint32_t s = ++c->rt_seq;
-    if (s == 0 || s == kRtStop) s = c->rt_seq = 1;
-    return s;
-}
+struct CallGuard {   // the staged entry points share one pinned/device staging buffer and one stream
+    pthread_mutex_t* m;
+    explicit CallGuard(gpsb_ctx* c) : m(&c->call_lock) { pthread_mutex_lock(m); }
+    ~CallGuard() { pthread_mutex_unlock(m); }
+};
 
-static int session_launch(gpsb_ctx* c, uint32_t last_seq)
+/* ------------------------------------------------------------------ closed-loop mailbox helpers */
+static int session_launch(gpsb_ctx* c)
 {
     // 250 ms without a command, or 20 s of life, and the kernel leaves on its own (it is re-launched on demand)
     k_epl_session<<<c->session_slots, kEplThreads, 0, c->rt_stream>>>(c->d_cmd, c->d_rsp, c->d_codes, c->d_signal,
-                                                                     c->ring_ms, last_seq, 250000000ull,
-                                                                     20000000000ull);
+                                                                     c->ring_ms, 250000000ull, 20000000000ull, 400u);
     return check_launch(c, "k_epl_session");
 }
 
-// Wait until response slots 0..n-1 carry `seq`, then copy the sums out.  `watch` is the stream whose work
-// produces them; in session mode a finished stream means the resident kernel timed out and is re-launched.
-static int collect_responses(gpsb_ctx* c, uint32_t n, uint32_t seq, int16_t* out, cudaStream_t watch, bool session)
+static uint32_t bump(uint32_t s)
 {
-    for (uint32_t i = 0; i < n; i++) {
-        volatile RtRsp* r = c->h_rsp + i;
-        uint64_t spins = 0;
-        while (r->seq != seq) {
-            if ((++spins & 0x3FFFF) != 0) continue;
-            cudaError_t q = cudaStreamQuery(watch);
-            if (q == cudaErrorNotReady) continue;
-            if (q != cudaSuccess) return fail(GPSB_ERR_CUDA, "closed-loop kernel failed: %s", cudaGetErrorString(q));
-            if (r->seq == seq) break;
-            if (!session) return fail(GPSB_ERR_CUDA, "k_epl_rt finished without publishing cell %u", i);
-            c->session_relaunches++;                 // the resident kernel left (idle / lease): start a new one
-            int rc = session_launch(c, seq - 1);
-            if (rc) return rc;
+    ++s;
+    if (s == 0 || s == kRtStop) s = 1;
+    return s;
+}
+
+// Wait until the response record of `slot` carries `seq`, then copy the six sums out.  `watch` is the stream
+// whose work produces it; in session mode a finished stream means the resident kernel timed out (idle / lease)
+// and a new one is started - by exactly one of the waiting threads.
+static int wait_slot(gpsb_ctx* c, uint32_t slot, uint32_t seq, int16_t* out6, cudaStream_t watch, bool session)
+{
+    volatile RtRsp* r = c->h_rsp + slot;
+    uint64_t spins = 0;
+    while (r->seq != seq) {
+        if ((++spins & 0x3FFFF) != 0) continue;
+        if (session) pthread_mutex_lock(&c->relaunch_lock);
+        cudaError_t q = cudaStreamQuery(watch);
+        int rc = GPSB_OK;
+        if (q != cudaErrorNotReady && r->seq != seq) {
+            if (q != cudaSuccess) rc = fail(GPSB_ERR_CUDA, "closed-loop kernel failed: %s", cudaGetErrorString(q));
+            else if (!session) rc = fail(GPSB_ERR_CUDA, "k_epl_rt finished without publishing cell %u", slot);
+            else {
+                c->session_relaunches++;
+                rc = session_launch(c);
+            }
         }
-        __atomic_thread_fence(__ATOMIC_ACQUIRE);
-        memcpy(out + 6u * i, (const void*)r->sums, 12);
+        if (session) pthread_mutex_unlock(&c->relaunch_lock);
+        if (rc) return rc;
     }
+    __atomic_thread_fence(__ATOMIC_ACQUIRE);
+    memcpy(out6, (const void*)r->sums, 12);
     return GPSB_OK;
+}
+
+// Write one command into a slot: payload first, then the tag in both 16-byte halves.
+static uint32_t post_slot(gpsb_ctx* c, uint32_t slot, const gpsb_epl_req* rq)
+{
+    volatile uint32_t* w = c->h_cmd[slot].w;
+    const uint32_t seq = c->slot_seq[slot] = bump(c->slot_seq[slot]);
+    if (rq) {
+        w[0] = rq->sv_slot;
+        w[1] = rq->ms_index;
+        w[2] = rq->acc0;
+        w[4] = rq->step32;
+        w[5] = (uint32_t)rq->off_e | ((uint32_t)rq->off_p << 16);
+        w[6] = (uint32_t)rq->off_l | ((uint32_t)rq->off_bits << 16);
+    } else {
+        w[0] = 0xFFFFFFFFu;                          // keep-alive: the slot has no work this millisecond
+    }
+    __atomic_thread_fence(__ATOMIC_RELEASE);         // payload before tags (x86 keeps store order anyway)
+    w[3] = seq;
+    w[7] = seq;
+    return seq;
 }
 
 static int session_exchange(gpsb_ctx* c, uint32_t n, const gpsb_epl_req* req, int16_t* out)
 {
-    const uint32_t seq = next_seq(c);
+    uint32_t seq[kRtMaxCells];
+    for (uint32_t i = 0; i < c->session_slots; i++) seq[i] = post_slot(c, i, i < n ? &req[i] : nullptr);
     for (uint32_t i = 0; i < n; i++) {
-        volatile uint32_t* w = c->h_cmd[i].w;
-        w[0] = req[i].sv_slot;
-        w[1] = req[i].ms_index;
-        w[2] = req[i].acc0;
-        w[4] = req[i].step32;
-        w[5] = (uint32_t)req[i].off_e | ((uint32_t)req[i].off_p << 16);
-        w[6] = (uint32_t)req[i].off_l | ((uint32_t)req[i].off_bits << 16);
+        int rc = wait_slot(c, i, seq[i], out + 6u * i, c->rt_stream, true);
+        if (rc) return rc;
     }
-    for (uint32_t i = n; i < c->session_slots; i++) c->h_cmd[i].w[0] = 0xFFFFFFFFu;   // keep idle slots alive
-    __atomic_thread_fence(__ATOMIC_RELEASE);         // payload before tags (x86: store order is kept anyway)
-    for (uint32_t i = 0; i < c->session_slots; i++) {
-        volatile uint32_t* w = c->h_cmd[i].w;
-        w[3] = seq;
-        w[7] = seq;
-    }
-    return collect_responses(c, n, seq, out, c->rt_stream, true);
+    return GPSB_OK;
 }
 
 extern "C" {
@@ -864,17 +909,26 @@ int gpsb_track_epl(gpsb_ctx* c, uint32_t n, const gpsb_epl_req* req, int16_t* ou
     if (rc) return rc;
     CU(cudaSetDevice(c->device));
     if (c->session_slots && n <= c->session_slots) return session_exchange(c, n, req, out);
-    if (c->realtime && n <= (uint32_t)kRtMaxCells) {
+    if (c->realtime && !c->session_slots && n <= (uint32_t)kRtMaxCells) {
         // closed-loop fast path: one launch, no copies, completion by sequence numbers in mapped host memory
         static_assert(sizeof(EplRtBatch) <= 4096, "request batch must fit the kernel parameter space");
         EplRtBatch batch;
         memcpy(batch.rq, req, (size_t)n * sizeof(gpsb_epl_req));
-        const uint32_t seq = next_seq(c);
+        // tags must differ from whatever the response records hold: continue each slot's own sequence
+        uint32_t seq = 0;
+        for (uint32_t i = 0; i < n; i++) seq = c->slot_seq[i] > seq ? c->slot_seq[i] : seq;
+        seq = bump(seq);
+        for (uint32_t i = 0; i < n; i++) c->slot_seq[i] = seq;
         k_epl_rt<<<n, kEplThreads, 0, c->stream>>>(batch, c->d_rsp, c->d_codes, c->d_signal, c->ring_ms, seq);
         rc = check_launch(c, "k_epl_rt");
         if (rc) return rc;
-        return collect_responses(c, n, seq, out, c->stream, false);
+        for (uint32_t i = 0; i < n; i++) {
+            rc = wait_slot(c, i, seq, out + 6u * i, c->stream, false);
+            if (rc) return rc;
+        }
+        return GPSB_OK;
     }
+    CallGuard guard(c);
     size_t req_b = (size_t)n * sizeof(gpsb_epl_req), out_b = (size_t)n * 12;
     size_t out_off = (req_b + 255) & ~(size_t)255;
     rc = ensure_stage(c, out_off + out_b);
@@ -911,6 +965,7 @@ int gpsb_search(gpsb_ctx* c, uint32_t n, const gpsb_search_req* req, gpsb_search
     if (n == 0) return GPSB_OK;
     int rc = check_search(c, n, req);
     if (rc) return rc;
+    CallGuard guard(c);
     CU(cudaSetDevice(c->device));
     // staging layout: [direct requests][direct index map][groups][results by original index]
     const size_t req_b = (size_t)n * sizeof(gpsb_search_req), map_b = (size_t)n * 4;
@@ -993,9 +1048,12 @@ int gpsb_session_begin(gpsb_ctx* c, uint32_t n_slots)
         return fail(GPSB_ERR_STATE, "tracking sessions disabled by GPSB_DISABLE_SESSION");
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));            // codes / frames uploaded so far are visible to the session
-    for (uint32_t i = 0; i < n_slots; i++) c->h_cmd[i].w[3] = c->h_cmd[i].w[7] = c->rt_seq;
+    for (uint32_t i = 0; i < n_slots; i++) {         // nothing pending: command tag == answered tag
+        c->h_cmd[i].w[3] = c->h_cmd[i].w[7] = c->slot_seq[i];
+        c->h_rsp[i].seq = c->slot_seq[i];
+    }
     c->session_slots = n_slots;
-    int rc = session_launch(c, c->rt_seq);
+    int rc = session_launch(c);
     if (rc) c->session_slots = 0;
     return rc;
 }
@@ -1009,9 +1067,33 @@ int gpsb_session_end(gpsb_ctx* c)
         w[3] = kRtStop;
         w[7] = kRtStop;
     }
+    const uint32_t n = c->session_slots;
     c->session_slots = 0;
     CU(cudaStreamSynchronize(c->rt_stream));
+    for (uint32_t i = 0; i < n; i++) c->h_cmd[i].w[3] = c->h_cmd[i].w[7] = c->slot_seq[i];
     return GPSB_OK;
+}
+
+/* Per-slot, thread-safe halves of a session exchange: each slot must be driven by one thread at a time, different
+ * slots may be driven by different threads concurrently (gpsb_rx_track_run gives every worker its own channels). */
+int gpsb_session_post(gpsb_ctx* c, uint32_t slot, const gpsb_epl_req* req, uint32_t* seq)
+{
+    if (!c || !seq) return fail(GPSB_ERR_ARG, "gpsb_session_post: null argument");
+    if (slot >= c->session_slots) return fail(GPSB_ERR_STATE, "slot %u is not part of the open session", slot);
+    if (req) {
+        if (req->sv_slot >= c->max_sv || !c->code_set[req->sv_slot]) return fail(GPSB_ERR_STATE, "no code set for slot %u", req->sv_slot);
+        if (req->off_e >= GPSB_OFFSETS || req->off_p >= GPSB_OFFSETS || req->off_l >= GPSB_OFFSETS || req->off_bits > 15)
+            return fail(GPSB_ERR_ARG, "offset out of range");
+    }
+    *seq = post_slot(c, slot, req);
+    return GPSB_OK;
+}
+
+int gpsb_session_wait(gpsb_ctx* c, uint32_t slot, uint32_t seq, int16_t out6[6])
+{
+    if (!c || !out6) return fail(GPSB_ERR_ARG, "gpsb_session_wait: null argument");
+    if (slot >= c->session_slots) return fail(GPSB_ERR_STATE, "slot %u is not part of the open session", slot);
+    return wait_slot(c, slot, seq, out6, c->rt_stream, true);
 }
 
 uint32_t gpsb_session_slots(const gpsb_ctx* c) { return c ? c->session_slots : 0; }

@@ -85,6 +85,8 @@ def load_library(path: Path | None = None) -> C.CDLL:
         "gpsb_session_begin": (i32, [vp, u32]),
         "gpsb_session_end": (i32, [vp]),
         "gpsb_session_slots": (u32, [vp]),
+        "gpsb_session_post": (i32, [vp, u32, vp, C.POINTER(u32)]),
+        "gpsb_session_wait": (i32, [vp, u32, u32, vp]),
         "gpsb_track_epl_dev": (i32, [vp, u32, vp, vp]),
         "gpsb_search_dev": (i32, [vp, u32, vp, vp]),
         "gpsb_sweep_dev": (i32, [vp, vp, u32, vp, u32, u32, u32, u32, vp]),

@@ -10,9 +10,9 @@
 #include "host_internal.h"
 
 static gpsb_ctx* g_ctx = NULL;
-static int g_last_status = 0;
+static __thread int g_last_status = 0;
 static uint32_t g_sat_cnt = GPS_SAT_CNT;
-static uint32_t g_packet_cnt = 0;
+static __thread uint32_t g_packet_cnt = 0;   /* per thread: batched workers run channels at their own pace */
 static int (*g_rand)(void) = NULL;
 gpsb_aux g_shared_aux;
 
@@ -37,7 +37,19 @@ __attribute__((weak)) uint32_t signal_capture_get_packet_cnt(void) { return g_pa
 uint32_t hx_now_ms(void) { return signal_capture_get_packet_cnt(); }
 
 void gpsb_host_set_rand(int (*fn)(void)) { g_rand = fn; }
-int hx_rand(void) { return g_rand ? g_rand() : rand(); }
+int hx_rand(gpsb_aux* aux)
+{
+    if (g_rand) return g_rand();
+    if (!aux || aux == &g_shared_aux) return rand();          /* reference-named API: the process-wide stream */
+    if (!aux->rnd_ready) {
+        memset(&aux->rnd, 0, sizeof aux->rnd);
+        initstate_r(1u, aux->rnd_state, sizeof aux->rnd_state, &aux->rnd);
+        aux->rnd_ready = 1;
+    }
+    int32_t v = 0;
+    random_r(&aux->rnd, &v);
+    return (int)v;
+}
 
 /* NCO word: fp32 divide then truncation (gps_misc.c:219, :199, :250). */
 uint32_t hx_nco_step(float freq_hz)

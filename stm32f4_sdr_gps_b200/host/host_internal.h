@@ -4,6 +4,7 @@
 
 #include <stddef.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "gpsb_host.h"
@@ -27,12 +28,17 @@ typedef struct gpsb_aux {
     uint8_t  slot_bits[GPSB_SLOT_LEN];          /* tmp_nav_data, nav_data.c:51 */
     uint32_t slot_start_ticks;                  /* gps_channel_tmp_start_time_ticks, nav_data.c:29 */
     int8_t   last_nav_bit;                      /* observer: bit handed to the word assembler this ms, or -1 */
+    /* private rand() stream of a batched channel: same generator and default seed as libc rand(), so the
+     * channel draws what it would draw as the only channel of a process (tracking.c:316) */
+    int      rnd_ready;
+    struct random_data rnd;
+    char     rnd_state[128];
 } gpsb_aux;
 
 extern gpsb_aux g_shared_aux;
 
 uint32_t hx_now_ms(void);
-int hx_rand(void);
+int hx_rand(gpsb_aux* aux);
 uint32_t hx_nco_step(float freq_hz);
 uint32_t hx_nco_step32(float freq_hz);
 

@@ -7,7 +7,9 @@
  * when that channel is the only active one (the reference's shared scratch, acquisition.c:28-33,
  * tracking.c:33-34, nav_data.c:29,48-51, only works one channel at a time).
  */
+#include <pthread.h>
 #include <stdlib.h>
+#include <unistd.h>
 
 #include "../../include/gpsb_flat_state.h"
 #include "host_internal.h"
@@ -24,7 +26,16 @@ struct gpsb_rx {
     gpsb_search_req* s_rq;
     gpsb_search_res* s_res;
     uint32_t* s_owner;
+    uint32_t threads;            /* 0 = automatic */
 };
+
+typedef struct track_job {
+    gpsb_rx* rx;
+    uint32_t worker, n_workers, ms0, n_ms;
+    int16_t* iq_log;
+    int8_t* nav_log;
+    int rc;
+} track_job;
 
 int gpsb_rx_create(gpsb_rx** out, gpsb_ctx* ctx, gps_ch_t* channels, uint32_t n_ch)
 {
@@ -125,12 +136,91 @@ int gpsb_rx_track_ms(gpsb_rx* rx, uint32_t ms)
     return GPSB_OK;
 }
 
+/* One worker of a threaded run: drives its own channels (i % n_workers == worker) through all n_ms milliseconds
+ * at its own pace - channels are independent, so nothing forces them through the millisecond in lockstep.  Per
+ * ms it posts every channel's cell to that channel's session slot first and only then collects, so the PCIe
+ * round trips of its channels overlap. */
+static void* track_worker(void* arg)
+{
+    track_job* job = (track_job*)arg;
+    gpsb_rx* rx = job->rx;
+    uint32_t seq[128];
+    job->rc = GPSB_OK;
+    for (uint32_t m = 0; m < job->n_ms && job->rc == GPSB_OK; m++) {
+        const uint32_t ms = job->ms0 + m;
+        const uint8_t index = (uint8_t)(ms % GPSB_SLOT_LEN);
+        gpsb_host_set_packet_cnt(ms);
+        for (uint32_t i = job->worker; i < rx->n_ch; i += job->n_workers) {
+            gpsb_plan* p = &rx->plan[i];
+            rx->aux[i].last_nav_bit = -1;
+            hx_trk_plan(&rx->ch[i], &rx->aux[i], ms, index, p);
+            int rc = gpsb_session_post(rx->ctx, i, p->want == GPSB_WANT_EPL ? &p->epl : NULL, &seq[i]);
+            if (rc != GPSB_OK) job->rc = hx_note(rc);
+        }
+        for (uint32_t i = job->worker; i < rx->n_ch && job->rc == GPSB_OK; i += job->n_workers) {
+            gpsb_plan* p = &rx->plan[i];
+            int16_t iq[6] = {0, 0, 0, 0, 0, 0};
+            if (p->want == GPSB_WANT_EPL) {
+                int rc = gpsb_session_wait(rx->ctx, i, seq[i], iq);
+                if (rc != GPSB_OK) { job->rc = hx_note(rc); break; }
+                hx_trk_finish_epl(&rx->ch[i], &rx->aux[i], index, iq);
+            } else if (p->want == GPSB_WANT_SEARCH) {
+                gpsb_search_res res = {0, 0, 0, 0};
+                if (p->search.start < p->search.stop) {
+                    int rc = gpsb_search(rx->ctx, 1, &p->search, &res);
+                    if (rc != GPSB_OK) { job->rc = hx_note(rc); break; }
+                }
+                hx_trk_finish_search(&rx->ch[i], &rx->aux[i], index, &res);
+            }
+            if (job->iq_log) memcpy(job->iq_log + ((size_t)m * rx->n_ch + i) * 6, iq, 12);
+            if (job->nav_log)
+                job->nav_log[(size_t)m * rx->n_ch + i] = p->want == GPSB_WANT_EPL ? rx->aux[i].last_nav_bit : -1;
+        }
+    }
+    return NULL;
+}
+
+void gpsb_rx_set_threads(gpsb_rx* rx, uint32_t n) { if (rx) rx->threads = n; }
+
+static uint32_t pick_workers(const gpsb_rx* rx)
+{
+    uint32_t n = rx->threads;
+    if (n == 0) {
+        long cpus = sysconf(_SC_NPROCESSORS_ONLN);
+        n = cpus > 2 ? (uint32_t)(cpus - 1) : 1;
+        if (n > 16) n = 16;
+    }
+    if (n > rx->n_ch) n = rx->n_ch;
+    return n ? n : 1;
+}
+
 int gpsb_rx_track_run(gpsb_rx* rx, uint32_t ms0, uint32_t n_ms, int16_t* iq_log, int8_t* nav_log)
 {
     if (!rx) return GPSB_ERR_ARG;
     /* a run of many milliseconds is served by resident CTAs (one per channel): no launch per ms */
     const int own_session = n_ms > 8 && rx->n_ch <= 128 && gpsb_session_slots(rx->ctx) == 0 &&
                             gpsb_session_begin(rx->ctx, rx->n_ch) == GPSB_OK;
+    const uint32_t n_workers = own_session ? pick_workers(rx) : 1;
+    if (own_session && n_workers > 1) {
+        pthread_t tid[16];
+        track_job job[16];
+        for (uint32_t w = 0; w < n_workers; w++) {
+            job[w] = (track_job){rx, w, n_workers, ms0, n_ms, iq_log, nav_log, GPSB_OK};
+            if (pthread_create(&tid[w], NULL, track_worker, &job[w]) != 0) {
+                job[w].rc = GPSB_ERR_NOMEM;
+                track_worker(&job[w]);               /* could not start a thread: do its share here */
+                tid[w] = 0;
+            }
+        }
+        int rc = GPSB_OK;
+        for (uint32_t w = 0; w < n_workers; w++) {
+            if (tid[w]) pthread_join(tid[w], NULL);
+            if (job[w].rc != GPSB_OK) rc = job[w].rc;
+        }
+        int rc_end = gpsb_session_end(rx->ctx);
+        gpsb_host_set_packet_cnt(ms0 + n_ms - 1);
+        return hx_note(rc != GPSB_OK ? rc : rc_end);
+    }
     for (uint32_t m = 0; m < n_ms; m++) {
         for (uint32_t i = 0; i < rx->n_ch; i++) rx->aux[i].last_nav_bit = -1;
         int rc = gpsb_rx_track_ms(rx, ms0 + m);

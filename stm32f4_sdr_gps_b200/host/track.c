@@ -212,7 +212,7 @@ static void pll_update(gps_ch_t* ch, uint8_t index, int16_t ip, int16_t qp)
 
 /* tracking.c:261-327: two or more sign flips of IP inside one 4-ms slot cannot be data; count them and,
  * after a long bad streak, jump the carrier to a random frequency at least 200 Hz away. */
-static void lock_check(gps_ch_t* ch, uint8_t index, int16_t ip)
+static void lock_check(gps_ch_t* ch, gpsb_aux* aux, uint8_t index, int16_t ip)
 {
     gps_tracking_t* t = &ch->tracking_data;
     if (index >= GPSB_SLOT_LEN) return;
@@ -239,7 +239,7 @@ static void lock_check(gps_ch_t* ch, uint8_t index, int16_t ip)
         t->pll_bad_state_cnt = 0;
         int16_t candidate, away;
         do {
-            uint16_t r = (uint16_t)(hx_rand() % ACQ_SEARCH_STEP_HZ);
+            uint16_t r = (uint16_t)(hx_rand(aux) % ACQ_SEARCH_STEP_HZ);
             candidate = (int16_t)(ch->acq_data.found_freq_offset_hz - r + (ACQ_SEARCH_STEP_HZ / 2));
             away = (int16_t)((int16_t)t->if_freq_offset_hz - candidate);
         } while (abs(away) < 200);
@@ -248,10 +248,10 @@ static void lock_check(gps_ch_t* ch, uint8_t index, int16_t ip)
 }
 
 /* tracking.c:214-256 */
-static void fll_update(gps_ch_t* ch, uint8_t index, int16_t ip, int16_t qp)
+static void fll_update(gps_ch_t* ch, gpsb_aux* aux, uint8_t index, int16_t ip, int16_t qp)
 {
     gps_tracking_t* t = &ch->tracking_data;
-    lock_check(ch, index, ip);
+    lock_check(ch, aux, index, ip);
     if (index == 0) {                                 /* first ms of a slot: previous sample is from another time */
         t->fll_old_i = ip;
         t->fll_old_q = qp;
@@ -276,7 +276,7 @@ void hx_trk_finish_epl(gps_ch_t* ch, gpsb_aux* aux, uint8_t index, const int16_t
     const int16_t ie = iq[0], qe = iq[1], ip = iq[2], qp = iq[3], il = iq[4], ql = iq[5];
     dll_update(t, ie, qe, il, ql);
     pll_update(ch, index, ip, qp);
-    fll_update(ch, index, ip, qp);
+    fll_update(ch, aux, index, ip, qp);
     hx_nav_new_code(ch, aux, index, ip);
 
     t->i_part_summ += (uint32_t)abs(ip);

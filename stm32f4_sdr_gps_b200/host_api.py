@@ -114,6 +114,7 @@ def load_host_library(path: Path | None = None) -> C.CDLL:
         "gpsb_rx_create": (i32, [C.POINTER(vp), vp, vp, u32]), "gpsb_rx_destroy": (None, [vp]),
         "gpsb_rx_track_ms": (i32, [vp, u32]), "gpsb_rx_track_run": (i32, [vp, u32, u32, vp, vp]),
         "gpsb_rx_acquire_ms": (i32, [vp, u32]),
+        "gpsb_rx_set_threads": (None, [vp, u32]),
         "gpsb_rx_cold_sweep": (i32, [vp, C.c_int32, C.c_int32, u32, u32, u32, vp, vp]),
         "gpsb_host_plan_acq": (i32, [vp, u32, C.POINTER(Plan)]),
         "gpsb_host_finish_acq": (i32, [vp, C.POINTER(Plan), C.POINTER(SearchRes)]),
@@ -191,6 +192,9 @@ class Receiver:
         self._check(self.lib.gpsb_rx_track_run(self._rx, ms0, n_ms, iq.ctypes.data if log else None,
                                                nav.ctypes.data if log else None))
         return iq, nav
+
+    def set_threads(self, n: int) -> None:
+        self.lib.gpsb_rx_set_threads(self._rx, n)
 
     def acquire_ms(self, ms: int) -> None:
         self._check(self.lib.gpsb_rx_acquire_ms(self._rx, ms))

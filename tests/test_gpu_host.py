@@ -22,13 +22,16 @@ def _armed_channels(golden, prns=(5, 14)):
     return ch
 
 
-def test_batched_receiver_closed_loop_equals_reference(host_engine, golden):
-    """600 ms closed loop (pre-track, E/P/L loops, nav-bit sync) for two satellites in one receiver:
+@pytest.mark.parametrize("threads", [0, 1])
+def test_batched_receiver_closed_loop_equals_reference(host_engine, golden, threads):
+    """threads=0: one host worker per channel, each driving its own resident-kernel slot at its own pace;
+    threads=1: single thread, all channels in lockstep.  600 ms closed loop (pre-track, E/P/L loops, nav-bit sync) for two satellites in one receiver:
     I/Q sums, nav bits and the final channel records equal the reference run per satellite."""
     sig = golden["scene_signal"]
     host_engine.upload_signal(0, sig)
     ch = _armed_channels(golden)
     rx = Receiver(host_engine, ch)
+    rx.set_threads(threads)
     launches0 = host_engine.launch_count
     iq, nav = rx.track_run(0, 600)
     assert host_engine.launch_count - launches0 <= 600 * 2          # one launch per kind per ms, not per channel

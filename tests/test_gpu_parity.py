@@ -336,3 +336,48 @@ def test_closed_loop_paths_agree(engine, oracle):
     finally:
         engine.session_end()
     assert np.array_equal(engine.track_epl(rq), want2)
+
+
+def test_sweep_tile_shapes_ring_wrap_and_big_batches(engine, oracle):
+    """Ragged / maximum-size inputs: every satellite-tile variant of the dp4a sweep (1..9 satellites), a
+    sweep whose milliseconds wrap around the end of the signal ring, an E/P/L batch larger than the
+    closed-loop fast path (n > 128), and one of exactly 128."""
+    rng = np.random.default_rng(55)
+    ring = engine.ring_ms
+    sig = rng.integers(0, 256, (3, 2046), dtype=np.uint8)
+    ms0 = ring * 3 - 1                                     # frames ring-1, 0, 1
+    engine.upload_signal(ms0, sig)
+    prns = list(range(2, 11))
+    for s, prn in enumerate(prns):
+        engine.set_code_prn(s, prn)
+    step = np.array([nco_step32(np.float32(IF_HZ + 750))], np.uint32)
+    full = None
+    for n_sv in (9, 5, 4, 3, 2, 1):
+        res = engine.sweep(np.arange(n_sv), step, ms0, 3, 1)
+        if full is None:
+            full = res
+            for (s, m) in ((0, 0), (8, 1), (3, 2)):
+                want = oracle.search_cell(oracle.ca_code(prns[s]), sig[m], float(np.float32(IF_HZ + 750)), 1, 0, 2046)
+                assert (res["max"][s, 0, m], res["phase"][s, 0, m], res["avg"][s, 0, m]) == want
+        else:
+            assert np.array_equal(res, full[:n_sv]), n_sv
+    assert engine.sweep(np.zeros(0, np.uint32), step, ms0, 3, 0).size == 0
+    for n in (128, 129, 700):
+        rq = np.zeros(n, EPL_REQ)
+        rq["sv_slot"] = rng.integers(0, 9, n)
+        rq["ms_index"] = ms0 + rng.integers(0, 3, n)
+        rq["acc0"] = rng.integers(0, 2**32, n, dtype=np.uint64)
+        rq["step32"] = rng.integers(0, 2**32, n, dtype=np.uint64)
+        rq["off_p"] = rng.integers(0, 2046, n)
+        rq["off_e"] = rng.integers(0, 2046, n)
+        rq["off_l"] = rng.integers(0, 2046, n)
+        rq["off_bits"] = rng.integers(0, 8, n)
+        out = engine.track_epl(rq)
+        engine.set_realtime(False)
+        assert np.array_equal(engine.track_epl(rq), out)
+        engine.set_realtime(True)
+        for i in rng.integers(0, n, 12):
+            want = oracle.epl_explicit(oracle.ca_code(prns[rq["sv_slot"][i]]), sig[rq["ms_index"][i] - ms0],
+                                       int(rq["acc0"][i]), int(rq["step32"][i]), int(rq["off_e"][i]),
+                                       int(rq["off_p"][i]), int(rq["off_l"][i]), int(rq["off_bits"][i]))
+            assert np.array_equal(out[i], want), (n, i)
