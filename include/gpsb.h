@@ -130,6 +130,45 @@ uint32_t gpsb_session_slots(const gpsb_ctx* ctx);
 int gpsb_session_post(gpsb_ctx* ctx, uint32_t slot, const gpsb_epl_req* req, uint32_t* seq);
 int gpsb_session_wait(gpsb_ctx* ctx, uint32_t slot, uint32_t seq, int16_t out6[6]);
 
+/* ---------------------------------------------------------------- device-resident tracking loop - */
+/*
+ * The whole closed loop of PM/GPS/tracking.c:92-170 + nav_data.c:46-138 for n_ch channels over n_ms
+ * consecutive milliseconds in ONE launch (k_track_run): per channel one CTA keeps the channel record in
+ * shared memory, correlates each millisecond from the HBM signal ring and runs the reference's DLL / PLL /
+ * FLL, false-lock check, NCO planning, bit synchronisation and word assembly on the device between two
+ * correlations - no host round trip per millisecond.  "Every satellite every millisecond" schedule: slot
+ * index = ms % 4, ms counter = frame index.
+ *
+ *   channels  n_ch records of gps_ch_t (include/gpsb_host.h; PM/GPS/gps_misc.h:184-193), channel_bytes each,
+ *             in GPS_TRACKING_RUN (or GPS_PRE_TRACK_DONE); satellite slot == prn; updated in place
+ *   aux       n_ch records of the per-channel scratch (gpsb_aux, core/gpsb_loop_core.h), aux_bytes each
+ *   iq_log    NULL or int16 [n_ms][n_ch][6]  IE,QE,IP,QP,IL,QL
+ *   nav_log   NULL or int8  [n_ms][n_ch]     -1, or the 20-ms data bit handed to the word assembler that ms
+ *   results   n_ch records: milliseconds completed and why the channel stopped early (0 = it did not):
+ *             1 the channel was not in a tracking state (nothing done), 2 the early+late power of millisecond
+ *             done_ms was zero (0/0 in the DLL): its sums are in iq[], the filters were not run - the caller
+ *             finishes that millisecond on the host.  Rows of the logs past done_ms are undefined.
+ * Record sizes are checked against the library's own (gpsb_track_loop_record_bytes).
+ */
+typedef struct gpsb_loop_result {
+    uint32_t done_ms;
+    int32_t  stop;
+    int16_t  iq[6];
+    uint32_t reserved;
+} gpsb_loop_result;
+int gpsb_track_loop(gpsb_ctx* ctx, uint32_t n_ch, void* channels, uint32_t channel_bytes, void* aux,
+                    uint32_t aux_bytes, uint32_t ms0, uint32_t n_ms, int16_t* iq_log, int8_t* nav_log,
+                    gpsb_loop_result* results);
+void gpsb_track_loop_record_bytes(uint32_t* channel_bytes, uint32_t* aux_bytes);
+/* Same loop on device-resident records (no copies, no synchronise): for callers that keep the channel
+ * records in HBM between runs and for timing the kernel alone.  All pointers are device pointers. */
+int gpsb_track_loop_dev(gpsb_ctx* ctx, uint32_t n_ch, void* d_channels, void* d_aux, uint32_t ms0, uint32_t n_ms,
+                        int16_t* d_iq_log, int8_t* d_nav_log, gpsb_loop_result* d_results);
+/* Self-test support: the loop's two float discriminators evaluated on the device for ip in
+ * [ip_lo, ip_lo + n_ip), every qp in [-8184, 8184]; out[(ip - ip_lo) * 16369 + qp + 8184] (host memory).
+ * kind 0: Costas error in units of pi (PM/GPS/tracking.c:180-183), kind 1: FLL angle (tracking.c:232). */
+int gpsb_l0_loop_math(gpsb_ctx* ctx, int kind, int32_t ip_lo, uint32_t n_ip, float* out);
+
 /*
  * One acquisition / pre-track cell = PM/GPS/acquisition.c:282-294 (freq search),
  * :198-209 (code-phase search) and PM/GPS/tracking.c:403-426 (pre-track):

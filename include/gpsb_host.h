@@ -274,6 +274,20 @@ int gpsb_rx_track_ms(gpsb_rx* rx, uint32_t ms);
  *   iq_log  [n_ms][n_ch][6]  IE,QE,IP,QP,IL,QL (zeros for channels not in GPS_TRACKING_RUN that ms)
  *   nav_log [n_ms][n_ch]     -1, or the 20-ms data bit handed to the word assembler that ms        */
 int gpsb_rx_track_run(gpsb_rx* rx, uint32_t ms0, uint32_t n_ms, int16_t* iq_log, int8_t* nav_log);
+/* Where gpsb_rx_track_run keeps the loop filters.  AUTO (default) and DEVICE: the whole run is one launch of the
+ * device-resident loop k_track_run (include/gpsb.h, gpsb_track_loop) for every channel that is tracking; its
+ * float discriminators are the fdlibm atanf/atan2f glibc ships and CUDA's double atan2, checked against the host
+ * libm over their whole (finite) input domain by gpsb_host_certify_loop_math().  HOST: one GPU round trip per
+ * millisecond with the filters on this machine's libm - for hosts whose libm the certificate rejects. */
+enum { GPSB_LOOP_AUTO = 0, GPSB_LOOP_HOST = 1, GPSB_LOOP_DEVICE = 2 };
+void gpsb_rx_set_loop_site(gpsb_rx* rx, int site);
+/* channel-milliseconds processed so far by the device-resident loop and by the per-millisecond host path */
+void gpsb_rx_loop_stats(const gpsb_rx* rx, uint64_t* device_ms, uint64_t* host_ms);
+/* Compares the device's Costas and FLL discriminators with THIS host's libm (atan2f, atan2, atanf as called by
+ * PM/GPS/tracking.c:180-183,232-233) for every (IP, QP) pair in [-8184, 8184]^2 - 2 x 268 M values - using
+ * n_threads host threads (0 = all).  Returns the number of differing bit patterns (0 = the device-resident loop
+ * is bit-exact with a host-resident one on this machine), or a negative gpsb_status. */
+int64_t gpsb_host_certify_loop_math(gpsb_ctx* ctx, uint32_t n_threads);
 /* Host threads used by gpsb_rx_track_run for the per-channel loop filters (each drives its own channels'
  * session slots): 0 = automatic (online CPUs - 1, at most 16, at most one per channel), 1 = single thread. */
 void gpsb_rx_set_threads(gpsb_rx* rx, uint32_t n);

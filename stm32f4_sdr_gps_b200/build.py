@@ -21,6 +21,7 @@ REPO_DIR = PKG_DIR.parent
 LIB_DIR = PKG_DIR / "lib"
 CSRC_DIR = PKG_DIR / "csrc"
 HOST_DIR = PKG_DIR / "host"
+CORE_DIR = PKG_DIR / "core"      # sources compiled into BOTH libraries (the per-millisecond loop step)
 INCLUDE_DIR = REPO_DIR / "include"
 
 CUDA_LIB = LIB_DIR / "libgpsb_cuda.so"
@@ -59,7 +60,7 @@ def _run(cmd) -> None:
 
 def build_cuda(force: bool = False) -> Path:
     srcs = sorted(CSRC_DIR.glob("*.cu"))
-    deps = srcs + sorted(CSRC_DIR.glob("*.cuh")) + sorted(INCLUDE_DIR.glob("*.h"))
+    deps = srcs + sorted(CSRC_DIR.glob("*.cuh")) + sorted(INCLUDE_DIR.glob("*.h")) + sorted(CORE_DIR.glob("*.h"))
     if not force and _newer(CUDA_LIB, deps):
         return CUDA_LIB
     LIB_DIR.mkdir(exist_ok=True)
@@ -71,7 +72,7 @@ def build_host(force: bool = False) -> Path:
     srcs = sorted(HOST_DIR.glob("*.c"))
     if not srcs:
         return HOST_LIB
-    deps = srcs + sorted(HOST_DIR.glob("*.h")) + sorted(INCLUDE_DIR.glob("*.h")) + [CUDA_LIB]
+    deps = srcs + sorted(HOST_DIR.glob("*.h")) + sorted(INCLUDE_DIR.glob("*.h")) + sorted(CORE_DIR.glob("*.h")) + [CUDA_LIB]
     if not force and _newer(HOST_LIB, deps):
         return HOST_LIB
     LIB_DIR.mkdir(exist_ok=True)

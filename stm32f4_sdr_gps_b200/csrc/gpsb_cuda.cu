@@ -33,6 +33,7 @@ struct SweepParams {
 }  // namespace gpsb
 
 #include "gpsb_acq_dp4a.cuh"
+#include "gpsb_track_loop.cuh"
 
 using namespace gpsb;
 
@@ -941,6 +942,87 @@ int gpsb_track_epl(gpsb_ctx* c, uint32_t n, const gpsb_epl_req* req, int16_t* ou
                        cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     memcpy(out, (uint8_t*)c->h_stage + out_off, out_b);
+    return GPSB_OK;
+}
+
+/* ------------------------------------------------------------------ device-resident tracking loop */
+void gpsb_track_loop_record_bytes(uint32_t* channel_bytes, uint32_t* aux_bytes)
+{
+    if (channel_bytes) *channel_bytes = (uint32_t)sizeof(gps_ch_t);
+    if (aux_bytes) *aux_bytes = (uint32_t)sizeof(gpsb_aux);
+}
+
+int gpsb_track_loop_dev(gpsb_ctx* c, uint32_t n_ch, void* d_channels, void* d_aux, uint32_t ms0, uint32_t n_ms,
+                        int16_t* d_iq_log, int8_t* d_nav_log, gpsb_loop_result* d_results)
+{
+    if (!c || !d_channels || !d_aux || !d_results) return fail(GPSB_ERR_ARG, "gpsb_track_loop_dev: null argument");
+    if (n_ch == 0) return GPSB_OK;
+    if (n_ms > c->ring_ms) return fail(GPSB_ERR_ARG, "run of %u ms exceeds the signal ring (%u ms)", n_ms, c->ring_ms);
+    CU(cudaSetDevice(c->device));
+    k_track_run<<<n_ch, kLoopThreads, 0, c->stream>>>((gps_ch_t*)d_channels, (gpsb_aux*)d_aux, c->d_codes, c->d_signal,
+                                                      c->ring_ms, ms0, n_ms, d_iq_log, d_nav_log, d_results);
+    return check_launch(c, "k_track_run");
+}
+
+int gpsb_track_loop(gpsb_ctx* c, uint32_t n_ch, void* channels, uint32_t channel_bytes, void* aux,
+                    uint32_t aux_bytes, uint32_t ms0, uint32_t n_ms, int16_t* iq_log, int8_t* nav_log,
+                    gpsb_loop_result* results)
+{
+    if (!c || !channels || !aux || !results) return fail(GPSB_ERR_ARG, "gpsb_track_loop: null argument");
+    if (channel_bytes != sizeof(gps_ch_t) || aux_bytes != sizeof(gpsb_aux))
+        return fail(GPSB_ERR_ARG, "record sizes %u/%u do not match this library's %zu/%zu", channel_bytes, aux_bytes,
+                    sizeof(gps_ch_t), sizeof(gpsb_aux));
+    if (n_ch == 0) return GPSB_OK;
+    const gps_ch_t* ch = (const gps_ch_t*)channels;
+    for (uint32_t i = 0; i < n_ch; i++) {
+        if (ch[i].prn >= c->max_sv) return fail(GPSB_ERR_ARG, "channel %u: prn %u out of range (max_sv %u)", i, ch[i].prn, c->max_sv);
+        if (!c->code_set[ch[i].prn]) return fail(GPSB_ERR_STATE, "channel %u: no code set for slot %u", i, ch[i].prn);
+    }
+    CallGuard guard(c);
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t ch_b = (size_t)n_ch * sizeof(gps_ch_t), aux_b = (size_t)n_ch * sizeof(gpsb_aux);
+    const size_t res_b = (size_t)n_ch * sizeof(gpsb_loop_result);
+    const size_t iq_b = iq_log ? (size_t)n_ms * n_ch * 12 : 0, nav_b = nav_log ? (size_t)n_ms * n_ch : 0;
+    const size_t o_aux = up(ch_b), o_res = o_aux + up(aux_b), o_iq = o_res + up(res_b), o_nav = o_iq + up(iq_b);
+    const size_t total = o_nav + up(nav_b);
+    int rc = ensure_stage(c, total);
+    if (rc) return rc;
+    uint8_t* h = (uint8_t*)c->h_stage;
+    uint8_t* d = (uint8_t*)c->d_stage;
+    memcpy(h, channels, ch_b);
+    memcpy(h + o_aux, aux, aux_b);
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(d, h, o_aux + aux_b, cudaMemcpyHostToDevice, c->stream));      // records: one copy in
+    rc = gpsb_track_loop_dev(c, n_ch, d, d + o_aux, ms0, n_ms, iq_log ? (int16_t*)(d + o_iq) : nullptr,
+                             nav_log ? (int8_t*)(d + o_nav) : nullptr, (gpsb_loop_result*)(d + o_res));
+    if (rc) return rc;
+    const size_t back = (nav_b ? o_nav + nav_b : iq_b ? o_iq + iq_b : o_res + res_b);
+    CU(cudaMemcpyAsync(h, d, back, cudaMemcpyDeviceToHost, c->stream));               // records + logs: one copy out
+    CU(cudaStreamSynchronize(c->stream));
+    memcpy(channels, h, ch_b);
+    memcpy(aux, h + o_aux, aux_b);
+    memcpy(results, h + o_res, res_b);
+    if (iq_log) memcpy(iq_log, h + o_iq, iq_b);
+    if (nav_log) memcpy(nav_log, h + o_nav, nav_b);
+    return GPSB_OK;
+}
+
+int gpsb_l0_loop_math(gpsb_ctx* c, int kind, int32_t ip_lo, uint32_t n_ip, float* out)
+{
+    if (!c || !out || (kind != 0 && kind != 1)) return fail(GPSB_ERR_ARG, "gpsb_l0_loop_math: bad argument");
+    if (n_ip == 0) return GPSB_OK;
+    if (ip_lo < -8184 || (int64_t)ip_lo + n_ip > 8185) return fail(GPSB_ERR_ARG, "ip range outside [-8184, 8184]");
+    CallGuard guard(c);
+    const size_t bytes = (size_t)n_ip * 16369u * sizeof(float);
+    int rc = ensure_stage(c, bytes);
+    if (rc) return rc;
+    CU(cudaSetDevice(c->device));
+    k_l0_loop_math<<<148 * 8, 256, 0, c->stream>>>(kind, ip_lo, (int)n_ip, (float*)c->d_stage);
+    rc = check_launch(c, "k_l0_loop_math");
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(c->h_stage, c->d_stage, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    memcpy(out, c->h_stage, bytes);
     return GPSB_OK;
 }
 

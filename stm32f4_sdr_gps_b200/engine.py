@@ -90,6 +90,10 @@ def load_library(path: Path | None = None) -> C.CDLL:
         "gpsb_track_epl_dev": (i32, [vp, u32, vp, vp]),
         "gpsb_search_dev": (i32, [vp, u32, vp, vp]),
         "gpsb_sweep_dev": (i32, [vp, vp, u32, vp, u32, u32, u32, u32, vp]),
+        "gpsb_track_loop": (i32, [vp, u32, vp, u32, vp, u32, u32, u32, vp, vp, vp]),
+        "gpsb_track_loop_dev": (i32, [vp, u32, vp, vp, u32, u32, vp, vp, vp]),
+        "gpsb_track_loop_record_bytes": (None, [C.POINTER(u32), C.POINTER(u32)]),
+        "gpsb_l0_loop_math": (i32, [vp, i32, C.c_int32, u32, vp]),
         "gpsb_l0_generate_prn_data2": (i32, [vp, vp, vp, u16]),
         "gpsb_l0_shift_to_zero_freq": (i32, [vp, vp, vp, vp, u32, u32, C.POINTER(u32)]),
         "gpsb_l0_correlation_iq": (i32, [vp, vp, vp, vp, u16, C.POINTER(C.c_int16), C.POINTER(C.c_int16)]),
@@ -259,6 +263,23 @@ class Engine:
                                             ms0, n_ms, off_bits, C.c_void_p(d_res)))
 
     # ------------------------------------------------------------------ level 0
+    def track_loop_dev(self, n_ch: int, d_channels: int, d_aux: int, ms0: int, n_ms: int, d_iq_log: int,
+                       d_nav_log: int, d_results: int) -> None:
+        """k_track_run on device-resident channel records (raw device pointers; only enqueued)."""
+        self._check(self.lib.gpsb_track_loop_dev(self._ctx, n_ch, d_channels, d_aux, ms0, n_ms, d_iq_log or None,
+                                                 d_nav_log or None, d_results))
+
+    def record_bytes(self):
+        a, b = C.c_uint32(), C.c_uint32()
+        self.lib.gpsb_track_loop_record_bytes(C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def l0_loop_math(self, kind: int, ip_lo: int, n_ip: int) -> np.ndarray:
+        """Device values of the Costas error (kind 0) / FLL angle (kind 1) for ip_lo.. x every qp."""
+        out = np.empty((n_ip, 16369), np.float32)
+        self._check(self.lib.gpsb_l0_loop_math(self._ctx, kind, ip_lo, n_ip, out.ctypes.data))
+        return out
+
     def l0_generate_prn_data2(self, chips: np.ndarray, offset_bits: int) -> np.ndarray:
         chips = np.ascontiguousarray(chips, dtype=np.uint8)
         data = np.zeros(1023, np.uint16)

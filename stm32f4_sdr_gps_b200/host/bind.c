@@ -40,29 +40,14 @@ void gpsb_host_set_rand(int (*fn)(void)) { g_rand = fn; }
 int hx_rand(gpsb_aux* aux)
 {
     if (g_rand) return g_rand();
-    if (!aux || aux == &g_shared_aux) return rand();          /* reference-named API: the process-wide stream */
-    if (!aux->rnd_ready) {
-        memset(&aux->rnd, 0, sizeof aux->rnd);
-        initstate_r(1u, aux->rnd_state, sizeof aux->rnd_state, &aux->rnd);
-        aux->rnd_ready = 1;
-    }
-    int32_t v = 0;
-    random_r(&aux->rnd, &v);
-    return (int)v;
+    if (!aux || aux == &g_shared_aux || aux->process_rand) return rand();   /* reference-named API: the process-wide stream */
+    /* batched channel: glibc's generator with its default seed, kept in the channel's own scratch so the
+     * channel draws what it would draw as the only channel of a process, on the host or on the device */
+    return lc_rand31_next(&aux->rnd);
 }
 
-/* NCO word: fp32 divide then truncation (gps_misc.c:219, :199, :250). */
-uint32_t hx_nco_step(float freq_hz)
-{
-    float q = freq_hz / IF_NCO_STEP_HZ;
-    return (uint32_t)q;
-}
-
-uint32_t hx_nco_step32(float freq_hz)
-{
-    uint64_t wide = (uint64_t)hx_nco_step(freq_hz) * 32u;   /* 32 samples per mixed word, gps_misc.c:220 */
-    return (uint32_t)wide;
-}
+uint32_t hx_nco_step(float freq_hz) { return lc_nco_step(freq_hz); }
+uint32_t hx_nco_step32(float freq_hz) { return lc_nco_step32(freq_hz); }
 
 /* Put one millisecond of host samples where the kernels can see it: ring frame (ms counter mod ring). */
 int hx_stage_frame(const uint8_t* data, uint32_t* frame_ms)
@@ -166,13 +151,8 @@ void gps_generate_prn_data2(gps_ch_t* channel, uint16_t* data, uint16_t offset_b
     if (rc == GPSB_OK && b && channel->prn_code[PRN_LENGTH - 1]) data[PRN_SPI_WORDS_CNT] |= (uint16_t)((0xFFFFu << b) >> 16);
 }
 
-/* Catch-up of the carrier NCO over skipped milliseconds (gps_misc.c:196-204).  Pure host arithmetic:
- * note the reference advances by acc_step*16368 per skipped ms although a processed ms advances by
- * 511*32 samples - reproduced as is. */
+/* Catch-up of the carrier NCO over skipped milliseconds (gps_misc.c:196-204), pure host arithmetic. */
 void gps_rewind_if_phase(gps_tracking_t* trk, uint8_t steps)
 {
-    if (!trk) return;
-    uint32_t per_sample = hx_nco_step((float)IF_FREQ_HZ + trk->if_freq_offset_hz);
-    uint64_t advance = (uint64_t)per_sample * BITS_IN_PRN * steps;
-    trk->if_freq_accum += (uint32_t)advance;
+    if (trk) lc_rewind_if_phase(trk, steps);
 }

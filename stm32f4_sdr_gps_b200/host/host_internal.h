@@ -8,33 +8,16 @@
 #include <string.h>
 
 #include "gpsb_host.h"
+#include "../core/gpsb_loop_core.h"
 
-#define GPSB_HALF_CHIPS        (2 * PRN_LENGTH)          /* 2046 code phases, acquisition.c:294 */
-#define GPSB_FINE_PER_HALFCHIP 8                          /* GPS_FINE_RATIO, tracking.c:23 */
-#define GPSB_FINE_RANGE        (GPSB_HALF_CHIPS * GPSB_FINE_PER_HALFCHIP)   /* 16368 */
-#define GPSB_SLOT_LEN          TRACKING_CH_LENGTH
-#define GPSB_FREQ_POINTS_MAX   25                         /* FREQ_SEARCH_POINTS_MAX_CNT, acquisition.c:12 */
-#define GPSB_MAX_BINS          64
+#define GPSB_HALF_CHIPS        LC_HALF_CHIPS             /* 2046 code phases, acquisition.c:294 */
+#define GPSB_FINE_PER_HALFCHIP LC_FINE_PER_HALFCHIP      /* GPS_FINE_RATIO, tracking.c:23 */
+#define GPSB_FINE_RANGE        LC_FINE_RANGE             /* 16368 */
+#define GPSB_SLOT_LEN          LC_SLOT_LEN
+#define GPSB_FREQ_POINTS_MAX   LC_FREQ_POINTS_MAX        /* FREQ_SEARCH_POINTS_MAX_CNT, acquisition.c:12 */
+#define GPSB_MAX_BINS          LC_MAX_BINS
 
-/* Cross-call scratch that the reference keeps in file-scope variables.  One shared instance backs
- * the reference-named API; the batched receiver owns one per channel. */
-typedef struct gpsb_aux {
-    uint32_t freq_hist[GPSB_MAX_BINS];          /* acq_freq_histogram, acquisition.c:28 (ACQ_COUNT used) */
-    uint16_t bin_phases[GPSB_FREQ_POINTS_MAX];  /* acq_single_freq_phases, acquisition.c:32 */
-    uint8_t  bin_count;                         /* acq_single_freq_count, acquisition.c:33 */
-    uint16_t pre_best_value;                    /* pre_track_best_corr_value, tracking.c:33 */
-    uint16_t pre_best_phase;                    /* pre_track_best_corr_phase, tracking.c:34 */
-    int16_t  slot_ip[GPSB_SLOT_LEN];            /* raw_ip_values, nav_data.c:48 */
-    uint8_t  slot_bits[GPSB_SLOT_LEN];          /* tmp_nav_data, nav_data.c:51 */
-    uint32_t slot_start_ticks;                  /* gps_channel_tmp_start_time_ticks, nav_data.c:29 */
-    int8_t   last_nav_bit;                      /* observer: bit handed to the word assembler this ms, or -1 */
-    /* private rand() stream of a batched channel: same generator and default seed as libc rand(), so the
-     * channel draws what it would draw as the only channel of a process (tracking.c:316) */
-    int      rnd_ready;
-    struct random_data rnd;
-    char     rnd_state[128];
-} gpsb_aux;
-
+/* gpsb_aux (the cross-call scratch the reference keeps in file-scope variables) is defined in the core. */
 extern gpsb_aux g_shared_aux;
 
 uint32_t hx_now_ms(void);

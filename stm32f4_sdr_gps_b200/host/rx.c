@@ -27,6 +27,9 @@ struct gpsb_rx {
     gpsb_search_res* s_res;
     uint32_t* s_owner;
     uint32_t threads;            /* 0 = automatic */
+    int loop_site;               /* GPSB_LOOP_AUTO / _HOST / _DEVICE */
+    gpsb_loop_result* loop_res;
+    uint64_t device_ms, host_ms; /* channel-milliseconds run by k_track_run / by the per-millisecond host path */
 };
 
 typedef struct track_job {
@@ -53,7 +56,8 @@ int gpsb_rx_create(gpsb_rx** out, gpsb_ctx* ctx, gps_ch_t* channels, uint32_t n_
     rx->s_rq = (gpsb_search_req*)calloc(n_ch, sizeof(gpsb_search_req));
     rx->s_res = (gpsb_search_res*)calloc(n_ch, sizeof(gpsb_search_res));
     rx->s_owner = (uint32_t*)calloc(n_ch, sizeof(uint32_t));
-    if (!rx->aux || !rx->plan || !rx->epl_rq || !rx->epl_out || !rx->epl_owner || !rx->s_rq || !rx->s_res ||
+    rx->loop_res = (gpsb_loop_result*)calloc(n_ch, sizeof(gpsb_loop_result));
+    if (!rx->loop_res || !rx->aux || !rx->plan || !rx->epl_rq || !rx->epl_out || !rx->epl_owner || !rx->s_rq || !rx->s_res ||
         !rx->s_owner) {
         gpsb_rx_destroy(rx);
         return GPSB_ERR_NOMEM;
@@ -84,6 +88,7 @@ void gpsb_rx_destroy(gpsb_rx* rx)
     free(rx->s_rq);
     free(rx->s_res);
     free(rx->s_owner);
+    free(rx->loop_res);
     free(rx);
 }
 
@@ -133,6 +138,7 @@ int gpsb_rx_track_ms(gpsb_rx* rx, uint32_t ms)
         if (k < n_s && rx->s_owner[k] == i) r = &rx->s_res[k++];
         hx_trk_finish_search(&rx->ch[i], &rx->aux[i], index, r);
     }
+    rx->host_ms += n_epl + n_s;
     return GPSB_OK;
 }
 
@@ -194,8 +200,151 @@ static uint32_t pick_workers(const gpsb_rx* rx)
     return n ? n : 1;
 }
 
+void gpsb_rx_set_loop_site(gpsb_rx* rx, int site) { if (rx) rx->loop_site = site; }
+
+void gpsb_rx_loop_stats(const gpsb_rx* rx, uint64_t* device_ms, uint64_t* host_ms)
+{
+    if (device_ms) *device_ms = rx ? rx->device_ms : 0;
+    if (host_ms) *host_ms = rx ? rx->host_ms : 0;
+}
+
+static int is_tracking(const gps_ch_t* ch)
+{
+    return ch->tracking_data.state == GPS_TRACKING_RUN || ch->tracking_data.state == GPS_PRE_TRACK_DONE;
+}
+
+/* One millisecond of ONE channel on the per-millisecond path (plan on the host, cell on the GPU, finish on the
+ * host): what the device-resident loop hands back, and channels that are still in pre-track. */
+static int host_step(gpsb_rx* rx, uint32_t i, uint32_t ms, int16_t* iq_row, int8_t* nav_row)
+{
+    const uint8_t index = (uint8_t)(ms % GPSB_SLOT_LEN);
+    gpsb_plan* p = &rx->plan[i];
+    int16_t iq[6] = {0, 0, 0, 0, 0, 0};
+    gpsb_host_set_packet_cnt(ms);
+    rx->aux[i].last_nav_bit = -1;
+    hx_trk_plan(&rx->ch[i], &rx->aux[i], ms, index, p);
+    if (p->want == GPSB_WANT_EPL) {
+        int rc = gpsb_track_epl(rx->ctx, 1, &p->epl, iq);
+        if (rc != GPSB_OK) return hx_note(rc);
+        hx_trk_finish_epl(&rx->ch[i], &rx->aux[i], index, iq);
+    } else if (p->want == GPSB_WANT_SEARCH) {
+        gpsb_search_res res = {0, 0, 0, 0};
+        if (p->search.start < p->search.stop) {
+            int rc = gpsb_search(rx->ctx, 1, &p->search, &res);
+            if (rc != GPSB_OK) return hx_note(rc);
+        }
+        hx_trk_finish_search(&rx->ch[i], &rx->aux[i], index, &res);
+    }
+    if (iq_row) memcpy(iq_row + 6u * i, iq, 12);
+    if (nav_row) nav_row[i] = p->want == GPSB_WANT_EPL ? rx->aux[i].last_nav_bit : -1;
+    rx->host_ms++;
+    return GPSB_OK;
+}
+
+/* Channel i over [ms, end): device-resident loop while the channel is in a tracking state, single host steps for
+ * what the loop hands back (a degenerate DLL millisecond) and for channels not tracking yet. */
+static int run_channel_span(gpsb_rx* rx, uint32_t i, uint32_t ms0, uint32_t ms, uint32_t end, int16_t* iq_log,
+                            int8_t* nav_log)
+{
+    const uint32_t n_ch = rx->n_ch;
+    while (ms < end) {
+        int16_t* iq_row = iq_log ? iq_log + (size_t)(ms - ms0) * n_ch * 6 : NULL;
+        int8_t* nav_row = nav_log ? nav_log + (size_t)(ms - ms0) * n_ch : NULL;
+        if (!is_tracking(&rx->ch[i])) {
+            int rc = host_step(rx, i, ms, iq_row, nav_row);
+            if (rc != GPSB_OK) return rc;
+            ms++;
+            continue;
+        }
+        const uint32_t n = end - ms;
+        int16_t* iq_tmp = iq_log ? (int16_t*)malloc((size_t)n * 12) : NULL;
+        int8_t* nav_tmp = nav_log ? (int8_t*)malloc(n) : NULL;
+        if ((iq_log && !iq_tmp) || (nav_log && !nav_tmp)) {
+            free(iq_tmp);
+            free(nav_tmp);
+            return hx_note(GPSB_ERR_NOMEM);
+        }
+        gpsb_loop_result r;
+        int rc = gpsb_track_loop(rx->ctx, 1, &rx->ch[i], (uint32_t)sizeof(gps_ch_t), &rx->aux[i], (uint32_t)sizeof(gpsb_aux),
+                                 ms, n, iq_tmp, nav_tmp, &r);
+        if (rc == GPSB_OK) {
+            const uint32_t rows = r.done_ms + (r.stop == LC_STOP_DLL_NAN ? 1u : 0u);
+            for (uint32_t k = 0; k < rows && k < n; k++) {
+                if (iq_log) memcpy(iq_log + ((size_t)(ms - ms0 + k) * n_ch + i) * 6, iq_tmp + 6u * k, 12);
+                if (nav_log) nav_log[(size_t)(ms - ms0 + k) * n_ch + i] = nav_tmp[k];
+            }
+        }
+        free(iq_tmp);
+        free(nav_tmp);
+        if (rc != GPSB_OK) return hx_note(rc);
+        lc_resolve_snr(&rx->ch[i], &rx->aux[i]);
+        rx->device_ms += r.done_ms;
+        ms += r.done_ms;
+        if (r.stop == LC_STOP_DLL_NAN && ms < end) {          /* sums delivered, filters not run: finish on the host */
+            gpsb_host_set_packet_cnt(ms);
+            rx->aux[i].last_nav_bit = -1;
+            hx_trk_finish_epl(&rx->ch[i], &rx->aux[i], (uint8_t)(ms % GPSB_SLOT_LEN), r.iq);
+            if (nav_log) nav_log[(size_t)(ms - ms0) * n_ch + i] = rx->aux[i].last_nav_bit;
+            rx->host_ms++;
+            ms++;
+        }
+    }
+    return GPSB_OK;
+}
+
+/* The whole run with the loops on the device: one k_track_run launch for every channel that is tracking, then
+ * whatever is left (channels handed back early, channels still in pre-track) channel by channel. */
+static int track_run_device(gpsb_rx* rx, uint32_t ms0, uint32_t n_ms, int16_t* iq_log, int8_t* nav_log)
+{
+    const uint32_t n_ch = rx->n_ch;
+    uint32_t n_trk = 0;
+    for (uint32_t i = 0; i < n_ch; i++) n_trk += is_tracking(&rx->ch[i]) ? 1u : 0u;
+    if (iq_log && n_trk != n_ch) memset(iq_log, 0, (size_t)n_ms * n_ch * 12);
+    if (nav_log && n_trk != n_ch) memset(nav_log, 0xFF, (size_t)n_ms * n_ch);
+    if (n_trk == n_ch) {
+        int rc = gpsb_track_loop(rx->ctx, n_ch, rx->ch, (uint32_t)sizeof(gps_ch_t), rx->aux, (uint32_t)sizeof(gpsb_aux), ms0,
+                                 n_ms, iq_log, nav_log, rx->loop_res);
+        if (rc != GPSB_OK) return hx_note(rc);
+        for (uint32_t i = 0; i < n_ch; i++) {
+            const gpsb_loop_result* r = &rx->loop_res[i];
+            lc_resolve_snr(&rx->ch[i], &rx->aux[i]);
+            rx->device_ms += r->done_ms;
+            uint32_t ms = ms0 + r->done_ms;
+            if (r->stop == LC_STOP_DLL_NAN && r->done_ms < n_ms) {
+                gpsb_host_set_packet_cnt(ms);
+                rx->aux[i].last_nav_bit = -1;
+                hx_trk_finish_epl(&rx->ch[i], &rx->aux[i], (uint8_t)(ms % GPSB_SLOT_LEN), r->iq);
+                if (nav_log) nav_log[(size_t)(ms - ms0) * n_ch + i] = rx->aux[i].last_nav_bit;
+                rx->host_ms++;
+                ms++;
+            }
+            if (ms < ms0 + n_ms) {
+                if (iq_log)
+                    for (uint32_t k = ms - ms0; k < n_ms; k++) memset(iq_log + ((size_t)k * n_ch + i) * 6, 0, 12);
+                if (nav_log)
+                    for (uint32_t k = ms - ms0; k < n_ms; k++) nav_log[(size_t)k * n_ch + i] = -1;
+                rc = run_channel_span(rx, i, ms0, ms, ms0 + n_ms, iq_log, nav_log);
+                if (rc != GPSB_OK) return rc;
+            }
+        }
+    } else {
+        for (uint32_t i = 0; i < n_ch; i++) {
+            int rc = run_channel_span(rx, i, ms0, ms0, ms0 + n_ms, iq_log, nav_log);
+            if (rc != GPSB_OK) return rc;
+        }
+    }
+    gpsb_host_set_packet_cnt(ms0 + n_ms - 1);
+    return GPSB_OK;
+}
+
 int gpsb_rx_track_run(gpsb_rx* rx, uint32_t ms0, uint32_t n_ms, int16_t* iq_log, int8_t* nav_log)
 {
+    if (!rx) return GPSB_ERR_ARG;
+    if (n_ms == 0) return GPSB_OK;
+    /* loops on the device: one launch for the whole run, no per-millisecond round trip */
+    if (rx->loop_site != GPSB_LOOP_HOST && (rx->loop_site == GPSB_LOOP_DEVICE || n_ms > 1) &&
+        gpsb_session_slots(rx->ctx) == 0)
+        return track_run_device(rx, ms0, n_ms, iq_log, nav_log);
     if (!rx) return GPSB_ERR_ARG;
     /* a run of many milliseconds is served by resident CTAs (one per channel): no launch per ms */
     const int own_session = n_ms > 8 && rx->n_ch <= 128 && gpsb_session_slots(rx->ctx) == 0 &&

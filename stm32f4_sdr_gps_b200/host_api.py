@@ -115,6 +115,9 @@ def load_host_library(path: Path | None = None) -> C.CDLL:
         "gpsb_rx_track_ms": (i32, [vp, u32]), "gpsb_rx_track_run": (i32, [vp, u32, u32, vp, vp]),
         "gpsb_rx_acquire_ms": (i32, [vp, u32]),
         "gpsb_rx_set_threads": (None, [vp, u32]),
+        "gpsb_rx_set_loop_site": (None, [vp, i32]),
+        "gpsb_rx_loop_stats": (None, [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+        "gpsb_host_certify_loop_math": (C.c_int64, [vp, u32]),
         "gpsb_rx_cold_sweep": (i32, [vp, C.c_int32, C.c_int32, u32, u32, u32, vp, vp]),
         "gpsb_host_plan_acq": (i32, [vp, u32, C.POINTER(Plan)]),
         "gpsb_host_finish_acq": (i32, [vp, C.POINTER(Plan), C.POINTER(SearchRes)]),
@@ -195,6 +198,16 @@ class Receiver:
 
     def set_threads(self, n: int) -> None:
         self.lib.gpsb_rx_set_threads(self._rx, n)
+
+    def set_loop_site(self, site: int) -> None:
+        """0 automatic (device-resident loop for runs), 1 host loop filters, 2 device."""
+        self.lib.gpsb_rx_set_loop_site(self._rx, site)
+
+    def loop_stats(self):
+        """(channel-milliseconds run by k_track_run, channel-milliseconds run on the per-ms host path)"""
+        a, b = C.c_uint64(), C.c_uint64()
+        self.lib.gpsb_rx_loop_stats(self._rx, C.byref(a), C.byref(b))
+        return a.value, b.value
 
     def acquire_ms(self, ms: int) -> None:
         self._check(self.lib.gpsb_rx_acquire_ms(self._rx, ms))

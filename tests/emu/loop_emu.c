@@ -1,0 +1,157 @@
+/*
+ * loop_emu.c - TEST INFRASTRUCTURE: a CPU emulation of the device-resident tracking loop k_track_run
+ * (stm32f4_sdr_gps_b200/csrc/gpsb_track_loop.cuh).  It compiles the SAME sources the kernel is made of
+ * (core/gpsb_loop_core.h with the device math selected, core/gpsb_epl_core.h) with gcc and runs the kernel's
+ * control flow thread by thread, so that the tests can check them against the compiled reference without a
+ * GPU.  What it cannot cover - CUDA's double atan2 and nvcc's code generation - is covered by the GPU tests.
+ * Never linked into the product libraries.
+ */
+#define LC_EMULATE_DEVICE 1
+#include "../../stm32f4_sdr_gps_b200/core/gpsb_loop_core.h"
+#include "../../stm32f4_sdr_gps_b200/core/gpsb_epl_core.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+uint32_t emu_sizeof_aux(void) { return (uint32_t)sizeof(gpsb_aux); }
+uint32_t emu_sizeof_channel(void) { return (uint32_t)sizeof(gps_ch_t); }
+
+static void expand_code(const uint8_t* chips, uint32_t* E)
+{
+    for (int w = 0; w < EC_WORDS; w++) {
+        uint32_t lo = chips[2 * w] ? 0x0000FFFFu : 0u;
+        uint32_t hi = (2 * w + 1 < PRN_LENGTH && chips[2 * w + 1]) ? 0xFFFF0000u : 0u;
+        E[w] = lo | hi;
+    }
+}
+
+/* One E/P/L cell with the kernel's work split: n_workers threads own nw consecutive words each. */
+void emu_epl_cell(const uint8_t* chips, const uint8_t* frame2046, uint32_t acc0, uint32_t step32, uint32_t off_e,
+                  uint32_t off_p, uint32_t off_l, uint32_t bits, uint32_t nw, int16_t iq[6])
+{
+    uint32_t E[EC_WORDS], S[EC_WORDS];
+    expand_code(chips, E);
+    memset(S, 0, sizeof S);
+    memcpy(S, frame2046, 2046);
+    const uint32_t off[3] = {off_e, off_p, off_l};
+    uint32_t total[3] = {0, 0, 0};
+    for (int W0 = 0; W0 < EC_WORDS; W0 += (int)nw) {
+        uint32_t acc[3] = {0, 0, 0};
+        ec_epl_partial(S, E, acc0, step32, off, bits, W0, (int)nw, acc);
+        for (int a = 0; a < 3; a++) total[a] += acc[a];
+    }
+    ec_unpack_sums(total, iq);
+}
+
+/* The kernel's loop for one channel.  Returns the stop reason; *done_ms = milliseconds completed. */
+int emu_track_run(gps_ch_t* ch, gpsb_aux* aux, const uint8_t* signal, uint32_t ms0, uint32_t n_ms, uint32_t nw,
+                  int16_t* iq_log, int8_t* nav_log, uint32_t* done_ms, int16_t stop_iq[6])
+{
+    uint32_t E[EC_WORDS], S[EC_WORDS];
+    expand_code(ch->prn_code, E);
+    gpsb_epl_req rq;
+    int stop = LC_STOP_NONE;
+    uint32_t m = 0;
+    if (ch->tracking_data.state == GPS_PRE_TRACK_DONE) ch->tracking_data.state = GPS_TRACKING_RUN;
+    if (ch->tracking_data.state != GPS_TRACKING_RUN) stop = LC_STOP_STATE;
+    else if (n_ms) lc_trk_plan_run(ch, ms0, ms0, &rq);
+    for (; m < n_ms && stop == LC_STOP_NONE; m++) {
+        const uint32_t ms = ms0 + m;
+        const uint8_t index = (uint8_t)(ms % LC_SLOT_LEN);
+        memset(S, 0, sizeof S);
+        memcpy(S, signal + (size_t)m * 2046, 2046);
+        const uint32_t off[3] = {rq.off_e, rq.off_p, rq.off_l};
+        uint32_t total[3] = {0, 0, 0};
+        for (int W0 = 0; W0 < EC_WORDS; W0 += (int)nw) {
+            uint32_t acc[3] = {0, 0, 0};
+            ec_epl_partial(S, E, rq.acc0, rq.step32, off, rq.off_bits, W0, (int)nw, acc);
+            for (int a = 0; a < 3; a++) total[a] += acc[a];
+        }
+        int16_t iq[6];
+        ec_unpack_sums(total, iq);
+        if (iq_log) memcpy(iq_log + 6 * (size_t)m, iq, 12);
+        if (nav_log) nav_log[m] = -1;
+        if (lc_dll_is_degenerate(iq)) {
+            stop = LC_STOP_DLL_NAN;
+            if (stop_iq) memcpy(stop_iq, iq, 12);
+            break;
+        }
+        lc_finish_loops(ch, aux, index, iq);
+        if (m + 1 < n_ms) lc_trk_plan_run(ch, ms + 1, ms + 1, &rq);   /* barrier B: next request published */
+        lc_finish_tail(ch, aux, index, iq[2], iq[3], ms);             /* overlaps the next correlation on the GPU */
+        if (nav_log) nav_log[m] = aux->last_nav_bit;
+    }
+    *done_ms = m;
+    return stop;
+}
+
+void emu_resolve_snr(gps_ch_t* ch, gpsb_aux* aux) { lc_resolve_snr(ch, aux); }
+
+/* --------------------------------------------------------------- device math against the host libm */
+static uint32_t fbits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+
+/* Compare the float-path functions the device uses with the host libm over ip in [ip_lo, ip_hi), every
+ * qp in [-8184, 8184].  kind 0: atan2f branch of the Costas discriminator (ip > 0); kind 1: FLL angle.
+ * Returns the number of mismatching bit patterns; first_bad[2] receives the first offending (ip, qp). */
+uint64_t emu_compare_float_math(int kind, int ip_lo, int ip_hi, int32_t first_bad[2])
+{
+    uint64_t bad = 0;
+    for (int ip = ip_lo; ip < ip_hi; ip++) {
+        for (int qp = -8184; qp <= 8184; qp++) {
+            float dev, host;
+            if (kind == 0) {
+                if (ip <= 0) continue;
+                dev = (float)(lc_atan2f((float)qp, (float)ip) / LC_PI);
+                host = (float)(atan2f((float)qp, (float)ip) / LC_PI);
+            } else {
+                if (ip == 0) continue;
+                dev = lc_atanf((float)qp / (float)ip);
+                host = atanf((float)qp / (float)ip);
+            }
+            if (fbits(dev) != fbits(host)) {
+                if (!bad && first_bad) { first_bad[0] = ip; first_bad[1] = qp; }
+                bad++;
+            }
+        }
+    }
+    return bad;
+}
+
+/* Host libm values of both discriminators for a block of the domain: what the GPU self-test is compared
+ * with.  out[(ip - ip_lo) * 16369 + (qp + 8184)] */
+void emu_host_costas(int ip_lo, int ip_hi, float* out)
+{
+    for (int ip = ip_lo; ip < ip_hi; ip++)
+        for (int qp = -8184; qp <= 8184; qp++) {
+            float v;
+            if (ip > 0) v = (float)(atan2f((float)qp, (float)ip) / LC_PI);
+            else v = (float)(atan2((float)-qp, (float)-ip) / LC_PI);
+            out[(size_t)(ip - ip_lo) * 16369 + (size_t)(qp + 8184)] = v;
+        }
+}
+void emu_host_fll_angle(int ip_lo, int ip_hi, float* out)
+{
+    for (int ip = ip_lo; ip < ip_hi; ip++)
+        for (int qp = -8184; qp <= 8184; qp++)
+            out[(size_t)(ip - ip_lo) * 16369 + (size_t)(qp + 8184)] =
+                (ip == 0) ? (float)(LC_PI / 2) : atanf((float)qp / (float)ip);
+}
+
+/* the private generator against libc's: n draws after the default seed */
+uint32_t emu_rand31_mismatches(uint32_t n)
+{
+    gpsb_rand31 g;
+    memset(&g, 0, sizeof g);
+    struct random_data rd;
+    char state[128];
+    memset(&rd, 0, sizeof rd);
+    initstate_r(1u, state, sizeof state, &rd);
+    uint32_t bad = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        int32_t want = 0;
+        random_r(&rd, &want);
+        if (lc_rand31_next(&g) != want) bad++;
+    }
+    return bad;
+}

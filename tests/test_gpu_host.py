@@ -22,19 +22,28 @@ def _armed_channels(golden, prns=(5, 14)):
     return ch
 
 
-@pytest.mark.parametrize("threads", [0, 1])
-def test_batched_receiver_closed_loop_equals_reference(host_engine, golden, threads):
-    """threads=0: one host worker per channel, each driving its own resident-kernel slot at its own pace;
-    threads=1: single thread, all channels in lockstep.  600 ms closed loop (pre-track, E/P/L loops, nav-bit sync) for two satellites in one receiver:
-    I/Q sums, nav bits and the final channel records equal the reference run per satellite."""
+@pytest.mark.parametrize("mode", ["device", "host-threads", "host-lockstep"])
+def test_batched_receiver_closed_loop_equals_reference(host_engine, golden, mode):
+    """600 ms closed loop (pre-track, E/P/L loops, nav-bit sync) for two satellites in one receiver: I/Q sums,
+    nav bits and the final channel records equal the reference run per satellite, whichever way the loop is
+    closed.  device: pre-track on the per-millisecond path, then ONE k_track_run launch per channel for the
+    rest (loop filters on the GPU).  host-threads: filters on the host, one worker per channel driving its own
+    resident-kernel slot.  host-lockstep: filters on the host, single thread, all channels per millisecond."""
     sig = golden["scene_signal"]
     host_engine.upload_signal(0, sig)
     ch = _armed_channels(golden)
     rx = Receiver(host_engine, ch)
-    rx.set_threads(threads)
+    rx.set_loop_site(2 if mode == "device" else 1)
+    rx.set_threads(1 if mode == "host-lockstep" else 0)
     launches0 = host_engine.launch_count
     iq, nav = rx.track_run(0, 600)
-    assert host_engine.launch_count - launches0 <= 600 * 2          # one launch per kind per ms, not per channel
+    assert host_engine.launch_count - launches0 <= 600 * 2          # never more than one launch per kind per ms
+    on_device, on_host = rx.loop_stats()
+    if mode == "device":
+        assert on_device > 2 * 400 and on_host < 2 * 200            # everything after pre-track ran inside k_track_run
+        assert host_engine.launch_count - launches0 <= on_host + 4
+    else:
+        assert on_device == 0
     for s in range(2):
         assert np.array_equal(iq[:, s, :], golden["track_iq"][s]), s
         assert np.array_equal(nav[:, s], golden["track_nav"][s]), s

@@ -1,0 +1,145 @@
+"""The device-resident tracking loop (k_track_run) on a real B200, through the C ABI, against the unmodified
+reference closed loop and against the host-resident loop of the same library - bit-exact."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from emu_lib import load_emulator
+from stm32f4_sdr_gps_b200 import Channels, FlatState, Receiver, load_host_library
+
+pytestmark = pytest.mark.gpu
+
+
+def test_loop_math_certificate_whole_domain(host_engine):
+    """Every (IP, QP) in [-8184, 8184]^2: the device's Costas error (fdlibm atan2f on one branch, CUDA double
+    atan2 on the other, then / pi in double, rounded to float) and FLL angle (fdlibm atanf) carry the host
+    libm's bit pattern.  2 x 268 M values, compared inside libgpsb_host.so on all host cores."""
+    lib = load_host_library()
+    assert lib.gpsb_host_certify_loop_math(host_engine.handle, 0) == 0
+
+
+def test_loop_math_rows_against_emulator_tables(host_engine):
+    """Independent path to the same statement for a few rows: device values vs libm values computed by the
+    test-side emulator library (tests/emu/loop_emu.c)."""
+    emu = load_emulator()
+    for ip_lo in (-8184, -4097, -3, 0, 1, 2, 777, 8180):
+        n = min(5, 8185 - ip_lo)
+        want = np.empty((n, 16369), np.float32)
+        for kind, fn in ((0, emu.emu_host_costas), (1, emu.emu_host_fll_angle)):
+            fn(ip_lo, ip_lo + n, want.ctypes.data)
+            got = host_engine.l0_loop_math(kind, ip_lo, n)
+            assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (kind, ip_lo)
+
+
+def _locked(ch, i, found_freq, freq_hz, fine, master=0, bad=0):
+    st = ch.snapshot(i)
+    st.acq_state, st.trk_state, st.found_freq_offset_hz = 9, 4, found_freq
+    st.if_freq_offset_hz_bits = int(np.float32(freq_hz).view(np.uint32))
+    st.code_phase_fine_bits = int(np.float32(fine).view(np.uint32))
+    st.pll_bad_state_cnt, st.pll_bad_state_master_cnt = bad, master
+    ch.restore(i, st)
+    return st
+
+
+def test_device_loop_many_channels_ring_wrap_equals_reference(host_engine, golden, reference):
+    """Six channels (two satellites present, each tracked by three channels from different starting points) in
+    ONE k_track_run launch, over a span of the signal ring that wraps around its end: per-millisecond sums, nav
+    bits and the final records equal the reference run of each channel."""
+    sig = golden["scene_signal"]
+    n_ms = 560
+    ms0 = host_engine.ring_ms * 5 - 200                 # frames ring-200 .. ring-1, 0 .. 359
+    host_engine.upload_signal(ms0, sig[:n_ms])
+    prns = [5, 14, 5, 14, 5, 14]
+    ch = Channels(prns)
+    rchans = reference.channels(len(prns))
+    for i, prn in enumerate(prns):
+        s = i % 2
+        fine = float(golden["track_found_phase"][s]) * 8.0 + (i // 2) * 3.0
+        freq = float(golden["track_found_freq"][s]) + (i // 2) * 40.0
+        st = _locked(ch, i, int(golden["track_found_freq"][s]), freq, fine)
+        rch = reference.channel_at(rchans, i)
+        reference.channel_init(rch, prn, 0)
+        reference.restore(rch, type(reference.snapshot(rch)).from_buffer_copy(bytes(st)))
+    rx = Receiver(host_engine, ch)
+    launches0 = host_engine.launch_count
+    iq, nav = rx.track_run(ms0, n_ms)
+    assert host_engine.launch_count - launches0 == 1                  # the whole run is one launch
+    assert rx.loop_stats() == (len(prns) * n_ms, 0)
+    for i in range(len(prns)):
+        rch = reference.channel_at(rchans, i)
+        want_iq, want_nav, _ = reference.track_run(rch, sig[:n_ms], ms0, n_ms)
+        assert np.array_equal(iq[:, i, :], want_iq), i
+        assert np.array_equal(nav[:, i], want_nav), i
+        assert bytes(ch.snapshot(i)) == bytes(reference.snapshot(rch)), i
+    rx.close()
+    ch.free()
+
+
+def test_device_loop_false_lock_reseed_equals_reference(host_engine, reference):
+    """Noise-only input: the false-lock kicker fires inside the kernel and draws from the channel's private
+    generator exactly what the reference draws from a freshly seeded libc rand() (tracking.c:300-326)."""
+    rng = np.random.default_rng(77)
+    n_ms = 1000
+    sig = rng.integers(0, 256, (n_ms, 2046), dtype=np.uint8)
+    host_engine.upload_signal(0, sig)
+    ch = Channels([9])
+    st = _locked(ch, 0, 1500, 1500.0, 4000.0, master=80, bad=10)
+    C.CDLL(None).srand(1)
+    rchans = reference.channels(1)
+    rch = reference.channel_at(rchans, 0)
+    reference.channel_init(rch, 9, 0)
+    reference.restore(rch, type(reference.snapshot(rch)).from_buffer_copy(bytes(st)))
+    want_iq, want_nav, _ = reference.track_run(rch, sig, 0, n_ms)
+    rx = Receiver(host_engine, ch)
+    iq, nav = rx.track_run(0, n_ms)
+    assert rx.loop_stats()[0] == n_ms
+    assert np.array_equal(iq[:, 0, :], want_iq)
+    assert np.array_equal(nav[:, 0], want_nav)
+    got, want = ch.snapshot(0), reference.snapshot(rch)
+    assert bytes(got) == bytes(want)
+    assert got.if_freq_offset_hz_bits != st.if_freq_offset_hz_bits
+    rx.close()
+    ch.free()
+
+
+def test_device_loop_split_runs_equal_one_run(host_engine, golden):
+    """State (NCO phase, filters, nav-bit buffers, rand stream, deferred SNR) survives the trip through host
+    memory: 600 ms as 1 + 3 + 96 + 500 ms in four calls equals one call."""
+    sig = golden["scene_signal"]
+    host_engine.upload_signal(0, sig)
+    runs = []
+    for parts in ((600,), (1, 3, 96, 500)):
+        ch = Channels([5, 14])
+        for i in range(2):
+            _locked(ch, i, int(golden["track_found_freq"][i]), float(golden["track_found_freq"][i]),
+                    float(golden["track_found_phase"][i]) * 8.0)
+        rx = Receiver(host_engine, ch)
+        rx.set_loop_site(2)
+        ms, iqs = 0, []
+        for n in parts:
+            iq, _ = rx.track_run(ms, n)
+            iqs.append(iq)
+            ms += n
+        runs.append((np.concatenate(iqs), [bytes(ch.snapshot(i)) for i in range(2)]))
+        rx.close()
+        ch.free()
+    assert np.array_equal(runs[0][0], runs[1][0])
+    assert runs[0][1] == runs[1][1]
+
+
+def test_device_loop_refuses_what_it_cannot_do(host_engine, golden):
+    """Through the raw C ABI: wrong record sizes and a satellite slot without a code are argument / state
+    errors; a channel that is not tracking comes back untouched with stop == 1."""
+    lib = host_engine.lib
+    host_engine.set_code_prn(5, 5)
+    ch = Channels([5])
+    ch_b, aux_b = host_engine.record_bytes()
+    aux = C.create_string_buffer(aux_b)
+    res = (C.c_uint8 * 24)()
+    assert lib.gpsb_track_loop(host_engine.handle, 1, ch.at(0), ch_b - 8, aux, aux_b, 0, 4, None, None, res) == -1
+    before = bytes(ch.snapshot(0))
+    assert lib.gpsb_track_loop(host_engine.handle, 1, ch.at(0), ch_b, aux, aux_b, 0, 4, None, None, res) == 0
+    done, stop = np.frombuffer(bytes(res), np.uint32, 2)
+    assert (int(done), int(stop)) == (0, 1) and bytes(ch.snapshot(0)) == before
+    ch.free()

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""Closed-loop timing probe: ms of wall time per 1000 ms of signal for several channel counts and host
-thread counts (gpsb_rx_track_run).  Diagnostic only - bench.py is what reports numbers."""
+"""Closed-loop timing probe: wall time per millisecond of signal for several channel counts, with the loop
+filters on the device (k_track_run) and on the host (resident session kernel / per-ms launches).
+Diagnostic only - bench.py is what reports numbers."""
 import sys
 import time
 from pathlib import Path
@@ -14,7 +15,7 @@ from stm32f4_sdr_gps_b200.signal_synth import Satellite, Scene, synthesize  # no
 
 
 def main():
-    n_ms = 500
+    n_ms = 1000
     rng = np.random.default_rng(5)
     for n_ch in (4, 32):
         sats = [Satellite(prn=p, doppler_hz=float(rng.uniform(-4000, 4000)), code_phase_samples=float(rng.uniform(0, 16368)),
@@ -27,7 +28,9 @@ def main():
         eng.upload_signal(0, sig)
         ch = Channels([s.prn for s in sats])
         rx = Receiver(eng, ch)
-        for threads in (1, 2, 4, 8, 0):
+        finals = {}
+        for site, threads, name in ((2, 1, "device loop"), (1, 1, "host loop, 1 thread"), (1, 0, "host loop, threads")):
+            rx.set_loop_site(site)
             rx.set_threads(threads)
             best = 1e9
             for rep in range(4):
@@ -35,8 +38,11 @@ def main():
                 t0 = time.perf_counter()
                 rx.track_run(0, n_ms, log=False)
                 best = min(best, time.perf_counter() - t0)
-            print("  n_ch %3d threads %2d: %.2f us per ms  (%.1fx real time)" % (n_ch, threads, best / n_ms * 1e6,
-                                                                              n_ms * 1e-3 / best), flush=True)
+            finals[name] = [bytes(ch.snapshot(i)) for i in range(n_ch)]
+            print("  n_ch %3d %-22s %8.3f us per ms  (%.1fx real time)  stats %s" % (
+                n_ch, name, best / n_ms * 1e6, n_ms * 1e-3 / best, rx.loop_stats()), flush=True)
+        names = list(finals)
+        print("  final channel records identical across paths:", all(finals[n] == finals[names[0]] for n in names), flush=True)
         rx.close()
         eng.close()
 
