@@ -308,20 +308,28 @@ LC_FN void lc_arm_offsets(float code_phase_fine, gpsb_epl_req* rq)
     rq->off_l = late;
 }
 
-/* tracking.c:92-123 for a channel in GPS_TRACKING_RUN: what to correlate this millisecond. */
-LC_FN void lc_trk_plan_run(gps_ch_t* ch, uint32_t now, uint32_t frame_ms, gpsb_epl_req* rq)
+/* tracking.c:92-123 for a channel in GPS_TRACKING_RUN: what to correlate this millisecond.  Two independent
+ * halves - the carrier NCO words depend on the PLL/FLL state only, the code offsets on the DLL state only - so
+ * the device-resident loop can run them on different threads. */
+LC_FN void lc_plan_carrier(gps_tracking_t* t, uint8_t prn, uint32_t now, uint32_t frame_ms, gpsb_epl_req* rq)
 {
-    gps_tracking_t* t = &ch->tracking_data;
+    /* the NCO word first: its divide is the long dependent chain of this function, and nothing below changes
+     * if_freq_offset_hz */
+    rq->step32 = lc_nco_step32((float)IF_FREQ_HZ + t->if_freq_offset_hz);
     uint32_t gap = now - t->prev_track_timestamp;
     t->prev_track_timestamp = now;
     if (gap > 50) gap = 1;                                         /* first step after start-up */
     if (gap != 1) lc_rewind_if_phase(t, (uint8_t)(gap - 1));       /* ms this channel did not see */
-    rq->sv_slot = ch->prn;
+    rq->sv_slot = prn;
     rq->ms_index = frame_ms;
-    lc_arm_offsets(t->code_phase_fine, rq);
     rq->acc0 = t->if_freq_accum;
-    rq->step32 = lc_nco_step32((float)IF_FREQ_HZ + t->if_freq_offset_hz);
     t->if_freq_accum += 511u * rq->step32;                         /* what the mixer leaves behind, gps_misc.c:261-273 */
+}
+LC_FN void lc_plan_code(const gps_tracking_t* t, gpsb_epl_req* rq) { lc_arm_offsets(t->code_phase_fine, rq); }
+LC_FN void lc_trk_plan_run(gps_ch_t* ch, uint32_t now, uint32_t frame_ms, gpsb_epl_req* rq)
+{
+    lc_plan_carrier(&ch->tracking_data, ch->prn, now, frame_ms, rq);
+    lc_plan_code(&ch->tracking_data, rq);
 }
 
 /* ------------------------------------------------------------------------------------------ loop filters */
@@ -361,23 +369,27 @@ LC_FN void lc_dll_update(gps_tracking_t* t, int16_t ie, int16_t qe, int16_t il, 
     t->dll_code_err = err;
 }
 
-/* Fold an angle difference back into [-pi/2, pi/2] the way the reference does (reflection, in double). */
+/* Fold an angle difference back into [-pi/2, pi/2] the way the reference does: `if (x > M_PI / 2) x = M_PI - x;
+ * if (x < -M_PI / 2) x = -M_PI - x;` with the DOUBLE M_PI (tracking.c:189-192, 238-247).  The comparisons promote
+ * the float to double; since (float)(pi/2) = 0x3FC90FDB is the smallest float above the double pi/2, "x > pi/2 in
+ * double" is exactly "x >= 0x3FC90FDB in float" - same truth value for every float, one compare instead of a
+ * conversion and a double compare.  The reflections themselves stay in double. */
 LC_FN float lc_fold_half_pi(float x)
 {
-    if (x > LC_PI / 2) x = (float)(LC_PI - x);
-    if (x < -LC_PI / 2) x = (float)(-LC_PI - x);
+    const float above_half_pi = lc_bits_float(0x3fc90fdb);
+    if (x >= above_half_pi) x = (float)(LC_PI - x);
+    if (x <= -above_half_pi) x = (float)(-LC_PI - x);
     return x;
 }
 
 /* tracking.c:175-209.  The reference evaluates the discriminator on every millisecond and uses it on slot
  * index 0 only; it is a pure function of (ip, qp), so it is evaluated only where it is used. */
-LC_FN void lc_pll_update(gps_ch_t* ch, uint8_t index, int16_t ip, int16_t qp)
+LC_FN void lc_pll_update(gps_tracking_t* t, int period_sync_ok, uint8_t index, int16_t ip, int16_t qp)
 {
-    gps_tracking_t* t = &ch->tracking_data;
     if (index != 0) return;
     float err = lc_costas_err(ip, qp);
     float delta = lc_fold_half_pi(err - t->pll_code_err);
-    if (ch->nav_data.period_sync_ok_flag)
+    if (period_sync_ok)
         t->if_freq_offset_hz -= TRACKING_PLL2_C1 * delta + (TRACKING_PLL2_C2 * LC_LOOP_DT_S * err);
     else
         t->if_freq_offset_hz -= TRACKING_PLL1_C1 * delta + (TRACKING_PLL1_C2 * LC_LOOP_DT_S * err);
@@ -393,11 +405,11 @@ LC_FN int lc_rand(gpsb_aux* aux) { return hx_rand(aux); }
 
 /* tracking.c:261-327: two or more sign flips of IP inside one 4-ms slot cannot be data; count them and,
  * after a long bad streak, jump the carrier to a random frequency at least 200 Hz away. */
-LC_FN void lc_lock_check(gps_ch_t* ch, gpsb_aux* aux, uint8_t index, int16_t ip)
+LC_FN void lc_lock_check(gps_tracking_t* t, gpsb_aux* aux, int16_t found_freq_offset_hz, uint8_t index, int16_t ip)
 {
-    gps_tracking_t* t = &ch->tracking_data;
     if (index >= LC_SLOT_LEN) return;
-    t->pll_check_buf[index] = ip;
+    for (uint8_t i = 0; i < LC_SLOT_LEN; i++)             /* pll_check_buf[index] = ip, with constant subscripts so that */
+        if (i == index) t->pll_check_buf[i] = ip;         /* a private copy of the record can live in registers */
     if (index < LC_SLOT_LEN - 1) return;
 
     uint8_t flips = 0;
@@ -421,25 +433,41 @@ LC_FN void lc_lock_check(gps_ch_t* ch, gpsb_aux* aux, uint8_t index, int16_t ip)
         int16_t candidate, away;
         do {
             uint16_t r = (uint16_t)(lc_rand(aux) % ACQ_SEARCH_STEP_HZ);
-            candidate = (int16_t)(ch->acq_data.found_freq_offset_hz - r + (ACQ_SEARCH_STEP_HZ / 2));
+            candidate = (int16_t)(found_freq_offset_hz - r + (ACQ_SEARCH_STEP_HZ / 2));
             away = (int16_t)((int16_t)t->if_freq_offset_hz - candidate);
         } while ((away < 0 ? -away : away) < 200);
         t->if_freq_offset_hz = (float)candidate;
     }
 }
 
+/* The angle of the PREVIOUS prompt sample is, from slot index 2 on, the angle computed one millisecond
+ * earlier from the same two integers; a caller may hand it back to save one divide + arctangent. */
+typedef struct lc_angle_cache {
+    int16_t i, q;
+    uint8_t valid;
+    float angle;
+} lc_angle_cache;
+
 /* tracking.c:214-256 */
-LC_FN void lc_fll_update(gps_ch_t* ch, gpsb_aux* aux, uint8_t index, int16_t ip, int16_t qp)
+LC_FN void lc_fll_update(gps_tracking_t* t, gpsb_aux* aux, int16_t found_freq_offset_hz, uint8_t index, int16_t ip,
+                         int16_t qp, lc_angle_cache* cache)
 {
-    gps_tracking_t* t = &ch->tracking_data;
-    lc_lock_check(ch, aux, index, ip);
+    lc_lock_check(t, aux, found_freq_offset_hz, index, ip);
     if (index == 0) {                                 /* first ms of a slot: previous sample is from another time */
         t->fll_old_i = ip;
         t->fll_old_q = qp;
         return;
     }
     float now = lc_fll_angle(ip, qp);
-    float before = lc_fll_angle(t->fll_old_i, t->fll_old_q);
+    float before;
+    if (cache && cache->valid && cache->i == t->fll_old_i && cache->q == t->fll_old_q) before = cache->angle;
+    else before = lc_fll_angle(t->fll_old_i, t->fll_old_q);
+    if (cache) {
+        cache->i = ip;
+        cache->q = qp;
+        cache->angle = now;
+        cache->valid = 1;
+    }
     float rot = lc_fold_half_pi(now - before);
     float rot_change = lc_fold_half_pi(rot - t->fll_err);
     float step_hz = TRACKING_FLL1_C1 * LC_LOOP_DT_S * rot_change + (TRACKING_FLL1_C2 * LC_LOOP_DT_S * rot);
@@ -452,9 +480,10 @@ LC_FN void lc_fll_update(gps_ch_t* ch, gpsb_aux* aux, uint8_t index, int16_t ip,
 /* First half of tracking.c:140-169: everything the NEXT millisecond's correlation depends on. */
 LC_FN void lc_finish_loops(gps_ch_t* ch, gpsb_aux* aux, uint8_t index, const int16_t iq[6])
 {
-    lc_dll_update(&ch->tracking_data, iq[0], iq[1], iq[4], iq[5]);
-    lc_pll_update(ch, index, iq[2], iq[3]);
-    lc_fll_update(ch, aux, index, iq[2], iq[3]);
+    gps_tracking_t* t = &ch->tracking_data;
+    lc_dll_update(t, iq[0], iq[1], iq[4], iq[5]);
+    lc_pll_update(t, ch->nav_data.period_sync_ok_flag, index, iq[2], iq[3]);
+    lc_fll_update(t, aux, ch->acq_data.found_freq_offset_hz, index, iq[2], iq[3], (lc_angle_cache*)0);
 }
 
 /* ------------------------------------------------------------------------------------------ nav bits */
@@ -631,24 +660,25 @@ LC_FN void lc_refine_edge(gps_ch_t* ch, const gpsb_aux* aux)
     n->accurate_swap_ok = 1;
 }
 
-/* nav_data.c:46-138 */
-LC_FN void lc_nav_new_code(gps_ch_t* ch, gpsb_aux* aux, uint8_t index, int16_t new_i, uint32_t now)
+/* nav_data.c:46-138 without its last step: returns 1 when the bit edge found at the end of this slot still has
+ * to be refined by lc_refine_edge (the only part that reads the code phase the DLL produced this millisecond). */
+LC_FN int lc_nav_new_code(gps_ch_t* ch, gpsb_aux* aux, uint8_t index, int16_t new_i, uint32_t now)
 {
     gps_nav_data_t* n = &ch->nav_data;
     aux->last_nav_bit = -1;
-    if (index >= LC_SLOT_LEN) return;
+    if (index >= LC_SLOT_LEN) return 0;
     uint8_t ms_bit = (uint8_t)((new_i > 0) ^ (n->inv_polarity_flag != 0));
     aux->slot_bits[index] = ms_bit;
     aux->slot_ip[index] = new_i;
     if (index == 0) aux->slot_start_ticks = now;
     if (n->period_sync_ok_flag == 1) lc_count_ms_into_bit(ch, aux, ms_bit, now);
-    if (index < LC_SLOT_LEN - 1) return;
+    if (index < LC_SLOT_LEN - 1) return 0;
 
     /* end of the 4-ms slot: exactly one sign flip is a candidate bit edge */
     uint8_t flips = 0, flip_pos = 0;
     for (uint8_t i = 1; i < LC_SLOT_LEN; i++)
         if (aux->slot_bits[i] != aux->slot_bits[i - 1]) { flips++; flip_pos = i; }
-    if (flips != 1) return;
+    if (flips != 1) return 0;
 
     uint32_t edge = aux->slot_start_ticks + flip_pos;
     uint8_t phase = (uint8_t)((edge - n->old_swap_time) % LC_MS_PER_BIT);
@@ -660,17 +690,14 @@ LC_FN void lc_nav_new_code(gps_ch_t* ch, gpsb_aux* aux, uint8_t index, int16_t n
         if (n->right_period_cnt < 3) n->period_sync_ok_flag = 0;
     }
     n->old_swap_time = edge;
-    if (n->period_sync_ok_flag && flip_pos == 2) lc_refine_edge(ch, aux);
+    return n->period_sync_ok_flag && flip_pos == 2;
 }
 
 /* ------------------------------------------------------------------------------------------ tail of the step */
-/* Second half of tracking.c:140-169: nav bits and the SNR estimate; nothing here feeds the next correlation
- * (period_sync_ok_flag is read by the NEXT millisecond's lc_pll_update, which runs after this). */
-LC_FN void lc_finish_tail(gps_ch_t* ch, gpsb_aux* aux, uint8_t index, int16_t ip, int16_t qp, uint32_t now)
+/* tracking.c:154-169: SNR estimate from the prompt sums of 200 ms */
+LC_FN void lc_snr_update(gps_ch_t* ch, gpsb_aux* aux, int16_t ip, int16_t qp)
 {
     gps_tracking_t* t = &ch->tracking_data;
-    lc_nav_new_code(ch, aux, index, ip, now);
-
     t->i_part_summ += (uint32_t)lc_iabs(ip);
     t->q_part_summ += (uint32_t)lc_iabs(qp);
     t->snr_summ_cnt++;
@@ -692,6 +719,14 @@ LC_FN void lc_finish_tail(gps_ch_t* ch, gpsb_aux* aux, uint8_t index, int16_t ip
         t->i_part_summ = 0;
         t->q_part_summ = 0;
     }
+}
+
+/* Second half of tracking.c:140-169: nav bits and the SNR estimate; nothing here feeds the next correlation
+ * (period_sync_ok_flag is written at slot index 3 and read by lc_pll_update at slot index 0). */
+LC_FN void lc_finish_tail(gps_ch_t* ch, gpsb_aux* aux, uint8_t index, int16_t ip, int16_t qp, uint32_t now)
+{
+    if (lc_nav_new_code(ch, aux, index, ip, now)) lc_refine_edge(ch, aux);
+    lc_snr_update(ch, aux, ip, qp);
 }
 
 #if !defined(__CUDACC__)

@@ -959,8 +959,41 @@ int gpsb_track_loop_dev(gpsb_ctx* c, uint32_t n_ch, void* d_channels, void* d_au
     if (n_ch == 0) return GPSB_OK;
     if (n_ms > c->ring_ms) return fail(GPSB_ERR_ARG, "run of %u ms exceeds the signal ring (%u ms)", n_ms, c->ring_ms);
     CU(cudaSetDevice(c->device));
-    k_track_run<<<n_ch, kLoopThreads, 0, c->stream>>>((gps_ch_t*)d_channels, (gpsb_aux*)d_aux, c->d_codes, c->d_signal,
-                                                      c->ring_ms, ms0, n_ms, d_iq_log, d_nav_log, d_results);
+    static const bool profile = getenv("GPSB_LOOP_PROFILE") != nullptr;     // diagnostic: per-phase clock64 ticks to stderr
+    if (profile) {
+        unsigned long long* d_prof = nullptr;
+        CU(cudaMalloc(&d_prof, (size_t)n_ch * 16 * sizeof(unsigned long long)));
+        CU(cudaMemsetAsync(d_prof, 0, (size_t)n_ch * 16 * sizeof(unsigned long long), c->stream));
+        k_track_run<true><<<n_ch, kLoopThreads, 0, c->stream>>>((gps_ch_t*)d_channels, (gpsb_aux*)d_aux, c->d_codes,
+                                                                c->d_signal, c->ring_ms, ms0, n_ms, d_iq_log, d_nav_log,
+                                                                d_results, d_prof);
+        int rc = check_launch(c, "k_track_run<profile>");
+        unsigned long long h[16] = {};
+        CU(cudaMemcpyAsync(h, d_prof, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        cudaFree(d_prof);
+        const double n = n_ms ? (double)n_ms : 1.0;
+        fprintf(stderr, "[k_track_run profile, channel 0, ticks per ms] workers: phase2+reduce %.0f (compute %.0f, redux %.0f, store %.0f), "
+                        "A -> phase 1 done %.0f (phase 1 alone: plain warp %.0f, edge warp %.0f) | code thread %.0f | nav thread %.0f | "
+                        "carrier thread %.0f (index 0: %.0f, %.0f%% float branch; others %.0f; waited at A %.0f) | loop total %.0f\n",
+                h[0] / n, h[7] / n, h[8] / n, h[9] / n, h[1] / n, h[12] / n, h[13] / n, h[2] / n, h[4] / n, h[3] / n, h[10] / (n / 4),
+                100.0 * h[11] / (n / 4), (h[3] - h[10]) / (n * 3 / 4), h[6] / n, h[5] / n);
+        return rc;
+    }
+#ifdef GPSB_LOOP_EXPERIMENTS
+    static const int experiment = getenv("GPSB_LOOP_EXPERIMENT") ? atoi(getenv("GPSB_LOOP_EXPERIMENT")) : 0;
+#define GPSB_EXP_LAUNCH(E)                                                                                               \
+    if (experiment == E) {                                                                                               \
+        k_track_run<false, E><<<n_ch, kLoopThreads, 0, c->stream>>>((gps_ch_t*)d_channels, (gpsb_aux*)d_aux, c->d_codes, \
+                                                                    c->d_signal, c->ring_ms, ms0, n_ms, d_iq_log,        \
+                                                                    d_nav_log, d_results, nullptr);                      \
+        return check_launch(c, "k_track_run<experiment>");                                                              \
+    }
+    GPSB_EXP_LAUNCH(1) GPSB_EXP_LAUNCH(2) GPSB_EXP_LAUNCH(3) GPSB_EXP_LAUNCH(4) GPSB_EXP_LAUNCH(5) GPSB_EXP_LAUNCH(7)
+#endif
+    k_track_run<false><<<n_ch, kLoopThreads, 0, c->stream>>>((gps_ch_t*)d_channels, (gpsb_aux*)d_aux, c->d_codes,
+                                                             c->d_signal, c->ring_ms, ms0, n_ms, d_iq_log, d_nav_log,
+                                                             d_results, nullptr);
     return check_launch(c, "k_track_run");
 }
 

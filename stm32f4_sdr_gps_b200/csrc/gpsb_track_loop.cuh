@@ -5,24 +5,31 @@
  * and the code offsets of millisecond t+1 come out of the DLL / PLL / FLL fed with the six sums of
  * millisecond t (Firmware/project_main/GPS/tracking.c:92-170).  With the loop filters on the host every
  * millisecond costs a PCIe round trip (several microseconds) for a fraction of a microsecond of arithmetic.
- * Here the whole loop of a channel lives in ONE CTA for a whole run of milliseconds:
+ * Here the whole loop of a channel lives in ONE CTA for a whole run of milliseconds, and the serial chain of a
+ * millisecond is cut into pieces that run side by side on different warps:
  *
- *   workers   (kLoopWorkers threads)  integrate-and-dump of the current millisecond straight from the raw
- *             frame in shared memory (core/gpsb_epl_core.h), REDUX per warp, three shared atomics per warp;
- *   control   (one thread of an extra warp) runs the reference's loop filters, false-lock check, NCO / code
- *             offset planning, nav-bit synchronisation and word assembly (core/gpsb_loop_core.h - the same
- *             source libgpsb_host.so is built from) on the channel record held in shared memory;
- *   frames    are fetched two milliseconds ahead by TMA bulk copies (cp.async.bulk -> mbarrier), issued by the
- *             control thread: they do not depend on the loop, so HBM/L2 latency never sits on the serial path.
+ *   workers  (255 threads, two data words each, + 12 "edge" lanes for words 0, 511 and the four bytes an odd offset
+ *            skips)  integrate-and-dump in two phases (core/gpsb_epl_core.h):
+ *            phase 1 needs only the code offsets and forms raw word ^ replica window + byte masks in registers;
+ *            phase 2 needs the carrier NCO words: ONE cos/sin pattern pair per word serves the three arms, then
+ *            LOP3 + POPC, REDUX per warp, one 16-byte store per warp.  Nothing mixed is ever staged in memory.
+ *   code     (1 thread)  DLL + code-offset planning (tracking.c:333-393, 115-130); releases phase 1 through an
+ *            mbarrier as soon as the offsets exist, while the carrier thread is still busy.
+ *   carrier  (1 thread)  Costas PLL / FLL / false-lock check + NCO planning (tracking.c:175-327, gps_misc.c:250).
+ *   nav      (1 thread)  bit synchronisation, word assembly, parity, SNR bookkeeping (nav_data.c:46-453,
+ *            tracking.c:154-169); waits for the DLL only for the rare bit-edge refinement that reads the code phase.
+ *   frames   arrive by TMA bulk copies (cp.async.bulk -> mbarrier) two milliseconds ahead; the eight sub-byte
+ *            shifted, periodically extended replica streams are built once per run.  Neither HBM/L2 latency nor
+ *            the period-2046-byte seam handling sits on the serial path.
  *
- * Per millisecond:  workers correlate(m) | control finishes tail(m-1)   -> barrier A ->
- *                   control: sums, DLL/PLL/FLL, plan(m+1)               -> barrier B -> ...
- * so the serial path is correlate + filters + two CTA barriers, and the nav-bit / SNR bookkeeping of a
- * millisecond overlaps the next millisecond's correlation.
+ * The control threads run the very functions libgpsb_host.so is built from (core/gpsb_loop_core.h); each field of
+ * the channel record is written by exactly one of them.  The one field read across threads,
+ * nav_data.period_sync_ok_flag, is written at slot index 3 only and read by the PLL at slot index 0 only.
  *
- * Bound: latency of one SM (a dependent chain of ~10^3 instructions per millisecond per channel); channels are
- * independent, one CTA each, so throughput scales with the channel count up to the SM count at no extra time.
- * Algorithmic HBM bytes per channel-millisecond: 2046 (frame, shared by all channels through L2) + 12 + 1 (logs).
+ * Per millisecond:  phase 2 -> barrier A -> { carrier | code | nav | workers: phase 1(m+1) } -> barrier B
+ * Bound: latency of one SM; channels are independent, one CTA each, so throughput scales with the channel count
+ * up to the SM count at no extra time.  Algorithmic HBM bytes per channel-millisecond: 2046 (frame, shared by all
+ * channels through L2) + 12 + 1 (logs).
  */
 #pragma once
 
@@ -33,26 +40,36 @@
 namespace gpsb {
 
 constexpr int kLoopWorkers = 256;
-constexpr int kLoopNw = kWords / kLoopWorkers;        // replica words per worker
-constexpr int kLoopThreads = kLoopWorkers + 32;       // + the control warp
+constexpr int kLoopNw = kWords / kLoopWorkers;        // data words per worker thread (words 1..510; 0 and 511 are edge words)
+constexpr int kSumSlots = kLoopWorkers / 32 + 1;       // worker warps + the edge warp
+constexpr int kLoopThreads = 384;                      // 8 worker warps + code, carrier, nav warps (+ 1 idle), see k_track_run
 static_assert(kLoopNw >= 1 && kLoopNw <= EC_NW_MAX && kLoopNw * kLoopWorkers == kWords, "work split");
 
 struct LoopSmem {
-    uint32_t S[2][kWords];          // raw frames m, m+1 (TMA destinations, 16-byte aligned)
-    uint32_t E[kWords];             // chip-expanded code of this channel's satellite
-    unsigned long long full[2];     // mbarriers: frame buffer b has landed
+    uint32_t S[2][kWords];              // raw frames m, m+1 (TMA destinations, 16-byte aligned)
+    uint32_t RX[8][EC_RX_WORDS + 3];    // replica stream of this satellite for sub-byte shifts 0..7, extended (ec_rx_word)
+    uint32_t E[kWords];                 // chip-expanded code of this channel's satellite
+    unsigned long long full[2];         // mbarriers: raw frame buffer b has landed
+    unsigned long long offs_ready;      // mbarrier: the code thread has published the next offsets
     gps_ch_t ch;
     gpsb_aux aux;
-    gpsb_epl_req rq;                // what the workers correlate this millisecond
-    uint32_t sums[2][4];            // packed I | Q << 16 per arm, double buffered by millisecond parity
+    gpsb_epl_req rq;                    // what the workers correlate next
+    uint4 sums[2][kSumSlots];           // per worker / edge warp: packed I | Q << 16 of the three arms; double buffered by ms parity
     int stop;
 };
+
+// warp -> worker index; warps 3, 7, 11 (scheduler 3) carry the control threads, warp 10 the edge lanes
+__constant__ int kWorkerOfWarp[12] = {0, 1, 2, -1, 3, 4, 5, -1, 6, 7, -1, -1};
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity)
 {
@@ -87,16 +104,55 @@ __device__ __forceinline__ void copy_words(T* dst, const T* src, int tid, int nt
     for (int i = tid; i < (int)(sizeof(T) / 4); i += nthreads) d[i] = s[i];
 }
 
+__device__ __forceinline__ void load_sums(const uint4* sums, int16_t iq[6])
+{
+    uint32_t packed[3] = {0u, 0u, 0u};
+#pragma unroll
+    for (int w = 0; w < kSumSlots; w++) {                   // independent 16-byte loads, then a short add tree
+        const uint4 v = sums[w];
+        packed[0] += v.x;
+        packed[1] += v.y;
+        packed[2] += v.z;
+    }
+    ec_unpack_sums(packed, iq);
+}
+
+// kProf: diagnostic build that accumulates clock64 ticks per phase into prof[chn * 16 ..] (GPSB_LOOP_PROFILE=1):
+//   0 workers: phase 2 + reduce   1 workers: A -> phase 1 of the next ms complete   2 code thread: DLL + offsets
+//   3 carrier thread              4 nav thread                                     5 whole loop
+//   6 carrier thread: wait at barrier A   7..9 phase 2 split   10, 11 carrier thread at slot index 0   12 phase-1 redos
+// kExp: timing experiments only (results wrong): bit 0 skips phase 1, bit 1 skips the carrier filters, bit 2 the DLL
+template <bool kProf, int kExp = 0>
 __global__ void __launch_bounds__(kLoopThreads, 1)
 k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uint32_t* __restrict__ codes,
             const uint32_t* __restrict__ signal, uint32_t ring_ms, uint32_t ms0, uint32_t n_ms,
-            int16_t* __restrict__ iq_log, int8_t* __restrict__ nav_log, gpsb_loop_result* __restrict__ results)
+            int16_t* __restrict__ iq_log, int8_t* __restrict__ nav_log, gpsb_loop_result* __restrict__ results,
+            unsigned long long* __restrict__ prof)
 {
     __shared__ __align__(128) LoopSmem sm;
+    long long pt[15] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long c0 = 0;
+    const long long loop_begin = kProf ? clock64() : 0;
     const int tid = threadIdx.x;
     const uint32_t chn = blockIdx.x, n_ch = gridDim.x;
-    const bool worker = tid < kLoopWorkers;
-    const bool control = tid == kLoopWorkers;
+    // Warp w issues from scheduler w % 4.  Both worker phases saturate the integer pipes of their schedulers, and a
+    // single thread's dependent chain issued on the same scheduler loses most of its slots to them (measured: the
+    // control threads run about twice as long next to busy workers).  So scheduler 3 belongs to the three control
+    // threads alone - latency-bound chains that interleave well with each other - and the eight worker warps share
+    // schedulers 0..2.
+    const int warp = tid >> 5, lane = tid & 31;
+    const int widx = kWorkerOfWarp[warp];                   // 0..7 for worker warps, -1 otherwise
+    const bool worker = widx >= 0;
+    const bool code_thr = warp == 3 && lane == 0;
+    const bool carrier_thr = warp == 7 && lane == 0;
+    const bool nav_thr = warp == 11 && lane == 0;
+    const bool edge_warp = warp == 10;                      // lanes 0..11: the irregular words and bytes (ec_epl_edge_phase1)
+    const bool edge = edge_warp && lane < EC_EDGE_LANES;
+    const int wtid = widx * 32 + lane;                      // worker thread index 0..255
+    const int w0 = wtid * kLoopNw + 1;                      // first data word of a worker: words 1..510
+    const bool plain = worker && wtid < kLoopWorkers - 1;   // the last worker thread has no words left
+    uint32_t edge_counts = 0u;
+    int edge_w = 0, edge_neg = 0;
 
     copy_words(&sm.ch, chans + chn, tid, kLoopThreads);
     copy_words(&sm.aux, auxs + chn, tid, kLoopThreads);
@@ -104,16 +160,17 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
         const uint32_t* __restrict__ e = codes + (size_t)chans[chn].prn * kWords;
         for (int i = tid; i < kWords; i += kLoopThreads) sm.E[i] = __ldg(e + i);
     }
-    if (control) {
+    if (code_thr) {
         mbar_init(&sm.full[0], 1);
         mbar_init(&sm.full[1], 1);
+        mbar_init(&sm.offs_ready, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         sm.stop = LC_STOP_NONE;
-        for (int b = 0; b < 2; b++)
-            for (int a = 0; a < 4; a++) sm.sums[b][a] = 0u;
     }
     __syncthreads();
-    if (control) {
+    for (int i = tid; i < 8 * EC_RX_WORDS; i += kLoopThreads)        // tracking only uses shifts 0..7, tracking.c:116
+        sm.RX[i / EC_RX_WORDS][i % EC_RX_WORDS] = ec_rx_word(sm.E, i % EC_RX_WORDS, (uint32_t)(i / EC_RX_WORDS));
+    if (code_thr) {
         if (sm.ch.tracking_data.state == GPS_PRE_TRACK_DONE) sm.ch.tracking_data.state = GPS_TRACKING_RUN;   // tracking.c:74-78
         if (sm.ch.tracking_data.state != GPS_TRACKING_RUN) {
             sm.stop = LC_STOP_STATE;
@@ -124,64 +181,176 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
         }
     }
     __syncthreads();
+    int stop = sm.stop;
+    ec_partial part;
+    if (stop == LC_STOP_NONE && n_ms && (plain || edge)) {  // phase 1 of millisecond 0
+        const uint32_t off[3] = {sm.rq.off_e, sm.rq.off_p, sm.rq.off_l};
+        mbar_wait(&sm.full[0], 0u);
+        if (plain) ec_epl_phase1(sm.S[0], sm.RX[sm.rq.off_bits & 7u], off, w0, kLoopNw, &part);
+        else edge_counts = ec_epl_edge_phase1(sm.S[0], sm.RX[sm.rq.off_bits & 7u], off, lane, &edge_w, &edge_neg);
+    }
+    __syncthreads();                                        // raw buffer 0 has been consumed
+    if (stop == LC_STOP_NONE && code_thr && n_ms > 2)
+        tma_load_frame(sm.S[0], signal + (size_t)((ms0 + 2) % ring_ms) * kWords, GPSB_FRAME_BYTES, &sm.full[0]);
+    lc_angle_cache angle_cache;
+    angle_cache.valid = 0;
+    // The code and the carrier thread keep private copies of the channel record for the whole run, so that the
+    // fields they own live in registers instead of taking a shared-memory round trip per access; what another
+    // thread reads (the code phase for the nav thread's edge refinement, the bit-sync flag for the PLL gains) is
+    // exchanged through sm.ch, and the owned fields are written back when the loop ends.
+    gps_tracking_t mine = sm.ch.tracking_data;
+    const uint8_t prn = sm.ch.prn;
+    const int16_t found_freq_offset_hz = sm.ch.acq_data.found_freq_offset_hz;
 
     uint32_t m = 0;
-    int stop = sm.stop;
     for (; m < n_ms && stop == LC_STOP_NONE; m++) {
         const uint32_t ms = ms0 + m;
         const uint32_t b = m & 1u;
         const uint8_t index = (uint8_t)(ms % LC_SLOT_LEN);
-        if (worker) {
-            const gpsb_epl_req rq = sm.rq;
-            const uint32_t off[3] = {rq.off_e, rq.off_p, rq.off_l};
+        const bool more = m + 1 < n_ms;
+        if (kProf) c0 = clock64();
+        if (worker || edge_warp) {                          // phase 2: the carrier phase of each word selects its I and Q count
             uint32_t acc[3] = {0u, 0u, 0u};
-            mbar_wait(&sm.full[b], (m >> 1) & 1u);
-            ec_epl_partial(sm.S[b], sm.E, rq.acc0, rq.step32, off, rq.off_bits, tid * kLoopNw, kLoopNw, acc);
-#pragma unroll
-            for (int a = 0; a < 3; a++) {
-                const uint32_t v = __reduce_add_sync(0xFFFFFFFFu, acc[a]);
-                if ((tid & 31) == 0) atomicAdd(&sm.sums[b][a], v);
+            if (plain) ec_epl_phase2(sm.rq.acc0, sm.rq.step32, w0, kLoopNw, &part, acc);
+            else if (edge) {
+                const uint32_t v = ec_epl_edge_phase2(sm.rq.acc0, sm.rq.step32, edge_w, edge_neg, edge_counts);
+                const int a = lane % 3;
+                acc[0] = a == 0 ? v : 0u;
+                acc[1] = a == 1 ? v : 0u;
+                acc[2] = a == 2 ? v : 0u;
             }
+            long long c1 = 0, c2 = 0;
+            if (kProf) { c1 = clock64(); c1 += (long long)(acc[0] & 0u); }
+            uint32_t v[3];
+#pragma unroll
+            for (int a = 0; a < 3; a++) v[a] = __reduce_add_sync(0xFFFFFFFFu, acc[a]);
+            if (kProf) { c2 = clock64(); c2 += (long long)(v[0] & 0u); }
+            if (lane == 0) sm.sums[b][edge_warp ? kSumSlots - 1 : widx] = make_uint4(v[0], v[1], v[2], 0u);
+            if (kProf && wtid == 0 && worker) { const long long c3 = clock64(); pt[0] += c3 - c0; pt[7] += c1 - c0; pt[8] += c2 - c1; pt[9] += c3 - c2; }
         }
-        __syncthreads();   // A: the six sums of millisecond m are complete, frame buffer b is free
-        int16_t iq[6];
-        if (control) {
-            const uint32_t packed[3] = {sm.sums[b][0], sm.sums[b][1], sm.sums[b][2]};
-            sm.sums[b][0] = sm.sums[b][1] = sm.sums[b][2] = 0u;
-            if (m + 2 < n_ms)
-                tma_load_frame(sm.S[b], signal + (size_t)((ms + 2) % ring_ms) * kWords, GPSB_FRAME_BYTES, &sm.full[b]);
-            ec_unpack_sums(packed, iq);
+        if (kProf && carrier_thr) c0 = clock64();
+        __syncthreads();   // A: the six sums of millisecond m are complete
+        if (worker || edge_warp) {
+            if (kProf) c0 = clock64();
+            if (more && (plain || edge)) {                  // phase 1 of millisecond m+1 as soon as its offsets exist
+                mbar_wait(&sm.full[b ^ 1u], ((m + 1) >> 1) & 1u);
+                mbar_wait(&sm.offs_ready, m & 1u);
+                long long c1 = 0;
+                if (kProf) c1 = clock64();
+                if (sm.stop == LC_STOP_NONE && !(kExp & 1)) {
+                    const uint32_t off[3] = {sm.rq.off_e, sm.rq.off_p, sm.rq.off_l};
+                    if (plain) ec_epl_phase1(sm.S[b ^ 1u], sm.RX[sm.rq.off_bits & 7u], off, w0, kLoopNw, &part);
+                    else edge_counts = ec_epl_edge_phase1(sm.S[b ^ 1u], sm.RX[sm.rq.off_bits & 7u], off, lane, &edge_w, &edge_neg);
+                }
+                if (kProf && lane == 0) { long long c2 = clock64(); c2 += (long long)((part.C[0][0] + edge_counts) & 0u); pt[13] += c2 - c1; }
+            }
+            if (kProf && wtid == 0 && worker) pt[1] += clock64() - c0;
+        } else if (code_thr) {
+            if (kProf) c0 = clock64();
+            int16_t iq[6];
+            load_sums(sm.sums[b], iq);
+            const bool degenerate = lc_dll_is_degenerate(iq);   // 0/0 in the DLL: x86 and the GPU disagree on NaN bits, host finishes this ms
+            if (degenerate) sm.stop = LC_STOP_DLL_NAN;
+            else {
+                if (!(kExp & 4)) lc_dll_update(&mine, iq[0], iq[1], iq[4], iq[5]);
+                if (more) lc_plan_code(&mine, &sm.rq);
+                sm.ch.tracking_data.code_phase_fine = mine.code_phase_fine;   // for lc_refine_edge
+            }
+            mbar_arrive(&sm.offs_ready);                    // DLL done: releases the offset check and the nav thread's edge refinement
+            if (kProf) pt[2] += clock64() - c0;
             if (iq_log) {
                 uint32_t* o = reinterpret_cast<uint32_t*>(iq_log + ((size_t)m * n_ch + chn) * 6);
                 o[0] = (uint16_t)iq[0] | ((uint32_t)(uint16_t)iq[1] << 16);
                 o[1] = (uint16_t)iq[2] | ((uint32_t)(uint16_t)iq[3] << 16);
                 o[2] = (uint16_t)iq[4] | ((uint32_t)(uint16_t)iq[5] << 16);
             }
-            if (lc_dll_is_degenerate(iq)) {          // 0/0 in the DLL: x86 and the GPU disagree on NaN bits, host finishes this ms
-                sm.stop = LC_STOP_DLL_NAN;
+            if (degenerate) {
                 gpsb_loop_result r;
                 r.done_ms = m;
                 r.stop = LC_STOP_DLL_NAN;
                 for (int k = 0; k < 6; k++) r.iq[k] = iq[k];
                 r.reserved = 0;
                 results[chn] = r;
-                if (nav_log) nav_log[(size_t)m * n_ch + chn] = -1;
-            } else {
-                lc_finish_loops(&sm.ch, &sm.aux, index, iq);
-                if (m + 1 < n_ms) lc_trk_plan_run(&sm.ch, ms + 1, ms + 1, &sm.rq);
             }
+        } else if (carrier_thr) {
+            if (kProf) { const long long c1 = clock64(); pt[6] += c1 - c0; c0 = c1; }
+            int16_t iq[6];
+            load_sums(sm.sums[b], iq);
+            if (!lc_dll_is_degenerate(iq)) {
+                // period_sync_ok_flag is written by the nav thread at slot index 3 and read here at slot index 0
+                if (!(kExp & 2)) {
+                    lc_pll_update(&mine, sm.ch.nav_data.period_sync_ok_flag, index, iq[2], iq[3]);
+                    lc_fll_update(&mine, &sm.aux, found_freq_offset_hz, index, iq[2], iq[3], &angle_cache);
+                }
+                if (more) lc_plan_carrier(&mine, prn, ms + 1, ms + 1, &sm.rq);
+            }
+            if (kProf) { const long long d = clock64() - c0; pt[3] += d; if (index == 0) { pt[10] += d; pt[11] += (iq[2] > 0); } }
+        } else if (nav_thr) {                               // nav bits and SNR of this millisecond (nav_data.c:46-453, tracking.c:154-169)
+            if (kProf) c0 = clock64();
+            int16_t iq[6];
+            load_sums(sm.sums[b], iq);
+            int8_t bit = -1;
+            if (!lc_dll_is_degenerate(iq)) {
+                const int refine = lc_nav_new_code(&sm.ch, &sm.aux, index, iq[2], ms);
+                bit = sm.aux.last_nav_bit;
+                if (refine) {                               // reads the code phase the DLL has just produced
+                    mbar_wait(&sm.offs_ready, m & 1u);
+                    lc_refine_edge(&sm.ch, &sm.aux);
+                }
+                lc_snr_update(&sm.ch, &sm.aux, iq[2], iq[3]);
+            }
+            if (nav_log) nav_log[(size_t)m * n_ch + chn] = bit;
+            if (kProf) pt[4] += clock64() - c0;
         }
-        __syncthreads();   // B: next request published
+        __syncthreads();   // B: next request published, sums consumed, raw buffer of frame m+1 consumed
         stop = sm.stop;
-        if (control && stop == LC_STOP_NONE) {       // overlaps the workers' next correlation
-            lc_finish_tail(&sm.ch, &sm.aux, index, iq[2], iq[3], ms);
-            if (nav_log) nav_log[(size_t)m * n_ch + chn] = sm.aux.last_nav_bit;
+        if (code_thr) {                                     // overlaps the workers' phase 2
+            if (m + 3 < n_ms)
+                tma_load_frame(sm.S[b ^ 1u], signal + (size_t)((ms + 3) % ring_ms) * kWords, GPSB_FRAME_BYTES, &sm.full[b ^ 1u]);
         }
     }
+    if (code_thr) {                                         // owned fields back into the shared record
+        gps_tracking_t* t = &sm.ch.tracking_data;
+        t->code_phase_fine = mine.code_phase_fine;
+        t->dll_code_err = mine.dll_code_err;
+#if (ENABLE_CODE_FILTER)
+        t->code_filt_cnt = mine.code_filt_cnt;
+        t->code_phase_fine_filt = mine.code_phase_fine_filt;
+#endif
+    } else if (carrier_thr) {
+        gps_tracking_t* t = &sm.ch.tracking_data;
+        t->if_freq_offset_hz = mine.if_freq_offset_hz;
+        t->if_freq_accum = mine.if_freq_accum;
+        t->prev_track_timestamp = mine.prev_track_timestamp;
+        t->pll_code_err = mine.pll_code_err;
+        t->fll_old_i = mine.fll_old_i;
+        t->fll_old_q = mine.fll_old_q;
+        t->fll_err = mine.fll_err;
+        for (int k = 0; k < TRACKING_CH_LENGTH; k++) t->pll_check_buf[k] = mine.pll_check_buf[k];
+        t->pll_bad_state_cnt = mine.pll_bad_state_cnt;
+        t->pll_bad_state_master_cnt = mine.pll_bad_state_master_cnt;
+    }
     __syncthreads();
+    if (kProf) {
+        if (worker && wtid == 0) {
+            prof[chn * 16 + 0] = (unsigned long long)pt[0]; prof[chn * 16 + 1] = (unsigned long long)pt[1];
+            prof[chn * 16 + 7] = (unsigned long long)pt[7]; prof[chn * 16 + 8] = (unsigned long long)pt[8];
+            prof[chn * 16 + 9] = (unsigned long long)pt[9]; prof[chn * 16 + 12] = (unsigned long long)pt[13];
+        }
+        if (edge_warp && lane == 0) prof[chn * 16 + 13] = (unsigned long long)pt[13];
+        if (code_thr) {
+            prof[chn * 16 + 2] = (unsigned long long)pt[2];
+            prof[chn * 16 + 5] = (unsigned long long)(clock64() - loop_begin);
+        }
+        if (carrier_thr) {
+            prof[chn * 16 + 3] = (unsigned long long)pt[3]; prof[chn * 16 + 6] = (unsigned long long)pt[6];
+            prof[chn * 16 + 10] = (unsigned long long)pt[10]; prof[chn * 16 + 11] = (unsigned long long)pt[11];
+        }
+        if (nav_thr) prof[chn * 16 + 4] = (unsigned long long)pt[4];
+    }
     copy_words(chans + chn, &sm.ch, tid, kLoopThreads);
     copy_words(auxs + chn, &sm.aux, tid, kLoopThreads);
-    if (control && stop != LC_STOP_DLL_NAN) {
+    if (code_thr && stop != LC_STOP_DLL_NAN) {
         gpsb_loop_result r;
         r.done_ms = m;
         r.stop = stop;

@@ -24,7 +24,7 @@ void gps_nav_data_words_detection(gps_ch_t* channel, uint8_t new_bit) { if (chan
 /* nav_data.c:46-138 */
 void hx_nav_new_code(gps_ch_t* ch, gpsb_aux* aux, uint8_t index, int16_t new_i)
 {
-    lc_nav_new_code(ch, aux, index, new_i, hx_now_ms());
+    if (lc_nav_new_code(ch, aux, index, new_i, hx_now_ms())) lc_refine_edge(ch, aux);
 }
 
 void gps_nav_data_analyse_new_code(gps_ch_t* channel, uint8_t index, int16_t new_i)

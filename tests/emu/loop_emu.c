@@ -26,50 +26,78 @@ static void expand_code(const uint8_t* chips, uint32_t* E)
     }
 }
 
-/* One E/P/L cell with the kernel's work split: n_workers threads own nw consecutive words each. */
+static void build_rx(const uint32_t* E, uint32_t bits, uint32_t* RX)
+{
+    for (int x = 0; x < EC_RX_WORDS; x++) RX[x] = ec_rx_word(E, x, bits);
+}
+
+/* the kernel's two worker phases: plain threads over data words 1..510 (nw consecutive words each, the last
+ * thread takes what is left) and the twelve edge lanes */
+static void epl_two_phase(const uint32_t* S, const uint32_t* E, const gpsb_epl_req* rq, uint32_t nw, int16_t iq[6])
+{
+    const uint32_t off[3] = {rq->off_e, rq->off_p, rq->off_l};
+    uint32_t RX[EC_RX_WORDS];
+    uint32_t total[3] = {0, 0, 0};
+    build_rx(E, rq->off_bits, RX);
+    for (int w0 = 1; w0 < EC_WORDS - 1; w0 += (int)nw) {
+        ec_partial part;
+        uint32_t acc[3] = {0, 0, 0};
+        const int n = w0 + (int)nw <= EC_WORDS - 1 ? (int)nw : EC_WORDS - 1 - w0;
+        ec_epl_phase1(S, RX, off, w0, n, &part);                            /* after the code thread's offsets */
+        ec_epl_phase2(rq->acc0, rq->step32, w0, n, &part, acc);             /* after the carrier thread's NCO words */
+        for (int a = 0; a < 3; a++) total[a] += acc[a];
+    }
+    for (int e = 0; e < EC_EDGE_LANES; e++) {
+        int w, negative;
+        const uint32_t c = ec_epl_edge_phase1(S, RX, off, e, &w, &negative);
+        total[e % 3] += ec_epl_edge_phase2(rq->acc0, rq->step32, w, negative, c);
+    }
+    ec_unpack_sums(total, iq);
+}
+
+/* One E/P/L cell with the kernel's work split: 512 / nw worker threads own nw consecutive words each. */
 void emu_epl_cell(const uint8_t* chips, const uint8_t* frame2046, uint32_t acc0, uint32_t step32, uint32_t off_e,
                   uint32_t off_p, uint32_t off_l, uint32_t bits, uint32_t nw, int16_t iq[6])
 {
     uint32_t E[EC_WORDS], S[EC_WORDS];
     expand_code(chips, E);
-    memset(S, 0, sizeof S);
+    for (int i = 0; i < EC_WORDS; i++) S[i] = 0xDEADBEEFu;      /* the pad bytes of a ring frame must not matter */
     memcpy(S, frame2046, 2046);
-    const uint32_t off[3] = {off_e, off_p, off_l};
-    uint32_t total[3] = {0, 0, 0};
-    for (int W0 = 0; W0 < EC_WORDS; W0 += (int)nw) {
-        uint32_t acc[3] = {0, 0, 0};
-        ec_epl_partial(S, E, acc0, step32, off, bits, W0, (int)nw, acc);
-        for (int a = 0; a < 3; a++) total[a] += acc[a];
-    }
-    ec_unpack_sums(total, iq);
+    gpsb_epl_req rq;
+    memset(&rq, 0, sizeof rq);
+    rq.acc0 = acc0;
+    rq.step32 = step32;
+    rq.off_e = (uint16_t)off_e;
+    rq.off_p = (uint16_t)off_p;
+    rq.off_l = (uint16_t)off_l;
+    rq.off_bits = (uint16_t)bits;
+    epl_two_phase(S, E, &rq, nw, iq);
 }
 
-/* The kernel's loop for one channel.  Returns the stop reason; *done_ms = milliseconds completed. */
+/* The kernel's loop for one channel, role by role in the order the barriers impose.  Returns the stop reason;
+ * *done_ms = milliseconds completed. */
 int emu_track_run(gps_ch_t* ch, gpsb_aux* aux, const uint8_t* signal, uint32_t ms0, uint32_t n_ms, uint32_t nw,
                   int16_t* iq_log, int8_t* nav_log, uint32_t* done_ms, int16_t stop_iq[6])
 {
     uint32_t E[EC_WORDS], S[EC_WORDS];
     expand_code(ch->prn_code, E);
     gpsb_epl_req rq;
+    lc_angle_cache cache;
+    memset(&cache, 0, sizeof cache);
     int stop = LC_STOP_NONE;
     uint32_t m = 0;
     if (ch->tracking_data.state == GPS_PRE_TRACK_DONE) ch->tracking_data.state = GPS_TRACKING_RUN;
     if (ch->tracking_data.state != GPS_TRACKING_RUN) stop = LC_STOP_STATE;
-    else if (n_ms) lc_trk_plan_run(ch, ms0, ms0, &rq);
+    else if (n_ms) {
+        lc_trk_plan_run(ch, ms0, ms0, &rq);
+    }
     for (; m < n_ms && stop == LC_STOP_NONE; m++) {
         const uint32_t ms = ms0 + m;
         const uint8_t index = (uint8_t)(ms % LC_SLOT_LEN);
-        memset(S, 0, sizeof S);
+        memset(S, 0xA5, sizeof S);
         memcpy(S, signal + (size_t)m * 2046, 2046);
-        const uint32_t off[3] = {rq.off_e, rq.off_p, rq.off_l};
-        uint32_t total[3] = {0, 0, 0};
-        for (int W0 = 0; W0 < EC_WORDS; W0 += (int)nw) {
-            uint32_t acc[3] = {0, 0, 0};
-            ec_epl_partial(S, E, rq.acc0, rq.step32, off, rq.off_bits, W0, (int)nw, acc);
-            for (int a = 0; a < 3; a++) total[a] += acc[a];
-        }
         int16_t iq[6];
-        ec_unpack_sums(total, iq);
+        epl_two_phase(S, E, &rq, nw, iq);
         if (iq_log) memcpy(iq_log + 6 * (size_t)m, iq, 12);
         if (nav_log) nav_log[m] = -1;
         if (lc_dll_is_degenerate(iq)) {
@@ -77,10 +105,23 @@ int emu_track_run(gps_ch_t* ch, gpsb_aux* aux, const uint8_t* signal, uint32_t m
             if (stop_iq) memcpy(stop_iq, iq, 12);
             break;
         }
-        lc_finish_loops(ch, aux, index, iq);
-        if (m + 1 < n_ms) lc_trk_plan_run(ch, ms + 1, ms + 1, &rq);   /* barrier B: next request published */
-        lc_finish_tail(ch, aux, index, iq[2], iq[3], ms);             /* overlaps the next correlation on the GPU */
+        /* The two control threads run side by side between the barriers; they touch disjoint fields except that
+         * the carrier thread READS nav_data.period_sync_ok_flag, which the code thread's tail may rewrite in the
+         * same millisecond - so the carrier thread samples the flag right after barrier A (kernel: `sync_ok`).
+         * Emulated here by running the carrier thread first. */
+        /* carrier thread */
+        lc_pll_update(&ch->tracking_data, ch->nav_data.period_sync_ok_flag, index, iq[2], iq[3]);
+        lc_fll_update(&ch->tracking_data, aux, ch->acq_data.found_freq_offset_hz, index, iq[2], iq[3], &cache);
+        if (m + 1 < n_ms) lc_plan_carrier(&ch->tracking_data, ch->prn, ms + 1, ms + 1, &rq);
+        /* nav thread, first part (does not need the DLL) */
+        const int refine = lc_nav_new_code(ch, aux, index, iq[2], ms);
         if (nav_log) nav_log[m] = aux->last_nav_bit;
+        /* code thread: DLL, next offsets */
+        lc_dll_update(&ch->tracking_data, iq[0], iq[1], iq[4], iq[5]);
+        if (m + 1 < n_ms) lc_plan_code(&ch->tracking_data, &rq);
+        /* nav thread, after the DLL's mbarrier */
+        if (refine) lc_refine_edge(ch, aux);
+        lc_snr_update(ch, aux, iq[2], iq[3]);
     }
     *done_ms = m;
     return stop;
@@ -152,6 +193,25 @@ uint32_t emu_rand31_mismatches(uint32_t n)
         int32_t want = 0;
         random_r(&rd, &want);
         if (lc_rand31_next(&g) != want) bad++;
+    }
+    return bad;
+}
+
+/* lc_fold_half_pi against the reference's literal form (double comparisons) for every float in [lo_bits, hi_bits] */
+uint64_t emu_fold_mismatches(uint32_t lo_bits, uint32_t hi_bits)
+{
+    uint64_t bad = 0;
+    for (uint64_t u = lo_bits; u <= hi_bits; u++) {
+        for (int neg = 0; neg < 2; neg++) {
+            float x;
+            uint32_t b = (uint32_t)u | (neg ? 0x80000000u : 0u);
+            memcpy(&x, &b, 4);
+            float want = x;
+            if (want > LC_PI / 2) want = (float)(LC_PI - want);
+            if (want < -LC_PI / 2) want = (float)(-LC_PI - want);
+            float got = lc_fold_half_pi(x);
+            if (fbits(got) != fbits(want)) bad++;
+        }
     }
     return bad;
 }

@@ -43,5 +43,7 @@ def load_emulator() -> C.CDLL:
     lib.emu_host_fll_angle.argtypes = [i32, i32, vp]
     lib.emu_rand31_mismatches.restype = u32
     lib.emu_rand31_mismatches.argtypes = [u32]
+    lib.emu_fold_mismatches.restype = C.c_uint64
+    lib.emu_fold_mismatches.argtypes = [u32, u32]
     _lib = lib
     return lib

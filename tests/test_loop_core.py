@@ -34,6 +34,15 @@ def test_device_float_math_equals_host_libm_on_the_whole_domain():
     assert not wrong, wrong[:5]
 
 
+def test_fold_half_pi_float_compare_equals_double_compare():
+    """lc_fold_half_pi compares in float against 0x3FC90FDB; the reference compares in double against M_PI/2.
+    Same result for every float from 0.5 up to the largest finite one, both signs (1.1 G values), plus the
+    neighbourhood of zero."""
+    emu = load_emulator()
+    assert emu.emu_fold_mismatches(0x3f000000, 0x7f7fffff) == 0
+    assert emu.emu_fold_mismatches(0x00000000, 0x00100000) == 0
+
+
 def test_private_rand_stream_equals_libc_default_sequence():
     assert load_emulator().emu_rand31_mismatches(200000) == 0
 
