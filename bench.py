@@ -6,10 +6,11 @@ Workload (BASELINE.json configs[1]): 4-satellite E/P/L tracking over 1 s of 16.3
 With N GPUs every rank tracks its own 4 satellites over the same second (satellites shard, no data-path
 collective): weak scaling, value = arm-samples of all ranks / max-over-ranks time.
 
-  value        arm-samples/s, signal + cell parameters already resident in HBM, device-timed (CUDA events)
-  e2e          same metric through the C ABI with HOST buffers: pinned signal upload + requests H2D +
-               results D2H inside the timed region
-  roofline     k_epl against the measured HBM peak (algorithmic bytes)
+  value        arm-samples/s of the closed loop with signal AND channel records already resident in HBM: one
+               k_track_run launch per step (loop filters on the device), device-timed (CUDA events)
+  e2e          same metric through the reference-facing host library (gpsb_rx_track_run) with HOST buffers:
+               pinned signal upload, channel records H2D, records + per-ms sums + nav bits D2H inside the timed region
+  roofline     k_track_run against the measured HBM peak (algorithmic bytes)
   cpu_baseline the unmodified reference C (oracle/_ref) on this box's host cores, same cells
   cold_acq     secondary metric: 32 SV x 21 bins x 10 ms x 2046 phases full-sky sweep (configs[2])
 
@@ -318,62 +319,93 @@ def run_gpu_arm(args) -> None:
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
 
-    # ---- closed-loop tracking through the host-side mirror (the drop-in path): value and e2e
+    # ---- closed-loop tracking: value (device-resident records, kernel only) and e2e (host library, host buffers)
+    import ctypes as C
     channels = Channels([s.prn for s in scene.sats])
     rx = Receiver(eng, channels)
+    n_ch = channels.n
     pinned_sig = torch.from_numpy(sig.copy()).pin_memory()
     eng.upload_signal(0, pinned_sig.numpy())
+    ch_bytes, aux_bytes = eng.record_bytes()
+    arm_locked(channels, scene)
+    host_records = np.ctypeslib.as_array(C.cast(channels.base, C.POINTER(C.c_uint8)), (n_ch * ch_bytes,)).copy()
+    d_pristine = torch.from_numpy(host_records).to(dev)
+    d_records = torch.empty_like(d_pristine)
+    d_aux = torch.zeros(n_ch * aux_bytes, dtype=torch.uint8, device=dev)
+    d_iq = torch.zeros(N_MS * n_ch * 6, dtype=torch.int16, device=dev)
+    d_nav = torch.zeros(N_MS * n_ch, dtype=torch.int8, device=dev)
+    d_result = torch.zeros(n_ch * 24, dtype=torch.uint8, device=dev)
+
+    def device_step():
+        d_records.copy_(d_pristine)          # re-arm (not timed)
+        d_aux.zero_()
+
     for _ in range(warm):
-        arm_locked(channels, scene)
-        rx.track_run(0, N_MS, log=False)
+        device_step()
+        eng.track_loop_dev(n_ch, d_records.data_ptr(), d_aux.data_ptr(), 0, N_MS, d_iq.data_ptr(), d_nav.data_ptr(),
+                           d_result.data_ptr())
     barrier()
     clocks = ClockSampler(local_rank)
     launches0 = eng.launch_count
     ev = events(steps)
-    wall0 = time.perf_counter()
     for k in range(steps):
-        arm_locked(channels, scene)
+        device_step()
         flush.fill_(k)                       # evict L2 between timed iterations (not timed)
         ev[k][0].record(stream)
-        rx.track_run(0, N_MS, log=False)
+        eng.track_loop_dev(n_ch, d_records.data_ptr(), d_aux.data_ptr(), 0, N_MS, d_iq.data_ptr(), d_nav.data_ptr(),
+                           d_result.data_ptr())
         ev[k][1].record(stream)
     barrier()
-    wall_loop = time.perf_counter() - wall0
     t_dev = float(np.sum([a.elapsed_time(b) for a, b in ev])) / 1e3
     launches_value = eng.launch_count - launches0
-    final_fine = [np.uint32(channels.snapshot(i).code_phase_fine_bits).view(np.float32) for i in range(channels.n)]
+    res = d_result.cpu().numpy().view(np.uint32).reshape(n_ch, 6)
+    assert (res[:, 0] == N_MS).all() and (res[:, 1] == 0).all(), res      # every channel ran every millisecond on the device
+    iq_dev = d_iq.cpu().numpy().reshape(N_MS, n_ch, 6)
 
+    # e2e: what a user of the host library calls, host buffers in and out
+    rx.set_loop_site(0)
+    for _ in range(warm):
+        arm_locked(channels, scene)
+        rx.track_run(0, N_MS, log=True)
+    barrier()
     ev = events(steps)
+    wall_e2e = 0.0
     for k in range(steps):
         arm_locked(channels, scene)
         flush.fill_(k)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
         ev[k][0].record(stream)
         eng.upload_signal(0, pinned_sig.numpy())          # host buffer -> HBM ring, inside the timed region
-        iq_log, nav_log = rx.track_run(0, N_MS, log=True)   # per-ms sums and nav bits land in host arrays
+        iq_log, nav_log = rx.track_run(0, N_MS, log=True)   # records in/out, per-ms sums and nav bits land in host arrays
         ev[k][1].record(stream)
+        torch.cuda.synchronize()
+        wall_e2e += time.perf_counter() - t0
     barrier()
     t_e2e = float(np.sum([a.elapsed_time(b) for a, b in ev])) / 1e3
+    t_e2e = max(t_e2e, wall_e2e)             # the call is synchronous: never report less than its wall time
     launches = eng.launch_count - launches0
+    on_device, on_host = rx.loop_stats()
+    assert np.array_equal(iq_log, iq_dev), "device-resident and host-library runs disagree"
+    final_fine = [np.uint32(channels.snapshot(i).code_phase_fine_bits).view(np.float32) for i in range(channels.n)]
 
-    # ---- the dominant kernel of that loop (k_epl_rt, N_SV cells per launch): average launch duration
-    from stm32f4_sdr_gps_b200 import EPL_REQ
-    rq_all, _, _ = truth_requests(scene, nco_step32)
-    rq_ms = rq_all.reshape(N_MS, -1)
-    n_probe = 200
-    pe = events(1)
-    for m in range(20):
-        eng.track_epl(rq_ms[m % N_MS])
-    barrier()
-    t0 = time.perf_counter()
-    pe[0][0].record(stream)
-    for m in range(n_probe):
-        eng.track_epl(rq_ms[m % N_MS])
-    pe[0][1].record(stream)
-    barrier()
-    rtt_us = (time.perf_counter() - t0) / n_probe * 1e6
-    rt_kernel_ms = pe[0][0].elapsed_time(pe[0][1]) / n_probe      # upper bound: includes launch gaps
+    # the same second with the loop filters on the HOST (one GPU round trip per millisecond), for comparison
+    rx.set_loop_site(1)
+    arm_locked(channels, scene)
+    rx.track_run(0, N_MS, log=False)
+    host_loop = []
+    for k in range(2):
+        arm_locked(channels, scene)
+        t0 = time.perf_counter()
+        iq_host, _ = rx.track_run(0, N_MS, log=True)
+        host_loop.append(time.perf_counter() - t0)
+    assert np.array_equal(iq_host, iq_dev), "host-resident and device-resident loops disagree"
+    host_loop_ms = min(host_loop) * 1e3
+    rx.set_loop_site(0)
 
     # ---- open-loop batch replay of the same 4000 cells in ONE launch (kernel-level throughput)
+    from stm32f4_sdr_gps_b200 import EPL_REQ  # noqa: F401
+    rq_all, _, _ = truth_requests(scene, nco_step32)
     n_cells = rq_all.size
     d_rq = torch.from_numpy(rq_all.view(np.uint8).copy()).to(dev)
     d_out = torch.zeros(n_cells * 6, dtype=torch.int16, device=dev)
@@ -458,10 +490,11 @@ def run_gpu_arm(args) -> None:
         units_step = world * N_SV_PER_GPU * ARMS * MS_SAMPLES * N_MS
         value = units_step * steps / t_dev
         e2e = units_step * steps / t_e2e
-        # algorithmic bytes: signal once per ms, 128 B of code per SV, 24 B request +
-        # 12 B result per cell
-        rt_bytes = 2046 + N_SV_PER_GPU * 128 + N_SV_PER_GPU * (24 + 12)
-        rt_achieved = rt_bytes / (rt_kernel_ms * 1e-3) / 1e9
+        # algorithmic bytes of one k_track_run launch: every frame once (all channels share it
+        # through L2), 128 B of code + channel record and scratch in and out per SV, 12 + 1 B of logs per cell
+        loop_bytes = N_MS * 2046 + N_SV_PER_GPU * (128 + 2 * (ch_bytes + aux_bytes) + 24) + N_MS * N_SV_PER_GPU * 13
+        loop_kernel_ms = t_dev * 1e3 / steps
+        loop_achieved = loop_bytes / (loop_kernel_ms * 1e-3) / 1e9
         batch_bytes = N_MS * 2046 + N_SV_PER_GPU * 128 + n_cells * (24 + 12)
         acq_bitmacs = ACQ_SV * ACQ_BINS * ACQ_MS * 2046 * 2 * 16368
         acq_alg_bytes = ACQ_MS * 2046 + len(my_sv) * 128 + n_acq_cells * 8
@@ -480,24 +513,33 @@ def run_gpu_arm(args) -> None:
             "metric": "correlator-samples/sec (E/P/L arms)", "value": value, "unit": "arm-samples/s",
             "n_gpus": world, "steps": steps, "warmup": warm,
             "ms_per_step": t_dev * 1e3 / steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u32 xor/popcount", "data": "synthetic",
+            "vs_baseline": None, "dtype": "u32 xor/popcount (sums), f32/f64 (loop filters)", "data": "synthetic",
             "config": {"workload": "config2: %d-SV E/P/L closed-loop tracking, 1 s @16.368 Msps 1-bit IF (4 SV per GPU, "
-                                   "every SV every ms, loop filters on the host)" % (world * N_SV_PER_GPU),
+                                   "every SV every ms, DLL/PLL/FLL + nav-bit logic in the loop)" % (world * N_SV_PER_GPU),
                        "n_sv": world * N_SV_PER_GPU, "n_ms": N_MS, "cells_per_step": world * n_cells,
+                       "loop_site": "device (k_track_run, one launch per step)",
                        "l2": "flushed between timed iterations (256 MiB fill)", "parallelism": "sv-shard x%d" % world},
-            "e2e": {"value": e2e, "unit": "arm-samples/s", "h2d_bytes_per_step": int(sig.nbytes + n_cells * 24),
-                    "d2h_bytes_per_step": int(n_cells * 12)},
+            "e2e": {"value": e2e, "unit": "arm-samples/s",
+                    "h2d_bytes_per_step": int(sig.nbytes + n_ch * (ch_bytes + aux_bytes)),
+                    "d2h_bytes_per_step": int(n_ch * (ch_bytes + aux_bytes + 24) + n_cells * 13),
+                    "ms_per_step": t_e2e * 1e3 / steps,
+                    "api": "gpsb_upload_signal + gpsb_rx_track_run (libgpsb_host.so), host buffers in and out"},
             "gpu_launches": int(launches),
             "clocks": clk,
-            "roofline": {"kernel": "k_epl_rt (4 cells per launch, 1000 serial launches per step)", "bound": "hbm",
-                         "achieved": rt_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": rt_achieved / hbm_peak,
+            "roofline": {"kernel": "k_track_run (1 launch per step, %d CTAs: one per satellite)" % n_ch, "bound": "hbm",
+                         "achieved": loop_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": loop_achieved / hbm_peak,
                          "traffic": None, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
-                         "algorithmic_bytes_per_launch": rt_bytes, "kernel_ms": rt_kernel_ms,
-                         "note": "latency-bound by construction: each launch depends on the previous launch's sums through "
-                                 "the host loop filters; round trip %.2f us per ms" % rtt_us},
+                         "algorithmic_bytes_per_launch": loop_bytes, "kernel_ms": loop_kernel_ms,
+                         "us_per_ms_of_signal": loop_kernel_ms * 1e3 / N_MS,
+                         "note": "serial by construction: millisecond t+1 is planned by the loop filters from the sums of "
+                                 "millisecond t (tracking.c:92-170), so the kernel is bound by the dependent-issue latency of "
+                                 "one SM per satellite, not by bandwidth; the same launch carries 1 to 148 satellites in "
+                                 "the same time"},
             "cpu_baseline": cpu,
-            "closed_loop": {"round_trip_us": rtt_us, "wall_ms_per_step": wall_loop * 1e3 / steps,
-                            "launches_per_step": launches_value / steps,
+            "closed_loop": {"device_loop_kernel_ms": loop_kernel_ms, "host_loop_ms": host_loop_ms,
+                            "host_loop_what": "same second with the loop filters on the host: one GPU round trip per ms",
+                            "launches_per_step_value": launches_value / steps,
+                            "channel_ms_on_device": int(on_device), "channel_ms_on_host_path": int(on_host),
                             "final_code_phase": [float(x) for x in final_fine]},
             "batch_replay": {"what": "the same %d cells replayed open loop in ONE k_epl launch (signal + requests resident)" % n_cells,
                              "value": N_SV_PER_GPU * ARMS * MS_SAMPLES * N_MS / (batch_ms * 1e-3), "unit": "arm-samples/s",
