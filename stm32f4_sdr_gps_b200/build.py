@@ -64,7 +64,8 @@ def build_cuda(force: bool = False) -> Path:
     if not force and _newer(CUDA_LIB, deps):
         return CUDA_LIB
     LIB_DIR.mkdir(exist_ok=True)
-    _run([_nvcc(), *NVCC_FLAGS, "-I", INCLUDE_DIR, "-o", CUDA_LIB, *srcs])
+    extra = os.environ.get("GPSB_NVCC_EXTRA", "").split()      # experiments only (e.g. -DGPSB_LOOP_EXPERIMENTS)
+    _run([_nvcc(), *NVCC_FLAGS, *extra, "-I", INCLUDE_DIR, "-o", CUDA_LIB, *srcs])
     return CUDA_LIB
 
 

@@ -132,13 +132,31 @@ EC_FN uint32_t ec_counts_masked(uint32_t t, uint32_t m, int mixed)
     return c;
 }
 
-/* the four pattern counts of a word in which all 32 bits count: the patterns 0xCCCCCCCC and 0x33333333 are
- * complements, so one POPC serves both */
-EC_FN uint32_t ec_counts_full(uint32_t x)
+/* the four pattern counts of a word in which all 32 bits count, with TWO population counts instead of four.
+ * Below the top nibble the four patterns are 0x9999999, 0xCCCCCCC, 0x6666666, 0x3333333: two complementary pairs, so
+ * over those 28 bits n0 = 28 - n2 and n1 = 28 - n3.  The top nibble (patterns 0x0, 0xC, 0x6, 0x3 - the reference's
+ * 0x9999999 literal has only seven nibbles) contributes one of 16 packed constants, ec_top_nibble_counts(x >> 28). */
+EC_FN uint32_t ec_top_nibble_counts(uint32_t v)
 {
-    const uint32_t n3 = (uint32_t)EC_POPC(x ^ 0x33333333u);
-    return ((uint32_t)EC_POPC(x ^ 0x66666666u) << 16) + (uint32_t)EC_POPC(x ^ 0x09999999u) + n3 * 0x00FFFF00u + 0x2000u;
+    uint32_t c = 0;
+    EC_UNROLL
+    for (uint32_t ph = 0; ph < 4; ph++) c |= (uint32_t)EC_POPC((v ^ (ec_cos_pattern(ph) >> 28)) & 0xFu) << (8u * ph);
+    return c;
 }
+#if defined(__CUDACC__)
+/* 16 x 4 bytes; lanes reading the same entry are served by one broadcast, different entries sit in different banks */
+#define EC_TOP_LUT(v) ec_top_lut[(v)]
+#else
+#define EC_TOP_LUT(v) ec_top_nibble_counts(v)
+#endif
+#define EC_COUNTS_FULL(x, out)                                                                                   \
+    do {                                                                                                         \
+        const uint32_t x_ = (x);                                                                                 \
+        const uint32_t n2_ = (uint32_t)EC_POPC((x_ & 0x0FFFFFFFu) ^ 0x06666666u);                                \
+        const uint32_t n3_ = (uint32_t)EC_POPC((x_ & 0x0FFFFFFFu) ^ 0x03333333u);                                \
+        /* (28 - n2) | (28 - n3) << 8 | n2 << 16 | n3 << 24, plus the top nibble's four counts */               \
+        (out) = n2_ * 0x0000FFFFu + n3_ * 0x00FFFF00u + 0x1C1Cu + EC_TOP_LUT(x_ >> 28);                          \
+    } while (0)
 
 /* ---- Phase 1 ------------------------------------------------------------------------------------------
  * Work split of a millisecond over a CTA:
@@ -151,7 +169,12 @@ EC_FN uint32_t ec_counts_full(uint32_t x)
 
 /* Plain thread.  S = raw frame, RX = extended replica for the current sub-byte shift, off[3] = byte offsets early,
  * prompt, late, data words w0 .. w0+nw-1 with 1 <= w0 and w0+nw <= 511. */
+#if defined(__CUDACC__)
+EC_FN void ec_epl_phase1(const uint32_t* S, const uint32_t* RX, const uint32_t off[3], int w0, int nw, ec_partial* p,
+                         const uint32_t* ec_top_lut)
+#else
 EC_FN void ec_epl_phase1(const uint32_t* S, const uint32_t* RX, const uint32_t off[3], int w0, int nw, ec_partial* p)
+#endif
 {
     uint32_t t[3][EC_NW_MAX], s[EC_NW_MAX];
     EC_UNROLL
@@ -199,7 +222,7 @@ EC_FN void ec_epl_phase1(const uint32_t* S, const uint32_t* RX, const uint32_t o
     for (int j = 0; j < EC_NW_MAX; j++) {
         if (j < nw) {
             EC_UNROLL
-            for (int a = 0; a < 3; a++) p->C[a][j] = ec_counts_full(t[a][j]);
+            for (int a = 0; a < 3; a++) EC_COUNTS_FULL(t[a][j], p->C[a][j]);
         }
     }
 }

@@ -53,6 +53,17 @@
 #include <string.h>
 #endif
 
+/* The loop-filter functions below touch only a few scalar fields of gps_tracking_t.  A C compiler sees them with
+ * the record itself (LC_TRK = gps_tracking_t); nvcc sees them as templates over the record type, so that k_track_run
+ * can instantiate them on small structs of the same field names that its control threads keep in REGISTERS (a
+ * private copy of the whole 152-byte record ends up in local memory: its arrays defeat scalar replacement). */
+#if defined(__CUDACC__)
+#define LC_TPL template <class LC_TRK>
+#else
+#define LC_TPL
+#define LC_TRK gps_tracking_t
+#endif
+
 #define LC_HALF_CHIPS        (2 * PRN_LENGTH)            /* 2046 code phases, acquisition.c:294 */
 #define LC_FINE_PER_HALFCHIP 8                            /* GPS_FINE_RATIO, tracking.c:23 */
 #define LC_FINE_RANGE        (LC_HALF_CHIPS * LC_FINE_PER_HALFCHIP)   /* 16368 */
@@ -281,7 +292,7 @@ LC_FN uint32_t lc_nco_step32(float freq_hz)
 }
 /* Catch-up of the carrier NCO over skipped milliseconds (gps_misc.c:196-204): the reference advances by
  * acc_step*16368 per skipped ms although a processed ms advances by 511*32 samples - reproduced as is. */
-LC_FN void lc_rewind_if_phase(gps_tracking_t* trk, uint8_t steps)
+LC_TPL LC_FN void lc_rewind_if_phase(LC_TRK* trk, uint8_t steps)
 {
     uint32_t per_sample = lc_nco_step((float)IF_FREQ_HZ + trk->if_freq_offset_hz);
     uint64_t advance = (uint64_t)per_sample * BITS_IN_PRN * steps;
@@ -311,7 +322,7 @@ LC_FN void lc_arm_offsets(float code_phase_fine, gpsb_epl_req* rq)
 /* tracking.c:92-123 for a channel in GPS_TRACKING_RUN: what to correlate this millisecond.  Two independent
  * halves - the carrier NCO words depend on the PLL/FLL state only, the code offsets on the DLL state only - so
  * the device-resident loop can run them on different threads. */
-LC_FN void lc_plan_carrier(gps_tracking_t* t, uint8_t prn, uint32_t now, uint32_t frame_ms, gpsb_epl_req* rq)
+LC_TPL LC_FN void lc_plan_carrier(LC_TRK* t, uint8_t prn, uint32_t now, uint32_t frame_ms, gpsb_epl_req* rq)
 {
     /* the NCO word first: its divide is the long dependent chain of this function, and nothing below changes
      * if_freq_offset_hz */
@@ -325,7 +336,7 @@ LC_FN void lc_plan_carrier(gps_tracking_t* t, uint8_t prn, uint32_t now, uint32_
     rq->acc0 = t->if_freq_accum;
     t->if_freq_accum += 511u * rq->step32;                         /* what the mixer leaves behind, gps_misc.c:261-273 */
 }
-LC_FN void lc_plan_code(const gps_tracking_t* t, gpsb_epl_req* rq) { lc_arm_offsets(t->code_phase_fine, rq); }
+LC_TPL LC_FN void lc_plan_code(const LC_TRK* t, gpsb_epl_req* rq) { lc_arm_offsets(t->code_phase_fine, rq); }
 LC_FN void lc_trk_plan_run(gps_ch_t* ch, uint32_t now, uint32_t frame_ms, gpsb_epl_req* rq)
 {
     lc_plan_carrier(&ch->tracking_data, ch->prn, now, frame_ms, rq);
@@ -342,7 +353,7 @@ LC_FN int lc_dll_is_degenerate(const int16_t iq[6])
 }
 
 /* tracking.c:333-393 */
-LC_FN void lc_dll_update(gps_tracking_t* t, int16_t ie, int16_t qe, int16_t il, int16_t ql)
+LC_TPL LC_FN void lc_dll_update(LC_TRK* t, int16_t ie, int16_t qe, int16_t il, int16_t ql)
 {
     int32_t early = (int32_t)ie * ie + (int32_t)qe * qe;
     int32_t late = (int32_t)il * il + (int32_t)ql * ql;
@@ -384,7 +395,7 @@ LC_FN float lc_fold_half_pi(float x)
 
 /* tracking.c:175-209.  The reference evaluates the discriminator on every millisecond and uses it on slot
  * index 0 only; it is a pure function of (ip, qp), so it is evaluated only where it is used. */
-LC_FN void lc_pll_update(gps_tracking_t* t, int period_sync_ok, uint8_t index, int16_t ip, int16_t qp)
+LC_TPL LC_FN void lc_pll_update(LC_TRK* t, int period_sync_ok, uint8_t index, int16_t ip, int16_t qp)
 {
     if (index != 0) return;
     float err = lc_costas_err(ip, qp);
@@ -405,20 +416,20 @@ LC_FN int lc_rand(gpsb_aux* aux) { return hx_rand(aux); }
 
 /* tracking.c:261-327: two or more sign flips of IP inside one 4-ms slot cannot be data; count them and,
  * after a long bad streak, jump the carrier to a random frequency at least 200 Hz away. */
-LC_FN void lc_lock_check(gps_tracking_t* t, gpsb_aux* aux, int16_t found_freq_offset_hz, uint8_t index, int16_t ip)
+LC_TPL LC_FN void lc_lock_check(LC_TRK* t, gpsb_aux* aux, int16_t found_freq_offset_hz, uint8_t index, int16_t ip)
 {
     if (index >= LC_SLOT_LEN) return;
-    for (uint8_t i = 0; i < LC_SLOT_LEN; i++)             /* pll_check_buf[index] = ip, with constant subscripts so that */
-        if (i == index) t->pll_check_buf[i] = ip;         /* a private copy of the record can live in registers */
+    /* pll_check_buf[index] = ip, spelled with constant subscripts (LC_SLOT_LEN is 4) so that a register-resident
+     * record never needs an address */
+    if (index == 0) t->pll_check_buf[0] = ip;
+    else if (index == 1) t->pll_check_buf[1] = ip;
+    else if (index == 2) t->pll_check_buf[2] = ip;
+    else t->pll_check_buf[3] = ip;
     if (index < LC_SLOT_LEN - 1) return;
 
-    uint8_t flips = 0;
-    uint8_t prev = t->pll_check_buf[0] > 0;
-    for (uint8_t i = 1; i < LC_SLOT_LEN; i++) {
-        uint8_t cur = t->pll_check_buf[i] > 0;
-        if (cur != prev) flips++;
-        prev = cur;
-    }
+    const uint8_t s0 = t->pll_check_buf[0] > 0, s1 = t->pll_check_buf[1] > 0;
+    const uint8_t s2 = t->pll_check_buf[2] > 0, s3 = t->pll_check_buf[3] > 0;
+    uint8_t flips = (uint8_t)((s0 != s1) + (s1 != s2) + (s2 != s3));
     if (flips > 1) {
         if (++t->pll_bad_state_cnt > 10) t->pll_bad_state_cnt = 10;
     } else if (t->pll_bad_state_cnt > 0) {
@@ -449,7 +460,7 @@ typedef struct lc_angle_cache {
 } lc_angle_cache;
 
 /* tracking.c:214-256 */
-LC_FN void lc_fll_update(gps_tracking_t* t, gpsb_aux* aux, int16_t found_freq_offset_hz, uint8_t index, int16_t ip,
+LC_TPL LC_FN void lc_fll_update(LC_TRK* t, gpsb_aux* aux, int16_t found_freq_offset_hz, uint8_t index, int16_t ip,
                          int16_t qp, lc_angle_cache* cache)
 {
     lc_lock_check(t, aux, found_freq_offset_hz, index, ip);

@@ -39,10 +39,17 @@
 
 namespace gpsb {
 
-constexpr int kLoopWorkers = 256;
+#ifndef GPSB_LOOP_WORKERS
+#define GPSB_LOOP_WORKERS 256
+#endif
+constexpr int kLoopWorkers = GPSB_LOOP_WORKERS;
 constexpr int kLoopNw = kWords / kLoopWorkers;        // data words per worker thread (words 1..510; 0 and 511 are edge words)
-constexpr int kSumSlots = kLoopWorkers / 32 + 1;       // worker warps + the edge warp
-constexpr int kLoopThreads = 384;                      // 8 worker warps + code, carrier, nav warps (+ 1 idle), see k_track_run
+// Warp w issues from scheduler w % 4.  Scheduler 3 (warps 3, 7, 11) belongs to the control threads; every other warp
+// is a worker warp, in order, and the one after the last worker warp carries the edge lanes.
+constexpr int kWorkerWarps = kLoopWorkers / 32;
+constexpr int kEdgeWarp = (kWorkerWarps / 3) * 4 + kWorkerWarps % 3;          // index of the (kWorkerWarps+1)-th non-control warp
+constexpr int kLoopWarps = (kEdgeWarp + 1 > 12 ? kEdgeWarp + 1 : 12);
+constexpr int kLoopThreads = kLoopWarps * 32;
 static_assert(kLoopNw >= 1 && kLoopNw <= EC_NW_MAX && kLoopNw * kLoopWorkers == kWords, "work split");
 
 struct LoopSmem {
@@ -54,12 +61,32 @@ struct LoopSmem {
     gps_ch_t ch;
     gpsb_aux aux;
     gpsb_epl_req rq;                    // what the workers correlate next
-    uint4 sums[2][kSumSlots];           // per worker / edge warp: packed I | Q << 16 of the three arms; double buffered by ms parity
+    uint32_t top_lut[16];               // ec_top_nibble_counts(0..15), see EC_COUNTS_FULL
+    uint4 sums[2];                      // packed I | Q << 16 of the three arms, accumulated by one shared-memory RED per warp
+                                        // and arm; double buffered by ms parity, re-zeroed by the code thread one ms later
     int stop;
 };
 
-// warp -> worker index; warps 3, 7, 11 (scheduler 3) carry the control threads, warp 10 the edge lanes
-__constant__ int kWorkerOfWarp[12] = {0, 1, 2, -1, 3, 4, 5, -1, 6, 7, -1, -1};
+// What the code thread and the carrier thread own of gps_tracking_t (PM/GPS/gps_misc.h:62-99), under the record's own
+// field names so that core/gpsb_loop_core.h instantiates on them: scalars only, so they live in registers for a whole run.
+struct CodeRegs {
+    float code_phase_fine, dll_code_err;
+#if (ENABLE_CODE_FILTER)
+    uint16_t code_filt_cnt;
+    float code_phase_fine_filt;
+#endif
+};
+struct CarrierRegs {
+    float if_freq_offset_hz;
+    uint32_t if_freq_accum, prev_track_timestamp;
+    float pll_code_err;
+    int16_t fll_old_i, fll_old_q;
+    float fll_err;
+    int16_t pll_check_buf[TRACKING_CH_LENGTH];
+    uint8_t pll_bad_state_cnt;
+    uint16_t pll_bad_state_master_cnt;
+};
+
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -106,14 +133,8 @@ __device__ __forceinline__ void copy_words(T* dst, const T* src, int tid, int nt
 
 __device__ __forceinline__ void load_sums(const uint4* sums, int16_t iq[6])
 {
-    uint32_t packed[3] = {0u, 0u, 0u};
-#pragma unroll
-    for (int w = 0; w < kSumSlots; w++) {                   // independent 16-byte loads, then a short add tree
-        const uint4 v = sums[w];
-        packed[0] += v.x;
-        packed[1] += v.y;
-        packed[2] += v.z;
-    }
+    const uint4 v = *sums;
+    const uint32_t packed[3] = {v.x, v.y, v.z};
     ec_unpack_sums(packed, iq);
 }
 
@@ -141,16 +162,17 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
     // threads alone - latency-bound chains that interleave well with each other - and the eight worker warps share
     // schedulers 0..2.
     const int warp = tid >> 5, lane = tid & 31;
-    const int widx = kWorkerOfWarp[warp];                   // 0..7 for worker warps, -1 otherwise
+    const int nonctl = (warp >> 2) * 3 + (warp & 3);       // rank of this warp among the non-control warps
+    const int widx = ((warp & 3) != 3 && nonctl < kWorkerWarps) ? nonctl : -1;   // worker warp index, -1 otherwise
     const bool worker = widx >= 0;
     const bool code_thr = warp == 3 && lane == 0;
     const bool carrier_thr = warp == 7 && lane == 0;
     const bool nav_thr = warp == 11 && lane == 0;
-    const bool edge_warp = warp == 10;                      // lanes 0..11: the irregular words and bytes (ec_epl_edge_phase1)
+    const bool edge_warp = warp == kEdgeWarp;                      // lanes 0..11: the irregular words and bytes (ec_epl_edge_phase1)
     const bool edge = edge_warp && lane < EC_EDGE_LANES;
     const int wtid = widx * 32 + lane;                      // worker thread index 0..255
     const int w0 = wtid * kLoopNw + 1;                      // first data word of a worker: words 1..510
-    const bool plain = worker && wtid < kLoopWorkers - 1;   // the last worker thread has no words left
+    const bool plain = worker && wtid < (kWords - 2) / kLoopNw;   // words 1..510; the last worker thread(s) have no words left
     uint32_t edge_counts = 0u;
     int edge_w = 0, edge_neg = 0;
 
@@ -166,8 +188,11 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
         mbar_init(&sm.offs_ready, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         sm.stop = LC_STOP_NONE;
+        sm.sums[0] = make_uint4(0u, 0u, 0u, 0u);
+        sm.sums[1] = make_uint4(0u, 0u, 0u, 0u);
     }
     __syncthreads();
+    if (tid < 16) sm.top_lut[tid] = ec_top_nibble_counts((uint32_t)tid);
     for (int i = tid; i < 8 * EC_RX_WORDS; i += kLoopThreads)        // tracking only uses shifts 0..7, tracking.c:116
         sm.RX[i / EC_RX_WORDS][i % EC_RX_WORDS] = ec_rx_word(sm.E, i % EC_RX_WORDS, (uint32_t)(i / EC_RX_WORDS));
     if (code_thr) {
@@ -186,7 +211,7 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
     if (stop == LC_STOP_NONE && n_ms && (plain || edge)) {  // phase 1 of millisecond 0
         const uint32_t off[3] = {sm.rq.off_e, sm.rq.off_p, sm.rq.off_l};
         mbar_wait(&sm.full[0], 0u);
-        if (plain) ec_epl_phase1(sm.S[0], sm.RX[sm.rq.off_bits & 7u], off, w0, kLoopNw, &part);
+        if (plain) ec_epl_phase1(sm.S[0], sm.RX[sm.rq.off_bits & 7u], off, w0, kLoopNw, &part, sm.top_lut);
         else edge_counts = ec_epl_edge_phase1(sm.S[0], sm.RX[sm.rq.off_bits & 7u], off, lane, &edge_w, &edge_neg);
     }
     __syncthreads();                                        // raw buffer 0 has been consumed
@@ -198,7 +223,30 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
     // fields they own live in registers instead of taking a shared-memory round trip per access; what another
     // thread reads (the code phase for the nav thread's edge refinement, the bit-sync flag for the PLL gains) is
     // exchanged through sm.ch, and the owned fields are written back when the loop ends.
-    gps_tracking_t mine = sm.ch.tracking_data;
+    CodeRegs cod;
+    CarrierRegs car;
+    {
+        const gps_tracking_t* t = &sm.ch.tracking_data;
+        cod.code_phase_fine = t->code_phase_fine;
+        cod.dll_code_err = t->dll_code_err;
+#if (ENABLE_CODE_FILTER)
+        cod.code_filt_cnt = t->code_filt_cnt;
+        cod.code_phase_fine_filt = t->code_phase_fine_filt;
+#endif
+        car.if_freq_offset_hz = t->if_freq_offset_hz;
+        car.if_freq_accum = t->if_freq_accum;
+        car.prev_track_timestamp = t->prev_track_timestamp;
+        car.pll_code_err = t->pll_code_err;
+        car.fll_old_i = t->fll_old_i;
+        car.fll_old_q = t->fll_old_q;
+        car.fll_err = t->fll_err;
+        car.pll_check_buf[0] = t->pll_check_buf[0];
+        car.pll_check_buf[1] = t->pll_check_buf[1];
+        car.pll_check_buf[2] = t->pll_check_buf[2];
+        car.pll_check_buf[3] = t->pll_check_buf[3];
+        car.pll_bad_state_cnt = t->pll_bad_state_cnt;
+        car.pll_bad_state_master_cnt = t->pll_bad_state_master_cnt;
+    }
     const uint8_t prn = sm.ch.prn;
     const int16_t found_freq_offset_hz = sm.ch.acq_data.found_freq_offset_hz;
 
@@ -225,7 +273,12 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
 #pragma unroll
             for (int a = 0; a < 3; a++) v[a] = __reduce_add_sync(0xFFFFFFFFu, acc[a]);
             if (kProf) { c2 = clock64(); c2 += (long long)(v[0] & 0u); }
-            if (lane == 0) sm.sums[b][edge_warp ? kSumSlots - 1 : widx] = make_uint4(v[0], v[1], v[2], 0u);
+            if (lane == 0) {
+                uint32_t* acc_s = reinterpret_cast<uint32_t*>(&sm.sums[b]);
+                atomicAdd(acc_s + 0, v[0]);
+                atomicAdd(acc_s + 1, v[1]);
+                atomicAdd(acc_s + 2, v[2]);
+            }
             if (kProf && wtid == 0 && worker) { const long long c3 = clock64(); pt[0] += c3 - c0; pt[7] += c1 - c0; pt[8] += c2 - c1; pt[9] += c3 - c2; }
         }
         if (kProf && carrier_thr) c0 = clock64();
@@ -239,7 +292,7 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
                 if (kProf) c1 = clock64();
                 if (sm.stop == LC_STOP_NONE && !(kExp & 1)) {
                     const uint32_t off[3] = {sm.rq.off_e, sm.rq.off_p, sm.rq.off_l};
-                    if (plain) ec_epl_phase1(sm.S[b ^ 1u], sm.RX[sm.rq.off_bits & 7u], off, w0, kLoopNw, &part);
+                    if (plain) ec_epl_phase1(sm.S[b ^ 1u], sm.RX[sm.rq.off_bits & 7u], off, w0, kLoopNw, &part, sm.top_lut);
                     else edge_counts = ec_epl_edge_phase1(sm.S[b ^ 1u], sm.RX[sm.rq.off_bits & 7u], off, lane, &edge_w, &edge_neg);
                 }
                 if (kProf && lane == 0) { long long c2 = clock64(); c2 += (long long)((part.C[0][0] + edge_counts) & 0u); pt[13] += c2 - c1; }
@@ -248,13 +301,14 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
         } else if (code_thr) {
             if (kProf) c0 = clock64();
             int16_t iq[6];
-            load_sums(sm.sums[b], iq);
+            load_sums(&sm.sums[b], iq);
+            sm.sums[b ^ 1u] = make_uint4(0u, 0u, 0u, 0u);      // consumed one ms ago by everybody (barrier B), filled again after this B
             const bool degenerate = lc_dll_is_degenerate(iq);   // 0/0 in the DLL: x86 and the GPU disagree on NaN bits, host finishes this ms
             if (degenerate) sm.stop = LC_STOP_DLL_NAN;
             else {
-                if (!(kExp & 4)) lc_dll_update(&mine, iq[0], iq[1], iq[4], iq[5]);
-                if (more) lc_plan_code(&mine, &sm.rq);
-                sm.ch.tracking_data.code_phase_fine = mine.code_phase_fine;   // for lc_refine_edge
+                if (!(kExp & 4)) lc_dll_update(&cod, iq[0], iq[1], iq[4], iq[5]);
+                if (more) lc_plan_code(&cod, &sm.rq);
+                sm.ch.tracking_data.code_phase_fine = cod.code_phase_fine;   // for lc_refine_edge
             }
             mbar_arrive(&sm.offs_ready);                    // DLL done: releases the offset check and the nav thread's edge refinement
             if (kProf) pt[2] += clock64() - c0;
@@ -275,20 +329,20 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
         } else if (carrier_thr) {
             if (kProf) { const long long c1 = clock64(); pt[6] += c1 - c0; c0 = c1; }
             int16_t iq[6];
-            load_sums(sm.sums[b], iq);
+            load_sums(&sm.sums[b], iq);
             if (!lc_dll_is_degenerate(iq)) {
                 // period_sync_ok_flag is written by the nav thread at slot index 3 and read here at slot index 0
                 if (!(kExp & 2)) {
-                    lc_pll_update(&mine, sm.ch.nav_data.period_sync_ok_flag, index, iq[2], iq[3]);
-                    lc_fll_update(&mine, &sm.aux, found_freq_offset_hz, index, iq[2], iq[3], &angle_cache);
+                    lc_pll_update(&car, sm.ch.nav_data.period_sync_ok_flag, index, iq[2], iq[3]);
+                    lc_fll_update(&car, &sm.aux, found_freq_offset_hz, index, iq[2], iq[3], &angle_cache);
                 }
-                if (more) lc_plan_carrier(&mine, prn, ms + 1, ms + 1, &sm.rq);
+                if (more) lc_plan_carrier(&car, prn, ms + 1, ms + 1, &sm.rq);
             }
             if (kProf) { const long long d = clock64() - c0; pt[3] += d; if (index == 0) { pt[10] += d; pt[11] += (iq[2] > 0); } }
         } else if (nav_thr) {                               // nav bits and SNR of this millisecond (nav_data.c:46-453, tracking.c:154-169)
             if (kProf) c0 = clock64();
             int16_t iq[6];
-            load_sums(sm.sums[b], iq);
+            load_sums(&sm.sums[b], iq);
             int8_t bit = -1;
             if (!lc_dll_is_degenerate(iq)) {
                 const int refine = lc_nav_new_code(&sm.ch, &sm.aux, index, iq[2], ms);
@@ -311,24 +365,27 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
     }
     if (code_thr) {                                         // owned fields back into the shared record
         gps_tracking_t* t = &sm.ch.tracking_data;
-        t->code_phase_fine = mine.code_phase_fine;
-        t->dll_code_err = mine.dll_code_err;
+        t->code_phase_fine = cod.code_phase_fine;
+        t->dll_code_err = cod.dll_code_err;
 #if (ENABLE_CODE_FILTER)
-        t->code_filt_cnt = mine.code_filt_cnt;
-        t->code_phase_fine_filt = mine.code_phase_fine_filt;
+        t->code_filt_cnt = cod.code_filt_cnt;
+        t->code_phase_fine_filt = cod.code_phase_fine_filt;
 #endif
     } else if (carrier_thr) {
         gps_tracking_t* t = &sm.ch.tracking_data;
-        t->if_freq_offset_hz = mine.if_freq_offset_hz;
-        t->if_freq_accum = mine.if_freq_accum;
-        t->prev_track_timestamp = mine.prev_track_timestamp;
-        t->pll_code_err = mine.pll_code_err;
-        t->fll_old_i = mine.fll_old_i;
-        t->fll_old_q = mine.fll_old_q;
-        t->fll_err = mine.fll_err;
-        for (int k = 0; k < TRACKING_CH_LENGTH; k++) t->pll_check_buf[k] = mine.pll_check_buf[k];
-        t->pll_bad_state_cnt = mine.pll_bad_state_cnt;
-        t->pll_bad_state_master_cnt = mine.pll_bad_state_master_cnt;
+        t->if_freq_offset_hz = car.if_freq_offset_hz;
+        t->if_freq_accum = car.if_freq_accum;
+        t->prev_track_timestamp = car.prev_track_timestamp;
+        t->pll_code_err = car.pll_code_err;
+        t->fll_old_i = car.fll_old_i;
+        t->fll_old_q = car.fll_old_q;
+        t->fll_err = car.fll_err;
+        t->pll_check_buf[0] = car.pll_check_buf[0];
+        t->pll_check_buf[1] = car.pll_check_buf[1];
+        t->pll_check_buf[2] = car.pll_check_buf[2];
+        t->pll_check_buf[3] = car.pll_check_buf[3];
+        t->pll_bad_state_cnt = car.pll_bad_state_cnt;
+        t->pll_bad_state_master_cnt = car.pll_bad_state_master_cnt;
     }
     __syncthreads();
     if (kProf) {
