@@ -147,7 +147,8 @@ int gpsb_session_wait(gpsb_ctx* ctx, uint32_t slot, uint32_t seq, int16_t out6[6
  *   results   n_ch records: milliseconds completed and why the channel stopped early (0 = it did not):
  *             1 the channel was not in a tracking state (nothing done), 2 the early+late power of millisecond
  *             done_ms was zero (0/0 in the DLL): its sums are in iq[], the filters were not run - the caller
- *             finishes that millisecond on the host.  Rows of the logs past done_ms are undefined.
+ *             finishes that millisecond on the host; 3 (streaming runs only) the producer did not deliver a frame
+ *             in time.  Rows of the logs past done_ms are undefined.
  * Record sizes are checked against the library's own (gpsb_track_loop_record_bytes).
  */
 typedef struct gpsb_loop_result {
@@ -164,6 +165,39 @@ void gpsb_track_loop_record_bytes(uint32_t* channel_bytes, uint32_t* aux_bytes);
  * records in HBM between runs and for timing the kernel alone.  All pointers are device pointers. */
 int gpsb_track_loop_dev(gpsb_ctx* ctx, uint32_t n_ch, void* d_channels, void* d_aux, uint32_t ms0, uint32_t n_ms,
                         int16_t* d_iq_log, int8_t* d_nav_log, gpsb_loop_result* d_results);
+int gpsb_track_loop_dev_ex(gpsb_ctx* ctx, uint32_t n_ch, void* d_channels, void* d_aux, uint32_t ms0, uint32_t n_ms,
+                           int16_t* d_iq_log, int8_t* d_nav_log, gpsb_loop_result* d_results, uint32_t flags);
+
+/* ---------------------------------------------------------------- streaming ingest -------------- */
+/*
+ * Replaces the SPI/DMA double buffer of PM/signal_capture.c:57-123 (half/full-transfer interrupts flip
+ * spi_curr_ready_rx_buf while the main loop consumes the other half): here the host keeps DMA-ing chunks of
+ * packed samples into the HBM ring on a copy stream WHILE a k_track_run launch is consuming them.  After each
+ * chunk the stream moves a watermark (first millisecond not yet uploaded) in device memory; a loop started with
+ * GPSB_LOOP_STREAMING never fetches a frame at or above the watermark - it waits for the producer, at most the
+ * stream time-out per frame (then the run ends with stop == 3, LC_STOP_STARVED, its done_ms complete and valid).
+ *
+ *   gpsb_stream_reset(ctx, ms)      frames below ms are declared present (synchronous); call before a run
+ *   gpsb_stream_push(ctx, ms0, n, p) enqueue n milliseconds (n * 2046 bytes at p, which must stay valid - ideally
+ *                                    pinned - until gpsb_stream_wait) and then the watermark ms0 + n; pushes must be
+ *                                    issued in ascending order and must not lap the consumer by more than the ring
+ *                                    (gpsb_stream_progress tells how far every channel of the running loop has got)
+ *   gpsb_stream_wait(ctx)           all pushes so far have landed
+ *   gpsb_track_loop_begin/_end      the two halves of gpsb_track_loop: _begin uploads the records and launches the loop
+ *                                    without waiting, _end waits and copies records and logs back.  Between the two
+ *                                    only gpsb_stream_* may be called on the context.
+ */
+#define GPSB_LOOP_STREAMING 1u
+int gpsb_stream_reset(gpsb_ctx* ctx, uint32_t ms_valid_upto);
+int gpsb_stream_push(gpsb_ctx* ctx, uint32_t ms0, uint32_t n_ms, const uint8_t* packed);
+int gpsb_stream_wait(gpsb_ctx* ctx);
+uint32_t gpsb_stream_progress(const gpsb_ctx* ctx, uint32_t n_ch);
+int gpsb_stream_set_timeout_ms(gpsb_ctx* ctx, uint32_t ms);
+int gpsb_track_loop_begin(gpsb_ctx* ctx, uint32_t n_ch, void* channels, uint32_t channel_bytes, void* aux,
+                          uint32_t aux_bytes, uint32_t ms0, uint32_t n_ms, int16_t* iq_log, int8_t* nav_log,
+                          gpsb_loop_result* results, uint32_t flags);
+int gpsb_track_loop_end(gpsb_ctx* ctx);
+
 /* Self-test support: the loop's two float discriminators evaluated on the device for ip in
  * [ip_lo, ip_lo + n_ip), every qp in [-8184, 8184]; out[(ip - ip_lo) * 16369 + qp + 8184] (host memory).
  * kind 0: Costas error in units of pi (PM/GPS/tracking.c:180-183), kind 1: FLL angle (tracking.c:232). */

@@ -274,6 +274,11 @@ int gpsb_rx_track_ms(gpsb_rx* rx, uint32_t ms);
  *   iq_log  [n_ms][n_ch][6]  IE,QE,IP,QP,IL,QL (zeros for channels not in GPS_TRACKING_RUN that ms)
  *   nav_log [n_ms][n_ch]     -1, or the 20-ms data bit handed to the word assembler that ms        */
 int gpsb_rx_track_run(gpsb_rx* rx, uint32_t ms0, uint32_t n_ms, int16_t* iq_log, int8_t* nav_log);
+/* Same run with the samples still in HOST memory (n_ms * 2046 bytes at packed, ideally pinned): uploads chunk_ms
+ * milliseconds (0 = 64), launches the device-resident loop and streams the rest into the HBM ring while the loop is
+ * already running - the B200 form of the reference's capture double buffer, PM/signal_capture.c:57-123. */
+int gpsb_rx_track_stream(gpsb_rx* rx, uint32_t ms0, uint32_t n_ms, const uint8_t* packed, uint32_t chunk_ms,
+                         int16_t* iq_log, int8_t* nav_log);
 /* Where gpsb_rx_track_run keeps the loop filters.  AUTO (default) and DEVICE: the whole run is one launch of the
  * device-resident loop k_track_run (include/gpsb.h, gpsb_track_loop) for every channel that is tracking; its
  * float discriminators are the fdlibm atanf/atan2f glibc ships and CUDA's double atan2, checked against the host

@@ -82,6 +82,7 @@
 #define LC_STOP_NONE       0
 #define LC_STOP_STATE      1      /* channel is not in GPS_TRACKING_RUN: nothing was done for that ms */
 #define LC_STOP_DLL_NAN    2      /* early+late power is zero: sums delivered, filters not run */
+#define LC_STOP_STARVED    3      /* streaming run: the producer did not deliver a frame in time; done_ms are complete */
 
 /* glibc's default rand(): TYPE_3 additive feedback x^31 + x^3 + 1 over 32-bit words (stdlib/random_r.c) */
 typedef struct gpsb_rand31 {

@@ -521,7 +521,21 @@ struct gpsb_ctx {
     uint32_t* d_l0 = nullptr;      // 4 x 512 words scratch for level-0 calls
     cudaEvent_t ev_start[8] = {}, ev_stop[8] = {};
     uint64_t launches = 0;
+    // streaming ingest (gpsb_stream_*): frames are DMA-ed on copy_stream while a k_track_run launch is in flight
+    cudaStream_t copy_stream = nullptr;
+    uint32_t* d_watermark = nullptr;     // first millisecond NOT yet uploaded (device memory, written by the copy stream)
+    uint32_t* h_wm_ring = nullptr;       // pinned source values of the watermark copies (one slot per push, cycled)
+    uint32_t wm_next = 0;
+    uint32_t* h_progress = nullptr;      // mapped pinned: millisecond each channel of the running loop has reached
+    uint32_t* d_progress = nullptr;
+    uint32_t stream_timeout_ms = 2000;
+    bool loop_open = false;              // between gpsb_track_loop_begin and _end (call_lock held)
+    struct {
+        void* channels; void* aux; gpsb_loop_result* results; int16_t* iq_log; int8_t* nav_log;
+        size_t ch_b, aux_b, res_b, iq_b, nav_b, o_aux, o_res, o_iq, o_nav;
+    } open_loop = {};
 };
+static const uint32_t kWmSlots = 4096;
 
 static int ensure_stage(gpsb_ctx* c, size_t bytes)
 {
@@ -688,6 +702,19 @@ int gpsb_create(gpsb_ctx** out, int device, uint32_t max_sv, uint32_t ring_ms)
         c->d_rsp = (RtRsp*)((uint8_t*)dp + kRtMaxCells * sizeof(RtCmd));
         CU(cudaStreamCreateWithFlags(&c->rt_stream, cudaStreamNonBlocking));
     }
+    CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CU(cudaMalloc(&c->d_watermark, 64));
+    CU(cudaMemset(c->d_watermark, 0, 64));
+    CU(cudaMallocHost(&c->h_wm_ring, kWmSlots * sizeof(uint32_t)));
+    {
+        void* hp = nullptr;
+        CU(cudaHostAlloc(&hp, 256 * sizeof(uint32_t), cudaHostAllocMapped));
+        memset(hp, 0, 256 * sizeof(uint32_t));
+        void* dp = nullptr;
+        CU(cudaHostGetDevicePointer(&dp, hp, 0));
+        c->h_progress = (uint32_t*)hp;
+        c->d_progress = (uint32_t*)dp;
+    }
     CU(cudaMalloc(&c->d_l0, 4 * kWords * 4 + 64));
     for (int i = 0; i < 8; i++) {
         CU(cudaEventCreate(&c->ev_start[i]));
@@ -718,6 +745,10 @@ void gpsb_destroy(gpsb_ctx* c)
     if (c->rt_stream) cudaStreamDestroy(c->rt_stream);
     if (c->h_cmd) cudaFreeHost((void*)c->h_cmd);
     if (c->d_l0) cudaFree(c->d_l0);
+    if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+    if (c->d_watermark) cudaFree(c->d_watermark);
+    if (c->h_wm_ring) cudaFreeHost(c->h_wm_ring);
+    if (c->h_progress) cudaFreeHost(c->h_progress);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     free(c->code_set);
     delete c;
@@ -952,13 +983,20 @@ void gpsb_track_loop_record_bytes(uint32_t* channel_bytes, uint32_t* aux_bytes)
     if (aux_bytes) *aux_bytes = (uint32_t)sizeof(gpsb_aux);
 }
 
-int gpsb_track_loop_dev(gpsb_ctx* c, uint32_t n_ch, void* d_channels, void* d_aux, uint32_t ms0, uint32_t n_ms,
-                        int16_t* d_iq_log, int8_t* d_nav_log, gpsb_loop_result* d_results)
+static int track_loop_launch(gpsb_ctx* c, uint32_t n_ch, void* d_channels, void* d_aux, uint32_t ms0, uint32_t n_ms,
+                             int16_t* d_iq_log, int8_t* d_nav_log, gpsb_loop_result* d_results, uint32_t flags)
 {
     if (!c || !d_channels || !d_aux || !d_results) return fail(GPSB_ERR_ARG, "gpsb_track_loop_dev: null argument");
     if (n_ch == 0) return GPSB_OK;
     if (n_ms > c->ring_ms) return fail(GPSB_ERR_ARG, "run of %u ms exceeds the signal ring (%u ms)", n_ms, c->ring_ms);
+    if ((flags & GPSB_LOOP_STREAMING) && n_ch > 256) return fail(GPSB_ERR_ARG, "a streaming run carries at most 256 channels");
     CU(cudaSetDevice(c->device));
+    StreamGate gate = {nullptr, nullptr, 0ull};
+    if (flags & GPSB_LOOP_STREAMING) {
+        gate.watermark = c->d_watermark;
+        gate.progress = c->d_progress;
+        gate.timeout_ns = (unsigned long long)c->stream_timeout_ms * 1000000ull;
+    }
     static const bool profile = getenv("GPSB_LOOP_PROFILE") != nullptr;     // diagnostic: per-phase clock64 ticks to stderr
     if (profile) {
         unsigned long long* d_prof = nullptr;
@@ -966,7 +1004,7 @@ int gpsb_track_loop_dev(gpsb_ctx* c, uint32_t n_ch, void* d_channels, void* d_au
         CU(cudaMemsetAsync(d_prof, 0, (size_t)n_ch * 16 * sizeof(unsigned long long), c->stream));
         k_track_run<true><<<n_ch, kLoopThreads, 0, c->stream>>>((gps_ch_t*)d_channels, (gpsb_aux*)d_aux, c->d_codes,
                                                                 c->d_signal, c->ring_ms, ms0, n_ms, d_iq_log, d_nav_log,
-                                                                d_results, d_prof);
+                                                                d_results, d_prof, gate);
         int rc = check_launch(c, "k_track_run<profile>");
         unsigned long long h[16] = {};
         CU(cudaMemcpyAsync(h, d_prof, sizeof h, cudaMemcpyDeviceToHost, c->stream));
@@ -986,58 +1024,173 @@ int gpsb_track_loop_dev(gpsb_ctx* c, uint32_t n_ch, void* d_channels, void* d_au
     if (experiment == E) {                                                                                               \
         k_track_run<false, E><<<n_ch, kLoopThreads, 0, c->stream>>>((gps_ch_t*)d_channels, (gpsb_aux*)d_aux, c->d_codes, \
                                                                     c->d_signal, c->ring_ms, ms0, n_ms, d_iq_log,        \
-                                                                    d_nav_log, d_results, nullptr);                      \
+                                                                    d_nav_log, d_results, nullptr, gate);                \
         return check_launch(c, "k_track_run<experiment>");                                                              \
     }
     GPSB_EXP_LAUNCH(1) GPSB_EXP_LAUNCH(2) GPSB_EXP_LAUNCH(3) GPSB_EXP_LAUNCH(4) GPSB_EXP_LAUNCH(5) GPSB_EXP_LAUNCH(7)
 #endif
+    if (flags & GPSB_LOOP_STREAMING) {
+        k_track_run<false, 0, true><<<n_ch, kLoopThreads, 0, c->stream>>>((gps_ch_t*)d_channels, (gpsb_aux*)d_aux, c->d_codes,
+                                                                          c->d_signal, c->ring_ms, ms0, n_ms, d_iq_log,
+                                                                          d_nav_log, d_results, nullptr, gate);
+        return check_launch(c, "k_track_run<streaming>");
+    }
     k_track_run<false><<<n_ch, kLoopThreads, 0, c->stream>>>((gps_ch_t*)d_channels, (gpsb_aux*)d_aux, c->d_codes,
                                                              c->d_signal, c->ring_ms, ms0, n_ms, d_iq_log, d_nav_log,
-                                                             d_results, nullptr);
+                                                             d_results, nullptr, gate);
     return check_launch(c, "k_track_run");
+}
+
+int gpsb_track_loop_dev(gpsb_ctx* c, uint32_t n_ch, void* d_channels, void* d_aux, uint32_t ms0, uint32_t n_ms,
+                        int16_t* d_iq_log, int8_t* d_nav_log, gpsb_loop_result* d_results)
+{
+    return track_loop_launch(c, n_ch, d_channels, d_aux, ms0, n_ms, d_iq_log, d_nav_log, d_results, 0u);
+}
+
+int gpsb_track_loop_dev_ex(gpsb_ctx* c, uint32_t n_ch, void* d_channels, void* d_aux, uint32_t ms0, uint32_t n_ms,
+                           int16_t* d_iq_log, int8_t* d_nav_log, gpsb_loop_result* d_results, uint32_t flags)
+{
+    return track_loop_launch(c, n_ch, d_channels, d_aux, ms0, n_ms, d_iq_log, d_nav_log, d_results, flags);
+}
+
+/* ------------------------------------------------------------------ streaming ingest */
+int gpsb_stream_reset(gpsb_ctx* c, uint32_t ms_valid_upto)
+{
+    if (!c) return fail(GPSB_ERR_ARG, "null context");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->copy_stream));
+    c->h_wm_ring[0] = ms_valid_upto;
+    c->wm_next = 1;
+    CU(cudaMemcpyAsync(c->d_watermark, &c->h_wm_ring[0], 4, cudaMemcpyHostToDevice, c->copy_stream));
+    CU(cudaStreamSynchronize(c->copy_stream));
+    for (int i = 0; i < 256; i++) c->h_progress[i] = ms_valid_upto;
+    return GPSB_OK;
+}
+
+int gpsb_stream_push(gpsb_ctx* c, uint32_t ms0, uint32_t n_ms, const uint8_t* packed)
+{
+    if (!c || !packed) return fail(GPSB_ERR_ARG, "gpsb_stream_push: null argument");
+    if (n_ms == 0) return GPSB_OK;
+    if (n_ms > c->ring_ms) return fail(GPSB_ERR_ARG, "n_ms %u exceeds ring capacity %u", n_ms, c->ring_ms);
+    CU(cudaSetDevice(c->device));
+    if (c->wm_next + 1 >= kWmSlots) {                    // the pinned source slots of earlier pushes are about to be reused
+        CU(cudaStreamSynchronize(c->copy_stream));
+        c->wm_next = 0;
+    }
+    const uint32_t f0 = ms0 % c->ring_ms;
+    const uint32_t first = (f0 + n_ms <= c->ring_ms) ? n_ms : c->ring_ms - f0;
+    CU(cudaMemcpy2DAsync((uint8_t*)c->d_signal + (size_t)f0 * GPSB_FRAME_BYTES, GPSB_FRAME_BYTES, packed, GPSB_MS_BYTES,
+                         GPSB_MS_BYTES, first, cudaMemcpyHostToDevice, c->copy_stream));
+    if (first < n_ms)
+        CU(cudaMemcpy2DAsync((uint8_t*)c->d_signal, GPSB_FRAME_BYTES, packed + (size_t)first * GPSB_MS_BYTES, GPSB_MS_BYTES,
+                             GPSB_MS_BYTES, n_ms - first, cudaMemcpyHostToDevice, c->copy_stream));
+    // same stream: the frames have landed when the watermark moves
+    uint32_t* slot = &c->h_wm_ring[c->wm_next++];
+    *slot = ms0 + n_ms;
+    CU(cudaMemcpyAsync(c->d_watermark, slot, 4, cudaMemcpyHostToDevice, c->copy_stream));
+    return GPSB_OK;
+}
+
+int gpsb_stream_wait(gpsb_ctx* c)
+{
+    if (!c) return fail(GPSB_ERR_ARG, "null context");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->copy_stream));
+    return GPSB_OK;
+}
+
+uint32_t gpsb_stream_progress(const gpsb_ctx* c, uint32_t n_ch)
+{
+    if (!c || n_ch == 0) return 0;
+    uint32_t lo = ((volatile uint32_t*)c->h_progress)[0];
+    for (uint32_t i = 1; i < n_ch && i < 256; i++) {
+        const uint32_t v = ((volatile uint32_t*)c->h_progress)[i];
+        if ((int32_t)(v - lo) < 0) lo = v;
+    }
+    return lo;
+}
+
+int gpsb_stream_set_timeout_ms(gpsb_ctx* c, uint32_t ms)
+{
+    if (!c || ms == 0) return fail(GPSB_ERR_ARG, "gpsb_stream_set_timeout_ms: bad argument");
+    c->stream_timeout_ms = ms;
+    return GPSB_OK;
+}
+
+int gpsb_track_loop_begin(gpsb_ctx* c, uint32_t n_ch, void* channels, uint32_t channel_bytes, void* aux,
+                          uint32_t aux_bytes, uint32_t ms0, uint32_t n_ms, int16_t* iq_log, int8_t* nav_log,
+                          gpsb_loop_result* results, uint32_t flags)
+{
+    if (!c || !channels || !aux || !results) return fail(GPSB_ERR_ARG, "gpsb_track_loop: null argument");
+    if (channel_bytes != sizeof(gps_ch_t) || aux_bytes != sizeof(gpsb_aux))
+        return fail(GPSB_ERR_ARG, "record sizes %u/%u do not match this library's %zu/%zu", channel_bytes, aux_bytes,
+                    sizeof(gps_ch_t), sizeof(gpsb_aux));
+    if (n_ch == 0) return fail(GPSB_ERR_ARG, "gpsb_track_loop: no channels");
+    const gps_ch_t* ch = (const gps_ch_t*)channels;
+    for (uint32_t i = 0; i < n_ch; i++) {
+        if (ch[i].prn >= c->max_sv) return fail(GPSB_ERR_ARG, "channel %u: prn %u out of range (max_sv %u)", i, ch[i].prn, c->max_sv);
+        if (!c->code_set[ch[i].prn]) return fail(GPSB_ERR_STATE, "channel %u: no code set for slot %u", i, ch[i].prn);
+    }
+    pthread_mutex_lock(&c->call_lock);                   // held until gpsb_track_loop_end: the staging buffers are in use
+    auto bail = [c](int rc) { pthread_mutex_unlock(&c->call_lock); return rc; };
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    auto& o = c->open_loop;
+    o.channels = channels; o.aux = aux; o.results = results; o.iq_log = iq_log; o.nav_log = nav_log;
+    o.ch_b = (size_t)n_ch * sizeof(gps_ch_t);
+    o.aux_b = (size_t)n_ch * sizeof(gpsb_aux);
+    o.res_b = (size_t)n_ch * sizeof(gpsb_loop_result);
+    o.iq_b = iq_log ? (size_t)n_ms * n_ch * 12 : 0;
+    o.nav_b = nav_log ? (size_t)n_ms * n_ch : 0;
+    o.o_aux = up(o.ch_b); o.o_res = o.o_aux + up(o.aux_b); o.o_iq = o.o_res + up(o.res_b); o.o_nav = o.o_iq + up(o.iq_b);
+    const size_t total = o.o_nav + up(o.nav_b);
+    int rc = ensure_stage(c, total);
+    if (rc) return bail(rc);
+    uint8_t* h = (uint8_t*)c->h_stage;
+    uint8_t* d = (uint8_t*)c->d_stage;
+    memcpy(h, channels, o.ch_b);
+    memcpy(h + o.o_aux, aux, o.aux_b);
+    cudaError_t e = cudaSetDevice(c->device);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d, h, o.o_aux + o.aux_b, cudaMemcpyHostToDevice, c->stream);   // records: one copy in
+    if (e != cudaSuccess) return bail(fail(GPSB_ERR_CUDA, "record upload failed: %s", cudaGetErrorString(e)));
+    rc = track_loop_launch(c, n_ch, d, d + o.o_aux, ms0, n_ms, iq_log ? (int16_t*)(d + o.o_iq) : nullptr,
+                           nav_log ? (int8_t*)(d + o.o_nav) : nullptr, (gpsb_loop_result*)(d + o.o_res), flags);
+    if (rc) return bail(rc);
+    const size_t back = (o.nav_b ? o.o_nav + o.nav_b : o.iq_b ? o.o_iq + o.iq_b : o.o_res + o.res_b);
+    e = cudaMemcpyAsync(h, d, back, cudaMemcpyDeviceToHost, c->stream);                                       // records + logs: one copy out
+    if (e != cudaSuccess) return bail(fail(GPSB_ERR_CUDA, "result download failed: %s", cudaGetErrorString(e)));
+    c->loop_open = true;
+    return GPSB_OK;
+}
+
+int gpsb_track_loop_end(gpsb_ctx* c)
+{
+    if (!c) return fail(GPSB_ERR_ARG, "null context");
+    if (!c->loop_open) return fail(GPSB_ERR_STATE, "gpsb_track_loop_end without gpsb_track_loop_begin");
+    c->loop_open = false;
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    int rc = GPSB_OK;
+    if (e != cudaSuccess) rc = fail(GPSB_ERR_CUDA, "k_track_run failed: %s", cudaGetErrorString(e));
+    else {
+        const auto& o = c->open_loop;
+        const uint8_t* h = (const uint8_t*)c->h_stage;
+        memcpy(o.channels, h, o.ch_b);
+        memcpy(o.aux, h + o.o_aux, o.aux_b);
+        memcpy(o.results, h + o.o_res, o.res_b);
+        if (o.iq_log) memcpy(o.iq_log, h + o.o_iq, o.iq_b);
+        if (o.nav_log) memcpy(o.nav_log, h + o.o_nav, o.nav_b);
+    }
+    pthread_mutex_unlock(&c->call_lock);
+    return rc;
 }
 
 int gpsb_track_loop(gpsb_ctx* c, uint32_t n_ch, void* channels, uint32_t channel_bytes, void* aux,
                     uint32_t aux_bytes, uint32_t ms0, uint32_t n_ms, int16_t* iq_log, int8_t* nav_log,
                     gpsb_loop_result* results)
 {
-    if (!c || !channels || !aux || !results) return fail(GPSB_ERR_ARG, "gpsb_track_loop: null argument");
-    if (channel_bytes != sizeof(gps_ch_t) || aux_bytes != sizeof(gpsb_aux))
-        return fail(GPSB_ERR_ARG, "record sizes %u/%u do not match this library's %zu/%zu", channel_bytes, aux_bytes,
-                    sizeof(gps_ch_t), sizeof(gpsb_aux));
-    if (n_ch == 0) return GPSB_OK;
-    const gps_ch_t* ch = (const gps_ch_t*)channels;
-    for (uint32_t i = 0; i < n_ch; i++) {
-        if (ch[i].prn >= c->max_sv) return fail(GPSB_ERR_ARG, "channel %u: prn %u out of range (max_sv %u)", i, ch[i].prn, c->max_sv);
-        if (!c->code_set[ch[i].prn]) return fail(GPSB_ERR_STATE, "channel %u: no code set for slot %u", i, ch[i].prn);
-    }
-    CallGuard guard(c);
-    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
-    const size_t ch_b = (size_t)n_ch * sizeof(gps_ch_t), aux_b = (size_t)n_ch * sizeof(gpsb_aux);
-    const size_t res_b = (size_t)n_ch * sizeof(gpsb_loop_result);
-    const size_t iq_b = iq_log ? (size_t)n_ms * n_ch * 12 : 0, nav_b = nav_log ? (size_t)n_ms * n_ch : 0;
-    const size_t o_aux = up(ch_b), o_res = o_aux + up(aux_b), o_iq = o_res + up(res_b), o_nav = o_iq + up(iq_b);
-    const size_t total = o_nav + up(nav_b);
-    int rc = ensure_stage(c, total);
+    if (c && n_ch == 0) return GPSB_OK;
+    int rc = gpsb_track_loop_begin(c, n_ch, channels, channel_bytes, aux, aux_bytes, ms0, n_ms, iq_log, nav_log, results, 0u);
     if (rc) return rc;
-    uint8_t* h = (uint8_t*)c->h_stage;
-    uint8_t* d = (uint8_t*)c->d_stage;
-    memcpy(h, channels, ch_b);
-    memcpy(h + o_aux, aux, aux_b);
-    CU(cudaSetDevice(c->device));
-    CU(cudaMemcpyAsync(d, h, o_aux + aux_b, cudaMemcpyHostToDevice, c->stream));      // records: one copy in
-    rc = gpsb_track_loop_dev(c, n_ch, d, d + o_aux, ms0, n_ms, iq_log ? (int16_t*)(d + o_iq) : nullptr,
-                             nav_log ? (int8_t*)(d + o_nav) : nullptr, (gpsb_loop_result*)(d + o_res));
-    if (rc) return rc;
-    const size_t back = (nav_b ? o_nav + nav_b : iq_b ? o_iq + iq_b : o_res + res_b);
-    CU(cudaMemcpyAsync(h, d, back, cudaMemcpyDeviceToHost, c->stream));               // records + logs: one copy out
-    CU(cudaStreamSynchronize(c->stream));
-    memcpy(channels, h, ch_b);
-    memcpy(aux, h + o_aux, aux_b);
-    memcpy(results, h + o_res, res_b);
-    if (iq_log) memcpy(iq_log, h + o_iq, iq_b);
-    if (nav_log) memcpy(nav_log, h + o_nav, nav_b);
-    return GPSB_OK;
+    return gpsb_track_loop_end(c);
 }
 
 int gpsb_l0_loop_math(gpsb_ctx* c, int kind, int32_t ip_lo, uint32_t n_ip, float* out)

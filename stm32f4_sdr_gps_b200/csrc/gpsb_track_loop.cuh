@@ -65,6 +65,7 @@ struct LoopSmem {
     uint4 sums[2];                      // packed I | Q << 16 of the three arms, accumulated by one shared-memory RED per warp
                                         // and arm; double buffered by ms parity, re-zeroed by the code thread one ms later
     int stop;
+    int starved;                        // streaming: the producer missed a frame; the current millisecond is the last of this run
 };
 
 // What the code thread and the carrier thread own of gps_tracking_t (PM/GPS/gps_misc.h:62-99), under the record's own
@@ -138,17 +139,52 @@ __device__ __forceinline__ void load_sums(const uint4* sums, int16_t iq[6])
     ec_unpack_sums(packed, iq);
 }
 
+// Streaming ingest: while a run is in flight the host keeps DMA-ing frames into the ring and, after each chunk, the
+// number of the first millisecond NOT yet uploaded into `*watermark` (device memory, same copy stream, so the frames
+// land first).  The code thread looks at it only when the frame it is about to fetch is not known to be there yet -
+// once per chunk in steady state - and never waits longer than timeout_ns in total for one frame (a stalled producer
+// ends the run with LC_STOP_STARVED instead of wedging the GPU).  watermark == nullptr: everything is resident.
+struct StreamGate {
+    const uint32_t* watermark;
+    uint32_t* progress;              // mapped host memory, [n_ch]: millisecond the channel has reached (flow control)
+    unsigned long long timeout_ns;
+};
+
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// 1 when frame `ms` is in the ring (known_upto caches the last watermark seen), 0 when the producer timed out
+__device__ __forceinline__ int frame_present(const StreamGate& gate, uint32_t ms, uint32_t& known_upto)
+{
+    if (!gate.watermark || (int32_t)(known_upto - ms) > 0) return 1;
+    unsigned long long t0 = 0;
+    for (;;) {
+        known_upto = ld_acquire_u32(gate.watermark);
+        if ((int32_t)(known_upto - ms) > 0) return 1;
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (!t0) t0 = now;
+        else if (now - t0 > gate.timeout_ns) return 0;
+        __nanosleep(200);
+    }
+}
+
 // kProf: diagnostic build that accumulates clock64 ticks per phase into prof[chn * 16 ..] (GPSB_LOOP_PROFILE=1):
 //   0 workers: phase 2 + reduce   1 workers: A -> phase 1 of the next ms complete   2 code thread: DLL + offsets
 //   3 carrier thread              4 nav thread                                     5 whole loop
 //   6 carrier thread: wait at barrier A   7..9 phase 2 split   10, 11 carrier thread at slot index 0   12 phase-1 redos
 // kExp: timing experiments only (results wrong): bit 0 skips phase 1, bit 1 skips the carrier filters, bit 2 the DLL
-template <bool kProf, int kExp = 0>
+// kStream: streaming-ingest build (the resident build carries none of its checks)
+template <bool kProf, int kExp = 0, bool kStream = false>
 __global__ void __launch_bounds__(kLoopThreads, 1)
 k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uint32_t* __restrict__ codes,
             const uint32_t* __restrict__ signal, uint32_t ring_ms, uint32_t ms0, uint32_t n_ms,
             int16_t* __restrict__ iq_log, int8_t* __restrict__ nav_log, gpsb_loop_result* __restrict__ results,
-            unsigned long long* __restrict__ prof)
+            unsigned long long* __restrict__ prof, StreamGate gate)
 {
     __shared__ __align__(128) LoopSmem sm;
     long long pt[15] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -188,6 +224,7 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
         mbar_init(&sm.offs_ready, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         sm.stop = LC_STOP_NONE;
+        sm.starved = 0;
         sm.sums[0] = make_uint4(0u, 0u, 0u, 0u);
         sm.sums[1] = make_uint4(0u, 0u, 0u, 0u);
     }
@@ -195,13 +232,21 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
     if (tid < 16) sm.top_lut[tid] = ec_top_nibble_counts((uint32_t)tid);
     for (int i = tid; i < 8 * EC_RX_WORDS; i += kLoopThreads)        // tracking only uses shifts 0..7, tracking.c:116
         sm.RX[i / EC_RX_WORDS][i % EC_RX_WORDS] = ec_rx_word(sm.E, i % EC_RX_WORDS, (uint32_t)(i / EC_RX_WORDS));
+    uint32_t known_upto = ms0;          // code thread: frames below this are known to be in the ring
+    uint32_t issued = 0, consumed = 0;  // code thread: frames fetched by bulk copy / frames the workers have waited for
     if (code_thr) {
         if (sm.ch.tracking_data.state == GPS_PRE_TRACK_DONE) sm.ch.tracking_data.state = GPS_TRACKING_RUN;   // tracking.c:74-78
         if (sm.ch.tracking_data.state != GPS_TRACKING_RUN) {
             sm.stop = LC_STOP_STATE;
         } else if (n_ms) {
-            for (uint32_t k = 0; k < 2 && k < n_ms; k++)
-                tma_load_frame(sm.S[k], signal + (size_t)((ms0 + k) % ring_ms) * kWords, GPSB_FRAME_BYTES, &sm.full[k]);
+            const uint32_t first = n_ms < 2 ? n_ms : 2;
+            if (kStream && !frame_present(gate, ms0 + first - 1, known_upto)) sm.stop = LC_STOP_STARVED;    // nothing fetched, nothing done
+            else {
+                for (uint32_t k = 0; k < first; k++)
+                    tma_load_frame(sm.S[k], signal + (size_t)((ms0 + k) % ring_ms) * kWords, GPSB_FRAME_BYTES, &sm.full[k]);
+                issued = first;
+                consumed = 1;           // phase 1 of millisecond 0, below
+            }
             lc_trk_plan_run(&sm.ch, ms0, ms0, &sm.rq);
         }
     }
@@ -215,8 +260,16 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
         else edge_counts = ec_epl_edge_phase1(sm.S[0], sm.RX[sm.rq.off_bits & 7u], off, lane, &edge_w, &edge_neg);
     }
     __syncthreads();                                        // raw buffer 0 has been consumed
-    if (stop == LC_STOP_NONE && code_thr && n_ms > 2)
-        tma_load_frame(sm.S[0], signal + (size_t)((ms0 + 2) % ring_ms) * kWords, GPSB_FRAME_BYTES, &sm.full[0]);
+    // A frame that is not there in time ends the run: the code thread raises sm.starved BEFORE barrier A of the next
+    // millisecond, every thread then treats that millisecond as the last one (no plan, no phase 1 for a successor),
+    // so the records leave the kernel exactly as after a shorter run.
+    if (stop == LC_STOP_NONE && code_thr && n_ms > 2) {
+        if (kStream && !frame_present(gate, ms0 + 2, known_upto)) sm.starved = 1;
+        else {
+            tma_load_frame(sm.S[0], signal + (size_t)((ms0 + 2) % ring_ms) * kWords, GPSB_FRAME_BYTES, &sm.full[0]);
+            issued = 3;
+        }
+    }
     lc_angle_cache angle_cache;
     angle_cache.valid = 0;
     // The code and the carrier thread keep private copies of the channel record for the whole run, so that the
@@ -255,7 +308,6 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
         const uint32_t ms = ms0 + m;
         const uint32_t b = m & 1u;
         const uint8_t index = (uint8_t)(ms % LC_SLOT_LEN);
-        const bool more = m + 1 < n_ms;
         if (kProf) c0 = clock64();
         if (worker || edge_warp) {                          // phase 2: the carrier phase of each word selects its I and Q count
             uint32_t acc[3] = {0u, 0u, 0u};
@@ -283,6 +335,7 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
         }
         if (kProf && carrier_thr) c0 = clock64();
         __syncthreads();   // A: the six sums of millisecond m are complete
+        const bool more = m + 1 < n_ms && !(kStream && *(volatile int*)&sm.starved);
         if (worker || edge_warp) {
             if (kProf) c0 = clock64();
             if (more && (plain || edge)) {                  // phase 1 of millisecond m+1 as soon as its offsets exist
@@ -303,9 +356,11 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
             int16_t iq[6];
             load_sums(&sm.sums[b], iq);
             sm.sums[b ^ 1u] = make_uint4(0u, 0u, 0u, 0u);      // consumed one ms ago by everybody (barrier B), filled again after this B
+            if (more) consumed++;                               // the workers wait for frame m+1 this millisecond
             const bool degenerate = lc_dll_is_degenerate(iq);   // 0/0 in the DLL: x86 and the GPU disagree on NaN bits, host finishes this ms
             if (degenerate) sm.stop = LC_STOP_DLL_NAN;
             else {
+                if (kStream && sm.starved) sm.stop = LC_STOP_STARVED;     // this millisecond is completed by every thread, then the run ends
                 if (!(kExp & 4)) lc_dll_update(&cod, iq[0], iq[1], iq[4], iq[5]);
                 if (more) lc_plan_code(&cod, &sm.rq);
                 sm.ch.tracking_data.code_phase_fine = cod.code_phase_fine;   // for lc_refine_edge
@@ -359,10 +414,18 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
         __syncthreads();   // B: next request published, sums consumed, raw buffer of frame m+1 consumed
         stop = sm.stop;
         if (code_thr) {                                     // overlaps the workers' phase 2
-            if (m + 3 < n_ms)
-                tma_load_frame(sm.S[b ^ 1u], signal + (size_t)((ms + 3) % ring_ms) * kWords, GPSB_FRAME_BYTES, &sm.full[b ^ 1u]);
+            if (m + 3 < n_ms && stop == LC_STOP_NONE && !(kStream && sm.starved)) {
+                if (kStream && !frame_present(gate, ms + 3, known_upto)) sm.starved = 1;
+                else {
+                    tma_load_frame(sm.S[b ^ 1u], signal + (size_t)((ms + 3) % ring_ms) * kWords, GPSB_FRAME_BYTES, &sm.full[b ^ 1u]);
+                    issued = m + 4;
+                }
+            }
+            if (kStream && gate.progress && (m & 63u) == 63u) *(volatile uint32_t*)(gate.progress + chn) = ms + 1;
         }
     }
+    if (code_thr)      // early exit: bulk copies nobody waited for may still be in flight - let them land before the CTA retires
+        for (uint32_t f = consumed; f < issued; f++) mbar_wait(&sm.full[f & 1u], (f >> 1) & 1u);
     if (code_thr) {                                         // owned fields back into the shared record
         gps_tracking_t* t = &sm.ch.tracking_data;
         t->code_phase_fine = cod.code_phase_fine;

@@ -92,6 +92,14 @@ def load_library(path: Path | None = None) -> C.CDLL:
         "gpsb_sweep_dev": (i32, [vp, vp, u32, vp, u32, u32, u32, u32, vp]),
         "gpsb_track_loop": (i32, [vp, u32, vp, u32, vp, u32, u32, u32, vp, vp, vp]),
         "gpsb_track_loop_dev": (i32, [vp, u32, vp, vp, u32, u32, vp, vp, vp]),
+        "gpsb_track_loop_dev_ex": (i32, [vp, u32, vp, vp, u32, u32, vp, vp, vp, u32]),
+        "gpsb_track_loop_begin": (i32, [vp, u32, vp, u32, vp, u32, u32, u32, vp, vp, vp, u32]),
+        "gpsb_track_loop_end": (i32, [vp]),
+        "gpsb_stream_reset": (i32, [vp, u32]),
+        "gpsb_stream_push": (i32, [vp, u32, u32, vp]),
+        "gpsb_stream_wait": (i32, [vp]),
+        "gpsb_stream_progress": (u32, [vp, u32]),
+        "gpsb_stream_set_timeout_ms": (i32, [vp, u32]),
         "gpsb_track_loop_record_bytes": (None, [C.POINTER(u32), C.POINTER(u32)]),
         "gpsb_l0_loop_math": (i32, [vp, i32, C.c_int32, u32, vp]),
         "gpsb_l0_generate_prn_data2": (i32, [vp, vp, vp, u16]),
@@ -268,6 +276,28 @@ class Engine:
         """k_track_run on device-resident channel records (raw device pointers; only enqueued)."""
         self._check(self.lib.gpsb_track_loop_dev(self._ctx, n_ch, d_channels, d_aux, ms0, n_ms, d_iq_log or None,
                                                  d_nav_log or None, d_results))
+
+    def track_loop_dev_ex(self, n_ch: int, d_channels: int, d_aux: int, ms0: int, n_ms: int, d_iq_log: int,
+                          d_nav_log: int, d_results: int, flags: int) -> None:
+        self._check(self.lib.gpsb_track_loop_dev_ex(self._ctx, n_ch, d_channels, d_aux, ms0, n_ms, d_iq_log or None,
+                                                    d_nav_log or None, d_results, flags))
+
+    # streaming ingest (include/gpsb.h): frames DMA-ed into the ring while a loop launch consumes them
+    def stream_reset(self, ms_valid_upto: int) -> None:
+        self._check(self.lib.gpsb_stream_reset(self._ctx, ms_valid_upto))
+
+    def stream_push(self, ms0: int, packed: np.ndarray) -> None:
+        packed = np.ascontiguousarray(packed, dtype=np.uint8)
+        self._check(self.lib.gpsb_stream_push(self._ctx, ms0, packed.size // MS_BYTES, _p(packed)))
+
+    def stream_wait(self) -> None:
+        self._check(self.lib.gpsb_stream_wait(self._ctx))
+
+    def stream_progress(self, n_ch: int) -> int:
+        return int(self.lib.gpsb_stream_progress(self._ctx, n_ch))
+
+    def stream_set_timeout_ms(self, ms: int) -> None:
+        self._check(self.lib.gpsb_stream_set_timeout_ms(self._ctx, ms))
 
     def record_bytes(self):
         a, b = C.c_uint32(), C.c_uint32()

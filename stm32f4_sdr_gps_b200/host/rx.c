@@ -292,6 +292,36 @@ static int run_channel_span(gpsb_rx* rx, uint32_t i, uint32_t ms0, uint32_t ms, 
     return GPSB_OK;
 }
 
+/* After a k_track_run launch over all channels: SNR values, statistics, and whatever the loop handed back (a
+ * degenerate DLL millisecond, a starved streaming run) finished channel by channel on the per-millisecond path. */
+static int finish_device_run(gpsb_rx* rx, uint32_t ms0, uint32_t n_ms, int16_t* iq_log, int8_t* nav_log)
+{
+    const uint32_t n_ch = rx->n_ch;
+    for (uint32_t i = 0; i < n_ch; i++) {
+        const gpsb_loop_result* r = &rx->loop_res[i];
+        lc_resolve_snr(&rx->ch[i], &rx->aux[i]);
+        rx->device_ms += r->done_ms;
+        uint32_t ms = ms0 + r->done_ms;
+        if (r->stop == LC_STOP_DLL_NAN && r->done_ms < n_ms) {
+            gpsb_host_set_packet_cnt(ms);
+            rx->aux[i].last_nav_bit = -1;
+            hx_trk_finish_epl(&rx->ch[i], &rx->aux[i], (uint8_t)(ms % GPSB_SLOT_LEN), r->iq);
+            if (nav_log) nav_log[(size_t)(ms - ms0) * n_ch + i] = rx->aux[i].last_nav_bit;
+            rx->host_ms++;
+            ms++;
+        }
+        if (ms < ms0 + n_ms) {
+            if (iq_log)
+                for (uint32_t k = ms - ms0; k < n_ms; k++) memset(iq_log + ((size_t)k * n_ch + i) * 6, 0, 12);
+            if (nav_log)
+                for (uint32_t k = ms - ms0; k < n_ms; k++) nav_log[(size_t)k * n_ch + i] = -1;
+            int rc = run_channel_span(rx, i, ms0, ms, ms0 + n_ms, iq_log, nav_log);
+            if (rc != GPSB_OK) return rc;
+        }
+    }
+    return GPSB_OK;
+}
+
 /* The whole run with the loops on the device: one k_track_run launch for every channel that is tracking, then
  * whatever is left (channels handed back early, channels still in pre-track) channel by channel. */
 static int track_run_device(gpsb_rx* rx, uint32_t ms0, uint32_t n_ms, int16_t* iq_log, int8_t* nav_log)
@@ -305,34 +335,56 @@ static int track_run_device(gpsb_rx* rx, uint32_t ms0, uint32_t n_ms, int16_t* i
         int rc = gpsb_track_loop(rx->ctx, n_ch, rx->ch, (uint32_t)sizeof(gps_ch_t), rx->aux, (uint32_t)sizeof(gpsb_aux), ms0,
                                  n_ms, iq_log, nav_log, rx->loop_res);
         if (rc != GPSB_OK) return hx_note(rc);
-        for (uint32_t i = 0; i < n_ch; i++) {
-            const gpsb_loop_result* r = &rx->loop_res[i];
-            lc_resolve_snr(&rx->ch[i], &rx->aux[i]);
-            rx->device_ms += r->done_ms;
-            uint32_t ms = ms0 + r->done_ms;
-            if (r->stop == LC_STOP_DLL_NAN && r->done_ms < n_ms) {
-                gpsb_host_set_packet_cnt(ms);
-                rx->aux[i].last_nav_bit = -1;
-                hx_trk_finish_epl(&rx->ch[i], &rx->aux[i], (uint8_t)(ms % GPSB_SLOT_LEN), r->iq);
-                if (nav_log) nav_log[(size_t)(ms - ms0) * n_ch + i] = rx->aux[i].last_nav_bit;
-                rx->host_ms++;
-                ms++;
-            }
-            if (ms < ms0 + n_ms) {
-                if (iq_log)
-                    for (uint32_t k = ms - ms0; k < n_ms; k++) memset(iq_log + ((size_t)k * n_ch + i) * 6, 0, 12);
-                if (nav_log)
-                    for (uint32_t k = ms - ms0; k < n_ms; k++) nav_log[(size_t)k * n_ch + i] = -1;
-                rc = run_channel_span(rx, i, ms0, ms, ms0 + n_ms, iq_log, nav_log);
-                if (rc != GPSB_OK) return rc;
-            }
-        }
+        rc = finish_device_run(rx, ms0, n_ms, iq_log, nav_log);
+        if (rc != GPSB_OK) return rc;
     } else {
         for (uint32_t i = 0; i < n_ch; i++) {
             int rc = run_channel_span(rx, i, ms0, ms0, ms0 + n_ms, iq_log, nav_log);
             if (rc != GPSB_OK) return rc;
         }
     }
+    gpsb_host_set_packet_cnt(ms0 + n_ms - 1);
+    return GPSB_OK;
+}
+
+/* Streaming form of gpsb_rx_track_run: the samples are still in HOST memory.  The first chunk is uploaded, the
+ * device-resident loop is launched for the whole run, and the remaining chunks are DMA-ed into the ring while the
+ * loop is already tracking (include/gpsb.h, "streaming ingest"): the upload disappears behind the run instead of
+ * preceding it.  Falls back to upload-then-run when some channel is not tracking yet or the loops are on the host. */
+int gpsb_rx_track_stream(gpsb_rx* rx, uint32_t ms0, uint32_t n_ms, const uint8_t* packed, uint32_t chunk_ms,
+                         int16_t* iq_log, int8_t* nav_log)
+{
+    if (!rx || !packed) return GPSB_ERR_ARG;
+    if (n_ms == 0) return GPSB_OK;
+    if (chunk_ms == 0) chunk_ms = 64;
+    const uint32_t n_ch = rx->n_ch;
+    uint32_t n_trk = 0;
+    for (uint32_t i = 0; i < n_ch; i++) n_trk += is_tracking(&rx->ch[i]) ? 1u : 0u;
+    if (n_trk != n_ch || n_ch > 256 || rx->loop_site == GPSB_LOOP_HOST || gpsb_session_slots(rx->ctx) != 0) {
+        int rc = gpsb_upload_signal(rx->ctx, ms0, n_ms, packed);
+        if (rc != GPSB_OK) return hx_note(rc);
+        return gpsb_rx_track_run(rx, ms0, n_ms, iq_log, nav_log);
+    }
+    int rc = gpsb_stream_reset(rx->ctx, ms0);
+    uint32_t sent = n_ms < chunk_ms ? n_ms : chunk_ms;
+    if (rc == GPSB_OK) rc = gpsb_stream_push(rx->ctx, ms0, sent, packed);
+    if (rc != GPSB_OK) return hx_note(rc);
+    rc = gpsb_track_loop_begin(rx->ctx, n_ch, rx->ch, (uint32_t)sizeof(gps_ch_t), rx->aux, (uint32_t)sizeof(gpsb_aux), ms0, n_ms,
+                               iq_log, nav_log, rx->loop_res, GPSB_LOOP_STREAMING);
+    if (rc != GPSB_OK) { gpsb_stream_wait(rx->ctx); return hx_note(rc); }
+    int rc_push = GPSB_OK;
+    while (sent < n_ms && rc_push == GPSB_OK) {
+        const uint32_t n = n_ms - sent < chunk_ms ? n_ms - sent : chunk_ms;
+        rc_push = gpsb_stream_push(rx->ctx, ms0 + sent, n, packed + (size_t)sent * GPSB_MS_BYTES);
+        sent += n;
+    }
+    rc = gpsb_track_loop_end(rx->ctx);        /* a failed push starves the loop, which then ends by its time-out */
+    int rc_wait = gpsb_stream_wait(rx->ctx);
+    if (rc_push != GPSB_OK) return hx_note(rc_push);
+    if (rc != GPSB_OK) return hx_note(rc);
+    if (rc_wait != GPSB_OK) return hx_note(rc_wait);
+    rc = finish_device_run(rx, ms0, n_ms, iq_log, nav_log);   /* the ring now holds the whole run */
+    if (rc != GPSB_OK) return rc;
     gpsb_host_set_packet_cnt(ms0 + n_ms - 1);
     return GPSB_OK;
 }

@@ -113,6 +113,7 @@ def load_host_library(path: Path | None = None) -> C.CDLL:
         "gps_generate_prn": (None, [vp, i32]),
         "gpsb_rx_create": (i32, [C.POINTER(vp), vp, vp, u32]), "gpsb_rx_destroy": (None, [vp]),
         "gpsb_rx_track_ms": (i32, [vp, u32]), "gpsb_rx_track_run": (i32, [vp, u32, u32, vp, vp]),
+        "gpsb_rx_track_stream": (i32, [vp, u32, u32, vp, u32, vp, vp]),
         "gpsb_rx_acquire_ms": (i32, [vp, u32]),
         "gpsb_rx_set_threads": (None, [vp, u32]),
         "gpsb_rx_set_loop_site": (None, [vp, i32]),
@@ -194,6 +195,18 @@ class Receiver:
         nav = np.zeros((n_ms, n), np.int8) if log else None
         self._check(self.lib.gpsb_rx_track_run(self._rx, ms0, n_ms, iq.ctypes.data if log else None,
                                                nav.ctypes.data if log else None))
+        return iq, nav
+
+    def track_stream(self, ms0: int, packed: np.ndarray, chunk_ms: int = 0, log: bool = True):
+        """gpsb_rx_track_stream: the samples (n_ms x 2046 bytes, host memory) are streamed into the HBM ring while
+        the device-resident loop is already tracking."""
+        packed = np.ascontiguousarray(packed, dtype=np.uint8)
+        n_ms = packed.size // 2046
+        n = self.channels.n
+        iq = np.zeros((n_ms, n, 6), np.int16) if log else None
+        nav = np.zeros((n_ms, n), np.int8) if log else None
+        self._check(self.lib.gpsb_rx_track_stream(self._rx, ms0, n_ms, packed.ctypes.data, chunk_ms,
+                                                  iq.ctypes.data if log else None, nav.ctypes.data if log else None))
         return iq, nav
 
     def set_threads(self, n: int) -> None:

@@ -143,3 +143,91 @@ def test_device_loop_refuses_what_it_cannot_do(host_engine, golden):
     done, stop = np.frombuffer(bytes(res), np.uint32, 2)
     assert (int(done), int(stop)) == (0, 1) and bytes(ch.snapshot(0)) == before
     ch.free()
+
+
+def _two_locked_channels(golden):
+    ch = Channels([5, 14])
+    for i in range(2):
+        _locked(ch, i, int(golden["track_found_freq"][i]), float(golden["track_found_freq"][i]),
+                float(golden["track_found_phase"][i]) * 8.0)
+    return ch
+
+
+def test_streaming_run_equals_resident_run(host_engine, golden):
+    """gpsb_rx_track_stream: the samples start in host memory and are DMA-ed into the ring in chunks WHILE the loop
+    launch is already tracking (watermark in device memory).  Sums, nav bits and final records equal the run on a
+    ring uploaded beforehand - for chunk sizes from one millisecond to the whole recording, and across a ring wrap."""
+    sig = np.ascontiguousarray(golden["scene_signal"][:600])
+    ms0 = host_engine.ring_ms * 3 - 77
+    host_engine.upload_signal(ms0, sig)
+    ch = _two_locked_channels(golden)
+    rx = Receiver(host_engine, ch)
+    want_iq, want_nav = rx.track_run(ms0, 600)
+    want_rec = [bytes(ch.snapshot(i)) for i in range(2)]
+    rx.close()
+    ch.free()
+    for chunk in (1, 7, 128, 0, 600, 5000):
+        host_engine.upload_signal(ms0, np.zeros_like(sig))          # nothing of the recording is left in the ring
+        ch = _two_locked_channels(golden)
+        rx = Receiver(host_engine, ch)
+        launches0 = host_engine.launch_count
+        iq, nav = rx.track_stream(ms0, sig, chunk_ms=chunk)
+        assert host_engine.launch_count - launches0 == 1, chunk      # still one launch for the whole run
+        assert rx.loop_stats() == (2 * 600, 0), chunk
+        assert np.array_equal(iq, want_iq) and np.array_equal(nav, want_nav), chunk
+        assert [bytes(ch.snapshot(i)) for i in range(2)] == want_rec, chunk
+        assert host_engine.stream_progress(2) >= ms0 + 512
+        rx.close()
+        ch.free()
+
+
+def test_streaming_run_starved_producer_ends_cleanly(host_engine, golden):
+    """Raw C ABI: a loop started in streaming mode whose producer stops after 100 ms neither hangs nor touches
+    frames that never arrived: it ends by its time-out with stop == 3 and the milliseconds it reports as done are
+    bit-identical to the same milliseconds of a resident run; the rest can be run afterwards."""
+    lib = host_engine.lib
+    sig = np.ascontiguousarray(golden["scene_signal"][:300])
+    host_engine.upload_signal(0, sig)
+    ch = _two_locked_channels(golden)
+    rx = Receiver(host_engine, ch)
+    want_iq, _ = rx.track_run(0, 300)
+    want_rec = [bytes(ch.snapshot(i)) for i in range(2)]
+    rx.close()
+    ch.free()
+
+    host_engine.upload_signal(0, np.zeros_like(sig))
+    ch = _two_locked_channels(golden)
+    ch_b, aux_b = host_engine.record_bytes()
+    aux = np.zeros(2 * aux_b, np.uint8)
+    rx = Receiver(host_engine, ch)                       # loads the codes
+    res = np.zeros((2, 6), np.uint32)
+    iq = np.zeros((300, 2, 6), np.int16)
+    host_engine.stream_set_timeout_ms(50)
+    host_engine.stream_reset(0)
+    host_engine.stream_push(0, sig[:100])
+    assert lib.gpsb_track_loop_begin(host_engine.handle, 2, ch.at(0), ch_b, aux.ctypes.data, aux_b, 0, 300,
+                                     iq.ctypes.data, None, res.ctypes.data, 1) == 0
+    assert lib.gpsb_track_loop_end(host_engine.handle) == 0
+    host_engine.stream_wait()
+    host_engine.stream_set_timeout_ms(2000)
+    for i in range(2):
+        done, stop = int(res[i, 0]), int(res[i, 1])
+        assert stop == 3 and 90 <= done <= 100, (done, stop)
+        assert np.array_equal(iq[:done, i, :], want_iq[:done, i, :])
+    # the rest of the recording, resident: the records end where the uninterrupted run ended
+    host_engine.upload_signal(0, sig)
+    res2 = np.zeros((1, 6), np.uint32)
+    for i in range(2):
+        done = int(res[i, 0])
+        a = aux.reshape(2, aux_b)[i]
+        assert lib.gpsb_track_loop(host_engine.handle, 1, ch.at(i), ch_b, a.ctypes.data, aux_b, done, 300 - done, None,
+                                   None, res2.ctypes.data) == 0
+        assert (int(res2[0, 0]), int(res2[0, 1])) == (300 - done, 0)
+    got = [bytes(ch.snapshot(i)) for i in range(2)]
+    # snr_value is finished on the host by the receiver layer (log10f); compare everything else via the flat state
+    for i in range(2):
+        a, b = FlatState.from_buffer_copy(got[i]), FlatState.from_buffer_copy(want_rec[i])
+        a.snr_value_bits = b.snr_value_bits = 0
+        assert bytes(a) == bytes(b), i
+    rx.close()
+    ch.free()
