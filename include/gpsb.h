@@ -55,6 +55,8 @@ const char* gpsb_last_error(void);
 uint32_t gpsb_abi_version(void);
 /* Number of kernel launches issued by this context so far (bench.py's gpu_launches). */
 uint64_t gpsb_launch_count(const gpsb_ctx* ctx);
+/* Capacity of the context's signal ring in milliseconds (the ring_ms given to gpsb_create). */
+uint32_t gpsb_ring_ms(const gpsb_ctx* ctx);
 /* Run all subsequent work of this context on an externally owned CUDA stream (cudaStream_t passed
  * as void*, e.g. torch.cuda.current_stream().cuda_stream).  NULL restores the context's own stream. */
 int gpsb_set_stream(gpsb_ctx* ctx, void* cuda_stream);
@@ -180,8 +182,10 @@ int gpsb_track_loop_dev_ex(gpsb_ctx* ctx, uint32_t n_ch, void* d_channels, void*
  *   gpsb_stream_reset(ctx, ms)      frames below ms are declared present (synchronous); call before a run
  *   gpsb_stream_push(ctx, ms0, n, p) enqueue n milliseconds (n * 2046 bytes at p, which must stay valid - ideally
  *                                    pinned - until gpsb_stream_wait) and then the watermark ms0 + n; pushes must be
- *                                    issued in ascending order and must not lap the consumer by more than the ring
- *                                    (gpsb_stream_progress tells how far every channel of the running loop has got)
+ *                                    issued in ascending order and must not lap the consumer: chunk [a, a+n) replaces
+ *                                    frames a-ring_ms .., so push it only once gpsb_stream_progress() >= a+n-ring_ms
+ *                                    (the millisecond every channel of the running loop has completed, updated every
+ *                                    64 ms; a channel that leaves the loop reports the end of the run)
  *   gpsb_stream_wait(ctx)           all pushes so far have landed
  *   gpsb_track_loop_begin/_end      the two halves of gpsb_track_loop: _begin uploads the records and launches the loop
  *                                    without waiting, _end waits and copies records and logs back.  Between the two
@@ -193,6 +197,9 @@ int gpsb_stream_push(gpsb_ctx* ctx, uint32_t ms0, uint32_t n_ms, const uint8_t* 
 int gpsb_stream_wait(gpsb_ctx* ctx);
 uint32_t gpsb_stream_progress(const gpsb_ctx* ctx, uint32_t n_ch);
 int gpsb_stream_set_timeout_ms(gpsb_ctx* ctx, uint32_t ms);
+/* 1 while the loop started by gpsb_track_loop_begin is still executing (a producer waiting for ring space checks
+ * this so that it never waits for a consumer that has already left). */
+int gpsb_stream_loop_running(gpsb_ctx* ctx);
 int gpsb_track_loop_begin(gpsb_ctx* ctx, uint32_t n_ch, void* channels, uint32_t channel_bytes, void* aux,
                           uint32_t aux_bytes, uint32_t ms0, uint32_t n_ms, int16_t* iq_log, int8_t* nav_log,
                           gpsb_loop_result* results, uint32_t flags);

@@ -649,6 +649,7 @@ extern "C" {
 uint32_t gpsb_abi_version(void) { return 1u; }
 const char* gpsb_last_error(void) { return g_err; }
 uint64_t gpsb_launch_count(const gpsb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+uint32_t gpsb_ring_ms(const gpsb_ctx* ctx) { return ctx ? ctx->ring_ms : 0; }
 
 int gpsb_create(gpsb_ctx** out, int device, uint32_t max_sv, uint32_t ring_ms)
 {
@@ -988,7 +989,11 @@ static int track_loop_launch(gpsb_ctx* c, uint32_t n_ch, void* d_channels, void*
 {
     if (!c || !d_channels || !d_aux || !d_results) return fail(GPSB_ERR_ARG, "gpsb_track_loop_dev: null argument");
     if (n_ch == 0) return GPSB_OK;
-    if (n_ms > c->ring_ms) return fail(GPSB_ERR_ARG, "run of %u ms exceeds the signal ring (%u ms)", n_ms, c->ring_ms);
+    // a resident run reads frames that are all in the ring already; a streaming run may be longer than the ring (the
+    // producer refills it behind the consumer, gpsb_stream_progress)
+    if (!(flags & GPSB_LOOP_STREAMING) && n_ms > c->ring_ms)
+        return fail(GPSB_ERR_ARG, "run of %u ms exceeds the signal ring (%u ms)", n_ms, c->ring_ms);
+    if ((flags & GPSB_LOOP_STREAMING) && c->ring_ms < 8) return fail(GPSB_ERR_ARG, "a streaming run needs a ring of at least 8 ms");
     if ((flags & GPSB_LOOP_STREAMING) && n_ch > 256) return fail(GPSB_ERR_ARG, "a streaming run carries at most 256 channels");
     CU(cudaSetDevice(c->device));
     StreamGate gate = {nullptr, nullptr, 0ull};
@@ -1108,6 +1113,12 @@ uint32_t gpsb_stream_progress(const gpsb_ctx* c, uint32_t n_ch)
         if ((int32_t)(v - lo) < 0) lo = v;
     }
     return lo;
+}
+
+int gpsb_stream_loop_running(gpsb_ctx* c)
+{
+    if (!c || !c->loop_open) return 0;
+    return cudaStreamQuery(c->stream) == cudaErrorNotReady ? 1 : 0;
 }
 
 int gpsb_stream_set_timeout_ms(gpsb_ctx* c, uint32_t ms)

@@ -424,6 +424,7 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
             if (kStream && gate.progress && (m & 63u) == 63u) *(volatile uint32_t*)(gate.progress + chn) = ms + 1;
         }
     }
+    if (kStream && code_thr && gate.progress) *(volatile uint32_t*)(gate.progress + chn) = ms0 + n_ms;   // needs no more frames
     if (code_thr)      // early exit: bulk copies nobody waited for may still be in flight - let them land before the CTA retires
         for (uint32_t f = consumed; f < issued; f++) mbar_wait(&sm.full[f & 1u], (f >> 1) & 1u);
     if (code_thr) {                                         // owned fields back into the shared record

@@ -64,6 +64,7 @@ def load_library(path: Path | None = None) -> C.CDLL:
         "gpsb_last_error": (C.c_char_p, []),
         "gpsb_abi_version": (u32, []),
         "gpsb_launch_count": (u64, [vp]),
+        "gpsb_ring_ms": (u32, [vp]),
         "gpsb_set_stream": (i32, [vp, vp]),
         "gpsb_synchronize": (i32, [vp]),
         "gpsb_timer_start": (i32, [vp, u32]),
@@ -100,6 +101,7 @@ def load_library(path: Path | None = None) -> C.CDLL:
         "gpsb_stream_wait": (i32, [vp]),
         "gpsb_stream_progress": (u32, [vp, u32]),
         "gpsb_stream_set_timeout_ms": (i32, [vp, u32]),
+        "gpsb_stream_loop_running": (i32, [vp]),
         "gpsb_track_loop_record_bytes": (None, [C.POINTER(u32), C.POINTER(u32)]),
         "gpsb_l0_loop_math": (i32, [vp, i32, C.c_int32, u32, vp]),
         "gpsb_l0_generate_prn_data2": (i32, [vp, vp, vp, u16]),

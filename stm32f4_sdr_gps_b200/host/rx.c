@@ -8,6 +8,7 @@
  * tracking.c:33-34, nav_data.c:29,48-51, only works one channel at a time).
  */
 #include <pthread.h>
+#include <sched.h>
 #include <stdlib.h>
 #include <unistd.h>
 
@@ -29,6 +30,7 @@ struct gpsb_rx {
     uint32_t threads;            /* 0 = automatic */
     int loop_site;               /* GPSB_LOOP_AUTO / _HOST / _DEVICE */
     gpsb_loop_result* loop_res;
+    uint32_t ring_ms;            /* capacity of the context's signal ring */
     uint64_t device_ms, host_ms; /* channel-milliseconds run by k_track_run / by the per-millisecond host path */
 };
 
@@ -46,6 +48,7 @@ int gpsb_rx_create(gpsb_rx** out, gpsb_ctx* ctx, gps_ch_t* channels, uint32_t n_
     gpsb_rx* rx = (gpsb_rx*)calloc(1, sizeof *rx);
     if (!rx) return GPSB_ERR_NOMEM;
     rx->ctx = ctx;
+    rx->ring_ms = gpsb_ring_ms(ctx);
     rx->ch = channels;
     rx->n_ch = n_ch;
     rx->aux = (gpsb_aux*)calloc(n_ch, sizeof(gpsb_aux));
@@ -358,12 +361,22 @@ int gpsb_rx_track_stream(gpsb_rx* rx, uint32_t ms0, uint32_t n_ms, const uint8_t
     if (n_ms == 0) return GPSB_OK;
     if (chunk_ms == 0) chunk_ms = 64;
     const uint32_t n_ch = rx->n_ch;
+    const uint32_t ring_ms = rx->ring_ms;
+    if (chunk_ms > ring_ms / 2) chunk_ms = ring_ms / 2 ? ring_ms / 2 : 1;   /* the producer must be able to run ahead */
     uint32_t n_trk = 0;
     for (uint32_t i = 0; i < n_ch; i++) n_trk += is_tracking(&rx->ch[i]) ? 1u : 0u;
-    if (n_trk != n_ch || n_ch > 256 || rx->loop_site == GPSB_LOOP_HOST || gpsb_session_slots(rx->ctx) != 0) {
-        int rc = gpsb_upload_signal(rx->ctx, ms0, n_ms, packed);
-        if (rc != GPSB_OK) return hx_note(rc);
-        return gpsb_rx_track_run(rx, ms0, n_ms, iq_log, nav_log);
+    if (n_trk != n_ch || n_ch > 256 || rx->loop_site == GPSB_LOOP_HOST || gpsb_session_slots(rx->ctx) != 0 ||
+        (n_ms > ring_ms && ring_ms < 192)) {        /* progress is reported every 64 ms: a smaller ring cannot be refilled behind the loop */
+        for (uint32_t at = 0; at < n_ms;) {         /* upload a ring-full, run it, repeat */
+            const uint32_t n = n_ms - at < ring_ms ? n_ms - at : ring_ms;
+            int rc = gpsb_upload_signal(rx->ctx, ms0 + at, n, packed + (size_t)at * GPSB_MS_BYTES);
+            if (rc != GPSB_OK) return hx_note(rc);
+            rc = gpsb_rx_track_run(rx, ms0 + at, n, iq_log ? iq_log + (size_t)at * n_ch * 6 : NULL,
+                                   nav_log ? nav_log + (size_t)at * n_ch : NULL);
+            if (rc != GPSB_OK) return rc;
+            at += n;
+        }
+        return GPSB_OK;
     }
     int rc = gpsb_stream_reset(rx->ctx, ms0);
     uint32_t sent = n_ms < chunk_ms ? n_ms : chunk_ms;
@@ -375,6 +388,10 @@ int gpsb_rx_track_stream(gpsb_rx* rx, uint32_t ms0, uint32_t n_ms, const uint8_t
     int rc_push = GPSB_OK;
     while (sent < n_ms && rc_push == GPSB_OK) {
         const uint32_t n = n_ms - sent < chunk_ms ? n_ms - sent : chunk_ms;
+        /* a run longer than the ring: chunk [sent, sent+n) replaces frames sent-ring .. - wait until every channel is past them */
+        while (sent + n > ring_ms && (int32_t)(gpsb_stream_progress(rx->ctx, n_ch) - (ms0 + sent + n - ring_ms)) < 0 &&
+               gpsb_stream_loop_running(rx->ctx))
+            sched_yield();
         rc_push = gpsb_stream_push(rx->ctx, ms0 + sent, n, packed + (size_t)sent * GPSB_MS_BYTES);
         sent += n;
     }
@@ -383,8 +400,40 @@ int gpsb_rx_track_stream(gpsb_rx* rx, uint32_t ms0, uint32_t n_ms, const uint8_t
     if (rc_push != GPSB_OK) return hx_note(rc_push);
     if (rc != GPSB_OK) return hx_note(rc);
     if (rc_wait != GPSB_OK) return hx_note(rc_wait);
-    rc = finish_device_run(rx, ms0, n_ms, iq_log, nav_log);   /* the ring now holds the whole run */
-    if (rc != GPSB_OK) return rc;
+    if (n_ms <= ring_ms) {
+        rc = finish_device_run(rx, ms0, n_ms, iq_log, nav_log);   /* the ring now holds the whole run */
+        if (rc != GPSB_OK) return rc;
+    } else {
+        /* The ring holds only the tail of the run.  A channel the loop handed back early (degenerate DLL millisecond,
+         * starved producer) is finished from the host copy, one ring-full at a time. */
+        for (uint32_t i = 0; i < n_ch; i++) {
+            rx->device_ms += rx->loop_res[i].done_ms;
+            lc_resolve_snr(&rx->ch[i], &rx->aux[i]);
+        }
+        for (uint32_t i = 0; i < n_ch; i++) {
+            gpsb_loop_result* r = &rx->loop_res[i];
+            if (r->done_ms >= n_ms) continue;
+            uint32_t at = r->done_ms;                              /* first millisecond still to do for this channel */
+            while (at < n_ms) {
+                const uint32_t n = n_ms - at < ring_ms ? n_ms - at : ring_ms;
+                rc = gpsb_upload_signal(rx->ctx, ms0 + at, n, packed + (size_t)at * GPSB_MS_BYTES);
+                if (rc != GPSB_OK) return hx_note(rc);
+                if (at == r->done_ms && r->stop == LC_STOP_DLL_NAN) {
+                    gpsb_host_set_packet_cnt(ms0 + at);
+                    rx->aux[i].last_nav_bit = -1;
+                    hx_trk_finish_epl(&rx->ch[i], &rx->aux[i], (uint8_t)((ms0 + at) % GPSB_SLOT_LEN), r->iq);
+                    if (nav_log) nav_log[(size_t)at * n_ch + i] = rx->aux[i].last_nav_bit;
+                    rx->host_ms++;
+                    if (n == 1) { at++; continue; }
+                    rc = run_channel_span(rx, i, ms0, ms0 + at + 1, ms0 + at + n, iq_log, nav_log);
+                } else {
+                    rc = run_channel_span(rx, i, ms0, ms0 + at, ms0 + at + n, iq_log, nav_log);
+                }
+                if (rc != GPSB_OK) return rc;
+                at += n;
+            }
+        }
+    }
     gpsb_host_set_packet_cnt(ms0 + n_ms - 1);
     return GPSB_OK;
 }

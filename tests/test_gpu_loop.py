@@ -231,3 +231,31 @@ def test_streaming_run_starved_producer_ends_cleanly(host_engine, golden):
         assert bytes(a) == bytes(b), i
     rx.close()
     ch.free()
+
+
+@pytest.mark.parametrize("ring_ms,chunk", [(256, 32), (192, 0), (64, 16)])
+def test_streaming_run_longer_than_the_ring(host_engine, golden, ring_ms, chunk):
+    """A 600-ms run through a ring of 256 / 192 ms: the producer refills the ring behind the loop (flow control on
+    the progress words), still one launch; a 64-ms ring cannot be refilled behind a loop that reports progress every
+    64 ms and is served ring-full by ring-full.  Same sums, nav bits and records as the resident run."""
+    from stm32f4_sdr_gps_b200 import Engine
+    sig = np.ascontiguousarray(golden["scene_signal"][:600])
+    host_engine.upload_signal(0, sig)
+    ch = _two_locked_channels(golden)
+    rx = Receiver(host_engine, ch)
+    want_iq, want_nav = rx.track_run(0, 600)
+    want_rec = [bytes(ch.snapshot(i)) for i in range(2)]
+    rx.close()
+    ch.free()
+    with Engine(device=0, max_sv=211, ring_ms=ring_ms) as eng:
+        ch = _two_locked_channels(golden)
+        rx = Receiver(eng, ch)
+        launches0 = eng.launch_count
+        iq, nav = rx.track_stream(0, sig, chunk_ms=chunk)
+        if ring_ms >= 192:
+            assert eng.launch_count - launches0 == 1
+        assert np.array_equal(iq, want_iq) and np.array_equal(nav, want_nav)
+        assert [bytes(ch.snapshot(i)) for i in range(2)] == want_rec
+        assert rx.loop_stats() == (2 * 600, 0)
+        rx.close()
+        ch.free()
