@@ -229,6 +229,31 @@ def reference_sweep_rate(acq_sig, n_sv: int = 2, n_ms: int = 2):
     return n_sv * ACQ_BINS * n_ms / best, n_sv * ACQ_BINS * n_ms
 
 
+def reference_prompt_rate(sig, n_ms: int = 8000):
+    """Reference C (oracle/_ref), config 1 repeated over a recording: replica + stateless mixer + one
+    gps_correlation_iq per millisecond on one core.  Returns (ms per second, I/Q of the sample) or (None, None)."""
+    import ctypes as C
+    sys.path.insert(0, str(REPO / "tests"))
+    from oracle_lib import Reference, have_reference
+    if not have_reference():
+        return None, None
+    ref = Reference()
+    lib = ref.lib
+    if not hasattr(lib, "ref_prompt_time"):
+        return None, None
+    lib.ref_prompt_time.restype = C.c_double
+    lib.ref_prompt_time.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_float, C.c_uint32, C.c_uint32, C.c_void_p]
+    chans = ref.channels(1)
+    ch = ref.channel_at(chans, 0)
+    ref.channel_init(ch, 1, 0)
+    n_ms = min(n_ms, sig.shape[0])
+    data = np.ascontiguousarray(sig[:n_ms])
+    out = np.zeros((n_ms, 2), np.int16)
+    best = min(lib.ref_prompt_time(ch, data.ctypes.data, n_ms, float(np.float32(IF_HZ + 2000)), 100, 0, out.ctypes.data)
+               for _ in range(3))
+    return n_ms / best, out
+
+
 def run_reference_arm(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -366,7 +391,7 @@ def run_gpu_arm(args) -> None:
     rx.set_loop_site(0)
     for _ in range(warm):
         arm_locked(channels, scene)
-        rx.track_run(0, N_MS, log=True)
+        rx.track_stream(0, pinned_sig.numpy(), log=True)
     barrier()
     ev = events(steps)
     wall_e2e = 0.0
@@ -376,8 +401,9 @@ def run_gpu_arm(args) -> None:
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         ev[k][0].record(stream)
-        eng.upload_signal(0, pinned_sig.numpy())          # host buffer -> HBM ring, inside the timed region
-        iq_log, nav_log = rx.track_run(0, N_MS, log=True)   # records in/out, per-ms sums and nav bits land in host arrays
+        # host buffer -> HBM ring in chunks WHILE the loop launch is tracking; records in/out, per-ms sums and nav bits
+        # land in host arrays; all inside the timed region
+        iq_log, nav_log = rx.track_stream(0, pinned_sig.numpy(), log=True)
         ev[k][1].record(stream)
         torch.cuda.synchronize()
         wall_e2e += time.perf_counter() - t0
@@ -403,6 +429,51 @@ def run_gpu_arm(args) -> None:
     host_loop_ms = min(host_loop) * 1e3
     rx.set_loop_site(0)
 
+    # upload-then-run (the non-overlapped form of the same call sequence), for comparison
+    t_seq = []
+    for k in range(5):
+        arm_locked(channels, scene)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        eng.upload_signal(0, pinned_sig.numpy())
+        rx.track_run(0, N_MS, log=True)
+        t_seq.append(time.perf_counter() - t0)
+    upload_then_run_ms = min(t_seq) * 1e3
+
+    # ---- config 5 shape on one GPU: 32 channels tracked continuously from a host-resident stream through a ring
+    # SHORTER than the run (256 ms), i.e. with the producer refilling the ring behind the loop.  The recording holds
+    # this rank's four satellites; eight channels follow each of them from slightly different starting points - the
+    # kernel's work per channel-millisecond does not depend on what is in the signal.
+    n_many = 32
+    many = Channels([scene.sats[i % n_ch].prn for i in range(n_many)])
+
+    def arm_many():
+        for i in range(n_many):
+            sat = scene.sats[i % n_ch]
+            st = many.snapshot(i)
+            st.acq_state, st.trk_state = 9, 4
+            st.found_freq_offset_hz = int(round(sat.doppler_hz / 500.0) * 500)
+            st.if_freq_offset_hz_bits = int(np.float32(sat.doppler_hz + 3.0 * (i // n_ch)).view(np.uint32))
+            st.code_phase_fine_bits = int(np.float32(sat.code_phase_samples).view(np.uint32))
+            many.restore(i, st)
+
+    many_blank = [many.snapshot(i) for i in range(n_many)]
+    stream_eng = Engine(device=local_rank, max_sv=211, ring_ms=256)
+    many_rx = Receiver(stream_eng, many)
+    t_many = []
+    for k in range(4):
+        for i in range(n_many):
+            many.restore(i, many_blank[i])
+        arm_many()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        many_rx.track_stream(0, pinned_sig.numpy(), log=True)
+        t_many.append(time.perf_counter() - t0)
+    many_ms = min(t_many) * 1e3
+    many_dev, many_host = many_rx.loop_stats()
+    many_rx.close()
+    stream_eng.close()
+
     # ---- open-loop batch replay of the same 4000 cells in ONE launch (kernel-level throughput)
     from stm32f4_sdr_gps_b200 import EPL_REQ  # noqa: F401
     rq_all, _, _ = truth_requests(scene, nco_step32)
@@ -420,6 +491,42 @@ def run_gpu_arm(args) -> None:
         ev[k][1].record(stream)
     barrier()
     batch_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+
+    # ---- config 1 batched: PRN 1, Doppler +2000 Hz, byte offset 100, one cell per millisecond of a LONG recording
+    # (every cell has its own 2046-byte frame, so the working set - 400 000 ms = 818 MB - exceeds L2 and the kernel is
+    # fed from HBM): k_epl_batch, prompt arm only (gps_correlation_iq) and all three arms
+    n_long = int(os.environ.get("GPSB_BENCH_LONG_MS", "400000"))
+    long_eng = Engine(device=local_rank, max_sv=4, ring_ms=n_long)
+    long_eng.set_stream(stream.cuda_stream)
+    long_eng.set_code_prn(1, 1)
+    rng_long = np.random.default_rng(0x5D120001 + 17 * rank)
+    long_sig = rng_long.integers(0, 256, (n_long, 2046), dtype=np.uint8)
+    long_eng.upload_signal(0, long_sig)
+    step_2k = nco_step32(np.float32(IF_HZ + 2000))
+    rq_long = np.zeros(n_long, EPL_REQ)
+    rq_long["sv_slot"], rq_long["ms_index"] = 1, np.arange(n_long)
+    rq_long["step32"] = step_2k                      # stateless mixer: phase 0 at the start of every millisecond
+    rq_long["off_e"], rq_long["off_p"], rq_long["off_l"] = 99, 100, 101
+    d_rq_long = torch.from_numpy(rq_long.view(np.uint8).copy()).to(dev)
+    d_out_long = torch.zeros(n_long * 6, dtype=torch.int16, device=dev)
+    long_ms = {}
+    for arms, fn in ((1, long_eng.prompt_iq_dev), (3, long_eng.track_epl_dev)):
+        for _ in range(warm):
+            fn(n_long, d_rq_long.data_ptr(), d_out_long.data_ptr())
+        barrier()
+        ev = events(steps)
+        for k in range(steps):
+            flush.fill_(k)
+            ev[k][0].record(stream)
+            fn(n_long, d_rq_long.data_ptr(), d_out_long.data_ptr())
+            ev[k][1].record(stream)
+        barrier()
+        long_ms[arms] = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+        if arms == 1:
+            long_prompt = d_out_long.cpu().numpy()[:2 * n_long].reshape(n_long, 2).copy()
+    long_epl = d_out_long.cpu().numpy().reshape(n_long, 6)
+    assert np.array_equal(long_epl[:, 2:4], long_prompt), "prompt-only and E/P/L forms of k_epl_batch disagree"
+    long_eng.close()
 
     # ---- cold acquisition (secondary metric, satellites sharded over ranks)
     from stm32f4_sdr_gps_b200.signal_synth import config3_scene
@@ -468,8 +575,8 @@ def run_gpu_arm(args) -> None:
     clk = clocks.stop()
 
     # ---- max over ranks
-    times = torch.tensor([t_dev, t_e2e, acq_ms["dp4a"], acq_ms["direct"], acq_e2e_ms, batch_ms], dtype=torch.float64,
-                         device=dev)
+    times = torch.tensor([t_dev, t_e2e, acq_ms["dp4a"], acq_ms["direct"], acq_e2e_ms, batch_ms, many_ms, long_ms[1], long_ms[3]],
+                         dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     # the one exchange of the path: all-gather of the sweep triples so every rank holds the full grid
@@ -478,7 +585,7 @@ def run_gpu_arm(args) -> None:
     grid = sharding.gather_sweep(sharding.pack_local(local, ACQ_SV, rank, world), ACQ_SV, world, device=dev)
     gather_ms = (time.perf_counter() - t0) * 1e3
     assert grid.shape == (ACQ_SV, ACQ_BINS, ACQ_MS, 4) and np.array_equal(grid[my_sv - 1], local)
-    t_dev, t_e2e, acq_dp4a_ms, acq_direct_ms, acq_e2e_ms, batch_ms = [float(x) for x in times.cpu()]
+    t_dev, t_e2e, acq_dp4a_ms, acq_direct_ms, acq_e2e_ms, batch_ms, many_ms, long1_ms, long3_ms = [float(x) for x in times.cpu()]
 
     if rank == 0:
         peaks = {}
@@ -504,6 +611,9 @@ def run_gpu_arm(args) -> None:
         idp_peak = 148 * 64 * sm_clk                       # IDP.4A: 64 lanes/clk/SM measured (tools/ubench_int.cu)
         cpu_t, cpu_cores, cpu_kind = reference_tracking_seconds(scene, sig, os.cpu_count() or 1, reps=3)
         acq_cpu_rate, acq_cpu_cells = reference_sweep_rate(acq_sig)
+        prompt_cpu_rate, prompt_cpu_iq = reference_prompt_rate(long_sig)
+        if prompt_cpu_iq is not None:      # the reference's own I/Q for the head of the long recording
+            assert np.array_equal(prompt_cpu_iq, long_prompt[:prompt_cpu_iq.shape[0]]), "config 1: GPU and reference C disagree"
         cpu = None
         if cpu_t:
             cpu = {"value": N_SV_PER_GPU * ARMS * MS_SAMPLES * N_MS / cpu_t, "unit": "arm-samples/s", "cores": cpu_cores,
@@ -523,7 +633,8 @@ def run_gpu_arm(args) -> None:
                     "h2d_bytes_per_step": int(sig.nbytes + n_ch * (ch_bytes + aux_bytes)),
                     "d2h_bytes_per_step": int(n_ch * (ch_bytes + aux_bytes + 24) + n_cells * 13),
                     "ms_per_step": t_e2e * 1e3 / steps,
-                    "api": "gpsb_upload_signal + gpsb_rx_track_run (libgpsb_host.so), host buffers in and out"},
+                    "api": "gpsb_rx_track_stream (libgpsb_host.so): host buffers in and out, signal DMA-ed into the HBM ring in 64-ms "
+                           "chunks while the loop launch is tracking"},
             "gpu_launches": int(launches),
             "clocks": clk,
             "roofline": {"kernel": "k_track_run (1 launch per step, %d CTAs: one per satellite)" % n_ch, "bound": "hbm",
@@ -536,17 +647,48 @@ def run_gpu_arm(args) -> None:
                                  "one SM per satellite, not by bandwidth; the same launch carries 1 to 148 satellites in "
                                  "the same time"},
             "cpu_baseline": cpu,
+            "streaming": {"what": "config 5 shape: %d channels per GPU tracked continuously from a HOST-resident stream through a "
+                                  "256-ms HBM ring (run = %d ms, producer refills the ring behind the loop; one launch)"
+                                  % (n_many, N_MS),
+                          "ms_per_s_of_signal": many_ms * 1e3 / N_MS, "times_real_time": N_MS / many_ms,
+                          "input_msps_sustained": MS_SAMPLES * N_MS / (many_ms * 1e-3) / 1e6,
+                          "arm_samples_per_s": world * n_many * ARMS * MS_SAMPLES * N_MS / (many_ms * 1e-3),
+                          "channel_ms_on_device": int(many_dev), "channel_ms_on_host_path": int(many_host),
+                          "target": "163.68 Msps (10x real time)"},
             "closed_loop": {"device_loop_kernel_ms": loop_kernel_ms, "host_loop_ms": host_loop_ms,
+                            "upload_then_run_ms": upload_then_run_ms,
                             "host_loop_what": "same second with the loop filters on the host: one GPU round trip per ms",
                             "launches_per_step_value": launches_value / steps,
                             "channel_ms_on_device": int(on_device), "channel_ms_on_host_path": int(on_host),
                             "final_code_phase": [float(x) for x in final_fine]},
-            "batch_replay": {"what": "the same %d cells replayed open loop in ONE k_epl launch (signal + requests resident)" % n_cells,
+            "batch_replay": {"what": "the same %d cells replayed open loop in ONE k_epl_batch launch (signal + requests resident)" % n_cells,
                              "value": N_SV_PER_GPU * ARMS * MS_SAMPLES * N_MS / (batch_ms * 1e-3), "unit": "arm-samples/s",
                              "kernel_ms": batch_ms,
                              "roofline": {"bound": "hbm", "achieved": batch_bytes / (batch_ms * 1e-3) / 1e9, "peak": hbm_peak,
                                           "unit": "GB/s", "frac": batch_bytes / (batch_ms * 1e-3) / 1e9 / hbm_peak,
                                           "algorithmic_bytes_per_launch": batch_bytes}},
+            "config1_batched": {
+                "what": "PRN 1, +2000 Hz, byte offset 100, bits 0: one prompt correlation per millisecond of a %d-ms recording "
+                        "(%.0f MB, larger than L2) in ONE k_epl_batch launch per rank; 'epl' = all three arms of the same cells"
+                        % (n_long, n_long * 2048 / 1e6),
+                "cells": n_long * world,
+                "prompt": {"kernel_ms": long1_ms, "cells_per_s": n_long * world / (long1_ms * 1e-3),
+                           "arm_samples_per_s": n_long * world * MS_SAMPLES / (long1_ms * 1e-3),
+                           "roofline": {"kernel": "k_epl_batch<1>", "bound": "hbm",
+                                        "achieved": n_long * (2046 + 24 + 4) / (long1_ms * 1e-3) / 1e9, "peak": hbm_peak,
+                                        "unit": "GB/s", "frac": n_long * (2046 + 24 + 4) / (long1_ms * 1e-3) / 1e9 / hbm_peak,
+                                        "algorithmic_bytes_per_launch": n_long * (2046 + 24 + 4)}},
+                "epl": {"kernel_ms": long3_ms, "cells_per_s": n_long * world / (long3_ms * 1e-3),
+                        "arm_samples_per_s": n_long * world * ARMS * MS_SAMPLES / (long3_ms * 1e-3),
+                        "roofline": {"kernel": "k_epl_batch<3>", "bound": "hbm",
+                                     "achieved": n_long * (2046 + 24 + 12) / (long3_ms * 1e-3) / 1e9, "peak": hbm_peak,
+                                     "unit": "GB/s", "frac": n_long * (2046 + 24 + 12) / (long3_ms * 1e-3) / 1e9 / hbm_peak,
+                                     "algorithmic_bytes_per_launch": n_long * (2046 + 24 + 12),
+                                     "popc_pipe_frac": n_long * 512 * 6 / (long3_ms * 1e-3) / (148 * 16 * sm_clk)}},
+                "cpu_baseline": None if not prompt_cpu_rate else {
+                    "value": prompt_cpu_rate, "unit": "cells/s (1 core)", "cores": 1, "kind": "reference",
+                    "sample": "first 8000 ms: gps_generate_prn_data2 + gps_shift_to_zero_freq + gps_correlation_iq per ms; "
+                              "I/Q identical to the GPU's"}},
             "cold_acq": {"metric": "full-sky 32-SV cold-acq ms", "value": acq_dp4a_ms, "unit": "ms",
                          "direct_xor_popc_ms": acq_direct_ms, "e2e_ms": acq_e2e_ms,
                          "cells": ACQ_SV * ACQ_BINS * ACQ_MS, "phases": 2046, "bit_macs": acq_bitmacs,

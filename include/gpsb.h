@@ -114,6 +114,15 @@ typedef struct gpsb_epl_req {
  * gpsb_set_realtime(ctx, 0) forces the staged-copy path used for larger batches. */
 int gpsb_track_epl(gpsb_ctx* ctx, uint32_t n, const gpsb_epl_req* req, int16_t* out);
 int gpsb_set_realtime(gpsb_ctx* ctx, int enabled);
+/* Batches of at least n_cells cells (default 512) are run by k_epl_batch - one warp per cell on a persistent grid,
+ * frames streamed from HBM straight into registers - instead of one CTA per cell; 0 = always, UINT32_MAX = never.
+ * Both kernels return identical sums. */
+int gpsb_set_epl_batch_min(gpsb_ctx* ctx, uint32_t n_cells);
+/* The prompt arm alone: out[2*i], out[2*i+1] = I, Q of request i at byte offset off_p (off_e / off_l ignored) =
+ * gps_generate_prn_data2(off_bits) + gps_shift_to_zero_freq_track(acc0, step32) + ONE gps_correlation_iq
+ * (PM/GPS/gps_misc.c:128-145): the reference's single-arm correlation, for long recordings replayed open loop
+ * (SURVEY.md section 8(d), config 1 batched). */
+int gpsb_prompt_iq(gpsb_ctx* ctx, uint32_t n, const gpsb_epl_req* req, int16_t* out);
 
 /* Tracking session: keeps one resident CTA per channel slot polling a command slot in mapped pinned
  * host memory, so that a gpsb_track_epl call of n <= n_slots cells costs one PCIe round trip instead
@@ -261,6 +270,7 @@ int gpsb_set_sweep_method(gpsb_ctx* ctx, int method);
  *      context stream without synchronising.  Used for kernel-only timing and for results that are
  *      gathered across GPUs (NCCL) before they are read. */
 int gpsb_track_epl_dev(gpsb_ctx* ctx, uint32_t n, const gpsb_epl_req* d_req, int16_t* d_out);
+int gpsb_prompt_iq_dev(gpsb_ctx* ctx, uint32_t n, const gpsb_epl_req* d_req, int16_t* d_out);
 int gpsb_search_dev(gpsb_ctx* ctx, uint32_t n, const gpsb_search_req* d_req, gpsb_search_res* d_res);
 int gpsb_sweep_dev(gpsb_ctx* ctx, const uint32_t* d_sv_slots, uint32_t n_sv, const uint32_t* d_step32,
                    uint32_t n_bins, uint32_t ms0, uint32_t n_ms, uint32_t off_bits,

@@ -426,3 +426,19 @@ double ref_sweep_time(gps_ch_t* chans, uint32_t n_sv, const uint8_t* signal, uin
     ref_sweep_cells(chans, n_sv, signal, n_ms, first_bin_hz, bin_step_hz, n_bins, offset_bits, out);
     return ref_now_s() - t0;
 }
+
+/* SURVEY.md section 8(d) config 1 repeated over a recording: per millisecond the reference's replica generator,
+ * stateless mixer and ONE gps_correlation_iq at a fixed offset (the recipe of project_single_sat/main.c:59-68 with
+ * the prompt correlation instead of the search).  out2[2*m], out2[2*m+1] = I, Q.  Returns seconds. */
+double ref_prompt_time(gps_ch_t* ch, const uint8_t* signal, uint32_t n_ms, float freq_hz, uint32_t offset,
+                       uint32_t offset_bits, int16_t* out2)
+{
+    double t0 = ref_now_s();
+    for (uint32_t m = 0; m < n_ms; m++) {
+        gps_generate_prn_data2(ch, tmp_prn_data, (uint16_t)offset_bits);
+        gps_shift_to_zero_freq((uint8_t*)(signal + 2046u * (size_t)m), (uint8_t*)tmp_data_i, (uint8_t*)tmp_data_q, freq_hz);
+        gps_correlation_iq(tmp_prn_data, tmp_data_i, tmp_data_q, (uint16_t)offset, &out2[2 * m], &out2[2 * m + 1]);
+    }
+    return ref_now_s() - t0;
+}
+

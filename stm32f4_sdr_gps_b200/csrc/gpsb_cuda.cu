@@ -33,6 +33,7 @@ struct SweepParams {
 }  // namespace gpsb
 
 #include "gpsb_acq_dp4a.cuh"
+#include "gpsb_epl_batch.cuh"
 #include "gpsb_track_loop.cuh"
 
 using namespace gpsb;
@@ -496,6 +497,9 @@ struct gpsb_ctx {
     cudaStream_t stream = nullptr;
     uint32_t* d_codes = nullptr;   // max_sv x 512 words
     uint32_t* d_schips = nullptr;  // max_sv x 256 words: +-1 chip bytes for the dp4a search
+    uint32_t* d_rxt = nullptr;     // max_sv x 16 x 4 x 1040 words: extended replica streams for k_epl_batch
+    uint32_t epl_batch_min = 512;  // gpsb_track_epl_dev batches of at least this many cells go to k_epl_batch
+    int n_sm = 148;
     int sweep_method = GPSB_SWEEP_DP4A;
     // closed-loop mailbox (mapped pinned host memory, see k_epl_rt / k_epl_session)
     RtCmd* h_cmd = nullptr;        // kRtMaxCells command slots, host view
@@ -679,6 +683,9 @@ int gpsb_create(gpsb_ctx** out, int device, uint32_t max_sv, uint32_t ring_ms)
     c->stream = c->own_stream;
     CU(cudaMalloc(&c->d_codes, (size_t)max_sv * kWords * 4));
     CU(cudaMemset(c->d_codes, 0, (size_t)max_sv * kWords * 4));
+    c->n_sm = prop.multiProcessorCount;
+    CU(cudaMalloc(&c->d_rxt, (size_t)max_sv * kRxtShifts * kRxtCopies * kRxtWords * 4));
+    CU(cudaMemset(c->d_rxt, 0, (size_t)max_sv * kRxtShifts * kRxtCopies * kRxtWords * 4));
     CU(cudaMalloc(&c->d_schips, (size_t)max_sv * kChipSteps * 4));
     CU(cudaMemset(c->d_schips, 0, (size_t)max_sv * kChipSteps * 4));
     CU(cudaFuncSetAttribute(k_acq_dp4a<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AcqSmem<8>)));
@@ -740,6 +747,7 @@ void gpsb_destroy(gpsb_ctx* c)
     if (c->d_stage) cudaFree(c->d_stage);
     if (c->d_codes) cudaFree(c->d_codes);
     if (c->d_schips) cudaFree(c->d_schips);
+    if (c->d_rxt) cudaFree(c->d_rxt);
     if (c->d_signal) cudaFree(c->d_signal);
     if (c->d_chips) cudaFree(c->d_chips);
     if (c->session_slots) gpsb_session_end(c);
@@ -802,6 +810,9 @@ int gpsb_set_code(gpsb_ctx* c, uint32_t slot, const uint8_t chips[GPSB_CHIPS])
                                             c->d_schips + (size_t)slot * kChipSteps);
     int rc = check_launch(c, "k_expand_code");
     if (rc) return rc;
+    k_build_rxt<<<32, 256, 0, c->stream>>>(c->d_codes + (size_t)slot * kWords, c->d_rxt + (size_t)slot * kRxtShifts * kRxtCopies * kRxtWords);
+    rc = check_launch(c, "k_build_rxt");
+    if (rc) return rc;
     CU(cudaStreamSynchronize(c->stream));
     c->code_set[slot] = 1;
     return GPSB_OK;
@@ -816,6 +827,9 @@ int gpsb_set_code_prn(gpsb_ctx* c, uint32_t slot, uint32_t prn)
     k_gen_code<<<1, 256, 0, c->stream>>>(prn, c->d_chips, c->d_codes + (size_t)slot * kWords,
                                          c->d_schips + (size_t)slot * kChipSteps);
     int rc = check_launch(c, "k_gen_code");
+    if (rc) return rc;
+    k_build_rxt<<<32, 256, 0, c->stream>>>(c->d_codes + (size_t)slot * kWords, c->d_rxt + (size_t)slot * kRxtShifts * kRxtCopies * kRxtWords);
+    rc = check_launch(c, "k_build_rxt");
     if (rc) return rc;
     CU(cudaStreamSynchronize(c->stream));
     c->code_set[slot] = 1;
@@ -930,8 +944,54 @@ int gpsb_track_epl_dev(gpsb_ctx* c, uint32_t n, const gpsb_epl_req* d_req, int16
     if (!c || !d_req || !d_out) return fail(GPSB_ERR_ARG, "gpsb_track_epl_dev: null argument");
     if (n == 0) return GPSB_OK;
     CU(cudaSetDevice(c->device));
+    if (n >= c->epl_batch_min) {            // large batches: one warp per cell, persistent grid (gpsb_epl_batch.cuh)
+        const uint32_t want = (n + kBatchThreads / 32 - 1) / (kBatchThreads / 32);
+        const uint32_t cap = (uint32_t)c->n_sm * kBatchCtasPerSm;
+        k_epl_batch<3><<<want < cap ? want : cap, kBatchThreads, 0, c->stream>>>(d_req, d_out, c->d_rxt, c->d_signal, c->ring_ms, n);
+        return check_launch(c, "k_epl_batch");
+    }
     k_epl<<<n, kEplThreads, 0, c->stream>>>(d_req, d_out, c->d_codes, c->d_signal, c->ring_ms);
     return check_launch(c, "k_epl");
+}
+
+int gpsb_set_epl_batch_min(gpsb_ctx* c, uint32_t n_cells)
+{
+    if (!c) return fail(GPSB_ERR_ARG, "null context");
+    c->epl_batch_min = n_cells;
+    return GPSB_OK;
+}
+
+int gpsb_prompt_iq_dev(gpsb_ctx* c, uint32_t n, const gpsb_epl_req* d_req, int16_t* d_out)
+{
+    if (!c || !d_req || !d_out) return fail(GPSB_ERR_ARG, "gpsb_prompt_iq_dev: null argument");
+    if (n == 0) return GPSB_OK;
+    CU(cudaSetDevice(c->device));
+    const uint32_t want = (n + kBatchThreads / 32 - 1) / (kBatchThreads / 32);
+    const uint32_t cap = (uint32_t)c->n_sm * kBatchCtasPerSm;
+    k_epl_batch<1><<<want < cap ? want : cap, kBatchThreads, 0, c->stream>>>(d_req, d_out, c->d_rxt, c->d_signal, c->ring_ms, n);
+    return check_launch(c, "k_epl_batch<prompt>");
+}
+
+int gpsb_prompt_iq(gpsb_ctx* c, uint32_t n, const gpsb_epl_req* req, int16_t* out)
+{
+    if (!c || !req || !out) return fail(GPSB_ERR_ARG, "gpsb_prompt_iq: null argument");
+    if (n == 0) return GPSB_OK;
+    int rc = check_epl(c, n, req);
+    if (rc) return rc;
+    CallGuard guard(c);
+    const size_t req_b = (size_t)n * sizeof(gpsb_epl_req), out_b = (size_t)n * 4;
+    const size_t out_off = (req_b + 255) & ~(size_t)255;
+    rc = ensure_stage(c, out_off + out_b);
+    if (rc) return rc;
+    memcpy(c->h_stage, req, req_b);
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(c->d_stage, c->h_stage, req_b, cudaMemcpyHostToDevice, c->stream));
+    rc = gpsb_prompt_iq_dev(c, n, (const gpsb_epl_req*)c->d_stage, (int16_t*)((uint8_t*)c->d_stage + out_off));
+    if (rc) return rc;
+    CU(cudaMemcpyAsync((uint8_t*)c->h_stage + out_off, (uint8_t*)c->d_stage + out_off, out_b, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    memcpy(out, (uint8_t*)c->h_stage + out_off, out_b);
+    return GPSB_OK;
 }
 
 int gpsb_track_epl(gpsb_ctx* c, uint32_t n, const gpsb_epl_req* req, int16_t* out)

@@ -1,0 +1,246 @@
+/*
+ * gpsb_epl_batch.cuh - k_epl_batch: open-loop integrate-and-dump over LARGE batches of cells, one WARP per cell.
+ *
+ * The closed loop (k_track_run) is serial per channel; a batch of cells whose NCO words and code offsets are all
+ * known in advance - a recording replayed along a known trajectory, the reference's single-millisecond prompt
+ * correlation (gps_correlation_iq, Firmware/project_main/GPS/gps_misc.c:128-145) repeated over a long recording,
+ * SURVEY.md section 8(d) config 1 "batched" - has no such chain and is bound by how fast frames leave HBM
+ * (2046 B per cell when every cell has its own millisecond) and by the POPC pipe (2 per word and arm).
+ *
+ *   frame     each lane fetches 4 x 16 bytes of the cell's frame straight into registers (coalesced 512-byte
+ *             requests, L1 bypassed), one cell ahead of the one being correlated; nothing is staged in shared memory
+ *   replica   the periodically extended replica stream of every (satellite slot, sub-byte shift) is resident in
+ *             HBM/L2 (RXT, built when the code is set: per slot 16 shifts x 4 word-displaced copies x 1040 words, two periods); the window of data word w for
+ *             byte offset `off` is one funnel shift of two RXT words at byte 4w - off + 2046 (no wrap to test for)
+ *   carrier   closed form of gps_misc.c:229-239 per word; the quadrant patterns are one byte repeated (top byte of
+ *             0x09999999 aside), so a pattern pair costs two PRMT byte broadcasts, shared by the arms
+ *   edges     word 511 (never mixed; 16 or 8 replica bits against zero data) is special-cased in its unrolled slot;
+ *             for odd offsets nine "edge" lanes then take back the three bytes the reference skips (gps_misc.c:59-89)
+ *             - the bookkeeping of core/gpsb_epl_core.h in direct (I, Q) form
+ *   reduce    REDUX per arm on packed I | Q << 16 sums, lane 0 stores the cell's int16 results
+ *
+ * kArms = 3: IE,QE,IP,QP,IL,QL per request (tracking.c:115-138); kArms = 1: the prompt arm only (I, Q).
+ */
+#pragma once
+
+#include "../core/gpsb_epl_core.h"
+#include "gpsb_kernels.cuh"
+
+namespace gpsb {
+
+constexpr int kRxtWords = 1040;         // two 2046-byte periods + the longest run a lane reads past them, rounded up to 16 bytes
+constexpr int kRxtShifts = 16;
+constexpr int kRxtCopies = 4;           // the stream displaced by 0..3 words (alignment of 128-bit loads)
+constexpr int kBatchThreads = 256;
+#ifndef GPSB_BATCH_CTAS
+#define GPSB_BATCH_CTAS 2
+#endif
+constexpr int kBatchCtasPerSm = GPSB_BATCH_CTAS;
+
+// RXT[slot][b][r][x] = bytes 4(x+r) .. 4(x+r)+3 (mod 2046) of the replica buffer gps_generate_prn_data2(b) produces
+// (gps_misc.c:282-300: chip k at sample bits [16k+b, 16k+b+16), no wrap, the spill beyond 2046 bytes dropped).
+// The four copies r = 0..3 are the same stream displaced by r words, so that a run starting at ANY word of the stream
+// starts 16-byte aligned in one of them and a lane fetches its four words with one 128-bit load.
+__global__ void k_build_rxt(const uint32_t* __restrict__ E, uint32_t* __restrict__ rxt)
+{
+    for (int i = threadIdx.x + blockIdx.x * blockDim.x; i < kRxtShifts * kRxtCopies * kRxtWords; i += blockDim.x * gridDim.x) {
+        const uint32_t b = (uint32_t)(i / (kRxtCopies * kRxtWords));
+        const int r = (i / kRxtWords) % kRxtCopies;
+        const int x = i % kRxtWords + r;
+        uint32_t v = 0;
+        for (int j = 0; j < 4; j++) {
+            const int byte = (4 * x + j) % (int)GPSB_MS_BYTES;
+            const uint32_t w = ec_replica_word(E, byte >> 2, b);
+            v |= ((w >> (8 * (byte & 3))) & 0xFFu) << (8 * j);
+        }
+        rxt[i] = v;
+    }
+}
+
+// PRMT with the selector taken as it is (the __byte_perm intrinsic masks it first: two more instructions per word)
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+
+// cos / sin quadrant patterns of carrier phase ph = nco >> 30 (gps_misc.c:216-217) by byte broadcast: every pattern is
+// one byte repeated, except that the top byte of 0x09999999 is 0x09 - bytes 0..2 come from one table word (selector
+// nibbles ph), byte 3 from a second one (selector nibble 4 + ph)
+__device__ __forceinline__ void quadrant_patterns(uint32_t nco, uint32_t& cp, uint32_t& sp)
+{
+    const uint32_t sel = (nco >> 30) * 0x1111u + 0x4000u;
+    cp = prmt(0x3366CC99u, 0x3366CC09u, sel);     // cos[ph]
+    sp = prmt(0x66CC9933u, 0x66CC0933u, sel);     // sin[ph] = cos[(ph + 3) & 3]
+}
+
+// frame index of millisecond ms: the modulo only when the ring has wrapped (an integer modulo is ~20 instructions)
+__device__ __forceinline__ uint32_t ring_frame(uint32_t ms, uint32_t ring_ms) { return ms < ring_ms ? ms : ms % ring_ms; }
+
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p)
+{
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
+// 32-bit replica window for data word w and byte offset off: bytes 4w - off (+ one period, so that the position is
+// never negative) .. +3 of the periodic stream
+__device__ __forceinline__ uint32_t rxt_window(const uint32_t* __restrict__ rx, int w, uint32_t off)
+{
+    const int p = 4 * w - (int)off + (int)GPSB_MS_BYTES;      // copy 0 of the table: the stream itself
+    return __funnelshift_r(__ldg(rx + (p >> 2)), __ldg(rx + (p >> 2) + 1), ((uint32_t)p & 3u) * 8u);
+}
+
+// One cell by one warp: `f` holds the cell's frame, lane l the 16-byte groups l, l+32, l+64, l+96.
+template <int kArms>
+__device__ __forceinline__ void batch_cell(const gpsb_epl_req& rq, const uint4 (&f)[4], int lane, uint32_t c,
+                                           int16_t* __restrict__ out, const uint32_t* __restrict__ rxt,
+                                           const uint32_t* __restrict__ signal, uint32_t ring_ms)
+{
+    const uint32_t* __restrict__ rx = rxt + ((size_t)rq.sv_slot * kRxtShifts + (rq.off_bits & 15u)) * (kRxtCopies * kRxtWords);
+    const uint32_t offs[3] = {kArms == 3 ? rq.off_e : rq.off_p, rq.off_p, rq.off_l};
+    uint32_t acc_i[kArms], acc_q[kArms];
+    // Replica run per arm: data word w meets the stream at byte 4w - off + 2046 (RXT spans two periods, so there is no
+    // wrap to test for); the sub-word shift is the same for every word of the cell.  A lane's group of four data words
+    // needs five consecutive stream words: four by one aligned 128-bit load from the copy of the stream displaced by
+    // (first word & 3), the fifth is the first word of the next lane's load (lane 31: of lane 0's load for the next
+    // group, which lane 0 hands over in the same shuffle).
+    uint32_t sh[kArms];
+    uint4 rr[kArms][4];
+    uint32_t r4[kArms][4];
+#pragma unroll
+    for (int a = 0; a < kArms; a++) {
+        acc_i[a] = acc_q[a] = 0u;
+        const int p = 16 * lane - (int)offs[kArms == 3 ? a : 1] + (int)GPSB_MS_BYTES;
+        sh[a] = ((uint32_t)p & 3u) * 8u;
+        const int first = p >> 2, copy = first & 3;
+        const uint32_t* q = rx + copy * kRxtWords + (first - copy);          // 16-byte aligned
+#pragma unroll
+        for (int k = 0; k < 4; k++) rr[a][k] = __ldg(reinterpret_cast<const uint4*>(q + 128 * k));
+        const uint32_t beyond = lane == 0 ? __ldg(q + 512) : 0u;              // first word of a fifth group, for lane 31
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t give = lane == 0 ? (k < 3 ? rr[a][k < 3 ? k + 1 : 3].x : beyond) : rr[a][k].x;
+            r4[a][k] = __shfl_sync(0xFFFFFFFFu, give, (lane + 1) & 31);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int w0 = 4 * (lane + 32 * k);
+        const uint32_t s[4] = {f[k].x, f[k].y, f[k].z, f[k].w};
+        uint32_t r[kArms][5];
+#pragma unroll
+        for (int a = 0; a < kArms; a++) {
+            r[a][0] = rr[a][k].x; r[a][1] = rr[a][k].y; r[a][2] = rr[a][k].z; r[a][3] = rr[a][k].w;
+            r[a][4] = r4[a][k];
+        }
+        uint32_t nco = rq.acc0 + (uint32_t)w0 * rq.step32;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            uint32_t cp, sp;
+            quadrant_patterns(nco, cp, sp);
+            nco += rq.step32;
+#pragma unroll
+            for (int a = 0; a < kArms; a++) {
+                const uint32_t win = __funnelshift_r(r[a][j], r[a][j + 1], sh[a]);
+                uint32_t xi = s[j] ^ cp ^ win, xq = s[j] ^ sp ^ win;
+                if (k == 3 && j == 3) {
+                    // word 511 (lane 31) is never mixed - its data is 0 - and only its bytes 2044 and, for even
+                    // offsets, 2045 exist: I = Q = those replica bits (gps_misc.c:229, :59-89)
+                    const uint32_t keep = (offs[kArms == 3 ? a : 1] & 1u) ? 0x000000FFu : 0x0000FFFFu;
+                    xi = lane == 31 ? (win & keep) : xi;
+                    xq = lane == 31 ? (win & keep) : xq;
+                }
+                acc_i[a] += (uint32_t)__popc(xi);
+                acc_q[a] += (uint32_t)__popc(xq);
+            }
+        }
+    }
+    uint32_t acc[kArms];
+#pragma unroll
+    for (int a = 0; a < kArms; a++) acc[a] = acc_i[a] + (acc_q[a] << 16);
+
+    // Odd offsets 2k+1 skip the replica words whose data bytes are {2045, 0} and {off-2, off-1} (gps_misc.c:59-89).
+    // Byte 2045 is handled above; edge lanes take back what the loop counted for the other three: role 0 byte 0,
+    // roles 1 / 2 bytes off-2 / off-1 (offsets >= 3).
+    bool any_odd = false;
+#pragma unroll
+    for (int a = 0; a < kArms; a++) any_odd |= (offs[kArms == 3 ? a : 1] & 1u) != 0u;
+    if (any_odd && lane < 3 * kArms) {
+        const int role = lane / kArms, a = lane % kArms;
+        const uint32_t o = offs[kArms == 3 ? a : 1];
+        const int d = role == 0 ? 0 : (int)o - (role == 1 ? 2 : 1);
+        if ((o & 1u) && (role == 0 || o >= 3u)) {
+            const int word = d >> 2;
+            const uint32_t m = 0xFFu << (8 * (d & 3));
+            const uint32_t win = rxt_window(rx, word, o);
+            uint32_t v;
+            if (word < kWords - 1) {
+                const uint32_t sw = __ldg(signal + (size_t)ring_frame(rq.ms_index, ring_ms) * kWords + word);
+                uint32_t cp, sp;
+                quadrant_patterns(rq.acc0 + (uint32_t)word * rq.step32, cp, sp);
+                v = (uint32_t)__popc((sw ^ cp ^ win) & m) + ((uint32_t)__popc((sw ^ sp ^ win) & m) << 16);
+            } else {
+                v = (uint32_t)__popc(win & m) * 0x00010001u;      // byte 2044 of offset 2045: counted above against zero data
+            }
+#pragma unroll
+            for (int b = 0; b < kArms; b++) acc[b] -= (b == a) ? v : 0u;
+        }
+    }
+
+    uint32_t tot[kArms];
+#pragma unroll
+    for (int a = 0; a < kArms; a++) tot[a] = __reduce_add_sync(0xFFFFFFFFu, acc[a]);
+    if (lane == 0) {
+        uint32_t* o32 = reinterpret_cast<uint32_t*>(out + (size_t)c * 2 * kArms);
+#pragma unroll
+        for (int a = 0; a < kArms; a++) {
+            const uint32_t i16 = (uint16_t)(int16_t)((int)(tot[a] & 0xFFFFu) - kHalfSum);
+            const uint32_t q16 = (uint16_t)(int16_t)((int)(tot[a] >> 16) - kHalfSum);
+            o32[a] = i16 | (q16 << 16);
+        }
+    }
+}
+
+template <int kArms>
+__global__ void __launch_bounds__(kBatchThreads, kBatchCtasPerSm)
+k_epl_batch(const gpsb_epl_req* __restrict__ reqs, int16_t* __restrict__ out, const uint32_t* __restrict__ rxt,
+            const uint32_t* __restrict__ signal, uint32_t ring_ms, uint32_t n)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t warps = (gridDim.x * kBatchThreads) >> 5;
+    uint32_t c = (blockIdx.x * kBatchThreads + threadIdx.x) >> 5;
+    if (c >= n) return;
+
+    // Software pipeline, unrolled by two so that the two frame buffers swap roles without register moves: while cell i
+    // is correlated, the frame of cell i+1 and the request of cell i+2 are in flight - neither the request fetch
+    // (which the frame address depends on) nor the frame fetch is waited for.
+    auto load_req = [&](uint32_t idx, const gpsb_epl_req& fallback) { return idx < n ? reqs[idx] : fallback; };
+    auto load_frame = [&](const gpsb_epl_req& r, uint4 (&f)[4]) {
+        const uint4* fp = reinterpret_cast<const uint4*>(signal + (size_t)ring_frame(r.ms_index, ring_ms) * kWords);
+#pragma unroll
+        for (int k = 0; k < 4; k++) f[k] = ldg_stream(fp + lane + 32 * k);
+    };
+    gpsb_epl_req rq_a = reqs[c];
+    gpsb_epl_req rq_b = load_req(c + warps, rq_a);
+    uint4 fa[4], fb[4];
+    load_frame(rq_a, fa);
+    for (;;) {
+        load_frame(rq_b, fb);                                  // past the end: re-reads a frame that is in L2 anyway
+        const gpsb_epl_req rq_c = load_req(c + 2 * warps, rq_b);
+        batch_cell<kArms>(rq_a, fa, lane, c, out, rxt, signal, ring_ms);
+        c += warps;
+        if (c >= n) break;
+        load_frame(rq_c, fa);
+        rq_a = load_req(c + 2 * warps, rq_c);                  // request of the cell after next, into the free slot
+        batch_cell<kArms>(rq_b, fb, lane, c, out, rxt, signal, ring_ms);
+        c += warps;
+        if (c >= n) break;
+        rq_b = rq_a;                                           // roles for the next round: a = cell c, b = cell c + warps
+        rq_a = rq_c;
+    }
+}
+
+}  // namespace gpsb

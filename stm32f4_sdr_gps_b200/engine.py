@@ -89,6 +89,9 @@ def load_library(path: Path | None = None) -> C.CDLL:
         "gpsb_session_post": (i32, [vp, u32, vp, C.POINTER(u32)]),
         "gpsb_session_wait": (i32, [vp, u32, u32, vp]),
         "gpsb_track_epl_dev": (i32, [vp, u32, vp, vp]),
+        "gpsb_prompt_iq_dev": (i32, [vp, u32, vp, vp]),
+        "gpsb_prompt_iq": (i32, [vp, u32, vp, vp]),
+        "gpsb_set_epl_batch_min": (i32, [vp, u32]),
         "gpsb_search_dev": (i32, [vp, u32, vp, vp]),
         "gpsb_sweep_dev": (i32, [vp, vp, u32, vp, u32, u32, u32, u32, vp]),
         "gpsb_track_loop": (i32, [vp, u32, vp, u32, vp, u32, u32, u32, vp, vp, vp]),
@@ -227,6 +230,16 @@ class Engine:
         self._check(self.lib.gpsb_track_epl(self._ctx, reqs.size, _p(reqs), _p(out)))
         return out
 
+    def prompt_iq(self, reqs: np.ndarray) -> np.ndarray:
+        """The prompt arm alone (I, Q) of every request: gpsb_prompt_iq."""
+        reqs = np.ascontiguousarray(reqs, dtype=EPL_REQ).reshape(-1)
+        out = np.zeros((reqs.size, 2), np.int16)
+        self._check(self.lib.gpsb_prompt_iq(self._ctx, reqs.size, _p(reqs), _p(out)))
+        return out
+
+    def set_epl_batch_min(self, n_cells: int) -> None:
+        self._check(self.lib.gpsb_set_epl_batch_min(self._ctx, n_cells))
+
     def search(self, reqs: np.ndarray) -> np.ndarray:
         reqs = np.ascontiguousarray(reqs, dtype=SEARCH_REQ).reshape(-1)
         res = np.zeros(reqs.size, SEARCH_RES)
@@ -261,6 +274,9 @@ class Engine:
         self._check(self.lib.gpsb_session_end(self._ctx))
 
     # device-resident variants: raw device pointers (ints), asynchronous on the context stream
+    def prompt_iq_dev(self, n: int, d_req: int, d_out: int) -> None:
+        self._check(self.lib.gpsb_prompt_iq_dev(self._ctx, n, C.c_void_p(d_req), C.c_void_p(d_out)))
+
     def track_epl_dev(self, n: int, d_req: int, d_out: int) -> None:
         self._check(self.lib.gpsb_track_epl_dev(self._ctx, n, C.c_void_p(d_req), C.c_void_p(d_out)))
 

@@ -381,3 +381,56 @@ def test_sweep_tile_shapes_ring_wrap_and_big_batches(engine, oracle):
                                        int(rq["acc0"][i]), int(rq["step32"][i]), int(rq["off_e"][i]),
                                        int(rq["off_p"][i]), int(rq["off_l"][i]), int(rq["off_bits"][i]))
             assert np.array_equal(out[i], want), (n, i)
+
+
+def test_epl_batch_kernel_vs_oracle_and_cta_kernel(engine, oracle):
+    """k_epl_batch (one warp per cell, frames streamed into registers, resident extended replica tables) against
+    the oracle and against k_epl on the same requests: every sub-byte shift 0..15, the offsets around the period
+    seam and around the odd-offset exclusions, unrelated arms, ring wrap, a batch that is not a multiple of the
+    warp count; and the prompt-only form gpsb_prompt_iq."""
+    rng = np.random.default_rng(4242)
+    ring = engine.ring_ms
+    n_ms, prns = 9, [1, 17, 32]
+    sig = rng.integers(0, 256, (n_ms, 2046), dtype=np.uint8)
+    ms0 = ring * 7 - 4                                       # wraps around the end of the ring
+    engine.upload_signal(ms0, sig)
+    for s, prn in enumerate(prns):
+        engine.set_code_prn(s, prn)
+    n = 2600 + 13
+    rq = np.zeros(n, EPL_REQ)
+    rq["sv_slot"] = rng.integers(0, 3, n)
+    rq["ms_index"] = ms0 + rng.integers(0, n_ms, n)
+    rq["acc0"] = rng.integers(0, 2**32, n, dtype=np.uint64)
+    rq["step32"] = rng.integers(0, 2**32, n, dtype=np.uint64)
+    rq["step32"][::3] &= 0x07FFFFFF                          # realistic Doppler range too
+    rq["off_p"] = rng.integers(0, 2046, n)
+    special = [0, 1, 2, 3, 4, 5, 2040, 2041, 2042, 2043, 2044, 2045, 1021, 1022, 1023, 1024]
+    rq["off_p"][:len(special)] = special
+    rq["off_e"] = np.where(rq["off_p"] == 0, 2045, rq["off_p"].astype(np.int32) - 1)
+    rq["off_l"] = np.where(rq["off_p"] == 2045, 0, rq["off_p"] + 1)
+    rq["off_e"][100:400] = rng.integers(0, 2046, 300)        # arbitrary, unrelated arms
+    rq["off_l"][100:400] = rng.integers(0, 2046, 300)
+    rq["off_bits"] = rng.integers(0, 16, n)
+    engine.set_epl_batch_min(0)                              # every size through k_epl_batch
+    try:
+        engine.set_realtime(False)
+        out = engine.track_epl(rq)
+        small = engine.track_epl(rq[:5])
+        prompt = engine.prompt_iq(rq)
+    finally:
+        engine.set_epl_batch_min(2**32 - 1)                  # never: the one-CTA-per-cell kernel
+    try:
+        ref = engine.track_epl(rq)
+    finally:
+        engine.set_epl_batch_min(512)
+        engine.set_realtime(True)
+    assert np.array_equal(out, ref)
+    assert np.array_equal(small, ref[:5])
+    assert np.array_equal(prompt, ref[:, 2:4])
+    check = list(range(len(special))) + list(range(100, 130)) + [int(i) for i in rng.integers(0, n, 60)] + [n - 1]
+    for i in check:
+        want = oracle.epl_explicit(oracle.ca_code(prns[rq["sv_slot"][i]]), sig[rq["ms_index"][i] - ms0],
+                                   int(rq["acc0"][i]), int(rq["step32"][i]), int(rq["off_e"][i]),
+                                   int(rq["off_p"][i]), int(rq["off_l"][i]), int(rq["off_bits"][i]))
+        assert np.array_equal(out[i], want), (i, rq[i])
+    assert engine.prompt_iq(np.zeros(0, EPL_REQ)).shape == (0, 2)
