@@ -95,6 +95,22 @@ typedef struct gpsb_flat_state {
     uint8_t  subframe_data[GPSB_FLAT_SUBFRAME_BYTES];
 } gpsb_flat_state;
 
+/* Layout-independent image of the channel's ephemeris container (sdreph_t / eph_t, PM/GPS/gps_misc.h:135-182), filled by
+ * gps_nav_data_decode_subframe (PM/GPS/nav_data_decode.c:33): doubles as their bit patterns. */
+typedef struct gpsb_flat_eph {
+    int32_t  sat, iode, iodc, sva, svh, week, code, flag;
+    int64_t  toe_time, toc_time, ttr_time;
+    uint64_t toe_sec_bits, toc_sec_bits, ttr_sec_bits;
+    uint64_t A, e, i0, OMG0, omg, M0, deln, OMGd, idot;          /* bit patterns of the doubles */
+    uint64_t crc, crs, cuc, cus, cic, cis;
+    uint64_t toes, fit, f0, f1, f2;
+    uint64_t tgd[4];
+    int32_t  ctype;
+    int32_t  week_gpst, cnt, cntth, update, prn, week_gst;
+    uint32_t sub_cnt, received_mask, received_mask_proc;
+    uint64_t tow_gpst;
+} gpsb_flat_eph;
+
 #ifdef __cplusplus
 }
 #endif

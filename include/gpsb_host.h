@@ -234,6 +234,10 @@ void gps_tracking_process(gps_ch_t* channel, uint8_t* data, uint8_t index);
 void gps_nav_data_analyse_new_code(gps_ch_t* channel, uint8_t index, int16_t new_i);
 void gps_nav_data_words_detection(gps_ch_t* channel, uint8_t new_bit);
 
+/* PM/GPS/nav_data_decode.h: ephemeris / clock fields of a completed subframe (channel->nav_data.subframe_data) into
+ * channel->eph_data; returns the subframe id.  Called by the word assembler whenever a subframe completes. */
+uint8_t gps_nav_data_decode_subframe(gps_ch_t* channel);
+
 /* PM/GPS/gps_master.h:7-15 (sequencing only: no UART, keys, RTCM or position solver here) */
 void    gps_master_handling(gps_ch_t* channels, uint8_t index);
 uint8_t gps_master_need_acq(void);
@@ -338,6 +342,11 @@ void gpsb_host_channels_free(gps_ch_t* p);
 gps_ch_t* gpsb_host_channel_at(gps_ch_t* base, uint32_t i);
 void gpsb_host_channel_init(gps_ch_t* ch, uint32_t prn, int32_t given_freq_offset_hz);
 const uint8_t* gpsb_host_channel_code(const gps_ch_t* ch);
+
+/* Replay helper: hand n data bits to the word assembler, the millisecond counter advancing 20 per bit from ms0. */
+void gpsb_host_feed_nav_bits(gps_ch_t* ch, const uint8_t* bits, uint32_t n, uint32_t ms0);
+struct gpsb_flat_eph;
+void gpsb_host_channel_eph(const gps_ch_t* ch, struct gpsb_flat_eph* out);
 
 /* Flat, layout-independent snapshot of one channel (include/gpsb_flat_state.h) for parity tests. */
 struct gpsb_flat_state;

@@ -442,3 +442,41 @@ double ref_prompt_time(gps_ch_t* ch, const uint8_t* signal, uint32_t n_ms, float
     return ref_now_s() - t0;
 }
 
+/* ------------------------------------------------------------------ ephemeris container, flat image */
+static uint64_t d2u(double d) { uint64_t u; memcpy(&u, &d, 8); return u; }
+void ref_channel_eph(const gps_ch_t* ch, gpsb_flat_eph* o)
+{
+    const sdreph_t* d = &ch->eph_data;
+    const eph_t* e = &d->eph;
+    memset(o, 0, sizeof *o);
+    o->sat = e->sat; o->iode = e->iode; o->iodc = e->iodc; o->sva = e->sva; o->svh = e->svh; o->week = e->week;
+    o->code = e->code; o->flag = e->flag;
+    o->toe_time = (int64_t)e->toe.time; o->toc_time = (int64_t)e->toc.time; o->ttr_time = (int64_t)e->ttr.time;
+    o->toe_sec_bits = d2u(e->toe.sec); o->toc_sec_bits = d2u(e->toc.sec); o->ttr_sec_bits = d2u(e->ttr.sec);
+    o->A = d2u(e->A); o->e = d2u(e->e); o->i0 = d2u(e->i0); o->OMG0 = d2u(e->OMG0); o->omg = d2u(e->omg);
+    o->M0 = d2u(e->M0); o->deln = d2u(e->deln); o->OMGd = d2u(e->OMGd); o->idot = d2u(e->idot);
+    o->crc = d2u(e->crc); o->crs = d2u(e->crs); o->cuc = d2u(e->cuc); o->cus = d2u(e->cus); o->cic = d2u(e->cic);
+    o->cis = d2u(e->cis); o->toes = d2u(e->toes); o->fit = d2u(e->fit); o->f0 = d2u(e->f0); o->f1 = d2u(e->f1);
+    o->f2 = d2u(e->f2);
+    for (int i = 0; i < 4; i++) o->tgd[i] = d2u(e->tgd[i]);
+    o->ctype = d->ctype; o->week_gpst = d->week_gpst; o->cnt = d->cnt; o->cntth = d->cntth; o->update = d->update;
+    o->prn = d->prn; o->week_gst = d->week_gst; o->sub_cnt = d->sub_cnt; o->received_mask = d->received_mask;
+    o->received_mask_proc = d->received_mask_proc; o->tow_gpst = d2u(d->tow_gpst);
+}
+
+/* gps_nav_data_decode_subframe() on a given 300-bit subframe image (nav_data_decode.c:33) */
+uint8_t gps_nav_data_decode_subframe(gps_ch_t* channel);
+uint32_t ref_decode_subframe(gps_ch_t* ch, const uint8_t image[38])
+{
+    memcpy(ch->nav_data.subframe_data, image, 38);
+    return gps_nav_data_decode_subframe(ch);
+}
+/* the word assembler fed bit by bit (nav_data.c:257), ms counter advancing 20 per bit from ms0 */
+void gps_nav_data_words_detection(gps_ch_t* channel, uint8_t new_bit);
+void ref_feed_nav_bits(gps_ch_t* ch, const uint8_t* bits, uint32_t n, uint32_t ms0)
+{
+    for (uint32_t i = 0; i < n; i++) {
+        g_packet_cnt = ms0 + 20u * i;
+        gps_nav_data_words_detection(ch, bits[i]);
+    }
+}

@@ -567,6 +567,117 @@ LC_FN void lc_clear_word(gps_nav_data_t* n)
     for (unsigned i = 0; i < GPS_NAV_WORD_LENGTH; i++) n->word_buf[i] = 0;
 }
 
+/* ------------------------------------------------------------------------------------------ ephemeris fields */
+/* nav_data_decode.c:144-181.  The subframe image keeps navigation bit i (0 = first bit of the TLM word) at byte
+ * i/8, bit i%8 (nav_data.c:409-426); fields are MSB first.  lc_field reads `len` bits from bit `pos`; a field split
+ * over two words is its upper part shifted up by the length of the lower one (getbitu2 / getbits2). */
+LC_FN uint32_t lc_field(const uint8_t* sf, int pos, int len)
+{
+    uint32_t v = 0;
+    for (int i = pos; i < pos + len; i++) v = (v << 1) | ((uint32_t)(sf[i >> 3] >> (i & 7)) & 1u);
+    return v;
+}
+LC_FN int32_t lc_field_signed(const uint8_t* sf, int pos, int len)
+{
+    uint32_t v = lc_field(sf, pos, len);
+    if (len > 0 && len < 32 && (v >> (len - 1)) & 1u) v |= ~0u << len;      /* two's complement of `len` bits */
+    return (int32_t)v;
+}
+LC_FN uint32_t lc_field2(const uint8_t* sf, int p1, int l1, int p2, int l2)
+{
+    return (lc_field(sf, p1, l1) << l2) + lc_field(sf, p2, l2);
+}
+LC_FN int32_t lc_field2_signed(const uint8_t* sf, int p1, int l1, int p2, int l2)
+{
+    /* the sign lives in the upper part; a non-negative value is the plain concatenation */
+    if (lc_field(sf, p1, 1)) return (int32_t)(((uint32_t)lc_field_signed(sf, p1, l1) << l2) + lc_field(sf, p2, l2));
+    return (int32_t)lc_field2(sf, p1, l1, p2, l2);
+}
+
+/* RTK/rtklib_common.c:32-43: GPS week + seconds of week -> time stamp (whole seconds since the Unix epoch, fraction) */
+LC_FN gtime_t lc_gpst2time(int week, double sec)
+{
+    gtime_t t;
+    if (sec < -1e9 || 1e9 < sec) sec = 0.0;
+    t.time = (time_t)315964800 + (time_t)(86400 * 7 * week + (int)sec);    /* the reference adds in int: reproduce */
+    t.sec = sec - (int)sec;
+    return t;
+}
+
+#define LC_GPS_BUILD_WEEK 2290                    /* config.h:73; resolves the 10-bit week number, nav_data_decode.c:184 */
+/* Scale factors as the reference spells them (rtk_common.h:9-32): 16-digit decimals, three of which (2^-33, 2^-43,
+ * 2^-55) do NOT round to the power of two they stand for but to the double one ulp below it - parity needs those. */
+#define LC_2P_5  0.03125
+#define LC_2P_19 1.907348632812500E-06
+#define LC_2P_29 1.862645149230957E-09
+#define LC_2P_31 4.656612873077393E-10
+#define LC_2P_33 1.164153218269348E-10
+#define LC_2P_43 1.136868377216160E-13
+#define LC_2P_55 2.775557561562891E-17
+#define LC_2P(n) LC_2P_##n
+#define LC_SC2RAD 3.1415926535898                 /* semicircles -> radians, rtk_common.h:45 */
+
+/* nav_data_decode.c:33-141: the ephemeris / clock fields of subframes 1..3 (IS-GPS-200 figure 20-1), transmit time and
+ * bookkeeping for 4 and 5.  Fields go straight into the channel's record, like the reference.  Returns the subframe id.
+ * Everything is integer -> double conversion and IEEE double multiplication in the reference's order of operations:
+ * identical bits from gcc (-ffp-contract=off) and nvcc (--fmad=false). */
+LC_FN_BIG uint8_t lc_decode_subframe(gps_ch_t* ch)
+{
+    const uint8_t* sf = ch->nav_data.subframe_data;
+    sdreph_t* d = &ch->eph_data;
+    eph_t* e = &d->eph;
+    const uint32_t id = lc_field(sf, 49, 3);
+    e->sat = ch->prn;
+    if (id >= 1 && id <= 5) d->tow_gpst = lc_field(sf, 30, 17) * 6.0;      /* HOW: time of week of the next subframe */
+    if (id == 1) {
+        const int week = (int)lc_field(sf, 60, 10) + 1024;
+        e->code = (int)lc_field(sf, 70, 2);
+        e->sva = (int)lc_field(sf, 72, 4);
+        e->svh = (int)lc_field(sf, 76, 6);
+        e->iodc = (int)lc_field2(sf, 82, 2, 210, 8);
+        e->flag = (int)lc_field(sf, 90, 1);
+        e->tgd[0] = lc_field_signed(sf, 196, 8) * LC_2P(31);
+        const double toc = lc_field(sf, 218, 16) * 16.0;
+        e->f2 = lc_field_signed(sf, 240, 8) * LC_2P(55);
+        e->f1 = lc_field_signed(sf, 248, 16) * LC_2P(43);
+        e->f0 = lc_field_signed(sf, 270, 22) * LC_2P(31);
+        e->week = week + (LC_GPS_BUILD_WEEK - week + 512) / 1024 * 1024;
+        d->week_gpst = e->week;
+        e->ttr = lc_gpst2time(e->week, d->tow_gpst);
+        e->toc = lc_gpst2time(e->week, toc);
+    } else if (id == 2) {
+        e->iode = (int)lc_field(sf, 60, 8);
+        e->crs = lc_field_signed(sf, 68, 16) * LC_2P(5);
+        e->deln = lc_field_signed(sf, 90, 16) * LC_2P(43) * LC_SC2RAD;
+        e->M0 = lc_field2_signed(sf, 106, 8, 120, 24) * LC_2P(31) * LC_SC2RAD;
+        e->cuc = lc_field_signed(sf, 150, 16) * LC_2P(29);
+        e->e = lc_field2(sf, 166, 8, 180, 24) * LC_2P(33);
+        e->cus = lc_field_signed(sf, 210, 16) * LC_2P(29);
+        const double root_a = lc_field2(sf, 226, 8, 240, 24) * LC_2P(19);
+        e->toes = lc_field(sf, 270, 16) * 16.0;
+        e->fit = lc_field(sf, 286, 1);
+        e->A = root_a * root_a;
+        e->toe = lc_gpst2time(e->week, e->toes);
+    } else if (id == 3) {
+        e->cic = lc_field_signed(sf, 60, 16) * LC_2P(29);
+        e->OMG0 = lc_field2_signed(sf, 76, 8, 90, 24) * LC_2P(31) * LC_SC2RAD;
+        e->cis = lc_field_signed(sf, 120, 16) * LC_2P(29);
+        e->i0 = lc_field2_signed(sf, 136, 8, 150, 24) * LC_2P(31) * LC_SC2RAD;
+        e->crc = lc_field_signed(sf, 180, 16) * LC_2P(5);
+        e->omg = lc_field2_signed(sf, 196, 8, 210, 24) * LC_2P(31) * LC_SC2RAD;
+        e->OMGd = lc_field_signed(sf, 240, 24) * LC_2P(43) * LC_SC2RAD;
+        e->iode = (int)lc_field(sf, 270, 8);
+        e->idot = lc_field_signed(sf, 278, 14) * LC_2P(43) * LC_SC2RAD;
+    }
+    if (id >= 1 && id <= 4) d->cnt++;                         /* subframe 5 does not count, nav_data_decode.c:137-141 */
+    if (id >= 1 && id <= 5) {
+        d->received_mask |= (uint8_t)(1u << (id - 1));
+        d->received_mask_proc |= (uint8_t)(1u << (id - 1));
+    }
+    d->sub_cnt++;
+    return (uint8_t)id;
+}
+
 /* nav_data.c:257-352 */
 LC_FN_BIG void lc_nav_word_bit(gps_ch_t* ch, uint8_t new_bit, uint32_t now)
 {
@@ -607,7 +718,7 @@ LC_FN_BIG void lc_nav_word_bit(gps_ch_t* ch, uint8_t new_bit, uint32_t now)
     n->word_detection_timestamp = now;
     n->polarity_found = 1;
     if (n->word_cnt == LC_WORDS_PER_SUBFRAME) {
-        ch->eph_data.sub_cnt++;                               /* nav_data_decode.c:47 (field decode not done here) */
+        lc_decode_subframe(ch);                               /* nav_data.c:335 */
         lc_stamp_subframe(n, now);
         n->word_cnt = 0;
         n->new_subframe_flag = 1;

@@ -259,3 +259,41 @@ def test_streaming_run_longer_than_the_ring(host_engine, golden, ring_ms, chunk)
         assert rx.loop_stats() == (2 * 600, 0)
         rx.close()
         ch.free()
+
+
+def test_device_loop_decodes_subframes_like_the_reference(host_engine, reference):
+    """Row N2 on the device: a 13-s recording of one satellite whose data bits are correctly encoded subframes 1 and 2
+    (tests/test_nav_decode.py builds them from the ICD), streamed through the 1024-ms ring into ONE k_track_run
+    launch.  Bit synchronisation, preamble hunt, parity, subframe assembly AND the ephemeris / clock field decode
+    (nav_data_decode.c, doubles) all happen in the kernel's nav thread: sums, nav bits, the whole channel record and
+    every field of eph_t equal the unmodified reference's run."""
+    from test_nav_decode import eph_diff, host_eph, make_subframe, ref_eph
+    from stm32f4_sdr_gps_b200.signal_synth import Satellite, Scene, synthesize
+    rng = np.random.default_rng(31)
+    bits = np.concatenate([rng.integers(0, 2, 50, dtype=np.uint8), make_subframe(rng, 1, 0x0F00F), make_subframe(rng, 2, 0x0F010),
+                           rng.integers(0, 2, 20, dtype=np.uint8)])
+    n_ms = 13200
+    sat = Satellite(prn=5, doppler_hz=1234.5, code_phase_samples=7001.3, cn0_dbhz=50.0, nav_bits=bits, nav_bit_offset_ms=7,
+                    carrier_phase_rad=3.14159)          # the Costas loop locks upright: no wait for two inverted preambles
+    sig = synthesize(Scene(sats=[sat], n_ms=n_ms, seed=99))
+    ch = Channels([5])
+    st = _locked(ch, 0, 1000, 1234.5, 7001.3)
+    rchans = reference.channels(1)
+    rch = reference.channel_at(rchans, 0)
+    reference.channel_init(rch, 5, 0)
+    reference.restore(rch, type(reference.snapshot(rch)).from_buffer_copy(bytes(st)))
+    want_iq, want_nav, _ = reference.track_run(rch, sig, 0, n_ms)
+    rx = Receiver(host_engine, ch)
+    launches0 = host_engine.launch_count
+    iq, nav = rx.track_stream(0, sig, chunk_ms=100)
+    assert host_engine.launch_count - launches0 == 1
+    assert rx.loop_stats() == (n_ms, 0)
+    assert np.array_equal(iq[:, 0, :], want_iq)
+    assert np.array_equal(nav[:, 0], want_nav)
+    assert bytes(ch.snapshot(0)) == bytes(reference.snapshot(rch))
+    lib = load_host_library()
+    got, want = host_eph(lib, ch.at(0)), ref_eph(reference, rch)
+    assert not eph_diff(got, want), eph_diff(got, want)
+    assert got.sub_cnt == 2 and got.received_mask == 3 and got.sat == 5      # both subframes went through the decode
+    rx.close()
+    ch.free()
