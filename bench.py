@@ -309,6 +309,10 @@ def arm_locked(channels, scene):
         channels.restore(i, st)
 
 
+# profiler runs only (never for a reported number): a kernel replayed by ncu cannot be fed by a concurrent copy stream
+NO_STREAM = os.environ.get("GPSB_BENCH_NO_STREAM") is not None
+
+
 def run_gpu_arm(args) -> None:
     import torch
     import torch.distributed as dist
@@ -389,9 +393,15 @@ def run_gpu_arm(args) -> None:
 
     # e2e: what a user of the host library calls, host buffers in and out
     rx.set_loop_site(0)
+    def e2e_call():
+        if NO_STREAM:
+            eng.upload_signal(0, pinned_sig.numpy())
+            return rx.track_run(0, N_MS, log=True)
+        return rx.track_stream(0, pinned_sig.numpy(), log=True)
+
     for _ in range(warm):
         arm_locked(channels, scene)
-        rx.track_stream(0, pinned_sig.numpy(), log=True)
+        e2e_call()
     barrier()
     ev = events(steps)
     wall_e2e = 0.0
@@ -403,7 +413,7 @@ def run_gpu_arm(args) -> None:
         ev[k][0].record(stream)
         # host buffer -> HBM ring in chunks WHILE the loop launch is tracking; records in/out, per-ms sums and nav bits
         # land in host arrays; all inside the timed region
-        iq_log, nav_log = rx.track_stream(0, pinned_sig.numpy(), log=True)
+        iq_log, nav_log = e2e_call()
         ev[k][1].record(stream)
         torch.cuda.synchronize()
         wall_e2e += time.perf_counter() - t0
@@ -461,7 +471,7 @@ def run_gpu_arm(args) -> None:
     stream_eng = Engine(device=local_rank, max_sv=211, ring_ms=256)
     many_rx = Receiver(stream_eng, many)
     t_many = []
-    for k in range(4):
+    for k in range(0 if NO_STREAM else 4):
         for i in range(n_many):
             many.restore(i, many_blank[i])
         arm_many()
@@ -469,7 +479,7 @@ def run_gpu_arm(args) -> None:
         t0 = time.perf_counter()
         many_rx.track_stream(0, pinned_sig.numpy(), log=True)
         t_many.append(time.perf_counter() - t0)
-    many_ms = min(t_many) * 1e3
+    many_ms = min(t_many) * 1e3 if t_many else float("nan")
     many_dev, many_host = many_rx.loop_stats()
     many_rx.close()
     stream_eng.close()
@@ -639,7 +649,10 @@ def run_gpu_arm(args) -> None:
             "clocks": clk,
             "roofline": {"kernel": "k_track_run (1 launch per step, %d CTAs: one per satellite)" % n_ch, "bound": "hbm",
                          "achieved": loop_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": loop_achieved / hbm_peak,
-                         "traffic": None, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+                         "traffic": 2134784 if (N_MS == 1000 and n_ch == 4) else None,
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this "
+                                           "launch (profiles/k_track_run_r1.txt)",
+                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                          "algorithmic_bytes_per_launch": loop_bytes, "kernel_ms": loop_kernel_ms,
                          "us_per_ms_of_signal": loop_kernel_ms * 1e3 / N_MS,
                          "note": "serial by construction: millisecond t+1 is planned by the loop filters from the sums of "
@@ -677,7 +690,9 @@ def run_gpu_arm(args) -> None:
                            "roofline": {"kernel": "k_epl_batch<1>", "bound": "hbm",
                                         "achieved": n_long * (2046 + 24 + 4) / (long1_ms * 1e-3) / 1e9, "peak": hbm_peak,
                                         "unit": "GB/s", "frac": n_long * (2046 + 24 + 4) / (long1_ms * 1e-3) / 1e9 / hbm_peak,
-                                        "algorithmic_bytes_per_launch": n_long * (2046 + 24 + 4)}},
+                                        "algorithmic_bytes_per_launch": n_long * (2046 + 24 + 4),
+                                        "traffic": 833011456 if n_long == 400000 else None,
+                                        "traffic_source": "profiles/k_epl_batch1_r1.txt"}},
                 "epl": {"kernel_ms": long3_ms, "cells_per_s": n_long * world / (long3_ms * 1e-3),
                         "arm_samples_per_s": n_long * world * ARMS * MS_SAMPLES / (long3_ms * 1e-3),
                         "roofline": {"kernel": "k_epl_batch<3>", "bound": "hbm",
