@@ -566,6 +566,18 @@ def run_gpu_arm(args) -> None:
             ev[k][1].record(stream)
         barrier()
         acq_ms[name] = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    # the fine grid of SURVEY.md section 8(d) config 3: 2046 half-chip offsets x 8 sub-byte shifts = 16368 phases
+    eng.set_sweep_method(1)
+    ev = events(steps)
+    for k in range(steps):
+        flush.fill_(k)
+        ev[k][0].record(stream)
+        for bits in range(8):
+            eng.sweep_dev(d_sv.data_ptr(), my_sv.size, d_step.data_ptr(), ACQ_BINS, N_MS, ACQ_MS, bits, d_res.data_ptr())
+        ev[k][1].record(stream)
+    barrier()
+    acq_fine_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    eng.sweep_dev(d_sv.data_ptr(), my_sv.size, d_step.data_ptr(), ACQ_BINS, N_MS, ACQ_MS, 0, d_res.data_ptr())   # leave the bits-0 grid
     # end to end: host signal in, all-channel Doppler votes out (upload + sweep + D2H + host chain votes)
     acq_ch = Channels([int(p) for p in my_sv])
     acq_rx = Receiver(eng, acq_ch)
@@ -706,6 +718,7 @@ def run_gpu_arm(args) -> None:
                               "I/Q identical to the GPU's"}},
             "cold_acq": {"metric": "full-sky 32-SV cold-acq ms", "value": acq_dp4a_ms, "unit": "ms",
                          "direct_xor_popc_ms": acq_direct_ms, "e2e_ms": acq_e2e_ms,
+                         "fine_grid_16368_phases_ms": acq_fine_ms,
                          "cells": ACQ_SV * ACQ_BINS * ACQ_MS, "phases": 2046, "bit_macs": acq_bitmacs,
                          "bit_macs_per_s": acq_bitmacs / (acq_dp4a_ms * 1e-3), "doppler_votes_passed_rank0": found,
                          "cpu_baseline": None if not acq_cpu_rate else {
