@@ -238,8 +238,12 @@ void gps_nav_data_words_detection(gps_ch_t* channel, uint8_t new_bit);
  * channel->eph_data; returns the subframe id.  Called by the word assembler whenever a subframe completes. */
 uint8_t gps_nav_data_decode_subframe(gps_ch_t* channel);
 
-/* PM/GPS/gps_master.h:7-15 (sequencing only: no UART, keys, RTCM or position solver here) */
+/* PM/GPS/gps_master.h:7-15 (sequencing and, in the idle slot index == 0xFF, the observations; no UART, keys, RTCM or
+ * position solver here) */
 void    gps_master_handling(gps_ch_t* channels, uint8_t index);
+/* PM/GPS/gps_master.c:159: subframe-time bookkeeping, code-phase filter, pseudorange and time of week of every channel
+ * into channels[i].obs_data (the reference calls it from gps_master_handling's idle slot). */
+void    gps_master_nav_handling(gps_ch_t* channels);
 uint8_t gps_master_need_acq(void);
 uint8_t gps_master_need_freq_search(gps_ch_t* channels);
 uint8_t gps_master_is_code_search3(gps_ch_t* channels);
@@ -347,6 +351,9 @@ const uint8_t* gpsb_host_channel_code(const gps_ch_t* ch);
 void gpsb_host_feed_nav_bits(gps_ch_t* ch, const uint8_t* bits, uint32_t n, uint32_t ms0);
 struct gpsb_flat_eph;
 void gpsb_host_channel_eph(const gps_ch_t* ch, struct gpsb_flat_eph* out);
+
+void gpsb_host_channel_obs(const gps_ch_t* ch, uint64_t out2[2]);     /* bit patterns of obs_data.pseudorange_m, tow_s */
+void gpsb_host_channel_set_tow(gps_ch_t* ch, double tow_gpst);
 
 /* Flat, layout-independent snapshot of one channel (include/gpsb_flat_state.h) for parity tests. */
 struct gpsb_flat_state;

@@ -480,3 +480,18 @@ void ref_feed_nav_bits(gps_ch_t* ch, const uint8_t* bits, uint32_t n, uint32_t m
         gps_nav_data_words_detection(ch, bits[i]);
     }
 }
+
+/* ------------------------------------------------------------------ observations (gps_master.c:159-327) */
+void gps_master_nav_handling(gps_ch_t* channels);
+void ref_nav_handling(gps_ch_t* chans, uint32_t now_ms)
+{
+    g_packet_cnt = now_ms;
+    gps_master_nav_handling(chans);
+}
+void ref_channel_obs(const gps_ch_t* ch, uint64_t out2[2])
+{
+    out2[0] = d2u(ch->obs_data.pseudorange_m);
+    out2[1] = d2u(ch->obs_data.tow_s);
+}
+void ref_channel_set_tow(gps_ch_t* ch, double tow_gpst) { ch->eph_data.tow_gpst = tow_gpst; }
+

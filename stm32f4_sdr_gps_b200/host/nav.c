@@ -68,3 +68,12 @@ void gpsb_host_channel_eph(const gps_ch_t* ch, gpsb_flat_eph* o)
     o->prn = d->prn; o->week_gst = d->week_gst; o->sub_cnt = d->sub_cnt; o->received_mask = d->received_mask;
     o->received_mask_proc = d->received_mask_proc; o->tow_gpst = d2u(d->tow_gpst);
 }
+
+/* observation pair of a channel as bit patterns, and a setter for the subframe time of week (test helpers) */
+void gpsb_host_channel_obs(const gps_ch_t* ch, uint64_t out2[2])
+{
+    out2[0] = d2u(ch->obs_data.pseudorange_m);
+    out2[1] = d2u(ch->obs_data.tow_s);
+}
+void gpsb_host_channel_set_tow(gps_ch_t* ch, double tow_gpst) { ch->eph_data.tow_gpst = tow_gpst; }
+
