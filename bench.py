@@ -8,11 +8,17 @@ collective): weak scaling, value = arm-samples of all ranks / max-over-ranks tim
 
   value        arm-samples/s of the closed loop with signal AND channel records already resident in HBM: one
                k_track_run launch per step (loop filters on the device), device-timed (CUDA events)
-  e2e          same metric through the reference-facing host library (gpsb_rx_track_run) with HOST buffers:
-               pinned signal upload, channel records H2D, records + per-ms sums + nav bits D2H inside the timed region
+  e2e          same metric through the reference-facing host library (gpsb_rx_track_stream) with HOST buffers:
+               the pinned signal is DMA-ed into the HBM ring in chunks while the loop launch is already tracking,
+               channel records H2D, records + per-ms sums + nav bits D2H, all inside the timed region
   roofline     k_track_run against the measured HBM peak (algorithmic bytes)
   cpu_baseline the unmodified reference C (oracle/_ref) on this box's host cores, same cells
-  cold_acq     secondary metric: 32 SV x 21 bins x 10 ms x 2046 phases full-sky sweep (configs[2])
+  streaming    config 5 shape: 32 channels from a host-resident stream through a ring shorter than the run
+  config1_batched  400 000 cells, one per ms of an 818-MB recording, in one k_epl_batch launch (prompt arm / three
+               arms), each against the HBM roofline, the reference C on a bounded sample beside it
+  batch_replay the closed loop's own 4000 cells replayed open loop in one launch
+  cold_acq     secondary metric: 32 SV x 21 bins x 10 ms x 2046 phases full-sky sweep (configs[2]), plus the
+               16368-phase grid (8 sub-byte shifts)
 
 `--impl reference` times the reference's own CPU path (oracle/_ref, else the oracle port) instead.
 """
