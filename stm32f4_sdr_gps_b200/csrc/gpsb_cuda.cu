@@ -533,6 +533,7 @@ struct gpsb_ctx {
     uint32_t* h_progress = nullptr;      // mapped pinned: millisecond each channel of the running loop has reached
     uint32_t* d_progress = nullptr;
     uint32_t stream_timeout_ms = 2000;
+    cudaEvent_t ev_reset = nullptr;
     bool loop_open = false;              // between gpsb_track_loop_begin and _end (call_lock held)
     struct {
         void* channels; void* aux; gpsb_loop_result* results; int16_t* iq_log; int8_t* nav_log;
@@ -711,6 +712,7 @@ int gpsb_create(gpsb_ctx** out, int device, uint32_t max_sv, uint32_t ring_ms)
         CU(cudaStreamCreateWithFlags(&c->rt_stream, cudaStreamNonBlocking));
     }
     CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&c->ev_reset, cudaEventDisableTiming));
     CU(cudaMalloc(&c->d_watermark, 64));
     CU(cudaMemset(c->d_watermark, 0, 64));
     CU(cudaMallocHost(&c->h_wm_ring, kWmSlots * sizeof(uint32_t)));
@@ -755,6 +757,7 @@ void gpsb_destroy(gpsb_ctx* c)
     if (c->h_cmd) cudaFreeHost((void*)c->h_cmd);
     if (c->d_l0) cudaFree(c->d_l0);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+    if (c->ev_reset) cudaEventDestroy(c->ev_reset);
     if (c->d_watermark) cudaFree(c->d_watermark);
     if (c->h_wm_ring) cudaFreeHost(c->h_wm_ring);
     if (c->h_progress) cudaFreeHost(c->h_progress);
@@ -1127,7 +1130,9 @@ int gpsb_stream_reset(gpsb_ctx* c, uint32_t ms_valid_upto)
     c->h_wm_ring[0] = ms_valid_upto;
     c->wm_next = 1;
     CU(cudaMemcpyAsync(c->d_watermark, &c->h_wm_ring[0], 4, cudaMemcpyHostToDevice, c->copy_stream));
-    CU(cudaStreamSynchronize(c->copy_stream));
+    // the loop launched next on the context stream must see this value: order the two streams on the device, not on the host
+    CU(cudaEventRecord(c->ev_reset, c->copy_stream));
+    CU(cudaStreamWaitEvent(c->stream, c->ev_reset, 0));
     for (int i = 0; i < 256; i++) c->h_progress[i] = ms_valid_upto;
     return GPSB_OK;
 }

@@ -335,10 +335,14 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
         }
         if (kProf && carrier_thr) c0 = clock64();
         __syncthreads();   // A: the six sums of millisecond m are complete
-        const bool more = m + 1 < n_ms && !(kStream && *(volatile int*)&sm.starved);
+        // `more`: the control threads plan a successor millisecond.  The workers only ask whether a successor frame
+        // exists (it has been fetched, so waiting for it and forming its phase 1 is harmless when the run is about to
+        // end for lack of LATER frames) - they do not read the starvation flag, which keeps it off their path.
+        const bool next_frame = m + 1 < n_ms;
+        const bool more = next_frame && !(kStream && !(worker || edge_warp) && *(volatile int*)&sm.starved);
         if (worker || edge_warp) {
             if (kProf) c0 = clock64();
-            if (more && (plain || edge)) {                  // phase 1 of millisecond m+1 as soon as its offsets exist
+            if (next_frame && (plain || edge)) {            // phase 1 of millisecond m+1 as soon as its offsets exist
                 mbar_wait(&sm.full[b ^ 1u], ((m + 1) >> 1) & 1u);
                 mbar_wait(&sm.offs_ready, m & 1u);
                 long long c1 = 0;
@@ -356,7 +360,7 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
             int16_t iq[6];
             load_sums(&sm.sums[b], iq);
             sm.sums[b ^ 1u] = make_uint4(0u, 0u, 0u, 0u);      // consumed one ms ago by everybody (barrier B), filled again after this B
-            if (more) consumed++;                               // the workers wait for frame m+1 this millisecond
+            if (next_frame) consumed++;                         // the workers wait for frame m+1 this millisecond
             const bool degenerate = lc_dll_is_degenerate(iq);   // 0/0 in the DLL: x86 and the GPU disagree on NaN bits, host finishes this ms
             if (degenerate) sm.stop = LC_STOP_DLL_NAN;
             else {
