@@ -203,6 +203,9 @@ int gpsb_track_loop_dev_ex(gpsb_ctx* ctx, uint32_t n_ch, void* d_channels, void*
 #define GPSB_LOOP_STREAMING 1u
 int gpsb_stream_reset(gpsb_ctx* ctx, uint32_t ms_valid_upto);
 int gpsb_stream_push(gpsb_ctx* ctx, uint32_t ms0, uint32_t n_ms, const uint8_t* packed);
+/* Same for the MAX2769-native 2-bit I / 2-bit Q container of gpsb_upload_signal_iq2 (one byte per sample, n * 16368
+ * bytes): copy and pack kernel run on the copy stream, then the watermark moves. */
+int gpsb_stream_push_iq2(gpsb_ctx* ctx, uint32_t ms0, uint32_t n_ms, const uint8_t* samples);
 int gpsb_stream_wait(gpsb_ctx* ctx);
 uint32_t gpsb_stream_progress(const gpsb_ctx* ctx, uint32_t n_ch);
 int gpsb_stream_set_timeout_ms(gpsb_ctx* ctx, uint32_t ms);

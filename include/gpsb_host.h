@@ -287,6 +287,9 @@ int gpsb_rx_track_run(gpsb_rx* rx, uint32_t ms0, uint32_t n_ms, int16_t* iq_log,
  * already running - the B200 form of the reference's capture double buffer, PM/signal_capture.c:57-123. */
 int gpsb_rx_track_stream(gpsb_rx* rx, uint32_t ms0, uint32_t n_ms, const uint8_t* packed, uint32_t chunk_ms,
                          int16_t* iq_log, int8_t* nav_log);
+/* Same, fed with the MAX2769-native 2-bit I / 2-bit Q container (one byte per sample, n_ms * 16368 bytes). */
+int gpsb_rx_track_stream_iq2(gpsb_rx* rx, uint32_t ms0, uint32_t n_ms, const uint8_t* samples, uint32_t chunk_ms,
+                             int16_t* iq_log, int8_t* nav_log);
 /* Where gpsb_rx_track_run keeps the loop filters.  AUTO (default) and DEVICE: the whole run is one launch of the
  * device-resident loop k_track_run (include/gpsb.h, gpsb_track_loop) for every channel that is tracking; its
  * float discriminators are the fdlibm atanf/atan2f glibc ships and CUDA's double atan2, checked against the host

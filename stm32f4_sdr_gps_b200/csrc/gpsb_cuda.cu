@@ -534,6 +534,8 @@ struct gpsb_ctx {
     uint32_t* d_progress = nullptr;
     uint32_t stream_timeout_ms = 2000;
     cudaEvent_t ev_reset = nullptr;
+    void* d_iq2 = nullptr;               // staging of gpsb_stream_push_iq2
+    size_t iq2_cap = 0;
     bool loop_open = false;              // between gpsb_track_loop_begin and _end (call_lock held)
     struct {
         void* channels; void* aux; gpsb_loop_result* results; int16_t* iq_log; int8_t* nav_log;
@@ -758,6 +760,7 @@ void gpsb_destroy(gpsb_ctx* c)
     if (c->d_l0) cudaFree(c->d_l0);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     if (c->ev_reset) cudaEventDestroy(c->ev_reset);
+    if (c->d_iq2) cudaFree(c->d_iq2);
     if (c->d_watermark) cudaFree(c->d_watermark);
     if (c->h_wm_ring) cudaFreeHost(c->h_wm_ring);
     if (c->h_progress) cudaFreeHost(c->h_progress);
@@ -1155,6 +1158,37 @@ int gpsb_stream_push(gpsb_ctx* c, uint32_t ms0, uint32_t n_ms, const uint8_t* pa
         CU(cudaMemcpy2DAsync((uint8_t*)c->d_signal, GPSB_FRAME_BYTES, packed + (size_t)first * GPSB_MS_BYTES, GPSB_MS_BYTES,
                              GPSB_MS_BYTES, n_ms - first, cudaMemcpyHostToDevice, c->copy_stream));
     // same stream: the frames have landed when the watermark moves
+    uint32_t* slot = &c->h_wm_ring[c->wm_next++];
+    *slot = ms0 + n_ms;
+    CU(cudaMemcpyAsync(c->d_watermark, slot, 4, cudaMemcpyHostToDevice, c->copy_stream));
+    return GPSB_OK;
+}
+
+int gpsb_stream_push_iq2(gpsb_ctx* c, uint32_t ms0, uint32_t n_ms, const uint8_t* samples)
+{
+    if (!c || !samples) return fail(GPSB_ERR_ARG, "gpsb_stream_push_iq2: null argument");
+    if (n_ms == 0) return GPSB_OK;
+    if (n_ms > c->ring_ms) return fail(GPSB_ERR_ARG, "n_ms %u exceeds ring capacity %u", n_ms, c->ring_ms);
+    CU(cudaSetDevice(c->device));
+    const size_t bytes = (size_t)n_ms * GPSB_MS_SAMPLES;
+    if (bytes + 64 > c->iq2_cap) {                       // staging for the byte-per-sample container, grown on demand
+        CU(cudaStreamSynchronize(c->copy_stream));
+        if (c->d_iq2) cudaFree(c->d_iq2);
+        c->d_iq2 = nullptr;
+        c->iq2_cap = 0;
+        CU(cudaMalloc(&c->d_iq2, bytes + 64));
+        c->iq2_cap = bytes + 64;
+    }
+    if (c->wm_next + 1 >= kWmSlots) {
+        CU(cudaStreamSynchronize(c->copy_stream));
+        c->wm_next = 0;
+    }
+    // one stream: the next push's copy into the staging buffer waits for this push's pack kernel
+    CU(cudaMemcpyAsync(c->d_iq2, samples, bytes, cudaMemcpyHostToDevice, c->copy_stream));
+    const uint32_t total = n_ms * kWords;
+    k_pack_iq2<<<(total + 255) / 256, 256, 0, c->copy_stream>>>((const uint4*)c->d_iq2, c->d_signal, ms0 % c->ring_ms, c->ring_ms, n_ms);
+    int rc = check_launch(c, "k_pack_iq2");
+    if (rc) return rc;
     uint32_t* slot = &c->h_wm_ring[c->wm_next++];
     *slot = ms0 + n_ms;
     CU(cudaMemcpyAsync(c->d_watermark, slot, 4, cudaMemcpyHostToDevice, c->copy_stream));

@@ -101,6 +101,7 @@ def load_library(path: Path | None = None) -> C.CDLL:
         "gpsb_track_loop_end": (i32, [vp]),
         "gpsb_stream_reset": (i32, [vp, u32]),
         "gpsb_stream_push": (i32, [vp, u32, u32, vp]),
+        "gpsb_stream_push_iq2": (i32, [vp, u32, u32, vp]),
         "gpsb_stream_wait": (i32, [vp]),
         "gpsb_stream_progress": (u32, [vp, u32]),
         "gpsb_stream_set_timeout_ms": (i32, [vp, u32]),

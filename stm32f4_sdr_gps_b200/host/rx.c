@@ -354,8 +354,36 @@ static int track_run_device(gpsb_rx* rx, uint32_t ms0, uint32_t n_ms, int16_t* i
  * device-resident loop is launched for the whole run, and the remaining chunks are DMA-ed into the ring while the
  * loop is already tracking (include/gpsb.h, "streaming ingest"): the upload disappears behind the run instead of
  * preceding it.  Falls back to upload-then-run when some channel is not tracking yet or the loops are on the host. */
+static int track_stream_impl(gpsb_rx* rx, uint32_t ms0, uint32_t n_ms, const uint8_t* packed, uint32_t chunk_ms,
+                             int16_t* iq_log, int8_t* nav_log, int iq2);
+
 int gpsb_rx_track_stream(gpsb_rx* rx, uint32_t ms0, uint32_t n_ms, const uint8_t* packed, uint32_t chunk_ms,
                          int16_t* iq_log, int8_t* nav_log)
+{
+    return track_stream_impl(rx, ms0, n_ms, packed, chunk_ms, iq_log, nav_log, 0);
+}
+
+/* The same run fed with the MAX2769-native 2-bit I / 2-bit Q container (one byte per sample, n_ms * 16368 bytes, bit 0 =
+ * I sign): every chunk is copied and packed to the 1-bit ring format on the copy stream (k_pack_iq2) behind the loop. */
+int gpsb_rx_track_stream_iq2(gpsb_rx* rx, uint32_t ms0, uint32_t n_ms, const uint8_t* samples, uint32_t chunk_ms,
+                             int16_t* iq_log, int8_t* nav_log)
+{
+    return track_stream_impl(rx, ms0, n_ms, samples, chunk_ms, iq_log, nav_log, 1);
+}
+
+static int push_chunk(gpsb_rx* rx, uint32_t ms, uint32_t n, const uint8_t* base, uint32_t at, int iq2)
+{
+    if (iq2) return gpsb_stream_push_iq2(rx->ctx, ms, n, base + (size_t)at * GPSB_MS_SAMPLES);
+    return gpsb_stream_push(rx->ctx, ms, n, base + (size_t)at * GPSB_MS_BYTES);
+}
+static int upload_span(gpsb_rx* rx, uint32_t ms, uint32_t n, const uint8_t* base, uint32_t at, int iq2)
+{
+    if (iq2) return gpsb_upload_signal_iq2(rx->ctx, ms, n, base + (size_t)at * GPSB_MS_SAMPLES);
+    return gpsb_upload_signal(rx->ctx, ms, n, base + (size_t)at * GPSB_MS_BYTES);
+}
+
+static int track_stream_impl(gpsb_rx* rx, uint32_t ms0, uint32_t n_ms, const uint8_t* packed, uint32_t chunk_ms,
+                             int16_t* iq_log, int8_t* nav_log, int iq2)
 {
     if (!rx || !packed) return GPSB_ERR_ARG;
     if (n_ms == 0) return GPSB_OK;
@@ -369,7 +397,7 @@ int gpsb_rx_track_stream(gpsb_rx* rx, uint32_t ms0, uint32_t n_ms, const uint8_t
         (n_ms > ring_ms && ring_ms < 192)) {        /* progress is reported every 64 ms: a smaller ring cannot be refilled behind the loop */
         for (uint32_t at = 0; at < n_ms;) {         /* upload a ring-full, run it, repeat */
             const uint32_t n = n_ms - at < ring_ms ? n_ms - at : ring_ms;
-            int rc = gpsb_upload_signal(rx->ctx, ms0 + at, n, packed + (size_t)at * GPSB_MS_BYTES);
+            int rc = upload_span(rx, ms0 + at, n, packed, at, iq2);
             if (rc != GPSB_OK) return hx_note(rc);
             rc = gpsb_rx_track_run(rx, ms0 + at, n, iq_log ? iq_log + (size_t)at * n_ch * 6 : NULL,
                                    nav_log ? nav_log + (size_t)at * n_ch : NULL);
@@ -380,7 +408,7 @@ int gpsb_rx_track_stream(gpsb_rx* rx, uint32_t ms0, uint32_t n_ms, const uint8_t
     }
     int rc = gpsb_stream_reset(rx->ctx, ms0);
     uint32_t sent = n_ms < chunk_ms ? n_ms : chunk_ms;
-    if (rc == GPSB_OK) rc = gpsb_stream_push(rx->ctx, ms0, sent, packed);
+    if (rc == GPSB_OK) rc = push_chunk(rx, ms0, sent, packed, 0, iq2);
     if (rc != GPSB_OK) return hx_note(rc);
     rc = gpsb_track_loop_begin(rx->ctx, n_ch, rx->ch, (uint32_t)sizeof(gps_ch_t), rx->aux, (uint32_t)sizeof(gpsb_aux), ms0, n_ms,
                                iq_log, nav_log, rx->loop_res, GPSB_LOOP_STREAMING);
@@ -392,7 +420,7 @@ int gpsb_rx_track_stream(gpsb_rx* rx, uint32_t ms0, uint32_t n_ms, const uint8_t
         while (sent + n > ring_ms && (int32_t)(gpsb_stream_progress(rx->ctx, n_ch) - (ms0 + sent + n - ring_ms)) < 0 &&
                gpsb_stream_loop_running(rx->ctx))
             sched_yield();
-        rc_push = gpsb_stream_push(rx->ctx, ms0 + sent, n, packed + (size_t)sent * GPSB_MS_BYTES);
+        rc_push = push_chunk(rx, ms0 + sent, n, packed, sent, iq2);
         sent += n;
     }
     rc = gpsb_track_loop_end(rx->ctx);        /* a failed push starves the loop, which then ends by its time-out */
@@ -416,7 +444,7 @@ int gpsb_rx_track_stream(gpsb_rx* rx, uint32_t ms0, uint32_t n_ms, const uint8_t
             uint32_t at = r->done_ms;                              /* first millisecond still to do for this channel */
             while (at < n_ms) {
                 const uint32_t n = n_ms - at < ring_ms ? n_ms - at : ring_ms;
-                rc = gpsb_upload_signal(rx->ctx, ms0 + at, n, packed + (size_t)at * GPSB_MS_BYTES);
+                rc = upload_span(rx, ms0 + at, n, packed, at, iq2);
                 if (rc != GPSB_OK) return hx_note(rc);
                 if (at == r->done_ms && r->stop == LC_STOP_DLL_NAN) {
                     gpsb_host_set_packet_cnt(ms0 + at);

@@ -114,6 +114,7 @@ def load_host_library(path: Path | None = None) -> C.CDLL:
         "gpsb_rx_create": (i32, [C.POINTER(vp), vp, vp, u32]), "gpsb_rx_destroy": (None, [vp]),
         "gpsb_rx_track_ms": (i32, [vp, u32]), "gpsb_rx_track_run": (i32, [vp, u32, u32, vp, vp]),
         "gpsb_rx_track_stream": (i32, [vp, u32, u32, vp, u32, vp, vp]),
+        "gpsb_rx_track_stream_iq2": (i32, [vp, u32, u32, vp, u32, vp, vp]),
         "gpsb_rx_acquire_ms": (i32, [vp, u32]),
         "gpsb_rx_set_threads": (None, [vp, u32]),
         "gpsb_rx_set_loop_site": (None, [vp, i32]),
@@ -195,6 +196,17 @@ class Receiver:
         nav = np.zeros((n_ms, n), np.int8) if log else None
         self._check(self.lib.gpsb_rx_track_run(self._rx, ms0, n_ms, iq.ctypes.data if log else None,
                                                nav.ctypes.data if log else None))
+        return iq, nav
+
+    def track_stream_iq2(self, ms0: int, samples: np.ndarray, chunk_ms: int = 0, log: bool = True):
+        """gpsb_rx_track_stream_iq2: the 2-bit I/Q container (one byte per sample) streamed and packed behind the loop."""
+        samples = np.ascontiguousarray(samples, dtype=np.uint8)
+        n_ms = samples.size // 16368
+        n = self.channels.n
+        iq = np.zeros((n_ms, n, 6), np.int16) if log else None
+        nav = np.zeros((n_ms, n), np.int8) if log else None
+        self._check(self.lib.gpsb_rx_track_stream_iq2(self._rx, ms0, n_ms, samples.ctypes.data, chunk_ms,
+                                                      iq.ctypes.data if log else None, nav.ctypes.data if log else None))
         return iq, nav
 
     def track_stream(self, ms0: int, packed: np.ndarray, chunk_ms: int = 0, log: bool = True):

@@ -297,3 +297,31 @@ def test_device_loop_decodes_subframes_like_the_reference(host_engine, reference
     assert got.sub_cnt == 2 and got.received_mask == 3 and got.sat == 5      # both subframes went through the decode
     rx.close()
     ch.free()
+
+
+@pytest.mark.parametrize("ring_ms,chunk", [(1024, 0), (256, 48)])
+def test_streaming_run_from_the_2bit_iq_container(golden, ring_ms, chunk):
+    """gpsb_rx_track_stream_iq2: the recording arrives as MAX2769-native 2-bit I / 2-bit Q samples (one byte each, only
+    the I sign carries signal); every chunk is copied and packed to the ring format on the copy stream behind the
+    running loop.  Same sums, nav bits and records as the packed recording - also through a ring shorter than the run."""
+    from stm32f4_sdr_gps_b200 import Engine
+    from stm32f4_sdr_gps_b200.signal_synth import iq2_from_packed
+    sig = np.ascontiguousarray(golden["scene_signal"][:600])
+    samples = iq2_from_packed(sig)
+    with Engine(device=0, max_sv=211, ring_ms=1024) as eng:
+        eng.upload_signal(0, sig)
+        ch = _two_locked_channels(golden)
+        rx = Receiver(eng, ch)
+        want_iq, want_nav = rx.track_run(0, 600)
+        want_rec = [bytes(ch.snapshot(i)) for i in range(2)]
+        rx.close()
+        ch.free()
+    with Engine(device=0, max_sv=211, ring_ms=ring_ms) as eng:
+        ch = _two_locked_channels(golden)
+        rx = Receiver(eng, ch)
+        iq, nav = rx.track_stream_iq2(0, samples, chunk_ms=chunk)
+        assert np.array_equal(iq, want_iq) and np.array_equal(nav, want_nav)
+        assert [bytes(ch.snapshot(i)) for i in range(2)] == want_rec
+        assert rx.loop_stats() == (2 * 600, 0)
+        rx.close()
+        ch.free()
