@@ -263,10 +263,12 @@ int gpsb_sweep(gpsb_ctx* ctx, const uint32_t* sv_slots, uint32_t n_sv, const uin
  * direct correlator or ... chosen by measurement"):
  *   GPSB_SWEEP_DIRECT  XOR + POPC per 32 samples for every offset (POPC-pipe bound)
  *   GPSB_SWEEP_DP4A    per-byte popcounts once per millisecond, then a +-1-chip x small-integer circular
- *                      correlation on the integer dot-product pipe (default; about 8x fewer issue slots)
+ *                      correlation on the integer dot-product pipe (default; about 8x fewer issue slots); one
+ *                      256-thread CTA per offset parity, two per SM, so epilogues overlap main loops
  * Applies to gpsb_sweep / gpsb_sweep_dev and to gpsb_search requests whose window is >= 384 offsets. */
 #define GPSB_SWEEP_DIRECT 0
 #define GPSB_SWEEP_DP4A   1
+#define GPSB_SWEEP_DP4A_FULL 2     /* the dp4a search with one 512-thread CTA per cell group (kept for comparison) */
 int gpsb_set_sweep_method(gpsb_ctx* ctx, int method);
 
 /* ---- device-resident variants: request / result arrays already in device memory, enqueued on the

@@ -19,6 +19,11 @@
  *   - odd offsets 2k+1 skip replica words 1022-k and 1022 (gps_misc.c:59-89)
  *   - data bytes 2044..2045 are never mixed and stay 0 (gps_misc.c:229)
  *
+ * Default form (kHalf): one CTA of 256 threads = one mixed millisecond x up to NSV satellites x the 1023 offsets of ONE
+ * parity; two CTAs per SM, so that while one is in its epilogue (the IEEE-sqrt detector of 4 x NSV results per thread,
+ * an eighth of a CTA's time, during which the dot-product pipe would idle) the other is in its main loop.  The two
+ * parities of a cell meet in a small global scratch record (atomic max / add); the CTA that arrives second writes the
+ * reference's triple.  The undivided form is kept below for comparison:
  * One CTA = one mixed millisecond (ms, NCO phase/step, b) x up to NSV satellites x all 2046 offsets.
  * 512 threads; thread (parity, q) owns offsets 2*(4q+r)+parity, r = 0..3, for every satellite of the
  * tile: NSV x 4 x {I,Q} accumulators fed by two 16-byte shared loads (I and Q, four byte-shifted
@@ -44,12 +49,20 @@ struct AcqGroup {                      // one mixed millisecond and the satellit
     uint32_t res_index[8];
 };
 
-template <int NSV>
+struct AcqScratch {                    // where the two parity halves of a cell meet (zeroed before the launch)
+    unsigned key;
+    int total;
+    unsigned arrived;
+    unsigned pad;
+};
+
+template <int NSV, bool kHalf = false>
 struct AcqSmem {
-    uint4 xv[4][kXvLen];               // [iq*2+parity][a] = H bytes 4a+r .. 4a+r+3 for r = 0..3
+    static constexpr int kPar = kHalf ? 1 : 2;   // parities handled by one CTA
+    uint4 xv[2 * kPar][kXvLen];        // [iq*kPar+parity][a] = H bytes 4a+r .. 4a+r+3 for r = 0..3
     uint32_t S[kChipSteps][NSV];       // int8x4: +1 for chip 0, -1 for chip 1, 0 beyond chip 1021
     uint32_t bits[2][kBitWords];       // mixed I / Q sample bits
-    uint8_t ext[4][kExtBytes];         // H values, parity-split, two periods
+    uint8_t ext[2 * kPar][kExtBytes];  // H values, parity-split, two periods
     uint32_t chipbits[NSV][32];        // chips as a bitmap (bit c of the stream = chip c)
     int ones[NSV];                     // number of 1-chips among chips 0..1021
     unsigned key[NSV];
@@ -70,21 +83,26 @@ __device__ __forceinline__ uint32_t replica16(const uint32_t* __restrict__ cb, i
     return ((cur << b) | (prev >> (16u - b))) & 0xFFFFu;
 }
 
-template <int NSV, bool kSweep>
-__global__ void __launch_bounds__(kAcqThreads, 1)
+template <int NSV, bool kSweep, bool kHalf = false>
+__global__ void __launch_bounds__(kHalf ? kAcqThreads / 2 : kAcqThreads, kHalf ? 2 : 1)
 k_acq_dp4a(const AcqGroup* __restrict__ groups, SweepParams sp, uint32_t n_sv_total,
            gpsb_search_res* __restrict__ res, const uint32_t* __restrict__ codes,
-           const uint32_t* __restrict__ schips, const uint32_t* __restrict__ signal, uint32_t ring_ms)
+           const uint32_t* __restrict__ schips, const uint32_t* __restrict__ signal, uint32_t ring_ms,
+           AcqScratch* __restrict__ scratch)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    AcqSmem<NSV>& s = *reinterpret_cast<AcqSmem<NSV>*>(smem_raw);
+    AcqSmem<NSV, kHalf>& s = *reinterpret_cast<AcqSmem<NSV, kHalf>*>(smem_raw);
+    constexpr int kThreads = kHalf ? kAcqThreads / 2 : kAcqThreads;
+    constexpr int kPar = kHalf ? 1 : 2;
     const int tid = threadIdx.x;
+    const uint32_t group_id = kHalf ? blockIdx.x >> 1 : blockIdx.x;
+    const int my_par = kHalf ? (int)(blockIdx.x & 1u) : 0;     // the parity this CTA owns (kHalf)
 
     // ---- which cells
     __shared__ AcqGroup g;
     if (tid == 0) {
-        if (kSweep) {   // blockIdx.x = (bin, ms) cell group; blockIdx.y = satellite tile
-            const uint32_t m = blockIdx.x % sp.n_ms, b = blockIdx.x / sp.n_ms;
+        if (kSweep) {   // group_id = (bin, ms) cell group; blockIdx.y = satellite tile
+            const uint32_t m = group_id % sp.n_ms, b = group_id / sp.n_ms;
             g.ms_index = sp.ms0 + m;
             g.acc0 = 0;
             g.step32 = sp.step32[b];
@@ -99,7 +117,7 @@ k_acq_dp4a(const AcqGroup* __restrict__ groups, SweepParams sp, uint32_t n_sv_to
                 g.res_index[v] = ((v0 + v) * sp.n_bins + b) * sp.n_ms + m;
             }
         } else {
-            g = groups[blockIdx.x];
+            g = groups[group_id];
         }
     }
     __syncthreads();
@@ -109,17 +127,17 @@ k_acq_dp4a(const AcqGroup* __restrict__ groups, SweepParams sp, uint32_t n_sv_to
     // ---- stage: mixed bit streams (closed-form NCO, gps_misc.c:229-239), chips, +-1 chip bytes
     {
         const uint32_t* frame = signal + (size_t)(g.ms_index % ring_ms) * kWords;
-        for (int w = tid; w < kMixWords; w += kAcqThreads) {
+        for (int w = tid; w < kMixWords; w += kThreads) {
             const uint32_t sg = __ldg(frame + w);
             const uint32_t ph = (g.acc0 + (uint32_t)w * g.step32) >> 30;
             s.bits[0][w] = cos_pattern(ph) ^ sg;
             s.bits[1][w] = sin_pattern(ph) ^ sg;
         }
-        for (int i = tid; i < kChipSteps * NSV; i += kAcqThreads) {
+        for (int i = tid; i < kChipSteps * NSV; i += kThreads) {
             const int k4 = i / NSV, v = i % NSV;
             s.S[k4][v] = v < n_sv ? __ldg(schips + (size_t)g.sv_slot[v] * kChipSteps + k4) : 0u;
         }
-        for (int i = tid; i < NSV * 32; i += kAcqThreads) {
+        for (int i = tid; i < NSV * 32; i += kThreads) {
             const int v = i >> 5, w = i & 31;
             uint32_t m = 0;
             if (v < n_sv) {   // E[x] = chip 2x in the low half, chip 2x+1 in the high half
@@ -159,16 +177,18 @@ k_acq_dp4a(const AcqGroup* __restrict__ groups, SweepParams sp, uint32_t n_sv_to
     __syncthreads();
 
     // ---- H[p] = popcount of the 16 data bits under a chip starting at byte p (+ b bits)
-    for (int i = tid; i < 2 * (int)GPSB_OFFSETS; i += kAcqThreads) {
-        const int iq = i >= (int)GPSB_OFFSETS, p = i - iq * (int)GPSB_OFFSETS;
+    for (int i = tid; i < kPar * (int)GPSB_OFFSETS; i += kThreads) {
+        // full form: every byte position p of both streams; half form: only the positions of this CTA's parity
+        const int iq = i >= kPar * 1023, k = i - iq * kPar * 1023;
+        const int p = kHalf ? 2 * k + my_par : k;
         const uint8_t h = (uint8_t)__popc(win16(s.bits[iq], 8u * p + bsh));
-        uint8_t* e = s.ext[iq * 2 + (p & 1)];
+        uint8_t* e = s.ext[kHalf ? iq : iq * 2 + (p & 1)];
         e[p >> 1] = h;
         e[(p >> 1) + 1023] = h;
     }
-    if (tid < 4 * (kExtBytes - 2046)) s.ext[tid / (kExtBytes - 2046)][2046 + tid % (kExtBytes - 2046)] = 0;
+    if (tid < 2 * kPar * (kExtBytes - 2046)) s.ext[tid / (kExtBytes - 2046)][2046 + tid % (kExtBytes - 2046)] = 0;
     __syncthreads();
-    for (int i = tid; i < 4 * (kXvLen - 1); i += kAcqThreads) {
+    for (int i = tid; i < 2 * kPar * (kXvLen - 1); i += kThreads) {
         const int arr = i / (kXvLen - 1), a = i % (kXvLen - 1);
         const uint32_t* e32 = reinterpret_cast<const uint32_t*>(s.ext[arr]);
         const uint32_t lo = e32[a], hi = e32[a + 1];
@@ -178,15 +198,15 @@ k_acq_dp4a(const AcqGroup* __restrict__ groups, SweepParams sp, uint32_t n_sv_to
     __syncthreads();
 
     // ---- main loop: 4 chips per step
-    const int q = tid & 255, par = tid >> 8;
+    const int q = tid & 255, par = kHalf ? my_par : tid >> 8;
     int accI[NSV][4], accQ[NSV][4];
 #pragma unroll
     for (int v = 0; v < NSV; v++)
 #pragma unroll
         for (int r = 0; r < 4; r++) accI[v][r] = accQ[v][r] = 0;
     {
-        const uint4* __restrict__ xi = s.xv[par] + q;
-        const uint4* __restrict__ xq = s.xv[2 + par] + q;
+        const uint4* __restrict__ xi = s.xv[kHalf ? 0 : par] + q;
+        const uint4* __restrict__ xq = s.xv[kHalf ? 1 : 2 + par] + q;
 #pragma unroll 2
         for (int k4 = 0; k4 < kChipSteps; k4++) {
             const uint4 hi = xi[k4], hq = xq[k4];
@@ -278,11 +298,23 @@ k_acq_dp4a(const AcqGroup* __restrict__ groups, SweepParams sp, uint32_t n_sv_to
     }
     __syncthreads();
     if (tid < n_sv) {
-        const unsigned k = s.key[tid];
+        unsigned k = s.key[tid];
+        int total = s.total[tid];
+        if (kHalf) {
+            // the other parity of this cell is another CTA's: meet in the scratch record, the second to arrive finishes
+            AcqScratch* sc = scratch + g.res_index[tid];
+            atomicMax(&sc->key, k);
+            atomicAdd(&sc->total, total);
+            __threadfence();
+            if (atomicAdd(&sc->arrived, 1u) == 0u) return;
+            __threadfence();
+            k = atomicMax(&sc->key, 0u);
+            total = atomicAdd(&sc->total, 0);
+        }
         gpsb_search_res o;
         o.max = (uint16_t)(k >> 16);
         o.phase = k ? (uint16_t)(0xFFFFu - (k & 0xFFFFu)) : 0;
-        o.avg = (uint16_t)(s.total[tid] / (2 * (int)GPSB_CHIPS));
+        o.avg = (uint16_t)(total / (2 * (int)GPSB_CHIPS));
         o.reserved = 0;
         res[g.res_index[tid]] = o;
     }

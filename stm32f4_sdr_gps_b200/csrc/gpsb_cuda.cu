@@ -534,6 +534,8 @@ struct gpsb_ctx {
     uint32_t* d_progress = nullptr;
     uint32_t stream_timeout_ms = 2000;
     cudaEvent_t ev_reset = nullptr;
+    AcqScratch* d_acq_scratch = nullptr; // where the two parity halves of a dp4a search cell meet
+    size_t acq_scratch_cap = 0;          // records
     void* d_iq2 = nullptr;               // staging of gpsb_stream_push_iq2
     size_t iq2_cap = 0;
     bool loop_open = false;              // between gpsb_track_loop_begin and _end (call_lock held)
@@ -651,6 +653,42 @@ static int session_exchange(gpsb_ctx* c, uint32_t n, const gpsb_epl_req* req, in
     return GPSB_OK;
 }
 
+// Scratch records of the parity-split dp4a search, zeroed on the stream ahead of the launch that uses them.
+static int acq_scratch(gpsb_ctx* c, size_t n_results)
+{
+    if (n_results > c->acq_scratch_cap) {
+        size_t cap = c->acq_scratch_cap ? c->acq_scratch_cap : 8192;
+        while (cap < n_results) cap *= 2;
+        CU(cudaStreamSynchronize(c->stream));
+        if (c->d_acq_scratch) cudaFree(c->d_acq_scratch);
+        c->d_acq_scratch = nullptr;
+        c->acq_scratch_cap = 0;
+        CU(cudaMalloc(&c->d_acq_scratch, cap * sizeof(AcqScratch)));
+        c->acq_scratch_cap = cap;
+    }
+    CU(cudaMemsetAsync(c->d_acq_scratch, 0, n_results * sizeof(AcqScratch), c->stream));
+    return GPSB_OK;
+}
+
+// One launch of the byte-popcount / dp4a search: parity-split form (two 256-thread CTAs per cell group and per SM) by
+// default, the undivided 512-thread form with GPSB_SWEEP_DP4A_FULL.  n_results = size of the result array.
+template <int NSV, bool kSweep>
+static int launch_acq(gpsb_ctx* c, dim3 grid, const AcqGroup* dg, SweepParams sp, uint32_t n_sv, gpsb_search_res* d_res,
+                      size_t n_results)
+{
+    if (c->sweep_method == GPSB_SWEEP_DP4A_FULL) {
+        k_acq_dp4a<NSV, kSweep, false><<<grid, kAcqThreads, sizeof(AcqSmem<NSV, false>), c->stream>>>(
+            dg, sp, n_sv, d_res, c->d_codes, c->d_schips, c->d_signal, c->ring_ms, nullptr);
+        return check_launch(c, "k_acq_dp4a(full)");
+    }
+    int rc = acq_scratch(c, n_results);
+    if (rc) return rc;
+    grid.x *= 2;                                           // blockIdx.x & 1 = parity
+    k_acq_dp4a<NSV, kSweep, true><<<grid, kAcqThreads / 2, sizeof(AcqSmem<NSV, true>), c->stream>>>(
+        dg, sp, n_sv, d_res, c->d_codes, c->d_schips, c->d_signal, c->ring_ms, c->d_acq_scratch);
+    return check_launch(c, "k_acq_dp4a");
+}
+
 extern "C" {
 
 uint32_t gpsb_abi_version(void) { return 1u; }
@@ -691,12 +729,11 @@ int gpsb_create(gpsb_ctx** out, int device, uint32_t max_sv, uint32_t ring_ms)
     CU(cudaMemset(c->d_rxt, 0, (size_t)max_sv * kRxtShifts * kRxtCopies * kRxtWords * 4));
     CU(cudaMalloc(&c->d_schips, (size_t)max_sv * kChipSteps * 4));
     CU(cudaMemset(c->d_schips, 0, (size_t)max_sv * kChipSteps * 4));
-    CU(cudaFuncSetAttribute(k_acq_dp4a<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AcqSmem<8>)));
-    CU(cudaFuncSetAttribute(k_acq_dp4a<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AcqSmem<8>)));
-    CU(cudaFuncSetAttribute(k_acq_dp4a<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AcqSmem<4>)));
-    CU(cudaFuncSetAttribute(k_acq_dp4a<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AcqSmem<4>)));
-    CU(cudaFuncSetAttribute(k_acq_dp4a<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AcqSmem<1>)));
-    CU(cudaFuncSetAttribute(k_acq_dp4a<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AcqSmem<1>)));
+#define GPSB_ACQ_ATTR(N, SW)                                                                                                      \
+    CU(cudaFuncSetAttribute(k_acq_dp4a<N, SW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AcqSmem<N, false>))); \
+    CU(cudaFuncSetAttribute(k_acq_dp4a<N, SW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AcqSmem<N, true>)));
+    GPSB_ACQ_ATTR(8, true) GPSB_ACQ_ATTR(8, false) GPSB_ACQ_ATTR(4, true) GPSB_ACQ_ATTR(4, false) GPSB_ACQ_ATTR(1, true) GPSB_ACQ_ATTR(1, false)
+#undef GPSB_ACQ_ATTR
     CU(cudaMalloc(&c->d_signal, (size_t)ring_ms * GPSB_FRAME_BYTES));
     CU(cudaMemset(c->d_signal, 0, (size_t)ring_ms * GPSB_FRAME_BYTES));
     CU(cudaMalloc(&c->d_chips, 1024));
@@ -761,6 +798,7 @@ void gpsb_destroy(gpsb_ctx* c)
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     if (c->ev_reset) cudaEventDestroy(c->ev_reset);
     if (c->d_iq2) cudaFree(c->d_iq2);
+    if (c->d_acq_scratch) cudaFree(c->d_acq_scratch);
     if (c->d_watermark) cudaFree(c->d_watermark);
     if (c->h_wm_ring) cudaFreeHost(c->h_wm_ring);
     if (c->h_progress) cudaFreeHost(c->h_progress);
@@ -1174,6 +1212,7 @@ int gpsb_stream_push_iq2(gpsb_ctx* c, uint32_t ms0, uint32_t n_ms, const uint8_t
     if (bytes + 64 > c->iq2_cap) {                       // staging for the byte-per-sample container, grown on demand
         CU(cudaStreamSynchronize(c->copy_stream));
         if (c->d_iq2) cudaFree(c->d_iq2);
+    if (c->d_acq_scratch) cudaFree(c->d_acq_scratch);
         c->d_iq2 = nullptr;
         c->iq2_cap = 0;
         CU(cudaMalloc(&c->d_iq2, bytes + 64));
@@ -1362,7 +1401,7 @@ int gpsb_search(gpsb_ctx* c, uint32_t n, const gpsb_search_req* req, gpsb_search
     for (uint32_t i = 0; i < n; i++) {
         const gpsb_search_req& r = req[i];
         if (r.start >= r.stop) continue;
-        const bool wide = c->sweep_method == GPSB_SWEEP_DP4A && (uint32_t)(r.stop - r.start) >= kWideWindow;
+        const bool wide = c->sweep_method != GPSB_SWEEP_DIRECT && (uint32_t)(r.stop - r.start) >= kWideWindow;
         if (!wide) {
             h_req[n_direct] = r;
             h_map[n_direct++] = i;
@@ -1399,16 +1438,9 @@ int gpsb_search(gpsb_ctx* c, uint32_t n, const gpsb_search_req* req, gpsb_search
     if (n_grp) {
         SweepParams sp = {};
         const AcqGroup* dg = (const AcqGroup*)(d + grp_off);
-        if (max_in_group > 4)
-            k_acq_dp4a<8, false><<<n_grp, kAcqThreads, sizeof(AcqSmem<8>), c->stream>>>(
-                dg, sp, 0, d_res, c->d_codes, c->d_schips, c->d_signal, c->ring_ms);
-        else if (max_in_group > 1)
-            k_acq_dp4a<4, false><<<n_grp, kAcqThreads, sizeof(AcqSmem<4>), c->stream>>>(
-                dg, sp, 0, d_res, c->d_codes, c->d_schips, c->d_signal, c->ring_ms);
-        else
-            k_acq_dp4a<1, false><<<n_grp, kAcqThreads, sizeof(AcqSmem<1>), c->stream>>>(
-                dg, sp, 0, d_res, c->d_codes, c->d_schips, c->d_signal, c->ring_ms);
-        rc = check_launch(c, "k_acq_dp4a");
+        if (max_in_group > 4) rc = launch_acq<8, false>(c, dim3(n_grp), dg, sp, 0, d_res, n);
+        else if (max_in_group > 1) rc = launch_acq<4, false>(c, dim3(n_grp), dg, sp, 0, d_res, n);
+        else rc = launch_acq<1, false>(c, dim3(n_grp), dg, sp, 0, d_res, n);
         if (rc) return rc;
     }
     CU(cudaMemcpyAsync(h + res_off, d + res_off, res_b, cudaMemcpyDeviceToHost, c->stream));
@@ -1486,7 +1518,8 @@ int gpsb_set_realtime(gpsb_ctx* c, int enabled)
 int gpsb_set_sweep_method(gpsb_ctx* c, int method)
 {
     if (!c) return fail(GPSB_ERR_ARG, "null context");
-    if (method != GPSB_SWEEP_DIRECT && method != GPSB_SWEEP_DP4A) return fail(GPSB_ERR_ARG, "unknown sweep method %d", method);
+    if (method != GPSB_SWEEP_DIRECT && method != GPSB_SWEEP_DP4A && method != GPSB_SWEEP_DP4A_FULL)
+        return fail(GPSB_ERR_ARG, "unknown sweep method %d", method);
     c->sweep_method = method;
     return GPSB_OK;
 }
@@ -1532,22 +1565,11 @@ int gpsb_sweep_dev(gpsb_ctx* c, const uint32_t* d_sv_slots, uint32_t n_sv, const
                                                                         c->d_codes, c->d_signal, c->ring_ms);
         return check_launch(c, "k_search(sweep)");
     }
-    // byte-popcount / dp4a search: one CTA per (bin, ms) x tile of up to 8 satellites
+    // byte-popcount / dp4a search: per (bin, ms) x tile of up to 8 satellites one CTA per offset parity
     const uint32_t groups = n_bins * n_ms;
-    if (n_sv > 4) {
-        dim3 grid(groups, (n_sv + 7) / 8);
-        k_acq_dp4a<8, true><<<grid, kAcqThreads, sizeof(AcqSmem<8>), c->stream>>>(
-            nullptr, sp, n_sv, d_res, c->d_codes, c->d_schips, c->d_signal, c->ring_ms);
-    } else if (n_sv > 1) {
-        dim3 grid(groups, 1);
-        k_acq_dp4a<4, true><<<grid, kAcqThreads, sizeof(AcqSmem<4>), c->stream>>>(
-            nullptr, sp, n_sv, d_res, c->d_codes, c->d_schips, c->d_signal, c->ring_ms);
-    } else {
-        dim3 grid(groups, 1);
-        k_acq_dp4a<1, true><<<grid, kAcqThreads, sizeof(AcqSmem<1>), c->stream>>>(
-            nullptr, sp, n_sv, d_res, c->d_codes, c->d_schips, c->d_signal, c->ring_ms);
-    }
-    return check_launch(c, "k_acq_dp4a(sweep)");
+    if (n_sv > 4) return launch_acq<8, true>(c, dim3(groups, (n_sv + 7) / 8), nullptr, sp, n_sv, d_res, (size_t)cells);
+    if (n_sv > 1) return launch_acq<4, true>(c, dim3(groups, 1), nullptr, sp, n_sv, d_res, (size_t)cells);
+    return launch_acq<1, true>(c, dim3(groups, 1), nullptr, sp, n_sv, d_res, (size_t)cells);
 }
 
 int gpsb_sweep(gpsb_ctx* c, const uint32_t* sv_slots, uint32_t n_sv, const uint32_t* step32, uint32_t n_bins,
