@@ -540,6 +540,24 @@ def run_gpu_arm(args) -> None:
         long_ms[arms] = float(np.mean([a.elapsed_time(b) for a, b in ev]))
         if arms == 1:
             long_prompt = d_out_long.cpu().numpy()[:2 * n_long].reshape(n_long, 2).copy()
+    # config 1 as the reference runs it: ONE cell.  Kernel time of a one-cell launch (events) and the latency of the
+    # synchronous host call gpsb_prompt_iq (request up, launch, result down).
+    ev = events(50)
+    for k in range(50):
+        ev[k][0].record(stream)
+        long_eng.prompt_iq_dev(1, d_rq_long.data_ptr(), d_out_long.data_ptr())
+        ev[k][1].record(stream)
+    barrier()
+    one_cell_kernel_us = float(np.median([a.elapsed_time(b) for a, b in ev][10:])) * 1e3
+    t_one = []
+    for k in range(60):
+        t0 = time.perf_counter()
+        one = long_eng.prompt_iq(rq_long[:1])
+        t_one.append(time.perf_counter() - t0)
+    one_cell_call_us = float(np.median(t_one[10:])) * 1e6
+    assert np.array_equal(one[0], long_prompt[0])
+    for _ in range(2):                      # restore the full three-arm result for the comparison below
+        long_eng.track_epl_dev(n_long, d_rq_long.data_ptr(), d_out_long.data_ptr())
     long_epl = d_out_long.cpu().numpy().reshape(n_long, 6)
     assert np.array_equal(long_epl[:, 2:4], long_prompt), "prompt-only and E/P/L forms of k_epl_batch disagree"
     long_eng.close()
@@ -703,6 +721,9 @@ def run_gpu_arm(args) -> None:
                         "(%.0f MB, larger than L2) in ONE k_epl_batch launch per rank; 'epl' = all three arms of the same cells"
                         % (n_long, n_long * 2048 / 1e6),
                 "cells": n_long * world,
+                "single_cell": {"what": "one cell, as the reference runs config 1", "kernel_us": one_cell_kernel_us,
+                                "host_call_us": one_cell_call_us,
+                                "api": "gpsb_prompt_iq(n = 1): request H2D, k_epl_batch<1> launch, result D2H, synchronous"},
                 "prompt": {"kernel_ms": long1_ms, "cells_per_s": n_long * world / (long1_ms * 1e-3),
                            "arm_samples_per_s": n_long * world * MS_SAMPLES / (long1_ms * 1e-3),
                            "roofline": {"kernel": "k_epl_batch<1>", "bound": "hbm",
