@@ -407,7 +407,9 @@ static int track_stream_impl(gpsb_rx* rx, uint32_t ms0, uint32_t n_ms, const uin
         return GPSB_OK;
     }
     int rc = gpsb_stream_reset(rx->ctx, ms0);
-    uint32_t sent = n_ms < chunk_ms ? n_ms : chunk_ms;
+    /* a short first chunk, so that the loop starts at once; the chunks behind it are as long as asked for */
+    const uint32_t first_ms = chunk_ms < 16 ? chunk_ms : 16;
+    uint32_t sent = n_ms < first_ms ? n_ms : first_ms;
     if (rc == GPSB_OK) rc = push_chunk(rx, ms0, sent, packed, 0, iq2);
     if (rc != GPSB_OK) return hx_note(rc);
     rc = gpsb_track_loop_begin(rx->ctx, n_ch, rx->ch, (uint32_t)sizeof(gps_ch_t), rx->aux, (uint32_t)sizeof(gpsb_aux), ms0, n_ms,
