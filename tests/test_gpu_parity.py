@@ -434,3 +434,37 @@ def test_epl_batch_kernel_vs_oracle_and_cta_kernel(engine, oracle):
                                    int(rq["off_p"][i]), int(rq["off_l"][i]), int(rq["off_bits"][i]))
         assert np.array_equal(out[i], want), (i, rq[i])
     assert engine.prompt_iq(np.zeros(0, EPL_REQ)).shape == (0, 2)
+
+
+def test_epl_batch_full_size_properties(oracle):
+    """k_epl_batch at the size of SURVEY.md section 8(d) config 1 'batched' (10^5 cells, one per millisecond of a 205-MB
+    recording), through size-independent properties: the prompt-only form equals the prompt arm of the three-arm
+    form; the result of a request does not depend on where in the batch it stands (a permuted batch gives the
+    permuted results); cells drawn at random equal the oracle; every sum lies in the range a popcount can produce."""
+    from stm32f4_sdr_gps_b200 import Engine
+    n = 100_000
+    rng = np.random.default_rng(8184)
+    sig = rng.integers(0, 256, (n, 2046), dtype=np.uint8)
+    with Engine(device=0, max_sv=4, ring_ms=n) as eng:
+        eng.set_code_prn(1, 1)
+        eng.set_code_prn(2, 19)
+        eng.upload_signal(0, sig)
+        rq = np.zeros(n, EPL_REQ)
+        rq["sv_slot"] = 1 + (np.arange(n) % 2)
+        rq["ms_index"] = np.arange(n)
+        rq["acc0"] = rng.integers(0, 2**32, n, dtype=np.uint64)
+        rq["step32"] = nco_step32(np.float32(IF_HZ + 2000))
+        rq["off_p"] = rng.integers(1, 2045, n)
+        rq["off_e"], rq["off_l"] = rq["off_p"] - 1, rq["off_p"] + 1
+        rq["off_bits"] = rng.integers(0, 8, n)
+        epl = eng.track_epl(rq)
+        prompt = eng.prompt_iq(rq)
+        assert np.array_equal(prompt, epl[:, 2:4])
+        perm = rng.permutation(n)
+        assert np.array_equal(eng.track_epl(rq[perm]), epl[perm])
+        assert epl.min() >= -8184 and epl.max() <= 8184
+        chips = {1: oracle.ca_code(1), 2: oracle.ca_code(19)}
+        for i in [0, n - 1] + [int(x) for x in rng.integers(0, n, 40)]:
+            want = oracle.epl_explicit(chips[int(rq["sv_slot"][i])], sig[i], int(rq["acc0"][i]), int(rq["step32"][i]),
+                                       int(rq["off_e"][i]), int(rq["off_p"][i]), int(rq["off_l"][i]), int(rq["off_bits"][i]))
+            assert np.array_equal(epl[i], want), (i, rq[i])
