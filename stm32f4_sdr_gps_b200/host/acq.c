@@ -128,7 +128,6 @@ void hx_acq_plan(gps_ch_t* ch, gpsb_aux* aux, uint32_t frame_ms, gpsb_plan* plan
 }
 
 /* ---------------------------------------------------------------------------- votes */
-static int cmp_u16(const void* x, const void* y) { return (int)*(const uint16_t*)x - (int)*(const uint16_t*)y; }
 
 /* Longest run of neighbouring code phases among the n best phases of one Doppler bin
  * (acquisition.c:322-352).  Neighbours closer than 15 half chips extend a run; a run only counts if it
@@ -136,7 +135,13 @@ static int cmp_u16(const void* x, const void* y) { return (int)*(const uint16_t*
  * reference.  phases[] is sorted in place.  *chain_phase (optional) = a member of the winning run. */
 uint8_t hx_chain_vote(uint16_t* phases, uint8_t n, uint16_t* chain_phase)
 {
-    qsort(phases, n, sizeof(uint16_t), cmp_u16);
+    /* ascending order, as the reference's qsort (acquisition.c:326) leaves it; at most 25 values: insertion sort */
+    for (uint8_t i = 1; i < n; i++) {
+        const uint16_t v = phases[i];
+        int k = (int)i - 1;
+        for (; k >= 0 && phases[k] > v; k--) phases[k + 1] = phases[k];
+        phases[k + 1] = v;
+    }
     uint8_t run = 0, tight = 0;
     uint16_t best = 0, best_phase = 0;
     for (uint8_t i = 1; i < n; i++) {
