@@ -1280,6 +1280,7 @@ int gpsb_track_loop_begin(gpsb_ctx* c, uint32_t n_ch, void* channels, uint32_t c
         if (ch[i].prn >= c->max_sv) return fail(GPSB_ERR_ARG, "channel %u: prn %u out of range (max_sv %u)", i, ch[i].prn, c->max_sv);
         if (!c->code_set[ch[i].prn]) return fail(GPSB_ERR_STATE, "channel %u: no code set for slot %u", i, ch[i].prn);
     }
+    if (c->loop_open) return fail(GPSB_ERR_STATE, "gpsb_track_loop_begin: the previous loop has not been ended (gpsb_track_loop_end)");
     pthread_mutex_lock(&c->call_lock);                   // held until gpsb_track_loop_end: the staging buffers are in use
     auto bail = [c](int rc) { pthread_mutex_unlock(&c->call_lock); return rc; };
     auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };

@@ -325,3 +325,25 @@ def test_streaming_run_from_the_2bit_iq_container(golden, ring_ms, chunk):
         assert rx.loop_stats() == (2 * 600, 0)
         rx.close()
         ch.free()
+
+
+def test_loop_begin_end_call_sequence_errors(host_engine, golden):
+    """gpsb_track_loop_begin / _end: a second begin before the end, and an end without a begin, are state errors
+    (negative status, message available), never a dead lock; the open loop still ends normally afterwards."""
+    lib = host_engine.lib
+    sig = np.ascontiguousarray(golden["scene_signal"][:64])
+    host_engine.upload_signal(0, sig)
+    ch = _two_locked_channels(golden)
+    rx = Receiver(host_engine, ch)                       # loads the codes
+    ch_b, aux_b = host_engine.record_bytes()
+    aux = np.zeros(2 * aux_b, np.uint8)
+    res = np.zeros((2, 6), np.uint32)
+    assert lib.gpsb_track_loop_end(host_engine.handle) == -4                      # GPSB_ERR_STATE
+    args = (host_engine.handle, 2, ch.at(0), ch_b, aux.ctypes.data, aux_b, 0, 64, None, None, res.ctypes.data, 0)
+    assert lib.gpsb_track_loop_begin(*args) == 0
+    assert lib.gpsb_track_loop_begin(*args) == -4
+    assert b"has not been ended" in lib.gpsb_last_error()
+    assert lib.gpsb_track_loop_end(host_engine.handle) == 0
+    assert [int(res[i, 0]) for i in range(2)] == [64, 64] and [int(res[i, 1]) for i in range(2)] == [0, 0]
+    rx.close()
+    ch.free()
