@@ -348,9 +348,7 @@ LC_FN void lc_trk_plan_run(gps_ch_t* ch, uint32_t now, uint32_t frame_ms, gpsb_e
 /* 1 when the DLL discriminator of this millisecond would be 0/0 */
 LC_FN int lc_dll_is_degenerate(const int16_t iq[6])
 {
-    int32_t early = (int32_t)iq[0] * iq[0] + (int32_t)iq[1] * iq[1];
-    int32_t late = (int32_t)iq[4] * iq[4] + (int32_t)iq[5] * iq[5];
-    return early + late == 0;
+    return (iq[0] | iq[1] | iq[4] | iq[5]) == 0;          /* a sum of four squares is zero iff all four sums are */
 }
 
 /* tracking.c:333-393 */

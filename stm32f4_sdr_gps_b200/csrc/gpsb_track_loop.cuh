@@ -26,7 +26,8 @@
  * the channel record is written by exactly one of them.  The one field read across threads,
  * nav_data.period_sync_ok_flag, is written at slot index 3 only and read by the PLL at slot index 0 only.
  *
- * Per millisecond:  phase 2 -> barrier A -> { carrier | code | nav | workers: phase 1(m+1) } -> barrier B
+ * Per millisecond:  phase 2 -> barrier A -> { carrier -> nco_ready | code -> offs_ready | nav | workers: wait offs_ready,
+ *                    phase 1(m+1), wait nco_ready }  - one full barrier; everything else is handed over by mbarriers
  * Bound: latency of one SM; channels are independent, one CTA each, so throughput scales with the channel count
  * up to the SM count at no extra time.  Algorithmic HBM bytes per channel-millisecond: 2046 (frame, shared by all
  * channels through L2) + 12 + 1 (logs).
@@ -44,11 +45,8 @@ namespace gpsb {
 #endif
 constexpr int kLoopWorkers = GPSB_LOOP_WORKERS;
 constexpr int kLoopNw = kWords / kLoopWorkers;        // data words per worker thread (words 1..510; 0 and 511 are edge words)
-// Warp w issues from scheduler w % 4.  Scheduler 3 (warps 3, 7, 11) belongs to the control threads; every other warp
-// is a worker warp, in order, and the one after the last worker warp carries the edge lanes.
 constexpr int kWorkerWarps = kLoopWorkers / 32;
-constexpr int kEdgeWarp = (kWorkerWarps / 3) * 4 + kWorkerWarps % 3;          // index of the (kWorkerWarps+1)-th non-control warp
-constexpr int kLoopWarps = (kEdgeWarp + 1 > 12 ? kEdgeWarp + 1 : 12);
+constexpr int kLoopWarps = kWorkerWarps + 4;          // + code, edge, nav, carrier
 constexpr int kLoopThreads = kLoopWarps * 32;
 static_assert(kLoopNw >= 1 && kLoopNw <= EC_NW_MAX && kLoopNw * kLoopWorkers == kWords, "work split");
 
@@ -58,6 +56,7 @@ struct LoopSmem {
     uint32_t E[kWords];                 // chip-expanded code of this channel's satellite
     unsigned long long full[2];         // mbarriers: raw frame buffer b has landed
     unsigned long long offs_ready;      // mbarrier: the code thread has published the next offsets
+    unsigned long long nco_ready;       // mbarrier: the carrier thread has published the next NCO words
     gps_ch_t ch;
     gpsb_aux aux;
     gpsb_epl_req rq;                    // what the workers correlate next
@@ -192,19 +191,17 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
     const long long loop_begin = kProf ? clock64() : 0;
     const int tid = threadIdx.x;
     const uint32_t chn = blockIdx.x, n_ch = gridDim.x;
-    // Warp w issues from scheduler w % 4.  Both worker phases saturate the integer pipes of their schedulers, and a
-    // single thread's dependent chain issued on the same scheduler loses most of its slots to them (measured: the
-    // control threads run about twice as long next to busy workers).  So scheduler 3 belongs to the three control
-    // threads alone - latency-bound chains that interleave well with each other - and the eight worker warps share
-    // schedulers 0..2.
     const int warp = tid >> 5, lane = tid & 31;
-    const int nonctl = (warp >> 2) * 3 + (warp & 3);       // rank of this warp among the non-control warps
-    const int widx = ((warp & 3) != 3 && nonctl < kWorkerWarps) ? nonctl : -1;   // worker warp index, -1 otherwise
+    // Warp w issues from scheduler w % 4.  The eight worker warps are spread over all four schedulers (two each: phase
+    // 1 is bound by the 16-lane integer pipes of a scheduler); the control threads and the edge lanes get one scheduler
+    // each, sharing it with two worker warps.  (With a second full barrier per millisecond the control threads were
+    // better off alone on one scheduler; now that the workers' phase 1 has to beat the carrier thread, they are not.)
+    const int widx = warp < kWorkerWarps ? warp : -1;      // worker warp index, -1 otherwise
     const bool worker = widx >= 0;
-    const bool code_thr = warp == 3 && lane == 0;
-    const bool carrier_thr = warp == 7 && lane == 0;
-    const bool nav_thr = warp == 11 && lane == 0;
-    const bool edge_warp = warp == kEdgeWarp;                      // lanes 0..11: the irregular words and bytes (ec_epl_edge_phase1)
+    const bool code_thr = warp == kWorkerWarps && lane == 0;
+    const bool edge_warp = warp == kWorkerWarps + 1;                // lanes 0..11: the irregular words and bytes (ec_epl_edge_phase1)
+    const bool nav_thr = warp == kWorkerWarps + 2 && lane == 0;
+    const bool carrier_thr = warp == kWorkerWarps + 3 && lane == 0;
     const bool edge = edge_warp && lane < EC_EDGE_LANES;
     const int wtid = widx * 32 + lane;                      // worker thread index 0..255
     const int w0 = wtid * kLoopNw + 1;                      // first data word of a worker: words 1..510
@@ -222,6 +219,7 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
         mbar_init(&sm.full[0], 1);
         mbar_init(&sm.full[1], 1);
         mbar_init(&sm.offs_ready, 1);
+        mbar_init(&sm.nco_ready, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         sm.stop = LC_STOP_NONE;
         sm.starved = 0;
@@ -260,16 +258,9 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
         else edge_counts = ec_epl_edge_phase1(sm.S[0], sm.RX[sm.rq.off_bits & 7u], off, lane, &edge_w, &edge_neg);
     }
     __syncthreads();                                        // raw buffer 0 has been consumed
-    // A frame that is not there in time ends the run: the code thread raises sm.starved BEFORE barrier A of the next
-    // millisecond, every thread then treats that millisecond as the last one (no plan, no phase 1 for a successor),
-    // so the records leave the kernel exactly as after a shorter run.
-    if (stop == LC_STOP_NONE && code_thr && n_ms > 2) {
-        if (kStream && !frame_present(gate, ms0 + 2, known_upto)) sm.starved = 1;
-        else {
-            tma_load_frame(sm.S[0], signal + (size_t)((ms0 + 2) % ring_ms) * kWords, GPSB_FRAME_BYTES, &sm.full[0]);
-            issued = 3;
-        }
-    }
+    // Streaming runs: a frame that is not there in time ends the run.  The code thread raises sm.starved before barrier A
+    // of the next millisecond; the control threads then treat that millisecond as the last one (no plan for a
+    // successor), so the records leave the kernel exactly as after a shorter run.
     lc_angle_cache angle_cache;
     angle_cache.valid = 0;
     // The code and the carrier thread keep private copies of the channel record for the whole run, so that the
@@ -303,6 +294,12 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
     const uint8_t prn = sm.ch.prn;
     const int16_t found_freq_offset_hz = sm.ch.acq_data.found_freq_offset_hz;
 
+    // One barrier per millisecond.  Phase 2 of millisecond m+1 needs two things, each handed over by its own
+    // mbarrier: the phase-1 partials (offs_ready: the DLL's offsets, then the warp's own phase 1) and the NCO words
+    // (nco_ready: the carrier thread).  A worker warp goes straight from its phase 1 into phase 2 the moment the NCO
+    // words exist; nobody waits for the slowest warp's phase 1 or for the nav thread in between.  Barrier A - all six
+    // sums complete - is the only full barrier; it also orders everything that is reused one millisecond later (the
+    // request record, the sum buffers, the frame buffers, the stop flag).
     uint32_t m = 0;
     for (; m < n_ms && stop == LC_STOP_NONE; m++) {
         const uint32_t ms = ms0 + m;
@@ -335,6 +332,7 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
         }
         if (kProf && carrier_thr) c0 = clock64();
         __syncthreads();   // A: the six sums of millisecond m are complete
+        if (m > 0 && (stop = sm.stop) != LC_STOP_NONE) break;      // the previous millisecond ended the run (flag written before this barrier)
         // `more`: the control threads plan a successor millisecond.  The workers only ask whether a successor frame
         // exists (it has been fetched, so waiting for it and forming its phase 1 is harmless when the run is about to
         // end for lack of LATER frames) - they do not read the starvation flag, which keeps it off their path.
@@ -353,13 +351,14 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
                     else edge_counts = ec_epl_edge_phase1(sm.S[b ^ 1u], sm.RX[sm.rq.off_bits & 7u], off, lane, &edge_w, &edge_neg);
                 }
                 if (kProf && lane == 0) { long long c2 = clock64(); c2 += (long long)((part.C[0][0] + edge_counts) & 0u); pt[13] += c2 - c1; }
+                if (kProf && wtid == 0 && worker) pt[1] += clock64() - c0;
+                mbar_wait(&sm.nco_ready, m & 1u);           // the NCO words of millisecond m+1: on to its phase 2
             }
-            if (kProf && wtid == 0 && worker) pt[1] += clock64() - c0;
         } else if (code_thr) {
             if (kProf) c0 = clock64();
             int16_t iq[6];
             load_sums(&sm.sums[b], iq);
-            sm.sums[b ^ 1u] = make_uint4(0u, 0u, 0u, 0u);      // consumed one ms ago by everybody (barrier B), filled again after this B
+            sm.sums[b ^ 1u] = make_uint4(0u, 0u, 0u, 0u);      // read one ms ago by everybody; filled again after the workers have seen offs_ready
             if (next_frame) consumed++;                         // the workers wait for frame m+1 this millisecond
             const bool degenerate = lc_dll_is_degenerate(iq);   // 0/0 in the DLL: x86 and the GPU disagree on NaN bits, host finishes this ms
             if (degenerate) sm.stop = LC_STOP_DLL_NAN;
@@ -371,6 +370,15 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
             }
             mbar_arrive(&sm.offs_ready);                    // DLL done: releases the offset check and the nav thread's edge refinement
             if (kProf) pt[2] += clock64() - c0;
+            // frame buffer b (millisecond m) was consumed before this barrier: fetch millisecond m+2 into it.  A frame
+            // that is missing is fetched all the same (the ring memory is there; nothing will use the result).
+            if (m + 2 < n_ms) {
+                if (kStream && !sm.starved && !frame_present(gate, ms + 2, known_upto)) sm.starved = 1;
+                tma_load_frame(sm.S[b], signal + (size_t)((ms + 2) % ring_ms) * kWords, GPSB_FRAME_BYTES, &sm.full[b]);
+                issued = m + 3;
+            }
+            if (kStream && gate.progress && (m & 63u) == 63u) *(volatile uint32_t*)(gate.progress + chn) = ms;
+
             if (iq_log) {
                 uint32_t* o = reinterpret_cast<uint32_t*>(iq_log + ((size_t)m * n_ch + chn) * 6);
                 o[0] = (uint16_t)iq[0] | ((uint32_t)(uint16_t)iq[1] << 16);
@@ -397,6 +405,15 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
                 }
                 if (more) lc_plan_carrier(&car, prn, ms + 1, ms + 1, &sm.rq);
             }
+            if (next_frame) mbar_arrive(&sm.nco_ready);     // always: the workers wait for it whether or not a plan was made
+            // Off the serial path: at slot index 1 the FLL needs the angle of THIS prompt sample as its "before" value;
+            // evaluate it now, while the workers are busy, instead of next to the new angle in the next millisecond.
+            if (index == 0 && !lc_dll_is_degenerate(iq)) {
+                angle_cache.i = iq[2];
+                angle_cache.q = iq[3];
+                angle_cache.angle = lc_fll_angle(iq[2], iq[3]);
+                angle_cache.valid = 1;
+            }
             if (kProf) { const long long d = clock64() - c0; pt[3] += d; if (index == 0) { pt[10] += d; pt[11] += (iq[2] > 0); } }
         } else if (nav_thr) {                               // nav bits and SNR of this millisecond (nav_data.c:46-453, tracking.c:154-169)
             if (kProf) c0 = clock64();
@@ -415,19 +432,9 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
             if (nav_log) nav_log[(size_t)m * n_ch + chn] = bit;
             if (kProf) pt[4] += clock64() - c0;
         }
-        __syncthreads();   // B: next request published, sums consumed, raw buffer of frame m+1 consumed
-        stop = sm.stop;
-        if (code_thr) {                                     // overlaps the workers' phase 2
-            if (m + 3 < n_ms && stop == LC_STOP_NONE && !(kStream && sm.starved)) {
-                if (kStream && !frame_present(gate, ms + 3, known_upto)) sm.starved = 1;
-                else {
-                    tma_load_frame(sm.S[b ^ 1u], signal + (size_t)((ms + 3) % ring_ms) * kWords, GPSB_FRAME_BYTES, &sm.full[b ^ 1u]);
-                    issued = m + 4;
-                }
-            }
-            if (kStream && gate.progress && (m & 63u) == 63u) *(volatile uint32_t*)(gate.progress + chn) = ms + 1;
-        }
     }
+    __syncthreads();                                        // the last millisecond's control work is done
+    stop = sm.stop;
     if (kStream && code_thr && gate.progress) *(volatile uint32_t*)(gate.progress + chn) = ms0 + n_ms;   // needs no more frames
     if (code_thr)      // early exit: bulk copies nobody waited for may still be in flight - let them land before the CTA retires
         for (uint32_t f = consumed; f < issued; f++) mbar_wait(&sm.full[f & 1u], (f >> 1) & 1u);
