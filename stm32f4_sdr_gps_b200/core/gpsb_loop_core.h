@@ -384,11 +384,19 @@ LC_TPL LC_FN void lc_dll_update(LC_TRK* t, int16_t ie, int16_t qe, int16_t il, i
  * the float to double; since (float)(pi/2) = 0x3FC90FDB is the smallest float above the double pi/2, "x > pi/2 in
  * double" is exactly "x >= 0x3FC90FDB in float" - same truth value for every float, one compare instead of a
  * conversion and a double compare.  The reflections themselves stay in double. */
-LC_FN float lc_fold_half_pi(float x)
+LC_FN_BIG float lc_reflect_half_pi(float x)
 {
     const float above_half_pi = lc_bits_float(0x3fc90fdb);
     if (x >= above_half_pi) x = (float)(LC_PI - x);
     if (x <= -above_half_pi) x = (float)(-LC_PI - x);
+    return x;
+}
+LC_FN float lc_fold_half_pi(float x)
+{
+    /* Inside (-pi/2, pi/2) - nearly always - nothing happens.  The reflections (double arithmetic) sit behind a real
+     * call so that a compiler cannot evaluate them speculatively on the serial path of the device-resident loop. */
+    const float above_half_pi = lc_bits_float(0x3fc90fdb);
+    if (x >= above_half_pi || x <= -above_half_pi) return lc_reflect_half_pi(x);
     return x;
 }
 
