@@ -11,14 +11,17 @@
  *   workers  (255 threads, two data words each, + 12 "edge" lanes for words 0, 511 and the four bytes an odd offset
  *            skips)  integrate-and-dump in two phases (core/gpsb_epl_core.h):
  *            phase 1 needs only the code offsets and forms raw word ^ replica window + byte masks in registers;
- *            phase 2 needs the carrier NCO words: ONE cos/sin pattern pair per word serves the three arms, then
- *            LOP3 + POPC, REDUX per warp, one 16-byte store per warp.  Nothing mixed is ever staged in memory.
+ *            phase 2 needs the carrier NCO words: the carrier phase of a word selects its I and Q count among the four
+ *            quadrant-pattern counts phase 1 left behind (one PRMT per arm), then REDUX per warp and one shared-memory
+ *            RED per warp and arm.  Nothing mixed is ever staged in memory.
  *   code     (1 thread)  DLL + code-offset planning (tracking.c:333-393, 115-130); releases phase 1 through an
  *            mbarrier as soon as the offsets exist, while the carrier thread is still busy.
- *   carrier  (1 thread)  Costas PLL / FLL / false-lock check + NCO planning (tracking.c:175-327, gps_misc.c:250).
+ *   carrier  (1 thread)  Costas PLL / FLL / false-lock check + NCO planning (tracking.c:175-327, gps_misc.c:250);
+ *            releases phase 2 through its own mbarrier.
  *   nav      (1 thread)  bit synchronisation, word assembly, parity, SNR bookkeeping (nav_data.c:46-453,
  *            tracking.c:154-169); waits for the DLL only for the rare bit-edge refinement that reads the code phase.
- *   frames   arrive by TMA bulk copies (cp.async.bulk -> mbarrier) two milliseconds ahead; the eight sub-byte
+ *   frames   arrive by TMA bulk copies (cp.async.bulk -> mbarrier) a millisecond ahead (code thread, after its DLL);
+ *            in a streaming run not before the producer's watermark has passed them; the eight sub-byte
  *            shifted, periodically extended replica streams are built once per run.  Neither HBM/L2 latency nor
  *            the period-2046-byte seam handling sits on the serial path.
  *
