@@ -971,6 +971,17 @@ static int check_epl(const gpsb_ctx* c, uint32_t n, const gpsb_epl_req* rq)
     return GPSB_OK;
 }
 
+static int check_prompt(const gpsb_ctx* c, uint32_t n, const gpsb_epl_req* rq)     // only the prompt arm's fields matter
+{
+    for (uint32_t i = 0; i < n; i++) {
+        if (rq[i].sv_slot >= c->max_sv) return fail(GPSB_ERR_ARG, "request %u: sv_slot %u out of range", i, rq[i].sv_slot);
+        if (!c->code_set[rq[i].sv_slot]) return fail(GPSB_ERR_STATE, "request %u: no code set for slot %u", i, rq[i].sv_slot);
+        if (rq[i].off_p >= GPSB_OFFSETS) return fail(GPSB_ERR_ARG, "request %u: byte offset out of range 0..2045", i);
+        if (rq[i].off_bits > 15) return fail(GPSB_ERR_ARG, "request %u: off_bits %u > 15", i, rq[i].off_bits);
+    }
+    return GPSB_OK;
+}
+
 static int check_search(const gpsb_ctx* c, uint32_t n, const gpsb_search_req* rq)
 {
     for (uint32_t i = 0; i < n; i++) {
@@ -1020,7 +1031,7 @@ int gpsb_prompt_iq(gpsb_ctx* c, uint32_t n, const gpsb_epl_req* req, int16_t* ou
 {
     if (!c || !req || !out) return fail(GPSB_ERR_ARG, "gpsb_prompt_iq: null argument");
     if (n == 0) return GPSB_OK;
-    int rc = check_epl(c, n, req);
+    int rc = check_prompt(c, n, req);
     if (rc) return rc;
     CallGuard guard(c);
     const size_t req_b = (size_t)n * sizeof(gpsb_epl_req), out_b = (size_t)n * 4;

@@ -434,6 +434,9 @@ def test_epl_batch_kernel_vs_oracle_and_cta_kernel(engine, oracle):
                                    int(rq["off_p"][i]), int(rq["off_l"][i]), int(rq["off_bits"][i]))
         assert np.array_equal(out[i], want), (i, rq[i])
     assert engine.prompt_iq(np.zeros(0, EPL_REQ)).shape == (0, 2)
+    junk = rq[:700].copy()                                   # the early / late fields play no part in the prompt-only form
+    junk["off_e"], junk["off_l"] = 65535, 40000
+    assert np.array_equal(engine.prompt_iq(junk), ref[:700, 2:4])
 
 
 def test_epl_batch_full_size_properties(oracle):
