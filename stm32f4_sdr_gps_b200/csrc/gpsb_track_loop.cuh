@@ -66,8 +66,12 @@ struct LoopSmem {
     uint32_t top_lut[16];               // ec_top_nibble_counts(0..15), see EC_COUNTS_FULL
     uint4 sums[2];                      // packed I | Q << 16 of the three arms, accumulated by one shared-memory RED per warp
                                         // and arm; double buffered by ms parity, re-zeroed by the code thread one ms later
-    int stop;
-    int starved;                        // streaming: the producer missed a frame; the current millisecond is the last of this run
+    int stop;                           // set before the loop: the run does not start (state, no frames)
+    int stop_at[2];                     // set DURING millisecond m into slot (m+1)&1, read after barrier A of millisecond m+1:
+                                        // two slots, so the flag is never written in the barrier interval in which it is read
+    int starved[2];                     // streaming: the producer missed a frame.  Slot (m+1)&1 is raised during millisecond m
+                                        // and read during millisecond m+1 (barrier A in between): millisecond m+1 is then the
+                                        // last of the run.  Two slots, so a flag is never written while it may be read.
 };
 
 // What the code thread and the carrier thread own of gps_tracking_t (PM/GPS/gps_misc.h:62-99), under the record's own
@@ -225,7 +229,8 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
         mbar_init(&sm.nco_ready, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         sm.stop = LC_STOP_NONE;
-        sm.starved = 0;
+        sm.stop_at[0] = sm.stop_at[1] = LC_STOP_NONE;
+        sm.starved[0] = sm.starved[1] = 0;
         sm.sums[0] = make_uint4(0u, 0u, 0u, 0u);
         sm.sums[1] = make_uint4(0u, 0u, 0u, 0u);
     }
@@ -261,9 +266,9 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
         else edge_counts = ec_epl_edge_phase1(sm.S[0], sm.RX[sm.rq.off_bits & 7u], off, lane, &edge_w, &edge_neg);
     }
     __syncthreads();                                        // raw buffer 0 has been consumed
-    // Streaming runs: a frame that is not there in time ends the run.  The code thread raises sm.starved before barrier A
-    // of the next millisecond; the control threads then treat that millisecond as the last one (no plan for a
-    // successor), so the records leave the kernel exactly as after a shorter run.
+    // Streaming runs: a frame that is not there in time ends the run.  The code thread raises the next millisecond's
+    // sm.starved slot; the control threads then treat that millisecond as the last one (no plan for a successor), so
+    // the records leave the kernel exactly as after a shorter run.
     lc_angle_cache angle_cache;
     angle_cache.valid = 0;
     // The code and the carrier thread keep private copies of the channel record for the whole run, so that the
@@ -335,12 +340,13 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
         }
         if (kProf && carrier_thr) c0 = clock64();
         __syncthreads();   // A: the six sums of millisecond m are complete
-        if (m > 0 && (stop = sm.stop) != LC_STOP_NONE) break;      // the previous millisecond ended the run (flag written before this barrier)
+        if (m > 0 && (stop = sm.stop_at[b]) != LC_STOP_NONE) break;   // the previous millisecond ended the run (flag written before this barrier)
         // `more`: the control threads plan a successor millisecond.  The workers only ask whether a successor frame
         // exists (it has been fetched, so waiting for it and forming its phase 1 is harmless when the run is about to
         // end for lack of LATER frames) - they do not read the starvation flag, which keeps it off their path.
         const bool next_frame = m + 1 < n_ms;
-        const bool more = next_frame && !(kStream && !(worker || edge_warp) && *(volatile int*)&sm.starved);
+        // (each control thread reads the flag where it needs it - at the END of its chain - so that the shared-memory
+        // round trip never sits in front of its arithmetic)
         if (worker || edge_warp) {
             if (kProf) c0 = clock64();
             if (next_frame && (plain || edge)) {            // phase 1 of millisecond m+1 as soon as its offsets exist
@@ -348,7 +354,7 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
                 mbar_wait(&sm.offs_ready, m & 1u);
                 long long c1 = 0;
                 if (kProf) c1 = clock64();
-                if (sm.stop == LC_STOP_NONE && !(kExp & 1)) {
+                if (sm.stop_at[b ^ 1u] == LC_STOP_NONE && !(kExp & 1)) {      // ordered after the code thread's write by offs_ready
                     const uint32_t off[3] = {sm.rq.off_e, sm.rq.off_p, sm.rq.off_l};
                     if (plain) ec_epl_phase1(sm.S[b ^ 1u], sm.RX[sm.rq.off_bits & 7u], off, w0, kLoopNw, &part, sm.top_lut);
                     else edge_counts = ec_epl_edge_phase1(sm.S[b ^ 1u], sm.RX[sm.rq.off_bits & 7u], off, lane, &edge_w, &edge_neg);
@@ -364,11 +370,11 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
             sm.sums[b ^ 1u] = make_uint4(0u, 0u, 0u, 0u);      // read one ms ago by everybody; filled again after the workers have seen offs_ready
             if (next_frame) consumed++;                         // the workers wait for frame m+1 this millisecond
             const bool degenerate = lc_dll_is_degenerate(iq);   // 0/0 in the DLL: x86 and the GPU disagree on NaN bits, host finishes this ms
-            if (degenerate) sm.stop = LC_STOP_DLL_NAN;
+            if (degenerate) sm.stop_at[b ^ 1u] = LC_STOP_DLL_NAN;
             else {
-                if (kStream && sm.starved) sm.stop = LC_STOP_STARVED;     // this millisecond is completed by every thread, then the run ends
+                if (kStream && sm.starved[b]) sm.stop_at[b ^ 1u] = LC_STOP_STARVED;   // this millisecond is completed by every thread, then the run ends
                 if (!(kExp & 4)) lc_dll_update(&cod, iq[0], iq[1], iq[4], iq[5]);
-                if (more) lc_plan_code(&cod, &sm.rq);
+                if (next_frame && !(kStream && sm.starved[b])) lc_plan_code(&cod, &sm.rq);
                 sm.ch.tracking_data.code_phase_fine = cod.code_phase_fine;   // for lc_refine_edge
             }
             mbar_arrive(&sm.offs_ready);                    // DLL done: releases the offset check and the nav thread's edge refinement
@@ -376,7 +382,7 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
             // frame buffer b (millisecond m) was consumed before this barrier: fetch millisecond m+2 into it.  A frame
             // that is missing is fetched all the same (the ring memory is there; nothing will use the result).
             if (m + 2 < n_ms) {
-                if (kStream && !sm.starved && !frame_present(gate, ms + 2, known_upto)) sm.starved = 1;
+                if (kStream && !sm.starved[b] && !frame_present(gate, ms + 2, known_upto)) sm.starved[b ^ 1u] = 1;
                 tma_load_frame(sm.S[b], signal + (size_t)((ms + 2) % ring_ms) * kWords, GPSB_FRAME_BYTES, &sm.full[b]);
                 issued = m + 3;
             }
@@ -406,7 +412,7 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
                     lc_pll_update(&car, sm.ch.nav_data.period_sync_ok_flag, index, iq[2], iq[3]);
                     lc_fll_update(&car, &sm.aux, found_freq_offset_hz, index, iq[2], iq[3], &angle_cache);
                 }
-                if (more) lc_plan_carrier(&car, prn, ms + 1, ms + 1, &sm.rq);
+                if (next_frame && !(kStream && *(volatile int*)&sm.starved[b])) lc_plan_carrier(&car, prn, ms + 1, ms + 1, &sm.rq);
             }
             if (next_frame) mbar_arrive(&sm.nco_ready);     // always: the workers wait for it whether or not a plan was made
             // Off the serial path: at slot index 1 the FLL needs the angle of THIS prompt sample as its "before" value;
@@ -437,7 +443,7 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
         }
     }
     __syncthreads();                                        // the last millisecond's control work is done
-    stop = sm.stop;
+    if (stop == LC_STOP_NONE) stop = sm.stop_at[m & 1u];    // a stop raised by the very last millisecond (m == n_ms here)
     if (kStream && code_thr && gate.progress) *(volatile uint32_t*)(gate.progress + chn) = ms0 + n_ms;   // needs no more frames
     if (code_thr)      // early exit: bulk copies nobody waited for may still be in flight - let them land before the CTA retires
         for (uint32_t f = consumed; f < issued; f++) mbar_wait(&sm.full[f & 1u], (f >> 1) & 1u);
