@@ -111,6 +111,19 @@ typedef struct gpsb_flat_eph {
     uint64_t tow_gpst;
 } gpsb_flat_eph;
 
+/* Position solver outputs (RTK/solving.c: gps_sol, final_pos, azel) as bit patterns. */
+#define GPSB_FLAT_FIX_SATS 32
+typedef struct gpsb_flat_fix {
+    int32_t  stat, ns, type, busy;
+    int64_t  time_time;
+    uint64_t time_sec_bits;
+    uint64_t rr[6];
+    uint32_t qr[6];
+    uint64_t dtr0;
+    uint64_t final_pos[3];                                       /* latitude, longitude (deg), height (m) */
+    uint64_t azel[2 * GPSB_FLAT_FIX_SATS];                       /* the reference holds 2 x 4 */
+} gpsb_flat_fix;
+
 #ifdef __cplusplus
 }
 #endif

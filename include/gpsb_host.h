@@ -191,6 +191,31 @@ typedef struct {
 } gps_ch_t;
 #endif /* _GPS_MISC_H */
 
+/* Records of the position solver (row N4): PM/GPS/RTK/rtk_common.h:50-59 and solving.h:17-32, same layout. */
+#define GPSB_FIX_MAX_SATS 32
+#ifndef _RTCM_COMMON_H
+typedef struct {
+    gtime_t time;                    /* receiver sampling time (GPST) */
+    unsigned char sat, rcv;
+    unsigned char SNR[1], LLI[1], code[1];
+    double L[1];                     /* carrier phase (cycles) - not produced */
+    double P[1];                     /* pseudorange (m) */
+    float  D[1];                     /* Doppler (Hz) */
+} obsd_t;
+#endif
+#ifndef _GPS_SOLVING_H
+#define SOLQ_NONE   0
+#define SOLQ_SINGLE 5
+typedef struct {
+    gtime_t time;                    /* GPST of the fix */
+    double rr[6];                    /* ECEF position (m) / velocity (always 0) */
+    float  qr[6];                    /* position covariance xx yy zz xy yz zx (m^2) */
+    double dtr[6];                   /* receiver clock bias (s) in [0] */
+    unsigned char type, stat, ns;    /* stat: SOLQ_NONE / SOLQ_SINGLE */
+    float age, ratio;
+} sol_t;
+#endif
+
 /* ------------------------------------------------------------------------------------------------
  * Binding to a GPU context and to the millisecond clock.
  * ---------------------------------------------------------------------------------------------- */
@@ -357,6 +382,39 @@ void gpsb_host_channel_eph(const gps_ch_t* ch, struct gpsb_flat_eph* out);
 
 void gpsb_host_channel_obs(const gps_ch_t* ch, uint64_t out2[2]);     /* bit patterns of obs_data.pseudorange_m, tow_s */
 void gpsb_host_channel_set_tow(gps_ch_t* ch, double tow_gpst);
+
+/* ------------------------------------------------------------------------------------------------
+ * Position fix: PM/GPS/RTK/solving.h:34-40, rtk_common.h:103-110 and
+ * gps_master.c:394.  Host C only - a fix is a few thousand double operations twice a second; bit-exact against the
+ * compiled reference (tests/test_fix.py).  gps_master_nav_handling ends with gps_master_calculate_pos, as in the
+ * reference, once gps_pos_solve_init has registered the channels.
+ * ------------------------------------------------------------------------------------------------ */
+extern sol_t  gps_sol;                               /* solving.c:49 */
+extern double final_pos[3];                          /* solving.c:51: latitude, longitude (deg), height (m) */
+extern double azel[2 * GPSB_FIX_MAX_SATS];           /* solving.c:52: azimuth / elevation per satellite (deg) */
+void    gps_pos_solve_init(gps_ch_t* channels);      /* registers the ephemerides of the first sat_cnt channels */
+void    gps_pos_solve(obsd_t* obs_p);                /* one sub-millisecond slice per call, like the reference */
+uint8_t solving_is_busy(void);
+void    gps_master_calculate_pos(gps_ch_t* channels);
+void    ecef2pos(const double* r, double* pos);
+void    sdrobs2obsd(gps_ch_t* channels, int ns, obsd_t* out);
+double  timediff(gtime_t t1, gtime_t t2);
+gtime_t timeadd(gtime_t t, double sec);
+gtime_t gpst2time(int week, double sec);
+double  time2gpst(gtime_t t, int* week);
+/* The same fix without the slicing (the reference's pntpos, solving.c:153): 1 = fix in *sol (and pos_deg, may be
+ * NULL), 0 = none.  gpsb_host_fix_channels runs it on the channels' current observations into gps_sol / final_pos. */
+int  gpsb_host_fix_once(const obsd_t* obs, int n, sol_t* sol, double pos_deg[3]);
+int  gpsb_host_fix_channels(gps_ch_t* channels, uint32_t n);
+void gpsb_host_fix_set_iono(const double coeff[8]);  /* Klobuchar a0..a3, b0..b3; NULL / zeros = the reference's defaults */
+void gpsb_host_fix_set_start(const double ecef_m[3]);   /* first iterate; default = previous fix (0,0,0 at start-up) */
+void gpsb_host_fix_reset(void);
+struct gpsb_flat_fix;
+void gpsb_host_fix_state(struct gpsb_flat_fix* out);
+void gpsb_host_channel_set_eph(gps_ch_t* ch, const struct gpsb_flat_eph* in);   /* assisted start: inject an ephemeris */
+void gpsb_host_channel_set_obs(gps_ch_t* ch, double pseudorange_m, double tow_s);
+uint32_t gpsb_host_sizeof_obsd(void);               /* 48 and 152, checked against the compiled reference */
+uint32_t gpsb_host_sizeof_sol(void);
 
 /* Flat, layout-independent snapshot of one channel (include/gpsb_flat_state.h) for parity tests. */
 struct gpsb_flat_state;

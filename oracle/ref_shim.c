@@ -40,16 +40,15 @@ double ref_now_s(void);
 
 /* ------------------------------------------------------------------ gps_master.c link stubs
  * gps_master.c (compiled unmodified for its acquisition/tracking sequencing, gps_master.c:68-156)
- * also references the terminal UI, the key handler and the position solver; none of them is on the
- * hot path, so they are inert here. */
+ * also references the terminal UI and the key handler; neither is on the hot path, so they are inert here
+ * (the position solver, RTK/solving.c, is compiled in as it lies for row N4). */
 #include "gps_master.h"
 #include "rtk_common.h"
 uint8_t key_up_presed = 0;
 void print_state_handling(uint32_t time_ms) { (void)time_ms; }
 void print_state_update_acquisition(gps_ch_t* channels, uint32_t time_ms) { (void)channels; (void)time_ms; }
 void print_state_update_tracking(gps_ch_t* channels, uint32_t time_ms) { (void)channels; (void)time_ms; }
-uint8_t solving_is_busy(void) { return 0; }
-void gps_pos_solve(obsd_t* obs_p) { (void)obs_p; }
+uint32_t get_dwt_value(void) { return 0; }            /* cycle counter the solver times itself with (delay_us_timer.h) */
 
 /* ------------------------------------------------------------------ ms counter seam */
 static uint32_t g_packet_cnt = 0;
@@ -495,3 +494,83 @@ void ref_channel_obs(const gps_ch_t* ch, uint64_t out2[2])
 }
 void ref_channel_set_tow(gps_ch_t* ch, double tow_gpst) { ch->eph_data.tow_gpst = tow_gpst; }
 
+
+/* ------------------------------------------------------------------ position fix (RTK/solving.c, row N4) */
+#include "solving.h"
+extern sol_t gps_sol;
+extern double final_pos[3];
+extern double azel[];
+static obsd_t g_ref_obsd[GPS_SAT_CNT];
+static double u2d(uint64_t u) { double d; memcpy(&d, &u, 8); return d; }
+
+void ref_channel_set_eph(gps_ch_t* ch, const gpsb_flat_eph* in)
+{
+    sdreph_t* d = &ch->eph_data;
+    eph_t* e = &d->eph;
+    e->sat = in->sat; e->iode = in->iode; e->iodc = in->iodc; e->sva = in->sva; e->svh = in->svh; e->week = in->week;
+    e->code = in->code; e->flag = in->flag;
+    e->toe.time = (time_t)in->toe_time; e->toc.time = (time_t)in->toc_time; e->ttr.time = (time_t)in->ttr_time;
+    e->toe.sec = u2d(in->toe_sec_bits); e->toc.sec = u2d(in->toc_sec_bits); e->ttr.sec = u2d(in->ttr_sec_bits);
+    e->A = u2d(in->A); e->e = u2d(in->e); e->i0 = u2d(in->i0); e->OMG0 = u2d(in->OMG0); e->omg = u2d(in->omg);
+    e->M0 = u2d(in->M0); e->deln = u2d(in->deln); e->OMGd = u2d(in->OMGd); e->idot = u2d(in->idot);
+    e->crc = u2d(in->crc); e->crs = u2d(in->crs); e->cuc = u2d(in->cuc); e->cus = u2d(in->cus); e->cic = u2d(in->cic);
+    e->cis = u2d(in->cis); e->toes = u2d(in->toes); e->fit = u2d(in->fit); e->f0 = u2d(in->f0); e->f1 = u2d(in->f1);
+    e->f2 = u2d(in->f2);
+    for (int i = 0; i < 4; i++) e->tgd[i] = u2d(in->tgd[i]);
+    d->ctype = in->ctype; d->week_gpst = in->week_gpst; d->cnt = in->cnt; d->cntth = in->cntth; d->update = in->update;
+    d->prn = in->prn; d->week_gst = in->week_gst; d->sub_cnt = (uint16_t)in->sub_cnt;
+    d->received_mask = (uint8_t)in->received_mask; d->received_mask_proc = (uint8_t)in->received_mask_proc;
+    d->tow_gpst = u2d(in->tow_gpst);
+}
+void ref_channel_set_obs(gps_ch_t* ch, double pseudorange_m, double tow_s)
+{
+    ch->obs_data.pseudorange_m = pseudorange_m;
+    ch->obs_data.tow_s = tow_s;
+}
+
+void ref_fix_init(gps_ch_t* chans) { gps_pos_solve_init(chans); }
+
+/* sdrobs2obsd + gps_pos_solve until solving_is_busy() drops (at most max_calls); returns the number of calls made */
+uint32_t ref_fix_run(gps_ch_t* chans, uint32_t max_calls)
+{
+    uint32_t calls = 0;
+    sdrobs2obsd(chans, GPS_SAT_CNT, g_ref_obsd);
+    do { gps_pos_solve(g_ref_obsd); calls++; } while (solving_is_busy() && calls < max_calls);
+    return calls;
+}
+
+/* the reference's one-shot pntpos (solving.c:153) into gps_sol, then the conversion gps_pos_solve would do */
+extern nav_t nav_data;
+int ref_fix_once(gps_ch_t* chans)
+{
+    sdrobs2obsd(chans, GPS_SAT_CNT, g_ref_obsd);
+    int ok = pntpos(g_ref_obsd, GPS_SAT_CNT, &nav_data, &gps_sol);
+    if (ok) {
+        ecef2pos(gps_sol.rr, final_pos);
+        final_pos[0] = final_pos[0] * R2D;
+        final_pos[1] = final_pos[1] * R2D;
+    }
+    return ok;
+}
+
+void ref_fix_set_start(const double rr3[3]) { for (int i = 0; i < 3; i++) gps_sol.rr[i] = rr3[i]; }
+
+void ref_fix_state(gpsb_flat_fix* o)
+{
+    memset(o, 0, sizeof *o);
+    o->stat = gps_sol.stat; o->ns = gps_sol.ns; o->type = gps_sol.type; o->busy = solving_is_busy();
+    o->time_time = (int64_t)gps_sol.time.time;
+    o->time_sec_bits = d2u(gps_sol.time.sec);
+    for (int k = 0; k < 6; k++) { o->rr[k] = d2u(gps_sol.rr[k]); o->qr[k] = f2u(gps_sol.qr[k]); }
+    o->dtr0 = d2u(gps_sol.dtr[0]);
+    for (int k = 0; k < 3; k++) o->final_pos[k] = d2u(final_pos[k]);
+    for (int k = 0; k < 2 * MAXSAT; k++) o->azel[k] = d2u(azel[k]);
+}
+
+void ref_obsd(gps_ch_t* chans, uint8_t* out, uint32_t bytes)
+{
+    sdrobs2obsd(chans, GPS_SAT_CNT, g_ref_obsd);
+    memcpy(out, g_ref_obsd, bytes < sizeof g_ref_obsd ? bytes : sizeof g_ref_obsd);
+}
+uint32_t ref_sizeof_obsd(void) { return (uint32_t)sizeof(obsd_t); }
+uint32_t ref_sizeof_sol(void) { return (uint32_t)sizeof(sol_t); }

@@ -167,6 +167,7 @@ void gps_master_nav_handling(gps_ch_t* ch)
         code_filter_restart(ch, n, now);
 #endif
     }
+    gps_master_calculate_pos(ch);                          /* gps_master.c:283-285; fix.c */
 }
 
 uint8_t gps_master_need_acq(void) { return g_need_acq; }
@@ -208,4 +209,5 @@ void gpsb_host_master_reset(void)
 {
     g_need_acq = 1;
     g_first_call = 1;
+    gpsb_host_fix_reset();
 }
