@@ -553,6 +553,14 @@ int ref_fix_once(gps_ch_t* chans)
     return ok;
 }
 
+/* the solver's global outputs back to zero (its function statics cannot be reached) */
+void ref_fix_clear(void)
+{
+    memset(&gps_sol, 0, sizeof gps_sol);
+    memset(final_pos, 0, sizeof final_pos);
+    memset(azel, 0, 2 * MAXSAT * sizeof(double));
+}
+
 void ref_fix_set_start(const double rr3[3]) { for (int i = 0; i < 3; i++) gps_sol.rr[i] = rr3[i]; }
 
 void ref_fix_state(gpsb_flat_fix* o)

@@ -421,10 +421,10 @@ static void fx_clear_slot(fx_state* s, int i)
 }
 
 /* The measurement row of satellite i (solving.c:742-781 / :841-873): residual, design row, variance.
- * s->accepted is the reference's count of valid satellites; the sliced driver there never clears it (a function
- * static, solving.c:459 with :866), so the `ns` it reports is a running total modulo 256 - reproduced, because
- * parity is on every field; the one-shot driver clears it per pass like the reference's pntpos. */
-static void fx_measure(fx_state* s, const obsd_t* obs, int i)
+ * *accepted is the reference's count of valid satellites.  Its sliced driver never clears it (a function static,
+ * solving.c:459 with :866), so the `ns` it reports is a running total modulo 256 - reproduced in fx_state.accepted,
+ * because parity is on every field; the one-shot driver counts per pass in a local, like the reference's pntpos. */
+static void fx_measure(fx_state* s, const obsd_t* obs, int i, int* accepted)
 {
     double los[3], r, dion, vion, dtrp, vtrp;
     double* az_el = azel + i * 2;
@@ -448,7 +448,7 @@ static void fx_measure(fx_state* s, const obsd_t* obs, int i)
     for (int j = 0; j < FX_NX; j++) s->H[j + row * FX_NX] = j < 3 ? -los[j] : (j == 3 ? 1.0 : 0.0);
     s->used[i] = 1;
     s->resid[i] = s->v[row];
-    s->accepted++;
+    (*accepted)++;
 
     const double vmeas = 0.0;
     const double elev_var = FX_SQ(1.0) * (FX_SQ(0.003) * (FX_SQ(0.003) + FX_SQ(0.003) / sin(az_el[1])));   /* :591-597 */
@@ -490,7 +490,7 @@ static int fx_converged(const fx_state* s)
 }
 
 /* solving.c:416-435 / :572-586 */
-static void fx_commit(const fx_state* s, const obsd_t* obs, sol_t* sol)
+static void fx_commit(const fx_state* s, const obsd_t* obs, int accepted, sol_t* sol)
 {
     sol->type = 0;
     sol->time = timeadd(obs[0].time, -s->x[3] / FX_CLIGHT);
@@ -500,7 +500,7 @@ static void fx_commit(const fx_state* s, const obsd_t* obs, sol_t* sol)
     sol->qr[3] = (float)s->Q[1];
     sol->qr[4] = (float)s->Q[2 + FX_NX];
     sol->qr[5] = (float)s->Q[2];
-    sol->ns = (unsigned char)s->accepted;
+    sol->ns = (unsigned char)accepted;
     sol->age = sol->ratio = 0.0;
     sol->stat = SOLQ_SINGLE;
 }
@@ -525,7 +525,7 @@ static int fx_residual_step(fx_state* s, const obsd_t* obs, int n, int i)
 {
     if (i == 0) fx_begin_pass(s);
     fx_clear_slot(s, i);
-    if (!(i < n - 1 && obs[i].sat == obs[i + 1].sat)) fx_measure(s, obs, i);
+    if (!(i < n - 1 && obs[i].sat == obs[i + 1].sat)) fx_measure(s, obs, i, &s->accepted);
     if (i + 1 != n) return -1;
     fx_pin_offsets(s);
     return s->rows;
@@ -554,7 +554,7 @@ static int fx_estimate_step(fx_state* s, const obsd_t* obs, int n, sol_t* sol)
         }
     }
     if (s->pass > FX_MAX_PASSES) res = -1;
-    if (res > 0) fx_commit(s, obs, sol);
+    if (res > 0) fx_commit(s, obs, s->accepted, sol);
     if (res != 0) s->pass = s->op = 0;
     return res;
 }
@@ -654,18 +654,18 @@ int gpsb_host_fix_once(const obsd_t* obs, int n, sol_t* sol, double pos_deg[3])
     int fixed = 0;
     for (int pass = 0; pass < FX_MAX_PASSES && !fixed; pass++) {
         fx_begin_pass(s);
-        s->accepted = 0;
+        int accepted = 0;
         for (int i = 0; i < n; i++) {
             fx_clear_slot(s, i);
             if (i < n - 1 && obs[i].sat == obs[i + 1].sat) { i++; continue; }
-            fx_measure(s, obs, i);
+            fx_measure(s, obs, i, &accepted);
         }
         fx_pin_offsets(s);
         if (s->rows < FX_NX) break;
         fx_whiten(s);
         if (fx_normal_solve(s->H, s->v, s->rows, s->dx, s->Q) > 0) break;
         for (int j = 0; j < FX_NX; j++) s->x[j] += s->dx[j];
-        if (fx_converged(s)) { fx_commit(s, obs, sol); fixed = 1; }
+        if (fx_converged(s)) { fx_commit(s, obs, accepted, sol); fixed = 1; }
     }
     for (int i = 0; i < 2 * n; i++) azel[i] = azel[i] * FX_R2D;
     if (fixed && pos_deg) {
@@ -698,7 +698,8 @@ void gpsb_host_fix_set_iono(const double coeff[8])
     for (int k = 0; k < 8; k++) g_fx.ion[k] = coeff ? coeff[k] : 0.0;
 }
 
-/* Forget a solve in flight and the request timer (the reference has no such entry: its statics live forever). */
+/* Forget a solve in flight, the request timer and the last fix (the reference has no such entry: its statics live
+ * forever).  The running satellite count of the sliced driver is kept. */
 void gpsb_host_fix_reset(void)
 {
     fx_state* s = &g_fx;
@@ -706,6 +707,9 @@ void gpsb_host_fix_reset(void)
     s->sat_slice = s->sat_ok = s->pass = s->op = 0;
     s->solving = s->converting = 0;
     s->last_request_ms = 0;
+    memset(&gps_sol, 0, sizeof gps_sol);
+    memset(final_pos, 0, sizeof final_pos);
+    memset(azel, 0, sizeof azel);
 }
 
 static uint64_t fx_bits(double d) { uint64_t u; memcpy(&u, &d, 8); return u; }
