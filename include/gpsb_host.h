@@ -263,8 +263,8 @@ void gps_nav_data_words_detection(gps_ch_t* channel, uint8_t new_bit);
  * channel->eph_data; returns the subframe id.  Called by the word assembler whenever a subframe completes. */
 uint8_t gps_nav_data_decode_subframe(gps_ch_t* channel);
 
-/* PM/GPS/gps_master.h:7-15 (sequencing and, in the idle slot index == 0xFF, the observations; no UART, keys, RTCM or
- * position solver here) */
+/* PM/GPS/gps_master.h:7-15 (sequencing and, in the idle slot index == 0xFF, the observations, the RTCM frames when enabled
+ * and the position fix; no UART or keys here) */
 void    gps_master_handling(gps_ch_t* channels, uint8_t index);
 /* PM/GPS/gps_master.c:159: subframe-time bookkeeping, code-phase filter, pseudorange and time of week of every channel
  * into channels[i].obs_data (the reference calls it from gps_master_handling's idle slot). */
@@ -415,6 +415,23 @@ void gpsb_host_channel_set_eph(gps_ch_t* ch, const struct gpsb_flat_eph* in);   
 void gpsb_host_channel_set_obs(gps_ch_t* ch, double pseudorange_m, double tow_s);
 uint32_t gpsb_host_sizeof_obsd(void);               /* 48 and 152, checked against the compiled reference */
 uint32_t gpsb_host_sizeof_sol(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * RTCM 3 output (row N4, second half): PM/GPS/obs_publish.h:8-9, RTK/rtk_common.h:100, gps_master.c:431.
+ * Message 1019 (GPS ephemeris) and 1075 (GPS MSM5 observations), byte-exact against the compiled reference
+ * (tests/test_rtcm.py).  Compiled out in the reference's shipped configuration (config.h:30); here a run-time
+ * switch, off by default.  Frames go to the sink the application registers (the reference's UART).
+ * ------------------------------------------------------------------------------------------------ */
+void gpsb_host_set_rtcm_sink(void (*send)(const uint8_t* frame, uint32_t bytes), int (*busy)(void));
+void gpsb_host_enable_rtcm(int on);                  /* gps_master_nav_handling then also calls gps_master_transmit_obs */
+int  gpsb_host_rtcm_enabled(void);
+void sendrtcmobs(obsd_t* obsd, int nsat);
+void sendrtcmnav(gps_ch_t* channel);
+void gps_master_transmit_obs(gps_ch_t* channels);
+void setbitu(unsigned char* buff, int pos, int len, unsigned int data);
+/* The same frames into a caller's buffer; return the frame length in bytes, 0 = nothing to send / does not fit. */
+int  gpsb_rtcm_encode_eph(const eph_t* eph, int sat, uint8_t* out, uint32_t cap);
+int  gpsb_rtcm_encode_obs(const obsd_t* obs, int n_obs, uint8_t* out, uint32_t cap);
 
 /* Flat, layout-independent snapshot of one channel (include/gpsb_flat_state.h) for parity tests. */
 struct gpsb_flat_state;

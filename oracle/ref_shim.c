@@ -582,3 +582,46 @@ void ref_obsd(gps_ch_t* chans, uint8_t* out, uint32_t bytes)
 }
 uint32_t ref_sizeof_obsd(void) { return (uint32_t)sizeof(obsd_t); }
 uint32_t ref_sizeof_sol(void) { return (uint32_t)sizeof(sol_t); }
+
+/* ------------------------------------------------------------------ RTCM frames (obs_publish.c via ref_rtcm_unit.c, RTK/rtcm3e.c) */
+#include "obs_publish.h"
+static uint8_t g_uart_frame[1200];
+static uint32_t g_uart_bytes = 0, g_uart_calls = 0;
+uint8_t uart_prim_dma_send_data(uint8_t* data, uint16_t size)      /* the UART the frames go out on (uart_comm.h:16) */
+{
+    g_uart_bytes = size;
+    g_uart_calls++;
+    memcpy(g_uart_frame, data, size < sizeof g_uart_frame ? size : sizeof g_uart_frame);
+    return 0;
+}
+uint8_t uart_prim_is_busy(void) { return 0; }
+
+static uint32_t take_frame(uint8_t* out, uint32_t cap)
+{
+    const uint32_t n = g_uart_bytes < cap ? g_uart_bytes : cap;
+    memcpy(out, g_uart_frame, n);
+    return g_uart_bytes;
+}
+/* sdrobs2obsd + sendrtcmobs (message 1075); returns the frame length */
+uint32_t ref_rtcm_obs(gps_ch_t* chans, uint8_t* out, uint32_t cap)
+{
+    g_uart_bytes = 0;
+    sdrobs2obsd(chans, GPS_SAT_CNT, g_ref_obsd);
+    sendrtcmobs(g_ref_obsd, GPS_SAT_CNT);
+    return take_frame(out, cap);
+}
+/* the same on caller-made observation records (n <= GPS_SAT_CNT) */
+uint32_t ref_rtcm_obs_records(const uint8_t* records, uint32_t n, uint8_t* out, uint32_t cap)
+{
+    g_uart_bytes = 0;
+    memcpy(g_ref_obsd, records, n * sizeof(obsd_t));
+    sendrtcmobs(g_ref_obsd, (int)n);
+    return take_frame(out, cap);
+}
+/* sendrtcmnav (message 1019) */
+uint32_t ref_rtcm_nav(gps_ch_t* ch, uint8_t* out, uint32_t cap)
+{
+    g_uart_bytes = 0;
+    sendrtcmnav(ch);
+    return take_frame(out, cap);
+}

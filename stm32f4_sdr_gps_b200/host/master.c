@@ -3,8 +3,9 @@
  *
  * Behaviour follows Firmware/project_main/GPS/gps_master.c: the sequencing half (:68-156, helpers :453-510) and the
  * observation half - subframe-time bookkeeping, code-phase filter and pseudorange / time-of-week assembly
- * (gps_master_nav_handling, :159-388; row N3 of SURVEY.md section 8(f)).  What comes after the observations in that
- * file (position solver, RTCM, terminal output, the key handler) is not part of this library.
+ * (gps_master_nav_handling, :159-388; row N3 of SURVEY.md section 8(f)).  The position fix and the RTCM frames that follow
+ * the observations in that file live in fix.c and rtcm.c (row N4); its terminal output and key handler are not part
+ * of this library.
  */
 #include <math.h>
 
@@ -167,6 +168,7 @@ void gps_master_nav_handling(gps_ch_t* ch)
         code_filter_restart(ch, n, now);
 #endif
     }
+    if (gpsb_host_rtcm_enabled()) gps_master_transmit_obs(ch);   /* gps_master.c:279-281; rtcm.c */
     gps_master_calculate_pos(ch);                          /* gps_master.c:283-285; fix.c */
 }
 
