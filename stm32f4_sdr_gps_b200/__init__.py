@@ -9,6 +9,6 @@ from .engine import (CHIPS, EPL_REQ, FRAME_BYTES, IF_FREQ_HZ, MS_BYTES, MS_SAMPL
 
 __all__ = ["CHIPS", "EPL_REQ", "FRAME_BYTES", "IF_FREQ_HZ", "MS_BYTES", "MS_SAMPLES", "OFFSETS",
            "SEARCH_REQ", "SEARCH_RES", "Engine", "GpsbError", "load_library", "nco_step", "nco_step32"]
-from .host_api import Channels, FlatState, Plan, Receiver, SearchRes, load_host_library  # noqa: E402
+from .host_api import Channels, FlatFix, FlatState, Plan, Receiver, SearchRes, load_host_library  # noqa: E402
 
-__all__ += ["Channels", "FlatState", "Plan", "Receiver", "SearchRes", "load_host_library"]
+__all__ += ["Channels", "FlatFix", "FlatState", "Plan", "Receiver", "SearchRes", "load_host_library"]

@@ -77,6 +77,13 @@ class FlatState(C.Structure):
 _hostlib = None
 
 
+class FlatFix(C.Structure):
+    """include/gpsb_flat_state.h, gpsb_flat_fix: the position solver's outputs, doubles / floats as bit patterns"""
+    _fields_ = [("stat", C.c_int32), ("ns", C.c_int32), ("type", C.c_int32), ("busy", C.c_int32),
+                ("time_time", C.c_int64), ("time_sec_bits", C.c_uint64), ("rr", C.c_uint64 * 6), ("qr", C.c_uint32 * 6),
+                ("dtr0", C.c_uint64), ("final_pos", C.c_uint64 * 3), ("azel", C.c_uint64 * 64)]
+
+
 def load_host_library(path: Path | None = None) -> C.CDLL:
     """Load libgpsb_host.so (in-tree).  Raises if it has not been built."""
     global _hostlib
@@ -131,6 +138,15 @@ def load_host_library(path: Path | None = None) -> C.CDLL:
         "gpsb_host_channels_alloc": (vp, [u32]), "gpsb_host_channels_free": (None, [vp]),
         "gpsb_host_channel_at": (vp, [vp, u32]), "gpsb_host_channel_init": (None, [vp, u32, C.c_int32]),
         "gpsb_host_channel_code": (C.POINTER(u8), [vp]),
+        # position fix and RTCM frames (rows N4; host/fix.c, host/rtcm.c)
+        "gps_pos_solve_init": (None, [vp]), "gps_pos_solve": (None, [vp]), "solving_is_busy": (u8, []),
+        "gps_master_calculate_pos": (None, [vp]), "sdrobs2obsd": (None, [vp, i32, vp]),
+        "gpsb_host_fix_channels": (i32, [vp, u32]), "gpsb_host_fix_state": (None, [C.POINTER(FlatFix)]),
+        "gpsb_host_fix_reset": (None, []), "gpsb_host_fix_set_start": (None, [vp]),
+        "gpsb_host_fix_set_iono": (None, [vp]),
+        "gpsb_host_enable_rtcm": (None, [i32]), "gpsb_host_rtcm_enabled": (i32, []),
+        "gps_master_transmit_obs": (None, [vp]),
+        "gpsb_rtcm_encode_obs": (i32, [vp, i32, vp, u32]),
     }
     for name, (res, args) in protos.items():
         fn = getattr(lib, name)
@@ -165,6 +181,28 @@ class Channels:
 
     def code(self, i: int) -> np.ndarray:
         return np.ctypeslib.as_array(self.lib.gpsb_host_channel_code(self.at(i)), (1023,)).copy()
+
+    def position_fix(self):
+        """One position fix from the channels' current observations and ephemerides (gpsb_host_fix_channels, the
+        reference's pntpos without the slicing).  Returns None without a fix, else a dict: latitude / longitude (deg),
+        height (m), ECEF position (m), receiver clock bias (s), azimuth / elevation per channel (deg)."""
+        self.lib.gps_pos_solve_init(self.base)
+        if self.lib.gpsb_host_fix_channels(self.base, self.n) != 1:
+            return None
+        f = FlatFix()
+        self.lib.gpsb_host_fix_state(C.byref(f))
+        dbl = lambda arr: np.array(list(arr), np.uint64).view(np.float64)
+        pos, ecef, azel = dbl(f.final_pos), dbl(f.rr)[:3], dbl(f.azel)[:2 * self.n].reshape(self.n, 2)
+        return dict(lat_deg=float(pos[0]), lon_deg=float(pos[1]), height_m=float(pos[2]), ecef_m=ecef,
+                    clock_bias_s=float(dbl([f.dtr0])[0]), azel_deg=azel)
+
+    def rtcm_observations(self) -> bytes:
+        """The channels' current observations as one RTCM 3 frame, message 1075 (empty when there is nothing to send)."""
+        obsd = (C.c_uint8 * (48 * self.n))()
+        self.lib.sdrobs2obsd(self.base, self.n, obsd)
+        out = (C.c_uint8 * 1200)()
+        n = self.lib.gpsb_rtcm_encode_obs(obsd, self.n, out, 1200)
+        return bytes(out[:n])
 
     def free(self) -> None:
         if self.base:

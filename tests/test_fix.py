@@ -381,6 +381,13 @@ def test_more_than_four_satellites(reference, n):
     assert [x for x in fix_diff(sliced, once, 2 * n) if x[0] != "ns"] == []
     fixed = np.array([dbl(u) for u in once.rr[:3]])
     assert np.linalg.norm(fixed - site) < 100.0
+    # the Python-side wrappers
+    pair.start((0.0, 0.0, 0.0))
+    fix = pair.ch.position_fix()
+    assert fix is not None and np.array_equal(fix["ecef_m"], fixed) and abs(fix["lat_deg"] - 35.7) < 1e-3
+    assert fix["azel_deg"].shape == (n, 2) and np.all(fix["azel_deg"][:, 1] > 5.0)
+    frame = pair.ch.rtcm_observations()
+    assert frame[0] == 0xD3 and len(frame) == 6 + ((frame[1] & 3) << 8 | frame[2])
     pair.lib.gpsb_host_set_sat_cnt(4)
     pair.free()
 
