@@ -285,7 +285,7 @@ def test_sliced_fix_equals_reference(reference, seed):
         assert not fix_diff(got, want), (k, fix_diff(got, want))
         assert got.stat == 5 and got.busy == 0
         fixed = np.array([dbl(u) for u in got.rr[:3]])
-        assert np.linalg.norm(fixed - site) < 300.0            # atmosphere models the truth does not have; geometry of 4
+        assert np.linalg.norm(fixed - site) < 50.0             # ~7 m: the atmosphere models the synthetic truth does not have
         assert abs(dbl(got.final_pos[0]) - lat) < 0.01 and abs(dbl(got.dtr0) - rx_clock) < 2e-6
     # the observation records themselves
     mine = (C.c_uint8 * 192)()
@@ -463,5 +463,5 @@ def test_idle_loop_observations_to_fix(reference):
     distinct = {tuple(f) for f in fixes}
     assert len(distinct) >= 5                                   # and was renewed twice a second
     worst = max(np.linalg.norm(f - site) for f in fixes)
-    assert worst < 2000.0, worst                                # the reference stamps the measurement 68.8 ms late: that, not noise
+    assert worst < 2000.0, worst        # exact observations give ~7 m; the assembly's time tags run a flight time late
     pair.free()
