@@ -1,0 +1,120 @@
+"""A receiver on the ground under four GPS satellites, as a raw IF recording: orbits -> quantised ephemerides -> subframes
+1-3 as navigation bits -> Doppler, code phase and bit timing of each satellite consistent with the geometry ->
+stm32f4_sdr_gps_b200.signal_synth.  Shared by the IF-samples-to-position tests."""
+import numpy as np
+
+from stm32f4_sdr_gps_b200.signal_synth import (CHIP_RATE_HZ, FS_HZ, IF_HZ, MS_SAMPLES, Satellite, ca_code)
+from test_bits_to_position import quantise, subframe_bits
+from test_fix import CLIGHT, geodetic_to_ecef, make_sky, pseudorange
+
+L1_HZ = 1575.42e6
+LEAD_BITS, TAIL_BITS = 50, 45
+FIRST_TOW_COUNT = 52000
+
+
+class PositionScene:
+    def __init__(self, seed=77, lat=52.52, lon=13.40, h=40.0, prns=(4, 11, 19, 26), cn0=50.0):
+        rng = np.random.default_rng(seed)
+        self.prns, self.lat, self.lon, self.h = list(prns), lat, lon, h
+        self.site = geodetic_to_ecef(lat, lon, h)
+        ids = [1, 2, 3]
+        t_sf = (FIRST_TOW_COUNT - 1) * 6.0                      # GPS time at which subframe 1 starts
+        self.t0 = t_sf - 0.02 * LEAD_BITS                       # ... and the first bit of the stream
+        self.t_end = (FIRST_TOW_COUNT + len(ids) - 1) * 6.0     # end of subframe 3 = the time of week its HOW carries
+        t_meas = self.t_end + 0.35
+        c_ms = CLIGHT / 1000.0
+        n_stream = LEAD_BITS + 300 * len(ids) + TAIL_BITS
+        while True:
+            self.sky, self.raws = [], []
+            for el in make_sky(rng, self.site, self.t_end, 4):
+                el["toes"] = el["toc"] = float(int(self.t_end) // 7200 * 7200)
+                raw, back = quantise(el, 1)
+                self.sky.append(back); self.raws.append(raw)
+            flight_m = np.array([pseudorange(el, self.site, t_meas, 0.0) for el in self.sky]) / c_ms       # ms at t_meas
+            rate = np.array([pseudorange(el, self.site, t_meas + 0.5, 0.0) - pseudorange(el, self.site, t_meas - 0.5, 0.0)
+                             for el in self.sky])               # m/s
+            # linear model anchored at the measurement: a signal sent at GPS time tau arrives flight(tau) later
+            flight_at = lambda tau: flight_m + rate / CLIGHT * (tau - t_meas) * 1000.0                    # ms
+            a0 = 102.3 - flight_at(self.t0).min()               # receiver ms of a zero-delay arrival of the stream start
+            first = a0 + flight_at(self.t0)                     # receiver ms at which stream bit 1 starts arriving
+            # The bit synchroniser only sees a data-bit edge that falls inside a 4-ms slot, and only refines the one at
+            # slot position 2 (nav_data.c:87-138).  The reference's 17-ms channel schedule walks every alignment past
+            # that window; with every millisecond processed in place (index = ms % 4) the alignment is fixed, so the
+            # scene is drawn until each satellite's edges land there: the millisecond that shows the sign flip - the one
+            # holding the edge if the edge comes in its first half, else the next - is 2 modulo 4.
+            whole, part = np.floor(first).astype(int), first % 1.0
+            flip_ms = np.where(part < 0.5, whole, whole + 1)
+            clear = ((part > 0.15) & (part < 0.42)) | ((part > 0.58) & (part < 0.85))     # and the code phase never wraps
+            if np.all(flip_ms % 4 == 2) and np.all(clear) and np.all(np.abs(rate) < 780.0):
+                break
+        self.a0, self.rate, self.flight_m, self.t_meas = a0, rate, flight_m, t_meas
+        self.doppler = -rate / (CLIGHT / L1_HZ)
+        self.offset_ms = np.floor(first).astype(int)
+        self.code_phase = (first - self.offset_ms) * 16368.0
+        sats = []
+        for i, prn in enumerate(self.prns):
+            stream = np.concatenate([rng.integers(0, 2, 1 + LEAD_BITS, dtype=np.uint8)] +
+                                    [subframe_bits(rng, sf, FIRST_TOW_COUNT + k, self.raws[i]) for k, sf in enumerate(ids)] +
+                                    [rng.integers(0, 2, TAIL_BITS + 40, dtype=np.uint8)])
+            sats.append(Satellite(prn=prn, doppler_hz=float(self.doppler[i]), code_phase_samples=float(self.code_phase[i]),
+                                  cn0_dbhz=cn0, nav_bits=stream, nav_bit_offset_ms=int(self.offset_ms[i])))
+        self.sats = sats
+        # receiver ms at which the end of subframe 3 of the latest satellite has arrived, plus the first filter window
+        last_edge = (a0 + (self.t_end - self.t0) * 1000.0 + flight_m).max()
+        self.n_first = int(last_edge) + 120
+        self.n_second = 300
+        self.n_ms = self.n_first + self.n_second + 8
+        self.seed = seed
+
+    def with_carrier_phases(self, phases):
+        for s, p in zip(self.sats, phases):
+            s.carrier_phase_rad = float(p)
+
+    def synthesize(self, n_ms=None, only=None):
+        sats = self.sats if only is None else [self.sats[only]]
+        return synthesize_long(sats, n_ms or self.n_ms, self.seed)
+
+
+def _block(args):
+    sats, m0, m1, seed = args
+    rng = np.random.default_rng([seed, m0])
+    t = np.arange(m0 * MS_SAMPLES, m1 * MS_SAMPLES, dtype=np.float64) / FS_HZ
+    acc = rng.standard_normal(t.size, dtype=np.float32)
+    for s in sats:
+        chips = np.concatenate([ca_code(s.prn), ca_code(s.prn)[:1]]).astype(np.float32) * 2 - 1
+        data = np.asarray(s.nav_bits, np.float32) * 2 - 1
+        amp = np.float32(np.sqrt(4.0 * 10.0 ** (s.cn0_dbhz / 10.0) / FS_HZ))
+        code_rate = CHIP_RATE_HZ * (1.0 + s.doppler_hz / 1575.42e6)
+        chip_pos = (t - s.code_phase_samples / FS_HZ) * code_rate
+        epoch = np.floor(chip_pos * (1.0 / 1023.0))
+        chip = (chip_pos - epoch * 1023.0).astype(np.int32)                 # 0..1023 (1023 only by rounding: chip 0 again)
+        bit = np.floor((epoch - s.nav_bit_offset_ms) * 0.05) + 1.0
+        np.clip(bit, 0, data.size - 1, out=bit)
+        carrier = np.cos((2.0 * np.pi * (IF_HZ + s.doppler_hz)) * t + s.carrier_phase_rad).astype(np.float32)
+        carrier *= chips[chip]
+        carrier *= data[bit.astype(np.int32)]
+        carrier *= amp
+        acc += carrier
+    return m0, np.packbits((acc < 0).reshape(m1 - m0, MS_SAMPLES), axis=1, bitorder="little")
+
+
+def synthesize_long(sats, n_ms, seed, block_ms=50, workers=None):
+    """The signal model of stm32f4_sdr_gps_b200.signal_synth.synthesize (1-bit samples of code x data x carrier in white
+    noise, packed LSB first) for recordings of tens of seconds: independent 50-ms blocks (noise seeded per block) on a
+    thread per core.  Returns (n_ms, 2046) uint8; the result does not depend on the number of workers."""
+    import os
+    from multiprocessing.pool import ThreadPool
+    jobs = [(sats, m0, min(n_ms, m0 + block_ms), seed) for m0 in range(0, n_ms, block_ms)]
+    out = np.empty((n_ms, MS_SAMPLES // 8), np.uint8)
+    workers = workers or max(1, min(32, (os.cpu_count() or 2) - 1, len(jobs)))
+    if workers == 1:
+        results = map(_block, jobs)
+    else:
+        pool = ThreadPool(workers)                              # numpy releases the GIL inside the array operations
+        results = pool.imap_unordered(_block, jobs)
+    for m0, block in results:
+        out[m0:m0 + block.shape[0]] = block
+    if workers > 1:
+        pool.close()
+        pool.join()
+    return out

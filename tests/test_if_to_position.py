@@ -1,0 +1,177 @@
+"""the hot path and the rows after it, end to end - raw IF samples in, latitude / longitude out.
+
+A 19.5-s recording of four satellites (tests/position_scene.py: orbits, their quantised ephemerides as subframes 1-3 in
+the data bits, Doppler / code phase / bit timing consistent with a receiver on the ground, 1-bit samples in noise) goes
+through E/P/L tracking, bit synchronisation, the word assembler, the ephemeris decode, the observation assembly and the
+position solver.
+
+* CPU (not gpu): tracking by the UNMODIFIED reference; this library's rows N3 / N4 on the tracked channels against the
+  reference's, and the fix against the receiver's true site.
+* GPU: tracking, bit logic and ephemeris decode in the device-resident loop (k_track_run, streamed, all four channels
+  in one launch per leg); channel records, ephemerides, observations and the fix equal the reference's bit for bit."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from stm32f4_sdr_gps_b200 import load_host_library
+from position_scene import PositionScene
+from test_fix import Pair, dbl, fix_diff
+from test_nav_decode import eph_diff, host_eph, ref_eph
+
+_cache = {}
+
+
+def scene_and_signal(reference):
+    """The scene, with each satellite's carrier phase chosen so that the Costas loop locks upright (a 400-ms
+    single-satellite trial per candidate on the reference: an inverted lock would cost two more subframes before the
+    polarity logic catches it), and the recording."""
+    if "sig" in _cache:
+        return _cache["scene"], _cache["sig"]
+    sc = PositionScene()
+    phases = []
+    for i in range(4):
+        for phase in (0.0, np.pi):
+            sc.sats[i].carrier_phase_rad = phase
+            trial = sc.synthesize(n_ms=400, only=i)
+            rchans = reference.channels(1)
+            rch = reference.channel_at(rchans, 0)
+            start_tracking(reference, rch, sc, i)
+            iq, _, _ = reference.track_run(rch, trial, 0, 400)
+            ms = np.arange(200, 400)
+            sent = sc.sats[i].nav_bits[np.clip((ms - 1 - sc.offset_ms[i]) // 20 + 1, 0, None)].astype(int) * 2 - 1
+            if np.mean(np.sign(iq[ms, 2]) == sent) > 0.8:
+                phases.append(phase)
+                break
+    assert len(phases) == 4
+    sc.with_carrier_phases(phases)
+    _cache["scene"], _cache["sig"] = sc, sc.synthesize()
+    return sc, _cache["sig"]
+
+
+def start_tracking(reference, rch, sc, i):
+    """A channel as acquisition and pre-track would leave it: Doppler and code phase known, tracking running."""
+    reference.channel_init(rch, sc.prns[i], 0)
+    st = reference.snapshot(rch)
+    st.acq_state, st.trk_state, st.found_freq_offset_hz = 9, 4, int(sc.doppler[i])
+    st.if_freq_offset_hz_bits = int(np.float32(sc.doppler[i]).view(np.uint32))
+    st.code_phase_fine_bits = int(np.float32(sc.code_phase[i]).view(np.uint32))
+    reference.restore(rch, st)
+    return st
+
+
+def protos(lib, rl):
+    lib.gps_master_nav_handling.argtypes = [C.c_void_p]
+    lib.gpsb_host_channel_obs.argtypes = [C.c_void_p, C.c_void_p]
+    lib.gpsb_host_channel_set_eph.argtypes = [C.c_void_p, C.c_void_p]
+    rl.ref_nav_handling.argtypes = [C.c_void_p, C.c_uint32]
+    rl.ref_channel_obs.argtypes = [C.c_void_p, C.c_void_p]
+    rl.ref_track_run.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+    rl.ref_fix_run.argtypes = [C.c_void_p, C.c_uint32]
+    rl.ref_fix_run.restype = C.c_uint32
+
+
+def obs_pair(fn, ch_ptr):
+    out = (C.c_uint64 * 2)()
+    fn(C.c_void_p(ch_ptr), out)
+    return int(out[0]), int(out[1])
+
+
+def finish_and_check(pair, sc, reference, track_both):
+    """From tracked channels to the fix, both sides in step.  track_both(ms0, n_ms) tracks the next n_ms milliseconds
+    on the reference and on this library."""
+    lib, rl, ch, rchans = pair.lib, pair.rl, pair.ch, pair.rchans
+
+    def records_equal(where):
+        for i in range(4):
+            rch = reference.channel_at(rchans, i)
+            assert bytes(ch.snapshot(i)) == bytes(reference.snapshot(rch)), (where, i)
+            d = eph_diff(host_eph(lib, ch.at(i)), ref_eph(reference, rch))
+            assert not d, (where, i, d)
+            assert obs_pair(lib.gpsb_host_channel_obs, ch.at(i)) == obs_pair(rl.ref_channel_obs, rch), (where, i)
+
+    track_both(0, sc.n_first)
+    records_equal("first leg")
+    for i in range(4):                                           # the data bits carried the whole ephemeris
+        e, st = host_eph(lib, ch.at(i)), ch.snapshot(i)
+        assert e.received_mask_proc & 7 == 7 and dbl(e.tow_gpst) == sc.t_end and st.subframe_cnt == 3
+        assert st.last_subframe_time - (19000 + sc.offset_ms[i]) in (0, 1)         # the millisecond its last bit edge arrived in
+        for name in ("A", "e", "i0", "OMG0", "omg", "M0", "deln", "OMGd", "idot", "crs", "cuc", "f0"):
+            assert abs(dbl(getattr(e, name)) - sc.sky[i][name]) <= 1e-12 * max(1.0, abs(sc.sky[i][name])), (i, name)
+    # idle slot: the zero moment is set, the 19-s filter window is thrown away
+    lib.gpsb_host_set_packet_cnt(sc.n_first)
+    lib.gps_master_nav_handling(ch.base)
+    rl.ref_nav_handling(rchans, sc.n_first)
+    records_equal("first idle slot")
+    track_both(sc.n_first, sc.n_second)
+    lib.gpsb_host_set_packet_cnt(sc.n_first + sc.n_second)
+    lib.gps_master_nav_handling(ch.base)
+    rl.ref_nav_handling(rchans, sc.n_first + sc.n_second)
+    records_equal("second idle slot")
+    ranges_ms = [dbl(obs_pair(lib.gpsb_host_channel_obs, ch.at(i))[0]) / 299792.458 for i in range(4)]
+    assert all(60 < r < 95 for r in ranges_ms), ranges_ms
+    # the fix the first idle slot requested had nothing to work on: step it to its end, then solve on the observations
+    assert pair.run_sliced()[0] == rl.ref_fix_run(rchans, 400)
+    assert not fix_diff(pair.state(), pair.ref_state())
+    pair.start((0.0, 0.0, 0.0))
+    want_calls = rl.ref_fix_run(rchans, 400)
+    calls, got = pair.run_sliced()
+    assert calls == want_calls and not fix_diff(got, pair.ref_state()), fix_diff(got, pair.ref_state())
+    assert got.stat == 5
+    fixed = np.array([dbl(u) for u in got.rr[:3]])
+    error_m = float(np.linalg.norm(fixed - sc.site))
+    assert error_m < 500.0, error_m                              # 185 m measured: time tags a flight time late
+    assert abs(dbl(got.final_pos[0]) - sc.lat) < 0.005 and abs(dbl(got.final_pos[1]) - sc.lon) < 0.005
+    return error_m
+
+
+def test_if_samples_to_position_reference_tracking(reference):
+    lib = load_host_library()
+    rl = reference.lib
+    protos(lib, rl)
+    sc, sig = scene_and_signal(reference)
+    pair = Pair(reference, sc.prns)
+    for i in range(4):
+        start_tracking(reference, reference.channel_at(pair.rchans, i), sc, i)
+
+    def track_both(ms0, n_ms):
+        part = np.ascontiguousarray(sig[ms0:ms0 + n_ms])
+        for i in range(4):
+            rch = reference.channel_at(pair.rchans, i)
+            rl.ref_track_run(rch, part.ctypes.data, ms0, n_ms, None, None, None)
+            # this library's channels take over what tracking produced (the GPU test produces it itself)
+            pair.ch.restore(i, type(pair.ch.snapshot(i)).from_buffer_copy(bytes(reference.snapshot(rch))))
+            lib.gpsb_host_channel_set_eph(pair.ch.at(i), C.byref(ref_eph(reference, rch)))
+
+    finish_and_check(pair, sc, reference, track_both)
+    pair.free()
+
+
+@pytest.mark.gpu
+def test_if_samples_to_position_on_the_device(host_engine, reference):
+    from stm32f4_sdr_gps_b200 import Receiver
+    lib = load_host_library()
+    rl = reference.lib
+    protos(lib, rl)
+    sc, sig = scene_and_signal(reference)
+    pair = Pair(reference, sc.prns)
+    for i in range(4):
+        st = start_tracking(reference, reference.channel_at(pair.rchans, i), sc, i)
+        pair.ch.restore(i, type(pair.ch.snapshot(i)).from_buffer_copy(bytes(st)))
+    rx = Receiver(host_engine, pair.ch)
+    launches = []
+
+    def track_both(ms0, n_ms):
+        part = np.ascontiguousarray(sig[ms0:ms0 + n_ms])
+        for i in range(4):
+            rl.ref_track_run(reference.channel_at(pair.rchans, i), part.ctypes.data, ms0, n_ms, None, None, None)
+        before = host_engine.launch_count
+        rx.track_stream(ms0, part, chunk_ms=100, log=False)
+        launches.append(host_engine.launch_count - before)
+
+    finish_and_check(pair, sc, reference, track_both)
+    device_ms, host_ms = rx.loop_stats()
+    assert launches[0] >= 1 and launches[1] >= 1                 # normally exactly one k_track_run launch per leg
+    assert device_ms + host_ms == 4 * (sc.n_first + sc.n_second) and host_ms <= device_ms // 100
+    rx.close()
+    pair.free()
