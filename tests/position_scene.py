@@ -61,7 +61,10 @@ class PositionScene:
         self.sats = sats
         # receiver ms at which the end of subframe 3 of the latest satellite has arrived, plus the first filter window
         last_edge = (a0 + (self.t_end - self.t0) * 1000.0 + flight_m).max()
-        self.n_first = int(last_edge) + 120
+        # legs end on a 4-ms slot boundary: the reference keeps the samples of the slot in progress in function statics
+        # shared by all channels (nav_data.c:48-51), so a leg cut inside a slot would hand channel k the leftovers of
+        # channel k-1 there, while this library keeps them per channel
+        self.n_first = (int(last_edge) + 120 + 3) // 4 * 4
         self.n_second = 300
         self.n_ms = self.n_first + self.n_second + 8
         self.seed = seed

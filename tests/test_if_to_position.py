@@ -85,7 +85,14 @@ def finish_and_check(pair, sc, reference, track_both):
     def records_equal(where):
         for i in range(4):
             rch = reference.channel_at(rchans, i)
-            assert bytes(ch.snapshot(i)) == bytes(reference.snapshot(rch)), (where, i)
+            mine, theirs = ch.snapshot(i), reference.snapshot(rch)
+            if bytes(mine) != bytes(theirs):
+                differing = [(n, bytes(getattr(mine, n)) if hasattr(getattr(mine, n), "__len__") else getattr(mine, n),
+                              bytes(getattr(theirs, n)) if hasattr(getattr(theirs, n), "__len__") else getattr(theirs, n))
+                             for n, _ in mine._fields_
+                             if (bytes(getattr(mine, n)) if hasattr(getattr(mine, n), "__len__") else getattr(mine, n)) !=
+                             (bytes(getattr(theirs, n)) if hasattr(getattr(theirs, n), "__len__") else getattr(theirs, n))]
+                raise AssertionError((where, i, differing))
             d = eph_diff(host_eph(lib, ch.at(i)), ref_eph(reference, rch))
             assert not d, (where, i, d)
             assert obs_pair(lib.gpsb_host_channel_obs, ch.at(i)) == obs_pair(rl.ref_channel_obs, rch), (where, i)
