@@ -71,6 +71,10 @@ def protos(lib, rl):
     rl.ref_fix_run.restype = C.c_uint32
 
 
+def plain(v):
+    return bytes(v) if hasattr(v, "__len__") else v
+
+
 def obs_pair(fn, ch_ptr):
     out = (C.c_uint64 * 2)()
     fn(C.c_void_p(ch_ptr), out)
@@ -86,13 +90,10 @@ def finish_and_check(pair, sc, reference, track_both):
         for i in range(4):
             rch = reference.channel_at(rchans, i)
             mine, theirs = ch.snapshot(i), reference.snapshot(rch)
-            if bytes(mine) != bytes(theirs):
-                differing = [(n, bytes(getattr(mine, n)) if hasattr(getattr(mine, n), "__len__") else getattr(mine, n),
-                              bytes(getattr(theirs, n)) if hasattr(getattr(theirs, n), "__len__") else getattr(theirs, n))
-                             for n, _ in mine._fields_
-                             if (bytes(getattr(mine, n)) if hasattr(getattr(mine, n), "__len__") else getattr(mine, n)) !=
-                             (bytes(getattr(theirs, n)) if hasattr(getattr(theirs, n), "__len__") else getattr(theirs, n))]
-                raise AssertionError((where, i, differing))
+            if bytes(mine) != bytes(theirs):                     # name the fields: a GPU run cannot be stepped through
+                raise AssertionError((where, i, [(n, plain(getattr(mine, n)), plain(getattr(theirs, n)))
+                                                 for n, _ in mine._fields_
+                                                 if plain(getattr(mine, n)) != plain(getattr(theirs, n))]))
             d = eph_diff(host_eph(lib, ch.at(i)), ref_eph(reference, rch))
             assert not d, (where, i, d)
             assert obs_pair(lib.gpsb_host_channel_obs, ch.at(i)) == obs_pair(rl.ref_channel_obs, rch), (where, i)
