@@ -315,6 +315,16 @@ int gpsb_rx_track_stream(gpsb_rx* rx, uint32_t ms0, uint32_t n_ms, const uint8_t
 /* Same, fed with the MAX2769-native 2-bit I / 2-bit Q container (one byte per sample, n_ms * 16368 bytes). */
 int gpsb_rx_track_stream_iq2(gpsb_rx* rx, uint32_t ms0, uint32_t n_ms, const uint8_t* samples, uint32_t chunk_ms,
                              int16_t* iq_log, int8_t* nav_log);
+/* The same run fed from a recording on disk (row N1, host/ingest.c).  The sample of ms0 starts at first_byte.  Default
+ * container: the MCU's memory image of the SPI stream (signal_capture.c:9-16), 2046 bytes per millisecond, LSB first -
+ * mapped and streamed as it lies.  GPSB_FILE_MSB_FIRST: first sample of each byte in bit 7 (bytes are bit-reversed on
+ * the way in).  GPSB_FILE_IQ2: 2-bit I / 2-bit Q, one byte per sample.  GPSB_ERR_ARG when the file is missing or
+ * shorter than the run.  gpsb_file_ms: whole milliseconds available from first_byte on (negative status on error). */
+#define GPSB_FILE_MSB_FIRST 1u
+#define GPSB_FILE_IQ2       2u
+int gpsb_rx_track_file(gpsb_rx* rx, const char* path, uint64_t first_byte, uint32_t ms0, uint32_t n_ms, uint32_t flags,
+                       int16_t* iq_log, int8_t* nav_log);
+int64_t gpsb_file_ms(const char* path, uint64_t first_byte, uint32_t flags);
 /* Where gpsb_rx_track_run keeps the loop filters.  AUTO (default) and DEVICE: the whole run is one launch of the
  * device-resident loop k_track_run (include/gpsb.h, gpsb_track_loop) for every channel that is tracking; its
  * float discriminators are the fdlibm atanf/atan2f glibc ships and CUDA's double atan2, checked against the host

@@ -122,6 +122,8 @@ def load_host_library(path: Path | None = None) -> C.CDLL:
         "gpsb_rx_track_ms": (i32, [vp, u32]), "gpsb_rx_track_run": (i32, [vp, u32, u32, vp, vp]),
         "gpsb_rx_track_stream": (i32, [vp, u32, u32, vp, u32, vp, vp]),
         "gpsb_rx_track_stream_iq2": (i32, [vp, u32, u32, vp, u32, vp, vp]),
+        "gpsb_rx_track_file": (i32, [vp, C.c_char_p, C.c_uint64, u32, u32, u32, vp, vp]),
+        "gpsb_file_ms": (C.c_int64, [C.c_char_p, C.c_uint64, u32]),
         "gpsb_rx_acquire_ms": (i32, [vp, u32]),
         "gpsb_rx_set_threads": (None, [vp, u32]),
         "gpsb_rx_set_loop_site": (None, [vp, i32]),
@@ -257,6 +259,18 @@ class Receiver:
         nav = np.zeros((n_ms, n), np.int8) if log else None
         self._check(self.lib.gpsb_rx_track_stream(self._rx, ms0, n_ms, packed.ctypes.data, chunk_ms,
                                                   iq.ctypes.data if log else None, nav.ctypes.data if log else None))
+        return iq, nav
+
+    def track_file(self, path, ms0: int, n_ms: int, first_byte: int = 0, msb_first: bool = False, iq2: bool = False,
+                   log: bool = True):
+        """gpsb_rx_track_file: n_ms milliseconds of a recording on disk, streamed into the ring behind the running loop.
+        msb_first: first sample of each byte in bit 7; iq2: the 2-bit I / 2-bit Q container (one byte per sample)."""
+        n = self.channels.n
+        iq = np.zeros((n_ms, n, 6), np.int16) if log else None
+        nav = np.zeros((n_ms, n), np.int8) if log else None
+        flags = (1 if msb_first else 0) | (2 if iq2 else 0)
+        self._check(self.lib.gpsb_rx_track_file(self._rx, str(path).encode(), first_byte, ms0, n_ms, flags,
+                                                iq.ctypes.data if log else None, nav.ctypes.data if log else None))
         return iq, nav
 
     def set_threads(self, n: int) -> None:
