@@ -539,6 +539,13 @@ uint32_t ref_fix_run(gps_ch_t* chans, uint32_t max_calls)
     return calls;
 }
 
+/* exactly n calls of gps_pos_solve on the channels' current observations (a solve left in flight) */
+void ref_fix_steps(gps_ch_t* chans, uint32_t n)
+{
+    sdrobs2obsd(chans, GPS_SAT_CNT, g_ref_obsd);
+    for (uint32_t k = 0; k < n; k++) gps_pos_solve(g_ref_obsd);
+}
+
 /* the reference's one-shot pntpos (solving.c:153) into gps_sol, then the conversion gps_pos_solve would do */
 extern nav_t nav_data;
 int ref_fix_once(gps_ch_t* chans)

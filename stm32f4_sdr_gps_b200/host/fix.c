@@ -39,11 +39,14 @@
 
 enum { FX_IDLE = 0, FX_SATELLITES, FX_ESTIMATE };
 
+/* broadcast data: the channels' own ephemeris records (gps_pos_solve_init) and the ionosphere coefficients */
 typedef struct {
-    /* broadcast data: the channels' own ephemeris records (gps_pos_solve_init) and the ionosphere coefficients */
     const eph_t* eph[FX_MAX_SATS];
     int n_eph;
     double ion[8];
+} fx_nav;
+
+typedef struct {
     /* satellite states at the transmission times */
     double pv[6 * FX_MAX_SATS], clk[2 * FX_MAX_SATS], pv_var[FX_MAX_SATS], resid[FX_MAX_SATS];
     int health[FX_MAX_SATS], used[FX_MAX_SATS];
@@ -59,7 +62,10 @@ typedef struct {
     uint32_t last_request_ms;
 } fx_state;
 
-static fx_state g_fx;
+static fx_nav g_nav;
+static fx_state g_fx;                            /* the sliced driver's work area (gps_pos_solve) */
+static fx_state g_once;                          /* the one-shot driver's: a fix may be taken while a sliced one is in flight,
+                                                    as with the reference's pntpos / pntpos_iterative */
 
 /* solving.c:48-52: results, under the names the reference's display code reads them by */
 sol_t gps_sol;
@@ -314,17 +320,17 @@ static double fx_tropo_delay(const double* geo, const double* az_el, double humi
 /* ------------------------------------------------------------------------------------------ broadcast orbits */
 
 /* solving.c:1057-1079 with iode < 0: the record of this satellite whose toe is closest to `when`, within 2 h */
-static const eph_t* fx_pick_eph(const fx_state* s, gtime_t when, int sat)
+static const eph_t* fx_pick_eph(gtime_t when, int sat)
 {
     const double limit = 7200.0 + 1.0;
     double best = limit + 1.0, age;
     int pick = -1;
-    for (int i = 0; i < s->n_eph; i++) {
-        if (s->eph[i]->sat != sat) continue;
-        if ((age = fabs(timediff(s->eph[i]->toe, when))) > limit) continue;
+    for (int i = 0; i < g_nav.n_eph; i++) {
+        if (g_nav.eph[i]->sat != sat) continue;
+        if ((age = fabs(timediff(g_nav.eph[i]->toe, when))) > limit) continue;
         if (age <= best) { pick = i; best = age; }
     }
-    return pick < 0 ? NULL : s->eph[pick];
+    return pick < 0 ? NULL : g_nav.eph[pick];
 }
 
 /* solving.c:1044-1054: clock polynomial, the argument corrected by its own value twice */
@@ -394,7 +400,7 @@ static int fx_satellite(fx_state* s, gtime_t teph, const obsd_t* obs, int i)
     s->health[i] = 0;
 
     gtime_t t = timeadd(obs[i].time, -obs[i].P[0] / FX_CLIGHT);          /* transmission time by the satellite clock */
-    const eph_t* eph = fx_pick_eph(s, teph, obs[i].sat);
+    const eph_t* eph = fx_pick_eph(teph, obs[i].sat);
     if (!eph) return 0;
     t = timeadd(t, -fx_clock_bias(t, eph));
 
@@ -432,12 +438,12 @@ static void fx_measure(fx_state* s, const obsd_t* obs, int i, int* accepted)
 
     double P = obs[i].P[0];
     double tgd = 0.0;                                                    /* group delay, solving.c:600-610 */
-    for (int k = 0; k < s->n_eph; k++)
-        if (s->eph[k]->sat == obs[i].sat) { tgd = FX_CLIGHT * s->eph[k]->tgd[0]; break; }
+    for (int k = 0; k < g_nav.n_eph; k++)
+        if (g_nav.eph[k]->sat == obs[i].sat) { tgd = FX_CLIGHT * g_nav.eph[k]->tgd[0]; break; }
     P -= tgd;
     if (s->health[i]) return;
 
-    dion = fx_iono_delay(obs[i].time, s->ion, s->geo, az_el);
+    dion = fx_iono_delay(obs[i].time, g_nav.ion, s->geo, az_el);
     vion = FX_SQ(dion * 0.5);
     dtrp = fx_tropo_delay(s->geo, az_el, 0.7);
     vtrp = FX_SQ(0.3 / (sin(az_el[1]) + 0.1));
@@ -596,8 +602,8 @@ void gps_pos_solve_init(gps_ch_t* channels)
 {
     uint32_t n = gpsb_host_sat_cnt();
     if (n > FX_MAX_SATS) n = FX_MAX_SATS;
-    for (uint32_t i = 0; channels && i < n; i++) g_fx.eph[i] = &channels[i].eph_data.eph;
-    g_fx.n_eph = channels ? (int)n : 0;
+    for (uint32_t i = 0; channels && i < n; i++) g_nav.eph[i] = &channels[i].eph_data.eph;
+    g_nav.n_eph = channels ? (int)n : 0;
 }
 
 /* solving.c:117-140: one slice per call until solving_is_busy() drops; the call after the fix converts it to
@@ -610,7 +616,7 @@ void gps_pos_solve(obsd_t* obs_p)
         final_pos[0] = final_pos[0] * FX_R2D;
         final_pos[1] = final_pos[1] * FX_R2D;
         s->converting = 0;
-    } else if (obs_p && fx_step(s, obs_p, s->n_eph, &gps_sol) > 0) {
+    } else if (obs_p && fx_step(s, obs_p, g_nav.n_eph, &gps_sol) > 0) {
         s->converting = 1;
     }
 }
@@ -640,11 +646,13 @@ void gps_master_calculate_pos(gps_ch_t* channels)
 /* The whole fix in one call (solving.c:153-181, pntpos, with estpos :376-448 and rescode :711-793), then the geodetic
  * conversion.  Differences from the sliced driver that the reference has too: a repeated satellite number drops both
  * entries, `ns` counts this pass only, and at most 10 passes.  One deliberate difference: the reference ignores a
- * singular normal matrix and goes on with stale increments; this returns "no fix".  Returns 1 = fix, 0 = none. */
+ * singular normal matrix and goes on with stale increments; this returns "no fix".  Has its own work area: it may be
+ * called while a sliced solve is in flight (both write gps_sol / azel when handed them, like the reference's two
+ * drivers).  Returns 1 = fix, 0 = none. */
 int gpsb_host_fix_once(const obsd_t* obs, int n, sol_t* sol, double pos_deg[3])
 {
-    fx_state* s = &g_fx;
-    if (!obs || !sol || s->solving || s->converting) return 0;
+    fx_state* s = &g_once;
+    if (!obs || !sol) return 0;
     sol->stat = SOLQ_NONE;
     if (n <= 0 || n > FX_MAX_SATS) return 0;
     sol->time = obs[0].time;
@@ -695,7 +703,7 @@ void gpsb_host_fix_set_start(const double ecef_m[3])
 
 void gpsb_host_fix_set_iono(const double coeff[8])
 {
-    for (int k = 0; k < 8; k++) g_fx.ion[k] = coeff ? coeff[k] : 0.0;
+    for (int k = 0; k < 8; k++) g_nav.ion[k] = coeff ? coeff[k] : 0.0;
 }
 
 /* Forget a solve in flight, the request timer and the last fix (the reference has no such entry: its statics live

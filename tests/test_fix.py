@@ -363,6 +363,33 @@ def test_one_shot_fix_equals_reference(reference, seed):
     pair.free()
 
 
+def test_one_shot_fix_while_a_sliced_one_is_in_flight(reference):
+    """The reference's pntpos and pntpos_iterative do not share work arrays, only the outputs: a one-shot fix taken
+    in the middle of a sliced solve (here after 3, 6 and 11 of its slices) succeeds, and the sliced solve then runs
+    to its end exactly as the reference's does - same number of calls, same outputs."""
+    rng = np.random.default_rng(5150)
+    prns = [1, 10, 20, 30]
+    pair = Pair(reference, prns)
+    pair.rl.ref_fix_steps.argtypes = [C.c_void_p, C.c_uint32]
+    site = geodetic_to_ecef(-12.0, 130.8, 30.0)
+    sky = make_sky(rng, site, 250000.0, 4)
+    for k, after in enumerate((3, 6, 11)):
+        load_scene(pair, sky, site, 250000.0 + k, 2e-4, prns)
+        obsd = (C.c_uint8 * 192)()
+        pair.lib.sdrobs2obsd(pair.ch.base, 4, obsd)
+        for _ in range(after):
+            pair.lib.gps_pos_solve(obsd)
+        pair.rl.ref_fix_steps(pair.rchans, after)
+        assert pair.lib.solving_is_busy() and pair.ref_state().busy
+        assert pair.lib.gpsb_host_fix_channels(pair.ch.base, 4) == pair.rl.ref_fix_once(pair.rchans) == 1
+        assert not fix_diff(pair.state(), pair.ref_state()), (after, fix_diff(pair.state(), pair.ref_state()))
+        want_calls = pair.rl.ref_fix_run(pair.rchans, 400)
+        calls, got = pair.run_sliced()
+        assert calls == want_calls and not fix_diff(got, pair.ref_state()), (after, calls, want_calls)
+        assert got.stat == 5 and not got.busy
+    pair.free()
+
+
 @pytest.mark.parametrize("n", [5, 8, 12])
 def test_more_than_four_satellites(reference, n):
     """Beyond the reference's GPS_SAT_CNT: sliced and one-shot drivers agree with each other, and the fix tightens."""

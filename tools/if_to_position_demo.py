@@ -56,7 +56,6 @@ def main():
             legs.append(time.perf_counter() - t0)
             lib.gpsb_host_set_packet_cnt(ms0 + n)
             lib.gps_master_nav_handling(ch.base)
-        lib.gpsb_host_fix_reset()
         t0 = time.perf_counter()
         fix = ch.position_fix()
         t_fix = time.perf_counter() - t0
