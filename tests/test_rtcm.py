@@ -262,3 +262,53 @@ def test_channels_to_frames_through_the_master(reference):
     assert sent[4][1] == fr.ref(rl.ref_rtcm_obs, pair.rchans)
     pair.free()
     fr.close()
+
+
+def test_ephemeris_frame_round_trip_without_the_reference():
+    """Navigation-message integers -> subframes 1-3 (encoder written from IS-GPS-200) -> word assembler + decoder ->
+    eph_t -> message 1019 -> a field parser written from RTCM 10403 table 3.5-21: the integers come back.  The
+    navigation message and message 1019 use the same scale factors, so this checks the decoder and the encoder against
+    the standards, not against the reference."""
+    from test_bits_to_position import quantise, subframe_bits
+    from test_fix import geodetic_to_ecef, make_sky
+    lib = load_host_library()
+    lib.gpsb_host_feed_nav_bits.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
+    lib.sendrtcmnav.argtypes = [C.c_void_p]
+    lib.gpsb_host_set_rtcm_sink.argtypes = [SINK, C.c_void_p]
+    frames = []
+    cb = SINK(lambda p, n: frames.append(bytes(p[:n])))
+    lib.gpsb_host_set_rtcm_sink(cb, None)
+    rng = np.random.default_rng(3)
+    site = geodetic_to_ecef(0.0, 0.0, 0.0)
+    layout = [("msg", 12, 0), ("sat", 6, 0), ("week", 10, 0), ("sva", 4, 0), ("code", 2, 0), ("idot", 14, 1), ("iode", 8, 0),
+              ("toc", 16, 0), ("af2", 8, 1), ("af1", 16, 1), ("af0", 22, 1), ("iodc", 10, 0), ("crs", 16, 1), ("deln", 16, 1),
+              ("M0", 32, 1), ("cuc", 16, 1), ("e", 32, 0), ("cus", 16, 1), ("sqrtA", 32, 0), ("toe", 16, 0), ("cic", 16, 1),
+              ("OMG0", 32, 1), ("cis", 16, 1), ("i0", 32, 1), ("crc", 16, 1), ("omg", 32, 1), ("OMGd", 24, 1), ("tgd", 8, 1),
+              ("svh", 6, 0), ("flag", 1, 0), ("fit", 1, 0)]
+    for trial, prn in enumerate((2, 17, 31)):
+        el = make_sky(rng, site, 90000.0, 1)[0]
+        el["toes"] = el["toc"] = 86400.0 + 7200.0 * trial
+        raw, _ = quantise(el, sva=trial + 1)
+        stream = np.concatenate([rng.integers(0, 2, 30, dtype=np.uint8)] +
+                                [subframe_bits(rng, sf, 15000 + k, raw) for k, sf in enumerate((1, 2, 3))])
+        ch = Channels([prn])
+        lib.gpsb_host_feed_nav_bits(ch.at(0), stream.ctypes.data, stream.size, 1000)
+        assert host_eph(lib, ch.at(0)).received_mask & 7 == 7
+        frames.clear()
+        lib.sendrtcmnav(ch.at(0))
+        frame = frames[-1]
+        check_frame(frame, 1019)
+        got, at = {}, 24
+        for name, bits_, signed in layout:
+            got[name] = field(frame, at, bits_, bool(signed))
+            at += bits_
+        assert at == 24 + 488
+        assert got["sat"] == prn and got["week"] == WEEK % 1024 and got["sva"] == trial + 1 and got["code"] == 1
+        for name in ("idot", "iode", "toc", "af2", "af1", "af0", "iodc", "crs", "deln", "M0", "cuc", "e", "cus", "sqrtA",
+                     "toe", "cic", "OMG0", "cis", "i0", "crc", "omg", "OMGd", "tgd"):
+            assert got[name] == raw[name], (prn, name, got[name], raw[name])
+        # the decoder keeps the raw fit-interval FLAG in eph->fit (nav_data_decode.c) where the encoder expects hours
+        # (rtcm3e.c:218, fit > 0 ? 0 : 1): a flag of 0 goes out as DF137 = 1 - the reference's behaviour, kept
+        assert got["svh"] == 0 and got["fit"] == 1
+        ch.free()
+    lib.gpsb_host_set_rtcm_sink(SINK(0), None)
