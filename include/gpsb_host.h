@@ -12,11 +12,16 @@
  *   (2) batched forms (gpsb_rx_*) that evaluate ALL channels of a millisecond - or a whole cold-start
  *       sweep - in one GPU launch; these are what a B200 deployment calls.
  *
+ *   (3) the steps that follow the path in the reference: subframe decode, observation
+ *       assembly, position fix and RTCM frames under the reference's names (PM/GPS/nav_data_decode.h,
+ *       RTK/solving.h, obs_publish.h) - plain host C, bit-exact against the compiled reference.
+ *
  * What runs where: every XOR/popcount correlation runs on the GPU (no CPU correlator exists in this
  * library; without a CUDA device the calls fail and report through gpsb_host_last_status()).  The
  * loop filters, votes and nav-bit logic are scalar float/integer code that feeds the next step's NCO
- * words; they run on the host with the host libm, exactly as the reference does, so their state is
- * bit-identical to the reference's (SURVEY.md section 7 "hard parts").
+ * words: ONE source (core/gpsb_loop_core.h) compiled for the host - used by the reference-named per-call
+ * entry points, exactly as the reference does - and for the device, where gpsb_rx_track_run keeps whole
+ * runs resident in one kernel launch; both are bit-identical to the reference.
  *
  * The reference keeps several pieces of cross-call state in file-scope globals that only work under
  * its one-channel-at-a-time schedule (PM/GPS/acquisition.c:28-33, tracking.c:33-34, nav_data.c:29,
@@ -161,7 +166,8 @@ typedef struct {
 
 typedef struct { double pseudorange_m; double tow_s; } gps_obs_data_t;
 
-/* RTKLIB-derived ephemeris containers; carried for layout only, the hot path never touches them. */
+/* RTKLIB-derived ephemeris containers (gps_misc.h:143-182): filled by the subframe decode, read by the position fix
+ * and the RTCM encoder; the correlator path never touches them. */
 typedef struct { time_t time; double sec; } gtime_t;
 typedef struct {
     int sat, iode, iodc, sva, svh, week, code, flag;
