@@ -5,8 +5,9 @@ the data bits, Doppler / code phase / bit timing consistent with a receiver on t
 through E/P/L tracking, bit synchronisation, the word assembler, the ephemeris decode, the observation assembly and the
 position solver.
 
-* CPU (not gpu): tracking by the UNMODIFIED reference; this library's rows N3 / N4 on the tracked channels against the
-  reference's, and the fix against the receiver's true site.
+* CPU (not gpu): this library's side tracked by the sources of the device-resident loop compiled for the CPU
+  (tests/emu/loop_emu.c), the reference's side by the UNMODIFIED reference; records, ephemerides, observations and the
+  fix compared stage by stage, and the fix against the receiver's true site.
 * GPU: tracking, bit logic and ephemeris decode in the device-resident loop (k_track_run, streamed, all four channels
   in one launch per leg); channel records, ephemerides, observations and the fix equal the reference's bit for bit."""
 import ctypes as C
@@ -133,23 +134,29 @@ def finish_and_check(pair, sc, reference, track_both):
     return error_m
 
 
-def test_if_samples_to_position_reference_tracking(reference):
+def test_if_samples_to_position_emulated_device_loop(reference):
+    """CPU leg: this library's side is tracked by the sources of k_track_run compiled with gcc (tests/emu/loop_emu.c:
+    loop filters with the device math, raw-frame correlator, bit logic, subframe decode), one channel after the other."""
+    from emu_lib import load_emulator
+    emu = load_emulator()
     lib = load_host_library()
     rl = reference.lib
     protos(lib, rl)
     sc, sig = scene_and_signal(reference)
     pair = Pair(reference, sc.prns)
     for i in range(4):
-        start_tracking(reference, reference.channel_at(pair.rchans, i), sc, i)
+        st = start_tracking(reference, reference.channel_at(pair.rchans, i), sc, i)
+        pair.ch.restore(i, type(pair.ch.snapshot(i)).from_buffer_copy(bytes(st)))
+    aux = [C.create_string_buffer(emu.emu_sizeof_aux()) for _ in range(4)]
 
     def track_both(ms0, n_ms):
         part = np.ascontiguousarray(sig[ms0:ms0 + n_ms])
         for i in range(4):
-            rch = reference.channel_at(pair.rchans, i)
-            rl.ref_track_run(rch, part.ctypes.data, ms0, n_ms, None, None, None)
-            # this library's channels take over what tracking produced (the GPU test produces it itself)
-            pair.ch.restore(i, type(pair.ch.snapshot(i)).from_buffer_copy(bytes(reference.snapshot(rch))))
-            lib.gpsb_host_channel_set_eph(pair.ch.at(i), C.byref(ref_eph(reference, rch)))
+            rl.ref_track_run(reference.channel_at(pair.rchans, i), part.ctypes.data, ms0, n_ms, None, None, None)
+            done = C.c_uint32()
+            stop = emu.emu_track_run(pair.ch.at(i), aux[i], part.ctypes.data, ms0, n_ms, 2, None, None, C.byref(done), None)
+            assert stop == 0 and done.value == n_ms, (i, stop, done.value)
+            emu.emu_resolve_snr(pair.ch.at(i), aux[i])
 
     finish_and_check(pair, sc, reference, track_both)
     pair.free()
