@@ -408,7 +408,8 @@ void gpsb_host_channel_set_tow(gps_ch_t* ch, double tow_gpst);
 extern sol_t  gps_sol;                               /* solving.c:49 */
 extern double final_pos[3];                          /* solving.c:51: latitude, longitude (deg), height (m) */
 extern double azel[2 * GPSB_FIX_MAX_SATS];           /* solving.c:52: azimuth / elevation per satellite (deg) */
-void    gps_pos_solve_init(gps_ch_t* channels);      /* registers the ephemerides of the first sat_cnt channels */
+void    gps_pos_solve_init(gps_ch_t* channels);      /* registers the ephemerides of the first sat_cnt channels: the
+                                                        solver keeps POINTERS into them (like the reference); NULL unregisters */
 void    gps_pos_solve(obsd_t* obs_p);                /* one sub-millisecond slice per call, like the reference */
 uint8_t solving_is_busy(void);
 void    gps_master_calculate_pos(gps_ch_t* channels);

@@ -189,6 +189,7 @@ class Channels:
         reference's pntpos without the slicing).  Returns None without a fix, else a dict: latitude / longitude (deg),
         height (m), ECEF position (m), receiver clock bias (s), azimuth / elevation per channel (deg)."""
         self.lib.gps_pos_solve_init(self.base)
+        self._fix_registered = True
         if self.lib.gpsb_host_fix_channels(self.base, self.n) != 1:
             return None
         f = FlatFix()
@@ -208,6 +209,8 @@ class Channels:
 
     def free(self) -> None:
         if self.base:
+            if getattr(self, "_fix_registered", False):          # the solver holds pointers into these records
+                self.lib.gps_pos_solve_init(None)
             self.lib.gpsb_host_channels_free(self.base)
             self.base = None
 

@@ -216,6 +216,8 @@ class Pair:
         return f
 
     def free(self):
+        self.lib.gpsb_host_fix_reset()
+        self.lib.gps_pos_solve_init(None)                      # the solver holds pointers into the channel records
         self.ch.free()
 
 
