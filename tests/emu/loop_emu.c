@@ -76,8 +76,20 @@ void emu_epl_cell(const uint8_t* chips, const uint8_t* frame2046, uint32_t acc0,
 
 /* The kernel's loop for one channel, role by role in the order the barriers impose.  Returns the stop reason;
  * *done_ms = milliseconds completed. */
+int emu_track_run_phase(gps_ch_t* ch, gpsb_aux* aux, const uint8_t* signal, uint32_t ms0, uint32_t n_ms, uint32_t nw,
+                        uint32_t slot_phase, int16_t* iq_log, int8_t* nav_log, uint32_t* done_ms, int16_t stop_iq[6]);
+
 int emu_track_run(gps_ch_t* ch, gpsb_aux* aux, const uint8_t* signal, uint32_t ms0, uint32_t n_ms, uint32_t nw,
                   int16_t* iq_log, int8_t* nav_log, uint32_t* done_ms, int16_t stop_iq[6])
+{
+    return emu_track_run_phase(ch, aux, signal, ms0, n_ms, nw, 0, iq_log, nav_log, done_ms, stop_iq);
+}
+
+/* slot_phase shifts where the 4-ms slots of the bit synchroniser start (index = (ms + slot_phase) % 4).  0 is what the
+ * kernel does today; other values are the per-channel slot phase DESIGN.md section 10 proposes for the next round,
+ * pinned here against the reference driven with the same index sequence. */
+int emu_track_run_phase(gps_ch_t* ch, gpsb_aux* aux, const uint8_t* signal, uint32_t ms0, uint32_t n_ms, uint32_t nw,
+                        uint32_t slot_phase, int16_t* iq_log, int8_t* nav_log, uint32_t* done_ms, int16_t stop_iq[6])
 {
     uint32_t E[EC_WORDS], S[EC_WORDS];
     expand_code(ch->prn_code, E);
@@ -93,7 +105,7 @@ int emu_track_run(gps_ch_t* ch, gpsb_aux* aux, const uint8_t* signal, uint32_t m
     }
     for (; m < n_ms && stop == LC_STOP_NONE; m++) {
         const uint32_t ms = ms0 + m;
-        const uint8_t index = (uint8_t)(ms % LC_SLOT_LEN);
+        const uint8_t index = (uint8_t)((ms + slot_phase) % LC_SLOT_LEN);
         memset(S, 0xA5, sizeof S);
         memcpy(S, signal + (size_t)m * 2046, 2046);
         int16_t iq[6];

@@ -33,6 +33,8 @@ def load_emulator() -> C.CDLL:
     lib.emu_epl_cell.argtypes = [vp, vp, u32, u32, u32, u32, u32, u32, u32, vp]
     lib.emu_track_run.restype = i32
     lib.emu_track_run.argtypes = [vp, vp, vp, u32, u32, u32, vp, vp, C.POINTER(u32), vp]
+    lib.emu_track_run_phase.restype = i32
+    lib.emu_track_run_phase.argtypes = [vp, vp, vp, u32, u32, u32, u32, vp, vp, C.POINTER(u32), vp]
     lib.emu_resolve_snr.restype = None
     lib.emu_resolve_snr.argtypes = [vp, vp]
     lib.emu_compare_float_math.restype = C.c_uint64

@@ -67,3 +67,46 @@ def test_edge_on_a_slot_boundary_needs_the_walking_schedule(oracle, reference):
     fin = mine.snapshot(0)
     assert fin.period_sync_ok_flag == 1 and fin.trk_state == 4
     mine.free()
+
+
+def test_slot_phase_moves_the_window_onto_the_edge(reference):
+    """What DESIGN.md section 10 proposes for the batched paths, pinned on the CPU: with the slots of the same
+    satellite started one millisecond later (index = (ms + 1) % 4), every millisecond still processed, the device
+    loop's sources synchronise - and equal the reference driven with the same index sequence."""
+    from emu_lib import load_emulator
+    emu = load_emulator()
+    prn, doppler, code_phase, n_ms = 12, 1500.0, 5000.3, 3000
+    rng = np.random.default_rng(4)
+    bits = np.tile([0, 1], n_ms // 40 + 2).astype(np.uint8)
+    bits[rng.integers(0, bits.size, bits.size // 8)] ^= 1
+    sat = Satellite(prn=prn, doppler_hz=doppler, code_phase_samples=code_phase, cn0_dbhz=50.0, nav_bits=bits,
+                    nav_bit_offset_ms=100)
+    sig = synthesize(Scene(sats=[sat], n_ms=n_ms, seed=12))
+
+    def locked(st):
+        st.acq_state, st.trk_state, st.found_freq_offset_hz = 9, 4, int(doppler)
+        st.if_freq_offset_hz_bits = int(np.float32(doppler).view(np.uint32))
+        st.code_phase_fine_bits = int(np.float32(code_phase).view(np.uint32))
+        return st
+
+    for phase, expect_sync in ((0, False), (1, True), (2, True)):
+        rchans = reference.channels(1)
+        rch = reference.channel_at(rchans, 0)
+        reference.channel_init(rch, prn, 0)
+        reference.restore(rch, locked(reference.snapshot(rch)))
+        for ms in range(n_ms):
+            reference.set_ms(ms)
+            reference.lib.gps_tracking_process(rch, sig[ms].ctypes.data, (ms + phase) % 4)
+        mine = Channels([prn])
+        mine.restore(0, locked(mine.snapshot(0)))
+        aux = C.create_string_buffer(emu.emu_sizeof_aux())
+        done = C.c_uint32()
+        stop = emu.emu_track_run_phase(mine.at(0), aux, sig.ctypes.data, 0, n_ms, 2, phase, None, None, C.byref(done), None)
+        assert stop == 0 and done.value == n_ms
+        emu.emu_resolve_snr(mine.at(0), aux)
+        a, b = mine.snapshot(0), reference.snapshot(rch)
+        assert states_equal(a, b), (phase, diff_fields(a, b))
+        assert bool(a.period_sync_ok_flag) == expect_sync, phase
+        if phase == 2:
+            assert a.accurate_swap_ok == 1                        # the edge shows at slot position 2: it is refined too
+        mine.free()
