@@ -305,7 +305,7 @@ int  gpsb_rx_create(gpsb_rx** out, gpsb_ctx* ctx, gps_ch_t* channels, uint32_t n
 void gpsb_rx_destroy(gpsb_rx* rx);
 
 /* One millisecond of tracking for every channel (gps_tracking_process for each, PM/main.c:155, in the
- * "every satellite every millisecond" schedule: slot index = ms % 4).  Frame `ms` must already be in
+ * "every satellite every millisecond" schedule: slot index = ms % 4, or as moved by gpsb_rx_set_slot_walk).  Frame `ms` must already be in
  * the ring (gpsb_upload_signal).  Exactly one k_epl launch (+ one search launch while any channel is
  * still in pre-track). */
 int gpsb_rx_track_ms(gpsb_rx* rx, uint32_t ms);
@@ -348,6 +348,35 @@ int64_t gpsb_host_certify_loop_math(gpsb_ctx* ctx, uint32_t n_threads);
 /* Host threads used by gpsb_rx_track_run for the per-channel loop filters (each drives its own channels'
  * session slots): 0 = automatic (online CPUs - 1, at most 16, at most one per channel), 1 = single thread. */
 void gpsb_rx_set_threads(gpsb_rx* rx, uint32_t n);
+
+/* Slot-phase walk.  The reference's bit synchroniser sees a data-bit edge only inside a 4-ms channel slot and refines
+ * only an edge at slot position 2 (PM/GPS/nav_data.c:87-138); subframe time stamps and pseudoranges need that refined
+ * edge (nav_data.c:356-360).  The MCU serves a channel 4 of every 17 ms (PM/main.c:134-155), so its slots walk over
+ * every edge alignment.  The batched paths process every millisecond - by default with slot index = ms % 4, an
+ * alignment that never moves.  With the walk enabled a channel that tracks but has no refined edge leaves 1..3
+ * milliseconds out between two slots (the MCU's own means: an unserved channel, PM/GPS/tracking.c:102-113) until its
+ * edges show at slot position 2: every satellite then delivers subframe stamps.  Results equal the unmodified
+ * reference called on the same (millisecond, slot index) schedule; idle milliseconds log zero sums and no nav bit.
+ * period_ms: patience at one slot phase without bit-period sync, 0 = 600.  Default: off (index = ms % 4). */
+int gpsb_rx_set_slot_walk(gpsb_rx* rx, int enable, uint32_t period_ms);
+/* Where a channel stands on its way to a time stamp (so a caller can tell "not yet" from "never"). */
+typedef struct gpsb_sync_status {
+    uint8_t  tracking;            /* in GPS_TRACKING_RUN */
+    uint8_t  bit_period_found;    /* nav_data.period_sync_ok_flag */
+    uint8_t  bit_edge_refined;    /* nav_data.accurate_swap_ok: subframe stamps can be made */
+    uint8_t  polarity_found;
+    uint8_t  slot_phase;          /* slot index of millisecond ms is (ms + slot_phase) % 4 */
+    uint8_t  walk_enabled, walk_pending;
+    uint8_t  reserved;
+    uint16_t walks;               /* idle gaps taken so far */
+    uint16_t subframes;           /* nav_data.subframe_cnt */
+    uint32_t words_ok;            /* nav_data.word_cnt_test */
+} gpsb_sync_status;
+int gpsb_rx_channel_sync(const gpsb_rx* rx, uint32_t i, gpsb_sync_status* out);
+/* The same switch / observer on one raw per-channel scratch record (callers of gpsb_track_loop that own their records).
+ * out: slot_phase, walk_enable, skip_ms, skip_len, walks, phase_since_ms. */
+void gpsb_host_aux_walk(void* aux_record, uint32_t enable, uint32_t period_ms);
+void gpsb_host_aux_walk_state(const void* aux_record, uint32_t out[6]);
 
 /* One acquisition snapshot for every channel (acquisition_process, PM/main.c:166) in one launch. */
 int gpsb_rx_acquire_ms(gpsb_rx* rx, uint32_t ms);

@@ -362,6 +362,99 @@ void ref_track_run(gps_ch_t* ch, const uint8_t* signal, uint32_t ms_first, uint3
     }
 }
 
+/*
+ * The same run on a schedule with idle gaps: the checker's own restatement of the slot-phase walk of this library's
+ * batched paths (include/gpsb_host.h, gpsb_rx_set_slot_walk), written from its description, driving the UNMODIFIED
+ * reference.  A channel is called with slot index (ms + slot_phase) % 4; inside an idle gap it is called with the
+ * reference's dummy index 0xFF (main.c:146-147), which tracking.c:96 ignores.  After a complete slot of a channel that
+ * has no refined bit edge (nav_data.accurate_swap_ok == 0):
+ *   bit period found and the last on-grid edge showed at slot position 3 -> idle 1 ms, at position 1 -> idle 3 ms;
+ *   no bit period for period_ms at this slot phase                      -> idle 2 ms;
+ * the gap begins 5 ms after the slot end at which it was decided, and the millisecond behind a gap is slot index 0.
+ * Edge positions are observed from outside: sign of the prompt sum XOR the polarity flag before the call, one flip in
+ * the slot, "on grid" = (edge - old_swap_time before the call) % 20 in {0, 1, 19} (nav_data.c:87-113).
+ *   idx_log : NULL or uint8[n_ms] = slot index used (0xFF = idle)
+ */
+typedef struct ref_walk {
+    uint32_t enable, period_ms;
+    uint32_t slot_phase, gap_first, gap_len, phase_since, gaps_taken, edge_pos;
+    uint32_t slot_first_ms;
+    uint8_t sign[4];
+} ref_walk;
+uint32_t ref_sizeof_walk(void) { return (uint32_t)sizeof(ref_walk); }
+
+void ref_track_run_walk(gps_ch_t* ch, const uint8_t* signal, uint32_t ms_first, uint32_t n_ms, ref_walk* w,
+                        int16_t* iq_log, int8_t* nav_log, uint8_t* idx_log)
+{
+    for (uint32_t k = 0; k < n_ms; k++) {
+        const uint32_t ms = ms_first + k;
+        uint8_t* frame = (uint8_t*)(signal + 2046u * (size_t)k);
+        g_packet_cnt = ms;
+        if (iq_log) memset(iq_log + 6u * k, 0, 12);
+        if (nav_log) nav_log[k] = -1;
+        if (w->gap_len && ms >= w->gap_first && ms < w->gap_first + w->gap_len) {      /* not served this millisecond */
+            if (idx_log) idx_log[k] = 0xFF;
+            gps_tracking_process(ch, frame, 0xFF);
+            if (ms == w->gap_first + w->gap_len - 1) {
+                w->slot_phase = (4u - ((ms + 1u) % 4u)) % 4u;
+                w->phase_since = ms + 1u;
+            }
+            continue;
+        }
+        const uint8_t index = (uint8_t)((ms + w->slot_phase) % TRACKING_CH_LENGTH);
+        if (idx_log) idx_log[k] = index;
+
+        const float fine_before = ch->tracking_data.code_phase_fine;
+        const gps_nav_data_t nb = ch->nav_data;
+        const int will_track = (ch->tracking_data.state == GPS_TRACKING_RUN) ||
+                               (ch->tracking_data.state == GPS_PRE_TRACK_DONE);
+        gps_tracking_process(ch, frame, index);
+        if (!will_track) continue;
+
+        int16_t o[6];
+        uint16_t oe, op, ol;
+        epl_offsets(fine_before, &oe, &op, &ol);
+        gps_correlation_iq(tmp_prn_data, tmp_data_i, tmp_data_q, oe, &o[0], &o[1]);
+        gps_correlation_iq(tmp_prn_data, tmp_data_i, tmp_data_q, op, &o[2], &o[3]);
+        gps_correlation_iq(tmp_prn_data, tmp_data_i, tmp_data_q, ol, &o[4], &o[5]);
+        if (iq_log) memcpy(iq_log + 6u * k, o, 12);
+        if (nav_log && nb.period_sync_ok_flag == 1) {
+            uint8_t rem = (uint8_t)((ms - nb.old_swap_time) % 20);
+            if (rem < nb.old_reminder) nav_log[k] = (nb.last_bit_pos_cnt > nb.last_bit_neg_cnt) ? 1 : 0;
+        }
+
+        /* the observer and the policy */
+        w->sign[index] = (uint8_t)((o[2] > 0 ? 1 : 0) ^ (nb.inv_polarity_flag ? 1 : 0));
+        if (index == 0) w->slot_first_ms = ms;
+        if (index != TRACKING_CH_LENGTH - 1) continue;
+        uint32_t changes = 0, where = 0;
+        for (uint32_t i = 1; i < TRACKING_CH_LENGTH; i++)
+            if (w->sign[i] != w->sign[i - 1]) { changes++; where = i; }
+        if (changes == 1) {
+            const uint32_t rem = (w->slot_first_ms + where - nb.old_swap_time) % 20u;
+            if (rem == 0 || rem == 1 || rem == 19) w->edge_pos = where;
+        }
+        if (w->gap_len) {
+            if (ms < w->gap_first + w->gap_len) continue;          /* decided, not taken yet */
+            w->gap_len = 0;
+        }
+        if (!w->enable || ch->nav_data.accurate_swap_ok) continue;
+        uint32_t gap = 0;
+        if (ch->nav_data.period_sync_ok_flag && w->edge_pos) {
+            if (w->edge_pos == 3) gap = 1;
+            else if (w->edge_pos == 1) gap = 3;
+        } else if (ms - w->phase_since >= (w->period_ms ? w->period_ms : 600u)) {
+            gap = 2;
+        }
+        if (gap) {
+            w->gap_first = ms + 5u;
+            w->gap_len = gap;
+            w->edge_pos = 0;
+            w->gaps_taken++;
+        }
+    }
+}
+
 /* The three fused calls of one tracking step on explicit parameters (no loop filters), used to pin
  * the fused E/P/L cell against the reference primitives for arbitrary NCO state. */
 void ref_epl_cell(gps_ch_t* ch, const uint8_t* signal, float if_freq_offset_hz, uint32_t accum_in,

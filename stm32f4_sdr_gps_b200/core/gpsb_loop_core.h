@@ -76,6 +76,9 @@
 #define LC_MS_PER_BIT        20                           /* CODES_IN_BIT, nav_data.c:15 */
 #define LC_WORDS_PER_SUBFRAME 10                          /* nav_data.c:17 */
 #define LC_POLARITY_TIMEOUT_MS 12000u                     /* two subframes, nav_data.c:22 */
+#define LC_WALK_PERIOD_MS    600u                         /* default patience of the slot-phase walk (this library's) */
+#define LC_WALK_LEAD_MS      5u                           /* a walk decided at the end of a slot idles after the NEXT slot */
+#define LC_IDLE_INDEX        0xFFu                        /* the reference's "dummy" slot index (main.c:146-147, tracking.c:96) */
 #define LC_PI                3.14159265358979323846       /* <math.h>'s double M_PI, see host/track.c */
 
 /* why a device-resident run stopped before its last millisecond */
@@ -106,6 +109,15 @@ typedef struct gpsb_aux {
     uint8_t  snr_pending;                       /* device run: snr_value awaits log10f of the two sums below */
     uint32_t snr_i, snr_q;
     gpsb_rand31 rnd;                            /* private rand() stream of a batched channel */
+    /* Slot-phase walk of the batched paths (lc_walk_*, below).  All zero = slots start at ms % 4 == 0 for ever. */
+    uint8_t  slot_phase;                        /* slot index of millisecond ms is (ms + slot_phase) % 4 */
+    uint8_t  walk_enable;                       /* 1: lc_walk_policy may move the slots of this channel */
+    uint8_t  skip_len;                          /* the channel idles in [skip_ms, skip_ms + skip_len): 0 = no walk decided */
+    uint8_t  last_flip_pos;                     /* observer: slot position (1..3) of the last bit edge seen on the 20-ms grid */
+    uint16_t walk_period_ms;                    /* patience at one slot phase without bit-period sync (0 = LC_WALK_PERIOD_MS) */
+    uint16_t walks;                             /* statistics: idle gaps taken so far */
+    uint32_t skip_ms;                           /* first idle millisecond of the pending (or last) walk */
+    uint32_t phase_since_ms;                    /* millisecond at which the current slot phase began */
 } gpsb_aux;
 
 /* ------------------------------------------------------------------------------------------ bits */
@@ -814,12 +826,71 @@ LC_FN int lc_nav_new_code(gps_ch_t* ch, gpsb_aux* aux, uint8_t index, int16_t ne
     if (phase < 2 || phase == LC_MS_PER_BIT - 1) {            /* a multiple of 20 ms since the last edge */
         if (n->right_period_cnt < 10) n->right_period_cnt++;
         if (n->right_period_cnt > 8) n->period_sync_ok_flag = 1;
+        aux->last_flip_pos = flip_pos;                        /* observer for lc_walk_policy; not reference state */
     } else {
         if (n->right_period_cnt > 0) n->right_period_cnt--;
         if (n->right_period_cnt < 3) n->period_sync_ok_flag = 0;
     }
     n->old_swap_time = edge;
     return n->period_sync_ok_flag && flip_pos == 2;
+}
+
+/* ------------------------------------------------------------------------------------------ slot-phase walk */
+/* The reference's bit synchroniser sees a data-bit edge only INSIDE a 4-ms slot and refines only an edge at slot
+ * position 2 (nav_data.c:87-138); subframe time stamps - and with them pseudoranges - need that refinement
+ * (nav_data.c:356-360).  On the MCU a channel is served 4 of every 17 ms (main.c:134-155), so its slots start one
+ * millisecond later, modulo 4, every cycle and every edge alignment passes the window.  The batched paths of this
+ * library process EVERY millisecond (index = ms % 4): data bits last 20 ms = 5 slots, so the alignment never moves
+ * and three satellites in four would never deliver a time stamp.
+ *
+ * The walk restores the MCU's behaviour with the MCU's own means - an idle gap between two slots: a channel that
+ * tracks but has no refined edge leaves 1..3 milliseconds unprocessed after a complete slot (exactly what the
+ * reference does with a channel it does not serve: no call, and gps_rewind_if_phase catches the carrier NCO up,
+ * tracking.c:102-113) and starts its next slot behind the gap.  Every slot stays a whole index 0..3 sequence, so the
+ * result equals the unmodified reference called on the same (millisecond, index) schedule - which is how the tests
+ * check it (oracle/ref_shim.c: ref_track_run_walk).  Policy (this library's, evaluated at the end of a slot):
+ *   - bit period found and the edges show at slot position 3 / 1: idle 1 / 3 ms - the edges then show at position 2;
+ *   - no bit period after walk_period_ms at this slot phase (edges on the slot boundary, or none seen): idle 2 ms;
+ *   - edges already at position 2, or the edge refined (accurate_swap_ok): nothing.
+ * A walk decided at the end of a slot takes effect LC_WALK_LEAD_MS later, behind the next slot, so that the thread
+ * that plans the carrier NCO of the device-resident loop knows it a whole slot ahead. */
+LC_FN int lc_walk_idle(uint32_t skip_ms, uint32_t skip_len, uint32_t ms) { return (uint32_t)(ms - skip_ms) < skip_len; }
+/* slot phase after an idle gap whose last millisecond is `ms`: the next millisecond starts a slot */
+LC_FN uint8_t lc_walk_phase_after(uint32_t ms) { return (uint8_t)((0u - (ms + 1u)) & (LC_SLOT_LEN - 1u)); }
+/* Slot index of millisecond `ms` for this channel, LC_IDLE_INDEX inside an idle gap; the gap's last millisecond
+ * moves the slot phase.  The one place the host paths take their index from. */
+LC_FN uint8_t lc_walk_index(gpsb_aux* aux, uint32_t ms)
+{
+    if (lc_walk_idle(aux->skip_ms, aux->skip_len, ms)) {
+        if (ms + 1u - aux->skip_ms == aux->skip_len) {
+            aux->slot_phase = lc_walk_phase_after(ms);
+            aux->phase_since_ms = ms + 1u;
+        }
+        return LC_IDLE_INDEX;
+    }
+    return (uint8_t)((ms + aux->slot_phase) & (LC_SLOT_LEN - 1u));
+}
+/* End of a slot (index 3) of a channel in GPS_TRACKING_RUN, after the nav-bit logic of that millisecond. */
+LC_FN void lc_walk_policy(const gps_ch_t* ch, gpsb_aux* aux, uint32_t ms)
+{
+    const gps_nav_data_t* n = &ch->nav_data;
+    if (aux->skip_len) {
+        if ((int32_t)(ms - (aux->skip_ms + aux->skip_len)) < 0) return;     /* a walk is pending */
+        aux->skip_len = 0;                                                  /* taken: forget it */
+    }
+    if (!aux->walk_enable || n->accurate_swap_ok) return;
+    const uint32_t patience = aux->walk_period_ms ? aux->walk_period_ms : LC_WALK_PERIOD_MS;
+    uint8_t idle = 0;
+    if (n->period_sync_ok_flag && aux->last_flip_pos) {
+        if (aux->last_flip_pos != 2) idle = (uint8_t)((aux->last_flip_pos + 2u) & 3u);     /* 3 -> 1 ms, 1 -> 3 ms */
+    } else if (ms - aux->phase_since_ms >= patience) {
+        idle = 2;
+    }
+    if (!idle) return;
+    aux->skip_ms = ms + LC_WALK_LEAD_MS;
+    aux->skip_len = idle;
+    aux->last_flip_pos = 0;
+    aux->walks++;
 }
 
 /* ------------------------------------------------------------------------------------------ tail of the step */

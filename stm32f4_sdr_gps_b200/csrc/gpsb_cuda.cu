@@ -1223,7 +1223,6 @@ int gpsb_stream_push_iq2(gpsb_ctx* c, uint32_t ms0, uint32_t n_ms, const uint8_t
     if (bytes + 64 > c->iq2_cap) {                       // staging for the byte-per-sample container, grown on demand
         CU(cudaStreamSynchronize(c->copy_stream));
         if (c->d_iq2) cudaFree(c->d_iq2);
-    if (c->d_acq_scratch) cudaFree(c->d_acq_scratch);
         c->d_iq2 = nullptr;
         c->iq2_cap = 0;
         CU(cudaMalloc(&c->d_iq2, bytes + 64));

@@ -253,11 +253,24 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
                 issued = first;
                 consumed = 1;           // phase 1 of millisecond 0, below
             }
-            lc_trk_plan_run(&sm.ch, ms0, ms0, &sm.rq);
+            // a run that starts inside an idle gap of the slot-phase walk (lc_walk_*): no carrier plan for that
+            // millisecond - the gap's last millisecond plans the first one behind it, in the loop
+            if (lc_walk_idle(sm.aux.skip_ms, sm.aux.skip_len, ms0)) {
+                sm.rq.sv_slot = sm.ch.prn;
+                sm.rq.ms_index = ms0;
+                sm.rq.acc0 = sm.rq.step32 = 0u;
+                lc_plan_code(&sm.ch.tracking_data, &sm.rq);
+            } else {
+                lc_trk_plan_run(&sm.ch, ms0, ms0, &sm.rq);
+            }
         }
     }
     __syncthreads();
     int stop = sm.stop;
+    // Slot-phase walk (core/gpsb_loop_core.h, lc_walk_*): every control thread keeps its own copy of the channel's slot
+    // phase and of the idle gap the nav thread may have decided; the nav thread writes a decision at slot index 3, the
+    // others re-read it at slot index 2 (barriers in between), a whole slot before it takes effect.
+    uint32_t w_phase = sm.aux.slot_phase, w_skip_ms = sm.aux.skip_ms, w_skip_len = sm.aux.skip_len;
     ec_partial part;
     if (stop == LC_STOP_NONE && n_ms && (plain || edge)) {  // phase 1 of millisecond 0
         const uint32_t off[3] = {sm.rq.off_e, sm.rq.off_p, sm.rq.off_l};
@@ -312,7 +325,9 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
     for (; m < n_ms && stop == LC_STOP_NONE; m++) {
         const uint32_t ms = ms0 + m;
         const uint32_t b = m & 1u;
-        const uint8_t index = (uint8_t)(ms % LC_SLOT_LEN);
+        const bool idle = lc_walk_idle(w_skip_ms, w_skip_len, ms);            // this channel leaves the millisecond out
+        const bool idle_next = lc_walk_idle(w_skip_ms, w_skip_len, ms + 1u);
+        const uint8_t index = idle ? (uint8_t)LC_IDLE_INDEX : (uint8_t)((ms + w_phase) & (LC_SLOT_LEN - 1u));
         if (kProf) c0 = clock64();
         if (worker || edge_warp) {                          // phase 2: the carrier phase of each word selects its I and Q count
             uint32_t acc[3] = {0u, 0u, 0u};
@@ -369,9 +384,12 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
             load_sums(&sm.sums[b], iq);
             sm.sums[b ^ 1u] = make_uint4(0u, 0u, 0u, 0u);      // read one ms ago by everybody; filled again after the workers have seen offs_ready
             if (next_frame) consumed++;                         // the workers wait for frame m+1 this millisecond
-            const bool degenerate = lc_dll_is_degenerate(iq);   // 0/0 in the DLL: x86 and the GPU disagree on NaN bits, host finishes this ms
+            if (idle) iq[0] = iq[1] = iq[2] = iq[3] = iq[4] = iq[5] = 0;   // idle gap of the walk: the sums are nobody's
+            const bool degenerate = !idle && lc_dll_is_degenerate(iq);   // 0/0 in the DLL: x86 and the GPU disagree on NaN bits, host finishes this ms
             if (degenerate) sm.stop_at[b ^ 1u] = LC_STOP_DLL_NAN;
-            else {
+            else if (idle) {
+                if (kStream && sm.starved[b]) sm.stop_at[b ^ 1u] = LC_STOP_STARVED;
+            } else {
                 if (kStream && sm.starved[b]) sm.stop_at[b ^ 1u] = LC_STOP_STARVED;   // this millisecond is completed by every thread, then the run ends
                 if (!(kExp & 4)) lc_dll_update(&cod, iq[0], iq[1], iq[4], iq[5]);
                 if (next_frame && !(kStream && sm.starved[b])) lc_plan_code(&cod, &sm.rq);
@@ -406,18 +424,20 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
             if (kProf) { const long long c1 = clock64(); pt[6] += c1 - c0; c0 = c1; }
             int16_t iq[6];
             load_sums(&sm.sums[b], iq);
-            if (!lc_dll_is_degenerate(iq)) {
+            const bool live = !idle && !lc_dll_is_degenerate(iq);
+            if (live && !(kExp & 2)) {
                 // period_sync_ok_flag is written by the nav thread at slot index 3 and read here at slot index 0
-                if (!(kExp & 2)) {
-                    lc_pll_update(&car, sm.ch.nav_data.period_sync_ok_flag, index, iq[2], iq[3]);
-                    lc_fll_update(&car, &sm.aux, found_freq_offset_hz, index, iq[2], iq[3], &angle_cache);
-                }
-                if (next_frame && !(kStream && *(volatile int*)&sm.starved[b])) lc_plan_carrier(&car, prn, ms + 1, ms + 1, &sm.rq);
+                lc_pll_update(&car, sm.ch.nav_data.period_sync_ok_flag, index, iq[2], iq[3]);
+                lc_fll_update(&car, &sm.aux, found_freq_offset_hz, index, iq[2], iq[3], &angle_cache);
             }
+            // no plan for a millisecond the channel leaves out: the last millisecond of the gap plans the one behind it
+            // (now - prev_track_timestamp = gap + 1: lc_plan_carrier catches the NCO up, tracking.c:102-113)
+            if ((live || idle) && next_frame && !idle_next && !(kStream && *(volatile int*)&sm.starved[b]))
+                lc_plan_carrier(&car, prn, ms + 1, ms + 1, &sm.rq);
             if (next_frame) mbar_arrive(&sm.nco_ready);     // always: the workers wait for it whether or not a plan was made
             // Off the serial path: at slot index 1 the FLL needs the angle of THIS prompt sample as its "before" value;
             // evaluate it now, while the workers are busy, instead of next to the new angle in the next millisecond.
-            if (index == 0 && !lc_dll_is_degenerate(iq)) {
+            if (index == 0 && live) {
                 angle_cache.i = iq[2];
                 angle_cache.q = iq[3];
                 angle_cache.angle = lc_fll_angle(iq[2], iq[3]);
@@ -429,7 +449,7 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
             int16_t iq[6];
             load_sums(&sm.sums[b], iq);
             int8_t bit = -1;
-            if (!lc_dll_is_degenerate(iq)) {
+            if (!idle && !lc_dll_is_degenerate(iq)) {
                 const int refine = lc_nav_new_code(&sm.ch, &sm.aux, index, iq[2], ms);
                 bit = sm.aux.last_nav_bit;
                 if (refine) {                               // reads the code phase the DLL has just produced
@@ -437,9 +457,19 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
                     lc_refine_edge(&sm.ch, &sm.aux);
                 }
                 lc_snr_update(&sm.ch, &sm.aux, iq[2], iq[3]);
+                if (index == LC_SLOT_LEN - 1) lc_walk_policy(&sm.ch, &sm.aux, ms);     // end of a slot: move the slots?
+            }
+            if (idle && !idle_next) {                       // last millisecond of an idle gap: the next one starts a slot
+                sm.aux.slot_phase = lc_walk_phase_after(ms);
+                sm.aux.phase_since_ms = ms + 1u;
             }
             if (nav_log) nav_log[(size_t)m * n_ch + chn] = bit;
             if (kProf) pt[4] += clock64() - c0;
+        }
+        if (idle && !idle_next) w_phase = lc_walk_phase_after(ms);
+        if (index == LC_SLOT_LEN - 2 && !worker) {          // a decision of the previous slot's end (barriers in between)
+            w_skip_ms = *(volatile uint32_t*)&sm.aux.skip_ms;
+            w_skip_len = *(volatile uint8_t*)&sm.aux.skip_len;
         }
     }
     __syncthreads();                                        // the last millisecond's control work is done

@@ -32,7 +32,19 @@ struct gpsb_rx {
     gpsb_loop_result* loop_res;
     uint32_t ring_ms;            /* capacity of the context's signal ring */
     uint64_t device_ms, host_ms; /* channel-milliseconds run by k_track_run / by the per-millisecond host path */
+    uint8_t* idx;                /* slot index of each channel in the millisecond being processed (gpsb_rx_track_ms) */
 };
+
+/* Slot index of channel i at millisecond ms: (ms + slot phase) % 4, or LC_IDLE_INDEX inside an idle gap of the
+ * slot-phase walk (core/gpsb_loop_core.h, lc_walk_*) - then the channel is not served, like a channel the MCU's
+ * 17-ms schedule does not reach (main.c:134-155). */
+static uint8_t rx_index(gpsb_rx* rx, uint32_t i, uint32_t ms) { return lc_walk_index(&rx->aux[i], ms); }
+/* after the loop filters of an E/P/L millisecond: at the end of a slot the walk policy may move the slots */
+static void rx_slot_end(gpsb_rx* rx, uint32_t i, uint32_t ms, uint8_t index)
+{
+    if (index == GPSB_SLOT_LEN - 1 && rx->ch[i].tracking_data.state == GPS_TRACKING_RUN)
+        lc_walk_policy(&rx->ch[i], &rx->aux[i], ms);
+}
 
 typedef struct track_job {
     gpsb_rx* rx;
@@ -60,7 +72,8 @@ int gpsb_rx_create(gpsb_rx** out, gpsb_ctx* ctx, gps_ch_t* channels, uint32_t n_
     rx->s_res = (gpsb_search_res*)calloc(n_ch, sizeof(gpsb_search_res));
     rx->s_owner = (uint32_t*)calloc(n_ch, sizeof(uint32_t));
     rx->loop_res = (gpsb_loop_result*)calloc(n_ch, sizeof(gpsb_loop_result));
-    if (!rx->loop_res || !rx->aux || !rx->plan || !rx->epl_rq || !rx->epl_out || !rx->epl_owner || !rx->s_rq || !rx->s_res ||
+    rx->idx = (uint8_t*)calloc(n_ch, 1);
+    if (!rx->idx || !rx->loop_res || !rx->aux || !rx->plan || !rx->epl_rq || !rx->epl_out || !rx->epl_owner || !rx->s_rq || !rx->s_res ||
         !rx->s_owner) {
         gpsb_rx_destroy(rx);
         return GPSB_ERR_NOMEM;
@@ -92,6 +105,7 @@ void gpsb_rx_destroy(gpsb_rx* rx)
     free(rx->s_res);
     free(rx->s_owner);
     free(rx->loop_res);
+    free(rx->idx);
     free(rx);
 }
 
@@ -125,21 +139,24 @@ int gpsb_rx_track_ms(gpsb_rx* rx, uint32_t ms)
 {
     if (!rx) return GPSB_ERR_ARG;
     gpsb_host_set_packet_cnt(ms);
-    const uint8_t index = (uint8_t)(ms % GPSB_SLOT_LEN);
-    for (uint32_t i = 0; i < rx->n_ch; i++) hx_trk_plan(&rx->ch[i], &rx->aux[i], ms, index, &rx->plan[i]);
+    for (uint32_t i = 0; i < rx->n_ch; i++) {
+        rx->idx[i] = rx_index(rx, i, ms);
+        hx_trk_plan(&rx->ch[i], &rx->aux[i], ms, rx->idx[i], &rx->plan[i]);
+    }
     uint32_t n_epl, n_s;
     int rc = run_plans(rx, &n_epl, &n_s);
     if (rc != GPSB_OK) return rc;
     for (uint32_t k = 0; k < n_epl; k++) {
         uint32_t i = rx->epl_owner[k];
-        hx_trk_finish_epl(&rx->ch[i], &rx->aux[i], index, rx->epl_out + 6u * k);
+        hx_trk_finish_epl(&rx->ch[i], &rx->aux[i], rx->idx[i], rx->epl_out + 6u * k);
+        rx_slot_end(rx, i, ms, rx->idx[i]);
     }
     uint32_t k = 0;
     for (uint32_t i = 0; i < rx->n_ch; i++) {
         if (rx->plan[i].want != GPSB_WANT_SEARCH) continue;
         const gpsb_search_res* r = &k_empty_window;
         if (k < n_s && rx->s_owner[k] == i) r = &rx->s_res[k++];
-        hx_trk_finish_search(&rx->ch[i], &rx->aux[i], index, r);
+        hx_trk_finish_search(&rx->ch[i], &rx->aux[i], rx->idx[i], r);
     }
     rx->host_ms += n_epl + n_s;
     return GPSB_OK;
@@ -157,22 +174,24 @@ static void* track_worker(void* arg)
     job->rc = GPSB_OK;
     for (uint32_t m = 0; m < job->n_ms && job->rc == GPSB_OK; m++) {
         const uint32_t ms = job->ms0 + m;
-        const uint8_t index = (uint8_t)(ms % GPSB_SLOT_LEN);
         gpsb_host_set_packet_cnt(ms);
         for (uint32_t i = job->worker; i < rx->n_ch; i += job->n_workers) {
             gpsb_plan* p = &rx->plan[i];
             rx->aux[i].last_nav_bit = -1;
-            hx_trk_plan(&rx->ch[i], &rx->aux[i], ms, index, p);
+            rx->idx[i] = rx_index(rx, i, ms);
+            hx_trk_plan(&rx->ch[i], &rx->aux[i], ms, rx->idx[i], p);
             int rc = gpsb_session_post(rx->ctx, i, p->want == GPSB_WANT_EPL ? &p->epl : NULL, &seq[i]);
             if (rc != GPSB_OK) job->rc = hx_note(rc);
         }
         for (uint32_t i = job->worker; i < rx->n_ch && job->rc == GPSB_OK; i += job->n_workers) {
             gpsb_plan* p = &rx->plan[i];
+            const uint8_t index = rx->idx[i];
             int16_t iq[6] = {0, 0, 0, 0, 0, 0};
             if (p->want == GPSB_WANT_EPL) {
                 int rc = gpsb_session_wait(rx->ctx, i, seq[i], iq);
                 if (rc != GPSB_OK) { job->rc = hx_note(rc); break; }
                 hx_trk_finish_epl(&rx->ch[i], &rx->aux[i], index, iq);
+                rx_slot_end(rx, i, ms, index);
             } else if (p->want == GPSB_WANT_SEARCH) {
                 gpsb_search_res res = {0, 0, 0, 0};
                 if (p->search.start < p->search.stop) {
@@ -220,7 +239,7 @@ static int is_tracking(const gps_ch_t* ch)
  * host): what the device-resident loop hands back, and channels that are still in pre-track. */
 static int host_step(gpsb_rx* rx, uint32_t i, uint32_t ms, int16_t* iq_row, int8_t* nav_row)
 {
-    const uint8_t index = (uint8_t)(ms % GPSB_SLOT_LEN);
+    const uint8_t index = rx_index(rx, i, ms);
     gpsb_plan* p = &rx->plan[i];
     int16_t iq[6] = {0, 0, 0, 0, 0, 0};
     gpsb_host_set_packet_cnt(ms);
@@ -230,6 +249,7 @@ static int host_step(gpsb_rx* rx, uint32_t i, uint32_t ms, int16_t* iq_row, int8
         int rc = gpsb_track_epl(rx->ctx, 1, &p->epl, iq);
         if (rc != GPSB_OK) return hx_note(rc);
         hx_trk_finish_epl(&rx->ch[i], &rx->aux[i], index, iq);
+        rx_slot_end(rx, i, ms, index);
     } else if (p->want == GPSB_WANT_SEARCH) {
         gpsb_search_res res = {0, 0, 0, 0};
         if (p->search.start < p->search.stop) {
@@ -286,7 +306,9 @@ static int run_channel_span(gpsb_rx* rx, uint32_t i, uint32_t ms0, uint32_t ms, 
         if (r.stop == LC_STOP_DLL_NAN && ms < end) {          /* sums delivered, filters not run: finish on the host */
             gpsb_host_set_packet_cnt(ms);
             rx->aux[i].last_nav_bit = -1;
-            hx_trk_finish_epl(&rx->ch[i], &rx->aux[i], (uint8_t)(ms % GPSB_SLOT_LEN), r.iq);
+            const uint8_t index = rx_index(rx, i, ms);
+            hx_trk_finish_epl(&rx->ch[i], &rx->aux[i], index, r.iq);
+            rx_slot_end(rx, i, ms, index);
             if (nav_log) nav_log[(size_t)(ms - ms0) * n_ch + i] = rx->aux[i].last_nav_bit;
             rx->host_ms++;
             ms++;
@@ -308,7 +330,9 @@ static int finish_device_run(gpsb_rx* rx, uint32_t ms0, uint32_t n_ms, int16_t* 
         if (r->stop == LC_STOP_DLL_NAN && r->done_ms < n_ms) {
             gpsb_host_set_packet_cnt(ms);
             rx->aux[i].last_nav_bit = -1;
-            hx_trk_finish_epl(&rx->ch[i], &rx->aux[i], (uint8_t)(ms % GPSB_SLOT_LEN), r->iq);
+            const uint8_t index = rx_index(rx, i, ms);
+            hx_trk_finish_epl(&rx->ch[i], &rx->aux[i], index, r->iq);
+            rx_slot_end(rx, i, ms, index);
             if (nav_log) nav_log[(size_t)(ms - ms0) * n_ch + i] = rx->aux[i].last_nav_bit;
             rx->host_ms++;
             ms++;
@@ -451,7 +475,9 @@ static int track_stream_impl(gpsb_rx* rx, uint32_t ms0, uint32_t n_ms, const uin
                 if (at == r->done_ms && r->stop == LC_STOP_DLL_NAN) {
                     gpsb_host_set_packet_cnt(ms0 + at);
                     rx->aux[i].last_nav_bit = -1;
-                    hx_trk_finish_epl(&rx->ch[i], &rx->aux[i], (uint8_t)((ms0 + at) % GPSB_SLOT_LEN), r->iq);
+                    const uint8_t index = rx_index(rx, i, ms0 + at);
+                    hx_trk_finish_epl(&rx->ch[i], &rx->aux[i], index, r->iq);
+                    rx_slot_end(rx, i, ms0 + at, index);
                     if (nav_log) nav_log[(size_t)at * n_ch + i] = rx->aux[i].last_nav_bit;
                     rx->host_ms++;
                     if (n == 1) { at++; continue; }
@@ -607,6 +633,48 @@ int gpsb_rx_cold_sweep(gpsb_rx* rx, int32_t first_bin_hz, int32_t bin_step_hz, u
     }
     free(cells); free(slots); free(who); free(step32);
     return hx_note(rc);
+}
+
+/* ---------------------------------------------------------------------------- slot-phase walk */
+int gpsb_rx_set_slot_walk(gpsb_rx* rx, int enable, uint32_t period_ms)
+{
+    if (!rx || period_ms > 65535u) return hx_note(GPSB_ERR_ARG);
+    for (uint32_t i = 0; i < rx->n_ch; i++) gpsb_host_aux_walk(&rx->aux[i], enable ? 1u : 0u, period_ms);
+    return GPSB_OK;
+}
+
+int gpsb_rx_channel_sync(const gpsb_rx* rx, uint32_t i, gpsb_sync_status* out)
+{
+    if (!rx || !out || i >= rx->n_ch) return hx_note(GPSB_ERR_ARG);
+    const gps_nav_data_t* n = &rx->ch[i].nav_data;
+    const gpsb_aux* a = &rx->aux[i];
+    memset(out, 0, sizeof *out);
+    out->tracking = rx->ch[i].tracking_data.state == GPS_TRACKING_RUN;
+    out->bit_period_found = n->period_sync_ok_flag;
+    out->bit_edge_refined = n->accurate_swap_ok;
+    out->polarity_found = n->polarity_found;
+    out->slot_phase = a->slot_phase;
+    out->walk_enabled = a->walk_enable;
+    out->walk_pending = a->skip_len != 0;
+    out->walks = a->walks;
+    out->subframes = n->subframe_cnt;
+    out->words_ok = n->word_cnt_test;
+    return GPSB_OK;
+}
+
+void gpsb_host_aux_walk(void* aux_record, uint32_t enable, uint32_t period_ms)
+{
+    gpsb_aux* a = (gpsb_aux*)aux_record;
+    if (!a) return;
+    a->walk_enable = (uint8_t)(enable != 0);
+    a->walk_period_ms = (uint16_t)period_ms;
+}
+
+void gpsb_host_aux_walk_state(const void* aux_record, uint32_t out[6])
+{
+    const gpsb_aux* a = (const gpsb_aux*)aux_record;
+    out[0] = a->slot_phase; out[1] = a->walk_enable; out[2] = a->skip_ms;
+    out[3] = a->skip_len;   out[4] = a->walks;       out[5] = a->phase_since_ms;
 }
 
 /* ---------------------------------------------------------------------------- split-phase API */

@@ -74,6 +74,14 @@ class FlatState(C.Structure):
     ]
 
 
+class SyncStatus(C.Structure):
+    """include/gpsb_host.h, gpsb_sync_status"""
+    _fields_ = [("tracking", C.c_uint8), ("bit_period_found", C.c_uint8), ("bit_edge_refined", C.c_uint8),
+                ("polarity_found", C.c_uint8), ("slot_phase", C.c_uint8), ("walk_enabled", C.c_uint8),
+                ("walk_pending", C.c_uint8), ("reserved", C.c_uint8), ("walks", C.c_uint16), ("subframes", C.c_uint16),
+                ("words_ok", C.c_uint32)]
+
+
 _hostlib = None
 
 
@@ -128,6 +136,10 @@ def load_host_library(path: Path | None = None) -> C.CDLL:
         "gpsb_rx_set_threads": (None, [vp, u32]),
         "gpsb_rx_set_loop_site": (None, [vp, i32]),
         "gpsb_rx_loop_stats": (None, [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+        "gpsb_rx_set_slot_walk": (i32, [vp, i32, u32]),
+        "gpsb_rx_channel_sync": (i32, [vp, u32, C.POINTER(SyncStatus)]),
+        "gpsb_host_aux_walk": (None, [vp, u32, u32]),
+        "gpsb_host_aux_walk_state": (None, [vp, C.POINTER(u32 * 6)]),
         "gpsb_host_certify_loop_math": (C.c_int64, [vp, u32]),
         "gpsb_rx_cold_sweep": (i32, [vp, C.c_int32, C.c_int32, u32, u32, u32, vp, vp]),
         "gpsb_host_plan_acq": (i32, [vp, u32, C.POINTER(Plan)]),
@@ -282,6 +294,16 @@ class Receiver:
     def set_loop_site(self, site: int) -> None:
         """0 automatic (device-resident loop for runs), 1 host loop filters, 2 device."""
         self.lib.gpsb_rx_set_loop_site(self._rx, site)
+
+    def set_slot_walk(self, enable: bool = True, period_ms: int = 0) -> None:
+        """gpsb_rx_set_slot_walk: let channels without a refined bit edge move their 4-ms slots (idle gaps between two
+        slots, like the MCU's 17-ms schedule) until every satellite delivers subframe time stamps."""
+        self._check(self.lib.gpsb_rx_set_slot_walk(self._rx, 1 if enable else 0, period_ms))
+
+    def sync_status(self, i: int) -> SyncStatus:
+        s = SyncStatus()
+        self._check(self.lib.gpsb_rx_channel_sync(self._rx, i, C.byref(s)))
+        return s
 
     def loop_stats(self):
         """(channel-milliseconds run by k_track_run, channel-milliseconds run on the per-ms host path)"""

@@ -101,17 +101,34 @@ int emu_track_run_phase(gps_ch_t* ch, gpsb_aux* aux, const uint8_t* signal, uint
     if (ch->tracking_data.state == GPS_PRE_TRACK_DONE) ch->tracking_data.state = GPS_TRACKING_RUN;
     if (ch->tracking_data.state != GPS_TRACKING_RUN) stop = LC_STOP_STATE;
     else if (n_ms) {
-        lc_trk_plan_run(ch, ms0, ms0, &rq);
+        if (slot_phase) aux->slot_phase = (uint8_t)slot_phase;
+        memset(&rq, 0, sizeof rq);
+        if (lc_walk_idle(aux->skip_ms, aux->skip_len, ms0)) lc_plan_code(&ch->tracking_data, &rq);   /* kernel prologue */
+        else lc_trk_plan_run(ch, ms0, ms0, &rq);
     }
+    /* the control threads' private copies of the walk state (kernel: w_phase, w_skip_ms, w_skip_len) */
+    uint32_t w_phase = aux->slot_phase, w_skip_ms = aux->skip_ms, w_skip_len = aux->skip_len;
     for (; m < n_ms && stop == LC_STOP_NONE; m++) {
         const uint32_t ms = ms0 + m;
-        const uint8_t index = (uint8_t)((ms + slot_phase) % LC_SLOT_LEN);
+        const int idle = lc_walk_idle(w_skip_ms, w_skip_len, ms);
+        const int idle_next = lc_walk_idle(w_skip_ms, w_skip_len, ms + 1u);
+        const uint8_t index = idle ? (uint8_t)LC_IDLE_INDEX : (uint8_t)((ms + w_phase) & (LC_SLOT_LEN - 1u));
         memset(S, 0xA5, sizeof S);
         memcpy(S, signal + (size_t)m * 2046, 2046);
         int16_t iq[6];
-        epl_two_phase(S, E, &rq, nw, iq);
+        epl_two_phase(S, E, &rq, nw, iq);            /* in an idle gap the workers correlate all the same; nobody looks */
+        if (idle) memset(iq, 0, sizeof iq);
         if (iq_log) memcpy(iq_log + 6 * (size_t)m, iq, 12);
         if (nav_log) nav_log[m] = -1;
+        if (idle) {
+            if (m + 1 < n_ms && !idle_next) lc_plan_carrier(&ch->tracking_data, ch->prn, ms + 1, ms + 1, &rq);
+            if (!idle_next) {
+                aux->slot_phase = lc_walk_phase_after(ms);
+                aux->phase_since_ms = ms + 1u;
+                w_phase = aux->slot_phase;
+            }
+            continue;
+        }
         if (lc_dll_is_degenerate(iq)) {
             stop = LC_STOP_DLL_NAN;
             if (stop_iq) memcpy(stop_iq, iq, 12);
@@ -124,7 +141,7 @@ int emu_track_run_phase(gps_ch_t* ch, gpsb_aux* aux, const uint8_t* signal, uint
         /* carrier thread */
         lc_pll_update(&ch->tracking_data, ch->nav_data.period_sync_ok_flag, index, iq[2], iq[3]);
         lc_fll_update(&ch->tracking_data, aux, ch->acq_data.found_freq_offset_hz, index, iq[2], iq[3], &cache);
-        if (m + 1 < n_ms) lc_plan_carrier(&ch->tracking_data, ch->prn, ms + 1, ms + 1, &rq);
+        if (m + 1 < n_ms && !idle_next) lc_plan_carrier(&ch->tracking_data, ch->prn, ms + 1, ms + 1, &rq);
         /* nav thread, first part (does not need the DLL) */
         const int refine = lc_nav_new_code(ch, aux, index, iq[2], ms);
         if (nav_log) nav_log[m] = aux->last_nav_bit;
@@ -134,6 +151,11 @@ int emu_track_run_phase(gps_ch_t* ch, gpsb_aux* aux, const uint8_t* signal, uint
         /* nav thread, after the DLL's mbarrier */
         if (refine) lc_refine_edge(ch, aux);
         lc_snr_update(ch, aux, iq[2], iq[3]);
+        if (index == LC_SLOT_LEN - 1) lc_walk_policy(ch, aux, ms);
+        if (index == LC_SLOT_LEN - 2) {               /* the other control threads re-read the decision here */
+            w_skip_ms = aux->skip_ms;
+            w_skip_len = aux->skip_len;
+        }
     }
     *done_ms = m;
     return stop;

@@ -197,6 +197,8 @@ class Reference:
         lib.ref_iq_cell.argtypes = [vp, vp, f32, u32, u32, u32, vp]
         lib.ref_sweep_cells.argtypes = [vp, u32, vp, u32, i32, i32, u32, u32, vp]
         lib.ref_track_run.argtypes = [vp, vp, u32, u32, vp, vp, vp]
+        lib.ref_track_run_walk.argtypes = [vp, vp, u32, u32, vp, vp, vp, vp]
+        lib.ref_sizeof_walk.restype = u32
         lib.ref_epl_cell.argtypes = [vp, vp, f32, u32, f32, vp, C.POINTER(u32)]
         lib.ref_now_s.restype = C.c_double
         # plain reference primitives (gps_misc.h:198-216)
@@ -278,6 +280,26 @@ class Reference:
         st = np.zeros((n_ms, 2), np.float32)
         self.lib.ref_track_run(ch, _p(signal), ms_first, n_ms, _p(iq), _p(nav), _p(st))
         return iq, nav, st
+
+
+class RefWalk(C.Structure):
+    """oracle/ref_shim.c, ref_walk: the checker's restatement of the slot-phase walk"""
+    _fields_ = [("enable", C.c_uint32), ("period_ms", C.c_uint32), ("slot_phase", C.c_uint32), ("gap_first", C.c_uint32),
+                ("gap_len", C.c_uint32), ("phase_since", C.c_uint32), ("gaps_taken", C.c_uint32), ("edge_pos", C.c_uint32),
+                ("slot_first_ms", C.c_uint32), ("sign", C.c_uint8 * 4)]
+
+
+def _track_run_walk(self, ch, signal: np.ndarray, ms_first: int, n_ms: int, walk: RefWalk):
+    """The unmodified reference on the walked (millisecond, slot index) schedule; returns iq, nav, index per ms."""
+    assert self.lib.ref_sizeof_walk() == C.sizeof(RefWalk)
+    iq = np.zeros((n_ms, 6), np.int16)
+    nav = np.zeros(n_ms, np.int8)
+    idx = np.zeros(n_ms, np.uint8)
+    self.lib.ref_track_run_walk(ch, _p(signal), ms_first, n_ms, C.byref(walk), _p(iq), _p(nav), _p(idx))
+    return iq, nav, idx
+
+
+Reference.track_run_walk = _track_run_walk
 
 
 def have_reference() -> bool:

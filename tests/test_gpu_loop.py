@@ -347,3 +347,70 @@ def test_loop_begin_end_call_sequence_errors(host_engine, golden):
     assert [int(res[i, 0]) for i in range(2)] == [64, 64] and [int(res[i, 1]) for i in range(2)] == [0, 0]
     rx.close()
     ch.free()
+
+
+def test_slot_walk_all_alignments_on_the_device(reference):
+    """Four satellites whose data-bit edges sit at all four slot alignments, tracked by ONE k_track_run launch with the
+    slot-phase walk enabled (gpsb_rx_set_slot_walk): every channel ends with a refined bit edge, and sums, nav bits,
+    the idle schedule and the channel records equal the UNMODIFIED reference driven on the walked (millisecond, slot
+    index) schedule by the checker's own restatement of the policy (oracle/ref_shim.c, ref_track_run_walk).  The same
+    recording streamed through a ring shorter than the run, split into several launches, and with the loop filters on
+    the host gives the same bytes."""
+    from stm32f4_sdr_gps_b200 import Engine
+    from test_slot_walk import N_MS, locked, reference_walk, walk_scene
+    scene, sig = walk_scene()
+    refs = [reference_walk(reference, sat, sig, N_MS) for sat in scene.sats]
+    eng = Engine(device=0, max_sv=40, ring_ms=4096)
+    eng.upload_signal(0, sig)
+
+    def fresh():
+        ch = Channels([s.prn for s in scene.sats])
+        for i, sat in enumerate(scene.sats):
+            ch.restore(i, locked(ch.snapshot(i), sat))
+        rx = Receiver(eng, ch)
+        rx.set_slot_walk(True)
+        return ch, rx
+
+    def check(ch, rx, iq, nav, what):
+        for i, (want, iq_ref, nav_ref, idx_ref, walk) in enumerate(refs):
+            assert np.array_equal(iq[:, i, :], iq_ref), (what, i)
+            assert np.array_equal(nav[:, i], nav_ref), (what, i)
+            assert np.array_equal(~iq[:, i, :].any(axis=1), idx_ref == 0xFF), (what, i)
+            assert bytes(ch.snapshot(i)) == bytes(want), (what, i)
+            s = rx.sync_status(i)
+            assert s.bit_edge_refined == 1 and s.walks == walk.gaps_taken and s.slot_phase == walk.slot_phase, (what, i)
+        assert sorted(int((~iq[:, i, :].any(axis=1)).sum()) for i in range(4)) == [0, 1, 2, 3], what
+
+    ch, rx = fresh()
+    launches0 = eng.launch_count
+    iq, nav = rx.track_run(0, N_MS)
+    assert eng.launch_count - launches0 == 1 and rx.loop_stats() == (4 * N_MS, 0)
+    check(ch, rx, iq, nav, "one launch")
+    rx.close(); ch.free()
+
+    ch, rx = fresh()                                   # cut inside slots and around the idle gaps
+    parts, at = [], 0
+    for end in (1203, 1207, 1810, 1811, 2404, N_MS):
+        parts.append(rx.track_run(at, end - at))
+        at = end
+    check(ch, rx, np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts]), "split launches")
+    rx.close(); ch.free()
+
+    ch, rx = fresh()                                   # loop filters on the host, one round trip per millisecond
+    rx.set_loop_site(1)
+    n_host = 2000
+    iq_h, nav_h = rx.track_run(0, n_host)
+    assert np.array_equal(iq_h, iq[:n_host]) and np.array_equal(nav_h, nav[:n_host])
+    rx.close(); ch.free()
+    eng.close()
+
+    small = Engine(device=0, max_sv=40, ring_ms=256)   # streamed through a ring shorter than the run
+    ch = Channels([s.prn for s in scene.sats])
+    for i, sat in enumerate(scene.sats):
+        ch.restore(i, locked(ch.snapshot(i), sat))
+    rx = Receiver(small, ch)
+    rx.set_slot_walk(True)
+    iq_s, nav_s = rx.track_stream(0, sig, chunk_ms=64)
+    check(ch, rx, iq_s, nav_s, "streamed")
+    rx.close(); ch.free()
+    small.close()
