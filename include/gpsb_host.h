@@ -357,7 +357,7 @@ void gpsb_rx_set_threads(gpsb_rx* rx, uint32_t n);
  * milliseconds out between two slots (the MCU's own means: an unserved channel, PM/GPS/tracking.c:102-113) until its
  * edges show at slot position 2: every satellite then delivers subframe stamps.  Results equal the unmodified
  * reference called on the same (millisecond, slot index) schedule; idle milliseconds log zero sums and no nav bit.
- * period_ms: patience at one slot phase without bit-period sync, 0 = 600.  Default: off (index = ms % 4). */
+ * period_ms: patience at one slot phase without any bit edge seen, 0 = 400.  Default: off (index = ms % 4). */
 int gpsb_rx_set_slot_walk(gpsb_rx* rx, int enable, uint32_t period_ms);
 /* Where a channel stands on its way to a time stamp (so a caller can tell "not yet" from "never"). */
 typedef struct gpsb_sync_status {

@@ -368,8 +368,9 @@ void ref_track_run(gps_ch_t* ch, const uint8_t* signal, uint32_t ms_first, uint3
  * reference.  A channel is called with slot index (ms + slot_phase) % 4; inside an idle gap it is called with the
  * reference's dummy index 0xFF (main.c:146-147), which tracking.c:96 ignores.  After a complete slot of a channel that
  * has no refined bit edge (nav_data.accurate_swap_ok == 0):
- *   bit period found and the last on-grid edge showed at slot position 3 -> idle 1 ms, at position 1 -> idle 3 ms;
- *   no bit period for period_ms at this slot phase                      -> idle 2 ms;
+ *   an on-grid edge has shown at slot position 2 since the last gap       -> nothing;
+ *   three or more on-grid edges since then, all at positions 3 or 1      -> idle 1 ms (most at 3, ties too) or 3 ms;
+ *   no on-grid edge seen for period_ms (default 400) at this slot phase   -> idle 2 ms;
  * the gap begins 5 ms after the slot end at which it was decided, and the millisecond behind a gap is slot index 0.
  * Edge positions are observed from outside: sign of the prompt sum XOR the polarity flag before the call, one flip in
  * the slot, "on grid" = (edge - old_swap_time before the call) % 20 in {0, 1, 19} (nav_data.c:87-113).
@@ -378,14 +379,31 @@ void ref_track_run(gps_ch_t* ch, const uint8_t* signal, uint32_t ms_first, uint3
 typedef struct ref_walk {
     uint32_t enable, period_ms;
     uint32_t slot_phase, gap_first, gap_len, phase_since, gaps_taken, edge_pos;
+    uint32_t edges_at[4];             /* on-grid edges seen per slot position since the last gap was decided */
     uint32_t slot_first_ms;
     uint8_t sign[4];
+    int16_t ip[4];
+    uint32_t slot_fill;               /* entries of sign[] / ip[] that belong to the slot in progress */
 } ref_walk;
 uint32_t ref_sizeof_walk(void) { return (uint32_t)sizeof(ref_walk); }
+
+void gps_nav_data_analyse_new_code(gps_ch_t* channel, uint8_t index, int16_t new_i);
 
 void ref_track_run_walk(gps_ch_t* ch, const uint8_t* signal, uint32_t ms_first, uint32_t n_ms, ref_walk* w,
                         int16_t* iq_log, int8_t* nav_log, uint8_t* idx_log)
 {
+    /* The reference keeps the samples of the slot in progress in function statics shared by all channels
+     * (nav_data.c:29,48-51).  A run that resumes inside a slot after ANOTHER channel was run puts this channel's
+     * samples back first, through the reference's own function on a scratch channel that does nothing else. */
+    if (w->slot_fill) {
+        static gps_ch_t scratch;
+        for (uint32_t i = 0; i < w->slot_fill && i < TRACKING_CH_LENGTH - 1; i++) {
+            memset(&scratch.nav_data, 0, sizeof scratch.nav_data);
+            scratch.nav_data.inv_polarity_flag = (uint8_t)(w->sign[i] ^ (w->ip[i] > 0 ? 1 : 0));
+            g_packet_cnt = w->slot_first_ms + i;
+            gps_nav_data_analyse_new_code(&scratch, (uint8_t)i, w->ip[i]);
+        }
+    }
     for (uint32_t k = 0; k < n_ms; k++) {
         const uint32_t ms = ms_first + k;
         uint8_t* frame = (uint8_t*)(signal + 2046u * (size_t)k);
@@ -425,14 +443,19 @@ void ref_track_run_walk(gps_ch_t* ch, const uint8_t* signal, uint32_t ms_first, 
 
         /* the observer and the policy */
         w->sign[index] = (uint8_t)((o[2] > 0 ? 1 : 0) ^ (nb.inv_polarity_flag ? 1 : 0));
+        w->ip[index] = o[2];
         if (index == 0) w->slot_first_ms = ms;
+        w->slot_fill = (index + 1u) % TRACKING_CH_LENGTH;
         if (index != TRACKING_CH_LENGTH - 1) continue;
         uint32_t changes = 0, where = 0;
         for (uint32_t i = 1; i < TRACKING_CH_LENGTH; i++)
             if (w->sign[i] != w->sign[i - 1]) { changes++; where = i; }
         if (changes == 1) {
             const uint32_t rem = (w->slot_first_ms + where - nb.old_swap_time) % 20u;
-            if (rem == 0 || rem == 1 || rem == 19) w->edge_pos = where;
+            if (rem == 0 || rem == 1 || rem == 19) {
+                w->edge_pos = where;
+                if (w->edges_at[where] < 255) w->edges_at[where]++;
+            }
         }
         if (w->gap_len) {
             if (ms < w->gap_first + w->gap_len) continue;          /* decided, not taken yet */
@@ -440,16 +463,16 @@ void ref_track_run_walk(gps_ch_t* ch, const uint8_t* signal, uint32_t ms_first, 
         }
         if (!w->enable || ch->nav_data.accurate_swap_ok) continue;
         uint32_t gap = 0;
-        if (ch->nav_data.period_sync_ok_flag && w->edge_pos) {
-            if (w->edge_pos == 3) gap = 1;
-            else if (w->edge_pos == 1) gap = 3;
-        } else if (ms - w->phase_since >= (w->period_ms ? w->period_ms : 600u)) {
-            gap = 2;
+        if (w->edges_at[2] == 0) {
+            if (w->edges_at[1] + w->edges_at[3] >= 3) gap = (w->edges_at[3] >= w->edges_at[1]) ? 1 : 3;
+            else if (w->edges_at[1] + w->edges_at[3] == 0 && ms - w->phase_since >= (w->period_ms ? w->period_ms : 400u))
+                gap = 2;
         }
         if (gap) {
             w->gap_first = ms + 5u;
             w->gap_len = gap;
             w->edge_pos = 0;
+            memset(w->edges_at, 0, sizeof w->edges_at);
             w->gaps_taken++;
         }
     }

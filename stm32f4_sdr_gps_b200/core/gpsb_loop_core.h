@@ -76,7 +76,8 @@
 #define LC_MS_PER_BIT        20                           /* CODES_IN_BIT, nav_data.c:15 */
 #define LC_WORDS_PER_SUBFRAME 10                          /* nav_data.c:17 */
 #define LC_POLARITY_TIMEOUT_MS 12000u                     /* two subframes, nav_data.c:22 */
-#define LC_WALK_PERIOD_MS    600u                         /* default patience of the slot-phase walk (this library's) */
+#define LC_WALK_PERIOD_MS    400u                         /* default patience of the slot-phase walk (this library's) */
+#define LC_WALK_CONFIDENCE   3u                           /* on-grid edges seen before their slot position is believed */
 #define LC_WALK_LEAD_MS      5u                           /* a walk decided at the end of a slot idles after the NEXT slot */
 #define LC_IDLE_INDEX        0xFFu                        /* the reference's "dummy" slot index (main.c:146-147, tracking.c:96) */
 #define LC_PI                3.14159265358979323846       /* <math.h>'s double M_PI, see host/track.c */
@@ -114,7 +115,8 @@ typedef struct gpsb_aux {
     uint8_t  walk_enable;                       /* 1: lc_walk_policy may move the slots of this channel */
     uint8_t  skip_len;                          /* the channel idles in [skip_ms, skip_ms + skip_len): 0 = no walk decided */
     uint8_t  last_flip_pos;                     /* observer: slot position (1..3) of the last bit edge seen on the 20-ms grid */
-    uint16_t walk_period_ms;                    /* patience at one slot phase without bit-period sync (0 = LC_WALK_PERIOD_MS) */
+    uint8_t  flip_cnt[4];                       /* observer: such edges seen per slot position at this slot phase (saturating) */
+    uint16_t walk_period_ms;                    /* patience at one slot phase without any bit edge seen (0 = LC_WALK_PERIOD_MS) */
     uint16_t walks;                             /* statistics: idle gaps taken so far */
     uint32_t skip_ms;                           /* first idle millisecond of the pending (or last) walk */
     uint32_t phase_since_ms;                    /* millisecond at which the current slot phase began */
@@ -826,7 +828,8 @@ LC_FN int lc_nav_new_code(gps_ch_t* ch, gpsb_aux* aux, uint8_t index, int16_t ne
     if (phase < 2 || phase == LC_MS_PER_BIT - 1) {            /* a multiple of 20 ms since the last edge */
         if (n->right_period_cnt < 10) n->right_period_cnt++;
         if (n->right_period_cnt > 8) n->period_sync_ok_flag = 1;
-        aux->last_flip_pos = flip_pos;                        /* observer for lc_walk_policy; not reference state */
+        aux->last_flip_pos = flip_pos;                        /* observers for lc_walk_policy; not reference state */
+        if (aux->flip_cnt[flip_pos & 3u] < 255u) aux->flip_cnt[flip_pos & 3u]++;
     } else {
         if (n->right_period_cnt > 0) n->right_period_cnt--;
         if (n->right_period_cnt < 3) n->period_sync_ok_flag = 0;
@@ -848,10 +851,13 @@ LC_FN int lc_nav_new_code(gps_ch_t* ch, gpsb_aux* aux, uint8_t index, int16_t ne
  * reference does with a channel it does not serve: no call, and gps_rewind_if_phase catches the carrier NCO up,
  * tracking.c:102-113) and starts its next slot behind the gap.  Every slot stays a whole index 0..3 sequence, so the
  * result equals the unmodified reference called on the same (millisecond, index) schedule - which is how the tests
- * check it (oracle/ref_shim.c: ref_track_run_walk).  Policy (this library's, evaluated at the end of a slot):
- *   - bit period found and the edges show at slot position 3 / 1: idle 1 / 3 ms - the edges then show at position 2;
- *   - no bit period after walk_period_ms at this slot phase (edges on the slot boundary, or none seen): idle 2 ms;
- *   - edges already at position 2, or the edge refined (accurate_swap_ok): nothing.
+ * check it (oracle/ref_shim.c: ref_track_run_walk).  Policy (this library's, evaluated at the end of a slot, from what the
+ * bit synchroniser has seen at the current slot phase):
+ *   - an edge on the 20-ms grid has shown at slot position 2: nothing - the synchroniser is on its way (an edge in the
+ *     middle of a millisecond shows at two neighbouring positions in turn; one of them being 2 is enough);
+ *   - LC_WALK_CONFIDENCE edges on the grid, all at positions 3 / 1: idle 1 / 3 ms (majority) - they then show at 2;
+ *   - no edge on the grid seen for walk_period_ms at this slot phase (they fall on the slot boundary): idle 2 ms;
+ *   - edge refined (accurate_swap_ok): nothing, for ever.
  * A walk decided at the end of a slot takes effect LC_WALK_LEAD_MS later, behind the next slot, so that the thread
  * that plans the carrier NCO of the device-resident loop knows it a whole slot ahead. */
 LC_FN int lc_walk_idle(uint32_t skip_ms, uint32_t skip_len, uint32_t ms) { return (uint32_t)(ms - skip_ms) < skip_len; }
@@ -881,15 +887,15 @@ LC_FN void lc_walk_policy(const gps_ch_t* ch, gpsb_aux* aux, uint32_t ms)
     if (!aux->walk_enable || n->accurate_swap_ok) return;
     const uint32_t patience = aux->walk_period_ms ? aux->walk_period_ms : LC_WALK_PERIOD_MS;
     uint8_t idle = 0;
-    if (n->period_sync_ok_flag && aux->last_flip_pos) {
-        if (aux->last_flip_pos != 2) idle = (uint8_t)((aux->last_flip_pos + 2u) & 3u);     /* 3 -> 1 ms, 1 -> 3 ms */
-    } else if (ms - aux->phase_since_ms >= patience) {
-        idle = 2;
-    }
+    const unsigned off_centre = (unsigned)aux->flip_cnt[1] + aux->flip_cnt[3];
+    if (aux->flip_cnt[2]) return;
+    if (off_centre >= LC_WALK_CONFIDENCE) idle = aux->flip_cnt[3] >= aux->flip_cnt[1] ? 1 : 3;
+    else if (off_centre == 0 && ms - aux->phase_since_ms >= patience) idle = 2;
     if (!idle) return;
     aux->skip_ms = ms + LC_WALK_LEAD_MS;
     aux->skip_len = idle;
     aux->last_flip_pos = 0;
+    aux->flip_cnt[1] = aux->flip_cnt[2] = aux->flip_cnt[3] = 0;
     aux->walks++;
 }
 

@@ -8,7 +8,7 @@ from test_bits_to_position import quantise, subframe_bits
 from test_fix import CLIGHT, geodetic_to_ecef, make_sky, pseudorange
 
 L1_HZ = 1575.42e6
-LEAD_BITS, TAIL_BITS = 50, 45
+LEAD_BITS, TAIL_BITS = 100, 45      # 2 s ahead of subframe 1: time for the slot-phase walk and the bit synchroniser
 FIRST_TOW_COUNT = 52000
 
 
@@ -24,29 +24,24 @@ class PositionScene:
         t_meas = self.t_end + 0.35
         c_ms = CLIGHT / 1000.0
         n_stream = LEAD_BITS + 300 * len(ids) + TAIL_BITS
-        while True:
-            self.sky, self.raws = [], []
-            for el in make_sky(rng, self.site, self.t_end, 4):
-                el["toes"] = el["toc"] = float(int(self.t_end) // 7200 * 7200)
-                raw, back = quantise(el, 1)
-                self.sky.append(back); self.raws.append(raw)
-            flight_m = np.array([pseudorange(el, self.site, t_meas, 0.0) for el in self.sky]) / c_ms       # ms at t_meas
-            rate = np.array([pseudorange(el, self.site, t_meas + 0.5, 0.0) - pseudorange(el, self.site, t_meas - 0.5, 0.0)
-                             for el in self.sky])               # m/s
-            # linear model anchored at the measurement: a signal sent at GPS time tau arrives flight(tau) later
-            flight_at = lambda tau: flight_m + rate / CLIGHT * (tau - t_meas) * 1000.0                    # ms
-            a0 = 102.3 - flight_at(self.t0).min()               # receiver ms of a zero-delay arrival of the stream start
-            first = a0 + flight_at(self.t0)                     # receiver ms at which stream bit 1 starts arriving
-            # The bit synchroniser only sees a data-bit edge that falls inside a 4-ms slot, and only refines the one at
-            # slot position 2 (nav_data.c:87-138).  The reference's 17-ms channel schedule walks every alignment past
-            # that window; with every millisecond processed in place (index = ms % 4) the alignment is fixed, so the
-            # scene is drawn until each satellite's edges land there: the millisecond that shows the sign flip - the one
-            # holding the edge if the edge comes in its first half, else the next - is 2 modulo 4.
-            whole, part = np.floor(first).astype(int), first % 1.0
-            flip_ms = np.where(part < 0.5, whole, whole + 1)
-            clear = ((part > 0.15) & (part < 0.42)) | ((part > 0.58) & (part < 0.85))     # and the code phase never wraps
-            if np.all(flip_ms % 4 == 2) and np.all(clear) and np.all(np.abs(rate) < 780.0):
-                break
+        # The geometry is taken as drawn.  Where each satellite's data-bit edges fall relative to the 4-ms channel slots
+        # (flip_ms % 4 below) is whatever the flight times give: the batched paths bring them to slot position 2 - the
+        # only one the reference's bit synchroniser refines, nav_data.c:87-138 - with the slot-phase walk
+        # (gpsb_rx_set_slot_walk), as the MCU's 17-ms channel schedule does on the hardware.
+        self.sky, self.raws = [], []
+        for el in make_sky(rng, self.site, self.t_end, 4):
+            el["toes"] = el["toc"] = float(int(self.t_end) // 7200 * 7200)
+            raw, back = quantise(el, 1)
+            self.sky.append(back); self.raws.append(raw)
+        flight_m = np.array([pseudorange(el, self.site, t_meas, 0.0) for el in self.sky]) / c_ms       # ms at t_meas
+        rate = np.array([pseudorange(el, self.site, t_meas + 0.5, 0.0) - pseudorange(el, self.site, t_meas - 0.5, 0.0)
+                         for el in self.sky])               # m/s
+        # linear model anchored at the measurement: a signal sent at GPS time tau arrives flight(tau) later
+        flight_at = lambda tau: flight_m + rate / CLIGHT * (tau - t_meas) * 1000.0                    # ms
+        a0 = 102.3 - flight_at(self.t0).min()               # receiver ms of a zero-delay arrival of the stream start
+        first = a0 + flight_at(self.t0)                     # receiver ms at which stream bit 1 starts arriving
+        whole, part = np.floor(first).astype(int), first % 1.0
+        self.flip_ms = np.where(part < 0.5, whole, whole + 1)   # the millisecond that shows the sign flip of an edge
         self.a0, self.rate, self.flight_m, self.t_meas = a0, rate, flight_m, t_meas
         self.doppler = -rate / (CLIGHT / L1_HZ)
         self.offset_ms = np.floor(first).astype(int)
@@ -61,10 +56,10 @@ class PositionScene:
         self.sats = sats
         # receiver ms at which the end of subframe 3 of the latest satellite has arrived, plus the first filter window
         last_edge = (a0 + (self.t_end - self.t0) * 1000.0 + flight_m).max()
-        # legs end on a 4-ms slot boundary: the reference keeps the samples of the slot in progress in function statics
-        # shared by all channels (nav_data.c:48-51), so a leg cut inside a slot would hand channel k the leftovers of
-        # channel k-1 there, while this library keeps them per channel
-        self.n_first = (int(last_edge) + 120 + 3) // 4 * 4
+        # (the reference keeps the samples of the slot in progress in function statics shared by all channels,
+        # nav_data.c:48-51; the checker's driver ref_track_run_walk puts a channel's own samples back when a leg resumes
+        # inside a slot, so legs may end anywhere)
+        self.n_first = int(last_edge) + 121
         self.n_second = 300
         self.n_ms = self.n_first + self.n_second + 8
         self.seed = seed

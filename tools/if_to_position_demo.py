@@ -4,7 +4,7 @@
     python tools/if_to_position_demo.py          # needs a B200; oracle/_ref is used only to pick the carrier phases
 
 Prints one JSON line: where the fix landed, how far from the true site, and how long the device-resident loop took for
-the two tracking legs (four channels, 19.2 s + 0.3 s of signal, streamed from host memory)."""
+the two tracking legs (four channels, 20.2 s + 0.3 s of signal, streamed from host memory; slot-phase walk on)."""
 import ctypes as C
 import json
 import sys
@@ -25,7 +25,7 @@ def main():
     lib = load_host_library()
     T.protos(lib, reference.lib)
     t0 = time.time()
-    sc, sig = T.scene_and_signal(reference)
+    sc, sig = T.scene_and_signal(reference, 83)          # bit edges at all four slot alignments
     t_synth = time.time() - t0
     with Engine(device=0, max_sv=211, ring_ms=1024) as eng:
         assert lib.gpsb_host_attach(eng.handle) == 0
@@ -48,6 +48,7 @@ def main():
         ch.free()
         ch = tracking_channels()
         rx = Receiver(eng, ch)
+        rx.set_slot_walk(True)                                    # every satellite gets its bit edges refined
         legs = []
         for ms0, n in ((0, sc.n_first), (sc.n_first, sc.n_second)):
             part = np.ascontiguousarray(sig[ms0:ms0 + n])
@@ -59,6 +60,7 @@ def main():
         t0 = time.perf_counter()
         fix = ch.position_fix()
         t_fix = time.perf_counter() - t0
+        rx_walks = [rx.sync_status(i).walks for i in range(4)]
         rx.close()
         lib.gpsb_host_attach(None)
     out = {"truth": {"lat_deg": sc.lat, "lon_deg": sc.lon, "height_m": sc.h},
@@ -67,6 +69,7 @@ def main():
            "signal_s": (sc.n_first + sc.n_second) / 1000.0, "channels": 4,
            "tracking_leg_ms": [round(1e3 * x, 2) for x in legs], "fix_us": round(1e6 * t_fix, 1),
            "times_real_time": round((sc.n_first + sc.n_second) / 1000.0 / sum(legs), 1),
+           "slot_walks": [int(rx_walks[i]) for i in range(4)], "bit_edge_alignments": [int(x) for x in sc.flip_ms % 4],
            "synthesis_s": round(t_synth, 1)}
     print(json.dumps(out))
 
