@@ -159,19 +159,22 @@ class ClockSampler:
 # ----------------------------------------------------------------------------- reference arm (CPU)
 def _ref_worker(args):
     """Closed-loop reference tracking of one satellite in its own process (reference globals are not
-    re-entrant)."""
-    prn, fo_hz, fine, sig_path, n_ms, reps = args
+    re-entrant).  Returns (best seconds over `reps` timed runs, logs or None): with want_logs a
+    further, untimed run returns the reference's own per-ms sums, nav bits and final channel record."""
+    prn, fo_hz, fine, sig_path, n_ms, reps, so_path, want_logs = args
+    import ctypes as C
     sys.path.insert(0, str(REPO / "tests"))
     from oracle_lib import Reference
-    ref = Reference()
-    sig = np.load(sig_path)
+    ref = Reference(so_path)
+    sig = np.load(sig_path, mmap_mode="r")
+    sig = np.ascontiguousarray(sig[:n_ms])
     chans = ref.channels(1)
     ch = ref.channel_at(chans, 0)
     lib = ref.lib
-    lib.ref_track_time.restype = __import__("ctypes").c_double
-    lib.ref_track_time.argtypes = [__import__("ctypes").c_void_p] * 2 + [__import__("ctypes").c_uint32] * 2
-    best = 1e30
-    for _ in range(reps):
+    lib.ref_track_time.restype = C.c_double
+    lib.ref_track_time.argtypes = [C.c_void_p] * 2 + [C.c_uint32] * 2
+
+    def arm():
         ref.channel_init(ch, prn, 0)
         st = ref.snapshot(ch)
         # start locked (GPS_ACQ_DONE / GPS_TRACKING_RUN) on the true code phase and Doppler so that all n_ms
@@ -181,45 +184,64 @@ def _ref_worker(args):
         st.if_freq_offset_hz_bits = int(np.float32(fo_hz).view(np.uint32))
         st.code_phase_fine_bits = int(np.float32(fine).view(np.uint32))
         ref.restore(ch, st)
+
+    best = 1e30
+    for _ in range(reps):
+        arm()
         best = min(best, lib.ref_track_time(ch, sig.ctypes.data, 0, n_ms))
-    return best
+    logs = None
+    if want_logs:
+        arm()
+        iq, nav, _ = ref.track_run(ch, sig, 0, n_ms)
+        logs = (iq, nav, bytes(ref.snapshot(ch)))
+    return best, logs
 
 
-def reference_tracking_seconds(scene, sig, max_procs: int, reps: int = 3):
-    """Wall time for the reference C to track all satellites of the scene over the whole recording,
-    one process per satellite on up to max_procs cores.  Returns (seconds, cores_used, kind)."""
+def reference_tracking(scenes_and_sigs, max_procs: int, reps: int = 3, so_path=None, want_logs: bool = False):
+    """The reference C tracking every satellite of every scene over its whole recording, one process per satellite on
+    up to max_procs cores AT THE SAME TIME (a channel's 1-kHz loop is serial, so one satellite cannot use more than one
+    core).  Returns (seconds for the whole job, processes used, logs per satellite or None)."""
     import multiprocessing as mp
     sys.path.insert(0, str(REPO / "tests"))
     from oracle_lib import have_reference
     if not have_reference():
-        return None, 0, "port"
-    path = Path(tempfile.gettempdir()) / ("gpsb_ref_sig_%d.npy" % os.getpid())
-    np.save(path, sig)
-    jobs = [(s.prn, float(s.doppler_hz), float(s.code_phase_samples), str(path), scene.n_ms, reps) for s in scene.sats]
+        return None, 0, None
+    jobs, paths = [], []
+    for k, (scene, sig) in enumerate(scenes_and_sigs):
+        path = Path(tempfile.gettempdir()) / ("gpsb_ref_sig_%d_%d.npy" % (os.getpid(), k))
+        np.save(path, sig)
+        paths.append(path)
+        jobs += [(s.prn, float(s.doppler_hz), float(s.code_phase_samples), str(path), scene.n_ms, reps,
+                  str(so_path) if so_path else None, want_logs) for s in scene.sats]
     procs = max(1, min(max_procs, len(jobs)))
-    t0 = time.perf_counter()
     if procs == 1:
-        per = [_ref_worker(j) for j in jobs]
-        wall = sum(per)
+        out = [_ref_worker(j) for j in jobs]
+        wall = sum(o[0] for o in out)
     else:
         with mp.get_context("fork").Pool(procs) as pool:
-            per = pool.map(_ref_worker, jobs)
-        # satellites run concurrently: the job takes as long as the slowest core's share
-        rounds = [per[i::procs] for i in range(procs)]
-        wall = max(sum(r) for r in rounds)
-    _ = time.perf_counter() - t0
-    path.unlink(missing_ok=True)
-    return wall, procs, "reference"
+            out = pool.map(_ref_worker, jobs, chunksize=1)
+        # satellites run concurrently: the job takes as long as the busiest core's share
+        per = [o[0] for o in out]
+        wall = max(sum(per[i::procs]) for i in range(procs))
+    for path in paths:
+        path.unlink(missing_ok=True)
+    return wall, procs, ([o[1] for o in out] if want_logs else None)
+
+
+def reference_tracking_seconds(scene, sig, max_procs: int, reps: int = 3):
+    wall, procs, _ = reference_tracking([(scene, sig)], max_procs, reps)
+    return wall, procs, "reference" if wall is not None else "port"
 
 
 def reference_sweep_rate(acq_sig, n_sv: int = 2, n_ms: int = 2):
     """Reference C (oracle/_ref) on a bounded sample of the cold-acquisition cells: n_sv x 21 bins x n_ms full
-    2046-phase searches on one core.  Returns (cells_per_second, n_cells) or (None, 0)."""
+    2046-phase searches on one core (PRN 1, 2; first n_ms milliseconds).  Returns (cells_per_second, n_cells, the
+    reference's (max, phase, avg) per cell) or (None, 0, None)."""
     import ctypes as C
     sys.path.insert(0, str(REPO / "tests"))
     from oracle_lib import Reference, have_reference
     if not have_reference():
-        return None, 0
+        return None, 0, None
     ref = Reference()
     lib = ref.lib
     lib.ref_sweep_time.restype = C.c_double
@@ -232,7 +254,7 @@ def reference_sweep_rate(acq_sig, n_sv: int = 2, n_ms: int = 2):
     sig = np.ascontiguousarray(acq_sig[:n_ms])
     best = min(lib.ref_sweep_time(chans, n_sv, sig.ctypes.data, n_ms, -5000, 500, ACQ_BINS, 0, out.ctypes.data)
                for _ in range(2))
-    return n_sv * ACQ_BINS * n_ms / best, n_sv * ACQ_BINS * n_ms
+    return n_sv * ACQ_BINS * n_ms / best, n_sv * ACQ_BINS * n_ms, out
 
 
 def reference_prompt_rate(sig, n_ms: int = 8000):
@@ -266,20 +288,18 @@ def run_reference_arm(args) -> None:
         return
     n_gpus = args.gpus
     scenes = [make_scene(r, N_MS) for r in range(n_gpus)]
+    pairs = [(sc, cached_signal("trk_r%d_%d" % (r, N_MS), sc)) for r, sc in enumerate(scenes)]
     cores = os.cpu_count() or 1
     times = []
     used = 1
     for w in range(args.warmup + args.steps):
-        t_step = 0.0
-        for r, sc in enumerate(scenes):
-            sig = cached_signal("trk_r%d_%d" % (r, N_MS), sc)
-            t, used, kind = reference_tracking_seconds(sc, sig, cores, reps=3)
-            if t is None:
-                print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libgpsref.so missing"}))
-                return
-            t_step += t
+        # every satellite of every rank's scene at once, one process each, on as many cores as the box has
+        t, used, _ = reference_tracking(pairs, cores, reps=3)
+        if t is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libgpsref.so missing"}))
+            return
         if w >= args.warmup:
-            times.append(t_step)
+            times.append(t)
     t = float(np.mean(times))
     units = n_gpus * N_SV_PER_GPU * ARMS * MS_SAMPLES * N_MS
     v = units / t
@@ -290,8 +310,10 @@ def run_reference_arm(args) -> None:
         "data": "synthetic",
         "config": {"workload": "config2: %d-SV E/P/L closed-loop tracking, 1 s @16.368 Msps 1-bit IF" % (n_gpus * N_SV_PER_GPU),
                    "n_sv": n_gpus * N_SV_PER_GPU, "n_ms": N_MS},
-        "cpu_baseline": {"value": v, "unit": "arm-samples/s", "cores": used, "kind": "reference",
-                         "sample": "whole workload: unmodified reference gps_tracking_process() closed loop, one process per SV"},
+        "cpu_baseline": {"value": v, "unit": "arm-samples/s", "cores": used, "host_cores": cores, "kind": "reference",
+                         "sample": "whole workload: unmodified reference gps_tracking_process() closed loop, one process per "
+                                   "SV, all %d SV at the same time on %d of the box's %d cores (a channel's loop is "
+                                   "serial: one SV cannot use more than one core)" % (n_gpus * N_SV_PER_GPU, used, cores)},
         "e2e": {"value": v, "unit": "arm-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -429,6 +451,9 @@ def run_gpu_arm(args) -> None:
     launches = eng.launch_count - launches0
     on_device, on_host = rx.loop_stats()
     assert np.array_equal(iq_log, iq_dev), "device-resident and host-library runs disagree"
+    nav_dev = d_nav.cpu().numpy().reshape(N_MS, n_ch)
+    assert np.array_equal(nav_log, nav_dev), "device-resident and host-library runs disagree (nav bits)"
+    final_records = [bytes(channels.snapshot(i)) for i in range(channels.n)]
     final_fine = [np.uint32(channels.snapshot(i).code_phase_fine_bits).view(np.float32) for i in range(channels.n)]
 
     # the same second with the loop filters on the HOST (one GPU round trip per millisecond), for comparison
@@ -456,37 +481,39 @@ def run_gpu_arm(args) -> None:
         t_seq.append(time.perf_counter() - t0)
     upload_then_run_ms = min(t_seq) * 1e3
 
-    # ---- config 5 shape on one GPU: 32 channels tracked continuously from a host-resident stream through a ring
-    # SHORTER than the run (256 ms), i.e. with the producer refilling the ring behind the loop.  The recording holds
-    # this rank's four satellites; eight channels follow each of them from slightly different starting points - the
-    # kernel's work per channel-millisecond does not depend on what is in the signal.
+    # ---- config 5 on ONE GPU: 32 different satellites tracked continuously from a host-resident stream through a ring
+    # SHORTER than the run (256 ms), i.e. with the producer refilling the ring behind the loop; one launch.
+    from stm32f4_sdr_gps_b200.signal_synth import config2_scene, synthesize_blocks
     n_many = 32
-    many = Channels([scene.sats[i % n_ch].prn for i in range(n_many)])
-
-    def arm_many():
-        for i in range(n_many):
-            sat = scene.sats[i % n_ch]
-            st = many.snapshot(i)
-            st.acq_state, st.trk_state = 9, 4
-            st.found_freq_offset_hz = int(round(sat.doppler_hz / 500.0) * 500)
-            st.if_freq_offset_hz_bits = int(np.float32(sat.doppler_hz + 3.0 * (i // n_ch)).view(np.uint32))
-            st.code_phase_fine_bits = int(np.float32(sat.code_phase_samples).view(np.uint32))
-            many.restore(i, st)
-
+    many_scene = config2_scene(n_ms=N_MS, prns=ALL_PRNS[:n_many], seed=0x5D120005)
+    many_path = Path(tempfile.gettempdir()) / ("gpsb_bench_cfg5_%d.npy" % N_MS)
+    if many_path.exists():
+        many_sig = np.load(many_path)
+    else:
+        many_sig = synthesize_blocks(many_scene.sats, N_MS, 0x5D120005)
+        if rank == 0:
+            try:
+                np.save(many_path, many_sig)
+            except OSError:
+                pass
+    pinned_many = torch.from_numpy(many_sig.copy()).pin_memory()
+    many = Channels([s.prn for s in many_scene.sats])
     many_blank = [many.snapshot(i) for i in range(n_many)]
     stream_eng = Engine(device=local_rank, max_sv=211, ring_ms=256)
     many_rx = Receiver(stream_eng, many)
     t_many = []
-    for k in range(0 if NO_STREAM else 4):
+    many_iq = many_nav = None
+    for k in range(0 if NO_STREAM else 5):
         for i in range(n_many):
             many.restore(i, many_blank[i])
-        arm_many()
+        arm_locked(many, many_scene)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        many_rx.track_stream(0, pinned_sig.numpy(), log=True)
+        many_iq, many_nav = many_rx.track_stream(0, pinned_many.numpy(), log=True)
         t_many.append(time.perf_counter() - t0)
-    many_ms = min(t_many) * 1e3 if t_many else float("nan")
+    many_ms = min(t_many[1:]) * 1e3 if t_many else float("nan")
     many_dev, many_host = many_rx.loop_stats()
+    many_records = [bytes(many.snapshot(i)) for i in range(n_many)]
     many_rx.close()
     stream_eng.close()
 
@@ -633,6 +660,7 @@ def run_gpu_arm(args) -> None:
     assert grid.shape == (ACQ_SV, ACQ_BINS, ACQ_MS, 4) and np.array_equal(grid[my_sv - 1], local)
     t_dev, t_e2e, acq_dp4a_ms, acq_direct_ms, acq_e2e_ms, batch_ms, many_ms, long1_ms, long3_ms = [float(x) for x in times.cpu()]
 
+    rank_has_prn12 = True        # the gathered grid holds every satellite on every rank
     if rank == 0:
         peaks = {}
         try:
@@ -655,16 +683,63 @@ def run_gpu_arm(args) -> None:
         acq_dp4a = ACQ_SV * ACQ_BINS * ACQ_MS * 4 * 1023 * 256 / world
         sm_clk = (clk.get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0) * 1e6
         idp_peak = 148 * 64 * sm_clk                       # IDP.4A: 64 lanes/clk/SM measured (tools/ubench_int.cu)
-        cpu_t, cpu_cores, cpu_kind = reference_tracking_seconds(scene, sig, os.cpu_count() or 1, reps=3)
-        acq_cpu_rate, acq_cpu_cells = reference_sweep_rate(acq_sig)
+        # ---- the reference's own C on this box's host cores, same workload, and the at-size parity of this run
+        sys.path.insert(0, str(REPO / "tests"))
+        from oracle_lib import best_o3_variant
+        host_cores = os.cpu_count() or 1
+        parity = {}
+        cpu_t, cpu_cores, ref_logs = reference_tracking([(scene, sig)], host_cores, reps=3, want_logs=True)
+        cpu = cpu_1core = cpu_o3 = None
+        if cpu_t:
+            for i, (r_iq, r_nav, r_rec) in enumerate(ref_logs):     # the reference's sums, nav bits and records vs this run's
+                assert np.array_equal(r_iq, iq_dev[:, i, :]), "config 2: sums of satellite %d differ from the reference's" % i
+                assert np.array_equal(r_nav, nav_dev[:, i]), "config 2: nav bits of satellite %d differ from the reference's" % i
+                assert r_rec == final_records[i], "config 2: final channel record %d differs from the reference's" % i
+            parity["config2_closed_loop"] = {"vs": "unmodified reference (oracle/_ref), same recording, same start",
+                                             "cells": int(n_ch * N_MS), "sums": int(n_ch * N_MS * 6), "nav_rows": int(n_ch * N_MS),
+                                             "channel_records": n_ch, "equal": True}
+            unit_sv = N_SV_PER_GPU * ARMS * MS_SAMPLES * N_MS
+            cpu = {"value": unit_sv / cpu_t, "unit": "arm-samples/s", "cores": cpu_cores, "host_cores": host_cores,
+                   "kind": "reference",
+                   "sample": "whole N=1 workload (4 SV x 1000 ms closed-loop gps_tracking_process), best of 3; one process per "
+                             "satellite - a channel's 1-kHz loop is serial, so 4 satellites can use 4 of the box's %d cores; "
+                             "32 satellites on all cores: see config5.cpu_baseline" % host_cores}
+            t1, _, _ = reference_tracking([(scene, sig)], 1, reps=3)
+            cpu_1core = {"value": unit_sv / t1, "unit": "arm-samples/s", "cores": 1, "kind": "reference",
+                         "sample": "same workload, the four satellites one after the other on one core"}
+            level, so_o3 = best_o3_variant()
+            if so_o3 is not None:
+                t3, c3, _ = reference_tracking([(scene, sig)], host_cores, reps=3, so_path=so_o3)
+                cpu_o3 = {"value": unit_sv / t3, "unit": "arm-samples/s", "cores": c3, "kind": "reference",
+                          "flags": "-O3 -march=%s -ffp-contract=off" % level,
+                          "sample": "same workload, the reference compiled at -O3 for the highest x86-64 level this box's CPU "
+                                    "has (the reference sources are not on the bench box, so -march=native cannot be built there)"}
+        # config 5 on one GPU: all 32 satellites against the reference, and the reference on all cores beside it
+        cfg5_cpu = None
+        if many_iq is not None:
+            t5, c5, logs5 = reference_tracking([(many_scene, many_sig)], host_cores, reps=2, want_logs=True)
+            if t5:
+                for i, (r_iq, r_nav, r_rec) in enumerate(logs5):
+                    assert np.array_equal(r_iq, many_iq[:, i, :]), "config 5: sums of satellite %d differ from the reference's" % i
+                    assert np.array_equal(r_nav, many_nav[:, i]), "config 5: nav bits of satellite %d differ from the reference's" % i
+                    assert r_rec == many_records[i], "config 5: final channel record %d differs from the reference's" % i
+                parity["config5_streaming_32sv"] = {"vs": "unmodified reference (oracle/_ref)", "cells": int(n_many * N_MS),
+                                                    "sums": int(n_many * N_MS * 6), "nav_rows": int(n_many * N_MS),
+                                                    "channel_records": n_many, "equal": True}
+                cfg5_cpu = {"value": n_many * ARMS * MS_SAMPLES * N_MS / t5, "unit": "arm-samples/s", "cores": c5,
+                            "host_cores": host_cores, "kind": "reference", "ms_per_s_of_signal": t5 * 1e3,
+                            "sample": "whole workload: 32 SV x 1000 ms, one process per satellite on %d cores at once" % c5}
+        acq_cpu_rate, acq_cpu_cells, acq_ref_cells = reference_sweep_rate(acq_sig)
+        if acq_ref_cells is not None and rank_has_prn12:
+            mine = grid[:acq_ref_cells.shape[0], :, :acq_ref_cells.shape[2], :3]
+            assert np.array_equal(mine, acq_ref_cells), "cold acquisition: (max, phase, avg) differ from the reference's"
+            parity["config3_sweep_sample"] = {"vs": "unmodified reference correlation_search", "cells": int(acq_ref_cells.size // 3),
+                                              "equal": True}
         prompt_cpu_rate, prompt_cpu_iq = reference_prompt_rate(long_sig)
         if prompt_cpu_iq is not None:      # the reference's own I/Q for the head of the long recording
             assert np.array_equal(prompt_cpu_iq, long_prompt[:prompt_cpu_iq.shape[0]]), "config 1: GPU and reference C disagree"
-        cpu = None
-        if cpu_t:
-            cpu = {"value": N_SV_PER_GPU * ARMS * MS_SAMPLES * N_MS / cpu_t, "unit": "arm-samples/s", "cores": cpu_cores,
-                   "kind": cpu_kind,
-                   "sample": "whole N=1 workload (4 SV x 1000 ms closed-loop gps_tracking_process), best of 3"}
+            parity["config1_batched"] = {"vs": "unmodified reference gps_correlation_iq", "cells": int(prompt_cpu_iq.shape[0]),
+                                         "equal": True}
         line = {
             "metric": "correlator-samples/sec (E/P/L arms)", "value": value, "unit": "arm-samples/s",
             "n_gpus": world, "steps": steps, "warmup": warm,
@@ -696,14 +771,21 @@ def run_gpu_arm(args) -> None:
                                  "one SM per satellite, not by bandwidth; the same launch carries 1 to 148 satellites in "
                                  "the same time"},
             "cpu_baseline": cpu,
-            "streaming": {"what": "config 5 shape: %d channels per GPU tracked continuously from a HOST-resident stream through a "
-                                  "256-ms HBM ring (run = %d ms, producer refills the ring behind the loop; one launch)"
-                                  % (n_many, N_MS),
-                          "ms_per_s_of_signal": many_ms * 1e3 / N_MS, "times_real_time": N_MS / many_ms,
-                          "input_msps_sustained": MS_SAMPLES * N_MS / (many_ms * 1e-3) / 1e6,
-                          "arm_samples_per_s": world * n_many * ARMS * MS_SAMPLES * N_MS / (many_ms * 1e-3),
-                          "channel_ms_on_device": int(many_dev), "channel_ms_on_host_path": int(many_host),
-                          "target": "163.68 Msps (10x real time)"},
+            "cpu_baseline_1core": cpu_1core,
+            "cpu_baseline_o3": cpu_o3,
+            "parity_checked": parity,
+            "config5": {"what": "config 5 on ONE GPU: %d different satellites tracked continuously from a HOST-resident stream "
+                                "through a 256-ms HBM ring (run = %d ms, the producer refills the ring behind the loop; one "
+                                "k_track_run launch, %d CTAs); host buffers in, per-ms sums + nav bits + records out"
+                                % (n_many, N_MS, n_many),
+                        "value": n_many * ARMS * MS_SAMPLES * N_MS / (many_ms * 1e-3), "unit": "arm-samples/s",
+                        "ms_per_s_of_signal": many_ms * 1e3 / N_MS, "times_real_time": N_MS / many_ms,
+                        "input_msps_sustained": MS_SAMPLES * N_MS / (many_ms * 1e-3) / 1e6,
+                        "target": "163.68 Msps (10x real time)",
+                        "channel_ms_on_device": int(many_dev), "channel_ms_on_host_path": int(many_host),
+                        "cpu_baseline": cfg5_cpu,
+                        "vs_cpu_baseline": None if not cfg5_cpu else
+                        n_many * ARMS * MS_SAMPLES * N_MS / (many_ms * 1e-3) / cfg5_cpu["value"]},
             "closed_loop": {"device_loop_kernel_ms": loop_kernel_ms, "host_loop_ms": host_loop_ms,
                             "upload_then_run_ms": upload_then_run_ms,
                             "host_loop_what": "same second with the loop filters on the host: one GPU round trip per ms",

@@ -768,7 +768,7 @@ LC_FN int lc_iabs(int v) { return v < 0 ? -v : v; }
 /* nav_data.c:145-218: decide whether the single sign flip seen at slot position 2 really happened
  * between samples 0/1 or 1/2, from the prompt amplitudes (the circular correlator smears an edge over
  * the millisecond in which it falls). */
-LC_FN void lc_refine_edge(gps_ch_t* ch, const gpsb_aux* aux)
+LC_FN_BIG void lc_refine_edge(gps_ch_t* ch, const gpsb_aux* aux)
 {
     gps_nav_data_t* n = &ch->nav_data;
     const int16_t* v = aux->slot_ip;
@@ -877,7 +877,7 @@ LC_FN uint8_t lc_walk_index(gpsb_aux* aux, uint32_t ms)
     return (uint8_t)((ms + aux->slot_phase) & (LC_SLOT_LEN - 1u));
 }
 /* End of a slot (index 3) of a channel in GPS_TRACKING_RUN, after the nav-bit logic of that millisecond. */
-LC_FN void lc_walk_policy(const gps_ch_t* ch, gpsb_aux* aux, uint32_t ms)
+LC_FN_BIG void lc_walk_policy(const gps_ch_t* ch, gpsb_aux* aux, uint32_t ms)
 {
     const gps_nav_data_t* n = &ch->nav_data;
     if (aux->skip_len) {

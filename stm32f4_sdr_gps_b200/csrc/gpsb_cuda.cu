@@ -1120,16 +1120,35 @@ static int track_loop_launch(gpsb_ctx* c, uint32_t n_ch, void* d_channels, void*
     static const bool profile = getenv("GPSB_LOOP_PROFILE") != nullptr;     // diagnostic: per-phase clock64 ticks to stderr
     if (profile) {
         unsigned long long* d_prof = nullptr;
-        CU(cudaMalloc(&d_prof, (size_t)n_ch * 16 * sizeof(unsigned long long)));
-        CU(cudaMemsetAsync(d_prof, 0, (size_t)n_ch * 16 * sizeof(unsigned long long), c->stream));
+        const size_t prof_words = (size_t)n_ch * (16 + (size_t)kLoopWarps * 4 * 8);
+        CU(cudaMalloc(&d_prof, prof_words * sizeof(unsigned long long)));
+        CU(cudaMemsetAsync(d_prof, 0, prof_words * sizeof(unsigned long long), c->stream));
         k_track_run<true><<<n_ch, kLoopThreads, 0, c->stream>>>((gps_ch_t*)d_channels, (gpsb_aux*)d_aux, c->d_codes,
                                                                 c->d_signal, c->ring_ms, ms0, n_ms, d_iq_log, d_nav_log,
                                                                 d_results, d_prof, gate);
         int rc = check_launch(c, "k_track_run<profile>");
         unsigned long long h[16] = {};
         CU(cudaMemcpyAsync(h, d_prof, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+        static unsigned long long tl[kLoopWarps * 4 * 8];                   // time line of channel 0, milliseconds 500..503
+        CU(cudaMemcpyAsync(tl, d_prof + (size_t)n_ch * 16, sizeof tl, cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
         cudaFree(d_prof);
+        if (n_ms > 504 && getenv("GPSB_LOOP_TIMELINE")) {
+            unsigned long long t0 = ~0ull;
+            for (unsigned long long v : tl) if (v && v < t0) t0 = v;
+            fprintf(stderr, "[k_track_run time line, channel 0, ms %u..%u: clock64 - first stamp; points 0 loop top / 1 phase-2 compute / "
+                            "2 redux / 3 red issued / 4 after barrier A / 5 offsets seen (control: sums loaded) / 6 phase 1 done "
+                            "(code: offsets out, carrier: filters done) / 7 nco seen (control: done)]\n", ms0 + 500, ms0 + 503);
+            for (int k = 0; k < 4; k++)
+                for (int w = 0; w < kLoopWarps; w++) {
+                    fprintf(stderr, "  ms+%d warp %2d:", k, w);
+                    for (int p = 0; p < 8; p++) {
+                        const unsigned long long v = tl[(w * 4 + k) * 8 + p];
+                        if (v) fprintf(stderr, " %6llu", v - t0); else fprintf(stderr, "      -");
+                    }
+                    fprintf(stderr, "\n");
+                }
+        }
         const double n = n_ms ? (double)n_ms : 1.0;
         fprintf(stderr, "[k_track_run profile, channel 0, ticks per ms] workers: phase2+reduce %.0f (compute %.0f, redux %.0f, store %.0f), "
                         "A -> phase 1 done %.0f (phase 1 alone: plain warp %.0f, edge warp %.0f) | code thread %.0f | nav thread %.0f | "

@@ -196,6 +196,15 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
     long long pt[15] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     long long c0 = 0;
     const long long loop_begin = kProf ? clock64() : 0;
+    // kProf: raw clock64 stamps of four consecutive milliseconds (kTlFirst ..) per warp, eight per millisecond, behind the
+    // per-phase totals: prof[n_ch * 16 + ((chn * kLoopWarps + warp) * 4 + k) * 8 + point]
+    constexpr uint32_t kTlFirst = 500u;
+#define GPSB_TL(point)                                                                                                  \
+    do {                                                                                                                \
+        if (kProf && (threadIdx.x & 31) == 0 && m >= kTlFirst && m < kTlFirst + 4u)                                      \
+            prof[gridDim.x * 16 + ((blockIdx.x * kLoopWarps + (threadIdx.x >> 5)) * 4 + (m - kTlFirst)) * 8 + (point)] = \
+                (unsigned long long)clock64();                                                                          \
+    } while (0)
     const int tid = threadIdx.x;
     const uint32_t chn = blockIdx.x, n_ch = gridDim.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -267,10 +276,20 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
     }
     __syncthreads();
     int stop = sm.stop;
-    // Slot-phase walk (core/gpsb_loop_core.h, lc_walk_*): every control thread keeps its own copy of the channel's slot
-    // phase and of the idle gap the nav thread may have decided; the nav thread writes a decision at slot index 3, the
-    // others re-read it at slot index 2 (barriers in between), a whole slot before it takes effect.
+    // Slot-phase walk (core/gpsb_loop_core.h, lc_walk_*).  The workers know nothing of it: in a millisecond the channel
+    // leaves out they correlate as ever and nobody looks at the sums.  Each CONTROL thread keeps its own copy of the
+    // channel's slot phase and of the idle gap the nav thread may have decided; the nav thread writes a decision at slot
+    // index 3, the others re-read it at the end of their slot-index-2 work (barriers in between), a whole slot before
+    // it takes effect.  Everything the walk adds sits inside the control threads' own branches, after their chains.
     uint32_t w_phase = sm.aux.slot_phase, w_skip_ms = sm.aux.skip_ms, w_skip_len = sm.aux.skip_len;
+#define GPSB_WALK_STEP_END()                                                                     \
+    do {                                                                                         \
+        if (idle && !idle_next) w_phase = lc_walk_phase_after(ms);                               \
+        if (index == LC_SLOT_LEN - 2) {                                                          \
+            w_skip_ms = *(volatile uint32_t*)&sm.aux.skip_ms;                                    \
+            w_skip_len = *(volatile uint8_t*)&sm.aux.skip_len;                                   \
+        }                                                                                        \
+    } while (0)
     ec_partial part;
     if (stop == LC_STOP_NONE && n_ms && (plain || edge)) {  // phase 1 of millisecond 0
         const uint32_t off[3] = {sm.rq.off_e, sm.rq.off_p, sm.rq.off_l};
@@ -325,11 +344,10 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
     for (; m < n_ms && stop == LC_STOP_NONE; m++) {
         const uint32_t ms = ms0 + m;
         const uint32_t b = m & 1u;
-        const bool idle = lc_walk_idle(w_skip_ms, w_skip_len, ms);            // this channel leaves the millisecond out
-        const bool idle_next = lc_walk_idle(w_skip_ms, w_skip_len, ms + 1u);
-        const uint8_t index = idle ? (uint8_t)LC_IDLE_INDEX : (uint8_t)((ms + w_phase) & (LC_SLOT_LEN - 1u));
+        const uint8_t index = (uint8_t)((ms + w_phase) & (LC_SLOT_LEN - 1u));   // control threads only (w_phase is theirs)
         if (kProf) c0 = clock64();
         if (worker || edge_warp) {                          // phase 2: the carrier phase of each word selects its I and Q count
+            GPSB_TL(0);
             uint32_t acc[3] = {0u, 0u, 0u};
             if (plain) ec_epl_phase2(sm.rq.acc0, sm.rq.step32, w0, kLoopNw, &part, acc);
             else if (edge) {
@@ -341,10 +359,12 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
             }
             long long c1 = 0, c2 = 0;
             if (kProf) { c1 = clock64(); c1 += (long long)(acc[0] & 0u); }
+            GPSB_TL(1);
             uint32_t v[3];
 #pragma unroll
             for (int a = 0; a < 3; a++) v[a] = __reduce_add_sync(0xFFFFFFFFu, acc[a]);
             if (kProf) { c2 = clock64(); c2 += (long long)(v[0] & 0u); }
+            GPSB_TL(2);
             if (lane == 0) {
                 uint32_t* acc_s = reinterpret_cast<uint32_t*>(&sm.sums[b]);
                 atomicAdd(acc_s + 0, v[0]);
@@ -352,6 +372,7 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
                 atomicAdd(acc_s + 2, v[2]);
             }
             if (kProf && wtid == 0 && worker) { const long long c3 = clock64(); pt[0] += c3 - c0; pt[7] += c1 - c0; pt[8] += c2 - c1; pt[9] += c3 - c2; }
+            GPSB_TL(3);
         }
         if (kProf && carrier_thr) c0 = clock64();
         __syncthreads();   // A: the six sums of millisecond m are complete
@@ -359,6 +380,7 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
         // `more`: the control threads plan a successor millisecond.  The workers only ask whether a successor frame
         // exists (it has been fetched, so waiting for it and forming its phase 1 is harmless when the run is about to
         // end for lack of LATER frames) - they do not read the starvation flag, which keeps it off their path.
+        GPSB_TL(4);
         const bool next_frame = m + 1 < n_ms;
         // (each control thread reads the flag where it needs it - at the END of its chain - so that the shared-memory
         // round trip never sits in front of its arithmetic)
@@ -369,6 +391,7 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
                 mbar_wait(&sm.offs_ready, m & 1u);
                 long long c1 = 0;
                 if (kProf) c1 = clock64();
+                GPSB_TL(5);
                 if (sm.stop_at[b ^ 1u] == LC_STOP_NONE && !(kExp & 1)) {      // ordered after the code thread's write by offs_ready
                     const uint32_t off[3] = {sm.rq.off_e, sm.rq.off_p, sm.rq.off_l};
                     if (plain) ec_epl_phase1(sm.S[b ^ 1u], sm.RX[sm.rq.off_bits & 7u], off, w0, kLoopNw, &part, sm.top_lut);
@@ -376,15 +399,21 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
                 }
                 if (kProf && lane == 0) { long long c2 = clock64(); c2 += (long long)((part.C[0][0] + edge_counts) & 0u); pt[13] += c2 - c1; }
                 if (kProf && wtid == 0 && worker) pt[1] += clock64() - c0;
+                GPSB_TL(6);
                 mbar_wait(&sm.nco_ready, m & 1u);           // the NCO words of millisecond m+1: on to its phase 2
+                GPSB_TL(7);
             }
         } else if (code_thr) {
             if (kProf) c0 = clock64();
             int16_t iq[6];
             load_sums(&sm.sums[b], iq);
+            if (kProf) iq[0] += (int16_t)(clock64() & 0);
+            GPSB_TL(5);
             sm.sums[b ^ 1u] = make_uint4(0u, 0u, 0u, 0u);      // read one ms ago by everybody; filled again after the workers have seen offs_ready
             if (next_frame) consumed++;                         // the workers wait for frame m+1 this millisecond
-            if (idle) iq[0] = iq[1] = iq[2] = iq[3] = iq[4] = iq[5] = 0;   // idle gap of the walk: the sums are nobody's
+            const bool idle = lc_walk_idle(w_skip_ms, w_skip_len, ms);            // the channel leaves this millisecond out
+            const bool idle_next = lc_walk_idle(w_skip_ms, w_skip_len, ms + 1u);
+            if (idle) iq[0] = iq[1] = iq[2] = iq[3] = iq[4] = iq[5] = 0;          // ... the sums are nobody's
             const bool degenerate = !idle && lc_dll_is_degenerate(iq);   // 0/0 in the DLL: x86 and the GPU disagree on NaN bits, host finishes this ms
             if (degenerate) sm.stop_at[b ^ 1u] = LC_STOP_DLL_NAN;
             else if (idle) {
@@ -397,6 +426,7 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
             }
             mbar_arrive(&sm.offs_ready);                    // DLL done: releases the offset check and the nav thread's edge refinement
             if (kProf) pt[2] += clock64() - c0;
+            GPSB_TL(6);
             // frame buffer b (millisecond m) was consumed before this barrier: fetch millisecond m+2 into it.  A frame
             // that is missing is fetched all the same (the ring memory is there; nothing will use the result).
             if (m + 2 < n_ms) {
@@ -420,21 +450,32 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
                 r.reserved = 0;
                 results[chn] = r;
             }
+            GPSB_TL(7);
+            GPSB_WALK_STEP_END();
         } else if (carrier_thr) {
             if (kProf) { const long long c1 = clock64(); pt[6] += c1 - c0; c0 = c1; }
             int16_t iq[6];
             load_sums(&sm.sums[b], iq);
+            if (kProf) iq[2] += (int16_t)(clock64() & 0);
+            GPSB_TL(5);
+            const bool idle = lc_walk_idle(w_skip_ms, w_skip_len, ms);            // the channel leaves this millisecond out
+            const bool idle_next = lc_walk_idle(w_skip_ms, w_skip_len, ms + 1u);
             const bool live = !idle && !lc_dll_is_degenerate(iq);
-            if (live && !(kExp & 2)) {
+            if (live) {
                 // period_sync_ok_flag is written by the nav thread at slot index 3 and read here at slot index 0
-                lc_pll_update(&car, sm.ch.nav_data.period_sync_ok_flag, index, iq[2], iq[3]);
-                lc_fll_update(&car, &sm.aux, found_freq_offset_hz, index, iq[2], iq[3], &angle_cache);
+                if (!(kExp & 2)) {
+                    lc_pll_update(&car, sm.ch.nav_data.period_sync_ok_flag, index, iq[2], iq[3]);
+                    lc_fll_update(&car, &sm.aux, found_freq_offset_hz, index, iq[2], iq[3], &angle_cache);
+                }
             }
             // no plan for a millisecond the channel leaves out: the last millisecond of the gap plans the one behind it
             // (now - prev_track_timestamp = gap + 1: lc_plan_carrier catches the NCO up, tracking.c:102-113)
+            if (kProf) car.if_freq_accum += (uint32_t)(clock64() & 0);
+            GPSB_TL(6);
             if ((live || idle) && next_frame && !idle_next && !(kStream && *(volatile int*)&sm.starved[b]))
                 lc_plan_carrier(&car, prn, ms + 1, ms + 1, &sm.rq);
-            if (next_frame) mbar_arrive(&sm.nco_ready);     // always: the workers wait for it whether or not a plan was made
+            if (next_frame) mbar_arrive(&sm.nco_ready);
+            GPSB_TL(7);     // always: the workers wait for it whether or not a plan was made
             // Off the serial path: at slot index 1 the FLL needs the angle of THIS prompt sample as its "before" value;
             // evaluate it now, while the workers are busy, instead of next to the new angle in the next millisecond.
             if (index == 0 && live) {
@@ -444,11 +485,14 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
                 angle_cache.valid = 1;
             }
             if (kProf) { const long long d = clock64() - c0; pt[3] += d; if (index == 0) { pt[10] += d; pt[11] += (iq[2] > 0); } }
+            GPSB_WALK_STEP_END();
         } else if (nav_thr) {                               // nav bits and SNR of this millisecond (nav_data.c:46-453, tracking.c:154-169)
             if (kProf) c0 = clock64();
             int16_t iq[6];
             load_sums(&sm.sums[b], iq);
             int8_t bit = -1;
+            const bool idle = lc_walk_idle(w_skip_ms, w_skip_len, ms);            // the channel leaves this millisecond out
+            const bool idle_next = lc_walk_idle(w_skip_ms, w_skip_len, ms + 1u);
             if (!idle && !lc_dll_is_degenerate(iq)) {
                 const int refine = lc_nav_new_code(&sm.ch, &sm.aux, index, iq[2], ms);
                 bit = sm.aux.last_nav_bit;
@@ -465,11 +509,8 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
             }
             if (nav_log) nav_log[(size_t)m * n_ch + chn] = bit;
             if (kProf) pt[4] += clock64() - c0;
-        }
-        if (idle && !idle_next) w_phase = lc_walk_phase_after(ms);
-        if (index == LC_SLOT_LEN - 2 && !worker) {          // a decision of the previous slot's end (barriers in between)
-            w_skip_ms = *(volatile uint32_t*)&sm.aux.skip_ms;
-            w_skip_len = *(volatile uint8_t*)&sm.aux.skip_len;
+            GPSB_TL(7);
+            GPSB_WALK_STEP_END();
         }
     }
     __syncthreads();                                        // the last millisecond's control work is done

@@ -101,6 +101,54 @@ def synthesize(scene: Scene, chunk_ms: int = 50) -> np.ndarray:
     return out
 
 
+def _block(args):
+    sats, m0, m1, seed = args
+    rng = np.random.default_rng([seed, m0])
+    t = np.arange(m0 * MS_SAMPLES, m1 * MS_SAMPLES, dtype=np.float64) / FS_HZ
+    acc = rng.standard_normal(t.size, dtype=np.float32)
+    for s in sats:
+        chips = np.concatenate([ca_code(s.prn), ca_code(s.prn)[:1]]).astype(np.float32) * 2 - 1
+        data = np.asarray(s.nav_bits, np.float32) * 2 - 1
+        amp = np.float32(np.sqrt(4.0 * 10.0 ** (s.cn0_dbhz / 10.0) / FS_HZ))
+        code_rate = CHIP_RATE_HZ * (1.0 + s.doppler_hz / L1_HZ)
+        chip_pos = (t - s.code_phase_samples / FS_HZ) * code_rate
+        epoch = np.floor(chip_pos * (1.0 / 1023.0))
+        chip = (chip_pos - epoch * 1023.0).astype(np.int32)                 # 0..1023 (1023 only by rounding: chip 0 again)
+        bit = np.floor((epoch - s.nav_bit_offset_ms) * 0.05) + 1.0
+        np.clip(bit, 0, data.size - 1, out=bit)
+        carrier = np.cos((2.0 * np.pi * (IF_HZ + s.doppler_hz)) * t + s.carrier_phase_rad).astype(np.float32)
+        carrier *= chips[chip]
+        carrier *= data[bit.astype(np.int32)]
+        carrier *= amp
+        acc += carrier
+    return m0, np.packbits((acc < 0).reshape(m1 - m0, MS_SAMPLES), axis=1, bitorder="little")
+
+
+def synthesize_blocks(sats, n_ms, seed, block_ms=50, workers=None):
+    """The signal model of synthesize() (1-bit samples of code x data x carrier in white
+    noise, packed LSB first) for recordings of tens of seconds: independent 50-ms blocks (noise seeded per block) on a
+    thread per core.  Returns (n_ms, 2046) uint8; the result does not depend on the number of workers."""
+    import os
+    from multiprocessing.pool import ThreadPool
+    for s in sats:                                              # data bits of a satellite that brings none: seeded per PRN
+        if s.nav_bits is None:
+            s.nav_bits = np.random.default_rng([seed, 1000 + s.prn]).integers(0, 2, n_ms // 20 + 3, dtype=np.uint8)
+    jobs = [(sats, m0, min(n_ms, m0 + block_ms), seed) for m0 in range(0, n_ms, block_ms)]
+    out = np.empty((n_ms, MS_SAMPLES // 8), np.uint8)
+    workers = workers or max(1, min(32, (os.cpu_count() or 2) - 1, len(jobs)))
+    if workers == 1:
+        results = map(_block, jobs)
+    else:
+        pool = ThreadPool(workers)                              # numpy releases the GIL inside the array operations
+        results = pool.imap_unordered(_block, jobs)
+    for m0, block in results:
+        out[m0:m0 + block.shape[0]] = block
+    if workers > 1:
+        pool.close()
+        pool.join()
+    return out
+
+
 def iq2_from_packed(packed: np.ndarray, seed: int = 7) -> np.ndarray:
     """Expand a packed recording to the MAX2769-native 2-bit I / 2-bit Q container, one byte per sample
     (bit0 I sign, bit1 I magnitude, bit2 Q sign, bit3 Q magnitude).  Only the I sign carries the signal

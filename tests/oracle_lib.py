@@ -17,6 +17,28 @@ REPO = Path(__file__).resolve().parent.parent
 ORACLE_DIR = REPO / "oracle"
 ORACLE_SO = ORACLE_DIR / "liboracle.so"
 REF_SO = ORACLE_DIR / "_ref" / "libgpsref.so"
+REF_O3 = {"x86-64-v4": ORACLE_DIR / "_ref" / "libgpsref_o3v4.so", "x86-64-v3": ORACLE_DIR / "_ref" / "libgpsref_o3v3.so"}
+# CPU flags (as /proc/cpuinfo spells them) each x86-64 micro-architecture level adds over the one below
+_LEVEL_FLAGS = {"x86-64-v3": ("avx", "avx2", "bmi1", "bmi2", "f16c", "fma", "abm", "movbe", "xsave"),
+                "x86-64-v4": ("avx512f", "avx512bw", "avx512cd", "avx512dq", "avx512vl")}
+
+
+def best_o3_variant():
+    """(march level, path) of the -O3 build of the reference this machine's CPU can run, or (None, None)."""
+    try:
+        flags = set()
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("flags"):
+                flags = set(line.split(":", 1)[1].split())
+                break
+    except OSError:
+        return None, None
+    v3 = all(f in flags for f in _LEVEL_FLAGS["x86-64-v3"])
+    v4 = v3 and all(f in flags for f in _LEVEL_FLAGS["x86-64-v4"])
+    for level, ok in (("x86-64-v4", v4), ("x86-64-v3", v3)):
+        if ok and REF_O3[level].exists():
+            return level, REF_O3[level]
+    return None, None
 
 sys.path.insert(0, str(REPO))
 
@@ -29,7 +51,8 @@ def _p(a: np.ndarray):
 
 
 def ensure_built() -> None:
-    if not ORACLE_SO.exists() or (not REF_SO.exists() and Path("/root/reference").exists()):
+    if not ORACLE_SO.exists() or (Path("/root/reference").exists() and
+                                  not all(p.exists() for p in (REF_SO, *REF_O3.values()))):
         subprocess.run(["make", "-C", str(ORACLE_DIR), "all"], check=True, capture_output=True)
 
 
@@ -171,11 +194,12 @@ class Oracle:
 class Reference:
     """The compiled, unmodified reference (oracle/_ref/libgpsref.so)."""
 
-    def __init__(self):
+    def __init__(self, so_path=None):
         ensure_built()
-        if not REF_SO.exists():
-            raise FileNotFoundError(str(REF_SO))
-        self.lib = lib = C.CDLL(str(REF_SO))
+        so_path = Path(so_path) if so_path else REF_SO
+        if not so_path.exists():
+            raise FileNotFoundError(str(so_path))
+        self.lib = lib = C.CDLL(str(so_path))
         vp, u32, i32, f32, u16 = C.c_void_p, C.c_uint32, C.c_int32, C.c_float, C.c_uint16
         lib.gps_fill_summ_table()
         lib.ref_set_packet_cnt.argtypes = [u32]
