@@ -281,6 +281,34 @@ int gpsb_sweep_dev(gpsb_ctx* ctx, const uint32_t* d_sv_slots, uint32_t n_sv, con
                    uint32_t n_bins, uint32_t ms0, uint32_t n_ms, uint32_t off_bits,
                    gpsb_search_res* d_res);
 
+/* ---------------------------------------------------------------- multi-GPU: sharded sweep + all-gather ----
+ * One process and one context per GPU.  The cells of a sweep are independent until the host vote (PM/GPS/acquisition.c:
+ * 280-297 has no cross-cell data flow), so the (bin, ms) cell groups are dealt round-robin over the ranks - every rank
+ * keeps whole 8-satellite tiles of the dp4a search - and the {max, phase, avg} triples are exchanged ONCE per sweep with
+ * ncclAllGather over NVLink / NVSwitch, straight out of device memory on the context stream (no host bounce), so that
+ * every rank holds the whole grid and can run the reference's votes.  Tracking needs no collective: channels are
+ * independent (PM/GPS/gps_misc.h:184).  NCCL is bound at run time (dlopen of libnccl.so.2; a copy already loaded into
+ * the process, e.g. torch's, is reused); a single-GPU user needs none.
+ *
+ *   gpsb_comm_unique_id   rank 0 makes the 128-byte rendezvous id; the caller hands it to every rank by any means
+ *                         (torch.distributed broadcast, MPI, a file)
+ *   gpsb_comm_init        ncclCommInitRank on the context's device; collective over all ranks
+ *   gpsb_sweep_gather     gpsb_sweep, sharded and gathered: collective, every rank passes the same arguments and
+ *                         receives the whole grid res[(sv*n_bins + b)*n_ms + m]; without a communicator (size 1)
+ *                         it is gpsb_sweep
+ *   gpsb_sweep_gather_dev the same enqueued on the context stream without synchronising; *d_grid = the grid in
+ *                         device memory owned by the context (valid until the next call) */
+typedef struct gpsb_nccl_id { char bytes[128]; } gpsb_nccl_id;
+int gpsb_comm_unique_id(gpsb_nccl_id* out);
+int gpsb_comm_init(gpsb_ctx* ctx, int rank, int n_ranks, const gpsb_nccl_id* id);
+int gpsb_comm_destroy(gpsb_ctx* ctx);
+int gpsb_comm_rank(const gpsb_ctx* ctx);
+int gpsb_comm_size(const gpsb_ctx* ctx);
+int gpsb_sweep_gather(gpsb_ctx* ctx, const uint32_t* sv_slots, uint32_t n_sv, const uint32_t* step32,
+                      uint32_t n_bins, uint32_t ms0, uint32_t n_ms, uint32_t off_bits, gpsb_search_res* res);
+int gpsb_sweep_gather_dev(gpsb_ctx* ctx, const uint32_t* d_sv_slots, uint32_t n_sv, const uint32_t* d_step32,
+                          uint32_t n_bins, uint32_t ms0, uint32_t n_ms, uint32_t off_bits, gpsb_search_res** d_grid);
+
 /* ---------------------------------------------------------------- level 0: the reference primitives
  * Same arithmetic and argument meaning as PM/GPS/gps_misc.h:198-216 on caller-owned HOST buffers
  * (each call round-trips through the device; meant for parity tests and for piecewise migration).

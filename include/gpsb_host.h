@@ -390,6 +390,43 @@ int gpsb_rx_acquire_ms(gpsb_rx* rx, uint32_t ms);
 int gpsb_rx_cold_sweep(gpsb_rx* rx, int32_t first_bin_hz, int32_t bin_step_hz, uint32_t n_bins,
                        uint32_t ms0, uint32_t n_ms, uint8_t* votes, uint16_t* phases);
 
+/* Cold start of every channel, any number of satellites - the acquisition half of gps_master_handling
+ * (PM/GPS/gps_master.c:68-129) without its one-channel-at-a-time Doppler search, which never ends on a satellite that is
+ * not in the sky (PM/GPS/acquisition.c:306-310):
+ *   1. Doppler: gpsb_rx_cold_sweep over snapshots ms0 .. ms0+sweep_ms-1 for the channels in GPS_ACQ_NEED_FREQ_SEARCH;
+ *      channels it leaves undecided get up to `sweeps` sweeps in all, each on the next sweep_ms snapshots, as the
+ *      reference's search does when it wraps round (acquisition.c:305-310);
+ *   2. code-phase rounds 1 and 2 (acquisition.c:89-104, 150-170, 196-275) from the next snapshot (ms_code0) on for every channel
+ *      whose vote passed (the others are not served any more), every such channel on EVERY snapshot, until none is left in rounds 1 / 2 or round_timeout_ms
+ *      snapshots have gone by (a Doppler vote that fired on noise does not get through the rounds; it is left behind);
+ *   3. round 3 (acquisition.c:106-130) started together at the next snapshot for the channels that finished round 2
+ *      (gps_master.c:113-118), until none is left in it or the time-out;
+ *   4. channels in GPS_ACQ_DONE get GPS_NEED_PRE_TRACK (gps_master.c:121-129): gpsb_rx_track_run takes them from there.
+ * The cells of up to window_ms coming snapshots are computed ahead in one launch (they are independent until each
+ * channel's vote) and consumed in order.  Several GPUs: with a communicator on the context (gpsb_comm_init, include/
+ * gpsb.h) the sweep's cell groups are sharded over the ranks and all-gathered, every rank runs the same votes, and
+ * serve_rank / serve_world deal the satellites found round-robin over the ranks for everything that follows (no further
+ * exchange: channels are independent).  Per channel the result equals the unmodified reference called on the same
+ * snapshots - acquisition_start_channel, its 10 cells per bin and sweep, acquisition_start_code_search_channel at ms_code0,
+ * acquisition_process_channel for ms_code0 .. ms_code12_last, acquisition_start_code_search3_channel at ms_code3_first,
+ * acquisition_process_channel for ms_code3_first .. ms_last - which is how the tests check it.  All frames
+ * ms0 .. ms_last must be in the ring.  opts == NULL or zero fields: the reference's Doppler grid (-7000 .. +7000 Hz in
+ * steps of 500, PM/config.h:41-44), 10 snapshots per bin, time-out 400, 16 snapshots ahead. */
+typedef struct gpsb_cold_start_opts {
+    int32_t  first_bin_hz, bin_step_hz;
+    uint32_t n_bins, sweep_ms, round_timeout_ms, window_ms;
+    uint32_t sweeps;                    /* Doppler sweeps at most (each on the next sweep_ms snapshots); 0 = 1 */
+    uint32_t serve_rank, serve_world;   /* multi-GPU: after the sweep this process goes on with channels i % serve_world ==
+                                           serve_rank only (0, 0 = all); the sweep itself is sharded by gpsb_sweep_gather
+                                           when the context has a communicator */
+} gpsb_cold_start_opts;
+typedef struct gpsb_cold_start_report {
+    uint32_t ms_sweep0, ms_code0, ms_code12_last, ms_code3_first, ms_last, ms_next;   /* the snapshot schedule */
+    uint32_t n_sweeps, n_searched, n_doppler_found, n_served, n_acquired;
+    uint32_t launches;                                                                 /* kernel launches spent */
+} gpsb_cold_start_report;
+int gpsb_rx_cold_start(gpsb_rx* rx, uint32_t ms0, const gpsb_cold_start_opts* opts, gpsb_cold_start_report* rep);
+
 /* ------------------------------------------------------------------------------------------------
  * (3) Split-phase form of the two per-channel steps.  PLAN performs the state transitions of
  * acquisition_process_channel() / gps_tracking_process() up to the point where a correlation is needed

@@ -368,9 +368,10 @@ void ref_track_run(gps_ch_t* ch, const uint8_t* signal, uint32_t ms_first, uint3
  * reference.  A channel is called with slot index (ms + slot_phase) % 4; inside an idle gap it is called with the
  * reference's dummy index 0xFF (main.c:146-147), which tracking.c:96 ignores.  After a complete slot of a channel that
  * has no refined bit edge (nav_data.accurate_swap_ok == 0):
- *   an on-grid edge has shown at slot position 2 since the last gap       -> nothing;
- *   three or more on-grid edges since then, all at positions 3 or 1      -> idle 1 ms (most at 3, ties too) or 3 ms;
- *   no on-grid edge seen for period_ms (default 400) at this slot phase   -> idle 2 ms;
+ *   three or more on-grid edges since the last gap at slot positions 3 or 1, and fewer than a fifth of all on-grid
+ *   edges at position 2                                                   -> idle 1 ms (most at 3, ties too) or 3 ms;
+ *   no on-grid edge at all for period_ms (default 400) at this slot phase -> idle 2 ms;
+ *   the first slot end only starts that clock;
  * the gap begins 5 ms after the slot end at which it was decided, and the millisecond behind a gap is slot index 0.
  * Edge positions are observed from outside: sign of the prompt sum XOR the polarity flag before the call, one flip in
  * the slot, "on grid" = (edge - old_swap_time before the call) % 20 in {0, 1, 19} (nav_data.c:87-113).
@@ -380,6 +381,7 @@ typedef struct ref_walk {
     uint32_t enable, period_ms;
     uint32_t slot_phase, gap_first, gap_len, phase_since, gaps_taken, edge_pos;
     uint32_t edges_at[4];             /* on-grid edges seen per slot position since the last gap was decided */
+    uint32_t armed;
     uint32_t slot_first_ms;
     uint8_t sign[4];
     int16_t ip[4];
@@ -463,11 +465,14 @@ void ref_track_run_walk(gps_ch_t* ch, const uint8_t* signal, uint32_t ms_first, 
         }
         if (!w->enable || ch->nav_data.accurate_swap_ok) continue;
         uint32_t gap = 0;
-        if (w->edges_at[2] == 0) {
-            if (w->edges_at[1] + w->edges_at[3] >= 3) gap = (w->edges_at[3] >= w->edges_at[1]) ? 1 : 3;
-            else if (w->edges_at[1] + w->edges_at[3] == 0 && ms - w->phase_since >= (w->period_ms ? w->period_ms : 400u))
-                gap = 2;
+        if (!w->armed) {
+            w->armed = 1;
+            w->phase_since = ms;
+            continue;
         }
+        const uint32_t side = w->edges_at[1] + w->edges_at[3];
+        if (side >= 3 && 4u * w->edges_at[2] < side) gap = (w->edges_at[3] >= w->edges_at[1]) ? 1 : 3;
+        else if (side + w->edges_at[2] == 0 && ms - w->phase_since >= (w->period_ms ? w->period_ms : 400u)) gap = 2;
         if (gap) {
             w->gap_first = ms + 5u;
             w->gap_len = gap;

@@ -116,6 +116,7 @@ typedef struct gpsb_aux {
     uint8_t  skip_len;                          /* the channel idles in [skip_ms, skip_ms + skip_len): 0 = no walk decided */
     uint8_t  last_flip_pos;                     /* observer: slot position (1..3) of the last bit edge seen on the 20-ms grid */
     uint8_t  flip_cnt[4];                       /* observer: such edges seen per slot position at this slot phase (saturating) */
+    uint8_t  walk_armed;                        /* the policy has seen this channel's first slot end */
     uint16_t walk_period_ms;                    /* patience at one slot phase without any bit edge seen (0 = LC_WALK_PERIOD_MS) */
     uint16_t walks;                             /* statistics: idle gaps taken so far */
     uint32_t skip_ms;                           /* first idle millisecond of the pending (or last) walk */
@@ -853,10 +854,12 @@ LC_FN int lc_nav_new_code(gps_ch_t* ch, gpsb_aux* aux, uint8_t index, int16_t ne
  * result equals the unmodified reference called on the same (millisecond, index) schedule - which is how the tests
  * check it (oracle/ref_shim.c: ref_track_run_walk).  Policy (this library's, evaluated at the end of a slot, from what the
  * bit synchroniser has seen at the current slot phase):
- *   - an edge on the 20-ms grid has shown at slot position 2: nothing - the synchroniser is on its way (an edge in the
- *     middle of a millisecond shows at two neighbouring positions in turn; one of them being 2 is enough);
- *   - LC_WALK_CONFIDENCE edges on the grid, all at positions 3 / 1: idle 1 / 3 ms (majority) - they then show at 2;
- *   - no edge on the grid seen for walk_period_ms at this slot phase (they fall on the slot boundary): idle 2 ms;
+ *   - at least LC_WALK_CONFIDENCE edges on the 20-ms grid at slot positions 3 / 1, and fewer than a fifth of all edges
+ *     at position 2: idle 1 / 3 ms (majority) - the edges then show at 2.  (An edge in the middle of a millisecond
+ *     shows at two neighbouring positions in turn: if one of them is 2 that is good enough and nothing happens; a lone
+ *     spurious edge at 2 while the loops pull in does not hold the channel back.)
+ *   - no edge on the grid seen for walk_period_ms at this slot phase (they fall on the slot boundary, or the loops have
+ *     not pulled in yet): idle 2 ms;
  *   - edge refined (accurate_swap_ok): nothing, for ever.
  * A walk decided at the end of a slot takes effect LC_WALK_LEAD_MS later, behind the next slot, so that the thread
  * that plans the carrier NCO of the device-resident loop knows it a whole slot ahead. */
@@ -887,10 +890,14 @@ LC_FN_BIG void lc_walk_policy(const gps_ch_t* ch, gpsb_aux* aux, uint32_t ms)
     if (!aux->walk_enable || n->accurate_swap_ok) return;
     const uint32_t patience = aux->walk_period_ms ? aux->walk_period_ms : LC_WALK_PERIOD_MS;
     uint8_t idle = 0;
-    const unsigned off_centre = (unsigned)aux->flip_cnt[1] + aux->flip_cnt[3];
-    if (aux->flip_cnt[2]) return;
-    if (off_centre >= LC_WALK_CONFIDENCE) idle = aux->flip_cnt[3] >= aux->flip_cnt[1] ? 1 : 3;
-    else if (off_centre == 0 && ms - aux->phase_since_ms >= patience) idle = 2;
+    const unsigned off_centre = (unsigned)aux->flip_cnt[1] + aux->flip_cnt[3], centre = aux->flip_cnt[2];
+    if (!aux->walk_armed) {                       /* first slot end of this channel's tracking: the clock starts here */
+        aux->walk_armed = 1;
+        aux->phase_since_ms = ms;
+        return;
+    }
+    if (off_centre >= LC_WALK_CONFIDENCE && centre * 4u < off_centre) idle = aux->flip_cnt[3] >= aux->flip_cnt[1] ? 1 : 3;
+    else if (off_centre + centre == 0 && ms - aux->phase_since_ms >= patience) idle = 2;
     if (!idle) return;
     aux->skip_ms = ms + LC_WALK_LEAD_MS;
     aux->skip_len = idle;

@@ -102,7 +102,8 @@ k_acq_dp4a(const AcqGroup* __restrict__ groups, SweepParams sp, uint32_t n_sv_to
     __shared__ AcqGroup g;
     if (tid == 0) {
         if (kSweep) {   // group_id = (bin, ms) cell group; blockIdx.y = satellite tile
-            const uint32_t m = group_id % sp.n_ms, b = group_id / sp.n_ms;
+            const uint32_t gg = sp.group0 + group_id * (sp.group_skip + 1u);
+            const uint32_t m = gg % sp.n_ms, b = gg / sp.n_ms;
             g.ms_index = sp.ms0 + m;
             g.acc0 = 0;
             g.step32 = sp.step32[b];
@@ -114,7 +115,7 @@ k_acq_dp4a(const AcqGroup* __restrict__ groups, SweepParams sp, uint32_t n_sv_to
                 g.sv_slot[v] = sp.sv_slots[v0 + v];
                 g.start[v] = 0;
                 g.stop[v] = GPSB_OFFSETS;
-                g.res_index[v] = ((v0 + v) * sp.n_bins + b) * sp.n_ms + m;
+                g.res_index[v] = sp.dense ? group_id * n_sv_total + (v0 + v) : ((v0 + v) * sp.n_bins + b) * sp.n_ms + m;
             }
         } else {
             g = groups[group_id];

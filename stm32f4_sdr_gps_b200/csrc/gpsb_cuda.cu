@@ -19,6 +19,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <dlfcn.h>
 #include <pthread.h>
 #include <new>
 
@@ -29,6 +30,10 @@ struct SweepParams {
     const uint32_t* sv_slots;
     const uint32_t* step32;
     uint32_t n_bins, ms0, n_ms, off_bits;
+    // multi-GPU sharding of the (bin, ms) cell groups: CTA group k of this launch is group group0 + k * (group_skip + 1)
+    // of the sweep; dense != 0: results go to res[k * n_sv + sv] (this rank's block of the all-gather) instead of the
+    // (sv, bin, ms) grid.  All zero = the whole sweep on one GPU.
+    uint32_t group0, group_skip, dense;
 };
 }  // namespace gpsb
 
@@ -538,6 +543,13 @@ struct gpsb_ctx {
     size_t acq_scratch_cap = 0;          // records
     void* d_iq2 = nullptr;               // staging of gpsb_stream_push_iq2
     size_t iq2_cap = 0;
+    // multi-GPU (gpsb_comm_*): one context per rank, NCCL communicator over NVLink / NVSwitch
+    void* comm = nullptr;                // ncclComm_t
+    int comm_rank = 0, comm_size = 1;
+    gpsb_search_res* d_part = nullptr;   // this rank's dense block of a sharded sweep
+    gpsb_search_res* d_all = nullptr;    // all ranks' blocks after the all-gather
+    gpsb_search_res* d_grid = nullptr;   // the whole sweep in (sv, bin, ms) order
+    size_t part_cap = 0, grid_cap = 0;   // records
     bool loop_open = false;              // between gpsb_track_loop_begin and _end (call_lock held)
     struct {
         void* channels; void* aux; gpsb_loop_result* results; int16_t* iq_log; int8_t* nav_log;
@@ -798,6 +810,10 @@ void gpsb_destroy(gpsb_ctx* c)
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     if (c->ev_reset) cudaEventDestroy(c->ev_reset);
     if (c->d_iq2) cudaFree(c->d_iq2);
+    if (c->comm) gpsb_comm_destroy(c);
+    if (c->d_part) cudaFree(c->d_part);
+    if (c->d_all) cudaFree(c->d_all);
+    if (c->d_grid) cudaFree(c->d_grid);
     if (c->d_acq_scratch) cudaFree(c->d_acq_scratch);
     if (c->d_watermark) cudaFree(c->d_watermark);
     if (c->h_wm_ring) cudaFreeHost(c->h_wm_ring);
@@ -1627,6 +1643,181 @@ int gpsb_sweep(gpsb_ctx* c, const uint32_t* sv_slots, uint32_t n_sv, const uint3
     if (rc) return rc;
     CU(cudaMemcpyAsync((uint8_t*)c->h_stage + res_off, (uint8_t*)c->d_stage + res_off, res_b,
                        cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    memcpy(res, (uint8_t*)c->h_stage + res_off, res_b);
+    return GPSB_OK;
+}
+
+/* ------------------------------------------------------------------ multi-GPU: sharded sweep + all-gather */
+// NCCL is bound at run time (dlopen): a single-GPU user of the library needs no NCCL at all.  If the process has one
+// loaded already (torch ships its own copy) that copy is used, so there is never a second NCCL in one process.
+namespace {
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, gpsb_nccl_id, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+pthread_mutex_t g_nccl_lock = PTHREAD_MUTEX_INITIALIZER;
+
+int nccl_bind()
+{
+    pthread_mutex_lock(&g_nccl_lock);
+    if (!g_nccl.lib) {
+        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);          // whatever the process already uses
+        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (h) {
+            g_nccl.GetUniqueId = (int (*)(void*))dlsym(h, "ncclGetUniqueId");
+            g_nccl.CommInitRank = (int (*)(void**, int, gpsb_nccl_id, int))dlsym(h, "ncclCommInitRank");
+            g_nccl.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
+            g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(h, "ncclAllGather");
+            g_nccl.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+            if (g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.CommDestroy && g_nccl.AllGather) g_nccl.lib = h;
+        }
+    }
+    const bool ok = g_nccl.lib != nullptr;
+    pthread_mutex_unlock(&g_nccl_lock);
+    return ok ? GPSB_OK : fail(GPSB_ERR_STATE, "NCCL (libnccl.so.2) is not available: %s", dlerror() ? dlerror() : "symbols missing");
+}
+const char* nccl_err(int rc) { return g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"; }
+
+// all[(r * n_local + k) * n_sv + v] (rank r's k-th cell group = group r + k * world) -> grid[(v * n_bins + b) * n_ms + m]
+__global__ void k_unshard(const gpsb_search_res* __restrict__ all, gpsb_search_res* __restrict__ grid, uint32_t n_sv,
+                          uint32_t n_bins, uint32_t n_ms, uint32_t world, uint32_t n_local)
+{
+    const uint32_t cells = n_sv * n_bins * n_ms;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += gridDim.x * blockDim.x) {
+        const uint32_t g = i % (n_bins * n_ms), v = i / (n_bins * n_ms);
+        grid[i] = all[((size_t)(g % world) * n_local + g / world) * n_sv + v];
+    }
+}
+}  // namespace
+
+int gpsb_comm_unique_id(gpsb_nccl_id* out)
+{
+    if (!out) return fail(GPSB_ERR_ARG, "gpsb_comm_unique_id: null argument");
+    int rc = nccl_bind();
+    if (rc) return rc;
+    const int n = g_nccl.GetUniqueId(out);
+    return n == 0 ? GPSB_OK : fail(GPSB_ERR_CUDA, "ncclGetUniqueId: %s", nccl_err(n));
+}
+
+int gpsb_comm_init(gpsb_ctx* c, int rank, int n_ranks, const gpsb_nccl_id* id)
+{
+    if (!c || !id || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(GPSB_ERR_ARG, "gpsb_comm_init: bad argument");
+    if (c->comm) return fail(GPSB_ERR_STATE, "the context already has a communicator");
+    int rc = nccl_bind();
+    if (rc) return rc;
+    CU(cudaSetDevice(c->device));
+    void* comm = nullptr;
+    const int n = g_nccl.CommInitRank(&comm, n_ranks, *id, rank);
+    if (n != 0) return fail(GPSB_ERR_CUDA, "ncclCommInitRank: %s", nccl_err(n));
+    c->comm = comm;
+    c->comm_rank = rank;
+    c->comm_size = n_ranks;
+    return GPSB_OK;
+}
+
+int gpsb_comm_destroy(gpsb_ctx* c)
+{
+    if (!c) return fail(GPSB_ERR_ARG, "null context");
+    if (c->comm) {
+        cudaSetDevice(c->device);
+        cudaStreamSynchronize(c->stream);
+        g_nccl.CommDestroy(c->comm);
+        c->comm = nullptr;
+    }
+    c->comm_rank = 0;
+    c->comm_size = 1;
+    return GPSB_OK;
+}
+
+int gpsb_comm_rank(const gpsb_ctx* c) { return c ? c->comm_rank : 0; }
+int gpsb_comm_size(const gpsb_ctx* c) { return c ? c->comm_size : 1; }
+
+// Enqueue on the context stream: this rank's share of the (bin, ms) cell groups (group g belongs to rank g % size, so
+// every rank keeps whole 8-satellite tiles), ncclAllGather of the dense blocks straight out of device memory, and the
+// permutation into the (sv, bin, ms) grid.  No host copy anywhere; *d_grid_out = the grid in this context's memory.
+int gpsb_sweep_gather_dev(gpsb_ctx* c, const uint32_t* d_sv_slots, uint32_t n_sv, const uint32_t* d_step32, uint32_t n_bins,
+                          uint32_t ms0, uint32_t n_ms, uint32_t off_bits, gpsb_search_res** d_grid_out)
+{
+    if (!c || !d_sv_slots || !d_step32) return fail(GPSB_ERR_ARG, "gpsb_sweep_gather_dev: null argument");
+    if (off_bits > 15) return fail(GPSB_ERR_ARG, "off_bits %u > 15", off_bits);
+    if (c->sweep_method == GPSB_SWEEP_DIRECT) return fail(GPSB_ERR_STATE, "the sharded sweep runs the dp4a search only");
+    const uint32_t world = (uint32_t)c->comm_size, rank = (uint32_t)c->comm_rank;
+    if (world > 1 && !c->comm) return fail(GPSB_ERR_STATE, "no communicator: call gpsb_comm_init first");
+    const uint32_t groups = n_bins * n_ms;
+    const uint64_t cells = (uint64_t)n_sv * groups;
+    if (cells == 0) return GPSB_OK;
+    if (cells > 0x7FFFFFFFull) return fail(GPSB_ERR_ARG, "sweep of %llu cells is too large", (unsigned long long)cells);
+    CU(cudaSetDevice(c->device));
+    const uint32_t n_local = (groups + world - 1) / world;                 // block size, equal on every rank (padded)
+    const uint32_t mine = groups > rank ? (groups - rank + world - 1) / world : 0;
+    const size_t part = (size_t)n_local * n_sv;
+    if (part > c->part_cap || cells > c->grid_cap) {
+        CU(cudaStreamSynchronize(c->stream));
+        if (c->d_part) cudaFree(c->d_part);
+        if (c->d_all) cudaFree(c->d_all);
+        if (c->d_grid) cudaFree(c->d_grid);
+        c->d_part = c->d_all = c->d_grid = nullptr;
+        c->part_cap = c->grid_cap = 0;
+        CU(cudaMalloc(&c->d_part, part * sizeof(gpsb_search_res)));
+        CU(cudaMalloc(&c->d_all, part * world * sizeof(gpsb_search_res)));
+        CU(cudaMalloc(&c->d_grid, (size_t)cells * sizeof(gpsb_search_res)));
+        CU(cudaMemsetAsync(c->d_part, 0, part * sizeof(gpsb_search_res), c->stream));
+        c->part_cap = part;
+        c->grid_cap = (size_t)cells;
+    }
+    if (mine) {
+        SweepParams sp = {d_sv_slots, d_step32, n_bins, ms0, n_ms, off_bits, rank, world - 1u, 1u};
+        int rc;
+        if (n_sv > 4) rc = launch_acq<8, true>(c, dim3(mine, (n_sv + 7) / 8), nullptr, sp, n_sv, c->d_part, part);
+        else if (n_sv > 1) rc = launch_acq<4, true>(c, dim3(mine, 1), nullptr, sp, n_sv, c->d_part, part);
+        else rc = launch_acq<1, true>(c, dim3(mine, 1), nullptr, sp, n_sv, c->d_part, part);
+        if (rc) return rc;
+    }
+    const gpsb_search_res* all = c->d_part;
+    if (world > 1) {
+        const int n = g_nccl.AllGather(c->d_part, c->d_all, part * sizeof(gpsb_search_res), /* ncclChar */ 0, c->comm, c->stream);
+        if (n != 0) return fail(GPSB_ERR_CUDA, "ncclAllGather: %s", nccl_err(n));
+        all = c->d_all;
+    }
+    k_unshard<<<(unsigned)((cells + 255) / 256), 256, 0, c->stream>>>(all, c->d_grid, n_sv, n_bins, n_ms, world, n_local);
+    int rc = check_launch(c, "k_unshard");
+    if (rc) return rc;
+    if (d_grid_out) *d_grid_out = c->d_grid;
+    return GPSB_OK;
+}
+
+int gpsb_sweep_gather(gpsb_ctx* c, const uint32_t* sv_slots, uint32_t n_sv, const uint32_t* step32, uint32_t n_bins,
+                      uint32_t ms0, uint32_t n_ms, uint32_t off_bits, gpsb_search_res* res)
+{
+    if (!c || !sv_slots || !step32 || !res) return fail(GPSB_ERR_ARG, "gpsb_sweep_gather: null argument");
+    for (uint32_t i = 0; i < n_sv; i++) {
+        if (sv_slots[i] >= c->max_sv) return fail(GPSB_ERR_ARG, "sv_slots[%u] = %u out of range", i, sv_slots[i]);
+        if (!c->code_set[sv_slots[i]]) return fail(GPSB_ERR_STATE, "no code set for slot %u", sv_slots[i]);
+    }
+    const size_t cells = (size_t)n_sv * n_bins * n_ms;
+    if (cells == 0) return GPSB_OK;
+    CU(cudaSetDevice(c->device));
+    const size_t sv_b = (size_t)n_sv * 4, st_b = (size_t)n_bins * 4;
+    const size_t st_off = (sv_b + 255) & ~(size_t)255;
+    const size_t res_off = (st_off + st_b + 255) & ~(size_t)255;
+    const size_t res_b = cells * sizeof(gpsb_search_res);
+    int rc = ensure_stage(c, res_off + res_b);
+    if (rc) return rc;
+    memcpy(c->h_stage, sv_slots, sv_b);
+    memcpy((uint8_t*)c->h_stage + st_off, step32, st_b);
+    CU(cudaMemcpyAsync(c->d_stage, c->h_stage, st_off + st_b, cudaMemcpyHostToDevice, c->stream));
+    gpsb_search_res* d_grid = nullptr;
+    rc = gpsb_sweep_gather_dev(c, (const uint32_t*)c->d_stage, n_sv, (const uint32_t*)((uint8_t*)c->d_stage + st_off), n_bins,
+                               ms0, n_ms, off_bits, &d_grid);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync((uint8_t*)c->h_stage + res_off, d_grid, res_b, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     memcpy(res, (uint8_t*)c->h_stage + res_off, res_b);
     return GPSB_OK;

@@ -94,6 +94,13 @@ def load_library(path: Path | None = None) -> C.CDLL:
         "gpsb_set_epl_batch_min": (i32, [vp, u32]),
         "gpsb_search_dev": (i32, [vp, u32, vp, vp]),
         "gpsb_sweep_dev": (i32, [vp, vp, u32, vp, u32, u32, u32, u32, vp]),
+        "gpsb_comm_unique_id": (i32, [vp]),
+        "gpsb_comm_init": (i32, [vp, i32, i32, vp]),
+        "gpsb_comm_destroy": (i32, [vp]),
+        "gpsb_comm_rank": (i32, [vp]),
+        "gpsb_comm_size": (i32, [vp]),
+        "gpsb_sweep_gather": (i32, [vp, vp, u32, vp, u32, u32, u32, u32, vp]),
+        "gpsb_sweep_gather_dev": (i32, [vp, vp, u32, vp, u32, u32, u32, u32, C.POINTER(vp)]),
         "gpsb_track_loop": (i32, [vp, u32, vp, u32, vp, u32, u32, u32, vp, vp, vp]),
         "gpsb_track_loop_dev": (i32, [vp, u32, vp, vp, u32, u32, vp, vp, vp]),
         "gpsb_track_loop_dev_ex": (i32, [vp, u32, vp, vp, u32, u32, vp, vp, vp, u32]),
@@ -288,6 +295,51 @@ class Engine:
                   off_bits: int, d_res: int) -> None:
         self._check(self.lib.gpsb_sweep_dev(self._ctx, C.c_void_p(d_sv), n_sv, C.c_void_p(d_step32), n_bins,
                                             ms0, n_ms, off_bits, C.c_void_p(d_res)))
+
+    # ------------------------------------------------------------------ multi-GPU
+    def comm_unique_id(self) -> bytes:
+        """gpsb_comm_unique_id: the 128-byte NCCL rendezvous id (made on rank 0, handed to every rank by the caller)."""
+        buf = C.create_string_buffer(128)
+        self._check(self.lib.gpsb_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, rank: int, n_ranks: int, unique_id: bytes) -> None:
+        """gpsb_comm_init: NCCL communicator over all ranks' contexts (collective)."""
+        assert len(unique_id) == 128
+        self._check(self.lib.gpsb_comm_init(self._ctx, rank, n_ranks, C.create_string_buffer(unique_id, 128)))
+
+    def comm_init_torch(self) -> None:
+        """The same with the id handed round by torch.distributed (must be initialised; any backend)."""
+        import torch
+        import torch.distributed as dist
+        rank, world = dist.get_rank(), dist.get_world_size()
+        box = [self.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        self.comm_init(rank, world, box[0])
+
+    def comm_destroy(self) -> None:
+        self._check(self.lib.gpsb_comm_destroy(self._ctx))
+
+    @property
+    def comm_size(self) -> int:
+        return int(self.lib.gpsb_comm_size(self._ctx))
+
+    def sweep_gather(self, sv_slots, step32, ms0: int, n_ms: int, off_bits: int = 0) -> np.ndarray:
+        """gpsb_sweep_gather: the sweep sharded over the communicator's ranks and all-gathered; every rank gets the whole
+        grid, shape (n_sv, n_bins, n_ms) of SEARCH_RES."""
+        sv = np.ascontiguousarray(sv_slots, dtype=np.uint32)
+        st = np.ascontiguousarray(step32, dtype=np.uint32)
+        res = np.zeros((sv.size, st.size, n_ms), SEARCH_RES)
+        self._check(self.lib.gpsb_sweep_gather(self._ctx, sv.ctypes.data, sv.size, st.ctypes.data, st.size, ms0, n_ms,
+                                               off_bits, res.ctypes.data))
+        return res
+
+    def sweep_gather_dev(self, d_sv: int, n_sv: int, d_step32: int, n_bins: int, ms0: int, n_ms: int, off_bits: int = 0) -> int:
+        """gpsb_sweep_gather_dev: only enqueued; returns the device address of the gathered (sv, bin, ms) grid."""
+        out = C.c_void_p()
+        self._check(self.lib.gpsb_sweep_gather_dev(self._ctx, C.c_void_p(d_sv), n_sv, C.c_void_p(d_step32), n_bins, ms0,
+                                                   n_ms, off_bits, C.byref(out)))
+        return int(out.value or 0)
 
     # ------------------------------------------------------------------ level 0
     def track_loop_dev(self, n_ch: int, d_channels: int, d_aux: int, ms0: int, n_ms: int, d_iq_log: int,

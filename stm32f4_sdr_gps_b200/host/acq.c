@@ -84,6 +84,13 @@ void acquisition_start_code_search3_channel(gps_ch_t* channel)
     begin_narrow_round(channel, &g_shared_aux, CODE_SEARCH3_WIDTH, GPS_ACQ_CODE_PHASE_SEARCH3);
 }
 
+/* the same two starts on a channel's own vote buffers (batched receiver) */
+void hx_acq_start_code_search3(gps_ch_t* ch, gpsb_aux* aux)
+{
+    if (ch->acq_data.state != GPS_ACQ_CODE_PHASE_SEARCH2_DONE) return;
+    begin_narrow_round(ch, aux, CODE_SEARCH3_WIDTH, GPS_ACQ_CODE_PHASE_SEARCH3);
+}
+
 uint32_t* acquisition_get_hist(void) { return g_shared_aux.freq_hist; }
 
 /* ---------------------------------------------------------------------------- plan */

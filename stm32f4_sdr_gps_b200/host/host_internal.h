@@ -28,6 +28,7 @@ uint32_t hx_nco_step32(float freq_hz);
 /* acquisition (acq.c) */
 void hx_acq_plan(gps_ch_t* ch, gpsb_aux* aux, uint32_t frame_ms, gpsb_plan* plan);
 void hx_acq_finish(gps_ch_t* ch, gpsb_aux* aux, const gpsb_plan* plan, const gpsb_search_res* res);
+void hx_acq_start_code_search3(gps_ch_t* ch, gpsb_aux* aux);
 uint8_t hx_chain_vote(uint16_t* phases, uint8_t n, uint16_t* chain_phase);
 void hx_freq_hist_decide(gps_ch_t* ch, const uint32_t* hist, uint32_t n_bins, int32_t first_bin_hz, int32_t step_hz);
 

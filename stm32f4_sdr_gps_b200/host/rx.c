@@ -270,6 +270,8 @@ static int run_channel_span(gpsb_rx* rx, uint32_t i, uint32_t ms0, uint32_t ms, 
                             int8_t* nav_log)
 {
     const uint32_t n_ch = rx->n_ch;
+    /* a channel that has not been handed to tracking (still in acquisition, or given up) has nothing to do here */
+    if (rx->ch[i].tracking_data.state == GPS_TRACKNG_IDLE) return GPSB_OK;
     while (ms < end) {
         int16_t* iq_row = iq_log ? iq_log + (size_t)(ms - ms0) * n_ch * 6 : NULL;
         int8_t* nav_row = nav_log ? nav_log + (size_t)(ms - ms0) * n_ch : NULL;
@@ -351,14 +353,65 @@ static int finish_device_run(gpsb_rx* rx, uint32_t ms0, uint32_t n_ms, int16_t* 
 
 /* The whole run with the loops on the device: one k_track_run launch for every channel that is tracking, then
  * whatever is left (channels handed back early, channels still in pre-track) channel by channel. */
+/* One millisecond of every channel in lockstep on the per-millisecond path (gpsb_rx_track_ms: one launch per kind of
+ * cell for all channels), with its rows of the logs. */
+static int lockstep_ms(gpsb_rx* rx, uint32_t ms, int16_t* iq_row, int8_t* nav_row)
+{
+    for (uint32_t i = 0; i < rx->n_ch; i++) rx->aux[i].last_nav_bit = -1;
+    int rc = gpsb_rx_track_ms(rx, ms);
+    if (rc != GPSB_OK) return rc;
+    if (iq_row) {
+        memset(iq_row, 0, (size_t)rx->n_ch * 12);
+        uint32_t k = 0;
+        for (uint32_t i = 0; i < rx->n_ch; i++)
+            if (rx->plan[i].want == GPSB_WANT_EPL) memcpy(iq_row + 6u * i, rx->epl_out + 6u * k++, 12);
+    }
+    if (nav_row)
+        for (uint32_t i = 0; i < rx->n_ch; i++)
+            nav_row[i] = rx->plan[i].want == GPSB_WANT_EPL ? rx->aux[i].last_nav_bit : -1;
+    return GPSB_OK;
+}
+
+static int in_pre_track(const gps_ch_t* ch)
+{
+    return ch->tracking_data.state == GPS_NEED_PRE_TRACK || ch->tracking_data.state == GPS_PRE_TRACK_RUN;
+}
+
+#define PRE_TRACK_LOCKSTEP_MAX_MS 400u   /* a pre-track that has not settled by then goes on channel by channel */
+
 static int track_run_device(gpsb_rx* rx, uint32_t ms0, uint32_t n_ms, int16_t* iq_log, int8_t* nav_log)
 {
     const uint32_t n_ch = rx->n_ch;
+    /* Channels still in pre-track (tracking.c:398-450: 7 correlations per millisecond for >= 84 ms) are stepped TOGETHER,
+     * one launch per millisecond for all of them (and one more for the channels already tracking), until every
+     * pre-track has settled: then the device-resident loop takes all channels in one launch. */
+    uint32_t lead = 0;
+    for (;;) {
+        int pre = 0;
+        for (uint32_t i = 0; i < n_ch; i++) pre |= in_pre_track(&rx->ch[i]);
+        if (!pre || lead >= n_ms || lead >= PRE_TRACK_LOCKSTEP_MAX_MS) break;
+        int rc = lockstep_ms(rx, ms0 + lead, iq_log ? iq_log + (size_t)lead * n_ch * 6 : NULL,
+                             nav_log ? nav_log + (size_t)lead * n_ch : NULL);
+        if (rc != GPSB_OK) return rc;
+        lead++;
+    }
+    if (lead) {
+        ms0 += lead;
+        n_ms -= lead;
+        if (iq_log) iq_log += (size_t)lead * n_ch * 6;
+        if (nav_log) nav_log += (size_t)lead * n_ch;
+        if (n_ms == 0) {
+            gpsb_host_set_packet_cnt(ms0 - 1);
+            return GPSB_OK;
+        }
+    }
     uint32_t n_trk = 0;
     for (uint32_t i = 0; i < n_ch; i++) n_trk += is_tracking(&rx->ch[i]) ? 1u : 0u;
     if (iq_log && n_trk != n_ch) memset(iq_log, 0, (size_t)n_ms * n_ch * 12);
     if (nav_log && n_trk != n_ch) memset(nav_log, 0xFF, (size_t)n_ms * n_ch);
-    if (n_trk == n_ch) {
+    if (n_trk > 0) {
+        /* one launch for every channel; a channel that is not tracking is refused by the loop (LC_STOP_STATE, nothing
+         * done) and taken from there channel by channel: pre-track on the per-millisecond path, idle channels not at all */
         int rc = gpsb_track_loop(rx->ctx, n_ch, rx->ch, (uint32_t)sizeof(gps_ch_t), rx->aux, (uint32_t)sizeof(gpsb_aux), ms0,
                                  n_ms, iq_log, nav_log, rx->loop_res);
         if (rc != GPSB_OK) return hx_note(rc);
@@ -610,7 +663,11 @@ int gpsb_rx_cold_sweep(gpsb_rx* rx, int32_t first_bin_hz, int32_t bin_step_hz, u
     gpsb_search_res* cells = NULL;
     if (n_sv) {
         cells = (gpsb_search_res*)malloc(sizeof(gpsb_search_res) * (size_t)n_sv * n_bins * n_ms);
-        rc = cells ? gpsb_sweep(rx->ctx, slots, n_sv, step32, n_bins, ms0, n_ms, 0, cells) : GPSB_ERR_NOMEM;
+        /* under a communicator (gpsb_comm_init) the cell groups are sharded over the ranks and all-gathered: every rank
+         * runs the same votes on the same grid */
+        if (!cells) rc = GPSB_ERR_NOMEM;
+        else if (gpsb_comm_size(rx->ctx) > 1) rc = gpsb_sweep_gather(rx->ctx, slots, n_sv, step32, n_bins, ms0, n_ms, 0, cells);
+        else rc = gpsb_sweep(rx->ctx, slots, n_sv, step32, n_bins, ms0, n_ms, 0, cells);
     }
     if (rc == GPSB_OK) {
         gpsb_host_set_packet_cnt(ms0 + n_ms - 1);
@@ -628,11 +685,207 @@ int gpsb_rx_cold_sweep(gpsb_rx* rx, int32_t first_bin_hz, int32_t bin_step_hz, u
                 if (chain >= 2) aux->freq_hist[b] += chain;
                 ch->acq_data.freq_index = (uint8_t)b;
                 hx_freq_hist_decide(ch, aux->freq_hist, n_bins, first_bin_hz, bin_step_hz);
+                /* The reference wipes its vote buffers - the Doppler histogram included - after EVERY bin
+                 * (acquisition_buffers_reset, acquisition.c:60-65, called at :303): the "histogram" only ever holds the
+                 * bin under test, so a satellite is accepted by the first bin whose ten snapshots agree in a chain of
+                 * three.  Reproduced as is. */
+                memset(aux->freq_hist, 0, sizeof aux->freq_hist);
+                ch->acq_data.freq_index = (uint8_t)(b + 1u >= n_bins ? 0u : b + 1u);   /* next bin, acquisition.c:305-310 */
             }
         }
     }
     free(cells); free(slots); free(who); free(step32);
     return hx_note(rc);
+}
+
+/* ---------------------------------------------------------------------------- cold start, N satellites */
+/* Code-phase rounds of every channel over the snapshots [ms, ms + n): within a round a channel's window and carrier
+ * are fixed, so the cells of the coming snapshots are independent until each vote - they are computed AHEAD in one
+ * launch and consumed in order.  A channel whose next cell differs from the one computed ahead (its round ended: new
+ * window) gets that one cell from a second, small launch and the run ends after that snapshot, so the next call starts
+ * from every channel's new window.  busy_mask: bit s set = a channel in acquisition state s still has work to do; the
+ * run also ends after the first snapshot that leaves no channel in such a state.  *consumed = snapshots processed. */
+static int acquire_ahead(gpsb_rx* rx, uint32_t ms, uint32_t n, uint32_t busy_mask, uint32_t* consumed, uint32_t* launches)
+{
+    const uint32_t n_ch = rx->n_ch;
+    *consumed = 0;
+    if (n == 0) return GPSB_OK;
+    gpsb_search_req* base = (gpsb_search_req*)calloc(n_ch, sizeof *base);
+    uint8_t* have = (uint8_t*)calloc(n_ch, 1);
+    uint32_t* col = (uint32_t*)calloc(n_ch, sizeof *col);
+    gpsb_search_req* rq = NULL;
+    gpsb_search_res* rs = NULL;
+    int rc = (base && have && col) ? GPSB_OK : GPSB_ERR_NOMEM;
+    uint32_t n_want = 0;
+    /* what every channel would correlate at snapshot `ms`, looked at without touching the channel */
+    for (uint32_t i = 0; i < n_ch && rc == GPSB_OK; i++) {
+        const gps_acq_t* a = &rx->ch[i].acq_data;
+        if (rx->ch[i].prn < 1) continue;
+        if (a->state != GPS_ACQ_CODE_PHASE_SEARCH1 && a->state != GPS_ACQ_CODE_PHASE_SEARCH2 &&
+            a->state != GPS_ACQ_CODE_PHASE_SEARCH3)
+            continue;
+        gps_ch_t probe = rx->ch[i];
+        gpsb_aux probe_aux = rx->aux[i];
+        gpsb_plan p;
+        hx_acq_plan(&probe, &probe_aux, ms, &p);
+        if (p.want != GPSB_WANT_SEARCH || p.search.start >= p.search.stop) continue;
+        base[i] = p.search;
+        have[i] = 1;
+        col[i] = n_want++;
+    }
+    if (rc == GPSB_OK && n_want) {
+        rq = (gpsb_search_req*)malloc(sizeof *rq * (size_t)n_want * n);
+        rs = (gpsb_search_res*)malloc(sizeof *rs * (size_t)n_want * n);
+        if (!rq || !rs) rc = GPSB_ERR_NOMEM;
+        for (uint32_t i = 0; i < n_ch && rc == GPSB_OK; i++) {
+            if (!have[i]) continue;
+            for (uint32_t k = 0; k < n; k++) {
+                rq[(size_t)k * n_want + col[i]] = base[i];
+                rq[(size_t)k * n_want + col[i]].ms_index = ms + k;
+            }
+        }
+        if (rc == GPSB_OK) {
+            rc = gpsb_search(rx->ctx, n_want * n, rq, rs);
+            if (launches) (*launches)++;
+        }
+    }
+    for (uint32_t k = 0; k < n && rc == GPSB_OK; k++) {
+        gpsb_host_set_packet_cnt(ms + k);
+        int cut = 0;
+        uint32_t n_miss = 0;
+        for (uint32_t i = 0; i < n_ch; i++) {
+            gpsb_plan* p = &rx->plan[i];
+            p->want = GPSB_WANT_NOTHING;
+            /* only channels in the code rounds are served: one whose Doppler vote did not pass would go on with its
+             * Doppler search (acquisition.c:141-146), which never ends on a satellite that is not there */
+            if (rx->ch[i].acq_data.state < GPS_ACQ_CODE_PHASE_SEARCH1) continue;
+            hx_acq_plan(&rx->ch[i], &rx->aux[i], ms + k, p);
+            if (p->want != GPSB_WANT_SEARCH) continue;
+            if (p->search.start >= p->search.stop) {
+                hx_acq_finish(&rx->ch[i], &rx->aux[i], p, &k_empty_window);
+            } else if (have[i] && p->search.step32 == base[i].step32 && p->search.start == base[i].start &&
+                       p->search.stop == base[i].stop && p->search.sv_slot == base[i].sv_slot &&
+                       p->search.off_bits == base[i].off_bits) {
+                hx_acq_finish(&rx->ch[i], &rx->aux[i], p, &rs[(size_t)k * n_want + col[i]]);
+            } else {
+                rx->s_rq[n_miss] = p->search;                    /* not computed ahead: this one cell now */
+                rx->s_owner[n_miss++] = i;
+                cut = 1;
+            }
+        }
+        if (n_miss) {
+            rc = gpsb_search(rx->ctx, n_miss, rx->s_rq, rx->s_res);
+            if (launches) (*launches)++;
+            for (uint32_t j = 0; j < n_miss && rc == GPSB_OK; j++) {
+                const uint32_t i = rx->s_owner[j];
+                hx_acq_finish(&rx->ch[i], &rx->aux[i], &rx->plan[i], &rx->s_res[j]);
+            }
+        }
+        *consumed = k + 1;
+        int busy = 0;
+        for (uint32_t i = 0; i < n_ch; i++)
+            if (rx->ch[i].prn >= 1 && ((busy_mask >> (uint32_t)rx->ch[i].acq_data.state) & 1u)) busy = 1;
+        if (!busy || cut) break;
+    }
+    free(base); free(have); free(col); free(rq); free(rs);
+    return hx_note(rc);
+}
+
+int gpsb_rx_cold_start(gpsb_rx* rx, uint32_t ms0, const gpsb_cold_start_opts* opts, gpsb_cold_start_report* rep)
+{
+    if (!rx) return hx_note(GPSB_ERR_ARG);
+    gpsb_cold_start_opts o;
+    memset(&o, 0, sizeof o);
+    if (opts) o = *opts;
+    if (o.n_bins == 0) {                       /* the reference's own grid, config.h:41-44 */
+        o.first_bin_hz = -ACQ_SEARCH_FREQ_HZ;
+        o.bin_step_hz = ACQ_SEARCH_STEP_HZ;
+        o.n_bins = ACQ_COUNT;
+    }
+    if (o.sweep_ms == 0) o.sweep_ms = 10;      /* ACQ_SINGLE_FREQ_LENGTH, acquisition.c:18 */
+    if (o.sweeps == 0) o.sweeps = 1;
+    if (o.round_timeout_ms == 0) o.round_timeout_ms = 400;
+    if (o.window_ms == 0) o.window_ms = 16;
+    gpsb_cold_start_report r;
+    memset(&r, 0, sizeof r);
+    r.ms_sweep0 = ms0;
+    const uint64_t launches0 = gpsb_launch_count(rx->ctx);
+    for (uint32_t i = 0; i < rx->n_ch; i++)
+        if (rx->ch[i].prn >= 1 && rx->ch[i].acq_data.state == GPS_ACQ_NEED_FREQ_SEARCH) r.n_searched++;
+    /* 1. Doppler: every (channel, bin, snapshot) cell in one launch, the reference's votes bin by bin */
+    /*    A satellite the first sweep leaves undecided gets further sweeps, each on the next sweep_ms snapshots, as the
+     *    reference's search does when it wraps round (acquisition.c:305-310). */
+    int rc = GPSB_OK;
+    uint32_t t = ms0;
+    for (uint32_t k = 0; k < o.sweeps; k++) {
+        uint32_t undecided = 0;
+        for (uint32_t i = 0; i < rx->n_ch; i++)
+            if (rx->ch[i].prn >= 1 && (rx->ch[i].acq_data.state == GPS_ACQ_NEED_FREQ_SEARCH ||
+                                       rx->ch[i].acq_data.state == GPS_ACQ_FREQ_SEARCH_RUN)) undecided++;
+        if (!undecided) break;
+        rc = gpsb_rx_cold_sweep(rx, o.first_bin_hz, o.bin_step_hz, o.n_bins, t, o.sweep_ms, NULL, NULL);
+        if (rc != GPSB_OK) return rc;
+        t += o.sweep_ms;
+        r.n_sweeps++;
+    }
+    /* 2. code phase, rounds 1 and 2 (acquisition.c:89-104, 150-170): all channels with a Doppler side by side */
+    r.ms_code0 = t;
+    gpsb_host_set_packet_cnt(t);
+    const uint32_t serve_world = o.serve_world ? o.serve_world : 1u;
+    for (uint32_t i = 0; i < rx->n_ch; i++) {
+        if (rx->ch[i].prn < 1 || rx->ch[i].acq_data.state != GPS_ACQ_FREQ_SEARCH_DONE) continue;
+        r.n_doppler_found++;
+        if (i % serve_world != o.serve_rank % serve_world) continue;        /* another rank's satellite from here on */
+        r.n_served++;
+        acquisition_start_code_search_channel(&rx->ch[i]);
+    }
+    const uint32_t busy12 = (1u << GPS_ACQ_CODE_PHASE_SEARCH1) | (1u << GPS_ACQ_CODE_PHASE_SEARCH1_DONE) |
+                            (1u << GPS_ACQ_CODE_PHASE_SEARCH2);
+    uint32_t launches = 0;
+    r.ms_code12_last = t ? t - 1 : 0;
+    while (r.n_served && t - r.ms_code0 < o.round_timeout_ms) {
+        uint32_t left = o.round_timeout_ms - (t - r.ms_code0), done = 0;
+        rc = acquire_ahead(rx, t, left < o.window_ms ? left : o.window_ms, busy12, &done, &launches);
+        if (rc != GPSB_OK) return rc;
+        t += done;
+        r.ms_code12_last = t - 1;
+        int busy = 0;
+        for (uint32_t i = 0; i < rx->n_ch; i++)
+            if (rx->ch[i].prn >= 1 && ((busy12 >> (uint32_t)rx->ch[i].acq_data.state) & 1u)) busy = 1;
+        if (!busy || done == 0) break;
+    }
+    /* 3. round 3 for every channel that finished round 2, started together (gps_master.c:113-118) */
+    r.ms_code3_first = t;
+    gpsb_host_set_packet_cnt(t);
+    uint32_t n_round3 = 0;
+    for (uint32_t i = 0; i < rx->n_ch; i++) {
+        if (rx->ch[i].prn < 1 || rx->ch[i].acq_data.state != GPS_ACQ_CODE_PHASE_SEARCH2_DONE) continue;
+        hx_acq_start_code_search3(&rx->ch[i], &rx->aux[i]);
+        n_round3++;
+    }
+    const uint32_t busy3 = (1u << GPS_ACQ_CODE_PHASE_SEARCH3) | (1u << GPS_ACQ_CODE_PHASE_SEARCH3_DONE);
+    r.ms_last = t ? t - 1 : 0;
+    while (n_round3 && t - r.ms_code3_first < o.round_timeout_ms) {
+        uint32_t left = o.round_timeout_ms - (t - r.ms_code3_first), done = 0;
+        rc = acquire_ahead(rx, t, left < o.window_ms ? left : o.window_ms, busy3, &done, &launches);
+        if (rc != GPSB_OK) return rc;
+        t += done;
+        r.ms_last = t - 1;
+        int busy = 0;
+        for (uint32_t i = 0; i < rx->n_ch; i++)
+            if (rx->ch[i].prn >= 1 && ((busy3 >> (uint32_t)rx->ch[i].acq_data.state) & 1u)) busy = 1;
+        if (!busy || done == 0) break;
+    }
+    /* 4. acquired channels go on to tracking (gps_master.c:121-129) */
+    for (uint32_t i = 0; i < rx->n_ch; i++) {
+        if (rx->ch[i].prn < 1 || rx->ch[i].acq_data.state != GPS_ACQ_DONE) continue;
+        r.n_acquired++;
+        if (rx->ch[i].tracking_data.state == GPS_TRACKNG_IDLE) rx->ch[i].tracking_data.state = GPS_NEED_PRE_TRACK;
+    }
+    r.ms_next = t;
+    r.launches = (uint32_t)(gpsb_launch_count(rx->ctx) - launches0);
+    if (rep) *rep = r;
+    return GPSB_OK;
 }
 
 /* ---------------------------------------------------------------------------- slot-phase walk */

@@ -82,6 +82,22 @@ class SyncStatus(C.Structure):
                 ("words_ok", C.c_uint32)]
 
 
+class ColdStartOpts(C.Structure):
+    """include/gpsb_host.h, gpsb_cold_start_opts (zero = the reference's defaults)"""
+    _fields_ = [("first_bin_hz", C.c_int32), ("bin_step_hz", C.c_int32), ("n_bins", C.c_uint32), ("sweep_ms", C.c_uint32),
+                ("round_timeout_ms", C.c_uint32), ("window_ms", C.c_uint32), ("sweeps", C.c_uint32), ("serve_rank", C.c_uint32),
+                ("serve_world", C.c_uint32)]
+
+
+class ColdStartReport(C.Structure):
+    """include/gpsb_host.h, gpsb_cold_start_report"""
+    _fields_ = [(n, C.c_uint32) for n in ("ms_sweep0", "ms_code0", "ms_code12_last", "ms_code3_first", "ms_last", "ms_next",
+                                          "n_sweeps", "n_searched", "n_doppler_found", "n_served", "n_acquired", "launches")]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
 _hostlib = None
 
 
@@ -136,6 +152,7 @@ def load_host_library(path: Path | None = None) -> C.CDLL:
         "gpsb_rx_set_threads": (None, [vp, u32]),
         "gpsb_rx_set_loop_site": (None, [vp, i32]),
         "gpsb_rx_loop_stats": (None, [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+        "gpsb_rx_cold_start": (i32, [vp, u32, C.POINTER(ColdStartOpts), C.POINTER(ColdStartReport)]),
         "gpsb_rx_set_slot_walk": (i32, [vp, i32, u32]),
         "gpsb_rx_channel_sync": (i32, [vp, u32, C.POINTER(SyncStatus)]),
         "gpsb_host_aux_walk": (None, [vp, u32, u32]),
@@ -321,6 +338,15 @@ class Receiver:
         self._check(self.lib.gpsb_rx_cold_sweep(self._rx, first_bin_hz, bin_step_hz, n_bins, ms0, n_ms,
                                                 votes.ctypes.data, phases.ctypes.data))
         return votes, phases
+
+    def cold_start(self, ms0: int, **opts) -> dict:
+        """gpsb_rx_cold_start: Doppler sweep, code-phase rounds 1..3 with the cells of coming snapshots computed ahead,
+        acquired channels handed to pre-track.  opts: fields of gpsb_cold_start_opts.  Returns the report as a dict."""
+        o, r = ColdStartOpts(), ColdStartReport()
+        for k, v in opts.items():
+            setattr(o, k, v)
+        self._check(self.lib.gpsb_rx_cold_start(self._rx, ms0, C.byref(o), C.byref(r)))
+        return r.as_dict()
 
     def close(self) -> None:
         if self._rx:

@@ -310,7 +310,7 @@ class RefWalk(C.Structure):
     """oracle/ref_shim.c, ref_walk: the checker's restatement of the slot-phase walk"""
     _fields_ = [("enable", C.c_uint32), ("period_ms", C.c_uint32), ("slot_phase", C.c_uint32), ("gap_first", C.c_uint32),
                 ("gap_len", C.c_uint32), ("phase_since", C.c_uint32), ("gaps_taken", C.c_uint32), ("edge_pos", C.c_uint32),
-                ("edges_at", C.c_uint32 * 4),
+                ("edges_at", C.c_uint32 * 4), ("armed", C.c_uint32),
                 ("slot_first_ms", C.c_uint32), ("sign", C.c_uint8 * 4), ("ip", C.c_int16 * 4), ("slot_fill", C.c_uint32)]
 
 

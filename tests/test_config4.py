@@ -1,0 +1,52 @@
+"""BASELINE configs[3] / SURVEY.md section 8(d) "Config 4" at its stated size on one GPU: 32 PRNs searched, 10 in the
+sky; cold sweep -> code-phase rounds 1..3 -> pre-track -> 10 000 ms of closed-loop tracking with nav-bit extraction
+(slot-phase walk on), every output diffed against the UNMODIFIED reference run satellite by satellite on the same
+snapshots (tests/config4_lib.py): found-PRN set, Doppler, code phase, the raw channel record of all 32 satellites, and for
+the acquired ones the per-millisecond sums of all three arms and the nav bits.  The sharded form (torchrun, one rank per
+GPU, satellites round-robin) is bench.py's config4 leg; tests/test_sharding.py covers its index arithmetic on the CPU."""
+import numpy as np
+import pytest
+
+import config4_lib as c4
+
+pytestmark = pytest.mark.gpu
+
+N_TRACK_MS = 10_000
+
+
+def test_config4_acquisition_and_10s_tracking_equal_the_reference(reference):
+    from stm32f4_sdr_gps_b200 import Engine
+    sc = c4.scene(N_TRACK_MS + 600)
+    sig = c4.signal(sc)
+    present = {s.prn: s for s in sc.sats}
+    eng = Engine(device=0, max_sv=40, ring_ms=sc.n_ms)
+    eng.upload_signal(0, sig)
+    launches0 = eng.launch_count
+    ch, rx, rep, logs = c4.product(eng, sig, c4.SEARCHED, N_TRACK_MS)
+    launches = eng.launch_count - launches0
+    refs = c4.reference_all(sig, c4.SEARCHED, rep, N_TRACK_MS)
+    summary = c4.diff(ch, logs, refs, c4.SEARCHED)
+    # and against the truth of the scene: every satellite in the sky was acquired and nothing else, code phase within
+    # four half chips.  The reference accepts the FIRST Doppler bin whose ten snapshots agree in a chain of three (its
+    # vote buffers are wiped after every bin, acquisition.c:299-303), which now and then is a side lobe 1.5 kHz off: such a
+    # channel "tracks" without ever finding the data bits, here and in the reference alike.  Everybody else pulls in to
+    # within 30 Hz and - the slot-phase walk on - ends with a refined bit edge.
+    assert set(summary["found_prns"]) == set(present), (summary["found_prns"], sorted(present))
+    good = 0
+    for a in summary["acquired"]:
+        sat = present[a["prn"]]
+        half_chip = (sat.code_phase_samples / 8.0) % 2046
+        assert min(abs(a["code_phase"] - half_chip), 2046 - abs(a["code_phase"] - half_chip)) <= 4, (a, half_chip)    # round 3 votes in cells of 2 half chips
+        if abs(a["doppler_hz"] - sat.doppler_hz) <= 500:
+            assert abs(a["carrier_hz"] - sat.doppler_hz) < 30 and a["bit_edge_refined"] == 1, a
+            good += 1
+    assert good >= len(present) - 2, summary["acquired"]
+    assert summary["nav_bits"] >= good * 350                     # 20-ms data bits handed to the word assembler, ~8 s each
+    assert summary["cells"] == len(present) * N_TRACK_MS
+    assert rep["n_searched"] == 32 and rep["n_acquired"] == len(present)
+    # one sweep launch + a few look-ahead windows instead of one launch per snapshot
+    assert rep["launches"] < (rep["ms_last"] - rep["ms_code0"] + 1), rep
+    assert rx.loop_stats()[0] >= len(present) * (N_TRACK_MS - 160)         # tracking ran in the device-resident loop
+    rx.close()
+    ch.free()
+    eng.close()
