@@ -597,26 +597,49 @@ def run_gpu_arm(args) -> None:
         eng.set_code_prn(prn, prn)
     eng.upload_signal(N_MS, acq_sig)                    # frames N_MS .. N_MS+9 of the ring
     step = np.array([nco_step32(np.float32(IF_HZ - 5000 + 500 * b)) for b in range(ACQ_BINS)], np.uint32)
-    from stm32f4_sdr_gps_b200 import sharding
-    my_sv = (sharding.shard_satellites(ACQ_SV, rank, world) + 1).astype(np.uint32)      # PRN = index + 1
-    d_sv = torch.from_numpy(my_sv.view(np.int32)).to(dev)
+    # One sweep = all 32 satellites x 21 bins x 10 ms.  value: the SHARDED sweep - the 210 (bin, ms) cell groups dealt
+    # round-robin over the ranks (every rank keeps whole 8-satellite tiles), ncclAllGather of the triples on the context
+    # stream straight out of device memory, permutation into the (sv, bin, ms) grid - timed warmed over `steps`
+    # iterations, gather INCLUDED.  Beside it the whole sweep on this rank's GPU alone (what one GPU needs).
+    if world > 1:
+        eng.comm_init_torch()
+    all_sv = np.arange(1, ACQ_SV + 1, dtype=np.uint32)
+    d_sv = torch.from_numpy(all_sv.view(np.int32)).to(dev)
     d_step = torch.from_numpy(step.view(np.int32)).to(dev)
-    n_acq_cells = my_sv.size * ACQ_BINS * ACQ_MS
+    n_acq_cells = ACQ_SV * ACQ_BINS * ACQ_MS
     d_res = torch.zeros(n_acq_cells * 4, dtype=torch.int16, device=dev)
     acq_ms = {}
     for method, name in ((0, "direct"), (1, "dp4a")):
         eng.set_sweep_method(method)
         for _ in range(3):
-            eng.sweep_dev(d_sv.data_ptr(), my_sv.size, d_step.data_ptr(), ACQ_BINS, N_MS, ACQ_MS, 0, d_res.data_ptr())
+            eng.sweep_dev(d_sv.data_ptr(), ACQ_SV, d_step.data_ptr(), ACQ_BINS, N_MS, ACQ_MS, 0, d_res.data_ptr())
         barrier()
         ev = events(steps)
         for k in range(steps):
             flush.fill_(k)
             ev[k][0].record(stream)
-            eng.sweep_dev(d_sv.data_ptr(), my_sv.size, d_step.data_ptr(), ACQ_BINS, N_MS, ACQ_MS, 0, d_res.data_ptr())
+            eng.sweep_dev(d_sv.data_ptr(), ACQ_SV, d_step.data_ptr(), ACQ_BINS, N_MS, ACQ_MS, 0, d_res.data_ptr())
             ev[k][1].record(stream)
         barrier()
         acq_ms[name] = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    one_gpu_grid = d_res.cpu().numpy().view(np.uint16).reshape(ACQ_SV, ACQ_BINS, ACQ_MS, 4).copy()
+    eng.set_sweep_method(1)
+    for _ in range(max(3, warm)):
+        d_grid_ptr = eng.sweep_gather_dev(d_sv.data_ptr(), ACQ_SV, d_step.data_ptr(), ACQ_BINS, N_MS, ACQ_MS, 0)
+    barrier()
+    ev = events(steps)
+    for k in range(steps):
+        flush.fill_(k)
+        if world > 1:
+            dist.barrier()                    # the ranks start a sweep together, as one job would
+        ev[k][0].record(stream)
+        d_grid_ptr = eng.sweep_gather_dev(d_sv.data_ptr(), ACQ_SV, d_step.data_ptr(), ACQ_BINS, N_MS, ACQ_MS, 0)
+        ev[k][1].record(stream)
+    barrier()
+    acq_ms["gathered"] = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    grid = eng.sweep_gather(all_sv, step, N_MS, ACQ_MS).view(np.uint16).reshape(ACQ_SV, ACQ_BINS, ACQ_MS, 4)
+    assert np.array_equal(grid, one_gpu_grid), "sharded + gathered sweep differs from the sweep on one GPU"
+    my_sv = all_sv
     # the fine grid of SURVEY.md section 8(d) config 3: 2046 half-chip offsets x 8 sub-byte shifts = 16368 phases
     eng.set_sweep_method(1)
     ev = events(steps)
@@ -629,6 +652,7 @@ def run_gpu_arm(args) -> None:
     barrier()
     acq_fine_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
     eng.sweep_dev(d_sv.data_ptr(), my_sv.size, d_step.data_ptr(), ACQ_BINS, N_MS, ACQ_MS, 0, d_res.data_ptr())   # leave the bits-0 grid
+    acq_fine_ms *= 1.0                    # (whole fine grid on this rank's GPU alone)
     # end to end: host signal in, all-channel Doppler votes out (upload + sweep + D2H + host chain votes)
     acq_ch = Channels([int(p) for p in my_sv])
     acq_rx = Receiver(eng, acq_ch)
@@ -645,20 +669,54 @@ def run_gpu_arm(args) -> None:
         t_acq_e2e.append((time.perf_counter() - t0) * 1e3)
     acq_e2e_ms = float(np.min(t_acq_e2e))
     found = int(sum(1 for i in range(acq_ch.n) if acq_ch.snapshot(i).acq_state == 2))
+
+    # ---- config 4 (BASELINE configs[3]): 32 PRNs searched, 10 in the sky; cold sweeps -> code-phase rounds 1..3 ->
+    # pre-track -> C4_MS ms of closed-loop tracking with nav bits (slot-phase walk on).  Several GPUs: the sweep's cell
+    # groups sharded + all-gathered (gpsb_sweep_gather), every rank runs the same votes, the satellites found are dealt
+    # round-robin over the ranks for everything after (no further exchange).  Every output of every satellite is
+    # diffed against the unmodified reference run on the same snapshots (tests/config4_lib.py).
+    sys.path.insert(0, str(REPO / "tests"))
+    import config4_lib as c4
+    C4_MS = int(os.environ.get("GPSB_BENCH_C4_MS", "10000"))
+    sc4 = c4.scene(C4_MS + 700)
+    path4 = Path(tempfile.gettempdir()) / ("gpsb_bench_cfg4_%d.npy" % C4_MS)
+    if rank == 0 and not path4.exists():
+        tmp4 = path4.with_suffix(".tmp.npy")
+        np.save(tmp4, c4.signal(sc4))
+        os.replace(tmp4, path4)
+    barrier()
+    sig4 = np.load(path4)
+    eng4 = Engine(device=local_rank, max_sv=40, ring_ms=sc4.n_ms)
+    if world > 1:
+        eng4.comm_init_torch()
+    eng4.upload_signal(0, sig4)
+    serve = dict(serve_rank=rank, serve_world=world)
+    ch_w, rx_w, _, _ = c4.product(eng4, sig4, c4.SEARCHED, 400, cold_start_opts=serve)        # warm-up (allocations, NCCL)
+    rx_w.close(); ch_w.free()
+    tm4 = {}
+    ch4, rx4, rep4, logs4 = c4.product(eng4, sig4, c4.SEARCHED, C4_MS, timers=tm4, cold_start_opts=serve, before_start=barrier)
+    c4_times = [tm4["cold_start_s"], tm4["pre_track_s"], tm4["tracking_s"], tm4["total_s"]]
+    mine4 = [i % world == rank for i in range(len(c4.SEARCHED))]
+    t0 = time.perf_counter()
+    refs4 = c4.reference_all(sig4, c4.SEARCHED, rep4, C4_MS, served=mine4, procs=max(1, (os.cpu_count() or 1) // world))
+    c4_twin_s = time.perf_counter() - t0
+    sum4 = c4.diff(ch4, logs4, refs4, c4.SEARCHED)          # raises on the first differing field / sum / nav bit
+    sum4["acquired"] = [a for a in sum4["acquired"] if mine4[c4.SEARCHED.index(a["prn"])]]
+    if world > 1:
+        box = [None] * world
+        dist.all_gather_object(box, (sum4, rep4, c4_twin_s))
+    else:
+        box = [(sum4, rep4, c4_twin_s)]
+    rx4.close(); ch4.free(); eng4.close()
     clk = clocks.stop()
 
     # ---- max over ranks
-    times = torch.tensor([t_dev, t_e2e, acq_ms["dp4a"], acq_ms["direct"], acq_e2e_ms, batch_ms, many_ms, long_ms[1], long_ms[3]],
-                         dtype=torch.float64, device=dev)
+    times = torch.tensor([t_dev, t_e2e, acq_ms["dp4a"], acq_ms["direct"], acq_e2e_ms, batch_ms, many_ms, long_ms[1], long_ms[3],
+                          acq_ms["gathered"]] + c4_times, dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    # the one exchange of the path: all-gather of the sweep triples so every rank holds the full grid
-    local = d_res.cpu().numpy().view(np.uint16).reshape(my_sv.size, ACQ_BINS, ACQ_MS, 4)
-    t0 = time.perf_counter()
-    grid = sharding.gather_sweep(sharding.pack_local(local, ACQ_SV, rank, world), ACQ_SV, world, device=dev)
-    gather_ms = (time.perf_counter() - t0) * 1e3
-    assert grid.shape == (ACQ_SV, ACQ_BINS, ACQ_MS, 4) and np.array_equal(grid[my_sv - 1], local)
-    t_dev, t_e2e, acq_dp4a_ms, acq_direct_ms, acq_e2e_ms, batch_ms, many_ms, long1_ms, long3_ms = [float(x) for x in times.cpu()]
+    (t_dev, t_e2e, acq_dp4a_ms, acq_direct_ms, acq_e2e_ms, batch_ms, many_ms, long1_ms, long3_ms, acq_gathered_ms,
+     c4_cold_s, c4_pre_s, c4_trk_s, c4_total_s) = [float(x) for x in times.cpu()]
 
     rank_has_prn12 = True        # the gathered grid holds every satellite on every rank
     if rank == 0:
@@ -678,16 +736,18 @@ def run_gpu_arm(args) -> None:
         loop_achieved = loop_bytes / (loop_kernel_ms * 1e-3) / 1e9
         batch_bytes = N_MS * 2046 + N_SV_PER_GPU * 128 + n_cells * (24 + 12)
         acq_bitmacs = ACQ_SV * ACQ_BINS * ACQ_MS * 2046 * 2 * 16368
-        acq_alg_bytes = ACQ_MS * 2046 + len(my_sv) * 128 + n_acq_cells * 8
+        acq_alg_bytes = ACQ_MS * 2046 + ACQ_SV * 128 + n_acq_cells * 8
         # dp4a issue slots of the sweep: 4 correlations (I/Q x parity) x 1023 lags x 256 steps per cell
-        acq_dp4a = ACQ_SV * ACQ_BINS * ACQ_MS * 4 * 1023 * 256 / world
+        acq_dp4a = ACQ_SV * ACQ_BINS * ACQ_MS * 4 * 1023 * 256
         sm_clk = (clk.get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0) * 1e6
         idp_peak = 148 * 64 * sm_clk                       # IDP.4A: 64 lanes/clk/SM measured (tools/ubench_int.cu)
         # ---- the reference's own C on this box's host cores, same workload, and the at-size parity of this run
         sys.path.insert(0, str(REPO / "tests"))
         from oracle_lib import best_o3_variant
         host_cores = os.cpu_count() or 1
-        parity = {}
+        parity = {"config4": {"vs": "unmodified reference per satellite", "channel_records": len(c4.SEARCHED),
+                              "tracking_cells": int(sum(b[0]["cells"] for b in box)), "equal": True},
+                  "cold_acq_sharded_vs_one_gpu": {"cells": int(n_acq_cells), "equal": True}}
         cpu_t, cpu_cores, ref_logs = reference_tracking([(scene, sig)], host_cores, reps=3, want_logs=True)
         cpu = cpu_1core = cpu_o3 = None
         if cpu_t:
@@ -825,19 +885,45 @@ def run_gpu_arm(args) -> None:
                     "value": prompt_cpu_rate, "unit": "cells/s (1 core)", "cores": 1, "kind": "reference",
                     "sample": "first 8000 ms: gps_generate_prn_data2 + gps_shift_to_zero_freq + gps_correlation_iq per ms; "
                               "I/Q identical to the GPU's"}},
-            "cold_acq": {"metric": "full-sky 32-SV cold-acq ms", "value": acq_dp4a_ms, "unit": "ms",
+            "config4": {
+                "what": "BASELINE configs[3]: 32 PRNs searched (10 in the sky), %d Doppler sweep(s) of 29 bins x 10 ms -> code-phase "
+                        "rounds 1..3 (look-ahead windows) -> pre-track -> %d ms closed-loop tracking with nav bits, slot-phase "
+                        "walk on; %s" % (rep4["n_sweeps"], C4_MS,
+                                         "one GPU" if world == 1 else "sweep cell groups sharded + ncclAllGather, satellites found "
+                                         "dealt round-robin over %d ranks" % world),
+                "wall_ms": c4_total_s * 1e3, "cold_start_ms": c4_cold_s * 1e3, "pre_track_ms": c4_pre_s * 1e3,
+                "tracking_ms": c4_trk_s * 1e3,
+                "time_to_decision_ms": c4_cold_s * 1e3, "time_to_first_tracking_ms": (c4_cold_s + c4_pre_s) * 1e3,
+                "signal_ms": int(rep4["ms_next"] + C4_MS), "times_real_time": (rep4["ms_next"] + C4_MS) / (c4_total_s * 1e3),
+                "launches_cold_start_rank0": rep4["launches"], "schedule_rank0": rep4,
+                "found_prns": sorted(p for b in box for p in [a["prn"] for a in b[0]["acquired"]]),
+                "in_the_sky": sorted(s_.prn for s_ in sc4.sats),
+                "bit_edges_refined": int(sum(a["bit_edge_refined"] for b in box for a in b[0]["acquired"])),
+                "parity": {"vs": "unmodified reference (oracle/_ref) per satellite on the same snapshots", "equal": True,
+                           "channel_records": len(c4.SEARCHED), "tracking_cells": int(sum(b[0]["cells"] for b in box)),
+                           "nav_bits": int(sum(b[0]["nav_bits"] for b in box))},
+                "reference_twin_s": max(b[2] for b in box),
+                "reference_twin_what": "the same work by the unmodified reference C, one process per satellite on the box's "
+                                       "cores (driven from Python, dominated by the 870 Doppler cells per PRN)"},
+            "cold_acq": {"metric": "full-sky 32-SV cold-acq ms", "value": acq_gathered_ms, "unit": "ms",
+                         "value_what": "sweep sharded over %d rank(s) by (bin, ms) cell group + ncclAllGather of the triples on "
+                                       "the context stream + permutation into the (sv, bin, ms) grid; warmed, events, max over "
+                                       "ranks" % world,
+                         "one_gpu_ms": acq_dp4a_ms,
                          "direct_xor_popc_ms": acq_direct_ms, "e2e_ms": acq_e2e_ms,
                          "fine_grid_16368_phases_ms": acq_fine_ms,
                          "cells": ACQ_SV * ACQ_BINS * ACQ_MS, "phases": 2046, "bit_macs": acq_bitmacs,
-                         "bit_macs_per_s": acq_bitmacs / (acq_dp4a_ms * 1e-3), "doppler_votes_passed_rank0": found,
+                         "bit_macs_per_s": acq_bitmacs / (acq_gathered_ms * 1e-3), "doppler_votes_passed_rank0": found,
                          "cpu_baseline": None if not acq_cpu_rate else {
                              "value": ACQ_SV * ACQ_BINS * ACQ_MS / acq_cpu_rate * 1e3, "unit": "ms (extrapolated, 1 core)",
                              "cores": 1, "kind": "reference",
                              "sample": "%d of the 6720 cells (2 SV x 21 bins x 2 ms), correlation_search 0..2046" % acq_cpu_cells},
-                         "gather_ms": gather_ms, "sharding": "satellites round-robin over %d rank(s)" % world,
+                         "sharding": "(bin, ms) cell groups round-robin over %d rank(s), whole 8-satellite tiles per rank" % world,
                          "roofline": {"kernel": "k_acq_dp4a", "bound": "int-dot-product pipe (IDP.4A 64 lanes/clk/SM)",
+                                      "what": "the whole sweep on one GPU (one_gpu_ms)",
                                       "achieved": acq_dp4a / (acq_dp4a_ms * 1e-3) / 1e12, "peak": idp_peak / 1e12,
                                       "unit": "T dp4a/s", "frac": acq_dp4a / (acq_dp4a_ms * 1e-3) / idp_peak,
+                                      "frac_sharded": acq_dp4a / (acq_gathered_ms * 1e-3) / (idp_peak * world),
                                       "hbm_frac": acq_alg_bytes / (acq_dp4a_ms * 1e-3) / 1e9 / hbm_peak}},
         }
         print(json.dumps(line))

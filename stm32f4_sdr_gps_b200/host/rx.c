@@ -339,11 +339,21 @@ static int finish_device_run(gpsb_rx* rx, uint32_t ms0, uint32_t n_ms, int16_t* 
             rx->host_ms++;
             ms++;
         }
+        rx->plan[i].stage = (int)(ms - ms0);          /* scratch: first row of channel i the loop did not deliver */
+    }
+    /* rows the loop did not deliver are blank until somebody fills them: one pass over the logs, row by row */
+    uint32_t first_blank = n_ms;
+    for (uint32_t i = 0; i < n_ch; i++)
+        if ((uint32_t)rx->plan[i].stage < first_blank) first_blank = (uint32_t)rx->plan[i].stage;
+    for (uint32_t k = first_blank; k < n_ms; k++)
+        for (uint32_t i = 0; i < n_ch; i++)
+            if (k >= (uint32_t)rx->plan[i].stage) {
+                if (iq_log) memset(iq_log + ((size_t)k * n_ch + i) * 6, 0, 12);
+                if (nav_log) nav_log[(size_t)k * n_ch + i] = -1;
+            }
+    for (uint32_t i = 0; i < n_ch; i++) {
+        const uint32_t ms = ms0 + (uint32_t)rx->plan[i].stage;
         if (ms < ms0 + n_ms) {
-            if (iq_log)
-                for (uint32_t k = ms - ms0; k < n_ms; k++) memset(iq_log + ((size_t)k * n_ch + i) * 6, 0, 12);
-            if (nav_log)
-                for (uint32_t k = ms - ms0; k < n_ms; k++) nav_log[(size_t)k * n_ch + i] = -1;
             int rc = run_channel_span(rx, i, ms0, ms, ms0 + n_ms, iq_log, nav_log);
             if (rc != GPSB_OK) return rc;
         }

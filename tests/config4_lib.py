@@ -38,7 +38,8 @@ def signal(sc):
     return synthesize_blocks(sc.sats, sc.n_ms, sc.seed)
 
 
-def product(engine, sig, prns, n_track_ms, pre_ms=160, walk=True, timers=None, sweeps=3, cold_start_opts=None):
+def product(engine, sig, prns, n_track_ms, pre_ms=160, walk=True, timers=None, sweeps=3, cold_start_opts=None,
+            before_start=None):
     """Returns (channels, receiver, report, per-channel logs).  The signal must already be in the engine's ring from
     frame 0 (gpsb_upload_signal).  timers: optional dict that receives wall-clock seconds per stage."""
     import time
@@ -47,6 +48,8 @@ def product(engine, sig, prns, n_track_ms, pre_ms=160, walk=True, timers=None, s
     rx = Receiver(engine, ch)
     if walk:
         rx.set_slot_walk(True)
+    if before_start:
+        before_start()                                          # e.g. a barrier over the ranks
     t0 = time.perf_counter()
     rep = rx.cold_start(0, sweeps=sweeps, **(cold_start_opts or {}))
     t1 = time.perf_counter()
@@ -61,8 +64,9 @@ def product(engine, sig, prns, n_track_ms, pre_ms=160, walk=True, timers=None, s
     return ch, rx, rep, (np.concatenate([iq_a, iq_b]), np.concatenate([nav_a, nav_b]))
 
 
-def reference(ref, sig, prn, rep, n_track_ms, walk=True):
+def reference(ref, sig, prn, rep, n_track_ms, walk=True, served=True):
     """One satellite through the unmodified reference on the schedule `rep` (a gpsb_cold_start_report as a dict).
+    served=False: a satellite another rank goes on with - this rank stops serving it after the sweeps.
     Returns (final channel record bytes, iq, nav, state after acquisition)."""
     from oracle_lib import RefWalk
     lib = ref.lib
@@ -79,7 +83,7 @@ def reference(ref, sig, prn, rep, n_track_ms, walk=True):
                     break
                 ref.set_ms(first + SWEEP_MS - 1)
                 lib.acquisition_process_channel(ch, sig[first + m].ctypes.data)
-    if ref.snapshot(ch).acq_state == 2:                     # GPS_ACQ_FREQ_SEARCH_DONE: the others are not served any more
+    if served and ref.snapshot(ch).acq_state == 2:          # GPS_ACQ_FREQ_SEARCH_DONE: the others are not served any more
         ref.set_ms(rep["ms_code0"])
         lib.acquisition_start_code_search_channel(ch)
         for ms in range(rep["ms_code0"], rep["ms_code12_last"] + 1):
@@ -143,15 +147,17 @@ def _ref_job(i):
     ref = _shared.get("ref")
     if ref is None:
         ref = _shared["ref"] = Reference()
-    return reference(ref, _shared["sig"], _shared["prns"][i], _shared["rep"], _shared["n_track_ms"], _shared["walk"])
+    return reference(ref, _shared["sig"], _shared["prns"][i], _shared["rep"], _shared["n_track_ms"], _shared["walk"],
+                     _shared["served"][i])
 
 
-def reference_all(sig, prns, rep, n_track_ms, walk=True, procs=None):
+def reference_all(sig, prns, rep, n_track_ms, walk=True, procs=None, served=None):
     """reference() for every searched satellite, one process each on up to `procs` cores (the reference's file-scope
-    scratch serves one channel at a time)."""
+    scratch serves one channel at a time).  served[i] False: satellite i belongs to another rank after the sweeps."""
     import multiprocessing as mp
     import os
-    _shared.update(sig=sig, prns=list(prns), rep=rep, n_track_ms=n_track_ms, walk=walk)
+    _shared.update(sig=sig, prns=list(prns), rep=rep, n_track_ms=n_track_ms, walk=walk,
+                   served=list(served) if served is not None else [True] * len(prns))
     _shared.pop("ref", None)
     procs = max(1, min(procs or (os.cpu_count() or 1), len(prns)))
     if procs == 1:
