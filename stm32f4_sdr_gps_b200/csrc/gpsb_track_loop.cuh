@@ -186,7 +186,7 @@ __device__ __forceinline__ int frame_present(const StreamGate& gate, uint32_t ms
 // kExp: timing experiments only (results wrong): bit 0 skips phase 1, bit 1 skips the carrier filters, bit 2 the DLL
 // kStream: streaming-ingest build (the resident build carries none of its checks)
 template <bool kProf, int kExp = 0, bool kStream = false>
-__global__ void __launch_bounds__(kLoopThreads, 1)
+__global__ void __maxnreg__(96)      // measured: 96 registers 1.068 us per ms, uncapped (123) 1.087, 80: 1.124
 k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uint32_t* __restrict__ codes,
             const uint32_t* __restrict__ signal, uint32_t ring_ms, uint32_t ms0, uint32_t n_ms,
             int16_t* __restrict__ iq_log, int8_t* __restrict__ nav_log, gpsb_loop_result* __restrict__ results,
@@ -199,11 +199,11 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
     // kProf: raw clock64 stamps of four consecutive milliseconds (kTlFirst ..) per warp, eight per millisecond, behind the
     // per-phase totals: prof[n_ch * 16 + ((chn * kLoopWarps + warp) * 4 + k) * 8 + point]
     constexpr uint32_t kTlFirst = 500u;
+    __shared__ uint32_t tl_buf[kProf ? kLoopWarps * 4 * 8 : 1];      // stamps go to shared memory (one STS), dumped after the loop
 #define GPSB_TL(point)                                                                                                  \
     do {                                                                                                                \
         if (kProf && (threadIdx.x & 31) == 0 && m >= kTlFirst && m < kTlFirst + 4u)                                      \
-            prof[gridDim.x * 16 + ((blockIdx.x * kLoopWarps + (threadIdx.x >> 5)) * 4 + (m - kTlFirst)) * 8 + (point)] = \
-                (unsigned long long)clock64();                                                                          \
+            tl_buf[((threadIdx.x >> 5) * 4 + (m - kTlFirst)) * 8 + (point)] = (uint32_t)clock();                         \
     } while (0)
     const int tid = threadIdx.x;
     const uint32_t chn = blockIdx.x, n_ch = gridDim.x;
@@ -225,6 +225,7 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
     uint32_t edge_counts = 0u;
     int edge_w = 0, edge_neg = 0;
 
+    if (kProf) for (int i = tid; i < kLoopWarps * 4 * 8; i += kLoopThreads) tl_buf[i] = 0u;
     copy_words(&sm.ch, chans + chn, tid, kLoopThreads);
     copy_words(&sm.aux, auxs + chn, tid, kLoopThreads);
     {
@@ -544,6 +545,8 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
     }
     __syncthreads();
     if (kProf) {
+        for (int i = tid; i < kLoopWarps * 4 * 8; i += kLoopThreads)
+            prof[gridDim.x * 16 + (size_t)blockIdx.x * kLoopWarps * 4 * 8 + i] = tl_buf[i];
         if (worker && wtid == 0) {
             prof[chn * 16 + 0] = (unsigned long long)pt[0]; prof[chn * 16 + 1] = (unsigned long long)pt[1];
             prof[chn * 16 + 7] = (unsigned long long)pt[7]; prof[chn * 16 + 8] = (unsigned long long)pt[8];
