@@ -339,6 +339,7 @@ def arm_locked(channels, scene):
 
 # profiler runs only (never for a reported number): a kernel replayed by ncu cannot be fed by a concurrent copy stream
 NO_STREAM = os.environ.get("GPSB_BENCH_NO_STREAM") is not None
+LOOP_FIXED_SLOTS = 2          # include/gpsb.h GPSB_LOOP_FIXED_SLOTS: config 2 tracks at slot index = ms % 4 (no slot-phase walk)
 
 
 def run_gpu_arm(args) -> None:
@@ -399,8 +400,8 @@ def run_gpu_arm(args) -> None:
 
     for _ in range(warm):
         device_step()
-        eng.track_loop_dev(n_ch, d_records.data_ptr(), d_aux.data_ptr(), 0, N_MS, d_iq.data_ptr(), d_nav.data_ptr(),
-                           d_result.data_ptr())
+        eng.track_loop_dev_ex(n_ch, d_records.data_ptr(), d_aux.data_ptr(), 0, N_MS, d_iq.data_ptr(), d_nav.data_ptr(),
+                              d_result.data_ptr(), LOOP_FIXED_SLOTS)
     barrier()
     clocks = ClockSampler(local_rank)
     launches0 = eng.launch_count
@@ -409,8 +410,8 @@ def run_gpu_arm(args) -> None:
         device_step()
         flush.fill_(k)                       # evict L2 between timed iterations (not timed)
         ev[k][0].record(stream)
-        eng.track_loop_dev(n_ch, d_records.data_ptr(), d_aux.data_ptr(), 0, N_MS, d_iq.data_ptr(), d_nav.data_ptr(),
-                           d_result.data_ptr())
+        eng.track_loop_dev_ex(n_ch, d_records.data_ptr(), d_aux.data_ptr(), 0, N_MS, d_iq.data_ptr(), d_nav.data_ptr(),
+                              d_result.data_ptr(), LOOP_FIXED_SLOTS)
         ev[k][1].record(stream)
     barrier()
     t_dev = float(np.sum([a.elapsed_time(b) for a, b in ev])) / 1e3

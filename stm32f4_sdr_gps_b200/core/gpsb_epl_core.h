@@ -231,10 +231,10 @@ EC_FN void ec_epl_phase1(const uint32_t* S, const uint32_t* RX, const uint32_t o
  * arm e % 3.  Returns the packed counts of its one (word, arm) entry, *w the data word it belongs to (for the
  * carrier phase in phase 2) and *negative = 1 when the entry is to be subtracted. */
 #define EC_EDGE_LANES 12
-EC_FN uint32_t ec_epl_edge_phase1(const uint32_t* S, const uint32_t* RX, const uint32_t off[3], int e, int* w, int* negative)
+/* The entry of one edge lane given its role (0..3) and the byte offset o of ITS arm: the caller reads that one offset
+ * (a lane only ever needs its own arm's; indexing an array of three by a run-time arm would put it in local memory). */
+EC_FN uint32_t ec_epl_edge_entry(const uint32_t* S, const uint32_t* RX, uint32_t o, int role, int* w, int* negative)
 {
-    const int role = e / 3, a = e % 3;
-    const uint32_t o = off[a];
     const int odd = (int)(o & 1u);
     int word, active = 1;
     uint32_t m;
@@ -257,6 +257,10 @@ EC_FN uint32_t ec_epl_edge_phase1(const uint32_t* S, const uint32_t* RX, const u
     *w = word;
     *negative = role >= 2;
     return active ? ec_counts_masked(x, m, mixed) : 0u;
+}
+EC_FN uint32_t ec_epl_edge_phase1(const uint32_t* S, const uint32_t* RX, const uint32_t off[3], int e, int* w, int* negative)
+{
+    return ec_epl_edge_entry(S, RX, off[e % 3], e / 3, w, negative);
 }
 
 /* Phase 2: per word the carrier phase ph picks the I count (pattern cos[ph]) and the Q count (pattern

@@ -1184,15 +1184,26 @@ static int track_loop_launch(gpsb_ctx* c, uint32_t n_ch, void* d_channels, void*
     }
     GPSB_EXP_LAUNCH(1) GPSB_EXP_LAUNCH(2) GPSB_EXP_LAUNCH(3) GPSB_EXP_LAUNCH(4) GPSB_EXP_LAUNCH(5) GPSB_EXP_LAUNCH(7)
 #endif
+    const bool fixed = (flags & GPSB_LOOP_FIXED_SLOTS) != 0;     // no channel walks its slots: the build without the walk
     if (flags & GPSB_LOOP_STREAMING) {
-        k_track_run<false, 0, true><<<n_ch, kLoopThreads, 0, c->stream>>>((gps_ch_t*)d_channels, (gpsb_aux*)d_aux, c->d_codes,
-                                                                          c->d_signal, c->ring_ms, ms0, n_ms, d_iq_log,
-                                                                          d_nav_log, d_results, nullptr, gate);
+        if (fixed)
+            k_track_run<false, 0, true, false><<<n_ch, kLoopThreads, 0, c->stream>>>(
+                (gps_ch_t*)d_channels, (gpsb_aux*)d_aux, c->d_codes, c->d_signal, c->ring_ms, ms0, n_ms, d_iq_log, d_nav_log,
+                d_results, nullptr, gate);
+        else
+            k_track_run<false, 0, true><<<n_ch, kLoopThreads, 0, c->stream>>>(
+                (gps_ch_t*)d_channels, (gpsb_aux*)d_aux, c->d_codes, c->d_signal, c->ring_ms, ms0, n_ms, d_iq_log, d_nav_log,
+                d_results, nullptr, gate);
         return check_launch(c, "k_track_run<streaming>");
     }
-    k_track_run<false><<<n_ch, kLoopThreads, 0, c->stream>>>((gps_ch_t*)d_channels, (gpsb_aux*)d_aux, c->d_codes,
-                                                             c->d_signal, c->ring_ms, ms0, n_ms, d_iq_log, d_nav_log,
-                                                             d_results, nullptr, gate);
+    if (fixed)
+        k_track_run<false, 0, false, false><<<n_ch, kLoopThreads, 0, c->stream>>>(
+            (gps_ch_t*)d_channels, (gpsb_aux*)d_aux, c->d_codes, c->d_signal, c->ring_ms, ms0, n_ms, d_iq_log, d_nav_log,
+            d_results, nullptr, gate);
+    else
+        k_track_run<false><<<n_ch, kLoopThreads, 0, c->stream>>>((gps_ch_t*)d_channels, (gpsb_aux*)d_aux, c->d_codes,
+                                                                 c->d_signal, c->ring_ms, ms0, n_ms, d_iq_log, d_nav_log,
+                                                                 d_results, nullptr, gate);
     return check_launch(c, "k_track_run");
 }
 
@@ -1347,6 +1358,13 @@ int gpsb_track_loop_begin(gpsb_ctx* c, uint32_t n_ch, void* channels, uint32_t c
     cudaError_t e = cudaSetDevice(c->device);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d, h, o.o_aux + o.aux_b, cudaMemcpyHostToDevice, c->stream);   // records: one copy in
     if (e != cudaSuccess) return bail(fail(GPSB_ERR_CUDA, "record upload failed: %s", cudaGetErrorString(e)));
+    // host records: the library sees for itself whether any channel walks its slots (core/gpsb_loop_core.h, lc_walk_*)
+    {
+        const gpsb_aux* ax = (const gpsb_aux*)aux;
+        bool walks = false;
+        for (uint32_t i = 0; i < n_ch; i++) walks |= ax[i].walk_enable || ax[i].slot_phase || ax[i].skip_len;
+        flags = walks ? (flags & ~GPSB_LOOP_FIXED_SLOTS) : (flags | GPSB_LOOP_FIXED_SLOTS);
+    }
     rc = track_loop_launch(c, n_ch, d, d + o.o_aux, ms0, n_ms, iq_log ? (int16_t*)(d + o.o_iq) : nullptr,
                            nav_log ? (int8_t*)(d + o.o_nav) : nullptr, (gpsb_loop_result*)(d + o.o_res), flags);
     if (rc) return bail(rc);

@@ -185,7 +185,10 @@ __device__ __forceinline__ int frame_present(const StreamGate& gate, uint32_t ms
 //   6 carrier thread: wait at barrier A   7..9 phase 2 split   10, 11 carrier thread at slot index 0   12 phase-1 redos
 // kExp: timing experiments only (results wrong): bit 0 skips phase 1, bit 1 skips the carrier filters, bit 2 the DLL
 // kStream: streaming-ingest build (the resident build carries none of its checks)
-template <bool kProf, int kExp = 0, bool kStream = false>
+// kWalk: the slot-phase walk (lc_walk_*) is compiled in.  A run whose channels all have it switched off, sit at slot
+// phase 0 and have no idle gap pending takes the build without it (the host checks the records; a record that does
+// not qualify makes that build refuse the channel with LC_STOP_STATE).
+template <bool kProf, int kExp = 0, bool kStream = false, bool kWalk = true>
 __global__ void __maxnreg__(96)      // measured: 96 registers 1.068 us per ms, uncapped (123) 1.087, 80: 1.124
 k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uint32_t* __restrict__ codes,
             const uint32_t* __restrict__ signal, uint32_t ring_ms, uint32_t ms0, uint32_t n_ms,
@@ -224,6 +227,7 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
     const bool plain = worker && wtid < (kWords - 2) / kLoopNw;   // words 1..510; the last worker thread(s) have no words left
     uint32_t edge_counts = 0u;
     int edge_w = 0, edge_neg = 0;
+    const int edge_role = lane / 3, edge_arm = lane % 3;    // an edge lane's entry: role 0..3, arm 0..2 (ec_epl_edge_entry)
 
     if (kProf) for (int i = tid; i < kLoopWarps * 4 * 8; i += kLoopThreads) tl_buf[i] = 0u;
     copy_words(&sm.ch, chans + chn, tid, kLoopThreads);
@@ -265,7 +269,9 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
             }
             // a run that starts inside an idle gap of the slot-phase walk (lc_walk_*): no carrier plan for that
             // millisecond - the gap's last millisecond plans the first one behind it, in the loop
-            if (lc_walk_idle(sm.aux.skip_ms, sm.aux.skip_len, ms0)) {
+            if (!kWalk && (sm.aux.walk_enable || sm.aux.slot_phase || sm.aux.skip_len)) {
+                sm.stop = LC_STOP_STATE;                    // the host picked the build without the walk for a walking channel
+            } else if (kWalk && lc_walk_idle(sm.aux.skip_ms, sm.aux.skip_len, ms0)) {
                 sm.rq.sv_slot = sm.ch.prn;
                 sm.rq.ms_index = ms0;
                 sm.rq.acc0 = sm.rq.step32 = 0u;
@@ -285,8 +291,8 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
     uint32_t w_phase = sm.aux.slot_phase, w_skip_ms = sm.aux.skip_ms, w_skip_len = sm.aux.skip_len;
 #define GPSB_WALK_STEP_END()                                                                     \
     do {                                                                                         \
-        if (idle && !idle_next) w_phase = lc_walk_phase_after(ms);                               \
-        if (index == LC_SLOT_LEN - 2) {                                                          \
+        if (kWalk && idle && !idle_next) w_phase = lc_walk_phase_after(ms);                      \
+        if (kWalk && index == LC_SLOT_LEN - 2) {                                                 \
             w_skip_ms = *(volatile uint32_t*)&sm.aux.skip_ms;                                    \
             w_skip_len = *(volatile uint8_t*)&sm.aux.skip_len;                                   \
         }                                                                                        \
@@ -296,7 +302,7 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
         const uint32_t off[3] = {sm.rq.off_e, sm.rq.off_p, sm.rq.off_l};
         mbar_wait(&sm.full[0], 0u);
         if (plain) ec_epl_phase1(sm.S[0], sm.RX[sm.rq.off_bits & 7u], off, w0, kLoopNw, &part, sm.top_lut);
-        else edge_counts = ec_epl_edge_phase1(sm.S[0], sm.RX[sm.rq.off_bits & 7u], off, lane, &edge_w, &edge_neg);
+        else edge_counts = ec_epl_edge_entry(sm.S[0], sm.RX[sm.rq.off_bits & 7u], (&sm.rq.off_e)[edge_arm], edge_role, &edge_w, &edge_neg);
     }
     __syncthreads();                                        // raw buffer 0 has been consumed
     // Streaming runs: a frame that is not there in time ends the run.  The code thread raises the next millisecond's
@@ -345,7 +351,8 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
     for (; m < n_ms && stop == LC_STOP_NONE; m++) {
         const uint32_t ms = ms0 + m;
         const uint32_t b = m & 1u;
-        const uint8_t index = (uint8_t)((ms + w_phase) & (LC_SLOT_LEN - 1u));   // control threads only (w_phase is theirs)
+        const uint8_t index = kWalk ? (uint8_t)((ms + w_phase) & (LC_SLOT_LEN - 1u))   // control threads only (w_phase is theirs)
+                                    : (uint8_t)(ms % LC_SLOT_LEN);
         if (kProf) c0 = clock64();
         if (worker || edge_warp) {                          // phase 2: the carrier phase of each word selects its I and Q count
             GPSB_TL(0);
@@ -353,7 +360,7 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
             if (plain) ec_epl_phase2(sm.rq.acc0, sm.rq.step32, w0, kLoopNw, &part, acc);
             else if (edge) {
                 const uint32_t v = ec_epl_edge_phase2(sm.rq.acc0, sm.rq.step32, edge_w, edge_neg, edge_counts);
-                const int a = lane % 3;
+                const int a = edge_arm;
                 acc[0] = a == 0 ? v : 0u;
                 acc[1] = a == 1 ? v : 0u;
                 acc[2] = a == 2 ? v : 0u;
@@ -394,9 +401,13 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
                 if (kProf) c1 = clock64();
                 GPSB_TL(5);
                 if (sm.stop_at[b ^ 1u] == LC_STOP_NONE && !(kExp & 1)) {      // ordered after the code thread's write by offs_ready
-                    const uint32_t off[3] = {sm.rq.off_e, sm.rq.off_p, sm.rq.off_l};
-                    if (plain) ec_epl_phase1(sm.S[b ^ 1u], sm.RX[sm.rq.off_bits & 7u], off, w0, kLoopNw, &part, sm.top_lut);
-                    else edge_counts = ec_epl_edge_phase1(sm.S[b ^ 1u], sm.RX[sm.rq.off_bits & 7u], off, lane, &edge_w, &edge_neg);
+                    if (plain) {
+                        const uint32_t off[3] = {sm.rq.off_e, sm.rq.off_p, sm.rq.off_l};
+                        ec_epl_phase1(sm.S[b ^ 1u], sm.RX[sm.rq.off_bits & 7u], off, w0, kLoopNw, &part, sm.top_lut);
+                    } else {                                // one load: the offset of this lane's own arm (off_e, off_p, off_l are consecutive)
+                        edge_counts = ec_epl_edge_entry(sm.S[b ^ 1u], sm.RX[sm.rq.off_bits & 7u], (&sm.rq.off_e)[edge_arm], edge_role,
+                                                        &edge_w, &edge_neg);
+                    }
                 }
                 if (kProf && lane == 0) { long long c2 = clock64(); c2 += (long long)((part.C[0][0] + edge_counts) & 0u); pt[13] += c2 - c1; }
                 if (kProf && wtid == 0 && worker) pt[1] += clock64() - c0;
@@ -412,8 +423,8 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
             GPSB_TL(5);
             sm.sums[b ^ 1u] = make_uint4(0u, 0u, 0u, 0u);      // read one ms ago by everybody; filled again after the workers have seen offs_ready
             if (next_frame) consumed++;                         // the workers wait for frame m+1 this millisecond
-            const bool idle = lc_walk_idle(w_skip_ms, w_skip_len, ms);            // the channel leaves this millisecond out
-            const bool idle_next = lc_walk_idle(w_skip_ms, w_skip_len, ms + 1u);
+            const bool idle = kWalk && lc_walk_idle(w_skip_ms, w_skip_len, ms);            // the channel leaves this millisecond out
+            const bool idle_next = kWalk && lc_walk_idle(w_skip_ms, w_skip_len, ms + 1u);
             if (idle) iq[0] = iq[1] = iq[2] = iq[3] = iq[4] = iq[5] = 0;          // ... the sums are nobody's
             const bool degenerate = !idle && lc_dll_is_degenerate(iq);   // 0/0 in the DLL: x86 and the GPU disagree on NaN bits, host finishes this ms
             if (degenerate) sm.stop_at[b ^ 1u] = LC_STOP_DLL_NAN;
@@ -459,8 +470,8 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
             load_sums(&sm.sums[b], iq);
             if (kProf) iq[2] += (int16_t)(clock64() & 0);
             GPSB_TL(5);
-            const bool idle = lc_walk_idle(w_skip_ms, w_skip_len, ms);            // the channel leaves this millisecond out
-            const bool idle_next = lc_walk_idle(w_skip_ms, w_skip_len, ms + 1u);
+            const bool idle = kWalk && lc_walk_idle(w_skip_ms, w_skip_len, ms);            // the channel leaves this millisecond out
+            const bool idle_next = kWalk && lc_walk_idle(w_skip_ms, w_skip_len, ms + 1u);
             const bool live = !idle && !lc_dll_is_degenerate(iq);
             if (live) {
                 // period_sync_ok_flag is written by the nav thread at slot index 3 and read here at slot index 0
@@ -492,8 +503,8 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
             int16_t iq[6];
             load_sums(&sm.sums[b], iq);
             int8_t bit = -1;
-            const bool idle = lc_walk_idle(w_skip_ms, w_skip_len, ms);            // the channel leaves this millisecond out
-            const bool idle_next = lc_walk_idle(w_skip_ms, w_skip_len, ms + 1u);
+            const bool idle = kWalk && lc_walk_idle(w_skip_ms, w_skip_len, ms);            // the channel leaves this millisecond out
+            const bool idle_next = kWalk && lc_walk_idle(w_skip_ms, w_skip_len, ms + 1u);
             if (!idle && !lc_dll_is_degenerate(iq)) {
                 const int refine = lc_nav_new_code(&sm.ch, &sm.aux, index, iq[2], ms);
                 bit = sm.aux.last_nav_bit;
@@ -502,7 +513,7 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
                     lc_refine_edge(&sm.ch, &sm.aux);
                 }
                 lc_snr_update(&sm.ch, &sm.aux, iq[2], iq[3]);
-                if (index == LC_SLOT_LEN - 1) lc_walk_policy(&sm.ch, &sm.aux, ms);     // end of a slot: move the slots?
+                if (kWalk && index == LC_SLOT_LEN - 1) lc_walk_policy(&sm.ch, &sm.aux, ms);     // end of a slot: move the slots?
             }
             if (idle && !idle_next) {                       // last millisecond of an idle gap: the next one starts a slot
                 sm.aux.slot_phase = lc_walk_phase_after(ms);

@@ -70,6 +70,11 @@ def reference(ref, sig, prn, rep, n_track_ms, walk=True, served=True):
     Returns (final channel record bytes, iq, nav, state after acquisition)."""
     from oracle_lib import RefWalk
     lib = ref.lib
+    # The reference keeps the best pre-track correlation of the slot in progress in two file-scope variables shared by
+    # all channels (tracking.c:33-34) and never resets the phase: a satellite run in a process that ran another one before
+    # would inherit them.  Every satellite starts from a clean process image, like a channel of this library does.
+    for name in ("pre_track_best_corr_value", "pre_track_best_corr_phase"):
+        C.c_uint16.in_dll(lib, name).value = 0
     chans = ref.channels(1)
     ch = ref.channel_at(chans, 0)
     ref.channel_init(ch, prn, 0)
