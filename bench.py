@@ -175,6 +175,7 @@ def _ref_worker(args):
     lib.ref_track_time.argtypes = [C.c_void_p] * 2 + [C.c_uint32] * 2
 
     def arm():
+        C.CDLL(None).srand(1)      # the reference's false-lock kicker draws from the process-wide rand(): a fresh process' state
         ref.channel_init(ch, prn, 0)
         st = ref.snapshot(ch)
         # start locked (GPS_ACQ_DONE / GPS_TRACKING_RUN) on the true code phase and Doppler so that all n_ms

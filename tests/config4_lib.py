@@ -75,6 +75,9 @@ def reference(ref, sig, prn, rep, n_track_ms, walk=True, served=True):
     # would inherit them.  Every satellite starts from a clean process image, like a channel of this library does.
     for name in ("pre_track_best_corr_value", "pre_track_best_corr_phase"):
         C.c_uint16.in_dll(lib, name).value = 0
+    # ... and its false-lock kicker draws from the process-wide rand() (tracking.c:316), where a channel of this library
+    # has its own generator, seeded like a fresh process (core/gpsb_loop_core.h, lc_rand31_*)
+    C.CDLL(None).srand(1)
     chans = ref.channels(1)
     ch = ref.channel_at(chans, 0)
     ref.channel_init(ch, prn, 0)
