@@ -100,6 +100,23 @@ def truth_requests(scene, nco_step32):
     return rq.reshape(-1), fo.reshape(-1), fine_f.reshape(-1)
 
 
+# ----------------------------------------------------------------------------- ncu evidence
+def profile_traffic(name: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum (bytes per launch) of the ncu --set full capture summarised in
+    profiles/<name> (tools/ncu_summary.py), or None when the file or the metrics are missing."""
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    total, seen = 0.0, 0
+    try:
+        for line in (REPO / "profiles" / name).read_text().splitlines():
+            f = line.split()
+            if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and f[2] in scale:
+                total += float(f[1].replace(",", "")) * scale[f[2]]
+                seen += 1
+    except OSError:
+        return None
+    return int(total) if seen == 2 else None
+
+
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler:
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -569,6 +586,20 @@ def run_gpu_arm(args) -> None:
         long_ms[arms] = float(np.mean([a.elapsed_time(b) for a, b in ev]))
         if arms == 1:
             long_prompt = d_out_long.cpu().numpy()[:2 * n_long].reshape(n_long, 2).copy()
+            long_eng.set_epl_batch_kernel(1)                     # the register-staged kernel this one replaced, for comparison
+            for _ in range(warm):
+                fn(n_long, d_rq_long.data_ptr(), d_out_long.data_ptr())
+            barrier()
+            ev = events(steps)
+            for k in range(steps):
+                flush.fill_(k)
+                ev[k][0].record(stream)
+                fn(n_long, d_rq_long.data_ptr(), d_out_long.data_ptr())
+                ev[k][1].record(stream)
+            barrier()
+            long1_reg_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+            assert np.array_equal(d_out_long.cpu().numpy()[:2 * n_long].reshape(n_long, 2), long_prompt), "the two batch kernels disagree"
+            long_eng.set_epl_batch_kernel(0)
     # config 1 as the reference runs it: ONE cell.  Kernel time of a one-cell launch (events) and the latency of the
     # synchronous host call gpsb_prompt_iq (request up, launch, result down).
     ev = events(50)
@@ -822,9 +853,9 @@ def run_gpu_arm(args) -> None:
             "clocks": clk,
             "roofline": {"kernel": "k_track_run (1 launch per step, %d CTAs: one per satellite)" % n_ch, "bound": "hbm",
                          "achieved": loop_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": loop_achieved / hbm_peak,
-                         "traffic": 2134784 if (N_MS == 1000 and n_ch == 4) else None,
+                         "traffic": profile_traffic("k_track_run_r2.txt") if (N_MS == 1000 and n_ch == 4) else None,
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this "
-                                           "launch (profiles/k_track_run_r1.txt)",
+                                           "launch, read from profiles/k_track_run_r2.txt",
                          "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                          "algorithmic_bytes_per_launch": loop_bytes, "kernel_ms": loop_kernel_ms,
                          "us_per_ms_of_signal": loop_kernel_ms * 1e3 / N_MS,
@@ -862,7 +893,8 @@ def run_gpu_arm(args) -> None:
                                           "algorithmic_bytes_per_launch": batch_bytes}},
             "config1_batched": {
                 "what": "PRN 1, +2000 Hz, byte offset 100, bits 0: one prompt correlation per millisecond of a %d-ms recording "
-                        "(%.0f MB, larger than L2) in ONE k_epl_batch launch per rank; 'epl' = all three arms of the same cells"
+                        "(%.0f MB, larger than L2) in ONE k_epl_batch_tma launch per rank (frames through a TMA ring in shared "
+                        "memory); 'epl' = all three arms of the same cells"
                         % (n_long, n_long * 2048 / 1e6),
                 "cells": n_long * world,
                 "single_cell": {"what": "one cell, as the reference runs config 1", "kernel_us": one_cell_kernel_us,
@@ -870,15 +902,19 @@ def run_gpu_arm(args) -> None:
                                 "api": "gpsb_prompt_iq(n = 1): request H2D, k_epl_batch<1> launch, result D2H, synchronous"},
                 "prompt": {"kernel_ms": long1_ms, "cells_per_s": n_long * world / (long1_ms * 1e-3),
                            "arm_samples_per_s": n_long * world * MS_SAMPLES / (long1_ms * 1e-3),
-                           "roofline": {"kernel": "k_epl_batch<1>", "bound": "hbm",
+                           "roofline": {"kernel": "k_epl_batch_tma<1>", "bound": "hbm",
                                         "achieved": n_long * (2046 + 24 + 4) / (long1_ms * 1e-3) / 1e9, "peak": hbm_peak,
                                         "unit": "GB/s", "frac": n_long * (2046 + 24 + 4) / (long1_ms * 1e-3) / 1e9 / hbm_peak,
                                         "algorithmic_bytes_per_launch": n_long * (2046 + 24 + 4),
-                                        "traffic": 833011456 if n_long == 400000 else None,
-                                        "traffic_source": "profiles/k_epl_batch1_r1.txt"}},
+                                        "traffic": profile_traffic("k_epl_batch_tma1_r2.txt") if n_long == 400000 else None,
+                                        "traffic_source": "read from profiles/k_epl_batch_tma1_r2.txt (ncu --set full of this launch)",
+                                        "limit": "issue slots: ALU pipe 70 %, issue active 75 %, XU (POPC) 53 %, scoreboard stalls "
+                                                 "0.4 per issue (profiles/k_epl_batch_tma1_r2.txt); the register-staged kernel it "
+                                                 "replaces waited on its loads (profiles/k_epl_batch1_r1.txt)"},
+                           "register_staged_kernel_ms": long1_reg_ms},
                 "epl": {"kernel_ms": long3_ms, "cells_per_s": n_long * world / (long3_ms * 1e-3),
                         "arm_samples_per_s": n_long * world * ARMS * MS_SAMPLES / (long3_ms * 1e-3),
-                        "roofline": {"kernel": "k_epl_batch<3>", "bound": "hbm",
+                        "roofline": {"kernel": "k_epl_batch_tma<3>", "bound": "hbm",
                                      "achieved": n_long * (2046 + 24 + 12) / (long3_ms * 1e-3) / 1e9, "peak": hbm_peak,
                                      "unit": "GB/s", "frac": n_long * (2046 + 24 + 12) / (long3_ms * 1e-3) / 1e9 / hbm_peak,
                                      "algorithmic_bytes_per_launch": n_long * (2046 + 24 + 12),

@@ -118,6 +118,13 @@ int gpsb_set_realtime(gpsb_ctx* ctx, int enabled);
  * frames streamed from HBM straight into registers - instead of one CTA per cell; 0 = always, UINT32_MAX = never.
  * Both kernels return identical sums. */
 int gpsb_set_epl_batch_min(gpsb_ctx* ctx, uint32_t n_cells);
+/* Two interchangeable, bit-identical forms of that batch kernel:
+ *   GPSB_BATCH_TMA        (default) every warp owns a ring of four 2048-byte frame buffers in shared memory, filled by the
+ *                         TMA engine (one cp.async.bulk per cell, four cells ahead, each on its own mbarrier)
+ *   GPSB_BATCH_REGISTERS  frames loaded straight into registers, one cell ahead (kept for comparison) */
+#define GPSB_BATCH_TMA        0
+#define GPSB_BATCH_REGISTERS  1
+int gpsb_set_epl_batch_kernel(gpsb_ctx* ctx, int kernel);
 /* The prompt arm alone: out[2*i], out[2*i+1] = I, Q of request i at byte offset off_p (off_e / off_l ignored) =
  * gps_generate_prn_data2(off_bits) + gps_shift_to_zero_freq_track(acc0, step32) + ONE gps_correlation_iq
  * (PM/GPS/gps_misc.c:128-145): the reference's single-arm correlation, for long recordings replayed open loop

@@ -504,6 +504,7 @@ struct gpsb_ctx {
     uint32_t* d_schips = nullptr;  // max_sv x 256 words: +-1 chip bytes for the dp4a search
     uint32_t* d_rxt = nullptr;     // max_sv x 16 x 4 x 1040 words: extended replica streams for k_epl_batch
     uint32_t epl_batch_min = 512;  // gpsb_track_epl_dev batches of at least this many cells go to k_epl_batch
+    int epl_batch_kernel = GPSB_BATCH_TMA;   // which of the two batch kernels (gpsb_set_epl_batch_kernel)
     int n_sm = 148;
     int sweep_method = GPSB_SWEEP_DP4A;
     // closed-loop mailbox (mapped pinned host memory, see k_epl_rt / k_epl_session)
@@ -1010,19 +1011,46 @@ static int check_search(const gpsb_ctx* c, uint32_t n, const gpsb_search_req* rq
 }
 
 /* ------------------------------------------------------------------ level 1 */
+}   // extern "C"
+// One warp per cell on a persistent grid: frames through the TMA ring (default) or staged in registers.
+template <int kArms>
+static int launch_batch(gpsb_ctx* c, uint32_t n, const gpsb_epl_req* d_req, int16_t* d_out)
+{
+    const uint32_t want = (n + kBatchThreads / 32 - 1) / (kBatchThreads / 32);
+    if (c->epl_batch_kernel == GPSB_BATCH_TMA) {
+        static bool attr_set[2] = {false, false};
+        if (!attr_set[kArms == 3]) {
+            CU(cudaFuncSetAttribute(k_epl_batch_tma<kArms>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BatchTmaSmem)));
+            attr_set[kArms == 3] = true;
+        }
+        const uint32_t cap = (uint32_t)c->n_sm * (kArms == 3 ? 2 : kTmaCtasPerSm);
+        k_epl_batch_tma<kArms><<<want < cap ? want : cap, kBatchThreads, sizeof(BatchTmaSmem), c->stream>>>(
+            d_req, d_out, c->d_rxt, c->d_signal, c->ring_ms, n);
+        return check_launch(c, kArms == 3 ? "k_epl_batch_tma" : "k_epl_batch_tma<prompt>");
+    }
+    const uint32_t cap = (uint32_t)c->n_sm * kBatchCtasPerSm;
+    k_epl_batch<kArms><<<want < cap ? want : cap, kBatchThreads, 0, c->stream>>>(d_req, d_out, c->d_rxt, c->d_signal, c->ring_ms, n);
+    return check_launch(c, kArms == 3 ? "k_epl_batch" : "k_epl_batch<prompt>");
+}
+extern "C" {
 int gpsb_track_epl_dev(gpsb_ctx* c, uint32_t n, const gpsb_epl_req* d_req, int16_t* d_out)
 {
     if (!c || !d_req || !d_out) return fail(GPSB_ERR_ARG, "gpsb_track_epl_dev: null argument");
     if (n == 0) return GPSB_OK;
     CU(cudaSetDevice(c->device));
     if (n >= c->epl_batch_min) {            // large batches: one warp per cell, persistent grid (gpsb_epl_batch.cuh)
-        const uint32_t want = (n + kBatchThreads / 32 - 1) / (kBatchThreads / 32);
-        const uint32_t cap = (uint32_t)c->n_sm * kBatchCtasPerSm;
-        k_epl_batch<3><<<want < cap ? want : cap, kBatchThreads, 0, c->stream>>>(d_req, d_out, c->d_rxt, c->d_signal, c->ring_ms, n);
-        return check_launch(c, "k_epl_batch");
+        return launch_batch<3>(c, n, d_req, d_out);
     }
     k_epl<<<n, kEplThreads, 0, c->stream>>>(d_req, d_out, c->d_codes, c->d_signal, c->ring_ms);
     return check_launch(c, "k_epl");
+}
+
+int gpsb_set_epl_batch_kernel(gpsb_ctx* c, int kernel)
+{
+    if (!c) return fail(GPSB_ERR_ARG, "null context");
+    if (kernel != GPSB_BATCH_TMA && kernel != GPSB_BATCH_REGISTERS) return fail(GPSB_ERR_ARG, "unknown batch kernel %d", kernel);
+    c->epl_batch_kernel = kernel;
+    return GPSB_OK;
 }
 
 int gpsb_set_epl_batch_min(gpsb_ctx* c, uint32_t n_cells)
@@ -1037,10 +1065,7 @@ int gpsb_prompt_iq_dev(gpsb_ctx* c, uint32_t n, const gpsb_epl_req* d_req, int16
     if (!c || !d_req || !d_out) return fail(GPSB_ERR_ARG, "gpsb_prompt_iq_dev: null argument");
     if (n == 0) return GPSB_OK;
     CU(cudaSetDevice(c->device));
-    const uint32_t want = (n + kBatchThreads / 32 - 1) / (kBatchThreads / 32);
-    const uint32_t cap = (uint32_t)c->n_sm * kBatchCtasPerSm;
-    k_epl_batch<1><<<want < cap ? want : cap, kBatchThreads, 0, c->stream>>>(d_req, d_out, c->d_rxt, c->d_signal, c->ring_ms, n);
-    return check_launch(c, "k_epl_batch<prompt>");
+    return launch_batch<1>(c, n, d_req, d_out);
 }
 
 int gpsb_prompt_iq(gpsb_ctx* c, uint32_t n, const gpsb_epl_req* req, int16_t* out)

@@ -243,4 +243,87 @@ k_epl_batch(const gpsb_epl_req* __restrict__ reqs, int16_t* __restrict__ out, co
     }
 }
 
+
+/* ------------------------------------------------------------------------------------------------------------
+ * k_epl_batch_tma: the same cells, frames fed by the TMA engine into a shared-memory ring.
+ *
+ * The register-staged kernel above keeps ONE frame per warp in flight (16 registers per lane) and is limited by that:
+ * ncu shows it waiting on the scoreboard of those loads with 23 % of the warp slots occupied (102 registers, 2 CTAs
+ * per SM).  Here every warp owns a ring of kTmaStages 2048-byte frame buffers in shared memory; lane 0 issues one
+ * cp.async.bulk per cell, kTmaStages cells ahead, each completing on its own mbarrier (complete_tx), so a warp has
+ * kTmaStages frames in flight at no register cost and three CTAs fit an SM.  The consumer side waits on the stage's
+ * mbarrier, pulls its four 16-byte groups out of shared memory (conflict free: consecutive lanes, consecutive
+ * groups) and runs the very same batch_cell as above, so the two kernels cannot differ in their sums.
+ * Requests: the frame address of a cell depends on its request, so lane 0 keeps the ms_index of the cell it will
+ * fetch next one iteration ahead; the request of the cell being correlated is loaded one cell ahead by all lanes. */
+constexpr int kTmaStages = 4;
+#ifndef GPSB_BATCH_TMA_CTAS
+#define GPSB_BATCH_TMA_CTAS 3
+#endif
+constexpr int kTmaCtasPerSm = GPSB_BATCH_TMA_CTAS;
+constexpr int kTmaWarps = kBatchThreads / 32;
+struct BatchTmaSmem {
+    uint4 frame[kTmaWarps][kTmaStages][GPSB_FRAME_BYTES / 16];     // 8 x 4 x 2 KB
+    unsigned long long full[kTmaWarps][kTmaStages];
+};
+
+template <int kArms>
+__global__ void __launch_bounds__(kBatchThreads, kArms == 3 ? 2 : kTmaCtasPerSm)     // three arms need their 128 registers
+k_epl_batch_tma(const gpsb_epl_req* __restrict__ reqs, int16_t* __restrict__ out, const uint32_t* __restrict__ rxt,
+                const uint32_t* __restrict__ signal, uint32_t ring_ms, uint32_t n)
+{
+    extern __shared__ __align__(128) unsigned char batch_smem_raw[];
+    BatchTmaSmem& sm = *reinterpret_cast<BatchTmaSmem*>(batch_smem_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t warps = (gridDim.x * kBatchThreads) >> 5;
+    const uint32_t c0 = (blockIdx.x * kBatchThreads + threadIdx.x) >> 5;
+    if (c0 >= n) return;                                           // whole warps leave; nothing below is CTA-wide
+    const uint32_t mine = (n - c0 + warps - 1) / warps;            // cells of this warp: c0 + i * warps
+
+    auto sa = [](const void* p) { return (uint32_t)__cvta_generic_to_shared(p); };
+    auto fetch = [&](uint32_t ms_index, int stage) {               // lane 0: one bulk copy of a whole frame
+        const void* src = signal + (size_t)ring_frame(ms_index, ring_ms) * kWords;
+        const uint32_t bar = sa(&sm.full[warp][stage]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)GPSB_FRAME_BYTES) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         sa(&sm.frame[warp][stage][0])),
+                     "l"(src), "r"((uint32_t)GPSB_FRAME_BYTES), "r"(bar)
+                     : "memory");
+    };
+    if (lane == 0) {
+        for (int s = 0; s < kTmaStages; s++)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sa(&sm.full[warp][s])), "r"(1u) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    uint32_t next_ms = 0;                                          // lane 0: ms_index of cell `kTmaStages` ahead
+    if (lane == 0) {
+        for (uint32_t s = 0; s < (uint32_t)kTmaStages && s < mine; s++) fetch(reqs[c0 + s * warps].ms_index, (int)s);
+        if ((uint32_t)kTmaStages < mine) next_ms = reqs[c0 + (uint32_t)kTmaStages * warps].ms_index;
+    }
+    gpsb_epl_req rq = reqs[c0];
+    for (uint32_t i = 0; i < mine; i++) {
+        const uint32_t c = c0 + i * warps;
+        const int stage = (int)(i % (uint32_t)kTmaStages);
+        const gpsb_epl_req rq_next = i + 1 < mine ? reqs[c + warps] : rq;          // in flight during this cell
+        uint32_t ms_after = 0;                                      // lane 0: request word of the fetch after the next one
+        if (lane == 0 && i + kTmaStages + 1 < mine) ms_after = reqs[c + (uint32_t)(kTmaStages + 1) * warps].ms_index;
+        {   // the frame of this cell has landed
+            const uint32_t bar = sa(&sm.full[warp][stage]), parity = (i / (uint32_t)kTmaStages) & 1u;
+            asm volatile(
+                "{\n.reg .pred p;\nW_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra D_%=;\nbra W_%=;\nD_%=:\n}\n" ::"r"(bar),
+                "r"(parity)
+                : "memory");
+        }
+        uint4 f[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) f[k] = sm.frame[warp][stage][lane + 32 * k];
+        __syncwarp();                                               // every lane has its groups: the buffer is free again
+        if (lane == 0 && i + kTmaStages < mine) fetch(next_ms, stage);
+        next_ms = ms_after;
+        batch_cell<kArms>(rq, f, lane, c, out, rxt, signal, ring_ms);
+        rq = rq_next;
+    }
+}
+
 }  // namespace gpsb

@@ -94,6 +94,7 @@ def load_library(path: Path | None = None) -> C.CDLL:
         "gpsb_set_epl_batch_min": (i32, [vp, u32]),
         "gpsb_search_dev": (i32, [vp, u32, vp, vp]),
         "gpsb_sweep_dev": (i32, [vp, vp, u32, vp, u32, u32, u32, u32, vp]),
+        "gpsb_set_epl_batch_kernel": (i32, [vp, i32]),
         "gpsb_comm_unique_id": (i32, [vp]),
         "gpsb_comm_init": (i32, [vp, i32, i32, vp]),
         "gpsb_comm_destroy": (i32, [vp]),
@@ -267,6 +268,10 @@ class Engine:
         res = np.zeros((sv.size, st.size, n_ms), SEARCH_RES)
         self._check(self.lib.gpsb_sweep(self._ctx, _p(sv), sv.size, _p(st), st.size, ms0, n_ms, off_bits, _p(res)))
         return res
+
+    def set_epl_batch_kernel(self, kernel: int) -> None:
+        """0 = TMA ring in shared memory (default), 1 = frames staged in registers (kept for comparison)."""
+        self._check(self.lib.gpsb_set_epl_batch_kernel(self._ctx, kernel))
 
     def set_sweep_method(self, method: int) -> None:
         """0 = direct XOR/popcount, 1 = byte-popcount dp4a correlation (default)."""

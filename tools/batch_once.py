@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """A few k_epl_batch launches at the size of bench.py's config1_batched leg (for ncu captures and quick timing).
-Usage: python tools/batch_once.py [n_ms] [arms]"""
+Usage: python tools/batch_once.py [n_ms] [arms] [kernel: 0 = TMA ring (default), 1 = register-staged]"""
 import sys
 import time
 from pathlib import Path
@@ -18,6 +18,8 @@ eng = Engine(device=0, max_sv=4, ring_ms=n)
 stream = torch.cuda.Stream(device=dev)
 torch.cuda.set_stream(stream)
 eng.set_stream(stream.cuda_stream)
+kernel = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+eng.set_epl_batch_kernel(kernel)
 eng.set_code_prn(1, 1)
 sig = np.random.default_rng(1).integers(0, 256, (n, 2046), dtype=np.uint8)
 eng.upload_signal(0, sig)
@@ -39,5 +41,5 @@ for k in range(8):
     torch.cuda.synchronize()
     ts.append(a.elapsed_time(b))
 t = float(np.median(ts[2:]))
-print("k_epl_batch<%d>: %d cells %.1f us  %.2f Gcells/s  %.0f GB/s" % (arms, n, t * 1e3, n / t / 1e6, n * 2046 / t / 1e6))
+print(("k_epl_batch_tma" if kernel == 0 else "k_epl_batch") + "<%d>: %d cells %.1f us  %.2f Gcells/s  %.0f GB/s" % (arms, n, t * 1e3, n / t / 1e6, n * 2046 / t / 1e6))
 eng.close()
