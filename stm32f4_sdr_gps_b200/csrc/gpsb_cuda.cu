@@ -561,6 +561,9 @@ static const uint32_t kWmSlots = 4096;
 
 static int ensure_stage(gpsb_ctx* c, size_t bytes)
 {
+    // Between gpsb_track_loop_begin and _end the staging buffers hold the loop's channel records and its queued copy back:
+    // no other entry point may write or reallocate them (only gpsb_stream_* may be called then, include/gpsb.h).
+    if (c->loop_open) return fail(GPSB_ERR_STATE, "a tracking loop is open on this context: only gpsb_stream_* until gpsb_track_loop_end");
     if (bytes <= c->stage_cap) return GPSB_OK;
     size_t cap = c->stage_cap ? c->stage_cap : (1u << 16);
     while (cap < bytes) cap *= 2;

@@ -16,6 +16,12 @@
  *     the sliced driver (gps_pos_solve) and the one-shot driver (gpsb_host_fix_once) run the same arithmetic;
  *   - work arrays are members of that record (the reference mallocs them per solve), sized for 32 satellites instead
  *     of GPS_SAT_CNT = 4; with four channels the results are the reference's.
+ *
+ * Provenance: two routines below are RTKLIB-derived in the reference itself and follow it operation for operation,
+ * because bit-exact doubles leave no freedom in the order of operations: fx_orbit (broadcast-ephemeris Kepler
+ * propagation, the reference's eph2pos, RTK/solving.c:1165-1215, RTKLIB ephemeris.c) and fx_lu / fx_lu_solve (Crout LU
+ * with partial pivoting, the reference's ludcmp / lubksb, RTK/solving.c:1348-1405, RTKLIB rtkcmn.c).  RTKLIB is
+ * BSD-2-Clause (T. Takasu); the rest of this file - the state record, the slicing, the drivers - is this project's.
  */
 #include <math.h>
 #include <time.h>
@@ -625,9 +631,14 @@ uint8_t solving_is_busy(void) { return (uint8_t)(g_fx.solving | g_fx.converting)
 
 /* gps_master.c:394-427: twice a second, once every channel holds subframes 1..3, start a fix from the current
  * observations and keep stepping it on the following calls. */
+/* ONE observation array for the solver and the RTCM publisher, as in the reference (obsd, gps_master.c:41): there
+ * gps_master_transmit_obs refreshes it on every idle slot, so a sliced solve in flight sees updated observations
+ * between its slices when RTCM output is on.  Shared here for the same behaviour (host/rtcm.c uses it too). */
+obsd_t hx_obsd[GPSB_FIX_MAX_SATS];
+
 void gps_master_calculate_pos(gps_ch_t* channels)
 {
-    static obsd_t obsd[FX_MAX_SATS];
+    obsd_t* const obsd = hx_obsd;
     fx_state* s = &g_fx;
     if (solving_is_busy()) { gps_pos_solve(obsd); return; }
     const uint32_t now = signal_capture_get_packet_cnt();

@@ -41,6 +41,9 @@ void hx_trk_finish_epl(gps_ch_t* ch, gpsb_aux* aux, uint8_t index, const int16_t
 void hx_nav_new_code(gps_ch_t* ch, gpsb_aux* aux, uint8_t index, int16_t new_i);
 void hx_nav_word_bit(gps_ch_t* ch, uint8_t new_bit);
 
+/* observations shared by the position solver and the RTCM publisher (fix.c), gps_master.c:41 */
+extern obsd_t hx_obsd[];
+
 /* binding (bind.c) */
 int hx_note(int status);
 int hx_stage_frame(const uint8_t* data, uint32_t* frame_ms);

@@ -367,7 +367,7 @@ void sendrtcmnav(gps_ch_t* channel)                           /* obs_publish.c:7
  * the ephemeris goes out as soon as subframe 1 is in, and takes the flags of 2 and 3 with it - reproduced. */
 void gps_master_transmit_obs(gps_ch_t* channels)
 {
-    static obsd_t obsd[GPSB_FIX_MAX_SATS];
+    obsd_t* const obsd = hx_obsd;                  /* the solver's array (gps_master.c:41), see host/fix.c */
     if (!channels || (g_sink_busy && g_sink_busy())) return;
     uint32_t n = gpsb_host_sat_cnt();
     if (n > GPSB_FIX_MAX_SATS) n = GPSB_FIX_MAX_SATS;

@@ -244,17 +244,18 @@ static int host_step(gpsb_rx* rx, uint32_t i, uint32_t ms, int16_t* iq_row, int8
     int16_t iq[6] = {0, 0, 0, 0, 0, 0};
     gpsb_host_set_packet_cnt(ms);
     rx->aux[i].last_nav_bit = -1;
+    const gps_tracking_t before = rx->ch[i].tracking_data;     /* put back if the GPU step fails (see host/track.c) */
     hx_trk_plan(&rx->ch[i], &rx->aux[i], ms, index, p);
     if (p->want == GPSB_WANT_EPL) {
         int rc = gpsb_track_epl(rx->ctx, 1, &p->epl, iq);
-        if (rc != GPSB_OK) return hx_note(rc);
+        if (rc != GPSB_OK) { rx->ch[i].tracking_data = before; return hx_note(rc); }
         hx_trk_finish_epl(&rx->ch[i], &rx->aux[i], index, iq);
         rx_slot_end(rx, i, ms, index);
     } else if (p->want == GPSB_WANT_SEARCH) {
         gpsb_search_res res = {0, 0, 0, 0};
         if (p->search.start < p->search.stop) {
             int rc = gpsb_search(rx->ctx, 1, &p->search, &res);
-            if (rc != GPSB_OK) return hx_note(rc);
+            if (rc != GPSB_OK) { rx->ch[i].tracking_data = before; return hx_note(rc); }
         }
         hx_trk_finish_search(&rx->ch[i], &rx->aux[i], index, &res);
     }

@@ -137,19 +137,26 @@ void gps_tracking_process(gps_ch_t* channel, uint8_t* data, uint8_t index)
     if (!channel) return;
     gpsb_ctx* ctx = gpsb_host_context();
     gpsb_plan plan;
+    /* Planning already moves the channel on (time stamp, carrier NCO, pre-track arming): should the GPU step that
+     * follows fail, the tracking record is put back, so that a failed millisecond counts as one the channel did not see
+     * (the reference cannot fail here; the status is in gpsb_host_last_status()). */
+    const gps_tracking_t before = channel->tracking_data;
     /* the frame goes to ring slot (ms counter mod ring); the plan only needs the number */
     hx_trk_plan(channel, &g_shared_aux, hx_now_ms(), index, &plan);
     if (plan.want == GPSB_WANT_NOTHING) return;
     uint32_t frame;
-    if (hx_stage_frame(data, &frame) != GPSB_OK) return;
+    if (hx_stage_frame(data, &frame) != GPSB_OK) { channel->tracking_data = before; return; }
     if (plan.want == GPSB_WANT_SEARCH) {
         gpsb_search_res res;
         memset(&res, 0, sizeof res);
-        if (plan.search.start < plan.search.stop && hx_note(gpsb_search(ctx, 1, &plan.search, &res)) != GPSB_OK) return;
+        if (plan.search.start < plan.search.stop && hx_note(gpsb_search(ctx, 1, &plan.search, &res)) != GPSB_OK) {
+            channel->tracking_data = before;
+            return;
+        }
         hx_trk_finish_search(channel, &g_shared_aux, index, &res);
     } else {
         int16_t iq[6];
-        if (hx_note(gpsb_track_epl(ctx, 1, &plan.epl, iq)) != GPSB_OK) return;
+        if (hx_note(gpsb_track_epl(ctx, 1, &plan.epl, iq)) != GPSB_OK) { channel->tracking_data = before; return; }
         hx_trk_finish_epl(channel, &g_shared_aux, index, iq);
     }
 }

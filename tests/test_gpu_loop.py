@@ -327,6 +327,30 @@ def test_streaming_run_from_the_2bit_iq_container(golden, ring_ms, chunk):
         ch.free()
 
 
+def test_sweep_scratch_survives_an_iq2_stream(golden):
+    """Round-1 advisor finding: gpsb_stream_push_iq2 used to free the acquisition scratch when it grew its own staging
+    buffer, so a sweep AFTER an iq2-streamed run worked on freed memory.  Cold sweep -> iq2-streamed tracking -> the same
+    sweep again: identical cells (this sequence is also what tools/profile_r2.sh puts under compute-sanitizer)."""
+    from stm32f4_sdr_gps_b200 import Engine, nco_step32
+    from stm32f4_sdr_gps_b200.signal_synth import iq2_from_packed
+    sig = np.ascontiguousarray(golden["scene_signal"][:300])
+    samples = iq2_from_packed(sig)
+    step = np.array([nco_step32(np.float32(4092000 - 5000 + 500 * b)) for b in range(21)], np.uint32)
+    with Engine(device=0, max_sv=211, ring_ms=256) as eng:
+        eng.upload_signal(0, sig[:16])
+        for prn in (5, 14, 20):
+            eng.set_code_prn(prn, prn)
+        first = eng.sweep([5, 14, 20], step, 0, 10)
+        ch = _two_locked_channels(golden)
+        rx = Receiver(eng, ch)
+        rx.track_stream_iq2(0, samples, chunk_ms=32)
+        rx.close()
+        ch.free()
+        eng.upload_signal(0, sig[:16])
+        again = eng.sweep([5, 14, 20], step, 0, 10)
+        assert np.array_equal(first, again)
+
+
 def test_loop_begin_end_call_sequence_errors(host_engine, golden):
     """gpsb_track_loop_begin / _end: a second begin before the end, and an end without a begin, are state errors
     (negative status, message available), never a dead lock; the open loop still ends normally afterwards."""
