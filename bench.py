@@ -724,7 +724,7 @@ def run_gpu_arm(args) -> None:
         eng4.comm_init_torch()
     eng4.upload_signal(0, sig4)
     serve = dict(serve_rank=rank, serve_world=world)
-    ch_w, rx_w, _, _ = c4.product(eng4, sig4, c4.SEARCHED, 400, cold_start_opts=serve)        # warm-up (allocations, NCCL)
+    ch_w, rx_w, _, _ = c4.product(eng4, sig4, c4.SEARCHED, C4_MS, cold_start_opts=serve)      # warm-up: staging buffers at their final size, NCCL
     rx_w.close(); ch_w.free()
     tm4 = {}
     ch4, rx4, rep4, logs4 = c4.product(eng4, sig4, c4.SEARCHED, C4_MS, timers=tm4, cold_start_opts=serve, before_start=barrier)
