@@ -80,3 +80,52 @@ def reduce_max_time(seconds: float, world: int, device=None) -> float:
     t = torch.tensor([seconds], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+# ---- acquisition, round 2: the sweep is sharded by (bin, ms) CELL GROUP, not by satellite (gpsb_sweep_gather) ----------
+# A cell group is one mixed millisecond serving every satellite searched on it, so a rank that owns whole groups keeps
+# whole 8-satellite tiles of the dp4a search whatever the number of ranks is.  These are the index rules of the C ABI
+# (csrc/gpsb_cuda.cu: gpsb_sweep_gather_dev, k_unshard), restated for the CPU tests of the N > 1 path.
+def group_owner(group: int, world: int) -> int:
+    """Rank that computes cell group `group` = bin * n_ms + ms: round-robin."""
+    return group % world
+
+
+def groups_of(rank: int, n_groups: int, world: int) -> np.ndarray:
+    return np.arange(rank, n_groups, world, dtype=np.int64)
+
+
+def group_block(full: np.ndarray, rank: int, world: int) -> np.ndarray:
+    """This rank's dense block of a sweep `full` (n_sv, n_bins, n_ms, 4): rows = its k-th group, padded to the common
+    block size ceil(groups / world); block[k, v] = the triple of satellite v on group rank + k * world."""
+    n_sv, n_bins, n_ms = full.shape[:3]
+    n_groups = n_bins * n_ms
+    n_local = (n_groups + world - 1) // world
+    flat = full.reshape(n_sv, n_groups, -1)
+    block = np.zeros((n_local, n_sv, flat.shape[-1]), full.dtype)
+    mine = groups_of(rank, n_groups, world)
+    block[:len(mine)] = flat[:, mine].transpose(1, 0, 2)
+    return block
+
+
+def unshard_groups(blocks, n_sv: int, n_bins: int, n_ms: int) -> np.ndarray:
+    """The all-gathered blocks (blocks[r] = rank r's group_block) -> the (n_sv, n_bins, n_ms, 4) grid: k_unshard."""
+    world = len(blocks)
+    first = np.asarray(blocks[0])
+    grid = np.zeros((n_sv, n_bins * n_ms, first.shape[-1]), first.dtype)
+    for g in range(n_bins * n_ms):
+        grid[:, g] = np.asarray(blocks[g % world])[g // world]
+    return grid.reshape(n_sv, n_bins, n_ms, -1)
+
+
+def gather_groups(local_block: np.ndarray, world: int):
+    """All-gather of the per-rank group blocks over torch.distributed (gloo in the CPU tests; the product exchanges them
+    with ncclAllGather inside gpsb_sweep_gather).  Returns the list of blocks, rank order."""
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return [local_block]
+    t = torch.from_numpy(np.ascontiguousarray(local_block).view(np.int16).astype(np.int32))   # gloo has no 16-bit integers
+    parts = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(parts, t)
+    return [p.numpy().astype(np.int16).view(np.uint16).reshape(local_block.shape) for p in parts]

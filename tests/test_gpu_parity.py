@@ -471,3 +471,20 @@ def test_epl_batch_full_size_properties(oracle):
             want = oracle.epl_explicit(chips[int(rq["sv_slot"][i])], sig[i], int(rq["acc0"][i]), int(rq["step32"][i]),
                                        int(rq["off_e"][i]), int(rq["off_p"][i]), int(rq["off_l"][i]), int(rq["off_bits"][i]))
             assert np.array_equal(epl[i], want), (i, rq[i])
+
+
+def test_sweep_gather_single_rank_equals_sweep(engine, golden):
+    """gpsb_sweep_gather without a communicator (one rank): the group-sharded launch (dense per-rank block) + k_unshard
+    must give exactly gpsb_sweep's grid - for tiles of 8, 4 and 1 satellites and a sub-byte shift.  (Two and eight
+    ranks: bench.py asserts the gathered grid equal to the one-GPU sweep in every run.)"""
+    from stm32f4_sdr_gps_b200 import nco_step32
+    sig = golden["scene_signal"]
+    engine.upload_signal(0, sig[:12])
+    for prn in range(1, 12):
+        engine.set_code_prn(prn, prn)
+    step = np.array([nco_step32(np.float32(4092000 - 2500 + 500 * b)) for b in range(11)], np.uint32)
+    for svs, bits in ((list(range(1, 12)), 0), ([5, 14 % 11 + 1, 3], 5), ([7], 0)):
+        want = engine.sweep(svs, step, 1, 10, bits)
+        got = engine.sweep_gather(svs, step, 1, 10, bits)
+        assert np.array_equal(got, want), (svs, bits)
+    assert engine.comm_size == 1

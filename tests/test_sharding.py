@@ -84,3 +84,51 @@ def test_single_rank_roundtrip():
     full = _fake_cells(7, 3, 2)
     block = sharding.pack_local(full, 7, 0, 1)
     assert np.array_equal(sharding.gather_sweep(block, 7, 1), full)
+
+
+# ---- round 2: the sweep sharded by (bin, ms) cell group (gpsb_sweep_gather), index rules on the CPU ---------------------
+def _group_worker(rank, world, port, n_sv, n_bins, n_ms, q):
+    try:
+        import torch.distributed as dist
+        os.environ["MASTER_ADDR"] = "127.0.0.1"
+        os.environ["MASTER_PORT"] = str(port)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        full = _fake_cells(n_sv, n_bins, n_ms)
+        block = sharding.group_block(full, rank, world)           # what this rank's sharded sweep writes (dense block)
+        got = sharding.unshard_groups(sharding.gather_groups(block, world), n_sv, n_bins, n_ms)
+        q.put((rank, bool(np.array_equal(got, full)), int(len(sharding.groups_of(rank, n_bins * n_ms, world)))))
+        dist.destroy_process_group()
+    except Exception as e:
+        q.put((rank, False, repr(e)))
+
+
+@pytest.mark.parametrize("shape", [(32, 21, 10), (5, 29, 10), (3, 1, 1)])
+def test_two_rank_gloo_group_sharded_sweep(shape):
+    """Two ranks each compute their share of the (bin, ms) cell groups, all-gather the dense blocks and permute them
+    into the (sv, bin, ms) grid: every rank ends up with the whole sweep.  (21 x 10 = 210 groups -> 105 each; 1 group
+    -> one rank idle with a padded block.)"""
+    import torch.multiprocessing as mp
+    n_sv, n_bins, n_ms = shape
+    ctx = mp.get_context("fork")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_group_worker, args=(r, 2, port, n_sv, n_bins, n_ms, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=60) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(r[1] is True for r in res), res
+    assert res[0][2] + res[1][2] == n_bins * n_ms and abs(res[0][2] - res[1][2]) <= 1
+
+
+def test_group_sharding_rules():
+    for world in (1, 2, 3, 4, 8):
+        full = _fake_cells(9, 7, 5)
+        blocks = [sharding.group_block(full, r, world) for r in range(world)]
+        assert len({b.shape for b in blocks}) == 1                                   # equal blocks: all_gather needs that
+        assert np.array_equal(sharding.unshard_groups(blocks, 9, 7, 5), full)
+        owned = np.concatenate([sharding.groups_of(r, 35, world) for r in range(world)])
+        assert sorted(owned.tolist()) == list(range(35))
+        assert all(sharding.group_owner(int(g), world) == r for r in range(world) for g in sharding.groups_of(r, 35, world))
