@@ -488,3 +488,39 @@ def test_sweep_gather_single_rank_equals_sweep(engine, golden):
         got = engine.sweep_gather(svs, step, 1, 10, bits)
         assert np.array_equal(got, want), (svs, bits)
     assert engine.comm_size == 1
+
+
+def _config3_ref_cells(args):
+    prn, bits = args
+    from oracle_lib import Reference
+    from stm32f4_sdr_gps_b200.signal_synth import config3_scene, synthesize
+    ref = Reference()
+    sig = _config3_ref_cells.sig
+    chans = ref.channels(1)
+    ref.channel_init(ref.channel_at(chans, 0), prn, 0)
+    return ref.sweep_cells(chans, 1, sig, sig.shape[0], -5000, 500, 21, bits)[0]
+
+
+def test_config3_every_cell_of_both_grids_equals_the_reference(reference):
+    """BASELINE configs[2] at its stated size: 32 PRNs x 21 bins (-5000 .. +5000 Hz) x 10 ms = 6720 cells, ALL of them,
+    on the reference's 2046-phase grid (sub-byte shift 0) and on one sub-byte shift of the 16368-phase grid (shift 3):
+    {max, first argmax, average} equal the unmodified reference's gps_generate_prn_data2 + gps_shift_to_zero_freq +
+    correlation_search (oracle/_ref), cell by cell."""
+    import multiprocessing as mp
+    import os
+    from stm32f4_sdr_gps_b200 import Engine, nco_step32
+    from stm32f4_sdr_gps_b200.signal_synth import config3_scene, synthesize
+    sig = synthesize(config3_scene(n_ms=10))
+    _config3_ref_cells.sig = sig
+    step = np.array([nco_step32(np.float32(4092000 - 5000 + 500 * b)) for b in range(21)], np.uint32)
+    with Engine(device=0, max_sv=40, ring_ms=16) as eng:
+        eng.upload_signal(0, sig)
+        for prn in range(1, 33):
+            eng.set_code_prn(prn, prn)
+        got = {bits: eng.sweep(np.arange(1, 33), step, 0, 10, bits) for bits in (0, 3)}
+    with mp.get_context("fork").Pool(min(32, os.cpu_count() or 1)) as pool:
+        for bits in (0, 3):
+            want = np.stack(pool.map(_config3_ref_cells, [(prn, bits) for prn in range(1, 33)]))
+            g = np.stack([got[bits]["max"], got[bits]["phase"], got[bits]["avg"]], axis=-1)
+            bad = np.argwhere((g != want).any(axis=-1))
+            assert g.shape == (32, 21, 10, 3) and len(bad) == 0, (bits, len(bad), bad[:3].tolist())
