@@ -101,7 +101,8 @@ __device__ __forceinline__ void batch_cell(const gpsb_epl_req& rq, const uint4 (
 {
     const uint32_t* __restrict__ rx = rxt + ((size_t)rq.sv_slot * kRxtShifts + (rq.off_bits & 15u)) * (kRxtCopies * kRxtWords);
     const uint32_t offs[3] = {kArms == 3 ? rq.off_e : rq.off_p, rq.off_p, rq.off_l};
-    uint32_t acc_i[kArms], acc_q[kArms];
+    uint32_t acc[kArms];            // packed I | Q << 16 (a whole millisecond is at most 16368 per component)
+    uint32_t acc_q[kArms];          // three arms: Q apart until the end (measured: the packed form costs them 3 %)
     // Replica run per arm: data word w meets the stream at byte 4w - off + 2046 (RXT spans two periods, so there is no
     // wrap to test for); the sub-word shift is the same for every word of the cell.  A lane's group of four data words
     // needs five consecutive stream words: four by one aligned 128-bit load from the copy of the stream displaced by
@@ -112,7 +113,7 @@ __device__ __forceinline__ void batch_cell(const gpsb_epl_req& rq, const uint4 (
     uint32_t r4[kArms][4];
 #pragma unroll
     for (int a = 0; a < kArms; a++) {
-        acc_i[a] = acc_q[a] = 0u;
+        acc[a] = acc_q[a] = 0u;
         const int p = 16 * lane - (int)offs[kArms == 3 ? a : 1] + (int)GPSB_MS_BYTES;
         sh[a] = ((uint32_t)p & 3u) * 8u;
         const int first = p >> 2, copy = first & 3;
@@ -136,12 +137,15 @@ __device__ __forceinline__ void batch_cell(const gpsb_epl_req& rq, const uint4 (
             r[a][0] = rr[a][k].x; r[a][1] = rr[a][k].y; r[a][2] = rr[a][k].z; r[a][3] = rr[a][k].w;
             r[a][4] = r4[a][k];
         }
-        uint32_t nco = rq.acc0 + (uint32_t)w0 * rq.step32;
+        // The ALU pipe is what bounds this kernel (70 % busy, profiles/k_epl_batch_tma1_r2.txt); multiply-adds issue on the
+        // FMA pipe, so the NCO word of every data word and the Q half of the packed sum are formed by IMAD.
+        uint32_t nco_run = rq.acc0 + (uint32_t)w0 * rq.step32;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             uint32_t cp, sp;
+            const uint32_t nco = kArms == 1 ? ((uint32_t)(w0 + j) * rq.step32 + rq.acc0) : nco_run;
+            nco_run += rq.step32;
             quadrant_patterns(nco, cp, sp);
-            nco += rq.step32;
 #pragma unroll
             for (int a = 0; a < kArms; a++) {
                 const uint32_t win = __funnelshift_r(r[a][j], r[a][j + 1], sh[a]);
@@ -153,14 +157,16 @@ __device__ __forceinline__ void batch_cell(const gpsb_epl_req& rq, const uint4 (
                     xi = lane == 31 ? (win & keep) : xi;
                     xq = lane == 31 ? (win & keep) : xq;
                 }
-                acc_i[a] += (uint32_t)__popc(xi);
-                acc_q[a] += (uint32_t)__popc(xq);
+                acc[a] += (uint32_t)__popc(xi);
+                if (kArms == 1) acc[a] = (uint32_t)__popc(xq) * 65536u + acc[a];
+                else acc_q[a] += (uint32_t)__popc(xq);
             }
         }
     }
-    uint32_t acc[kArms];
+    if (kArms != 1) {
 #pragma unroll
-    for (int a = 0; a < kArms; a++) acc[a] = acc_i[a] + (acc_q[a] << 16);
+        for (int a = 0; a < kArms; a++) acc[a] += acc_q[a] << 16;
+    }
 
     // Odd offsets 2k+1 skip the replica words whose data bytes are {2045, 0} and {off-2, off-1} (gps_misc.c:59-89).
     // Byte 2045 is handled above; edge lanes take back what the loop counted for the other three: role 0 byte 0,
@@ -256,7 +262,10 @@ k_epl_batch(const gpsb_epl_req* __restrict__ reqs, int16_t* __restrict__ out, co
  * groups) and runs the very same batch_cell as above, so the two kernels cannot differ in their sums.
  * Requests: the frame address of a cell depends on its request, so lane 0 keeps the ms_index of the cell it will
  * fetch next one iteration ahead; the request of the cell being correlated is loaded one cell ahead by all lanes. */
-constexpr int kTmaStages = 4;
+#ifndef GPSB_BATCH_TMA_STAGES
+#define GPSB_BATCH_TMA_STAGES 4
+#endif
+constexpr int kTmaStages = GPSB_BATCH_TMA_STAGES;
 #ifndef GPSB_BATCH_TMA_CTAS
 #define GPSB_BATCH_TMA_CTAS 3
 #endif
