@@ -87,6 +87,7 @@
 #define LC_STOP_STATE      1      /* channel is not in GPS_TRACKING_RUN: nothing was done for that ms */
 #define LC_STOP_DLL_NAN    2      /* early+late power is zero: sums delivered, filters not run */
 #define LC_STOP_STARVED    3      /* streaming run: the producer did not deliver a frame in time; done_ms are complete */
+#define LC_STOP_PRE_DONE   4      /* k_pretrack_run: pre-track settled in millisecond done_ms - 1, the channel is in GPS_PRE_TRACK_DONE */
 
 /* glibc's default rand(): TYPE_3 additive feedback x^31 + x^3 + 1 over 32-bit words (stdlib/random_r.c) */
 typedef struct gpsb_rand31 {
@@ -357,6 +358,85 @@ LC_FN void lc_trk_plan_run(gps_ch_t* ch, uint32_t now, uint32_t frame_ms, gpsb_e
 {
     lc_plan_carrier(&ch->tracking_data, ch->prn, now, frame_ms, rq);
     lc_plan_code(&ch->tracking_data, rq);
+}
+
+/* ------------------------------------------------------------------------------------------ pre-track */
+#define LC_PRE_TRACK_ZONE    30                                   /* GPS_PRE_TRACK_ZONE, tracking.c:17 */
+#define LC_PRE_TRACK_PER_MS  (LC_PRE_TRACK_ZONE / LC_SLOT_LEN)    /* 7 offsets per ms, tracking.c:20 */
+
+/* tracking.c:52-72: load the acquisition result into a +-15 half-chip pre-track window */
+LC_FN void lc_pre_arm(gps_ch_t* ch)
+{
+    gps_tracking_t* t = &ch->tracking_data;
+    uint16_t lo = (uint16_t)(ch->acq_data.found_code_phase - LC_PRE_TRACK_ZONE / 2);
+    uint16_t hi = (uint16_t)(ch->acq_data.found_code_phase + LC_PRE_TRACK_ZONE / 2);
+    if (lo > LC_HALF_CHIPS) lo = 0;
+    if (hi > LC_HALF_CHIPS) hi = LC_HALF_CHIPS;
+    t->code_search_start = lo;
+    t->code_search_stop = hi;
+    t->if_freq_offset_hz = (float)ch->acq_data.found_freq_offset_hz;
+    t->pre_track_count = 0;
+    for (unsigned i = 0; i < PRE_TRACK_POINTS_MAX_CNT; i++) t->pre_track_phases[i] = 0;
+    t->state = GPS_PRE_TRACK_RUN;
+}
+
+/* tracking.c:411-415: the seven offsets of slot index `index` (0..3); *last is exclusive */
+LC_FN void lc_pre_window(const gps_tracking_t* t, uint8_t index, uint16_t* first, uint16_t* last)
+{
+    unsigned lo = (uint16_t)(t->code_search_start + index * LC_PRE_TRACK_PER_MS);
+    unsigned hi = (uint16_t)(lo + LC_PRE_TRACK_PER_MS);
+    if (hi > LC_HALF_CHIPS) hi = LC_HALF_CHIPS;
+    *first = (uint16_t)lo;
+    *last = (uint16_t)hi;
+}
+
+/* tracking.c:459-499: most frequent phase among the collected slot winners (longest run of equal values after
+ * sorting; a phase of 0 means "nothing found").  The reference sorts with qsort; any sort of plain integers leaves
+ * the same array behind, so an insertion sort (at most 30 values) serves the host and the device alike. */
+LC_FN void lc_pre_settle(gps_ch_t* ch, uint8_t n)
+{
+    gps_tracking_t* t = &ch->tracking_data;
+    for (uint8_t i = 1; i < n; i++) {
+        const uint16_t v = t->pre_track_phases[i];
+        int k = (int)i - 1;
+        for (; k >= 0 && t->pre_track_phases[k] > v; k--) t->pre_track_phases[k + 1] = t->pre_track_phases[k];
+        t->pre_track_phases[k + 1] = v;
+    }
+    uint8_t run = 0;
+    uint16_t best_run = 0, winner = 0;
+    for (uint8_t i = 1; i < n; i++) {
+        if (t->pre_track_phases[i] == t->pre_track_phases[i - 1]) {
+            run++;
+        } else {
+            if (run > best_run) { best_run = run; winner = t->pre_track_phases[i - 1]; }
+            run = 0;
+        }
+    }
+    if (run > best_run) { best_run = run; winner = t->pre_track_phases[n - 1]; }
+    if (winner) {
+        t->code_phase_fine = (float)(winner * LC_FINE_PER_HALFCHIP);
+        t->state = GPS_PRE_TRACK_DONE;
+    }
+}
+
+/* tracking.c:417-449.  (max, phase) = the window's maximum and its first position: scanning the window with a strict
+ * '>' against the running best is the same as comparing the window maximum once. */
+LC_FN void lc_pre_finish(gps_ch_t* ch, gpsb_aux* aux, uint8_t index, uint16_t max, uint16_t phase)
+{
+    gps_tracking_t* t = &ch->tracking_data;
+    if ((int16_t)max > (int16_t)aux->pre_best_value) {
+        aux->pre_best_value = max;
+        aux->pre_best_phase = phase;
+    }
+    if (index != LC_SLOT_LEN - 1) return;
+    t->pre_track_phases[t->pre_track_count] = aux->pre_best_phase;   /* note: the phase is NOT reset per slot */
+    t->pre_track_count++;
+    if (t->pre_track_count > PRE_TRACK_POINTS_MAX_CNT - 10) lc_pre_settle(ch, t->pre_track_count);
+    if (t->pre_track_count >= PRE_TRACK_POINTS_MAX_CNT) {
+        t->pre_track_count = 0;
+        for (unsigned i = 0; i < PRE_TRACK_POINTS_MAX_CNT; i++) t->pre_track_phases[i] = 0;
+    }
+    aux->pre_best_value = 0;
 }
 
 /* ------------------------------------------------------------------------------------------ loop filters */

@@ -437,6 +437,72 @@ k_search(const gpsb_search_req* __restrict__ reqs, SweepParams sp, gpsb_search_r
     search_window(s, rq.start, rq.stop, res + (res_map ? res_map[blockIdx.x] : blockIdx.x), iq, sk, st);
 }
 
+// ---------------------------------------------------------------------------------- device-resident pre-track
+// k_pretrack_run: gps_pre_track_process (tracking.c:398-450) for a whole run of milliseconds in ONE launch, one CTA per
+// channel: per millisecond the seven-offset search cell of k_search (replica at shift 0 staged once, stateless mixer at
+// the acquisition's Doppler, gps_correlation8 over code_search_start + 7 * index ..), then the slot's running maximum,
+// the collected winners and their mode (core/gpsb_loop_core.h, lc_pre_*: the same source the host path runs) by thread 0.
+// A channel whose pre-track settles in millisecond k is left in GPS_PRE_TRACK_DONE with first[chn] = ms0 + k + 1, which is
+// where k_track_run - launched behind this kernel on the same stream - takes it up; channels that are not in pre-track
+// are not touched (first[chn] = ms0).  Replaces about a hundred per-millisecond launches and host round trips per cold start.
+__global__ void __launch_bounds__(kSearchThreads)
+k_pretrack_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uint32_t* __restrict__ codes,
+               const uint32_t* __restrict__ signal, uint32_t ring_ms, uint32_t ms0, uint32_t n_ms,
+               uint32_t* __restrict__ first)
+{
+    __shared__ CellSmem s;
+    __shared__ uint32_t sk[kSearchThreads / 32];
+    __shared__ int st[kSearchThreads / 32];
+    __shared__ gps_ch_t ch;
+    __shared__ gpsb_aux aux;
+    __shared__ gpsb_search_res cell;
+    __shared__ uint32_t win[4];          // start, stop, step32, go
+    const int tid = threadIdx.x;
+    const uint32_t chn = blockIdx.x;
+    {
+        const uint32_t state = chans[chn].tracking_data.state;      // uniform over the CTA
+        if ((state != GPS_NEED_PRE_TRACK && state != GPS_PRE_TRACK_RUN) || auxs[chn].skip_len != 0) {
+            if (tid == 0) first[chn] = ms0;
+            return;
+        }
+    }
+    copy_words(&ch, chans + chn, tid, kSearchThreads);
+    copy_words(&aux, auxs + chn, tid, kSearchThreads);
+    __syncthreads();
+    stage_replica(s.R, codes + (size_t)ch.prn * kWords, 0u, tid, kSearchThreads);      // tracking.c:404: shift 0
+    uint32_t done = n_ms;
+    for (uint32_t m = 0; m < n_ms; m++) {
+        const uint32_t ms = ms0 + m;
+        const uint8_t index = (uint8_t)((ms + aux.slot_phase) & (LC_SLOT_LEN - 1u));
+        if (tid == 0) {
+            if (ch.tracking_data.state == GPS_NEED_PRE_TRACK) lc_pre_arm(&ch);
+            uint16_t lo, hi;
+            lc_pre_window(&ch.tracking_data, index, &lo, &hi);
+            win[0] = lo;
+            win[1] = hi;
+            win[2] = lc_nco_step32((float)IF_FREQ_HZ + ch.tracking_data.if_freq_offset_hz);
+        }
+        __syncthreads();
+        stage_mix(s.I, s.Q, signal + (size_t)(ms % ring_ms) * kWords, 0u, win[2], tid, kSearchThreads);
+        extend_period<kSearchThreads>(s.I, s.Q, tid);
+        if (tid == 0) cell = gpsb_search_res{0, 0, 0, 0};           // empty window: max 0, phase 0 (gps_misc.c:161-181)
+        if (win[0] < win[1]) search_window(s, win[0], win[1], &cell, nullptr, sk, st);
+        __syncthreads();
+        if (tid == 0) {
+            lc_pre_finish(&ch, &aux, index, cell.max, cell.phase);
+            win[3] = ch.tracking_data.state == GPS_PRE_TRACK_RUN;
+        }
+        __syncthreads();
+        if (!win[3]) {                    // settled (GPS_PRE_TRACK_DONE): tracking starts with the next millisecond
+            done = m + 1;
+            break;
+        }
+    }
+    copy_words(chans + chn, &ch, tid, kSearchThreads);
+    copy_words(auxs + chn, &aux, tid, kSearchThreads);
+    if (tid == 0) first[chn] = ms0 + done;
+}
+
 // ---------------------------------------------------------------------------------- level 0
 __global__ void k_l0_replica(const uint32_t* __restrict__ E, uint32_t bits, uint32_t* __restrict__ out)
 {
@@ -1144,7 +1210,8 @@ void gpsb_track_loop_record_bytes(uint32_t* channel_bytes, uint32_t* aux_bytes)
 }
 
 static int track_loop_launch(gpsb_ctx* c, uint32_t n_ch, void* d_channels, void* d_aux, uint32_t ms0, uint32_t n_ms,
-                             int16_t* d_iq_log, int8_t* d_nav_log, gpsb_loop_result* d_results, uint32_t flags)
+                             int16_t* d_iq_log, int8_t* d_nav_log, gpsb_loop_result* d_results, uint32_t flags,
+                             const uint32_t* d_first = nullptr)
 {
     if (!c || !d_channels || !d_aux || !d_results) return fail(GPSB_ERR_ARG, "gpsb_track_loop_dev: null argument");
     if (n_ch == 0) return GPSB_OK;
@@ -1169,7 +1236,7 @@ static int track_loop_launch(gpsb_ctx* c, uint32_t n_ch, void* d_channels, void*
         CU(cudaMemsetAsync(d_prof, 0, prof_words * sizeof(unsigned long long), c->stream));
         k_track_run<true><<<n_ch, kLoopThreads, 0, c->stream>>>((gps_ch_t*)d_channels, (gpsb_aux*)d_aux, c->d_codes,
                                                                 c->d_signal, c->ring_ms, ms0, n_ms, d_iq_log, d_nav_log,
-                                                                d_results, d_prof, gate);
+                                                                d_results, d_prof, gate, d_first);
         int rc = check_launch(c, "k_track_run<profile>");
         unsigned long long h[16] = {};
         CU(cudaMemcpyAsync(h, d_prof, sizeof h, cudaMemcpyDeviceToHost, c->stream));
@@ -1207,7 +1274,7 @@ static int track_loop_launch(gpsb_ctx* c, uint32_t n_ch, void* d_channels, void*
     if (experiment == E) {                                                                                               \
         k_track_run<false, E><<<n_ch, kLoopThreads, 0, c->stream>>>((gps_ch_t*)d_channels, (gpsb_aux*)d_aux, c->d_codes, \
                                                                     c->d_signal, c->ring_ms, ms0, n_ms, d_iq_log,        \
-                                                                    d_nav_log, d_results, nullptr, gate);                \
+                                                                    d_nav_log, d_results, nullptr, gate, d_first);       \
         return check_launch(c, "k_track_run<experiment>");                                                              \
     }
     GPSB_EXP_LAUNCH(1) GPSB_EXP_LAUNCH(2) GPSB_EXP_LAUNCH(3) GPSB_EXP_LAUNCH(4) GPSB_EXP_LAUNCH(5) GPSB_EXP_LAUNCH(7)
@@ -1217,21 +1284,21 @@ static int track_loop_launch(gpsb_ctx* c, uint32_t n_ch, void* d_channels, void*
         if (fixed)
             k_track_run<false, 0, true, false><<<n_ch, kLoopThreads, 0, c->stream>>>(
                 (gps_ch_t*)d_channels, (gpsb_aux*)d_aux, c->d_codes, c->d_signal, c->ring_ms, ms0, n_ms, d_iq_log, d_nav_log,
-                d_results, nullptr, gate);
+                d_results, nullptr, gate, d_first);
         else
             k_track_run<false, 0, true><<<n_ch, kLoopThreads, 0, c->stream>>>(
                 (gps_ch_t*)d_channels, (gpsb_aux*)d_aux, c->d_codes, c->d_signal, c->ring_ms, ms0, n_ms, d_iq_log, d_nav_log,
-                d_results, nullptr, gate);
+                d_results, nullptr, gate, d_first);
         return check_launch(c, "k_track_run<streaming>");
     }
     if (fixed)
         k_track_run<false, 0, false, false><<<n_ch, kLoopThreads, 0, c->stream>>>(
             (gps_ch_t*)d_channels, (gpsb_aux*)d_aux, c->d_codes, c->d_signal, c->ring_ms, ms0, n_ms, d_iq_log, d_nav_log,
-            d_results, nullptr, gate);
+            d_results, nullptr, gate, d_first);
     else
         k_track_run<false><<<n_ch, kLoopThreads, 0, c->stream>>>((gps_ch_t*)d_channels, (gpsb_aux*)d_aux, c->d_codes,
                                                                  c->d_signal, c->ring_ms, ms0, n_ms, d_iq_log, d_nav_log,
-                                                                 d_results, nullptr, gate);
+                                                                 d_results, nullptr, gate, d_first);
     return check_launch(c, "k_track_run");
 }
 
@@ -1369,6 +1436,10 @@ int gpsb_track_loop_begin(gpsb_ctx* c, uint32_t n_ch, void* channels, uint32_t c
     auto bail = [c](int rc) { pthread_mutex_unlock(&c->call_lock); return rc; };
     auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
     auto& o = c->open_loop;
+    bool pretrack = false;               // some channel is still in pre-track: k_pretrack_run goes ahead of the loop
+    for (uint32_t i = 0; i < n_ch; i++)
+        pretrack |= ch[i].tracking_data.state == GPS_NEED_PRE_TRACK || ch[i].tracking_data.state == GPS_PRE_TRACK_RUN;
+    if (pretrack && (flags & GPSB_LOOP_STREAMING)) pretrack = false;      // a streamed run starts from tracking channels
     o.channels = channels; o.aux = aux; o.results = results; o.iq_log = iq_log; o.nav_log = nav_log;
     o.ch_b = (size_t)n_ch * sizeof(gps_ch_t);
     o.aux_b = (size_t)n_ch * sizeof(gpsb_aux);
@@ -1376,7 +1447,8 @@ int gpsb_track_loop_begin(gpsb_ctx* c, uint32_t n_ch, void* channels, uint32_t c
     o.iq_b = iq_log ? (size_t)n_ms * n_ch * 12 : 0;
     o.nav_b = nav_log ? (size_t)n_ms * n_ch : 0;
     o.o_aux = up(o.ch_b); o.o_res = o.o_aux + up(o.aux_b); o.o_iq = o.o_res + up(o.res_b); o.o_nav = o.o_iq + up(o.iq_b);
-    const size_t total = o.o_nav + up(o.nav_b);
+    const size_t o_first = o.o_nav + up(o.nav_b);
+    const size_t total = o_first + up((size_t)n_ch * 4);
     int rc = ensure_stage(c, total);
     if (rc) return bail(rc);
     uint8_t* h = (uint8_t*)c->h_stage;
@@ -1393,8 +1465,20 @@ int gpsb_track_loop_begin(gpsb_ctx* c, uint32_t n_ch, void* channels, uint32_t c
         for (uint32_t i = 0; i < n_ch; i++) walks |= ax[i].walk_enable || ax[i].slot_phase || ax[i].skip_len;
         flags = walks ? (flags & ~GPSB_LOOP_FIXED_SLOTS) : (flags | GPSB_LOOP_FIXED_SLOTS);
     }
+    const uint32_t* d_first = nullptr;
+    if (pretrack) {
+        // rows of the logs a channel spends in pre-track stay blank (zero sums, no nav bit)
+        if (o.iq_b) e = cudaMemsetAsync(d + o.o_iq, 0, o.iq_b, c->stream);
+        if (e == cudaSuccess && o.nav_b) e = cudaMemsetAsync(d + o.o_nav, 0xFF, o.nav_b, c->stream);
+        if (e != cudaSuccess) return bail(fail(GPSB_ERR_CUDA, "log clear failed: %s", cudaGetErrorString(e)));
+        k_pretrack_run<<<n_ch, kSearchThreads, 0, c->stream>>>((gps_ch_t*)d, (gpsb_aux*)(d + o.o_aux), c->d_codes, c->d_signal,
+                                                             c->ring_ms, ms0, n_ms, (uint32_t*)(d + o_first));
+        rc = check_launch(c, "k_pretrack_run");
+        if (rc) return bail(rc);
+        d_first = (const uint32_t*)(d + o_first);
+    }
     rc = track_loop_launch(c, n_ch, d, d + o.o_aux, ms0, n_ms, iq_log ? (int16_t*)(d + o.o_iq) : nullptr,
-                           nav_log ? (int8_t*)(d + o.o_nav) : nullptr, (gpsb_loop_result*)(d + o.o_res), flags);
+                           nav_log ? (int8_t*)(d + o.o_nav) : nullptr, (gpsb_loop_result*)(d + o.o_res), flags, d_first);
     if (rc) return bail(rc);
     const size_t back = (o.nav_b ? o.o_nav + o.nav_b : o.iq_b ? o.o_iq + o.iq_b : o.o_res + o.res_b);
     e = cudaMemcpyAsync(h, d, back, cudaMemcpyDeviceToHost, c->stream);                                       // records + logs: one copy out

@@ -193,9 +193,21 @@ __global__ void __maxnreg__(96)      // measured: 96 registers 1.068 us per ms, 
 k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uint32_t* __restrict__ codes,
             const uint32_t* __restrict__ signal, uint32_t ring_ms, uint32_t ms0, uint32_t n_ms,
             int16_t* __restrict__ iq_log, int8_t* __restrict__ nav_log, gpsb_loop_result* __restrict__ results,
-            unsigned long long* __restrict__ prof, StreamGate gate)
+            unsigned long long* __restrict__ prof, StreamGate gate, const uint32_t* __restrict__ first_ms)
 {
     __shared__ __align__(128) LoopSmem sm;
+    // first_ms != nullptr: channel c starts at millisecond first_ms[c] >= ms0 instead of ms0 (k_pretrack_run, launched ahead of
+    // this kernel, left it there); rows of the logs and done_ms stay relative to ms0.
+    uint32_t done_base = 0;
+    if (first_ms) {
+        uint32_t skip = first_ms[blockIdx.x] - ms0;
+        if (skip > n_ms) skip = n_ms;
+        done_base = skip;
+        ms0 += skip;
+        n_ms -= skip;
+        if (iq_log) iq_log += (size_t)skip * gridDim.x * 6;
+        if (nav_log) nav_log += (size_t)skip * gridDim.x;
+    }
     long long pt[15] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     long long c0 = 0;
     const long long loop_begin = kProf ? clock64() : 0;
@@ -255,8 +267,12 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
     uint32_t known_upto = ms0;          // code thread: frames below this are known to be in the ring
     uint32_t issued = 0, consumed = 0;  // code thread: frames fetched by bulk copy / frames the workers have waited for
     if (code_thr) {
-        if (sm.ch.tracking_data.state == GPS_PRE_TRACK_DONE) sm.ch.tracking_data.state = GPS_TRACKING_RUN;   // tracking.c:74-78
-        if (sm.ch.tracking_data.state != GPS_TRACKING_RUN) {
+        // tracking.c:74-78 - on the channel's NEXT millisecond, so not when it has none left in this run (k_pretrack_run
+        // may have used them all)
+        if (n_ms && sm.ch.tracking_data.state == GPS_PRE_TRACK_DONE) sm.ch.tracking_data.state = GPS_TRACKING_RUN;
+        if (n_ms == 0) {
+            sm.stop = LC_STOP_NONE;                         // nothing to do: done_ms = what k_pretrack_run used
+        } else if (sm.ch.tracking_data.state != GPS_TRACKING_RUN) {
             sm.stop = LC_STOP_STATE;
         } else if (n_ms) {
             const uint32_t first = n_ms < 2 ? n_ms : 2;
@@ -456,7 +472,7 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
             }
             if (degenerate) {
                 gpsb_loop_result r;
-                r.done_ms = m;
+                r.done_ms = m + done_base;
                 r.stop = LC_STOP_DLL_NAN;
                 for (int k = 0; k < 6; k++) r.iq[k] = iq[k];
                 r.reserved = 0;
@@ -578,7 +594,7 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
     copy_words(auxs + chn, &sm.aux, tid, kLoopThreads);
     if (code_thr && stop != LC_STOP_DLL_NAN) {
         gpsb_loop_result r;
-        r.done_ms = m;
+        r.done_ms = m + done_base;
         r.stop = stop;
         for (int k = 0; k < 6; k++) r.iq[k] = 0;
         r.reserved = 0;

@@ -364,65 +364,26 @@ static int finish_device_run(gpsb_rx* rx, uint32_t ms0, uint32_t n_ms, int16_t* 
 
 /* The whole run with the loops on the device: one k_track_run launch for every channel that is tracking, then
  * whatever is left (channels handed back early, channels still in pre-track) channel by channel. */
-/* One millisecond of every channel in lockstep on the per-millisecond path (gpsb_rx_track_ms: one launch per kind of
- * cell for all channels), with its rows of the logs. */
-static int lockstep_ms(gpsb_rx* rx, uint32_t ms, int16_t* iq_row, int8_t* nav_row)
-{
-    for (uint32_t i = 0; i < rx->n_ch; i++) rx->aux[i].last_nav_bit = -1;
-    int rc = gpsb_rx_track_ms(rx, ms);
-    if (rc != GPSB_OK) return rc;
-    if (iq_row) {
-        memset(iq_row, 0, (size_t)rx->n_ch * 12);
-        uint32_t k = 0;
-        for (uint32_t i = 0; i < rx->n_ch; i++)
-            if (rx->plan[i].want == GPSB_WANT_EPL) memcpy(iq_row + 6u * i, rx->epl_out + 6u * k++, 12);
-    }
-    if (nav_row)
-        for (uint32_t i = 0; i < rx->n_ch; i++)
-            nav_row[i] = rx->plan[i].want == GPSB_WANT_EPL ? rx->aux[i].last_nav_bit : -1;
-    return GPSB_OK;
-}
-
 static int in_pre_track(const gps_ch_t* ch)
 {
     return ch->tracking_data.state == GPS_NEED_PRE_TRACK || ch->tracking_data.state == GPS_PRE_TRACK_RUN;
 }
 
-#define PRE_TRACK_LOCKSTEP_MAX_MS 400u   /* a pre-track that has not settled by then goes on channel by channel */
-
 static int track_run_device(gpsb_rx* rx, uint32_t ms0, uint32_t n_ms, int16_t* iq_log, int8_t* nav_log)
 {
     const uint32_t n_ch = rx->n_ch;
-    /* Channels still in pre-track (tracking.c:398-450: 7 correlations per millisecond for >= 84 ms) are stepped TOGETHER,
-     * one launch per millisecond for all of them (and one more for the channels already tracking), until every
-     * pre-track has settled: then the device-resident loop takes all channels in one launch. */
-    uint32_t lead = 0;
-    for (;;) {
-        int pre = 0;
-        for (uint32_t i = 0; i < n_ch; i++) pre |= in_pre_track(&rx->ch[i]);
-        if (!pre || lead >= n_ms || lead >= PRE_TRACK_LOCKSTEP_MAX_MS) break;
-        int rc = lockstep_ms(rx, ms0 + lead, iq_log ? iq_log + (size_t)lead * n_ch * 6 : NULL,
-                             nav_log ? nav_log + (size_t)lead * n_ch : NULL);
-        if (rc != GPSB_OK) return rc;
-        lead++;
-    }
-    if (lead) {
-        ms0 += lead;
-        n_ms -= lead;
-        if (iq_log) iq_log += (size_t)lead * n_ch * 6;
-        if (nav_log) nav_log += (size_t)lead * n_ch;
-        if (n_ms == 0) {
-            gpsb_host_set_packet_cnt(ms0 - 1);
-            return GPSB_OK;
-        }
-    }
+    /* Channels still in pre-track (tracking.c:398-450: 7 correlations per millisecond for >= 84 ms) go into the same
+     * call: gpsb_track_loop runs k_pretrack_run ahead of k_track_run on the same stream and every channel enters the
+     * tracking loop at the millisecond behind its own pre-track - one host round trip for the whole span. */
+    uint32_t n_pre = 0;
+    for (uint32_t i = 0; i < n_ch; i++) n_pre += in_pre_track(&rx->ch[i]) ? 1u : 0u;
     uint32_t n_trk = 0;
     for (uint32_t i = 0; i < n_ch; i++) n_trk += is_tracking(&rx->ch[i]) ? 1u : 0u;
     if (iq_log && n_trk != n_ch) memset(iq_log, 0, (size_t)n_ms * n_ch * 12);
     if (nav_log && n_trk != n_ch) memset(nav_log, 0xFF, (size_t)n_ms * n_ch);
-    if (n_trk > 0) {
-        /* one launch for every channel; a channel that is not tracking is refused by the loop (LC_STOP_STATE, nothing
-         * done) and taken from there channel by channel: pre-track on the per-millisecond path, idle channels not at all */
+    if (n_trk + n_pre > 0) {
+        /* one launch for every channel; a channel that is neither tracking nor in pre-track is refused by the loop
+         * (LC_STOP_STATE, nothing done): idle channels have nothing to do, anything else is taken channel by channel */
         int rc = gpsb_track_loop(rx->ctx, n_ch, rx->ch, (uint32_t)sizeof(gps_ch_t), rx->aux, (uint32_t)sizeof(gpsb_aux), ms0,
                                  n_ms, iq_log, nav_log, rx->loop_res);
         if (rc != GPSB_OK) return hx_note(rc);

@@ -18,25 +18,8 @@
 
 #include "host_internal.h"
 
-#define PRE_TRACK_ZONE         30                                   /* tracking.c:17 */
-#define PRE_TRACK_PER_MS       (PRE_TRACK_ZONE / GPSB_SLOT_LEN)     /* 7 offsets per ms, tracking.c:20 */
-
-/* ---------------------------------------------------------------------------- plan */
-/* tracking.c:52-72: load the acquisition result into a +-15 half-chip pre-track window */
-static void arm_pre_track(gps_ch_t* ch)
-{
-    gps_tracking_t* t = &ch->tracking_data;
-    uint16_t lo = (uint16_t)(ch->acq_data.found_code_phase - PRE_TRACK_ZONE / 2);
-    uint16_t hi = (uint16_t)(ch->acq_data.found_code_phase + PRE_TRACK_ZONE / 2);
-    if (lo > GPSB_HALF_CHIPS) lo = 0;
-    if (hi > GPSB_HALF_CHIPS) hi = GPSB_HALF_CHIPS;
-    t->code_search_start = lo;
-    t->code_search_stop = hi;
-    t->if_freq_offset_hz = (float)ch->acq_data.found_freq_offset_hz;
-    t->pre_track_count = 0;
-    memset(t->pre_track_phases, 0, sizeof t->pre_track_phases);
-    t->state = GPS_PRE_TRACK_RUN;
-}
+/* the pre-track arithmetic (tracking.c:52-72, 398-499) is in core/gpsb_loop_core.h (lc_pre_*): one source for this
+ * library and for the device-resident pre-track loop k_pretrack_run */
 
 void hx_trk_plan(gps_ch_t* ch, gpsb_aux* aux, uint32_t frame_ms, uint8_t index, gpsb_plan* plan)
 {
@@ -45,13 +28,12 @@ void hx_trk_plan(gps_ch_t* ch, gpsb_aux* aux, uint32_t frame_ms, uint8_t index, 
     plan->want = GPSB_WANT_NOTHING;
     plan->stage = 0;
 
-    if (t->state == GPS_NEED_PRE_TRACK) arm_pre_track(ch);
+    if (t->state == GPS_NEED_PRE_TRACK) lc_pre_arm(ch);
 
     if (t->state == GPS_PRE_TRACK_RUN) {                          /* tracking.c:398-426 */
         if (index >= GPSB_SLOT_LEN) return;
-        unsigned first = (uint16_t)(t->code_search_start + index * PRE_TRACK_PER_MS);
-        unsigned last = (uint16_t)(first + PRE_TRACK_PER_MS);
-        if (last > GPSB_HALF_CHIPS) last = GPSB_HALF_CHIPS;
+        uint16_t first, last;
+        lc_pre_window(t, index, &first, &last);
         plan->want = GPSB_WANT_SEARCH;
         plan->stage = 3;
         plan->search.sv_slot = ch->prn;
@@ -59,8 +41,8 @@ void hx_trk_plan(gps_ch_t* ch, gpsb_aux* aux, uint32_t frame_ms, uint8_t index, 
         plan->search.acc0 = 0;
         plan->search.step32 = hx_nco_step32((float)IF_FREQ_HZ + t->if_freq_offset_hz);
         plan->search.off_bits = 0;
-        plan->search.start = (uint16_t)first;
-        plan->search.stop = (uint16_t)last;
+        plan->search.start = first;
+        plan->search.stop = last;
         plan->search.flags = 0;
         return;                                                    /* a run that completes stays DONE this ms */
     }
@@ -75,50 +57,10 @@ void hx_trk_plan(gps_ch_t* ch, gpsb_aux* aux, uint32_t frame_ms, uint8_t index, 
 }
 
 /* ---------------------------------------------------------------------------- pre-track finish */
-static int cmp_u16(const void* x, const void* y) { return (int)*(const uint16_t*)x - (int)*(const uint16_t*)y; }
-
-/* tracking.c:459-499: most frequent phase among the collected slot winners (longest run of equal
- * values after sorting; a phase of 0 means "nothing found"). */
-static void settle_pre_track(gps_ch_t* ch, uint8_t n)
-{
-    gps_tracking_t* t = &ch->tracking_data;
-    qsort(t->pre_track_phases, n, sizeof(uint16_t), cmp_u16);
-    uint8_t run = 0;
-    uint16_t best_run = 0, winner = 0;
-    for (uint8_t i = 1; i < n; i++) {
-        uint16_t gap = (uint16_t)(t->pre_track_phases[i] - t->pre_track_phases[i - 1]);
-        if (abs(gap) < 1) {
-            run++;
-        } else {
-            if (run > best_run) { best_run = run; winner = t->pre_track_phases[i - 1]; }
-            run = 0;
-        }
-    }
-    if (run > best_run) { best_run = run; winner = t->pre_track_phases[n - 1]; }
-    if (winner) {
-        t->code_phase_fine = (float)(winner * GPSB_FINE_PER_HALFCHIP);
-        t->state = GPS_PRE_TRACK_DONE;
-    }
-}
-
-/* tracking.c:417-449.  res is the window's (max, first argmax): scanning the window with a strict
- * '>' against the running best is the same as comparing the window maximum once. */
+/* tracking.c:417-449, 459-499 (core/gpsb_loop_core.h, lc_pre_finish / lc_pre_settle) */
 void hx_trk_finish_search(gps_ch_t* ch, gpsb_aux* aux, uint8_t index, const gpsb_search_res* res)
 {
-    gps_tracking_t* t = &ch->tracking_data;
-    if (res && (int16_t)res->max > (int16_t)aux->pre_best_value) {
-        aux->pre_best_value = res->max;
-        aux->pre_best_phase = res->phase;
-    }
-    if (index != GPSB_SLOT_LEN - 1) return;
-    t->pre_track_phases[t->pre_track_count] = aux->pre_best_phase;   /* note: phase is NOT reset per slot */
-    t->pre_track_count++;
-    if (t->pre_track_count > PRE_TRACK_POINTS_MAX_CNT - 10) settle_pre_track(ch, t->pre_track_count);
-    if (t->pre_track_count >= PRE_TRACK_POINTS_MAX_CNT) {
-        t->pre_track_count = 0;
-        memset(t->pre_track_phases, 0, sizeof t->pre_track_phases);
-    }
-    aux->pre_best_value = 0;
+    lc_pre_finish(ch, aux, index, res ? res->max : 0, res ? res->phase : 0);
 }
 
 /* ---------------------------------------------------------------------------- loop filters */
