@@ -38,7 +38,7 @@ def signal(sc):
     return synthesize_blocks(sc.sats, sc.n_ms, sc.seed)
 
 
-def product(engine, sig, prns, n_track_ms, pre_ms=160, walk=True, timers=None, sweeps=3, cold_start_opts=None,
+def product(engine, sig, prns, n_track_ms, pre_ms=100, walk=True, timers=None, sweeps=3, cold_start_opts=None,
             before_start=None):
     """Returns (channels, receiver, report, per-channel logs).  The signal must already be in the engine's ring from
     frame 0 (gpsb_upload_signal).  timers: optional dict that receives wall-clock seconds per stage."""
@@ -54,7 +54,8 @@ def product(engine, sig, prns, n_track_ms, pre_ms=160, walk=True, timers=None, s
     rep = rx.cold_start(0, sweeps=sweeps, **(cold_start_opts or {}))
     t1 = time.perf_counter()
     t_trk = rep["ms_next"]
-    # pre-track (>= 84 ms, tracking.c:398-450) on the per-millisecond path, then one k_track_run launch for everybody
+    # the first call covers pre-track (>= 84 ms, tracking.c:398-450; k_pretrack_run + k_track_run in one round trip),
+    # the second everything after: one k_track_run launch for everybody
     iq_a, nav_a = rx.track_run(t_trk, pre_ms)
     t2 = time.perf_counter()
     iq_b, nav_b = rx.track_run(t_trk + pre_ms, n_track_ms - pre_ms)

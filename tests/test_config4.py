@@ -46,7 +46,7 @@ def test_config4_acquisition_and_10s_tracking_equal_the_reference(reference):
     assert rep["n_searched"] == 32 and rep["n_acquired"] == len(present)
     # one sweep launch + a few look-ahead windows instead of one launch per snapshot
     assert rep["launches"] < (rep["ms_last"] - rep["ms_code0"] + 1), rep
-    assert rx.loop_stats()[0] >= len(present) * (N_TRACK_MS - 160)         # tracking ran in the device-resident loop
+    assert rx.loop_stats() == (len(present) * N_TRACK_MS, 0)               # pre-track and tracking ran on the device, nothing per millisecond on the host
     rx.close()
     ch.free()
     eng.close()
