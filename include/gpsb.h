@@ -221,9 +221,15 @@ int gpsb_stream_push_iq2(gpsb_ctx* ctx, uint32_t ms0, uint32_t n_ms, const uint8
 int gpsb_stream_wait(gpsb_ctx* ctx);
 uint32_t gpsb_stream_progress(const gpsb_ctx* ctx, uint32_t n_ch);
 int gpsb_stream_set_timeout_ms(gpsb_ctx* ctx, uint32_t ms);
+uint32_t gpsb_stream_timeout_ms(const gpsb_ctx* ctx);
 /* 1 while the loop started by gpsb_track_loop_begin is still executing (a producer waiting for ring space checks
  * this so that it never waits for a consumer that has already left). */
 int gpsb_stream_loop_running(gpsb_ctx* ctx);
+/* The producer gives up: a streaming loop that is (or comes to be) waiting for a frame ends at once with stop == 3
+ * instead of waiting out the time-out; its done_ms are complete and exact.  Cleared by gpsb_stream_reset.
+ * gpsb_stream_copies_pending: 1 while pushes are still queued behind something on the copy stream. */
+int gpsb_stream_abort(gpsb_ctx* ctx);
+int gpsb_stream_copies_pending(gpsb_ctx* ctx);
 int gpsb_track_loop_begin(gpsb_ctx* ctx, uint32_t n_ch, void* channels, uint32_t channel_bytes, void* aux,
                           uint32_t aux_bytes, uint32_t ms0, uint32_t n_ms, int16_t* iq_log, int8_t* nav_log,
                           gpsb_loop_result* results, uint32_t flags);

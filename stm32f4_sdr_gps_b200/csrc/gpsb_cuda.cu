@@ -624,6 +624,7 @@ struct gpsb_ctx {
     } open_loop = {};
 };
 static const uint32_t kWmSlots = 4096;
+static const uint32_t kAbortWord = 256;      // h_progress[kAbortWord] != 0: a streaming loop stops waiting for frames
 
 static int ensure_stage(gpsb_ctx* c, size_t bytes)
 {
@@ -839,8 +840,8 @@ int gpsb_create(gpsb_ctx** out, int device, uint32_t max_sv, uint32_t ring_ms)
     CU(cudaMallocHost(&c->h_wm_ring, kWmSlots * sizeof(uint32_t)));
     {
         void* hp = nullptr;
-        CU(cudaHostAlloc(&hp, 256 * sizeof(uint32_t), cudaHostAllocMapped));
-        memset(hp, 0, 256 * sizeof(uint32_t));
+        CU(cudaHostAlloc(&hp, 320 * sizeof(uint32_t), cudaHostAllocMapped));       // 256 progress words + the abort word
+        memset(hp, 0, 320 * sizeof(uint32_t));
         void* dp = nullptr;
         CU(cudaHostGetDevicePointer(&dp, hp, 0));
         c->h_progress = (uint32_t*)hp;
@@ -1222,10 +1223,11 @@ static int track_loop_launch(gpsb_ctx* c, uint32_t n_ch, void* d_channels, void*
     if ((flags & GPSB_LOOP_STREAMING) && c->ring_ms < 8) return fail(GPSB_ERR_ARG, "a streaming run needs a ring of at least 8 ms");
     if ((flags & GPSB_LOOP_STREAMING) && n_ch > 256) return fail(GPSB_ERR_ARG, "a streaming run carries at most 256 channels");
     CU(cudaSetDevice(c->device));
-    StreamGate gate = {nullptr, nullptr, 0ull};
+    StreamGate gate = {nullptr, nullptr, 0ull, nullptr};
     if (flags & GPSB_LOOP_STREAMING) {
         gate.watermark = c->d_watermark;
         gate.progress = c->d_progress;
+        gate.abort = c->d_progress + kAbortWord;
         gate.timeout_ns = (unsigned long long)c->stream_timeout_ms * 1000000ull;
     }
     static const bool profile = getenv("GPSB_LOOP_PROFILE") != nullptr;     // diagnostic: per-phase clock64 ticks to stderr
@@ -1327,6 +1329,7 @@ int gpsb_stream_reset(gpsb_ctx* c, uint32_t ms_valid_upto)
     CU(cudaEventRecord(c->ev_reset, c->copy_stream));
     CU(cudaStreamWaitEvent(c->stream, c->ev_reset, 0));
     for (int i = 0; i < 256; i++) c->h_progress[i] = ms_valid_upto;
+    c->h_progress[kAbortWord] = 0;
     return GPSB_OK;
 }
 
@@ -1404,11 +1407,26 @@ uint32_t gpsb_stream_progress(const gpsb_ctx* c, uint32_t n_ch)
     return lo;
 }
 
+int gpsb_stream_abort(gpsb_ctx* c)
+{
+    if (!c) return fail(GPSB_ERR_ARG, "null context");
+    ((volatile uint32_t*)c->h_progress)[kAbortWord] = 1u;
+    return GPSB_OK;
+}
+
+int gpsb_stream_copies_pending(gpsb_ctx* c)
+{
+    if (!c) return 0;
+    return cudaStreamQuery(c->copy_stream) == cudaErrorNotReady ? 1 : 0;
+}
+
 int gpsb_stream_loop_running(gpsb_ctx* c)
 {
     if (!c || !c->loop_open) return 0;
     return cudaStreamQuery(c->stream) == cudaErrorNotReady ? 1 : 0;
 }
+
+uint32_t gpsb_stream_timeout_ms(const gpsb_ctx* c) { return c ? c->stream_timeout_ms : 0; }
 
 int gpsb_stream_set_timeout_ms(gpsb_ctx* c, uint32_t ms)
 {

@@ -154,6 +154,8 @@ struct StreamGate {
     const uint32_t* watermark;
     uint32_t* progress;              // mapped host memory, [n_ch]: millisecond the channel has reached (flow control)
     unsigned long long timeout_ns;
+    const uint32_t* abort;           // mapped host memory: non-zero = the producer has given up (gpsb_stream_abort): a wait
+                                     // for a frame ends at once with "starved" instead of running into the time-out
 };
 
 __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p)
@@ -175,6 +177,7 @@ __device__ __forceinline__ int frame_present(const StreamGate& gate, uint32_t ms
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
         if (!t0) t0 = now;
         else if (now - t0 > gate.timeout_ns) return 0;
+        if (gate.abort && *(volatile const uint32_t*)gate.abort) return 0;
         __nanosleep(200);
     }
 }

@@ -9,6 +9,7 @@
  */
 #include <pthread.h>
 #include <sched.h>
+#include <time.h>
 #include <stdlib.h>
 #include <unistd.h>
 
@@ -420,6 +421,8 @@ int gpsb_rx_track_stream_iq2(gpsb_rx* rx, uint32_t ms0, uint32_t n_ms, const uin
     return track_stream_impl(rx, ms0, n_ms, samples, chunk_ms, iq_log, nav_log, 1);
 }
 
+#define RX_STREAM_PATIENCE_MS 100u
+
 static int push_chunk(gpsb_rx* rx, uint32_t ms, uint32_t n, const uint8_t* base, uint32_t at, int iq2)
 {
     if (iq2) return gpsb_stream_push_iq2(rx->ctx, ms, n, base + (size_t)at * GPSB_MS_SAMPLES);
@@ -456,16 +459,23 @@ static int track_stream_impl(gpsb_rx* rx, uint32_t ms0, uint32_t n_ms, const uin
         return GPSB_OK;
     }
     int rc = gpsb_stream_reset(rx->ctx, ms0);
+    /* The samples are in host memory: this call is its own producer and pushes without delay, so a loop that sees no
+     * frame for RX_STREAM_PATIENCE_MS is not waiting for a slow source - the copy engine is not running beside the kernel
+     * at all (a profiler that makes launches synchronous, CUDA_LAUNCH_BLOCKING).  The loop then ends with its
+     * milliseconds complete and the run is finished upload-then-run below, in ~0.1 s instead of the 2-s default. */
+    const uint32_t patience_before = gpsb_stream_timeout_ms(rx->ctx);
+    if (patience_before > RX_STREAM_PATIENCE_MS) gpsb_stream_set_timeout_ms(rx->ctx, RX_STREAM_PATIENCE_MS);
     /* a short first chunk, so that the loop starts at once; the chunks behind it are as long as asked for */
     const uint32_t first_ms = chunk_ms < 16 ? chunk_ms : 16;
     uint32_t sent = n_ms < first_ms ? n_ms : first_ms;
     if (rc == GPSB_OK) rc = push_chunk(rx, ms0, sent, packed, 0, iq2);
-    if (rc != GPSB_OK) return hx_note(rc);
+    if (rc != GPSB_OK) { gpsb_stream_set_timeout_ms(rx->ctx, patience_before); return hx_note(rc); }
     rc = gpsb_track_loop_begin(rx->ctx, n_ch, rx->ch, (uint32_t)sizeof(gps_ch_t), rx->aux, (uint32_t)sizeof(gpsb_aux), ms0, n_ms,
                                iq_log, nav_log, rx->loop_res, GPSB_LOOP_STREAMING);
-    if (rc != GPSB_OK) { gpsb_stream_wait(rx->ctx); return hx_note(rc); }
+    if (rc != GPSB_OK) { gpsb_stream_wait(rx->ctx); gpsb_stream_set_timeout_ms(rx->ctx, patience_before); return hx_note(rc); }
     int rc_push = GPSB_OK;
-    while (sent < n_ms && rc_push == GPSB_OK) {
+    int checked_overlap = 0, no_overlap = 0;
+    while (sent < n_ms && rc_push == GPSB_OK && !no_overlap) {
         const uint32_t n = n_ms - sent < chunk_ms ? n_ms - sent : chunk_ms;
         /* a run longer than the ring: chunk [sent, sent+n) replaces frames sent-ring .. - wait until every channel is past them */
         while (sent + n > ring_ms && (int32_t)(gpsb_stream_progress(rx->ctx, n_ch) - (ms0 + sent + n - ring_ms)) < 0 &&
@@ -473,13 +483,60 @@ static int track_stream_impl(gpsb_rx* rx, uint32_t ms0, uint32_t n_ms, const uin
             sched_yield();
         rc_push = push_chunk(rx, ms0 + sent, n, packed, sent, iq2);
         sent += n;
+        if (!checked_overlap && rc_push == GPSB_OK) {
+            /* Streaming needs the copy engine to run WHILE the loop kernel does.  Where something serialises the two (a
+             * profiler replaying kernels, CUDA_LAUNCH_BLOCKING) the first chunk pushed behind the launch never lands,
+             * the loop would wait out its starvation time-out (2 s by default) and the call would take seconds instead of
+             * a millisecond.  Looked at once: if that chunk is still queued after 30 ms and the loop is still running,
+             * the loop is told to stop waiting (it ends with its milliseconds complete) and the rest of the run is done
+             * upload-then-run, below. */
+            checked_overlap = 1;
+            struct timespec t0, t1;
+            clock_gettime(CLOCK_MONOTONIC, &t0);
+            while (gpsb_stream_copies_pending(rx->ctx) && gpsb_stream_loop_running(rx->ctx)) {
+                clock_gettime(CLOCK_MONOTONIC, &t1);
+                if ((t1.tv_sec - t0.tv_sec) * 1000000000L + (t1.tv_nsec - t0.tv_nsec) > 30000000L) {
+                    no_overlap = 1;
+                    gpsb_stream_abort(rx->ctx);
+                    break;
+                }
+                sched_yield();
+            }
+        }
     }
     rc = gpsb_track_loop_end(rx->ctx);        /* a failed push starves the loop, which then ends by its time-out */
     int rc_wait = gpsb_stream_wait(rx->ctx);
+    gpsb_stream_set_timeout_ms(rx->ctx, patience_before);
+    if (rc == GPSB_OK && rc_push == GPSB_OK && rx->loop_res[0].stop == LC_STOP_STARVED) no_overlap = 1;   /* starved by nobody but us */
     if (rc_push != GPSB_OK) return hx_note(rc_push);
     if (rc != GPSB_OK) return hx_note(rc);
     if (rc_wait != GPSB_OK) return hx_note(rc_wait);
-    if (n_ms <= ring_ms) {
+    if (no_overlap) {
+        /* copies and the loop kernel do not overlap here: every channel stopped where the frames ended (same millisecond,
+         * same watermark); the rest of the run goes upload-then-run, all channels per launch */
+        uint32_t at = rx->loop_res[0].done_ms;
+        int together = 1;
+        for (uint32_t i = 0; i < n_ch; i++)
+            together &= rx->loop_res[i].done_ms == at && rx->loop_res[i].stop == LC_STOP_STARVED;
+        if (together && at < n_ms) {
+            for (uint32_t i = 0; i < n_ch; i++) {
+                rx->device_ms += at;
+                lc_resolve_snr(&rx->ch[i], &rx->aux[i]);
+            }
+            while (at < n_ms) {
+                const uint32_t n = n_ms - at < ring_ms ? n_ms - at : ring_ms;
+                rc = upload_span(rx, ms0 + at, n, packed, at, iq2);
+                if (rc != GPSB_OK) return hx_note(rc);
+                rc = track_run_device(rx, ms0 + at, n, iq_log ? iq_log + (size_t)at * n_ch * 6 : NULL,
+                                      nav_log ? nav_log + (size_t)at * n_ch : NULL);
+                if (rc != GPSB_OK) return rc;
+                at += n;
+            }
+            gpsb_host_set_packet_cnt(ms0 + n_ms - 1);
+            return GPSB_OK;
+        }
+    }
+    if (n_ms <= ring_ms && !no_overlap) {
         rc = finish_device_run(rx, ms0, n_ms, iq_log, nav_log);   /* the ring now holds the whole run */
         if (rc != GPSB_OK) return rc;
     } else {

@@ -181,6 +181,24 @@ def test_streaming_run_equals_resident_run(host_engine, golden):
         ch.free()
 
 
+def test_streaming_call_where_copies_cannot_overlap_the_kernel():
+    """gpsb_rx_track_stream in a process whose launches are synchronous (CUDA_LAUNCH_BLOCKING=1; a profiler's kernel
+    replay does the same): the frames pushed behind the launch can never arrive while the loop kernel runs.  The call
+    notices (the loop ends starved after ~0.1 s instead of the 2-s producer time-out), finishes upload-then-run, and
+    the sums equal those of the overlapped run (tools/stream_blocked_probe.py compares them itself)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CUDA_LAUNCH_BLOCKING="1", PROBE_MS="600")
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "stream_blocked_probe.py")], env=env, cwd=root,
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "sums identical: True" in out.stdout
+    calls = [float(l.split(":")[1].split("ms")[0]) for l in out.stdout.splitlines() if l.startswith("ring")]
+    assert len(calls) == 2 and max(calls) < 600.0, out.stdout        # nowhere near the 2-s time-out
+
+
 def test_streaming_run_starved_producer_ends_cleanly(host_engine, golden):
     """Raw C ABI: a loop started in streaming mode whose producer stops after 100 ms neither hangs nor touches
     frames that never arrived: it ends by its time-out with stop == 3 and the milliseconds it reports as done are
