@@ -69,9 +69,9 @@ struct LoopSmem {
     int stop;                           // set before the loop: the run does not start (state, no frames)
     int stop_at[2];                     // set DURING millisecond m into slot (m+1)&1, read after barrier A of millisecond m+1:
                                         // two slots, so the flag is never written in the barrier interval in which it is read
-    int starved[2];                     // streaming: the producer missed a frame.  Slot (m+1)&1 is raised during millisecond m
-                                        // and read during millisecond m+1 (barrier A in between): millisecond m+1 is then the
-                                        // last of the run.  Two slots, so a flag is never written while it may be read.
+                                        // Streaming: kLastMs in slot (m+1)&1 = the producer missed frame m+2, millisecond m+1
+                                        // is the last of the run (the control threads plan no successor); it rides in the
+                                        // word every thread reads after barrier A anyway, so the check costs no load.
 };
 
 // What the code thread and the carrier thread own of gps_tracking_t (PM/GPS/gps_misc.h:62-99), under the record's own
@@ -150,6 +150,7 @@ __device__ __forceinline__ void load_sums(const uint4* sums, int16_t iq[6])
 // land first).  The code thread looks at it only when the frame it is about to fetch is not known to be there yet -
 // once per chunk in steady state - and never waits longer than timeout_ns in total for one frame (a stalled producer
 // ends the run with LC_STOP_STARVED instead of wedging the GPU).  watermark == nullptr: everything is resident.
+constexpr int kLastMs = 0x100;          // LoopSmem::stop_at: not a stop code - "this millisecond is the last one" (streaming)
 struct StreamGate {
     const uint32_t* watermark;
     uint32_t* progress;              // mapped host memory, [n_ch]: millisecond the channel has reached (flow control)
@@ -259,7 +260,6 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         sm.stop = LC_STOP_NONE;
         sm.stop_at[0] = sm.stop_at[1] = LC_STOP_NONE;
-        sm.starved[0] = sm.starved[1] = 0;
         sm.sums[0] = make_uint4(0u, 0u, 0u, 0u);
         sm.sums[1] = make_uint4(0u, 0u, 0u, 0u);
     }
@@ -324,9 +324,9 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
         else edge_counts = ec_epl_edge_entry(sm.S[0], sm.RX[sm.rq.off_bits & 7u], (&sm.rq.off_e)[edge_arm], edge_role, &edge_w, &edge_neg);
     }
     __syncthreads();                                        // raw buffer 0 has been consumed
-    // Streaming runs: a frame that is not there in time ends the run.  The code thread raises the next millisecond's
-    // sm.starved slot; the control threads then treat that millisecond as the last one (no plan for a successor), so
-    // the records leave the kernel exactly as after a shorter run.
+    // Streaming runs: a frame that is not there in time ends the run.  The code thread marks the next millisecond as the
+    // last one (kLastMs in its sm.stop_at slot); the control threads then plan no successor, so the records leave the
+    // kernel exactly as after a shorter run.
     lc_angle_cache angle_cache;
     angle_cache.valid = 0;
     // The code and the carrier thread keep private copies of the channel record for the whole run, so that the
@@ -403,14 +403,18 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
         }
         if (kProf && carrier_thr) c0 = clock64();
         __syncthreads();   // A: the six sums of millisecond m are complete
-        if (m > 0 && (stop = sm.stop_at[b]) != LC_STOP_NONE) break;   // the previous millisecond ended the run (flag written before this barrier)
+        // the previous millisecond ended the run (flag written before this barrier) - or, streaming, made this one the last
+        bool last = false;
+        if (m > 0) {
+            const int flag = sm.stop_at[b];
+            if (kStream && flag == kLastMs) last = true;
+            else if (flag != LC_STOP_NONE) { stop = flag; break; }
+        }
         // `more`: the control threads plan a successor millisecond.  The workers only ask whether a successor frame
         // exists (it has been fetched, so waiting for it and forming its phase 1 is harmless when the run is about to
         // end for lack of LATER frames) - they do not read the starvation flag, which keeps it off their path.
         GPSB_TL(4);
         const bool next_frame = m + 1 < n_ms;
-        // (each control thread reads the flag where it needs it - at the END of its chain - so that the shared-memory
-        // round trip never sits in front of its arithmetic)
         if (worker || edge_warp) {
             if (kProf) c0 = clock64();
             if (next_frame && (plain || edge)) {            // phase 1 of millisecond m+1 as soon as its offsets exist
@@ -448,11 +452,11 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
             const bool degenerate = !idle && lc_dll_is_degenerate(iq);   // 0/0 in the DLL: x86 and the GPU disagree on NaN bits, host finishes this ms
             if (degenerate) sm.stop_at[b ^ 1u] = LC_STOP_DLL_NAN;
             else if (idle) {
-                if (kStream && sm.starved[b]) sm.stop_at[b ^ 1u] = LC_STOP_STARVED;
+                if (kStream && last) sm.stop_at[b ^ 1u] = LC_STOP_STARVED;
             } else {
-                if (kStream && sm.starved[b]) sm.stop_at[b ^ 1u] = LC_STOP_STARVED;   // this millisecond is completed by every thread, then the run ends
+                if (kStream && last) sm.stop_at[b ^ 1u] = LC_STOP_STARVED;   // this millisecond is completed by every thread, then the run ends
                 if (!(kExp & 4)) lc_dll_update(&cod, iq[0], iq[1], iq[4], iq[5]);
-                if (next_frame && !(kStream && sm.starved[b])) lc_plan_code(&cod, &sm.rq);
+                if (next_frame && !(kStream && last)) lc_plan_code(&cod, &sm.rq);
                 sm.ch.tracking_data.code_phase_fine = cod.code_phase_fine;   // for lc_refine_edge
             }
             mbar_arrive(&sm.offs_ready);                    // DLL done: releases the offset check and the nav thread's edge refinement
@@ -461,7 +465,9 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
             // frame buffer b (millisecond m) was consumed before this barrier: fetch millisecond m+2 into it.  A frame
             // that is missing is fetched all the same (the ring memory is there; nothing will use the result).
             if (m + 2 < n_ms) {
-                if (kStream && !sm.starved[b] && !frame_present(gate, ms + 2, known_upto)) sm.starved[b ^ 1u] = 1;
+                // (a stop this millisecond has already put there stays: the run then ends one barrier earlier anyway)
+                if (kStream && !last && !frame_present(gate, ms + 2, known_upto) && sm.stop_at[b ^ 1u] == LC_STOP_NONE)
+                    sm.stop_at[b ^ 1u] = kLastMs;
                 tma_load_frame(sm.S[b], signal + (size_t)((ms + 2) % ring_ms) * kWords, GPSB_FRAME_BYTES, &sm.full[b]);
                 issued = m + 3;
             }
@@ -503,7 +509,7 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
             // (now - prev_track_timestamp = gap + 1: lc_plan_carrier catches the NCO up, tracking.c:102-113)
             if (kProf) car.if_freq_accum += (uint32_t)(clock64() & 0);
             GPSB_TL(6);
-            if ((live || idle) && next_frame && !idle_next && !(kStream && *(volatile int*)&sm.starved[b]))
+            if ((live || idle) && next_frame && !idle_next && !(kStream && last))
                 lc_plan_carrier(&car, prn, ms + 1, ms + 1, &sm.rq);
             if (next_frame) mbar_arrive(&sm.nco_ready);
             GPSB_TL(7);     // always: the workers wait for it whether or not a plan was made
