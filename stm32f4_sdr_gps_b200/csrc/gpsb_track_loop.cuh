@@ -67,11 +67,11 @@ struct LoopSmem {
     uint4 sums[2];                      // packed I | Q << 16 of the three arms, accumulated by one shared-memory RED per warp
                                         // and arm; double buffered by ms parity, re-zeroed by the code thread one ms later
     int stop;                           // set before the loop: the run does not start (state, no frames)
-    int stop_at[2];                     // set DURING millisecond m into slot (m+1)&1, read after barrier A of millisecond m+1:
-                                        // two slots, so the flag is never written in the barrier interval in which it is read
-                                        // Streaming: kLastMs in slot (m+1)&1 = the producer missed frame m+2, millisecond m+1
-                                        // is the last of the run (the control threads plan no successor); it rides in the
-                                        // word every thread reads after barrier A anyway, so the check costs no load.
+    int2 ctl[2];                        // .x = stop code, set DURING millisecond m into slot (m+1)&1, read after barrier A of
+                                        // millisecond m+1: two slots, so it is never written in the barrier interval in which it
+                                        // is read.  .y (streaming) = the run's length: n_ms, or m+2 once the producer has missed
+                                        // frame m+2 - millisecond m+1 is then the last (nobody plans a successor) and the loop
+                                        // ends as at the end of a shorter run.  One 8-byte load per thread and millisecond.
 };
 
 // What the code thread and the carrier thread own of gps_tracking_t (PM/GPS/gps_misc.h:62-99), under the record's own
@@ -150,7 +150,6 @@ __device__ __forceinline__ void load_sums(const uint4* sums, int16_t iq[6])
 // land first).  The code thread looks at it only when the frame it is about to fetch is not known to be there yet -
 // once per chunk in steady state - and never waits longer than timeout_ns in total for one frame (a stalled producer
 // ends the run with LC_STOP_STARVED instead of wedging the GPU).  watermark == nullptr: everything is resident.
-constexpr int kLastMs = 0x100;          // LoopSmem::stop_at: not a stop code - "this millisecond is the last one" (streaming)
 struct StreamGate {
     const uint32_t* watermark;
     uint32_t* progress;              // mapped host memory, [n_ch]: millisecond the channel has reached (flow control)
@@ -259,7 +258,7 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
         mbar_init(&sm.nco_ready, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         sm.stop = LC_STOP_NONE;
-        sm.stop_at[0] = sm.stop_at[1] = LC_STOP_NONE;
+        sm.ctl[0] = sm.ctl[1] = make_int2(LC_STOP_NONE, (int)n_ms);
         sm.sums[0] = make_uint4(0u, 0u, 0u, 0u);
         sm.sums[1] = make_uint4(0u, 0u, 0u, 0u);
     }
@@ -324,9 +323,9 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
         else edge_counts = ec_epl_edge_entry(sm.S[0], sm.RX[sm.rq.off_bits & 7u], (&sm.rq.off_e)[edge_arm], edge_role, &edge_w, &edge_neg);
     }
     __syncthreads();                                        // raw buffer 0 has been consumed
-    // Streaming runs: a frame that is not there in time ends the run.  The code thread marks the next millisecond as the
-    // last one (kLastMs in its sm.stop_at slot); the control threads then plan no successor, so the records leave the
-    // kernel exactly as after a shorter run.
+    // Streaming runs: a frame that is not there in time ends the run.  The code thread shortens the run (sm.ctl[].y) so
+    // that the next millisecond is the last one; nobody plans a successor, so the records leave the kernel exactly as
+    // after a shorter run.
     lc_angle_cache angle_cache;
     angle_cache.valid = 0;
     // The code and the carrier thread keep private copies of the channel record for the whole run, so that the
@@ -367,7 +366,8 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
     // sums complete - is the only full barrier; it also orders everything that is reused one millisecond later (the
     // request record, the sum buffers, the frame buffers, the stop flag).
     uint32_t m = 0;
-    for (; m < n_ms && stop == LC_STOP_NONE; m++) {
+    uint32_t limit = n_ms;              // streaming: re-read every millisecond (sm.ctl[].y)
+    for (; m < limit && stop == LC_STOP_NONE; m++) {
         const uint32_t ms = ms0 + m;
         const uint32_t b = m & 1u;
         const uint8_t index = kWalk ? (uint8_t)((ms + w_phase) & (LC_SLOT_LEN - 1u))   // control threads only (w_phase is theirs)
@@ -403,18 +403,21 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
         }
         if (kProf && carrier_thr) c0 = clock64();
         __syncthreads();   // A: the six sums of millisecond m are complete
-        // the previous millisecond ended the run (flag written before this barrier) - or, streaming, made this one the last
-        bool last = false;
-        if (m > 0) {
-            const int flag = sm.stop_at[b];
-            if (kStream && flag == kLastMs) last = true;
-            else if (flag != LC_STOP_NONE) { stop = flag; break; }
+        if (m > 0) {                    // the previous millisecond ended the run (written before this barrier) or, streaming, shortened it
+            if (kStream) {
+                const int2 f = sm.ctl[b];
+                stop = f.x;
+                limit = (uint32_t)f.y;
+            } else {
+                stop = sm.ctl[b].x;
+            }
+            if (stop != LC_STOP_NONE) break;
         }
         // `more`: the control threads plan a successor millisecond.  The workers only ask whether a successor frame
         // exists (it has been fetched, so waiting for it and forming its phase 1 is harmless when the run is about to
         // end for lack of LATER frames) - they do not read the starvation flag, which keeps it off their path.
         GPSB_TL(4);
-        const bool next_frame = m + 1 < n_ms;
+        const bool next_frame = m + 1 < limit;
         if (worker || edge_warp) {
             if (kProf) c0 = clock64();
             if (next_frame && (plain || edge)) {            // phase 1 of millisecond m+1 as soon as its offsets exist
@@ -423,7 +426,7 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
                 long long c1 = 0;
                 if (kProf) c1 = clock64();
                 GPSB_TL(5);
-                if (sm.stop_at[b ^ 1u] == LC_STOP_NONE && !(kExp & 1)) {      // ordered after the code thread's write by offs_ready
+                if (sm.ctl[b ^ 1u].x == LC_STOP_NONE && !(kExp & 1)) {      // ordered after the code thread's write by offs_ready
                     if (plain) {
                         const uint32_t off[3] = {sm.rq.off_e, sm.rq.off_p, sm.rq.off_l};
                         ec_epl_phase1(sm.S[b ^ 1u], sm.RX[sm.rq.off_bits & 7u], off, w0, kLoopNw, &part, sm.top_lut);
@@ -450,13 +453,10 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
             const bool idle_next = kWalk && lc_walk_idle(w_skip_ms, w_skip_len, ms + 1u);
             if (idle) iq[0] = iq[1] = iq[2] = iq[3] = iq[4] = iq[5] = 0;          // ... the sums are nobody's
             const bool degenerate = !idle && lc_dll_is_degenerate(iq);   // 0/0 in the DLL: x86 and the GPU disagree on NaN bits, host finishes this ms
-            if (degenerate) sm.stop_at[b ^ 1u] = LC_STOP_DLL_NAN;
-            else if (idle) {
-                if (kStream && last) sm.stop_at[b ^ 1u] = LC_STOP_STARVED;
-            } else {
-                if (kStream && last) sm.stop_at[b ^ 1u] = LC_STOP_STARVED;   // this millisecond is completed by every thread, then the run ends
+            if (degenerate) sm.ctl[b ^ 1u].x = LC_STOP_DLL_NAN;
+            else if (!idle) {
                 if (!(kExp & 4)) lc_dll_update(&cod, iq[0], iq[1], iq[4], iq[5]);
-                if (next_frame && !(kStream && last)) lc_plan_code(&cod, &sm.rq);
+                if (next_frame) lc_plan_code(&cod, &sm.rq);
                 sm.ch.tracking_data.code_phase_fine = cod.code_phase_fine;   // for lc_refine_edge
             }
             mbar_arrive(&sm.offs_ready);                    // DLL done: releases the offset check and the nav thread's edge refinement
@@ -464,10 +464,8 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
             GPSB_TL(6);
             // frame buffer b (millisecond m) was consumed before this barrier: fetch millisecond m+2 into it.  A frame
             // that is missing is fetched all the same (the ring memory is there; nothing will use the result).
-            if (m + 2 < n_ms) {
-                // (a stop this millisecond has already put there stays: the run then ends one barrier earlier anyway)
-                if (kStream && !last && !frame_present(gate, ms + 2, known_upto) && sm.stop_at[b ^ 1u] == LC_STOP_NONE)
-                    sm.stop_at[b ^ 1u] = kLastMs;
+            if (m + 2 < limit) {
+                if (kStream && !frame_present(gate, ms + 2, known_upto)) sm.ctl[b ^ 1u].y = (int)(m + 2);   // millisecond m+1 is the last
                 tma_load_frame(sm.S[b], signal + (size_t)((ms + 2) % ring_ms) * kWords, GPSB_FRAME_BYTES, &sm.full[b]);
                 issued = m + 3;
             }
@@ -509,7 +507,7 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
             // (now - prev_track_timestamp = gap + 1: lc_plan_carrier catches the NCO up, tracking.c:102-113)
             if (kProf) car.if_freq_accum += (uint32_t)(clock64() & 0);
             GPSB_TL(6);
-            if ((live || idle) && next_frame && !idle_next && !(kStream && last))
+            if ((live || idle) && next_frame && !idle_next)
                 lc_plan_carrier(&car, prn, ms + 1, ms + 1, &sm.rq);
             if (next_frame) mbar_arrive(&sm.nco_ready);
             GPSB_TL(7);     // always: the workers wait for it whether or not a plan was made
@@ -551,7 +549,8 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
         }
     }
     __syncthreads();                                        // the last millisecond's control work is done
-    if (stop == LC_STOP_NONE) stop = sm.stop_at[m & 1u];    // a stop raised by the very last millisecond (m == n_ms here)
+    if (stop == LC_STOP_NONE) stop = sm.ctl[m & 1u].x;      // a stop raised by the very last millisecond (m == limit here)
+    if (kStream && stop == LC_STOP_NONE && m < n_ms) stop = LC_STOP_STARVED;      // the run was shortened: the producer missed a frame
     if (kStream && code_thr && gate.progress) *(volatile uint32_t*)(gate.progress + chn) = ms0 + n_ms;   // needs no more frames
     if (code_thr)      // early exit: bulk copies nobody waited for may still be in flight - let them land before the CTA retires
         for (uint32_t f = consumed; f < issued; f++) mbar_wait(&sm.full[f & 1u], (f >> 1) & 1u);

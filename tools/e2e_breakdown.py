@@ -34,12 +34,13 @@ d_aux = torch.zeros(ch.n * aux_b, dtype=torch.uint8, device=dev)
 d_iq = torch.zeros(n_ms * ch.n * 6, dtype=torch.int16, device=dev)
 d_nav = torch.zeros(n_ms * ch.n, dtype=torch.int8, device=dev)
 d_res = torch.zeros(ch.n * 24, dtype=torch.uint8, device=dev)
-for flags, name in ((0, "resident kernel"), (1, "streaming build, watermark already at the end")):
+for flags, name in ((0, "resident kernel"), (1, "streaming build, watermark already at the end"),
+                    (2, "resident kernel, fixed slots (no walk code)"), (3, "streaming build, fixed slots, watermark at the end")):
     ts = []
     for k in range(8):
         d_rec.copy_(d_pr)
         d_aux.zero_()
-        if flags:
+        if flags & 1:
             eng.stream_reset(n_ms)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(stream)
