@@ -46,6 +46,9 @@ namespace gpsb {
 #ifndef GPSB_LOOP_WORKERS
 #define GPSB_LOOP_WORKERS 256
 #endif
+#ifndef GPSB_LOOP_WORKER_DLL
+#define GPSB_LOOP_WORKER_DLL 1
+#endif
 constexpr int kLoopWorkers = GPSB_LOOP_WORKERS;
 constexpr int kLoopNw = kWords / kLoopWorkers;        // data words per worker thread (words 1..510; 0 and 511 are edge words)
 constexpr int kWorkerWarps = kLoopWorkers / 32;
@@ -356,6 +359,11 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
         car.pll_bad_state_cnt = t->pll_bad_state_cnt;
         car.pll_bad_state_master_cnt = t->pll_bad_state_master_cnt;
     }
+    // kWorkerDll: the workers do not wait for the code thread's offsets - every worker thread runs the DLL itself on the
+    // six sums it reads after barrier A (same IEEE arithmetic, same result in every thread) and goes straight into
+    // phase 1: the hand-over code thread -> shared memory -> mbarrier -> workers leaves the serial path.
+    constexpr bool kWorkerDll = GPSB_LOOP_WORKER_DLL && !kWalk && !kProf && kExp == 0;
+    CodeRegs wcod = cod;
     const uint8_t prn = sm.ch.prn;
     const int16_t found_freq_offset_hz = sm.ch.acq_data.found_freq_offset_hz;
 
@@ -420,7 +428,26 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
         const bool next_frame = m + 1 < limit;
         if (worker || edge_warp) {
             if (kProf) c0 = clock64();
-            if (next_frame && (plain || edge)) {            // phase 1 of millisecond m+1 as soon as its offsets exist
+            if (kWorkerDll) {
+                if (next_frame && (plain || edge)) {
+                    int16_t iq[6];
+                    load_sums(&sm.sums[b], iq);
+                    if (!lc_dll_is_degenerate(iq)) {        // (a degenerate millisecond ends the run at the next barrier)
+                        lc_dll_update(&wcod, iq[0], iq[1], iq[4], iq[5]);
+                        gpsb_epl_req wrq;
+                        lc_arm_offsets(wcod.code_phase_fine, &wrq);
+                        mbar_wait(&sm.full[b ^ 1u], ((m + 1) >> 1) & 1u);
+                        if (plain) {
+                            const uint32_t off[3] = {wrq.off_e, wrq.off_p, wrq.off_l};
+                            ec_epl_phase1(sm.S[b ^ 1u], sm.RX[wrq.off_bits & 7u], off, w0, kLoopNw, &part, sm.top_lut);
+                        } else {
+                            const uint32_t o = edge_arm == 0 ? wrq.off_e : edge_arm == 1 ? wrq.off_p : wrq.off_l;
+                            edge_counts = ec_epl_edge_entry(sm.S[b ^ 1u], sm.RX[wrq.off_bits & 7u], o, edge_role, &edge_w, &edge_neg);
+                        }
+                    }
+                    mbar_wait(&sm.nco_ready, m & 1u);       // the NCO words of millisecond m+1: on to its phase 2
+                }
+            } else if (next_frame && (plain || edge)) {     // phase 1 of millisecond m+1 as soon as its offsets exist
                 mbar_wait(&sm.full[b ^ 1u], ((m + 1) >> 1) & 1u);
                 mbar_wait(&sm.offs_ready, m & 1u);
                 long long c1 = 0;
@@ -496,6 +523,9 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
             const bool idle = kWalk && lc_walk_idle(w_skip_ms, w_skip_len, ms);            // the channel leaves this millisecond out
             const bool idle_next = kWalk && lc_walk_idle(w_skip_ms, w_skip_len, ms + 1u);
             const bool live = !idle && !lc_dll_is_degenerate(iq);
+            // no plan for a millisecond the channel leaves out: the last millisecond of the gap plans the one behind it
+            // (now - prev_track_timestamp = gap + 1: lc_plan_carrier catches the NCO up, tracking.c:102-113).
+            const bool plan = (live || idle) && next_frame && !idle_next;
             if (live) {
                 // period_sync_ok_flag is written by the nav thread at slot index 3 and read here at slot index 0
                 if (!(kExp & 2)) {
@@ -503,12 +533,9 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
                     lc_fll_update(&car, &sm.aux, found_freq_offset_hz, index, iq[2], iq[3], &angle_cache);
                 }
             }
-            // no plan for a millisecond the channel leaves out: the last millisecond of the gap plans the one behind it
-            // (now - prev_track_timestamp = gap + 1: lc_plan_carrier catches the NCO up, tracking.c:102-113)
             if (kProf) car.if_freq_accum += (uint32_t)(clock64() & 0);
             GPSB_TL(6);
-            if ((live || idle) && next_frame && !idle_next)
-                lc_plan_carrier(&car, prn, ms + 1, ms + 1, &sm.rq);
+            if (plan) lc_plan_carrier(&car, prn, ms + 1, ms + 1, &sm.rq);
             if (next_frame) mbar_arrive(&sm.nco_ready);
             GPSB_TL(7);     // always: the workers wait for it whether or not a plan was made
             // Off the serial path: at slot index 1 the FLL needs the angle of THIS prompt sample as its "before" value;
