@@ -235,6 +235,22 @@ int gpsb_track_loop_begin(gpsb_ctx* ctx, uint32_t n_ch, void* channels, uint32_t
                           gpsb_loop_result* results, uint32_t flags);
 int gpsb_track_loop_end(gpsb_ctx* ctx);
 
+/*
+ * Device-resident code-phase rounds = PM/GPS/acquisition.c:134-275 (the CODE_PHASE_SEARCH1..3 states of
+ * acquisition_process_channel: window search at the Doppler the sweep found, 32-cell histogram vote, narrowing) for a
+ * whole span of snapshots in ONE launch, one CTA per channel - instead of one search launch and host round trip per
+ * look-ahead window.  Channel and aux records as for gpsb_track_loop (host memory, copied in and out).
+ *   mode[i] 0  channel i is left alone
+ *           1  snapshots ms0, ms0+1, .. until the channel's acquisition state is no longer in busy_mask (bit s = state s),
+ *              at most n_ms
+ *           2  exactly n_ms snapshots (a channel that is served but does not keep a round alive)
+ *   used[i]    snapshots channel i consumed.
+ * The frames ms0 .. ms0 + n_ms - 1 must be in the ring.  The snapshot's millisecond is the reference's packet counter
+ * (signal_capture_get_packet_cnt) for the round's time stamps.
+ */
+int gpsb_code_rounds(gpsb_ctx* ctx, uint32_t n_ch, void* channels, uint32_t channel_bytes, void* aux, uint32_t aux_bytes,
+                     uint32_t ms0, uint32_t n_ms, uint32_t busy_mask, const uint8_t* mode, uint32_t* used);
+
 /* Self-test support: the loop's two float discriminators evaluated on the device for ip in
  * [ip_lo, ip_lo + n_ip), every qp in [-8184, 8184]; out[(ip - ip_lo) * 16369 + qp + 8184] (host memory).
  * kind 0: Costas error in units of pi (PM/GPS/tracking.c:180-183), kind 1: FLL angle (tracking.c:232). */

@@ -411,7 +411,7 @@ int gpsb_rx_cold_sweep(gpsb_rx* rx, int32_t first_bin_hz, int32_t bin_step_hz, u
  * acquisition_process_channel for ms_code0 .. ms_code12_last, acquisition_start_code_search3_channel at ms_code3_first,
  * acquisition_process_channel for ms_code3_first .. ms_last - which is how the tests check it.  All frames
  * ms0 .. ms_last must be in the ring.  opts == NULL or zero fields: the reference's Doppler grid (-7000 .. +7000 Hz in
- * steps of 500, PM/config.h:41-44), 10 snapshots per bin, time-out 400, 16 snapshots ahead. */
+ * steps of 500, PM/config.h:41-44), 10 snapshots per bin, time-out 400, 16 snapshots ahead at first. */
 typedef struct gpsb_cold_start_opts {
     int32_t  first_bin_hz, bin_step_hz;
     uint32_t n_bins, sweep_ms, round_timeout_ms, window_ms;
@@ -419,6 +419,12 @@ typedef struct gpsb_cold_start_opts {
     uint32_t serve_rank, serve_world;   /* multi-GPU: after the sweep this process goes on with channels i % serve_world ==
                                            serve_rank only (0, 0 = all); the sweep itself is sharded by gpsb_sweep_gather
                                            when the context has a communicator */
+    uint32_t window_max_ms;             /* a window that was consumed whole (no channel changed its window) is followed by one
+                                           twice as long, up to this many snapshots; 0 = up to the round time-out */
+    uint32_t code_rounds;               /* 0: look-ahead windows, search cells of many snapshots side by side on all SMs
+                                           (default); 1: k_code_rounds_run (gpsb_code_rounds, include/gpsb.h) - one launch per
+                                           round, each channel's snapshots strictly one after the other on one SM: fewer
+                                           launches, but a channel that never settles holds the launch for its whole time-out */
 } gpsb_cold_start_opts;
 typedef struct gpsb_cold_start_report {
     uint32_t ms_sweep0, ms_code0, ms_code12_last, ms_code3_first, ms_last, ms_next;   /* the snapshot schedule */

@@ -40,6 +40,7 @@ struct SweepParams {
 #include "gpsb_acq_dp4a.cuh"
 #include "gpsb_epl_batch.cuh"
 #include "gpsb_track_loop.cuh"
+#include "../core/gpsb_acq_core.h"
 
 using namespace gpsb;
 
@@ -504,6 +505,69 @@ k_pretrack_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const 
 }
 
 // ---------------------------------------------------------------------------------- level 0
+// ---------------------------------------------------------------------------------- device-resident code-phase rounds
+// k_code_rounds_run: the code-phase narrowing rounds of the acquisition (acquisition.c:134-275) over a whole span of
+// snapshots in ONE launch, one CTA per channel: per snapshot thread 0 runs the state machine (core/gpsb_acq_core.h, ac_*:
+// the same source the host path runs), all threads the window's search cell (replica at shift 0 staged once, stateless
+// mixer at the Doppler the sweep found, gps_correlation8 over [code_search_start, code_search_stop)), thread 0 the
+// histogram vote.  mode[chn]: 0 = not this channel; 1 = snapshots ms0 .. until the channel's state has left busy_mask
+// (at most n_ms); 2 = exactly n_ms snapshots (a channel that is served but does not keep the round alive).
+// used[chn] = snapshots consumed.  Replaces one search launch + host round trip per look-ahead window.
+__global__ void __launch_bounds__(kSearchThreads)
+k_code_rounds_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uint32_t* __restrict__ codes,
+                  const uint32_t* __restrict__ signal, uint32_t ring_ms, uint32_t ms0, uint32_t n_ms, uint32_t busy_mask,
+                  const uint8_t* __restrict__ mode, uint32_t* __restrict__ used)
+{
+    __shared__ CellSmem s;
+    __shared__ uint32_t sk[kSearchThreads / 32];
+    __shared__ int st[kSearchThreads / 32];
+    __shared__ gps_ch_t ch;
+    __shared__ gpsb_aux aux;
+    __shared__ gpsb_search_res cell;
+    __shared__ uint32_t win[4];          // start, stop, search wanted, go on
+    const int tid = threadIdx.x;
+    const uint32_t chn = blockIdx.x;
+    const uint32_t how = mode[chn];      // uniform over the CTA
+    if (how == 0 || n_ms == 0) {
+        if (tid == 0) used[chn] = 0;
+        return;
+    }
+    copy_words(&ch, chans + chn, tid, kSearchThreads);
+    copy_words(&aux, auxs + chn, tid, kSearchThreads);
+    __syncthreads();
+    stage_replica(s.R, codes + (size_t)ch.prn * kWords, 0u, tid, kSearchThreads);      // off_bits 0, acquisition.c:289
+    // the Doppler does not change during the code rounds: int -> float at the call, acquisition.c:288
+    const uint32_t step32 = lc_nco_step32((float)(IF_FREQ_HZ + ch.acq_data.found_freq_offset_hz));
+    uint32_t done = 0;
+    if (how == 1 && !((busy_mask >> (uint32_t)ch.acq_data.state) & 1u)) n_ms = 0;      // nothing to do for this one
+    for (uint32_t m = 0; m < n_ms; m++) {
+        const uint32_t ms = ms0 + m;
+        if (tid == 0) {
+            win[2] = (uint32_t)ac_code_plan(&ch, &aux, ms);
+            win[0] = ch.acq_data.code_search_start;
+            win[1] = ch.acq_data.code_search_stop;
+            cell = gpsb_search_res{0, 0, 0, 0};                     // empty window: max 0, phase 0 (gps_misc.c:161-181)
+        }
+        __syncthreads();
+        if (win[2] && win[0] < win[1]) {
+            stage_mix(s.I, s.Q, signal + (size_t)(ms % ring_ms) * kWords, 0u, step32, tid, kSearchThreads);
+            extend_period<kSearchThreads>(s.I, s.Q, tid);
+            search_window(s, win[0], win[1], &cell, nullptr, sk, st);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            if (win[2]) ac_finish_code_window(&ch, cell.phase, ms);
+            win[3] = how == 2 || ((busy_mask >> (uint32_t)ch.acq_data.state) & 1u);
+        }
+        __syncthreads();
+        done = m + 1;
+        if (!win[3]) break;
+    }
+    copy_words(chans + chn, &ch, tid, kSearchThreads);
+    copy_words(auxs + chn, &aux, tid, kSearchThreads);
+    if (tid == 0) used[chn] = done;
+}
+
 __global__ void k_l0_replica(const uint32_t* __restrict__ E, uint32_t bits, uint32_t* __restrict__ out)
 {
     for (int W = threadIdx.x; W < kWords; W += blockDim.x) out[W] = replica_word(E, W, bits & 15u);
@@ -1524,6 +1588,48 @@ int gpsb_track_loop_end(gpsb_ctx* c)
     }
     pthread_mutex_unlock(&c->call_lock);
     return rc;
+}
+
+int gpsb_code_rounds(gpsb_ctx* c, uint32_t n_ch, void* channels, uint32_t channel_bytes, void* aux, uint32_t aux_bytes,
+                     uint32_t ms0, uint32_t n_ms, uint32_t busy_mask, const uint8_t* mode, uint32_t* used)
+{
+    if (!c || !channels || !aux || !mode || !used) return fail(GPSB_ERR_ARG, "gpsb_code_rounds: null argument");
+    if (channel_bytes != sizeof(gps_ch_t) || aux_bytes != sizeof(gpsb_aux))
+        return fail(GPSB_ERR_ARG, "record sizes %u/%u do not match this library's %zu/%zu", channel_bytes, aux_bytes,
+                    sizeof(gps_ch_t), sizeof(gpsb_aux));
+    if (n_ch == 0) return fail(GPSB_ERR_ARG, "gpsb_code_rounds: no channels");
+    if (n_ms > c->ring_ms) return fail(GPSB_ERR_ARG, "gpsb_code_rounds: %u snapshots exceed the ring (%u ms)", n_ms, c->ring_ms);
+    const gps_ch_t* ch = (const gps_ch_t*)channels;
+    for (uint32_t i = 0; i < n_ch; i++) {
+        if (!mode[i]) continue;
+        if (mode[i] > 2) return fail(GPSB_ERR_ARG, "channel %u: mode %u", i, mode[i]);
+        if (ch[i].prn >= c->max_sv) return fail(GPSB_ERR_ARG, "channel %u: prn %u out of range (max_sv %u)", i, ch[i].prn, c->max_sv);
+        if (!c->code_set[ch[i].prn]) return fail(GPSB_ERR_STATE, "channel %u: no code set for slot %u", i, ch[i].prn);
+    }
+    CallGuard guard(c);
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t ch_b = (size_t)n_ch * sizeof(gps_ch_t), aux_b = (size_t)n_ch * sizeof(gpsb_aux);
+    const size_t o_aux = up(ch_b), o_used = o_aux + up(aux_b), o_mode = o_used + up((size_t)n_ch * 4);
+    const size_t total = o_mode + up(n_ch);
+    int rc = ensure_stage(c, total);
+    if (rc) return rc;
+    uint8_t* h = (uint8_t*)c->h_stage;
+    uint8_t* d = (uint8_t*)c->d_stage;
+    memcpy(h, channels, ch_b);
+    memcpy(h + o_aux, aux, aux_b);
+    memcpy(h + o_mode, mode, n_ch);
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(d, h, o_mode + n_ch, cudaMemcpyHostToDevice, c->stream));                  // records + modes: one copy in
+    k_code_rounds_run<<<n_ch, kSearchThreads, 0, c->stream>>>((gps_ch_t*)d, (gpsb_aux*)(d + o_aux), c->d_codes, c->d_signal,
+                                                            c->ring_ms, ms0, n_ms, busy_mask, d + o_mode, (uint32_t*)(d + o_used));
+    rc = check_launch(c, "k_code_rounds_run");
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(h, d, o_used + (size_t)n_ch * 4, cudaMemcpyDeviceToHost, c->stream));      // records + counts: one copy out
+    CU(cudaStreamSynchronize(c->stream));
+    memcpy(channels, h, ch_b);
+    memcpy(aux, h + o_aux, aux_b);
+    memcpy(used, h + o_used, (size_t)n_ch * 4);
+    return GPSB_OK;
 }
 
 int gpsb_track_loop(gpsb_ctx* c, uint32_t n_ch, void* channels, uint32_t channel_bytes, void* aux,

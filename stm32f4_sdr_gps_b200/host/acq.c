@@ -10,41 +10,12 @@
 #include <stdlib.h>
 
 #include "host_internal.h"
+#include "../core/gpsb_acq_core.h"
 
-#define CODE_SEARCH_TIMEOUT_MS   120000u     /* acquisition.c:13 */
-#define CODE_SEARCH2_WIDTH       500         /* acquisition.c:15 */
-#define CODE_SEARCH3_WIDTH       60          /* acquisition.c:16 */
+/* the code-phase rounds live in core/gpsb_acq_core.h (ac_*): one source for this file and for k_code_rounds_run */
 #define SNAPSHOTS_PER_BIN        10          /* ACQ_SINGLE_FREQ_LENGTH, acquisition.c:18 */
 
-static void clear_vote_buffers(gpsb_aux* aux)      /* acquisition_buffers_reset, acquisition.c:60-65 */
-{
-    memset(aux->freq_hist, 0, sizeof aux->freq_hist);
-    memset(aux->bin_phases, 0, sizeof aux->bin_phases);
-    aux->bin_count = 0;
-}
-
-/* Window of `width` half chips centred on the phase found so far; uint16 wrap-around below zero and
- * overshoot past 2046 are both clamped the way the reference does (acquisition.c:112-118, 156-164). */
-static void centre_window(gps_acq_t* a, unsigned width)
-{
-    uint16_t lo = (uint16_t)(a->found_code_phase - width / 2);
-    uint16_t hi = (uint16_t)(a->found_code_phase + width / 2);
-    if (lo > GPSB_HALF_CHIPS) lo = 0;
-    if (hi > GPSB_HALF_CHIPS) hi = GPSB_HALF_CHIPS;
-    a->code_search_start = lo;
-    a->code_search_stop = hi;
-    a->code_hist_step = (uint16_t)(width / ACQ_PHASE1_HIST_SIZE + 1);
-}
-
-static void begin_narrow_round(gps_ch_t* ch, gpsb_aux* aux, unsigned width, gps_acq_state_t next)
-{
-    gps_acq_t* a = &ch->acq_data;
-    memset(a->code_phase_histogram, 0, ACQ_PHASE1_HIST_SIZE);
-    centre_window(a, width);
-    clear_vote_buffers(aux);
-    a->start_timestamp = hx_now_ms();
-    a->state = next;
-}
+static void clear_vote_buffers(gpsb_aux* aux) { ac_clear_vote_buffers(aux); }
 
 /* acquisition.c:68-87 */
 static void start_channel(gps_ch_t* ch, gpsb_aux* aux)
@@ -66,30 +37,17 @@ void acquisition_start_channel(gps_ch_t* channel) { if (channel) start_channel(c
 /* acquisition.c:89-104: first narrowing round covers every half chip with 64-wide histogram bins */
 void acquisition_start_code_search_channel(gps_ch_t* channel)
 {
-    if (!channel) return;
-    gps_acq_t* a = &channel->acq_data;
-    if (a->state != GPS_ACQ_FREQ_SEARCH_DONE) return;
-    memset(a->code_phase_histogram, 0, ACQ_PHASE1_HIST_SIZE);
-    a->code_search_start = 0;
-    a->code_search_stop = GPSB_HALF_CHIPS;
-    a->code_hist_step = ACQ_PHASE1_HIST_STEP;
-    a->start_timestamp = hx_now_ms();
-    a->state = GPS_ACQ_CODE_PHASE_SEARCH1;
+    if (channel) ac_start_code_search(channel, hx_now_ms());
 }
 
 /* acquisition.c:106-130.  NOTE: shares (and clears) the one set of vote buffers, like the reference. */
 void acquisition_start_code_search3_channel(gps_ch_t* channel)
 {
-    if (!channel || channel->acq_data.state != GPS_ACQ_CODE_PHASE_SEARCH2_DONE) return;
-    begin_narrow_round(channel, &g_shared_aux, CODE_SEARCH3_WIDTH, GPS_ACQ_CODE_PHASE_SEARCH3);
+    if (channel) ac_start_code_search3(channel, &g_shared_aux, hx_now_ms());
 }
 
-/* the same two starts on a channel's own vote buffers (batched receiver) */
-void hx_acq_start_code_search3(gps_ch_t* ch, gpsb_aux* aux)
-{
-    if (ch->acq_data.state != GPS_ACQ_CODE_PHASE_SEARCH2_DONE) return;
-    begin_narrow_round(ch, aux, CODE_SEARCH3_WIDTH, GPS_ACQ_CODE_PHASE_SEARCH3);
-}
+/* the same start on a channel's own vote buffers (batched receiver) */
+void hx_acq_start_code_search3(gps_ch_t* ch, gpsb_aux* aux) { ac_start_code_search3(ch, aux, hx_now_ms()); }
 
 uint32_t* acquisition_get_hist(void) { return g_shared_aux.freq_hist; }
 
@@ -122,14 +80,7 @@ void hx_acq_plan(gps_ch_t* ch, gpsb_aux* aux, uint32_t frame_ms, gpsb_plan* plan
         fill_search(plan, ch, frame_ms, IF_FREQ_HZ + offset_hz, 0, GPSB_HALF_CHIPS, 1);
         return;
     }
-    if (a->state == GPS_ACQ_CODE_PHASE_SEARCH1_DONE) {        /* arm round 2, work starts next snapshot */
-        begin_narrow_round(ch, aux, CODE_SEARCH2_WIDTH, GPS_ACQ_CODE_PHASE_SEARCH2);
-        return;
-    }
-    if (a->state == GPS_ACQ_CODE_PHASE_SEARCH3_DONE) a->state = GPS_ACQ_DONE;                   /* :176-180 */
-
-    if (a->state == GPS_ACQ_CODE_PHASE_SEARCH1 || a->state == GPS_ACQ_CODE_PHASE_SEARCH2 ||
-        a->state == GPS_ACQ_CODE_PHASE_SEARCH3)
+    if (ac_code_plan(ch, aux, hx_now_ms()))                   /* the code rounds: core/gpsb_acq_core.h */
         fill_search(plan, ch, frame_ms, IF_FREQ_HZ + a->found_freq_offset_hz, a->code_search_start,
                     a->code_search_stop, 2);
 }
@@ -213,44 +164,7 @@ static void finish_freq_cell(gps_ch_t* ch, gpsb_aux* aux, const gpsb_search_res*
 }
 
 /* acquisition.c:211-275 */
-static void finish_code_window(gps_ch_t* ch, const gpsb_search_res* res)
-{
-    gps_acq_t* a = &ch->acq_data;
-    uint16_t best = res->phase;
-    if (best < a->code_search_start || best >= a->code_search_stop) return;
-
-    uint32_t now = hx_now_ms();
-    if (now - a->start_timestamp > CODE_SEARCH_TIMEOUT_MS) {      /* stale votes: start the round over */
-        memset(a->code_phase_histogram, 0, ACQ_PHASE1_HIST_SIZE);
-        a->start_timestamp = now;
-    }
-    uint8_t cell = (uint8_t)((best - a->code_search_start) / a->code_hist_step);
-    if (cell < ACQ_PHASE1_HIST_SIZE) a->code_phase_histogram[cell]++;
-
-    uint16_t used = (uint16_t)((a->code_search_stop + 2 - a->code_search_start) / a->code_hist_step);
-    uint8_t top = 0, top_cell = 0, occupied = 0;
-    for (uint8_t i = 0; i < used; i++) {          /* reference reads past 32 cells only if used > 32: it is not */
-        uint8_t v = a->code_phase_histogram[i];
-        if (v > top) { top = v; top_cell = i; }
-        if (v > 0) occupied++;
-    }
-    if (top < 2) return;
-
-    uint32_t sum = 0;
-    uint8_t cnt = 0;
-    for (uint8_t i = 0; i < ACQ_PHASE1_HIST_SIZE; i++)
-        if (a->code_phase_histogram[i] > 0) { sum += a->code_phase_histogram[i]; cnt++; }
-    float mean = (float)sum / (float)cnt;
-    if (mean < 0.01f) return;
-    float ratio = (float)top / mean;
-    if (occupied == 1 && top > 3) ratio = 10.0f;
-    if (ratio > 3.2f) {
-        a->found_code_phase = (uint16_t)(a->code_search_start + top_cell * a->code_hist_step);
-        if (a->state == GPS_ACQ_CODE_PHASE_SEARCH1) a->state = GPS_ACQ_CODE_PHASE_SEARCH1_DONE;
-        else if (a->state == GPS_ACQ_CODE_PHASE_SEARCH2) a->state = GPS_ACQ_CODE_PHASE_SEARCH2_DONE;
-        else if (a->state == GPS_ACQ_CODE_PHASE_SEARCH3) a->state = GPS_ACQ_CODE_PHASE_SEARCH3_DONE;
-    }
-}
+static void finish_code_window(gps_ch_t* ch, const gpsb_search_res* res) { ac_finish_code_window(ch, res->phase, hx_now_ms()); }
 
 void hx_acq_finish(gps_ch_t* ch, gpsb_aux* aux, const gpsb_plan* plan, const gpsb_search_res* res)
 {

@@ -731,22 +731,44 @@ int gpsb_rx_cold_sweep(gpsb_rx* rx, int32_t first_bin_hz, int32_t bin_step_hz, u
 /* Code-phase rounds of every channel over the snapshots [ms, ms + n): within a round a channel's window and carrier
  * are fixed, so the cells of the coming snapshots are independent until each vote - they are computed AHEAD in one
  * launch and consumed in order.  A channel whose next cell differs from the one computed ahead (its round ended: new
- * window) gets that one cell from a second, small launch and the run ends after that snapshot, so the next call starts
- * from every channel's new window.  busy_mask: bit s set = a channel in acquisition state s still has work to do; the
- * run also ends after the first snapshot that leaves no channel in such a state.  *consumed = snapshots processed. */
+ * window) has its cells for the REST of the span computed in a second, small launch - the others keep theirs - and the
+ * span goes on.  busy_mask: bit s set = a channel in acquisition state s still has work to do; the run ends after the
+ * first snapshot that leaves no channel in such a state.  *consumed = snapshots processed. */
+static int same_cell(const gpsb_search_req* a, const gpsb_search_req* b)
+{
+    return a->step32 == b->step32 && a->start == b->start && a->stop == b->stop && a->sv_slot == b->sv_slot &&
+           a->off_bits == b->off_bits;
+}
+
 static int acquire_ahead(gpsb_rx* rx, uint32_t ms, uint32_t n, uint32_t busy_mask, uint32_t* consumed, uint32_t* launches)
 {
     const uint32_t n_ch = rx->n_ch;
     *consumed = 0;
     if (n == 0) return GPSB_OK;
-    gpsb_search_req* base = (gpsb_search_req*)calloc(n_ch, sizeof *base);
+    gpsb_search_req* base = (gpsb_search_req*)calloc(n_ch, sizeof *base);     /* the cell computed ahead for channel i */
     uint8_t* have = (uint8_t*)calloc(n_ch, 1);
-    uint32_t* col = (uint32_t*)calloc(n_ch, sizeof *col);
-    gpsb_search_req* rq = NULL;
-    gpsb_search_res* rs = NULL;
-    int rc = (base && have && col) ? GPSB_OK : GPSB_ERR_NOMEM;
-    uint32_t n_want = 0;
+    uint32_t* who = (uint32_t*)calloc(n_ch, sizeof *who);
+    gpsb_search_res* ahead = (gpsb_search_res*)malloc(sizeof *ahead * (size_t)n_ch * n);    /* [channel][snapshot] */
+    gpsb_search_req* rq = (gpsb_search_req*)malloc(sizeof *rq * (size_t)n_ch * n);
+    gpsb_search_res* rs = (gpsb_search_res*)malloc(sizeof *rs * (size_t)n_ch * n);
+    int rc = (base && have && who && ahead && rq && rs) ? GPSB_OK : GPSB_ERR_NOMEM;
+    /* cells of `cnt` channels (who[]) for the snapshots k0 .. n-1, one launch; results into ahead[][] */
+#define RX_AHEAD_LAUNCH(cnt, k0)                                                                      \
+    do {                                                                                              \
+        const uint32_t span_ = n - (k0);                                                              \
+        for (uint32_t j_ = 0; j_ < (cnt); j_++)                                                       \
+            for (uint32_t k_ = 0; k_ < span_; k_++) {                                                 \
+                rq[(size_t)k_ * (cnt) + j_] = base[who[j_]];                                          \
+                rq[(size_t)k_ * (cnt) + j_].ms_index = ms + (k0) + k_;                                \
+            }                                                                                         \
+        rc = gpsb_search(rx->ctx, (cnt) * span_, rq, rs);                                             \
+        if (launches) (*launches)++;                                                                  \
+        for (uint32_t j_ = 0; j_ < (cnt) && rc == GPSB_OK; j_++)                                      \
+            for (uint32_t k_ = 0; k_ < span_; k_++)                                                   \
+                ahead[(size_t)who[j_] * n + (k0) + k_] = rs[(size_t)k_ * (cnt) + j_];                 \
+    } while (0)
     /* what every channel would correlate at snapshot `ms`, looked at without touching the channel */
+    uint32_t n_want = 0;
     for (uint32_t i = 0; i < n_ch && rc == GPSB_OK; i++) {
         const gps_acq_t* a = &rx->ch[i].acq_data;
         if (rx->ch[i].prn < 1) continue;
@@ -760,27 +782,11 @@ static int acquire_ahead(gpsb_rx* rx, uint32_t ms, uint32_t n, uint32_t busy_mas
         if (p.want != GPSB_WANT_SEARCH || p.search.start >= p.search.stop) continue;
         base[i] = p.search;
         have[i] = 1;
-        col[i] = n_want++;
+        who[n_want++] = i;
     }
-    if (rc == GPSB_OK && n_want) {
-        rq = (gpsb_search_req*)malloc(sizeof *rq * (size_t)n_want * n);
-        rs = (gpsb_search_res*)malloc(sizeof *rs * (size_t)n_want * n);
-        if (!rq || !rs) rc = GPSB_ERR_NOMEM;
-        for (uint32_t i = 0; i < n_ch && rc == GPSB_OK; i++) {
-            if (!have[i]) continue;
-            for (uint32_t k = 0; k < n; k++) {
-                rq[(size_t)k * n_want + col[i]] = base[i];
-                rq[(size_t)k * n_want + col[i]].ms_index = ms + k;
-            }
-        }
-        if (rc == GPSB_OK) {
-            rc = gpsb_search(rx->ctx, n_want * n, rq, rs);
-            if (launches) (*launches)++;
-        }
-    }
+    if (rc == GPSB_OK && n_want) RX_AHEAD_LAUNCH(n_want, 0u);
     for (uint32_t k = 0; k < n && rc == GPSB_OK; k++) {
         gpsb_host_set_packet_cnt(ms + k);
-        int cut = 0;
         uint32_t n_miss = 0;
         for (uint32_t i = 0; i < n_ch; i++) {
             gpsb_plan* p = &rx->plan[i];
@@ -790,33 +796,74 @@ static int acquire_ahead(gpsb_rx* rx, uint32_t ms, uint32_t n, uint32_t busy_mas
             if (rx->ch[i].acq_data.state < GPS_ACQ_CODE_PHASE_SEARCH1) continue;
             hx_acq_plan(&rx->ch[i], &rx->aux[i], ms + k, p);
             if (p->want != GPSB_WANT_SEARCH) continue;
-            if (p->search.start >= p->search.stop) {
-                hx_acq_finish(&rx->ch[i], &rx->aux[i], p, &k_empty_window);
-            } else if (have[i] && p->search.step32 == base[i].step32 && p->search.start == base[i].start &&
-                       p->search.stop == base[i].stop && p->search.sv_slot == base[i].sv_slot &&
-                       p->search.off_bits == base[i].off_bits) {
-                hx_acq_finish(&rx->ch[i], &rx->aux[i], p, &rs[(size_t)k * n_want + col[i]]);
-            } else {
-                rx->s_rq[n_miss] = p->search;                    /* not computed ahead: this one cell now */
-                rx->s_owner[n_miss++] = i;
-                cut = 1;
-            }
+            if (p->search.start >= p->search.stop) hx_acq_finish(&rx->ch[i], &rx->aux[i], p, &k_empty_window);
+            else if (have[i] && same_cell(&p->search, &base[i])) hx_acq_finish(&rx->ch[i], &rx->aux[i], p, &ahead[(size_t)i * n + k]);
+            else who[n_miss++] = i;                              /* not computed ahead: a new window from here on */
         }
         if (n_miss) {
-            rc = gpsb_search(rx->ctx, n_miss, rx->s_rq, rx->s_res);
-            if (launches) (*launches)++;
+            for (uint32_t j = 0; j < n_miss; j++) {
+                base[who[j]] = rx->plan[who[j]].search;
+                have[who[j]] = 1;
+            }
+            RX_AHEAD_LAUNCH(n_miss, k);
             for (uint32_t j = 0; j < n_miss && rc == GPSB_OK; j++) {
-                const uint32_t i = rx->s_owner[j];
-                hx_acq_finish(&rx->ch[i], &rx->aux[i], &rx->plan[i], &rx->s_res[j]);
+                const uint32_t i = who[j];
+                hx_acq_finish(&rx->ch[i], &rx->aux[i], &rx->plan[i], &ahead[(size_t)i * n + k]);
             }
         }
         *consumed = k + 1;
         int busy = 0;
         for (uint32_t i = 0; i < n_ch; i++)
             if (rx->ch[i].prn >= 1 && ((busy_mask >> (uint32_t)rx->ch[i].acq_data.state) & 1u)) busy = 1;
-        if (!busy || cut) break;
+        if (!busy) break;
     }
-    free(base); free(have); free(col); free(rq); free(rs);
+#undef RX_AHEAD_LAUNCH
+    free(base); free(have); free(who); free(ahead); free(rq); free(rs);
+    return hx_note(rc);
+}
+
+/* The code-phase rounds of every served channel on the device: one launch for the channels that keep the round alive
+ * (each until its state has left busy_mask, at most n snapshots), a second one - only if there are any - for served
+ * channels that do not (they see exactly the snapshots the round lasted).  Same outcome as acquire_ahead() window by
+ * window: channels never share vote buffers in the code rounds, so each one's snapshots are its own affair.
+ * *consumed = snapshots the round lasted. */
+static int rounds_on_device(gpsb_rx* rx, uint32_t ms, uint32_t n, uint32_t busy_mask, uint32_t* consumed, uint32_t* launches)
+{
+    const uint32_t n_ch = rx->n_ch;
+    *consumed = 0;
+    if (n == 0) return GPSB_OK;
+    uint8_t* mode = (uint8_t*)calloc(n_ch, 1);
+    uint32_t* used = (uint32_t*)calloc(n_ch, sizeof *used);
+    if (!mode || !used) { free(mode); free(used); return hx_note(GPSB_ERR_NOMEM); }
+    uint32_t n_busy = 0, n_idle = 0;
+    for (uint32_t i = 0; i < n_ch; i++) {
+        const uint32_t st = (uint32_t)rx->ch[i].acq_data.state;
+        if (rx->ch[i].prn < 1 || st < GPS_ACQ_CODE_PHASE_SEARCH1 || st == GPS_ACQ_DONE) continue;
+        if ((busy_mask >> st) & 1u) { mode[i] = 1; n_busy++; }
+        else if (st != GPS_ACQ_CODE_PHASE_SEARCH2_DONE) n_idle++;       /* SEARCH2_DONE waits for round 3: nothing happens to it */
+    }
+    int rc = GPSB_OK;
+    uint32_t lasted = 0;
+    if (n_busy) {
+        rc = gpsb_code_rounds(rx->ctx, n_ch, rx->ch, (uint32_t)sizeof(gps_ch_t), rx->aux, (uint32_t)sizeof(gpsb_aux), ms, n,
+                              busy_mask, mode, used);
+        if (launches) (*launches)++;
+        for (uint32_t i = 0; i < n_ch; i++) lasted = used[i] > lasted ? used[i] : lasted;
+    }
+    if (rc == GPSB_OK && n_idle && lasted) {
+        for (uint32_t i = 0; i < n_ch; i++) {
+            const uint32_t st = (uint32_t)rx->ch[i].acq_data.state;
+            const int served = rx->ch[i].prn >= 1 && st >= GPS_ACQ_CODE_PHASE_SEARCH1 && st != GPS_ACQ_DONE &&
+                               st != GPS_ACQ_CODE_PHASE_SEARCH2_DONE;
+            mode[i] = (uint8_t)((served && !mode[i]) ? 2 : 0);          /* mode[i] was 1: that channel has had its snapshots */
+        }
+        rc = gpsb_code_rounds(rx->ctx, n_ch, rx->ch, (uint32_t)sizeof(gps_ch_t), rx->aux, (uint32_t)sizeof(gpsb_aux), ms, lasted,
+                              busy_mask, mode, used);
+        if (launches) (*launches)++;
+    }
+    if (lasted) gpsb_host_set_packet_cnt(ms + lasted - 1);
+    *consumed = lasted;
+    free(mode); free(used);
     return hx_note(rc);
 }
 
@@ -871,10 +918,20 @@ int gpsb_rx_cold_start(gpsb_rx* rx, uint32_t ms0, const gpsb_cold_start_opts* op
     const uint32_t busy12 = (1u << GPS_ACQ_CODE_PHASE_SEARCH1) | (1u << GPS_ACQ_CODE_PHASE_SEARCH1_DONE) |
                             (1u << GPS_ACQ_CODE_PHASE_SEARCH2);
     uint32_t launches = 0;
+    /* Look-ahead windows by default: a code round is throughput work (a 2046-phase window is 68 us on one SM), and the
+     * cells of many coming snapshots run side by side on all SMs; a window consumed whole is followed by one twice as
+     * long, so a channel that never settles costs a handful of launches for its whole time-out.  On request the rounds
+     * run device-resident instead (k_code_rounds_run: same records, same schedule, one launch per round). */
+    const int on_device = o.code_rounds == 1 && gpsb_session_slots(rx->ctx) == 0;
+    const uint32_t window_max = o.window_max_ms ? o.window_max_ms : o.round_timeout_ms;
+    uint32_t window = o.window_ms;
     r.ms_code12_last = t ? t - 1 : 0;
     while (r.n_served && t - r.ms_code0 < o.round_timeout_ms) {
         uint32_t left = o.round_timeout_ms - (t - r.ms_code0), done = 0;
-        rc = acquire_ahead(rx, t, left < o.window_ms ? left : o.window_ms, busy12, &done, &launches);
+        const uint32_t ahead = left < window ? left : window;
+        rc = on_device ? rounds_on_device(rx, t, left, busy12, &done, &launches)
+                       : acquire_ahead(rx, t, ahead, busy12, &done, &launches);
+        if (done == ahead && window < window_max) window = 2 * window < window_max ? 2 * window : window_max;
         if (rc != GPSB_OK) return rc;
         t += done;
         r.ms_code12_last = t - 1;
@@ -893,10 +950,14 @@ int gpsb_rx_cold_start(gpsb_rx* rx, uint32_t ms0, const gpsb_cold_start_opts* op
         n_round3++;
     }
     const uint32_t busy3 = (1u << GPS_ACQ_CODE_PHASE_SEARCH3) | (1u << GPS_ACQ_CODE_PHASE_SEARCH3_DONE);
+    window = o.window_ms;
     r.ms_last = t ? t - 1 : 0;
     while (n_round3 && t - r.ms_code3_first < o.round_timeout_ms) {
         uint32_t left = o.round_timeout_ms - (t - r.ms_code3_first), done = 0;
-        rc = acquire_ahead(rx, t, left < o.window_ms ? left : o.window_ms, busy3, &done, &launches);
+        const uint32_t ahead = left < window ? left : window;
+        rc = on_device ? rounds_on_device(rx, t, left, busy3, &done, &launches)
+                       : acquire_ahead(rx, t, ahead, busy3, &done, &launches);
+        if (done == ahead && window < window_max) window = 2 * window < window_max ? 2 * window : window_max;
         if (rc != GPSB_OK) return rc;
         t += done;
         r.ms_last = t - 1;

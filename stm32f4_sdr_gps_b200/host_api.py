@@ -86,7 +86,7 @@ class ColdStartOpts(C.Structure):
     """include/gpsb_host.h, gpsb_cold_start_opts (zero = the reference's defaults)"""
     _fields_ = [("first_bin_hz", C.c_int32), ("bin_step_hz", C.c_int32), ("n_bins", C.c_uint32), ("sweep_ms", C.c_uint32),
                 ("round_timeout_ms", C.c_uint32), ("window_ms", C.c_uint32), ("sweeps", C.c_uint32), ("serve_rank", C.c_uint32),
-                ("serve_world", C.c_uint32)]
+                ("serve_world", C.c_uint32), ("window_max_ms", C.c_uint32), ("code_rounds", C.c_uint32)]
 
 
 class ColdStartReport(C.Structure):

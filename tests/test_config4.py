@@ -44,9 +44,37 @@ def test_config4_acquisition_and_10s_tracking_equal_the_reference(reference):
     assert summary["nav_bits"] >= good * 350                     # 20-ms data bits handed to the word assembler, ~8 s each
     assert summary["cells"] == len(present) * N_TRACK_MS
     assert rep["n_searched"] == 32 and rep["n_acquired"] == len(present)
-    # one sweep launch + a few look-ahead windows instead of one launch per snapshot
-    assert rep["launches"] < (rep["ms_last"] - rep["ms_code0"] + 1), rep
+    # one launch per sweep, then look-ahead windows that double while nothing changes: a handful of launches even though
+    # one satellite (Doppler vote passed, but it is not there) keeps rounds 1 + 2 alive for the whole 400-ms time-out
+    assert rep["launches"] <= rep["n_sweeps"] + 14, rep
     assert rx.loop_stats() == (len(present) * N_TRACK_MS, 0)               # pre-track and tracking ran on the device, nothing per millisecond on the host
     rx.close()
     ch.free()
+    eng.close()
+
+
+def test_code_rounds_on_the_device_equal_the_look_ahead_path():
+    """gpsb_rx_cold_start with the code-phase rounds in k_code_rounds_run (code_rounds = 1: one launch per round), with
+    the default look-ahead windows (doubling) and with fixed 16-snapshot windows: same schedule, same channel and
+    vote-buffer records for all 32 searched satellites."""
+    from stm32f4_sdr_gps_b200 import Channels, Engine, Receiver
+    sc = c4.scene(600)
+    sig = c4.signal(sc)
+    eng = Engine(device=0, max_sv=40, ring_ms=sc.n_ms)
+    eng.upload_signal(0, sig)
+    out = []
+    for opts in (dict(code_rounds=1), dict(), dict(window_max_ms=16)):
+        ch = Channels(c4.SEARCHED)
+        rx = Receiver(eng, ch)
+        rep = rx.cold_start(0, sweeps=3, **opts)
+        out.append((rep, [bytes(ch.snapshot(i)) for i in range(len(c4.SEARCHED))]))
+        rx.close()
+        ch.free()
+    (rep_dev, rec_dev), (rep_grow, rec_grow), (rep_fixed, rec_fixed) = out
+    assert rep_dev["n_acquired"] == len(sc.sats)
+    assert rep_dev["launches"] < rep_grow["launches"] < rep_fixed["launches"], (rep_dev, rep_grow, rep_fixed)
+    for k in rep_dev:
+        if k != "launches":
+            assert rep_dev[k] == rep_grow[k] == rep_fixed[k], (k, rep_dev, rep_grow, rep_fixed)
+    assert rec_dev == rec_grow == rec_fixed
     eng.close()
