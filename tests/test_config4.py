@@ -78,3 +78,32 @@ def test_code_rounds_on_the_device_equal_the_look_ahead_path():
             assert rep_dev[k] == rep_grow[k] == rep_fixed[k], (k, rep_dev, rep_grow, rep_fixed)
     assert rec_dev == rec_grow == rec_fixed
     eng.close()
+
+
+def test_pre_track_on_the_device_equals_the_per_ms_path():
+    """After a cold start the first tracking call takes the channels through pre-track: in k_pretrack_run chained ahead of
+    k_track_run (one round trip) and, with the loop filters asked to stay on the host, one search cell per channel and
+    millisecond.  Same records, same per-ms sums and nav bits.  (Small enough to run under compute-sanitizer.)"""
+    from stm32f4_sdr_gps_b200 import Channels, Engine, Receiver
+    sc = c4.scene(700)
+    sig = c4.signal(sc)
+    eng = Engine(device=0, max_sv=40, ring_ms=sc.n_ms)
+    eng.upload_signal(0, sig)
+    out = []
+    for site in (0, 1):
+        ch = Channels(c4.SEARCHED)
+        rx = Receiver(eng, ch)
+        rx.set_slot_walk(True)
+        rep = rx.cold_start(0, sweeps=3)
+        rx.set_loop_site(site)
+        iq, nav = rx.track_run(rep["ms_next"], 200)
+        out.append((rep, iq, nav, [bytes(ch.snapshot(i)) for i in range(len(c4.SEARCHED))], rx.loop_stats()))
+        rx.close()
+        ch.free()
+    dev, host = out
+    assert dev[0]["n_acquired"] == len(sc.sats)
+    assert np.array_equal(dev[1], host[1]) and np.array_equal(dev[2], host[2])
+    assert dev[3] == host[3]
+    assert dev[4][1] == 0 and host[4][0] == 0           # all on the device / all on the host path
+    assert dev[1].any()                                  # tracking did start inside the span
+    eng.close()

@@ -23,12 +23,13 @@ GPSB_BENCH_NMS=40 GPSB_BENCH_LONG_MS=20000 GPSB_BENCH_C4_MS=300 timeout 300 $NCU
     -o gpurun_out/prof_k_acq_dp4a_r2 python bench.py --steps 2 --warmup 1 > gpurun_out/ncu_k_acq_dp4a_r2.log 2>&1
 ls -la gpurun_out/*_r2.ncu-rep
 # compute-sanitizer: memcheck + racecheck over the kernels this round touched - k_track_run (slot-phase walk, streamed and
-# resident), k_epl_batch_tma, the sweep -> iq2 stream -> sweep sequence of the round-1 advisor finding, the sharded sweep
+# resident), k_epl_batch_tma, the sweep -> iq2 stream -> sweep sequence of the round-1 advisor finding, the sharded sweep,
+# k_pretrack_run and k_code_rounds_run (cold start of 32 PRNs + the first tracking call)
 unset GPSB_BENCH_NO_STREAM GPSB_DISABLE_SESSION
 SEL="slot_walk or sweep_scratch or split_runs or streaming_run_equals or starved"
 for tool in memcheck racecheck; do
     timeout 1200 compute-sanitizer --tool $tool --error-exitcode 9 --log-file gpurun_out/sanitizer_${tool}_r2.log \
-        python -m pytest tests/test_gpu_loop.py tests/test_gpu_parity.py -x -q -k "$SEL or batch" > gpurun_out/sanitizer_${tool}_pytest_r2.log 2>&1
+        python -m pytest tests/test_gpu_loop.py tests/test_gpu_parity.py tests/test_config4.py -x -q -k "$SEL or batch or code_rounds or pre_track" > gpurun_out/sanitizer_${tool}_pytest_r2.log 2>&1
     echo "$tool rc=$? $(tail -1 gpurun_out/sanitizer_${tool}_pytest_r2.log)"
     grep -E "ERROR SUMMARY|RACECHECK SUMMARY" gpurun_out/sanitizer_${tool}_r2.log | tail -2
 done
