@@ -114,6 +114,10 @@ def load_library(path: Path | None = None) -> C.CDLL:
         "gpsb_stream_progress": (u32, [vp, u32]),
         "gpsb_stream_set_timeout_ms": (i32, [vp, u32]),
         "gpsb_stream_loop_running": (i32, [vp]),
+        "gpsb_stream_timeout_ms": (u32, [vp]),
+        "gpsb_stream_abort": (i32, [vp]),
+        "gpsb_stream_copies_pending": (i32, [vp]),
+        "gpsb_code_rounds": (i32, [vp, u32, vp, u32, vp, u32, u32, u32, u32, vp, vp]),
         "gpsb_track_loop_record_bytes": (None, [C.POINTER(u32), C.POINTER(u32)]),
         "gpsb_l0_loop_math": (i32, [vp, i32, C.c_int32, u32, vp]),
         "gpsb_l0_generate_prn_data2": (i32, [vp, vp, vp, u16]),
@@ -374,6 +378,25 @@ class Engine:
 
     def stream_set_timeout_ms(self, ms: int) -> None:
         self._check(self.lib.gpsb_stream_set_timeout_ms(self._ctx, ms))
+
+    def stream_timeout_ms(self) -> int:
+        return int(self.lib.gpsb_stream_timeout_ms(self._ctx))
+
+    def stream_abort(self) -> None:
+        """gpsb_stream_abort: the producer gives up - a streaming loop waiting for a frame ends at once (stop == 3)."""
+        self._check(self.lib.gpsb_stream_abort(self._ctx))
+
+    def code_rounds(self, n_ch: int, channels: int, aux: np.ndarray, ms0: int, n_ms: int, busy_mask: int, mode) -> np.ndarray:
+        """gpsb_code_rounds: the code-phase rounds of the acquisition device-resident (k_code_rounds_run), one CTA per
+        channel.  channels: address of n_ch host channel records; aux: their aux records (uint8, in place);
+        mode[i] 0 skip / 1 until the state leaves busy_mask / 2 exactly n_ms snapshots.  Returns snapshots used per channel."""
+        ch_b, aux_b = self.record_bytes()
+        mode = np.ascontiguousarray(mode, dtype=np.uint8)
+        used = np.zeros(n_ch, np.uint32)
+        assert mode.size == n_ch and aux.dtype == np.uint8 and aux.size == n_ch * aux_b
+        self._check(self.lib.gpsb_code_rounds(self._ctx, n_ch, C.c_void_p(channels), ch_b, aux.ctypes.data, aux_b, ms0, n_ms,
+                                              busy_mask, mode.ctypes.data, used.ctypes.data))
+        return used
 
     def record_bytes(self):
         a, b = C.c_uint32(), C.c_uint32()

@@ -391,6 +391,36 @@ def test_loop_begin_end_call_sequence_errors(host_engine, golden):
     ch.free()
 
 
+def test_code_rounds_arguments_and_idle_channels(host_engine, golden):
+    """gpsb_code_rounds (raw C ABI): bad arguments are refused with a message; mode 0 leaves a channel's records
+    untouched and reports 0 snapshots; mode 1 on a channel whose state is not in busy_mask consumes nothing."""
+    lib = host_engine.lib
+    sig = np.ascontiguousarray(golden["scene_signal"][:64])
+    host_engine.upload_signal(0, sig)
+    ch = _two_locked_channels(golden)                    # GPS_ACQ_DONE: not in any code round
+    rx = Receiver(host_engine, ch)                       # loads the codes
+    ch_b, aux_b = host_engine.record_bytes()
+    aux = np.zeros(2 * aux_b, np.uint8)
+    before = [bytes(ch.snapshot(i)) for i in range(2)]
+    busy12 = (1 << 3) | (1 << 4) | (1 << 5)              # CODE_PHASE_SEARCH1, _1_DONE, _2 (gps_acq_state_t)
+    used = host_engine.code_rounds(2, ch.at(0), aux, 0, 16, busy12, [0, 1])
+    assert used.tolist() == [0, 0]
+    assert [bytes(ch.snapshot(i)) for i in range(2)] == before and not aux.any()
+    mode = np.array([3, 0], np.uint8)
+    used = np.zeros(2, np.uint32)
+    assert lib.gpsb_code_rounds(host_engine.handle, 2, ch.at(0), ch_b, aux.ctypes.data, aux_b, 0, 16, busy12,
+                                mode.ctypes.data, used.ctypes.data) == -1          # GPSB_ERR_ARG
+    assert b"mode 3" in lib.gpsb_last_error()
+    mode[0] = 1
+    assert lib.gpsb_code_rounds(host_engine.handle, 2, ch.at(0), ch_b, aux.ctypes.data, aux_b, 0, 1 << 20, busy12,
+                                mode.ctypes.data, used.ctypes.data) == -1
+    assert b"exceed the ring" in lib.gpsb_last_error()
+    assert lib.gpsb_code_rounds(host_engine.handle, 2, ch.at(0), ch_b + 8, aux.ctypes.data, aux_b, 0, 16, busy12,
+                                mode.ctypes.data, used.ctypes.data) == -1
+    rx.close()
+    ch.free()
+
+
 def test_slot_walk_all_alignments_on_the_device(reference):
     """Four satellites whose data-bit edges sit at all four slot alignments, tracked by ONE k_track_run launch with the
     slot-phase walk enabled (gpsb_rx_set_slot_walk): every channel ends with a refined bit edge, and sums, nav bits,

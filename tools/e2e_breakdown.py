@@ -59,5 +59,18 @@ for name, fn in (("gpsb_rx_track_run (records in/out, resident signal)", lambda:
         fn()
         ts.append(time.perf_counter() - t0)
     print("%-48s %.3f ms" % (name, min(ts) * 1e3))
+# the same two calls the way bench.py times them: L2 flushed (a 256-MB fill) before every call
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+for name, fn in (("gpsb_rx_track_run, L2 flushed before the call", lambda: rx.track_run(0, n_ms, log=True)),
+                 ("gpsb_rx_track_stream, L2 flushed before the call", lambda: rx.track_stream(0, pinned, log=True))):
+    ts = []
+    for k in range(8):
+        bench.arm_locked(ch, scene)
+        flush.fill_(k)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        fn()
+        ts.append(time.perf_counter() - t0)
+    print("%-48s %.3f ms (median %.3f)" % (name, min(ts) * 1e3, float(np.median(ts)) * 1e3))
 rx.close()
 eng.close()
