@@ -251,6 +251,59 @@ def test_streaming_run_starved_producer_ends_cleanly(host_engine, golden):
     ch.free()
 
 
+def test_stream_abort_ends_a_waiting_loop_at_once(host_engine, golden):
+    """gpsb_stream_abort (raw C ABI): a streaming loop waiting for frames that will never come ends when the producer says
+    so - not after the stream time-out (5 s here) - with stop == 3 and its milliseconds complete and exact."""
+    import time
+    lib = host_engine.lib
+    sig = np.ascontiguousarray(golden["scene_signal"][:300])
+    host_engine.upload_signal(0, sig)
+    ch = _two_locked_channels(golden)
+    rx = Receiver(host_engine, ch)
+    want_iq, _ = rx.track_run(0, 300)
+    rx.close()
+    ch.free()
+
+    host_engine.upload_signal(0, np.zeros_like(sig))
+    ch = _two_locked_channels(golden)
+    ch_b, aux_b = host_engine.record_bytes()
+    aux = np.zeros(2 * aux_b, np.uint8)
+    rx = Receiver(host_engine, ch)                       # loads the codes
+    res = np.zeros((2, 6), np.uint32)
+    iq = np.zeros((300, 2, 6), np.int16)
+    host_engine.stream_set_timeout_ms(5000)
+    host_engine.stream_reset(0)
+    host_engine.stream_push(0, sig[:100])
+    assert lib.gpsb_track_loop_begin(host_engine.handle, 2, ch.at(0), ch_b, aux.ctypes.data, aux_b, 0, 300,
+                                     iq.ctypes.data, None, res.ctypes.data, 1) == 0
+    time.sleep(0.05)                                     # the loop has long run out of frames and is waiting
+    assert lib.gpsb_stream_loop_running(host_engine.handle) == 1
+    t0 = time.perf_counter()
+    host_engine.stream_abort()
+    assert lib.gpsb_track_loop_end(host_engine.handle) == 0
+    waited = time.perf_counter() - t0
+    host_engine.stream_wait()
+    host_engine.stream_set_timeout_ms(2000)
+    assert waited < 1.0, waited
+    for i in range(2):
+        done, stop = int(res[i, 0]), int(res[i, 1])
+        assert stop == 3 and 90 <= done <= 100, (done, stop)
+        assert np.array_equal(iq[:done, i, :], want_iq[:done, i, :])
+    host_engine.stream_reset(0)                          # clears the abort: the next streamed run is unaffected
+    host_engine.stream_push(0, sig)
+    ch2 = _two_locked_channels(golden)
+    aux2 = np.zeros(2 * aux_b, np.uint8)
+    assert lib.gpsb_track_loop_begin(host_engine.handle, 2, ch2.at(0), ch_b, aux2.ctypes.data, aux_b, 0, 300,
+                                     iq.ctypes.data, None, res.ctypes.data, 1) == 0
+    assert lib.gpsb_track_loop_end(host_engine.handle) == 0
+    host_engine.stream_wait()
+    assert [int(res[i, 0]) for i in range(2)] == [300, 300] and [int(res[i, 1]) for i in range(2)] == [0, 0]
+    assert np.array_equal(iq, want_iq)
+    rx.close()
+    ch.free()
+    ch2.free()
+
+
 @pytest.mark.parametrize("ring_ms,chunk", [(256, 32), (192, 0), (64, 16)])
 def test_streaming_run_longer_than_the_ring(host_engine, golden, ring_ms, chunk):
     """A 600-ms run through a ring of 256 / 192 ms: the producer refills the ring behind the loop (flow control on
