@@ -314,7 +314,7 @@ def run_reference_arm(args) -> None:
         # every satellite of every rank's scene at once, one process each, on as many cores as the box has
         t, used, _ = reference_tracking(pairs, cores, reps=3)
         if t is None:
-            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libgpsref.so missing"}))
+            emit({"impl": "reference", "unavailable": "oracle/_ref/libgpsref.so missing"})
             return
         if w >= args.warmup:
             times.append(t)
@@ -334,7 +334,7 @@ def run_reference_arm(args) -> None:
                                    "serial: one SV cannot use more than one core)" % (n_gpus * N_SV_PER_GPU, used, cores)},
         "e2e": {"value": v, "unit": "arm-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ----------------------------------------------------------------------------- own arm (GPU)
@@ -964,7 +964,7 @@ def run_gpu_arm(args) -> None:
                                       "frac_sharded": acq_dp4a / (acq_gathered_ms * 1e-3) / (idp_peak * world),
                                       "hbm_frac": acq_alg_bytes / (acq_dp4a_ms * 1e-3) / 1e9 / hbm_peak}},
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     rx.close()
@@ -972,7 +972,24 @@ def run_gpu_arm(args) -> None:
     eng.close()
 
 
+_json_out = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line of the contract, on the process's real stdout."""
+    out = _json_out or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main() -> None:
+    # stdout carries the JSON line and nothing else: the compiled reference (oracle/_ref) printf()s its acquisition
+    # decisions ("PRN=.. FINAL FREQ=..") from C, in this process and in the forked per-satellite workers.  File descriptor 1
+    # is pointed at stderr for everybody; the JSON line goes to a private duplicate of the original stdout.
+    global _json_out
+    sys.stdout.flush()
+    _json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

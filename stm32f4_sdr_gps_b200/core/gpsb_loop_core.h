@@ -285,8 +285,14 @@ LC_FN float lc_atan2f(float y, float x)
  * to double for the division by (double) M_PI on one branch and calls the double atan2 on the other. */
 LC_FN float lc_costas_err(int16_t ip, int16_t qp)
 {
+#if defined(__CUDACC__) && defined(GPSB_COSTAS_MUL)
+    /* experiment: a double multiply instead of the double divide; only valid if the whole-domain certificate passes */
+    if (ip > 0) return (float)(LC_ATAN2F((float)qp, (float)ip) * 0.31830988618379067154);
+    return (float)(LC_ATAN2((float)-qp, (float)-ip) * 0.31830988618379067154);
+#else
     if (ip > 0) return (float)(LC_ATAN2F((float)qp, (float)ip) / LC_PI);
     return (float)(LC_ATAN2((float)-qp, (float)-ip) / LC_PI);
+#endif
 }
 
 /* One arm of the frequency discriminator, tracking.c:232-233 */

@@ -49,6 +49,9 @@ namespace gpsb {
 #ifndef GPSB_LOOP_WORKER_DLL
 #define GPSB_LOOP_WORKER_DLL 1
 #endif
+#ifndef GPSB_LOOP_WORKER_DLL_WALK
+#define GPSB_LOOP_WORKER_DLL_WALK 0
+#endif
 constexpr int kLoopWorkers = GPSB_LOOP_WORKERS;
 constexpr int kLoopNw = kWords / kLoopWorkers;        // data words per worker thread (words 1..510; 0 and 511 are edge words)
 constexpr int kWorkerWarps = kLoopWorkers / 32;
@@ -362,7 +365,7 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
     // kWorkerDll: the workers do not wait for the code thread's offsets - every worker thread runs the DLL itself on the
     // six sums it reads after barrier A (same IEEE arithmetic, same result in every thread) and goes straight into
     // phase 1: the hand-over code thread -> shared memory -> mbarrier -> workers leaves the serial path.
-    constexpr bool kWorkerDll = GPSB_LOOP_WORKER_DLL && !kWalk && !kProf && kExp == 0;
+    constexpr bool kWorkerDll = GPSB_LOOP_WORKER_DLL && (!kWalk || GPSB_LOOP_WORKER_DLL_WALK) && !kProf && kExp == 0;
     CodeRegs wcod = cod;
     const uint8_t prn = sm.ch.prn;
     const int16_t found_freq_offset_hz = sm.ch.acq_data.found_freq_offset_hz;
@@ -432,8 +435,13 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
                 if (next_frame && (plain || edge)) {
                     int16_t iq[6];
                     load_sums(&sm.sums[b], iq);
-                    if (!lc_dll_is_degenerate(iq)) {        // (a degenerate millisecond ends the run at the next barrier)
-                        lc_dll_update(&wcod, iq[0], iq[1], iq[4], iq[5]);
+                    // Walk build: a millisecond the channel leaves out moves no code phase (the sums are nobody's).  The gap is
+                    // read from the record itself: the nav thread writes it at least LC_WALK_LEAD_MS before it begins and after
+                    // the previous one has ended, so whichever of the two values a worker sees - or a mix of them - says "not
+                    // idle" for the millisecond at hand.
+                    const bool w_idle = kWalk && lc_walk_idle(*(volatile uint32_t*)&sm.aux.skip_ms, *(volatile uint8_t*)&sm.aux.skip_len, ms);
+                    if (w_idle || !lc_dll_is_degenerate(iq)) {        // (a degenerate millisecond ends the run at the next barrier)
+                        if (!w_idle) lc_dll_update(&wcod, iq[0], iq[1], iq[4], iq[5]);
                         gpsb_epl_req wrq;
                         lc_arm_offsets(wcod.code_phase_fine, &wrq);
                         mbar_wait(&sm.full[b ^ 1u], ((m + 1) >> 1) & 1u);

@@ -9,7 +9,7 @@ for rep in $(seq ${REPS:-2}); do
         cp $v $lib
         echo -n "$(basename $v .so): "
         if [ -n "$BATCH" ]; then python tools/batch_once.py 400000 1 2>&1 | tail -1 | tr '\n' ' '; python tools/batch_once.py 400000 3 2>&1 | tail -1
-        elif [ -n "$STREAM" ]; then python tools/e2e_breakdown.py 2>&1 | grep -E "streaming build|track_stream" | tr '\n' ' '; echo
+        elif [ -n "$STREAM" ]; then python tools/e2e_breakdown.py 2>&1 | grep -E "resident kernel  |streaming build|track_stream" | tr '\n' ' '; echo
         else GPSB_LOOP_EXPERIMENT=0 python tools/rtt_probe.py 2>&1 | grep "device loop" | sed 's/  n_ch   4 device loop//'; fi
     done
 done
