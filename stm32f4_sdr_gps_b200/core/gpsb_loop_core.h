@@ -285,8 +285,13 @@ LC_FN float lc_atan2f(float y, float x)
  * to double for the division by (double) M_PI on one branch and calls the double atan2 on the other. */
 LC_FN float lc_costas_err(int16_t ip, int16_t qp)
 {
-#if defined(__CUDACC__) && defined(GPSB_COSTAS_MUL)
-    /* experiment: a double multiply instead of the double divide; only valid if the whole-domain certificate passes */
+#if defined(__CUDACC__) && !defined(GPSB_COSTAS_DIVIDE)
+    /* On the device the double DIVISION by pi is a double MULTIPLICATION by 1/pi (a divide is ~100 dependent cycles on
+     * the carrier thread's chain at every slot index 0).  The two differ in the last bit of the double now and then,
+     * never after the rounding to float on this function's domain: ip, qp are sums in [-8184, 8184], and
+     * gpsb_l0_loop_math evaluates all 16369 x 16369 pairs on the GPU against the host's division
+     * (tests/test_gpu_loop.py, test_loop_math_certificate_whole_domain) - the certificate that already covers the
+     * arctangents. */
     if (ip > 0) return (float)(LC_ATAN2F((float)qp, (float)ip) * 0.31830988618379067154);
     return (float)(LC_ATAN2((float)-qp, (float)-ip) * 0.31830988618379067154);
 #else
