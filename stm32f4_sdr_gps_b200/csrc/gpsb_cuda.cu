@@ -632,7 +632,7 @@ struct gpsb_ctx {
     cudaStream_t stream = nullptr;
     uint32_t* d_codes = nullptr;   // max_sv x 512 words
     uint32_t* d_schips = nullptr;  // max_sv x 256 words: +-1 chip bytes for the dp4a search
-    uint32_t* d_rxt = nullptr;     // max_sv x 16 x 4 x 1040 words: extended replica streams for k_epl_batch
+    uint32_t* d_rxt = nullptr;     // max_sv x 16 x 16 x 1040 words (1 MB per slot): extended replica streams for k_epl_batch
     uint32_t epl_batch_min = 512;  // gpsb_track_epl_dev batches of at least this many cells go to k_epl_batch
     int epl_batch_kernel = GPSB_BATCH_TMA;   // which of the two batch kernels (gpsb_set_epl_batch_kernel)
     int n_sm = 148;

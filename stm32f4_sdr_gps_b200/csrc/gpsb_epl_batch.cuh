@@ -10,8 +10,9 @@
  *   frame     each lane fetches 4 x 16 bytes of the cell's frame straight into registers (coalesced 512-byte
  *             requests, L1 bypassed), one cell ahead of the one being correlated; nothing is staged in shared memory
  *   replica   the periodically extended replica stream of every (satellite slot, sub-byte shift) is resident in
- *             HBM/L2 (RXT, built when the code is set: per slot 16 shifts x 4 word-displaced copies x 1040 words, two periods); the window of data word w for
- *             byte offset `off` is one funnel shift of two RXT words at byte 4w - off + 2046 (no wrap to test for)
+ *             HBM/L2 (RXT, built when the code is set: per slot 16 shifts x 16 byte-displaced copies x 1040 words, two
+ *             periods, 1 MB); the window of data word w for byte offset `off` is the word at byte 4w - off + 2046 of the
+ *             copy displaced by that position's low four bits (no shift, no wrap to test for)
  *   carrier   closed form of gps_misc.c:229-239 per word; the quadrant patterns are one byte repeated (top byte of
  *             0x09999999 aside), so a pattern pair costs two PRMT byte broadcasts, shared by the arms
  *   edges     word 511 (never mixed; 16 or 8 replica bits against zero data) is special-cased in its unrolled slot;
@@ -30,26 +31,28 @@ namespace gpsb {
 
 constexpr int kRxtWords = 1040;         // two 2046-byte periods + the longest run a lane reads past them, rounded up to 16 bytes
 constexpr int kRxtShifts = 16;
-constexpr int kRxtCopies = 4;           // the stream displaced by 0..3 words (alignment of 128-bit loads)
+constexpr int kRxtCopies = 16;          // the stream displaced by 0..15 BYTES: a run starting at any byte is 16-byte aligned in one of them
 constexpr int kBatchThreads = 256;
 #ifndef GPSB_BATCH_CTAS
 #define GPSB_BATCH_CTAS 2
 #endif
 constexpr int kBatchCtasPerSm = GPSB_BATCH_CTAS;
 
-// RXT[slot][b][r][x] = bytes 4(x+r) .. 4(x+r)+3 (mod 2046) of the replica buffer gps_generate_prn_data2(b) produces
+// RXT[slot][b][r][x] = bytes 4x+r .. 4x+r+3 (mod 2046) of the replica buffer gps_generate_prn_data2(b) produces
 // (gps_misc.c:282-300: chip k at sample bits [16k+b, 16k+b+16), no wrap, the spill beyond 2046 bytes dropped).
-// The four copies r = 0..3 are the same stream displaced by r words, so that a run starting at ANY word of the stream
-// starts 16-byte aligned in one of them and a lane fetches its four words with one 128-bit load.
+// The sixteen copies r = 0..15 are the same stream displaced by r BYTES, so that a run starting at ANY byte of the stream
+// starts 16-byte aligned in one of them: a lane fetches the replica windows of four data words with one 128-bit load and
+// uses them as they are - no funnel shift per word, no fifth word from the neighbouring lane (round 2: the ALU pipe is
+// what bounds the kernel, and the byte offset used to cost it one shift per word and arm).
 __global__ void k_build_rxt(const uint32_t* __restrict__ E, uint32_t* __restrict__ rxt)
 {
     for (int i = threadIdx.x + blockIdx.x * blockDim.x; i < kRxtShifts * kRxtCopies * kRxtWords; i += blockDim.x * gridDim.x) {
         const uint32_t b = (uint32_t)(i / (kRxtCopies * kRxtWords));
         const int r = (i / kRxtWords) % kRxtCopies;
-        const int x = i % kRxtWords + r;
+        const int x = i % kRxtWords;
         uint32_t v = 0;
         for (int j = 0; j < 4; j++) {
-            const int byte = (4 * x + j) % (int)GPSB_MS_BYTES;
+            const int byte = (4 * x + r + j) % (int)GPSB_MS_BYTES;
             const uint32_t w = ec_replica_word(E, byte >> 2, b);
             v |= ((w >> (8 * (byte & 3))) & 0xFFu) << (8 * j);
         }
@@ -104,38 +107,26 @@ __device__ __forceinline__ void batch_cell(const gpsb_epl_req& rq, const uint4 (
     uint32_t acc[kArms];            // packed I | Q << 16 (a whole millisecond is at most 16368 per component)
     uint32_t acc_q[kArms];          // three arms: Q apart until the end (measured: the packed form costs them 3 %)
     // Replica run per arm: data word w meets the stream at byte 4w - off + 2046 (RXT spans two periods, so there is no
-    // wrap to test for); the sub-word shift is the same for every word of the cell.  A lane's group of four data words
-    // needs five consecutive stream words: four by one aligned 128-bit load from the copy of the stream displaced by
-    // (first word & 3), the fifth is the first word of the next lane's load (lane 31: of lane 0's load for the next
-    // group, which lane 0 hands over in the same shuffle).
-    uint32_t sh[kArms];
+    // wrap to test for).  A lane's group of four data words is sixteen consecutive stream bytes starting at byte
+    // p + 512 k: one aligned 128-bit load from the copy of the stream displaced by (p & 15) bytes.
     uint4 rr[kArms][4];
-    uint32_t r4[kArms][4];
 #pragma unroll
     for (int a = 0; a < kArms; a++) {
         acc[a] = acc_q[a] = 0u;
         const int p = 16 * lane - (int)offs[kArms == 3 ? a : 1] + (int)GPSB_MS_BYTES;
-        sh[a] = ((uint32_t)p & 3u) * 8u;
-        const int first = p >> 2, copy = first & 3;
-        const uint32_t* q = rx + copy * kRxtWords + (first - copy);          // 16-byte aligned
+        const int copy = p & 15;
+        const uint32_t* q = rx + copy * kRxtWords + ((p - copy) >> 2);        // 16-byte aligned
 #pragma unroll
         for (int k = 0; k < 4; k++) rr[a][k] = __ldg(reinterpret_cast<const uint4*>(q + 128 * k));
-        const uint32_t beyond = lane == 0 ? __ldg(q + 512) : 0u;              // first word of a fifth group, for lane 31
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const uint32_t give = lane == 0 ? (k < 3 ? rr[a][k < 3 ? k + 1 : 3].x : beyond) : rr[a][k].x;
-            r4[a][k] = __shfl_sync(0xFFFFFFFFu, give, (lane + 1) & 31);
-        }
     }
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const int w0 = 4 * (lane + 32 * k);
         const uint32_t s[4] = {f[k].x, f[k].y, f[k].z, f[k].w};
-        uint32_t r[kArms][5];
+        uint32_t r[kArms][4];
 #pragma unroll
         for (int a = 0; a < kArms; a++) {
             r[a][0] = rr[a][k].x; r[a][1] = rr[a][k].y; r[a][2] = rr[a][k].z; r[a][3] = rr[a][k].w;
-            r[a][4] = r4[a][k];
         }
         // The ALU pipe is what bounds this kernel (70 % busy, profiles/k_epl_batch_tma1_r2.txt); multiply-adds issue on the
         // FMA pipe, so the NCO word of every data word and the Q half of the packed sum are formed by IMAD.
@@ -148,7 +139,7 @@ __device__ __forceinline__ void batch_cell(const gpsb_epl_req& rq, const uint4 (
             quadrant_patterns(nco, cp, sp);
 #pragma unroll
             for (int a = 0; a < kArms; a++) {
-                const uint32_t win = __funnelshift_r(r[a][j], r[a][j + 1], sh[a]);
+                const uint32_t win = r[a][j];
                 uint32_t xi = s[j] ^ cp ^ win, xq = s[j] ^ sp ^ win;
                 if (k == 3 && j == 3) {
                     // word 511 (lane 31) is never mixed - its data is 0 - and only its bytes 2044 and, for even
