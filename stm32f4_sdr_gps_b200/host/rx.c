@@ -740,6 +740,23 @@ static int same_cell(const gpsb_search_req* a, const gpsb_search_req* b)
            a->off_bits == b->off_bits;
 }
 
+/* cells of `cnt` channels (who[]) for the snapshots k0 .. n-1 of the span, one launch; results into ahead[channel][snapshot] */
+static int ahead_launch(gpsb_rx* rx, const gpsb_search_req* base, const uint32_t* who, uint32_t cnt, uint32_t ms, uint32_t k0,
+                        uint32_t n, gpsb_search_req* rq, gpsb_search_res* rs, gpsb_search_res* ahead, uint32_t* launches)
+{
+    const uint32_t span = n - k0;
+    for (uint32_t j = 0; j < cnt; j++)
+        for (uint32_t k = 0; k < span; k++) {
+            rq[(size_t)k * cnt + j] = base[who[j]];
+            rq[(size_t)k * cnt + j].ms_index = ms + k0 + k;
+        }
+    int rc = gpsb_search(rx->ctx, cnt * span, rq, rs);
+    if (launches) (*launches)++;
+    for (uint32_t j = 0; j < cnt && rc == GPSB_OK; j++)
+        for (uint32_t k = 0; k < span; k++) ahead[(size_t)who[j] * n + k0 + k] = rs[(size_t)k * cnt + j];
+    return rc;
+}
+
 static int acquire_ahead(gpsb_rx* rx, uint32_t ms, uint32_t n, uint32_t busy_mask, uint32_t* consumed, uint32_t* launches)
 {
     const uint32_t n_ch = rx->n_ch;
@@ -752,21 +769,6 @@ static int acquire_ahead(gpsb_rx* rx, uint32_t ms, uint32_t n, uint32_t busy_mas
     gpsb_search_req* rq = (gpsb_search_req*)malloc(sizeof *rq * (size_t)n_ch * n);
     gpsb_search_res* rs = (gpsb_search_res*)malloc(sizeof *rs * (size_t)n_ch * n);
     int rc = (base && have && who && ahead && rq && rs) ? GPSB_OK : GPSB_ERR_NOMEM;
-    /* cells of `cnt` channels (who[]) for the snapshots k0 .. n-1, one launch; results into ahead[][] */
-#define RX_AHEAD_LAUNCH(cnt, k0)                                                                      \
-    do {                                                                                              \
-        const uint32_t span_ = n - (k0);                                                              \
-        for (uint32_t j_ = 0; j_ < (cnt); j_++)                                                       \
-            for (uint32_t k_ = 0; k_ < span_; k_++) {                                                 \
-                rq[(size_t)k_ * (cnt) + j_] = base[who[j_]];                                          \
-                rq[(size_t)k_ * (cnt) + j_].ms_index = ms + (k0) + k_;                                \
-            }                                                                                         \
-        rc = gpsb_search(rx->ctx, (cnt) * span_, rq, rs);                                             \
-        if (launches) (*launches)++;                                                                  \
-        for (uint32_t j_ = 0; j_ < (cnt) && rc == GPSB_OK; j_++)                                      \
-            for (uint32_t k_ = 0; k_ < span_; k_++)                                                   \
-                ahead[(size_t)who[j_] * n + (k0) + k_] = rs[(size_t)k_ * (cnt) + j_];                 \
-    } while (0)
     /* what every channel would correlate at snapshot `ms`, looked at without touching the channel */
     uint32_t n_want = 0;
     for (uint32_t i = 0; i < n_ch && rc == GPSB_OK; i++) {
@@ -784,7 +786,7 @@ static int acquire_ahead(gpsb_rx* rx, uint32_t ms, uint32_t n, uint32_t busy_mas
         have[i] = 1;
         who[n_want++] = i;
     }
-    if (rc == GPSB_OK && n_want) RX_AHEAD_LAUNCH(n_want, 0u);
+    if (rc == GPSB_OK && n_want) rc = ahead_launch(rx, base, who, n_want, ms, 0u, n, rq, rs, ahead, launches);
     for (uint32_t k = 0; k < n && rc == GPSB_OK; k++) {
         gpsb_host_set_packet_cnt(ms + k);
         uint32_t n_miss = 0;
@@ -805,7 +807,7 @@ static int acquire_ahead(gpsb_rx* rx, uint32_t ms, uint32_t n, uint32_t busy_mas
                 base[who[j]] = rx->plan[who[j]].search;
                 have[who[j]] = 1;
             }
-            RX_AHEAD_LAUNCH(n_miss, k);
+            rc = ahead_launch(rx, base, who, n_miss, ms, k, n, rq, rs, ahead, launches);
             for (uint32_t j = 0; j < n_miss && rc == GPSB_OK; j++) {
                 const uint32_t i = who[j];
                 hx_acq_finish(&rx->ch[i], &rx->aux[i], &rx->plan[i], &ahead[(size_t)i * n + k]);
@@ -817,7 +819,6 @@ static int acquire_ahead(gpsb_rx* rx, uint32_t ms, uint32_t n, uint32_t busy_mas
             if (rx->ch[i].prn >= 1 && ((busy_mask >> (uint32_t)rx->ch[i].acq_data.state) & 1u)) busy = 1;
         if (!busy) break;
     }
-#undef RX_AHEAD_LAUNCH
     free(base); free(have); free(who); free(ahead); free(rq); free(rs);
     return hx_note(rc);
 }
