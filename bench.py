@@ -985,11 +985,17 @@ def emit(line: dict) -> None:
 def main() -> None:
     # stdout carries the JSON line and nothing else: the compiled reference (oracle/_ref) printf()s its acquisition
     # decisions ("PRN=.. FINAL FREQ=..") from C, in this process and in the forked per-satellite workers.  File descriptor 1
-    # is pointed at stderr for everybody; the JSON line goes to a private duplicate of the original stdout.
+    # is pointed at /dev/null for everybody (GPSB_BENCH_KEEP_STDOUT=1: at stderr); the JSON line goes to a private
+    # duplicate of the original stdout.
     global _json_out
     sys.stdout.flush()
     _json_out = os.fdopen(os.dup(1), "w")
-    os.dup2(2, 1)
+    if os.environ.get("GPSB_BENCH_KEEP_STDOUT"):
+        os.dup2(2, 1)
+    else:
+        sink = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(sink, 1)
+        os.close(sink)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
