@@ -49,6 +49,9 @@ namespace gpsb {
 #ifndef GPSB_LOOP_WORKER_DLL
 #define GPSB_LOOP_WORKER_DLL 1
 #endif
+#ifndef GPSB_LOOP_SLOTS             // -1: per build (see kSlots); 0 / 1: all builds without / with the per-warp slots (experiments)
+#define GPSB_LOOP_SLOTS (-1)
+#endif
 #ifndef GPSB_LOOP_WORKER_DLL_WALK
 #define GPSB_LOOP_WORKER_DLL_WALK 0
 #endif
@@ -72,6 +75,8 @@ struct LoopSmem {
     uint32_t top_lut[16];               // ec_top_nibble_counts(0..15), see EC_COUNTS_FULL
     uint4 sums[2];                      // packed I | Q << 16 of the three arms, accumulated by one shared-memory RED per warp
                                         // and arm; double buffered by ms parity, re-zeroed by the code thread one ms later
+    uint4 partial[2][16];               // kSlots builds instead: per warp (slots 0..7 the workers, 9 the edge warp; the others
+                                        // stay zero) its packed partial sums of a millisecond, double buffered by ms parity
     int stop;                           // set before the loop: the run does not start (state, no frames)
     int2 ctl[2];                        // .x = stop code, set DURING millisecond m into slot (m+1)&1, read after barrier A of
                                         // millisecond m+1: two slots, so it is never written in the barrier interval in which it
@@ -267,6 +272,7 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
         sm.ctl[0] = sm.ctl[1] = make_int2(LC_STOP_NONE, (int)n_ms);
         sm.sums[0] = make_uint4(0u, 0u, 0u, 0u);
         sm.sums[1] = make_uint4(0u, 0u, 0u, 0u);
+        for (int i = 0; i < 16; i++) sm.partial[0][i] = sm.partial[1][i] = make_uint4(0u, 0u, 0u, 0u);
     }
     __syncthreads();
     if (tid < 16) sm.top_lut[tid] = ec_top_nibble_counts((uint32_t)tid);
@@ -376,6 +382,12 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
     // words exist; nobody waits for the slowest warp's phase 1 or for the nav thread in between.  Barrier A - all six
     // sums complete - is the only full barrier; it also orders everything that is reused one millisecond later (the
     // request record, the sum buffers, the frame buffers, the stop flag).
+    // How the six sums get from nine warps to everybody.  kSlots: one 16-byte store per warp into a slot of its own, every warp
+    // adds the slots up after barrier A (three REDUX).  Otherwise: 27 shared-memory atomics on three words in front of the
+    // barrier, one 16-byte load behind it.  Measured per build (tools/ab_run.sh, us per ms of signal, atomics -> slots):
+    // resident without the walk 0.985 -> 0.950; streaming without the walk 0.979 -> 1.007; resident with the walk 1.012 -> 1.021.
+    // So each build takes what is faster for it (the difference is instruction scheduling, not the algorithm).
+    constexpr bool kSlots = GPSB_LOOP_SLOTS >= 0 ? (GPSB_LOOP_SLOTS != 0) : (!kStream && !kWalk && !kProf && kExp == 0);
     uint32_t m = 0;
     uint32_t limit = n_ms;              // streaming: re-read every millisecond (sm.ctl[].y)
     for (; m < limit && stop == LC_STOP_NONE; m++) {
@@ -403,7 +415,9 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
             for (int a = 0; a < 3; a++) v[a] = __reduce_add_sync(0xFFFFFFFFu, acc[a]);
             if (kProf) { c2 = clock64(); c2 += (long long)(v[0] & 0u); }
             GPSB_TL(2);
-            if (lane == 0) {
+            if (kSlots) {
+                if (lane == 0) sm.partial[b][warp] = make_uint4(v[0], v[1], v[2], 0u);     // one 16-byte store into the warp's own slot
+            } else if (lane == 0) {
                 uint32_t* acc_s = reinterpret_cast<uint32_t*>(&sm.sums[b]);
                 atomicAdd(acc_s + 0, v[0]);
                 atomicAdd(acc_s + 1, v[1]);
@@ -414,6 +428,17 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
         }
         if (kProf && carrier_thr) c0 = clock64();
         __syncthreads();   // A: the six sums of millisecond m are complete
+        // kSlots: every warp forms the six sums for itself - lane l < 16 takes slot l, three REDUX - so they sit in the registers
+        // of every thread that needs them (control threads, and the workers for their own DLL): no contending atomics in front of
+        // the barrier, no shared-memory round trip behind it, no buffer to clear.
+        int16_t sums[6] = {0, 0, 0, 0, 0, 0};
+        if (kSlots) {
+            const uint4 pv = sm.partial[b][lane & 15];
+            const bool mine = lane < 16;
+            const uint32_t packed[3] = {__reduce_add_sync(0xFFFFFFFFu, mine ? pv.x : 0u), __reduce_add_sync(0xFFFFFFFFu, mine ? pv.y : 0u),
+                                        __reduce_add_sync(0xFFFFFFFFu, mine ? pv.z : 0u)};
+            ec_unpack_sums(packed, sums);
+        }
         if (m > 0) {                    // the previous millisecond ended the run (written before this barrier) or, streaming, shortened it
             if (kStream) {
                 const int2 f = sm.ctl[b];
@@ -434,7 +459,7 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
             if (kWorkerDll) {
                 if (next_frame && (plain || edge)) {
                     int16_t iq[6];
-                    load_sums(&sm.sums[b], iq);
+                    if (kSlots) { for (int k = 0; k < 6; k++) iq[k] = sums[k]; } else load_sums(&sm.sums[b], iq);
                     // Walk build: a millisecond the channel leaves out moves no code phase (the sums are nobody's).  The gap is
                     // read from the record itself: the nav thread writes it at least LC_WALK_LEAD_MS before it begins and after
                     // the previous one has ended, so whichever of the two values a worker sees - or a mix of them - says "not
@@ -479,10 +504,10 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
         } else if (code_thr) {
             if (kProf) c0 = clock64();
             int16_t iq[6];
-            load_sums(&sm.sums[b], iq);
+            if (kSlots) { for (int k = 0; k < 6; k++) iq[k] = sums[k]; } else load_sums(&sm.sums[b], iq);
             if (kProf) iq[0] += (int16_t)(clock64() & 0);
             GPSB_TL(5);
-            sm.sums[b ^ 1u] = make_uint4(0u, 0u, 0u, 0u);      // read one ms ago by everybody; filled again after the workers have seen offs_ready
+            if (!kSlots) sm.sums[b ^ 1u] = make_uint4(0u, 0u, 0u, 0u);      // read one ms ago by everybody; filled again after the workers have seen offs_ready
             if (next_frame) consumed++;                         // the workers wait for frame m+1 this millisecond
             const bool idle = kWalk && lc_walk_idle(w_skip_ms, w_skip_len, ms);            // the channel leaves this millisecond out
             const bool idle_next = kWalk && lc_walk_idle(w_skip_ms, w_skip_len, ms + 1u);
@@ -525,7 +550,7 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
         } else if (carrier_thr) {
             if (kProf) { const long long c1 = clock64(); pt[6] += c1 - c0; c0 = c1; }
             int16_t iq[6];
-            load_sums(&sm.sums[b], iq);
+            if (kSlots) { for (int k = 0; k < 6; k++) iq[k] = sums[k]; } else load_sums(&sm.sums[b], iq);
             if (kProf) iq[2] += (int16_t)(clock64() & 0);
             GPSB_TL(5);
             const bool idle = kWalk && lc_walk_idle(w_skip_ms, w_skip_len, ms);            // the channel leaves this millisecond out
@@ -559,7 +584,7 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
         } else if (nav_thr) {                               // nav bits and SNR of this millisecond (nav_data.c:46-453, tracking.c:154-169)
             if (kProf) c0 = clock64();
             int16_t iq[6];
-            load_sums(&sm.sums[b], iq);
+            if (kSlots) { for (int k = 0; k < 6; k++) iq[k] = sums[k]; } else load_sums(&sm.sums[b], iq);
             int8_t bit = -1;
             const bool idle = kWalk && lc_walk_idle(w_skip_ms, w_skip_len, ms);            // the channel leaves this millisecond out
             const bool idle_next = kWalk && lc_walk_idle(w_skip_ms, w_skip_len, ms + 1u);
