@@ -203,7 +203,13 @@ __device__ __forceinline__ int frame_present(const StreamGate& gate, uint32_t ms
 // phase 0 and have no idle gap pending takes the build without it (the host checks the records; a record that does
 // not qualify makes that build refuse the channel with LC_STOP_STATE).
 template <bool kProf, int kExp = 0, bool kStream = false, bool kWalk = true>
-__global__ void __maxnreg__(96)      // measured: 96 registers 1.068 us per ms, uncapped (123) 1.087, 80: 1.124
+#ifndef GPSB_LOOP_STREAM_WDLL
+#define GPSB_LOOP_STREAM_WDLL 1
+#endif
+// Register cap per build, measured (tools/ab_run.sh, us per ms of signal): 96 for the resident builds (88: 0.977, 96: 0.951,
+// 104: 0.962 without the walk; uncapped 123 registers: 1.087 in round 2's first pass) and for the builds with the walk
+// (96: 1.016 / 1.051 streaming, 104: 1.030 / 1.089); 104 for the streaming build without the walk (96: 0.979, 104: 0.964).
+__global__ void __maxnreg__((kStream && !kWalk) ? 104 : 96)      // measured: 96 registers 1.068 us per ms, uncapped (123) 1.087, 80: 1.124
 k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uint32_t* __restrict__ codes,
             const uint32_t* __restrict__ signal, uint32_t ring_ms, uint32_t ms0, uint32_t n_ms,
             int16_t* __restrict__ iq_log, int8_t* __restrict__ nav_log, gpsb_loop_result* __restrict__ results,
@@ -371,7 +377,7 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
     // kWorkerDll: the workers do not wait for the code thread's offsets - every worker thread runs the DLL itself on the
     // six sums it reads after barrier A (same IEEE arithmetic, same result in every thread) and goes straight into
     // phase 1: the hand-over code thread -> shared memory -> mbarrier -> workers leaves the serial path.
-    constexpr bool kWorkerDll = GPSB_LOOP_WORKER_DLL && (!kWalk || GPSB_LOOP_WORKER_DLL_WALK) && !kProf && kExp == 0;
+    constexpr bool kWorkerDll = GPSB_LOOP_WORKER_DLL && (!kWalk || GPSB_LOOP_WORKER_DLL_WALK) && (!kStream || GPSB_LOOP_STREAM_WDLL) && !kProf && kExp == 0;
     CodeRegs wcod = cod;
     const uint8_t prn = sm.ch.prn;
     const int16_t found_freq_offset_hz = sm.ch.acq_data.found_freq_offset_hz;
