@@ -206,10 +206,17 @@ template <bool kProf, int kExp = 0, bool kStream = false, bool kWalk = true>
 #ifndef GPSB_LOOP_STREAM_WDLL
 #define GPSB_LOOP_STREAM_WDLL 1
 #endif
-// Register cap per build, measured (tools/ab_run.sh, us per ms of signal): 96 for the resident builds (88: 0.977, 96: 0.951,
-// 104: 0.962 without the walk; uncapped 123 registers: 1.087 in round 2's first pass) and for the builds with the walk
-// (96: 1.016 / 1.051 streaming, 104: 1.030 / 1.089); 104 for the streaming build without the walk (96: 0.979, 104: 0.964).
-__global__ void __maxnreg__((kStream && !kWalk) ? 104 : 96)      // measured: 96 registers 1.068 us per ms, uncapped (123) 1.087, 80: 1.124
+// Register cap per build, measured (tools/ab_run.sh, us per ms of signal; profiles/loop_experiments_r2.txt):
+//   resident, no walk (per-warp sum slots)    88: 0.977   96: 0.951   104: 0.962   112: 0.960   128: 0.964      -> 96
+//   streaming, no walk (per-warp sum slots)   96: 1.007   104: 0.967  112: 0.947   120: 0.955   128: 0.960      -> 112
+//   builds with the walk (shared atomics)     96: 1.016 resident / 1.051 streaming   104: 1.030 / 1.089         -> 96
+#ifndef GPSB_LOOP_REGS_STREAM
+#define GPSB_LOOP_REGS_STREAM 112
+#endif
+#ifndef GPSB_LOOP_REGS_RESIDENT
+#define GPSB_LOOP_REGS_RESIDENT 96
+#endif
+__global__ void __maxnreg__(kWalk ? 96 : kStream ? GPSB_LOOP_REGS_STREAM : GPSB_LOOP_REGS_RESIDENT)      // measured: 96 registers 1.068 us per ms, uncapped (123) 1.087, 80: 1.124
 k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uint32_t* __restrict__ codes,
             const uint32_t* __restrict__ signal, uint32_t ring_ms, uint32_t ms0, uint32_t n_ms,
             int16_t* __restrict__ iq_log, int8_t* __restrict__ nav_log, gpsb_loop_result* __restrict__ results,
@@ -391,9 +398,10 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
     // How the six sums get from nine warps to everybody.  kSlots: one 16-byte store per warp into a slot of its own, every warp
     // adds the slots up after barrier A (three REDUX).  Otherwise: 27 shared-memory atomics on three words in front of the
     // barrier, one 16-byte load behind it.  Measured per build (tools/ab_run.sh, us per ms of signal, atomics -> slots):
-    // resident without the walk 0.985 -> 0.950; streaming without the walk 0.979 -> 1.007; resident with the walk 1.012 -> 1.021.
-    // So each build takes what is faster for it (the difference is instruction scheduling, not the algorithm).
-    constexpr bool kSlots = GPSB_LOOP_SLOTS >= 0 ? (GPSB_LOOP_SLOTS != 0) : (!kStream && !kWalk && !kProf && kExp == 0);
+    // resident without the walk 0.985 -> 0.950; streaming without the walk 0.979 -> 1.007 at 96 registers, but 0.962 -> 0.947 at
+    // 112; resident with the walk 1.012 -> 1.021.  So each build takes what is faster for it (the difference is instruction
+    // scheduling and register allocation, not the algorithm): slots without the walk, atomics with it.
+    constexpr bool kSlots = GPSB_LOOP_SLOTS >= 0 ? (GPSB_LOOP_SLOTS != 0) : (!kWalk && !kProf && kExp == 0);
     uint32_t m = 0;
     uint32_t limit = n_ms;              // streaming: re-read every millisecond (sm.ctl[].y)
     for (; m < limit && stop == LC_STOP_NONE; m++) {
