@@ -209,14 +209,15 @@ template <bool kProf, int kExp = 0, bool kStream = false, bool kWalk = true>
 // Register cap per build, measured (tools/ab_run.sh, us per ms of signal; profiles/loop_experiments_r2.txt):
 //   resident, no walk (per-warp sum slots)    88: 0.977   96: 0.951   104: 0.962   112: 0.960   128: 0.964      -> 96
 //   streaming, no walk (per-warp sum slots)   96: 1.007   104: 0.967  112: 0.947   120: 0.955   128: 0.960      -> 112
-//   builds with the walk (shared atomics)     96: 1.016 resident / 1.051 streaming   104: 1.030 / 1.089         -> 96
+//   resident, walk                            96 + atomics: 1.016   112 + atomics: 1.014   104 / 112 / 120 + slots: 1.034 / 1.030 / 1.021   -> 96, atomics
+//   streaming, walk                           96 + atomics: 1.056   112 + atomics: 1.038   104 / 112 / 120 + slots: 1.015 / 1.042 / 1.044   -> 104, slots
 #ifndef GPSB_LOOP_REGS_STREAM
 #define GPSB_LOOP_REGS_STREAM 112
 #endif
 #ifndef GPSB_LOOP_REGS_RESIDENT
 #define GPSB_LOOP_REGS_RESIDENT 96
 #endif
-__global__ void __maxnreg__(kWalk ? 96 : kStream ? GPSB_LOOP_REGS_STREAM : GPSB_LOOP_REGS_RESIDENT)      // measured: 96 registers 1.068 us per ms, uncapped (123) 1.087, 80: 1.124
+__global__ void __maxnreg__(kWalk ? (kStream ? 104 : 96) : kStream ? GPSB_LOOP_REGS_STREAM : GPSB_LOOP_REGS_RESIDENT)      // measured: 96 registers 1.068 us per ms, uncapped (123) 1.087, 80: 1.124
 k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uint32_t* __restrict__ codes,
             const uint32_t* __restrict__ signal, uint32_t ring_ms, uint32_t ms0, uint32_t n_ms,
             int16_t* __restrict__ iq_log, int8_t* __restrict__ nav_log, gpsb_loop_result* __restrict__ results,
@@ -400,8 +401,8 @@ k_track_run(gps_ch_t* __restrict__ chans, gpsb_aux* __restrict__ auxs, const uin
     // barrier, one 16-byte load behind it.  Measured per build (tools/ab_run.sh, us per ms of signal, atomics -> slots):
     // resident without the walk 0.985 -> 0.950; streaming without the walk 0.979 -> 1.007 at 96 registers, but 0.962 -> 0.947 at
     // 112; resident with the walk 1.012 -> 1.021.  So each build takes what is faster for it (the difference is instruction
-    // scheduling and register allocation, not the algorithm): slots without the walk, atomics with it.
-    constexpr bool kSlots = GPSB_LOOP_SLOTS >= 0 ? (GPSB_LOOP_SLOTS != 0) : (!kWalk && !kProf && kExp == 0);
+    // scheduling and register allocation, not the algorithm): slots everywhere but in the resident build with the walk.
+    constexpr bool kSlots = GPSB_LOOP_SLOTS >= 0 ? (GPSB_LOOP_SLOTS != 0) : ((!kWalk || kStream) && !kProf && kExp == 0);
     uint32_t m = 0;
     uint32_t limit = n_ms;              // streaming: re-read every millisecond (sm.ctl[].y)
     for (; m < limit && stop == LC_STOP_NONE; m++) {
