@@ -13,7 +13,8 @@
  *            phase 1 needs only the code offsets and forms raw word ^ replica window + byte masks in registers;
  *            phase 2 needs the carrier NCO words: the carrier phase of a word selects its I and Q count among the four
  *            quadrant-pattern counts phase 1 left behind (one PRMT per arm), then REDUX per warp and one shared-memory
- *            RED per warp and arm.  Nothing mixed is ever staged in memory.
+ *            RED per warp and arm - or, in the builds it is faster in, one 16-byte store per warp into a slot of its own, the
+ *            nine slots added up by every warp behind the barrier (kSlots).  Nothing mixed is ever staged in memory.
  *   code     (1 thread)  DLL + code-offset planning (tracking.c:333-393, 115-130); releases phase 1 through an
  *            mbarrier as soon as the offsets exist, while the carrier thread is still busy.
  *   carrier  (1 thread)  Costas PLL / FLL / false-lock check + NCO planning (tracking.c:175-327, gps_misc.c:250);
