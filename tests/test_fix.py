@@ -422,6 +422,23 @@ def test_more_than_four_satellites(reference, n):
 
 
 def test_idle_loop_observations_to_fix(reference):
+    _idle_loop_observations_to_fix(reference, rtcm=False)
+
+
+def test_idle_loop_observations_to_fix_with_rtcm_output_on():
+    """The same timeline with the RTCM output switched ON on both sides (the reference ships with it compiled out,
+    config.h:30; oracle/ref_master_rtcm_unit.c compiles its gps_master.c with the switch on into _ref/libgpsref_rtcm.so).
+    gps_master_transmit_obs then runs ahead of gps_master_calculate_pos on every idle slot and refreshes the ONE observation
+    array the sliced solver reads between its slices (gps_master.c:41, :279-285, :439): channel records, observations and the
+    solver's state still equal the reference's after every call."""
+    from oracle_lib import REF_SO, Reference
+    so = REF_SO.parent / "libgpsref_rtcm.so"
+    if not so.exists():
+        pytest.skip("oracle/_ref/libgpsref_rtcm.so not built (make -C oracle ref)")
+    _idle_loop_observations_to_fix(Reference(so), rtcm=True)
+
+
+def _idle_loop_observations_to_fix(reference, rtcm):
     """Rows N3 + N4 chained the way the reference's main loop runs them: gps_master_nav_handling every 17 ms on four
     channels whose subframe stamps and code phases follow a physically consistent scene (satellites on orbits, a
     receiver on the ground), ephemerides in place.  The code-phase filter closes windows, pseudoranges and times of week
@@ -431,6 +448,8 @@ def test_idle_loop_observations_to_fix(reference):
     lib = load_host_library()
     rl = reference.lib
     lib.gps_master_nav_handling.argtypes = [C.c_void_p]
+    lib.gpsb_host_enable_rtcm.argtypes = [C.c_int]
+    lib.gpsb_host_enable_rtcm(1 if rtcm else 0)
     lib.gpsb_host_channel_set_tow.argtypes = [C.c_void_p, C.c_double]
     rl.ref_nav_handling.argtypes = [C.c_void_p, C.c_uint32]
     rl.ref_channel_set_tow.argtypes = [C.c_void_p, C.c_double]
@@ -460,6 +479,7 @@ def test_idle_loop_observations_to_fix(reference):
         return tow0 + flight0[ref_i] / 1000.0 + (ms - arrival[ref_i]) / 1000.0
 
     fixes = []
+    busy_calls = 0
     for now in range(10000, 17000, 17):
         t = true_time(now)
         for i, el in enumerate(sky):
@@ -486,11 +506,21 @@ def test_idle_loop_observations_to_fix(reference):
             assert bytes(ch.snapshot(i)) == bytes(reference.snapshot(reference.channel_at(rchans, i))), (now, i)
         got, want = pair.state(), pair.ref_state()
         assert not fix_diff(got, want), (now, fix_diff(got, want))
+        busy_calls += 1 if got.busy else 0
         if got.stat == 5 and not got.busy:
             fixes.append(np.array([dbl(u) for u in got.rr[:3]]))
+    if rtcm:
+        # The point of this variant is the equality after every call, above.  (With its RTCM output on, the reference
+        # refreshes the observations under a solve in flight on every idle slot; on this timeline its sliced solver then
+        # keeps starting over - here exactly as there.)
+        assert busy_calls > 100
+        lib.gpsb_host_enable_rtcm(0)
+        pair.free()
+        return
     assert len(fixes) > 100                                     # a fix stood for most of the run
     distinct = {tuple(f) for f in fixes}
     assert len(distinct) >= 5                                   # and was renewed twice a second
     worst = max(np.linalg.norm(f - site) for f in fixes)
     assert worst < 2000.0, worst        # exact observations give ~7 m; the assembly's time tags run a flight time late
+    lib.gpsb_host_enable_rtcm(0)
     pair.free()
