@@ -78,6 +78,34 @@ __device__ __forceinline__ void quadrant_patterns(uint32_t nco, uint32_t& cp, ui
     sp = prmt(0x66CC9933u, 0x66CC0933u, sel);     // sin[ph] = cos[(ph + 3) & 3]
 }
 
+// The same pattern pair from a table in shared memory: 32 entries of (cos, sin) indexed by the top FIVE bits of the NCO
+// word (every quadrant eight times), so the index is one shift; the address is formed by a multiply-add on the FMA pipe
+// (`eight` holds 8 in a register the assembler cannot see through) and the pair arrives by one 8-byte load.  Per word
+// that is 1 ALU + 1 FMA + 1 LSU instruction instead of 3 ALU + 1 FMA (shift, selector, two PRMT): the ALU pipe is what
+// bounds k_epl_batch_tma<1>.  A warp has a table of its own (warps leave these kernels independently).
+#ifndef GPSB_BATCH_LUT
+#define GPSB_BATCH_LUT 1
+#endif
+__device__ __forceinline__ void quadrant_lut_fill(uint2* lut, int lane)
+{
+    uint32_t cp, sp;
+    quadrant_patterns((uint32_t)lane << 27, cp, sp);
+    lut[lane] = make_uint2(cp, sp);
+    __syncwarp();
+}
+__device__ __forceinline__ void quadrant_patterns_lut(uint32_t nco, uint32_t lut_addr, uint32_t eight, uint32_t& cp, uint32_t& sp)
+{
+    uint32_t a;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(a) : "r"(nco >> 27), "r"(eight), "r"(lut_addr));
+    asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(cp), "=r"(sp) : "r"(a));
+}
+__device__ __forceinline__ uint32_t batch_opaque_one()      // 1, from a special register (gridDim.y == 1 in these launches)
+{
+    uint32_t v;
+    asm volatile("mov.u32 %0, %%nctaid.y;" : "=r"(v));
+    return v;
+}
+
 // frame index of millisecond ms: the modulo only when the ring has wrapped (an integer modulo is ~20 instructions)
 __device__ __forceinline__ uint32_t ring_frame(uint32_t ms, uint32_t ring_ms) { return ms < ring_ms ? ms : ms % ring_ms; }
 
@@ -100,8 +128,9 @@ __device__ __forceinline__ uint32_t rxt_window(const uint32_t* __restrict__ rx, 
 template <int kArms>
 __device__ __forceinline__ void batch_cell(const gpsb_epl_req& rq, const uint4 (&f)[4], int lane, uint32_t c,
                                            int16_t* __restrict__ out, const uint32_t* __restrict__ rxt,
-                                           const uint32_t* __restrict__ signal, uint32_t ring_ms)
+                                           const uint32_t* __restrict__ signal, uint32_t ring_ms, uint32_t lut_addr)
 {
+    const uint32_t eight = batch_opaque_one() << 3;
     const uint32_t* __restrict__ rx = rxt + ((size_t)rq.sv_slot * kRxtShifts + (rq.off_bits & 15u)) * (kRxtCopies * kRxtWords);
     const uint32_t offs[3] = {kArms == 3 ? rq.off_e : rq.off_p, rq.off_p, rq.off_l};
     uint32_t acc[kArms];            // packed I | Q << 16 (a whole millisecond is at most 16368 per component)
@@ -136,7 +165,8 @@ __device__ __forceinline__ void batch_cell(const gpsb_epl_req& rq, const uint4 (
             uint32_t cp, sp;
             const uint32_t nco = kArms == 1 ? ((uint32_t)(w0 + j) * rq.step32 + rq.acc0) : nco_run;
             nco_run += rq.step32;
-            quadrant_patterns(nco, cp, sp);
+            if (GPSB_BATCH_LUT) quadrant_patterns_lut(nco, lut_addr, eight, cp, sp);
+            else quadrant_patterns(nco, cp, sp);
 #pragma unroll
             for (int a = 0; a < kArms; a++) {
                 const uint32_t win = r[a][j];
@@ -206,10 +236,13 @@ __global__ void __launch_bounds__(kBatchThreads, kBatchCtasPerSm)
 k_epl_batch(const gpsb_epl_req* __restrict__ reqs, int16_t* __restrict__ out, const uint32_t* __restrict__ rxt,
             const uint32_t* __restrict__ signal, uint32_t ring_ms, uint32_t n)
 {
+    __shared__ uint2 lut[kBatchThreads / 32][32];
     const int lane = threadIdx.x & 31;
     const uint32_t warps = (gridDim.x * kBatchThreads) >> 5;
     uint32_t c = (blockIdx.x * kBatchThreads + threadIdx.x) >> 5;
     if (c >= n) return;
+    quadrant_lut_fill(lut[threadIdx.x >> 5], lane);
+    const uint32_t lut_addr = (uint32_t)__cvta_generic_to_shared(lut[threadIdx.x >> 5]);
 
     // Software pipeline, unrolled by two so that the two frame buffers swap roles without register moves: while cell i
     // is correlated, the frame of cell i+1 and the request of cell i+2 are in flight - neither the request fetch
@@ -227,12 +260,12 @@ k_epl_batch(const gpsb_epl_req* __restrict__ reqs, int16_t* __restrict__ out, co
     for (;;) {
         load_frame(rq_b, fb);                                  // past the end: re-reads a frame that is in L2 anyway
         const gpsb_epl_req rq_c = load_req(c + 2 * warps, rq_b);
-        batch_cell<kArms>(rq_a, fa, lane, c, out, rxt, signal, ring_ms);
+        batch_cell<kArms>(rq_a, fa, lane, c, out, rxt, signal, ring_ms, lut_addr);
         c += warps;
         if (c >= n) break;
         load_frame(rq_c, fa);
         rq_a = load_req(c + 2 * warps, rq_c);                  // request of the cell after next, into the free slot
-        batch_cell<kArms>(rq_b, fb, lane, c, out, rxt, signal, ring_ms);
+        batch_cell<kArms>(rq_b, fb, lane, c, out, rxt, signal, ring_ms, lut_addr);
         c += warps;
         if (c >= n) break;
         rq_b = rq_a;                                           // roles for the next round: a = cell c, b = cell c + warps
@@ -265,6 +298,7 @@ constexpr int kTmaWarps = kBatchThreads / 32;
 struct BatchTmaSmem {
     uint4 frame[kTmaWarps][kTmaStages][GPSB_FRAME_BYTES / 16];     // 8 x 4 x 2 KB
     unsigned long long full[kTmaWarps][kTmaStages];
+    uint2 lut[kTmaWarps][32];                                      // quadrant pattern pairs, one table per warp
 };
 
 template <int kArms>
@@ -279,6 +313,8 @@ k_epl_batch_tma(const gpsb_epl_req* __restrict__ reqs, int16_t* __restrict__ out
     const uint32_t c0 = (blockIdx.x * kBatchThreads + threadIdx.x) >> 5;
     if (c0 >= n) return;                                           // whole warps leave; nothing below is CTA-wide
     const uint32_t mine = (n - c0 + warps - 1) / warps;            // cells of this warp: c0 + i * warps
+    quadrant_lut_fill(sm.lut[warp], lane);
+    const uint32_t lut_addr = (uint32_t)__cvta_generic_to_shared(sm.lut[warp]);
 
     auto sa = [](const void* p) { return (uint32_t)__cvta_generic_to_shared(p); };
     auto fetch = [&](uint32_t ms_index, int stage) {               // lane 0: one bulk copy of a whole frame
@@ -321,7 +357,7 @@ k_epl_batch_tma(const gpsb_epl_req* __restrict__ reqs, int16_t* __restrict__ out
         __syncwarp();                                               // every lane has its groups: the buffer is free again
         if (lane == 0 && i + kTmaStages < mine) fetch(next_ms, stage);
         next_ms = ms_after;
-        batch_cell<kArms>(rq, f, lane, c, out, rxt, signal, ring_ms);
+        batch_cell<kArms>(rq, f, lane, c, out, rxt, signal, ring_ms, lut_addr);
         rq = rq_next;
     }
 }
